@@ -1,0 +1,219 @@
+/* melissa_b200.h -- C ABI of libmelissa_b200.so (hand-written sm_100a CUDA).
+ *
+ * The reference (RaffaeleGalliera/melissa) is pure Python and has no FFI layer; its
+ * boundary for the rollout hot path is Python duck typing.  Each entry point below names
+ * the reference interface it replaces (file:line under the reference root).  Host code
+ * (melissa_b200/*.py) binds these with ctypes; INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless the name ends in _host; the caller (PyTorch)
+ *    owns every buffer; the library allocates nothing;
+ *  - every call enqueues on the given cudaStream_t (passed as void*) and never synchronises;
+ *  - return 0 = OK, negative = error; mls_last_error() gives the message (thread local);
+ *  - B episodes, N nodes per graph, W = mls_words_per_row(N) words per bitmask row
+ *    (ceil(N/32) rounded up to 1, 2, 4 or 8); bit j of a row lives in word j/32, bit j%32.
+ */
+#ifndef MELISSA_B200_H
+#define MELISSA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MLS_VERSION 100
+#define MLS_MAX_NODES 256
+
+/* ---- errors ------------------------------------------------------------------------- */
+#define MLS_OK 0
+#define MLS_ERR_INVALID (-1) /* bad argument (the reference raises ValueError)            */
+#define MLS_ERR_CUDA (-2)    /* a CUDA runtime call failed                                */
+#define MLS_ERR_UNSUPPORTED (-3)
+
+int mls_version(void);
+const char* mls_last_error(void);
+/* sm count / compute capability of the current device; -2 if no usable GPU. */
+int mls_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);
+/* words per bitmask row for N nodes: 1 (N<=32), 2 (<=64), 4 (<=128), 8 (<=256). */
+int mls_words_per_row(int n_nodes);
+
+/* ===== environment round ===============================================================
+ * Replaces graph_env/env/utils/core.py (World: reset :343-437, step :225-266,
+ * relay_message :268-279, move_graph :281-319, neighbour masks :321-341),
+ * graph_env/env/utils/heuristics/{core.py:12-62, mpr.py:7-72},
+ * graph_env/env/utils/selector.py:1-52 and the round logic of graph_env/env/graph.py
+ * (step :303-359, _execute_world_step :361-389, reward :402-463, obs rows :254-271,
+ * get_info :149-179). */
+
+enum MlsHeuristic { /* graph_env/env/utils/heuristics/__init__.py:4-11 */
+  MLS_HEUR_NONE = 0,
+  MLS_HEUR_SILENT = 1,
+  MLS_HEUR_SIMPLE_BROADCAST = 2,
+  MLS_HEUR_BROADCAST_IF_ANY_INTERESTED = 3,
+  MLS_HEUR_PROBABILISTIC_GOSSIP = 4, /* random bits are host-fed (reference uses global np.random) */
+  MLS_HEUR_PROBABILISTIC_RELAY = 5,  /* idem */
+  MLS_HEUR_MPR = 6
+};
+
+typedef struct MlsEnvDesc {
+  int32_t n_episodes; /* B */
+  int32_t n_nodes;    /* N <= MLS_MAX_NODES */
+  int32_t dynamic;    /* dynamic_graph (graph.py:39)                                     */
+  int32_t is_testing; /* graph.py:37: scripted agents are policy-stepped too             */
+  int32_t heuristic;  /* enum MlsHeuristic                                               */
+  int32_t reserved[3];
+} MlsEnvDesc;
+
+/* per-node packed state word (node[b][i]) */
+#define MLS_F_HAS_MESSAGE 0x01u
+#define MLS_F_INTERESTED 0x02u
+#define MLS_F_SCRIPTED 0x04u
+#define MLS_F_ORIGIN 0x08u
+#define MLS_F_HAS_TAKEN_ACTION 0x10u
+#define MLS_F_TRUNCATED 0x20u
+#define MLS_F_ACTIVE 0x40u
+#define MLS_NODE_STEPS_SHIFT 8 /* bits 8..15 steps_taken, bits 16..23 messages_transmitted */
+#define MLS_NODE_MSGS_SHIFT 16
+
+/* per-episode scalars (episode[b][MLS_EP_*]) */
+#define MLS_EP_SOURCE 0
+#define MLS_EP_WORLD_MSGS 1
+#define MLS_EP_NUM_MOVES 2
+#define MLS_EP_GRAPH 3     /* index into the topology pool                                */
+#define MLS_EP_N_RESETS 4  /* how many episodes this slot has started (recycling cursor)  */
+#define MLS_EP_STRIDE 8
+
+typedef struct MlsEnvState {
+  uint32_t* node;          /* [B][N]   packed flags | steps | msgs                        */
+  uint16_t* recv_count;    /* [B][N]   sum_j received_from[i][j]                          */
+  uint32_t* recv_from;     /* [B][N][W] (received_from[i][j] > 0); needed for MPR / prob. relay, else NULL */
+  int32_t* episode;        /* [B][MLS_EP_STRIDE]                                          */
+  double* rewards_sum;     /* [B]      episode_rewards_sum (graph.py:389)                 */
+  uint32_t* adj;           /* [B][N][W] per-episode adjacency; dynamic mode only, else NULL */
+  double* pos;             /* [B][N][2] per-episode positions;  dynamic mode only, else NULL */
+  const uint32_t* pool_adj; /* [G][N][W] topology pool (static mode reads it every round)  */
+  const double* pool_pos;   /* [G][N][2]                                                   */
+  int32_t pool_size;        /* G */
+  int32_t pad_;
+} MlsEnvState;
+
+/* What an episode starts from (reference reset chain, core.py:371-395; drawn on the host). */
+typedef struct MlsResetTuples {
+  const int32_t* graph_index;    /* [n] index into the pool                               */
+  const int32_t* source;         /* [n]                                                   */
+  const uint32_t* interested;    /* [n][W] bitmask                                        */
+  const uint32_t* scripted;      /* [n][W] bitmask                                        */
+  int32_t count;                 /* n                                                     */
+  int32_t pad_;
+} MlsResetTuples;
+
+typedef struct MlsInfo { /* graph.py:149-179 as integer counts; fractions = count / N etc. */
+  int32_t total_messages_transmitted;
+  int32_t covered;                   /* sum has_message                                   */
+  int32_t messages_sent;
+  int32_t messages_received;
+  int32_t n_neighbours;
+  int32_t interested_agents;
+  int32_t coverage_interested_count;
+  int32_t uninterested_with_message;
+  int32_t num_moves;
+  int32_t n_acted;                   /* agent-transitions of the round just played        */
+  int32_t episodes_started;
+  int32_t reserved;
+  double episode_rewards_sum;
+} MlsInfo;
+
+typedef struct MlsRoundInputs {
+  const int8_t* actions;        /* [B][N] -1 = None, 0, 1; only entries of active agents are read (graph.py:312-318) */
+  const double* move_offsets;   /* [B][2][N] dynamic mode: 0.06*U(-1,1), x then y (core.py:316-319); NULL -> Philox */
+  const uint8_t* gossip_bits;   /* [B][N]    probabilistic_gossip draws, else NULL         */
+  const uint32_t* relay_bits;   /* [B][N][W] probabilistic_relay draws, else NULL          */
+  uint64_t philox_seed;         /* movement stream when move_offsets == NULL               */
+} MlsRoundInputs;
+
+typedef struct MlsRoundOutputs {
+  float* obs;          /* [B][N][8] obs_matrix rows (graph.py:254-271); NULL = not wanted  */
+  double* reward;      /* [B][N]   reward of each agent that acted, 0 elsewhere; NULL ok   */
+  uint8_t* active;     /* [B][N]   agents that act next round (graph.py:336-345)           */
+  uint8_t* terminated; /* [B][N]   TTL reached (graph.py:330-334); NULL ok                 */
+  uint8_t* done;       /* [B]      no agent left to act; NULL ok                           */
+  MlsInfo* info;       /* [B]      NULL ok                                                 */
+  unsigned long long* transitions; /* [1] += agent-transitions of this round; NULL ok      */
+} MlsRoundOutputs;
+
+/* Reset the episodes env_ids[0..n) (NULL = episodes 0..n) from tuples[0..n), including the
+ * forced first world step in which the source broadcasts (core.py:437, :246).
+ * `in` may carry move_offsets / gossip_bits / relay_bits for that forced step, indexed by
+ * tuple (not by episode).  Writes obs/active rows of the reset episodes. */
+int mls_env_reset(const MlsEnvDesc* desc, const MlsEnvState* state, const int32_t* env_ids,
+                  const MlsResetTuples* tuples, const MlsRoundInputs* in,
+                  const MlsRoundOutputs* out, void* stream);
+
+/* One round for all B episodes.  If `recycle` is non-NULL an episode that ends in this round
+ * is restarted in the same launch from tuple (b + n_resets*B) % count: reward/terminated/
+ * done/info describe the finished round, obs/active describe the fresh episode. */
+int mls_env_step(const MlsEnvDesc* desc, const MlsEnvState* state, const MlsRoundInputs* in,
+                 const MlsRoundOutputs* out, const MlsResetTuples* recycle, void* stream);
+
+/* get_info (graph.py:149-179) for all episodes without stepping. */
+int mls_env_info(const MlsEnvDesc* desc, const MlsEnvState* state, MlsInfo* info, void* stream);
+
+/* ===== Q-network forward + action selection ============================================
+ * Replaces graph_env/env/utils/networks/{common.py:6-64, dgn_r.py:82-129, l_dgn.py:92-151,
+ * hl_dgn.py:82-119} (and the PyG / tianshou ops they call) and tianshou
+ * DQNPolicy.forward / exploration_noise as driven by
+ * graph_env/env/utils/policies/multi_agent_managers/shared_policy.py:81-183. */
+
+enum MlsNetKind { MLS_NET_DGN_R = 0, MLS_NET_L_DGN = 1, MLS_NET_HL_DGN = 2 };
+enum MlsPool { MLS_POOL_MEAN = 0, MLS_POOL_ADD = 1, MLS_POOL_MAX = 2 };
+enum MlsPrecision { MLS_PREC_FP32 = 0, MLS_PREC_BF16 = 1 };
+
+typedef struct MlsNetDesc {
+  int32_t kind;       /* enum MlsNetKind                                                  */
+  int32_t n_nodes;    /* agents_num                                                       */
+  int32_t hidden;     /* hidden_dim (128)                                                 */
+  int32_t heads;      /* num_heads (4)                                                    */
+  int32_t input_dim;  /* 5                                                                */
+  int32_t pool;       /* enum MlsPool (HL-DGN aggregator)                                 */
+  int32_t precision;  /* enum MlsPrecision                                                */
+  int32_t head_hidden;/* dueling hidden size (128), two hidden layers                     */
+} MlsNetDesc;
+
+/* fp32 parameters exactly as in the reference state_dict ([out, in] row major). */
+typedef struct MlsNetWeights {
+  const float *enc_w0, *enc_b0, *enc_w1, *enc_b1;      /* encoder.model.{0,2}             */
+  /* GATv2 (L-DGN, HL-DGN): convK.{lin_l,lin_r}.{weight,bias}, convK.att [H*C], convK.bias [H*C]
+   * Transformer (DGN-R):   convK.{lin_query,lin_key,lin_value}.{weight,bias}              */
+  const float *c1_wa, *c1_ba, *c1_wb, *c1_bb, *c1_wc, *c1_bc, *c1_att, *c1_bias;
+  const float *c2_wa, *c2_ba, *c2_wb, *c2_bb, *c2_wc, *c2_bc, *c2_att, *c2_bias;
+  const float *q_w0, *q_b0, *q_w1, *q_b1, *q_w2, *q_b2; /* Q.model.{0,2,4}                 */
+  const float *v_w0, *v_b0, *v_w1, *v_b1, *v_w2, *v_b2; /* V.model.{0,2,4}                 */
+} MlsNetWeights;
+
+typedef struct MlsForwardArgs {
+  const float* obs;          /* graph g starts at obs + g*obs_stride; N rows of 8 floats     */
+  int64_t obs_stride;        /* floats: 8N for an obs matrix batch, 8N+1 for agent-obs rows  */
+  int32_t n_graphs;
+  int32_t ctrl_mode;         /* 0: ctrl_mask[g][N] (q/act are [g][N][..]); 1: one controlling
+                                node per graph = clamp(obs[g][8N], 0, N-1) (common.py:63), q is [g][2] */
+  const uint8_t* ctrl_mask;  /* mode 0 */
+  float* q;                  /* out */
+  int8_t* act;               /* out, NULL ok: greedy / epsilon-greedy action, -1 where not controlling */
+  float eps;                 /* exploration rate (tianshou DQNPolicy.exploration_noise)      */
+  int32_t pad_;
+  uint64_t philox_seed, philox_offset;
+  const double* rand3;       /* optional host-fed uniforms [rows][3] = (u_eps, u_act0, u_act1) */
+  void* workspace;           /* mls_dgn_workspace_bytes() bytes                              */
+  size_t workspace_bytes;
+} MlsForwardArgs;
+
+size_t mls_dgn_workspace_bytes(const MlsNetDesc* desc, int32_t n_graphs);
+int mls_dgn_forward(const MlsNetDesc* desc, const MlsNetWeights* w, const MlsForwardArgs* args,
+                    void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MELISSA_B200_H */

@@ -1,0 +1,27 @@
+// Error reporting + device probe for libmelissa_b200.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void mls_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" int mls_version(void) { return MLS_VERSION; }
+extern "C" const char* mls_last_error(void) { return g_err; }
+
+extern "C" int mls_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor) {
+  int dev = 0;
+  MLS_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  MLS_CUDA(cudaGetDeviceProperties(&prop, dev));
+  if (sm_count) *sm_count = prop.multiProcessorCount;
+  if (cc_major) *cc_major = prop.major;
+  if (cc_minor) *cc_minor = prop.minor;
+  return MLS_OK;
+}

@@ -1,0 +1,219 @@
+"""Shared host code of the three Q-network modules.
+
+The modules keep the reference's constructor signature, attribute names and state_dict
+keys so that checkpoints written by the reference load
+unchanged, but their forward pass is one call into ``mls_dgn_forward``
+(include/melissa_b200.h): obs never leaves the device, the graph is rebuilt from the node
+positions inside the kernels (reference networks/common.py:47-48) and the GNN body runs
+once per graph for all controlling agents.
+
+Parameter containers only hold tensors; they have no torch compute.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Any, Dict, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import _lib
+
+RADIUS_OF_INFLUENCE = 0.20      # reference constants.py:1
+
+
+class MLPParams(nn.Module):
+    """Parameter layout of tianshou ``MLP``: ``model = Sequential(Linear, ReLU, ..., Linear)``
+    -> keys ``model.0.weight``, ``model.2.weight``, ..."""
+
+    def __init__(self, input_dim: int, output_dim: int, hidden_sizes):
+        super().__init__()
+        dims = [input_dim, *hidden_sizes, output_dim]
+        layers = []
+        for k in range(len(dims) - 1):
+            layers.append(nn.Linear(dims[k], dims[k + 1]))
+            if k + 2 < len(dims):
+                layers.append(nn.ReLU())
+        self.model = nn.Sequential(*layers)
+
+    def linears(self):
+        return [m for m in self.model if isinstance(m, nn.Linear)]
+
+
+def _glorot_(t: torch.Tensor):
+    a = math.sqrt(6.0 / (t.size(-2) + t.size(-1)))
+    with torch.no_grad():
+        t.uniform_(-a, a)
+
+
+class GATv2Params(nn.Module):
+    """Parameter layout + default init of PyG ``GATv2Conv(in, out, heads)``."""
+
+    def __init__(self, in_channels: int, out_channels: int, heads: int):
+        super().__init__()
+        self.lin_l = nn.Linear(in_channels, heads * out_channels)
+        self.lin_r = nn.Linear(in_channels, heads * out_channels)
+        self.att = nn.Parameter(torch.empty(1, heads, out_channels))
+        self.bias = nn.Parameter(torch.zeros(heads * out_channels))
+        for lin in (self.lin_l, self.lin_r):
+            _glorot_(lin.weight)
+            nn.init.zeros_(lin.bias)
+        _glorot_(self.att)
+
+
+class TransformerConvParams(nn.Module):
+    """Parameter layout of PyG ``TransformerConv(in, out, heads, root_weight=False)``.
+    ``lin_skip`` is constructed by PyG and saved in checkpoints but never used in forward."""
+
+    def __init__(self, in_channels: int, out_channels: int, heads: int):
+        super().__init__()
+        self.lin_key = nn.Linear(in_channels, heads * out_channels)
+        self.lin_query = nn.Linear(in_channels, heads * out_channels)
+        self.lin_value = nn.Linear(in_channels, heads * out_channels)
+        self.lin_skip = nn.Linear(in_channels, heads * out_channels)
+
+
+class _Workspace:
+    def __init__(self):
+        self.buf = None
+
+    def get(self, nbytes: int, device):
+        if self.buf is None or self.buf.numel() < nbytes or self.buf.device != device:
+            self.buf = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device)
+        return self.buf
+
+
+class DGNBase(nn.Module):
+    """Common machinery: validation, weight struct, C-ABI call."""
+
+    KIND = ""
+
+    def _init_common(self, input_dim, hidden_dim, output_dim, num_heads, agents_num, dueling_param, device,
+                     edge_attributes):
+        self.device = device
+        self.input_dim = input_dim
+        self.hidden_dim = hidden_dim
+        self.output_dim = output_dim
+        self.num_heads = num_heads
+        self.agents_num = agents_num
+        self.edge_attributes = edge_attributes      # accepted; no effect on results (convs get no edge_attr)
+        self.use_dueling = dueling_param is not None
+        self.precision = "fp32"
+        self._ws = _Workspace()
+        self._wcache = None
+
+    def _build_heads(self, latent, dueling_param, output_dim):
+        if dueling_param is None:
+            raise NotImplementedError("only the dueling head used by every reference script is implemented")
+        q_kwargs, v_kwargs = dict(dueling_param[0]), dict(dueling_param[1])
+        qh, vh = list(q_kwargs.get("hidden_sizes", ())), list(v_kwargs.get("hidden_sizes", ()))
+        if len(qh) != 2 or qh != vh or qh[0] != qh[1]:
+            raise NotImplementedError("dueling heads must be two equal hidden layers, e.g. [128, 128]")
+        self.head_hidden = qh[0]
+        q_out = q_kwargs.get("output_dim", output_dim)
+        if q_out != 2:
+            raise NotImplementedError("the environment's action space is Discrete(2)")
+        self.Q = MLPParams(latent, q_out, qh)
+        self.V = MLPParams(latent, v_kwargs.get("output_dim", 1), vh)
+        self.output_dim = q_out
+
+    # ------------------------------------------------------------------ C-ABI plumbing
+    def set_precision(self, precision: str):
+        if precision not in _lib.PRECISIONS:
+            raise ValueError(precision)
+        self.precision = precision
+        return self
+
+    def _desc(self):
+        return _lib.MlsNetDesc(_lib.NET_KINDS[self.KIND], self.agents_num, self.hidden_dim, self.num_heads,
+                               self.input_dim, _lib.POOLS[getattr(self, "aggregator_name", "mean")],
+                               _lib.PRECISIONS[self.precision], self.head_hidden)
+
+    def _conv_tensors(self, conv):
+        raise NotImplementedError
+
+    def weights_struct(self):
+        """MlsNetWeights over the live parameters (must be fp32, contiguous, on the GPU)."""
+        enc = self.encoder.linears()
+        q, v = self.Q.linears(), self.V.linears()
+        t = {"enc_w0": enc[0].weight, "enc_b0": enc[0].bias, "enc_w1": enc[1].weight, "enc_b1": enc[1].bias}
+        for name, conv in (("c1", self.conv1), ("c2", getattr(self, "conv2", None))):
+            vals = self._conv_tensors(conv) if conv is not None else [None] * 8
+            for k, val in zip(("wa", "ba", "wb", "bb", "wc", "bc", "att", "bias"), vals):
+                t[f"{name}_{k}"] = val
+        for pre, lins in (("q", q), ("v", v)):
+            for k, lin in enumerate(lins):
+                t[f"{pre}_w{k}"], t[f"{pre}_b{k}"] = lin.weight, lin.bias
+        keep = []
+        ws = _lib.MlsNetWeights()
+        for k in _lib.WEIGHT_FIELDS:
+            x = t.get(k)
+            if x is None:
+                setattr(ws, k, None)
+                continue
+            x = x.detach()
+            if x.dtype != torch.float32 or not x.is_cuda:
+                raise _lib.MelissaLibraryError(
+                    f"parameter {k} must be a float32 CUDA tensor (module on {x.device}, {x.dtype}); "
+                    "there is no CPU forward -- move the module to the GPU")
+            x = x.contiguous()
+            keep.append(x)
+            setattr(ws, k, x.data_ptr())
+        return ws, keep
+
+    def _validate_obs(self, obs):
+        if obs.ndim != 2:
+            raise ValueError(f"Expected obs to be 2D, but got shape {obs.shape}")
+        bs, dim = obs.shape
+        expected = self.agents_num * (self.input_dim + 2 + 1)
+        if dim - 1 != expected:
+            raise ValueError(f"Expected {expected} feature cols for nodes, got {dim - 1}")
+        return bs
+
+    def _call(self, obs, stride, n_graphs, ctrl_mode, ctrl_mask, q, act, eps, seed, offset, rand3):
+        L = _lib.lib()
+        desc = self._desc()
+        ws, keep = self.weights_struct()
+        nbytes = L.mls_dgn_workspace_bytes(C.byref(desc), n_graphs)
+        wsp = self._ws.get(nbytes, obs.device)
+        args = _lib.MlsForwardArgs(obs.data_ptr(), stride, n_graphs, ctrl_mode, _lib.ptr(ctrl_mask), q.data_ptr(),
+                                   _lib.ptr(act), float(eps), 0, int(seed), int(offset), _lib.ptr(rand3),
+                                   wsp.data_ptr(), wsp.numel())
+        _lib.check(L.mls_dgn_forward(C.byref(desc), C.byref(ws), C.byref(args), _lib.current_stream_ptr()))
+
+    # ------------------------------------------------------------------ public
+    def forward(self, obs, state=None, info={}):
+        """Reference signature: obs [bs, 8N+1] (ndarray or tensor; last column = controlling
+        agent index) -> (q [bs, 2], state)."""
+        dev = next(self.parameters()).device
+        if isinstance(obs, np.ndarray):
+            obs = torch.as_tensor(obs, device=dev)
+        bs = self._validate_obs(obs)
+        obs = obs.to(device=dev, dtype=torch.float32).contiguous()
+        q = torch.empty(bs, 2, dtype=torch.float32, device=dev)
+        if bs:
+            self._call(obs, obs.shape[1], bs, 1, None, q, None, 0.0, 0, 0, None)
+        return q, self._state_out(state)
+
+    def _state_out(self, state):
+        return state
+
+    @torch.no_grad()
+    def forward_graphs(self, obs_matrix: torch.Tensor, ctrl_mask: torch.Tensor, *, eps: float = 0.0,
+                       philox_seed: int = 0, philox_offset: int = 0, rand3: Optional[torch.Tensor] = None,
+                       q_out: Optional[torch.Tensor] = None, act_out: Optional[torch.Tensor] = None):
+        """Rollout form: obs_matrix f32 [B, N, 8] (what ``BatchedGraphEnv`` emits), ctrl_mask
+        u8 [B, N] (the active set).  One GNN pass per graph; returns (q f32 [B,N,2] -- zero
+        where not controlling, act i8 [B,N] -- -1 where not controlling)."""
+        B, N, F = obs_matrix.shape
+        if N != self.agents_num or F != self.input_dim + 3:
+            raise ValueError(f"Expected obs_matrix [B, {self.agents_num}, {self.input_dim + 3}], got {tuple(obs_matrix.shape)}")
+        dev = obs_matrix.device
+        q = q_out if q_out is not None else torch.empty(B, N, 2, dtype=torch.float32, device=dev)
+        act = act_out if act_out is not None else torch.empty(B, N, dtype=torch.int8, device=dev)
+        if B:
+            self._call(obs_matrix.contiguous(), N * F, B, 0, ctrl_mask.contiguous(), q, act, eps, philox_seed,
+                       philox_offset, rand3)
+        return q, act

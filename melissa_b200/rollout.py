@@ -1,0 +1,90 @@
+"""Batched rollout: env round + Q-network forward + epsilon-greedy action selection for
+thousands of independent episodes, all on one CUDA stream with no host synchronisation.
+
+This is the loop the reference's collectors drive one agent at a time
+(graph_env/env/utils/collectors/multi_agent_collector.py:150-308): ``policy(batch)`` ->
+``exploration_noise`` -> ``env.step``.  The unit of work is the agent-transition the
+reference counts at multi_agent_collector.py:274 (one live agent taking one decision).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .batched_env import BatchedGraphEnv, ResetTuplesDevice
+from .networks.common import DGNBase
+from . import reset_chain
+
+
+class Rollout:
+    def __init__(self, env: BatchedGraphEnv, net: DGNBase | None, *, eps: float = 0.05, seed: int = 9):
+        self.env, self.net = env, net
+        self.eps, self.seed = float(eps), int(seed)
+        self.round_index = 0
+        B, N, dev = env.B, env.N, env.device
+        self.q = torch.zeros(B, N, 2, dtype=torch.float32, device=dev)
+        self.act = torch.full((B, N), -1, dtype=torch.int8, device=dev)
+        # host mirrors for the end-to-end (host buffer) path
+        self._host = None
+
+    # ---------------------------------------------------------------- setup helpers
+    @staticmethod
+    def make_tuples(env: BatchedGraphEnv, count: int, base_seed: int = 9, scripted_agents_ratio: float = 0.0):
+        gi, src, inter, scr, _ = reset_chain.episode_pool(base_seed, count, env.N, len(env.pool), scripted_agents_ratio)
+        return ResetTuplesDevice(gi, src, inter, scr, env.N, env.device)
+
+    def start(self, tuples: ResetTuplesDevice, recycle: bool = True):
+        """Reset every episode from the first B tuples; finished episodes restart from the pool."""
+        first = ResetTuplesDevice.__new__(ResetTuplesDevice)
+        first.count = self.env.B
+        first.graph_index, first.source = tuples.graph_index[: self.env.B], tuples.source[: self.env.B]
+        first.interested, first.scripted = tuples.interested[: self.env.B], tuples.scripted[: self.env.B]
+        self.env.reset(first)
+        self.env.set_recycling(tuples if recycle else None)
+        self.round_index = 0
+
+    # ---------------------------------------------------------------- device loop
+    def round(self):
+        """forward (one GNN pass per graph for all its active agents) -> eps-greedy -> env round."""
+        env = self.env
+        if self.net is not None:
+            self.net.forward_graphs(env.obs, env.active, eps=self.eps, philox_seed=self.seed,
+                                    philox_offset=self.round_index, q_out=self.q, act_out=self.act)
+        env.step_device(self.act)
+        self.round_index += 1
+
+    def transitions(self) -> int:
+        return int(self.env.transitions.item())
+
+    # ---------------------------------------------------------------- host-buffer loop (end to end)
+    def _host_buffers(self):
+        if self._host is None:
+            env = self.env
+            pin = lambda t: torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            self._host = dict(obs=pin(env.obs), active=pin(env.active), reward=pin(env.reward), done=pin(env.done),
+                              act=pin(self.act))
+            self._host["obs"].copy_(env.obs)
+            self._host["active"].copy_(env.active)
+            self._dev_in = dict(obs=torch.empty_like(env.obs), active=torch.empty_like(env.active))
+        return self._host
+
+    def round_host(self):
+        """The same round through host buffers, as a caller holding numpy observations would
+        drive it: obs/active H2D -> forward + act -> env round -> obs/reward/active/done/act D2H.
+        Returns (h2d_bytes, d2h_bytes)."""
+        h = self._host_buffers()
+        env = self.env
+        self._dev_in["obs"].copy_(h["obs"], non_blocking=True)
+        self._dev_in["active"].copy_(h["active"], non_blocking=True)
+        if self.net is not None:
+            self.net.forward_graphs(self._dev_in["obs"], self._dev_in["active"], eps=self.eps, philox_seed=self.seed,
+                                    philox_offset=self.round_index, q_out=self.q, act_out=self.act)
+        env.step_device(self.act)
+        self.round_index += 1
+        h["act"].copy_(self.act, non_blocking=True)
+        h["obs"].copy_(env.obs, non_blocking=True)
+        h["reward"].copy_(env.reward, non_blocking=True)
+        h["active"].copy_(env.active, non_blocking=True)
+        h["done"].copy_(env.done, non_blocking=True)
+        nb = lambda t: t.numel() * t.element_size()
+        return nb(h["obs"]) + nb(h["active"]), nb(h["act"]) + nb(h["obs"]) + nb(h["reward"]) + nb(h["active"]) + nb(h["done"])

@@ -1,0 +1,170 @@
+"""GPU parity of mls_dgn_forward (through the nn.Module mirrors and the C ABI) against the
+pure-torch fp32 restatement in oracle/net_oracle.py.
+
+Tolerance (fp32 mode), as BASELINE.json states: Q-values within 1e-5 relative.  Written
+here as  max|q_cuda - q_ref| <= 1e-5 * max(1, max|q_ref|)  per batch, plus greedy-action
+agreement wherever the reference's own margin |q1 - q0| exceeds 1e-4.
+"""
+import numpy as np
+import pytest
+import torch
+
+from melissa_b200 import reset_chain
+from melissa_b200.topology import GraphPool
+from oracle import net_oracle as no
+
+pytestmark = pytest.mark.gpu
+
+DUELING = lambda: ({"hidden_sizes": [128, 128]}, {"hidden_sizes": [128, 128]})
+REL_TOL = 1e-5
+
+
+def _module(kind, N, sd, **kw):
+    from melissa_b200.networks import NETWORKS
+    m = NETWORKS[kind](5, 128, 2, 4, N, dueling_param=DUELING(), device="cuda", **kw)
+    m.load_state_dict(sd)
+    return m.cuda()
+
+
+def _random_sd(kind, seed):
+    sd = no.init_state_dict(kind, seed=seed)
+    g = torch.Generator().manual_seed(seed + 1)
+    for k in sd:                      # non-zero biases everywhere so a dropped bias cannot hide
+        if k.endswith("bias"):
+            sd[k] = (torch.rand(sd[k].shape, generator=g) - 0.5) * 0.2
+    return sd
+
+
+def _obs_matrix(N, B, seed, scripted_ratio=0.3):
+    """Plausible obs matrices: positions of real synthetic graphs + random feature columns."""
+    pool = GraphPool.synthetic(N, min(B, 8), first_seed=seed, side=None if N in (20, 50) else min(1.0, (N / 50) ** 0.5))
+    rng = np.random.default_rng(seed)
+    gi = rng.integers(0, len(pool), size=B)
+    om = np.zeros((B, N, 8), dtype=np.float32)
+    om[:, :, :2] = pool.pos[gi]
+    om[:, :, 2] = pool.adj[gi].sum(2)
+    om[:, :, 3] = rng.integers(0, 5, size=(B, N))
+    om[:, :, 4] = rng.integers(0, 2, size=(B, N))
+    om[:, :, 5] = rng.integers(0, 2, size=(B, N))
+    om[:, :, 6] = rng.integers(0, 2, size=(B, N))
+    om[:, :, 7] = rng.random((B, N)) >= scripted_ratio
+    return om
+
+
+def _assert_q(got, want, what=""):
+    got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
+    scale = max(1.0, float(np.abs(want).max()) if want.size else 1.0)
+    err = float(np.abs(got - want).max()) if want.size else 0.0
+    assert err <= REL_TOL * scale, f"{what}: max abs err {err:.3e} > {REL_TOL} * {scale:.3f}"
+
+
+@pytest.mark.parametrize("kind", ["l_dgn", "dgn_r", "hl_dgn"])
+@pytest.mark.parametrize("N", [20, 50])
+def test_forward_agent_rows_matches_oracle(kind, N):
+    """Drop-in call: obs [bs, 8N+1] with the controlling index in the last column."""
+    bs = 24
+    sd = _random_sd(kind, 11)
+    om = _obs_matrix(N, bs, 5)
+    ctrl = np.random.default_rng(1).integers(0, N, size=bs).astype(np.float32)
+    ctrl[0], ctrl[1] = -4.0, N + 7.0                      # clamped (common.py:63)
+    rows = np.concatenate([om.reshape(bs, -1), ctrl[:, None]], axis=1)
+    kw = dict(aggregator="max") if kind == "hl_dgn" else {}
+    want = no.FORWARDS[kind](sd, torch.as_tensor(rows), N, **kw).numpy()
+    m = _module(kind, N, sd, **kw)
+    q, state = m(rows)                                    # numpy in, like tianshou feeds it
+    assert q.shape == (bs, 2) and q.dtype == torch.float32
+    _assert_q(q.cpu().numpy(), want, f"{kind} N={N}")
+    q2, _ = m(torch.as_tensor(rows, device="cuda"))
+    np.testing.assert_array_equal(q.cpu().numpy(), q2.cpu().numpy())
+    with pytest.raises(ValueError):
+        m(rows[:, :-1])
+    with pytest.raises(ValueError):
+        m(rows[0])
+
+
+@pytest.mark.parametrize("kind,kw", [("l_dgn", {}), ("dgn_r", {}), ("hl_dgn", {"aggregator": "max"}),
+                                      ("hl_dgn", {"aggregator": "mean"}), ("hl_dgn", {"aggregator": "add"})])
+@pytest.mark.parametrize("N,B", [(20, 40), (50, 20)])
+def test_forward_graphs_matches_oracle(kind, kw, N, B):
+    sd = _random_sd(kind, 21)
+    om = _obs_matrix(N, B, 9)
+    rng = np.random.default_rng(2)
+    cm = rng.random((B, N)) < 0.25
+    cm[0] = False                                         # a graph without controlling agents
+    cm[1] = True
+    want = no.forward_graphs(kind, sd, torch.as_tensor(om), torch.as_tensor(cm), N, **kw).numpy()
+    m = _module(kind, N, sd, **kw)
+    q, act = m.forward_graphs(torch.as_tensor(om, device="cuda"), torch.as_tensor(cm, device="cuda").to(torch.uint8))
+    q, act = q.cpu().numpy(), act.cpu().numpy()
+    _assert_q(q, want, f"{kind} N={N}")
+    assert np.all(q[~cm] == 0) and np.all(act[~cm] == -1)
+    margin = np.abs(want[..., 1] - want[..., 0])
+    sure = cm & (margin > 1e-4)
+    np.testing.assert_array_equal(act[sure], (want[..., 1] > want[..., 0]).astype(np.int8)[sure])
+
+
+def test_chunked_batches_and_many_graphs():
+    """More graphs than one workspace chunk: results must not depend on chunking."""
+    N, B = 20, 1500
+    sd = _random_sd("l_dgn", 3)
+    om = _obs_matrix(N, B, 13)
+    cm = np.random.default_rng(3).random((B, N)) < 0.2
+    m = _module("l_dgn", N, sd)
+    q, act = m.forward_graphs(torch.as_tensor(om, device="cuda"), torch.as_tensor(cm, device="cuda").to(torch.uint8))
+    sel = np.r_[0:40, 700:740, 1460:1500]
+    want = no.forward_graphs("l_dgn", sd, torch.as_tensor(om[sel]), torch.as_tensor(cm[sel]), N).numpy()
+    _assert_q(q.cpu().numpy()[sel], want, "chunked")
+
+
+@pytest.mark.parametrize("kind", ["l_dgn", "dgn_r"])
+def test_degenerate_graphs(kind):
+    """All nodes at one point (reference test fixture: pos=(0,0)) -> complete graph, capped at
+    32 neighbours in index order for N > 33; plus fully isolated nodes."""
+    for N in (12, 50):
+        sd = _random_sd(kind, 31)
+        B = 6
+        om = _obs_matrix(N, B, 17)
+        om[:3, :, :2] = 0.0
+        om[3:, :, 0] = np.arange(N)[None, :] * 1.0       # far apart: no edges at all
+        om[3:, :, 1] = 0.0
+        cm = np.ones((B, N), dtype=bool)
+        want = no.forward_graphs(kind, sd, torch.as_tensor(om), torch.as_tensor(cm), N).numpy()
+        m = _module(kind, N, sd)
+        q, _ = m.forward_graphs(torch.as_tensor(om, device="cuda"), torch.as_tensor(cm, device="cuda").to(torch.uint8))
+        _assert_q(q.cpu().numpy(), want, f"{kind} degenerate N={N}")
+
+
+def test_epsilon_greedy_with_host_fed_uniforms_and_philox():
+    N, B = 20, 64
+    sd = _random_sd("l_dgn", 41)
+    om = _obs_matrix(N, B, 19)
+    rng = np.random.default_rng(4)
+    cm = rng.random((B, N)) < 0.5
+    m = _module("l_dgn", N, sd)
+    om_d, cm_d = torch.as_tensor(om, device="cuda"), torch.as_tensor(cm, device="cuda").to(torch.uint8)
+    q, greedy = m.forward_graphs(om_d, cm_d)
+    rand3 = rng.random((B * N, 3))
+    eps = 0.3
+    _, act = m.forward_graphs(om_d, cm_d, eps=eps, rand3=torch.as_tensor(rand3, device="cuda"))
+    qn = q.cpu().numpy().reshape(B * N, 2)
+    want = no.exploration_noise(no.dqn_act(qn, np.ones((B * N, 2))), eps, rand3[:, 0], rand3[:, 1:], np.ones((B * N, 2)))
+    got = act.cpu().numpy().reshape(-1)
+    flat = cm.reshape(-1)
+    np.testing.assert_array_equal(got[flat], want[flat].astype(np.int8))
+    np.testing.assert_array_equal(greedy.cpu().numpy().reshape(-1)[flat], no.dqn_act(qn, None)[flat].astype(np.int8))
+    # Philox stream: deterministic in (seed, offset), explores at roughly the requested rate
+    _, a1 = m.forward_graphs(om_d, cm_d, eps=0.5, philox_seed=9, philox_offset=1)
+    _, a2 = m.forward_graphs(om_d, cm_d, eps=0.5, philox_seed=9, philox_offset=1)
+    _, a3 = m.forward_graphs(om_d, cm_d, eps=0.5, philox_seed=9, philox_offset=2)
+    assert torch.equal(a1, a2) and not torch.equal(a1, a3)
+    changed = (a1 != greedy).cpu().numpy().reshape(-1)[flat].mean()
+    assert 0.15 < changed < 0.35                          # eps/2 of the draws flip a binary action
+
+
+def test_checkpoint_keys_and_cpu_module_fails_loudly():
+    from melissa_b200 import _lib
+    from melissa_b200.networks import LDGNNetwork
+    m = LDGNNetwork(5, 128, 2, 4, 20, dueling_param=DUELING())
+    assert set(m.state_dict()) == set(no.init_state_dict("l_dgn"))
+    with pytest.raises(_lib.MelissaLibraryError):
+        m(np.zeros((1, 161), dtype=np.float32))           # parameters on the CPU: no fallback
