@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""bench.py -- agent-transitions/s of the batched rollout round (env round + DGN forward +
+epsilon-greedy action selection) on N B200s of one node.
+
+    python bench.py [--gpus N --steps K --warmup W] [--model l_dgn|hl_dgn|dgn_r] [--impl reference]
+
+A "step" is one round of the hot path over all resident episodes (BASELINE.json metric:
+"agent-transitions/sec (env step + DGN forward), 50-node graphs").  Workload at N=1: the
+per-GPU shard of BASELINE config 3 (L-DGN, 50-node graphs, 65536 episodes over 2 GPUs =
+32768 episodes per GPU); more GPUs hold more episodes (weak scaling, no data-path collective).
+Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "agent_transitions_per_sec"
+UNIT = "agent-transitions/s"
+CACHE_DIR = os.path.join(ROOT, "graph_topologies")
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default="l_dgn", choices=["l_dgn", "hl_dgn", "dgn_r", "none"])
+    ap.add_argument("--nodes", type=int, default=50)
+    ap.add_argument("--episodes", type=int, default=32768, help="episodes per GPU")
+    ap.add_argument("--graphs", type=int, default=1024)
+    ap.add_argument("--eps", type=float, default=0.05)
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--preroll", type=int, default=32, help="untimed rounds so episodes are spread over their lifetime")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-episodes", type=int, default=8, help="episodes per CPU process in the CPU arm")
+    ap.add_argument("--prof-kernel", default=None)
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------ synthetic inputs
+def load_pool(N, G):
+    from melissa_b200.topology import GraphPool
+    path = os.path.join(CACHE_DIR, f"pool_n{N}_{G}.npz")
+    if os.path.exists(path):
+        return GraphPool.load_npz(path)
+    pool = GraphPool.synthetic(N, G, first_seed=0)
+    try:
+        os.makedirs(CACHE_DIR, exist_ok=True)
+        pool.save_npz(path)
+    except OSError:
+        pass
+    return pool
+
+
+def _tuple_shard(args):
+    from melissa_b200 import reset_chain
+    base, count, N, G = args
+    return reset_chain.episode_pool(base, count, N, G)
+
+
+def load_tuples(N, G, count, base_seed=9):
+    """Reset tuples drawn with the reference's RNG chain, env seed = base_seed + k (tianshou
+    seeds vector env k with seed + k); graph k % G."""
+    path = os.path.join(CACHE_DIR, f"tuples_n{N}_g{G}_c{count}_s{base_seed}.npz")
+    if os.path.exists(path):
+        z = np.load(path)
+        return z["gi"], z["src"], z["inter"], z["scr"]
+    import multiprocessing as mp
+    procs = max(1, min(os.cpu_count() or 1, 16))
+    per = (count + procs - 1) // procs
+    jobs = [(base_seed + p * per, min(per, count - p * per), N, G) for p in range(procs) if p * per < count]
+    with mp.get_context("spawn").Pool(len(jobs)) as pool:
+        parts = pool.map(_tuple_shard, jobs)
+    gi = (np.arange(count) % G).astype(np.int32)
+    src = np.concatenate([p[1] for p in parts])
+    inter = np.concatenate([p[2] for p in parts])
+    scr = np.concatenate([p[3] for p in parts])
+    try:
+        np.savez_compressed(path, gi=gi, src=src, inter=inter, scr=scr)
+    except OSError:
+        pass
+    return gi, src, inter, scr
+
+
+# ------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v.lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------ our arm
+def algorithmic_flops(model, N, E_plus_self, A):
+    """SURVEY.md section 8d formulas, per graph-round."""
+    if model == "hl_dgn":
+        return N * 296192 + E_plus_self * 3072 + 328448
+    if model == "l_dgn":
+        return N * 1344768 + 2 * E_plus_self * 3072 + A * 656128
+    if model == "dgn_r":
+        return N * 2000128 + 2 * (E_plus_self - N) * 2048 + A * 656128
+    return 0
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from melissa_b200 import _lib
+    from melissa_b200.batched_env import BatchedGraphEnv, ResetTuplesDevice
+    from melissa_b200.networks import NETWORKS
+    from melissa_b200.rollout import Rollout
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except (OSError, ValueError):
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    tensor_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    peak_src = "measured" if peaks else "fallback"
+
+    N, B, G = args.nodes, args.episodes, args.graphs
+    pool = load_pool(N, G)
+    P = 2 * B
+    if rank == 0:
+        tup = load_tuples(N, G, P)
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        tup = load_tuples(N, G, P)
+    gi, src, inter, scr = [np.roll(a, -rank * (B // 2), axis=0) for a in tup]   # each rank starts elsewhere in the pool
+    env = BatchedGraphEnv(B, N, pool, device=dev, want_obs=True)
+    net = None
+    if args.model != "none":
+        torch.manual_seed(9)
+        kw = dict(aggregator="max") if args.model == "hl_dgn" else {}
+        net = NETWORKS[args.model](5, 128, 2, 4, N, dueling_param=({"hidden_sizes": [128, 128]}, {"hidden_sizes": [128, 128]}),
+                                   device=str(dev), **kw).to(dev)
+        net.set_precision(args.precision)
+    ro = Rollout(env, net, eps=args.eps, seed=9 + rank)
+    ro.start(ResetTuplesDevice(gi, src, inter, scr, N, dev))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    if net is None:
+        ro.act.copy_(torch.randint(0, 2, ro.act.shape, device=dev, dtype=torch.int8))
+    for _ in range(args.preroll):
+        ro.round()
+    for _ in range(args.warmup):
+        ro.round()
+    sync_all()
+
+    prof_name = args.prof_kernel or ("proj2" if args.model in ("l_dgn", "dgn_r") else "proj1")
+    pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if net is not None:
+        net.set_profile_events(prof_name, pe0, pe1)
+
+    def timed(fn, steps):
+        """K steps, L2 flushed between steps (outside the per-step event pairs)."""
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        t_before = ro.transitions()
+        l_before = _lib.lib().mls_launch_count()
+        prof_ms, extra = [], []
+        sync_all()
+        for s in range(steps):
+            flush.zero_()
+            evs[s][0].record()
+            extra.append(fn())
+            evs[s][1].record()
+            if net is not None:
+                evs[s][1].synchronize()
+                prof_ms.append(pe0.elapsed_time(pe1))
+        sync_all()
+        ms = sum(a.elapsed_time(b) for a, b in evs)
+        return ms, ro.transitions() - t_before, _lib.lib().mls_launch_count() - l_before, prof_ms, extra
+
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    ms, trans, launches, prof_ms, _ = timed(ro.round, args.steps)
+    clk = clocks.stop() if rank == 0 else None
+
+    # env kernel alone (HBM roofline of the environment round)
+    env_evs = []
+    for s in range(min(args.steps, 10)):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); env.step_device(ro.act); b.record()
+        env_evs.append((a, b))
+    torch.cuda.synchronize()
+    env_ms = float(np.mean([a.elapsed_time(b) for a, b in env_evs]))
+
+    e2e = None
+    if not args.no_e2e:
+        if net is not None:
+            net.set_profile_events(None)
+        for _ in range(2):
+            ro.round_host()
+        e_ms, e_trans, _, _, ex = timed(ro.round_host, args.steps)
+        e2e = (e_ms, e_trans, ex[0])
+
+    def reduce(v, op):
+        if world == 1:
+            return v
+        t = torch.tensor([float(v)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    ms_max = reduce(ms, dist.ReduceOp.MAX if world > 1 else None)
+    trans_sum = reduce(trans, dist.ReduceOp.SUM if world > 1 else None)
+    launches_sum = reduce(launches, dist.ReduceOp.SUM if world > 1 else None)
+    if e2e is not None:
+        e_ms_max = reduce(e2e[0], dist.ReduceOp.MAX if world > 1 else None)
+        e_trans_sum = reduce(e2e[1], dist.ReduceOp.SUM if world > 1 else None)
+
+    out = None
+    if rank == 0:
+        steps = args.steps
+        value = trans_sum / (ms_max / 1e3)
+        A = trans / (steps * B)                                   # mean active agents per graph-round (this rank)
+        deg = float(pool.adj.sum()) / len(pool)                   # directed edges per graph
+        flops_round = algorithmic_flops(args.model, N, deg + N, A)
+        # dominant kernel: projection GEMM launch that was bracketed with events (first chunk of every forward)
+        HC, hid = 512, 128
+        chunk_rows = min(B, max(1, 8192 // N)) * N
+        K = HC if prof_name == "proj2" else hid
+        kern_flops = 2.0 * chunk_rows * HC * K
+        kern_ms = float(np.mean(prof_ms)) if prof_ms else None
+        roofline = None
+        if kern_ms:
+            ach = kern_flops / (kern_ms * 1e-3) / 1e12
+            roofline = {"kernel": f"{args.precision} projection GEMM ({prof_name}, [{chunk_rows}x{K}]x[{K}x{HC}])",
+                        "bound": "tensor", "achieved": round(ach, 3), "peak": tensor_peak, "unit": "TFLOP/s",
+                        "frac": round(ach / tensor_peak, 5), "traffic": None, "peak_source": f"{peak_src} (sustained bf16)",
+                        "kernel_ms": round(kern_ms, 5), "launch_flops": kern_flops}
+        W = _lib.words_per_row(N)
+        env_bytes = B * (N * (4 * W + 4 + 4 + 2 + 2 + 1 + 32 + 8 + 1 + 1) + 8 * 4 + 8 + 1)   # adj+pos(pool, L2) not counted
+        env_roof = {"kernel": "env_round_kernel", "bound": "hbm", "achieved": round(env_bytes / (env_ms * 1e-3) / 1e9, 1),
+                    "peak": hbm_peak, "unit": "GB/s", "frac": round(env_bytes / (env_ms * 1e-3) / 1e9 / hbm_peak, 4),
+                    "kernel_ms": round(env_ms, 5), "launch_bytes": env_bytes, "peak_source": peak_src}
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": args.warmup,
+            "ms_per_step": ms_max / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
+            "config": {
+                "workload": f"{args.model} rollout round (env round + forward + eps-greedy), {N}-node graphs, "
+                            f"{B} episodes per GPU (BASELINE config 3 per-GPU shard)",
+                "episodes_per_gpu": B, "n_nodes": N, "graph_pool": len(pool), "eps": args.eps, "precision": args.precision,
+                "preroll_rounds": args.preroll, "l2": "flushed between timed steps (256 MiB memset outside the timed events)",
+                "active_agents_per_graph_round": round(A, 3), "graph_rounds_per_s": world * B * steps / (ms_max / 1e3),
+                "model_tflops_algorithmic": round(flops_round * B * steps / (ms / 1e3) / 1e12, 3),
+            },
+            "gpu_launches": int(launches_sum),
+            "clocks": clk,
+            "roofline": roofline if roofline else env_roof,
+            "roofline_env": env_roof,
+        }
+        if e2e is not None:
+            out["e2e"] = {"value": e_trans_sum / (e_ms_max / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(e2e[2][0]),
+                          "d2h_bytes_per_step": int(e2e[2][1]), "ms_per_step": e_ms_max / steps}
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return out
+
+
+# ------------------------------------------------------------------------------ CPU arms
+def cpu_arm(model, N, eps, episodes_per_proc, rounds, warmup):
+    from oracle import cpu_rollout
+    kind = None if model == "none" else model
+    r = cpu_rollout.run_parallel(kind, N, episodes_per_proc, rounds, warmup, eps=eps)
+    return r
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return None
+    r = cpu_arm(args.model, args.nodes, args.eps, args.cpu_episodes, args.steps, args.warmup)
+    sample = (f"oracle port (numpy env + per-agent-obs torch forward), {r['cores']} processes x {args.cpu_episodes} episodes, "
+              f"{args.steps} rounds each after {args.warmup} warm-up rounds")
+    return {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": r["seconds"] * 1e3 / max(1, args.steps), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.model} rollout round, {args.nodes}-node graphs, CPU port of the reference path",
+                   "n_nodes": args.nodes, "eps": args.eps},
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": sample},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        out = run_reference(args)
+        if out is not None:
+            print(json.dumps(out), flush=True)
+        return
+    out = run_ours(args)
+    if out is None:
+        return
+    if not args.no_cpu_baseline and args.gpus == 1:
+        t0 = time.time()
+        r = cpu_arm(args.model, args.nodes, args.eps, args.cpu_episodes, 4, 1)
+        out["cpu_baseline"] = {
+            "value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+            "sample": f"oracle port, {r['cores']} processes x {args.cpu_episodes} episodes x 4 rounds (1 warm-up), "
+                      f"{r['transitions']} transitions in {r['seconds']:.1f}s (wall {time.time() - t0:.0f}s)"}
+    print(json.dumps(out), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -38,6 +38,8 @@ const char* mls_last_error(void);
 int mls_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);
 /* words per bitmask row for N nodes: 1 (N<=32), 2 (<=64), 4 (<=128), 8 (<=256). */
 int mls_words_per_row(int n_nodes);
+/* kernels launched by this library since it was loaded (process wide; for bench accounting). */
+unsigned long long mls_launch_count(void);
 
 /* ===== environment round ===============================================================
  * Replaces graph_env/env/utils/core.py (World: reset :343-437, step :225-266,
@@ -207,7 +209,22 @@ typedef struct MlsForwardArgs {
   const double* rand3;       /* optional host-fed uniforms [rows][3] = (u_eps, u_act0, u_act1) */
   void* workspace;           /* mls_dgn_workspace_bytes() bytes                              */
   size_t workspace_bytes;
+  /* optional timing hook: cudaEvent_t pair recorded right before / after ONE launch of the
+   * kernel class `prof_kernel` (enum MlsProfKernel) in the first chunk of this call */
+  void* prof_start;
+  void* prof_stop;
+  int32_t prof_kernel;
+  int32_t pad2_;
 } MlsForwardArgs;
+
+enum MlsProfKernel {
+  MLS_PROF_NONE = 0,
+  MLS_PROF_PROJ1 = 1, /* conv1 projection GEMM (first weight tensor)                         */
+  MLS_PROF_PROJ2 = 2, /* conv2 projection GEMM (first weight tensor)                         */
+  MLS_PROF_EDGE1 = 3, /* conv1 edge softmax/aggregate                                        */
+  MLS_PROF_EDGE2 = 4, /* conv2 edge softmax/aggregate                                        */
+  MLS_PROF_HEAD0 = 5  /* first dueling-head layer (Q)                                        */
+};
 
 size_t mls_dgn_workspace_bytes(const MlsNetDesc* desc, int32_t n_graphs);
 int mls_dgn_forward(const MlsNetDesc* desc, const MlsNetWeights* w, const MlsForwardArgs* args,

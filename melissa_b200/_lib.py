@@ -76,10 +76,14 @@ class MlsForwardArgs(C.Structure):
     _fields_ = [("obs", vp), ("obs_stride", C.c_int64), ("n_graphs", C.c_int32), ("ctrl_mode", C.c_int32),
                 ("ctrl_mask", vp), ("q", vp), ("act", vp), ("eps", C.c_float), ("pad_", C.c_int32),
                 ("philox_seed", C.c_uint64), ("philox_offset", C.c_uint64), ("rand3", vp), ("workspace", vp),
-                ("workspace_bytes", C.c_size_t)]
+                ("workspace_bytes", C.c_size_t), ("prof_start", vp), ("prof_stop", vp), ("prof_kernel", C.c_int32),
+                ("pad2_", C.c_int32)]
 
 
-EXPORTS = ["mls_version", "mls_last_error", "mls_device_info", "mls_words_per_row", "mls_env_reset", "mls_env_step",
+PROF_KERNELS = {None: 0, "proj1": 1, "proj2": 2, "edge1": 3, "edge2": 4, "head0": 5}
+
+
+EXPORTS = ["mls_version", "mls_last_error", "mls_device_info", "mls_words_per_row", "mls_launch_count", "mls_env_reset", "mls_env_step",
            "mls_env_info", "mls_dgn_workspace_bytes", "mls_dgn_forward"]
 
 _lib = None
@@ -103,6 +107,7 @@ def lib():
     L.mls_last_error.restype = C.c_char_p
     L.mls_device_info.argtypes = [C.POINTER(C.c_int32)] * 3
     L.mls_words_per_row.argtypes = [C.c_int]
+    L.mls_launch_count.restype = C.c_ulonglong
     P = C.POINTER
     L.mls_env_reset.argtypes = [P(MlsEnvDesc), P(MlsEnvState), vp, P(MlsResetTuples), P(MlsRoundInputs),
                                 P(MlsRoundOutputs), vp]

@@ -3,7 +3,11 @@
 
 #include "common.cuh"
 
+#include <atomic>
 static thread_local char g_err[512] = "";
+static std::atomic<unsigned long long> g_launches{0};
+void mls_count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+extern "C" unsigned long long mls_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 void mls_set_error(const char* fmt, ...) {
   va_list ap;

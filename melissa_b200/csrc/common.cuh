@@ -7,6 +7,7 @@
 #include "../../include/melissa_b200.h"
 
 void mls_set_error(const char* fmt, ...);
+void mls_count_launch(int n = 1);
 
 #define MLS_CHECK_ARG(cond, ...)          \
   do {                                    \

@@ -411,6 +411,7 @@ void sgemm(cudaStream_t st, const float* A, int lda, const float* obs_scale, int
            int ldw, const float* bias, float* C, int ldc, int M, const int* m_dev, int Nout, int K, int relu) {
   dim3 grid((Nout + GB - 1) / GB, (M + GB - 1) / GB);
   sgemm_kernel<<<grid, 256, 0, st>>>(A, lda, obs_scale, obs_stride, N, Wt, ldw, bias, C, ldc, M, m_dev, Nout, K, relu);
+  mls_count_launch();
 }
 
 template <int W>
@@ -418,12 +419,14 @@ void launch_gat_edge(cudaStream_t st, const float* P, int ldp, const float* obs,
                      const float* att, const float* bias, float* out, int ldo) {
   const long long warps = (long long)rows * H;
   gatv2_edge_kernel<W><<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(P, ldp, obs, os, N, rows, H, att, bias, out, ldo);
+  mls_count_launch();
 }
 template <int W>
 void launch_tr_edge(cudaStream_t st, const float* P, int ldp, const float* obs, int64_t os, int N, int rows, int H,
                     float* out, int ldo) {
   const long long warps = (long long)rows * H;
   transformer_edge_kernel<W><<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(P, ldp, obs, os, N, rows, H, out, ldo);
+  mls_count_launch();
 }
 
 }  // namespace
@@ -466,6 +469,10 @@ extern "C" int mls_dgn_forward(const MlsNetDesc* d, const MlsNetWeights* w, cons
     if (a->act) MLS_CUDA(cudaMemsetAsync(a->act, 0xFF, (size_t)a->n_graphs * N, st));
   }
 
+  cudaEvent_t ev0 = reinterpret_cast<cudaEvent_t>(a->prof_start), ev1 = reinterpret_cast<cudaEvent_t>(a->prof_stop);
+  bool first_chunk = true;
+  auto prof_begin = [&](int which) { if (first_chunk && ev0 && ev1 && a->prof_kernel == which) cudaEventRecord(ev0, st); };
+  auto prof_end = [&](int which) { if (first_chunk && ev0 && ev1 && a->prof_kernel == which) cudaEventRecord(ev1, st); };
   auto edge = [&](const float* P, const float* obs, int rows, const float* att, const float* bias, float* out) {
     if (tr) {
       switch (Wn) {
@@ -484,13 +491,15 @@ extern "C" int mls_dgn_forward(const MlsNetDesc* d, const MlsNetWeights* w, cons
     }
   };
   // projection weights are separate tensors in the state_dict: one GEMM per tensor, written side by side
-  auto project = [&](const float* X, int K, const float* obs_scale, const float* obs, const float* wa, const float* ba,
+  auto project = [&](const float* X, int K, const float* obs_scale, int prof_id, const float* wa, const float* ba,
                      const float* wb, const float* bb, const float* wc, const float* bc, int rows) {
     const float* ws_[3] = {wa, wb, wc};
     const float* bs_[3] = {ba, bb, bc};
-    for (int t = 0; t < nproj; ++t)
+    for (int t = 0; t < nproj; ++t) {
+      if (t == 0) prof_begin(prof_id);
       sgemm(st, X, K, obs_scale, a->obs_stride, N, ws_[t], K, bs_[t], ws.P + (size_t)t * HC, nproj * HC, rows, nullptr, HC, K, 0);
-    (void)obs;
+      if (t == 0) prof_end(prof_id);
+    }
   };
 
   for (int g0 = 0; g0 < a->n_graphs; g0 += Gc) {
@@ -502,40 +511,52 @@ extern "C" int mls_dgn_forward(const MlsNetDesc* d, const MlsNetWeights* w, cons
     {
       dim3 blk(32, 8);
       enc0_kernel<<<(rows + 7) / 8, blk, 0, st>>>(obs, a->obs_stride, N, rows, d->input_dim, w->enc_w0, w->enc_b0, hid, ws.h);
+      mls_count_launch();
       sgemm(st, ws.h, hid, nullptr, 0, N, w->enc_w1, hid, w->enc_b1, ws.x0, hid, rows, nullptr, hid, hid, 1);
     }
     // conv1 (+relu)
-    if (tr) project(ws.x0, hid, nullptr, obs, w->c1_wa, w->c1_ba, w->c1_wb, w->c1_bb, w->c1_wc, w->c1_bc, rows);
-    else project(ws.x0, hid, nullptr, obs, w->c1_wa, w->c1_ba, w->c1_wb, w->c1_bb, nullptr, nullptr, rows);
+    if (tr) project(ws.x0, hid, nullptr, MLS_PROF_PROJ1, w->c1_wa, w->c1_ba, w->c1_wb, w->c1_bb, w->c1_wc, w->c1_bc, rows);
+    else project(ws.x0, hid, nullptr, MLS_PROF_PROJ1, w->c1_wa, w->c1_ba, w->c1_wb, w->c1_bb, nullptr, nullptr, rows);
+    prof_begin(MLS_PROF_EDGE1);
     edge(ws.P, obs, rows, w->c1_att, w->c1_bias, ws.x1);
+    prof_end(MLS_PROF_EDGE1);
     if (!hl) {
       // conv2 on x1 * dm (+relu); the x1 snapshot used by the head stays unmasked
-      if (tr) project(ws.x1, HC, obs, obs, w->c2_wa, w->c2_ba, w->c2_wb, w->c2_bb, w->c2_wc, w->c2_bc, rows);
-      else project(ws.x1, HC, obs, obs, w->c2_wa, w->c2_ba, w->c2_wb, w->c2_bb, nullptr, nullptr, rows);
+      if (tr) project(ws.x1, HC, obs, MLS_PROF_PROJ2, w->c2_wa, w->c2_ba, w->c2_wb, w->c2_bb, w->c2_wc, w->c2_bc, rows);
+      else project(ws.x1, HC, obs, MLS_PROF_PROJ2, w->c2_wa, w->c2_ba, w->c2_wb, w->c2_bb, nullptr, nullptr, rows);
+      prof_begin(MLS_PROF_EDGE2);
       edge(ws.P, obs, rows, w->c2_att, w->c2_bias, ws.x2);
+      prof_end(MLS_PROF_EDGE2);
       MLS_CUDA(cudaMemsetAsync(ws.count, 0, sizeof(int), st));
       ctrl_list_kernel<<<(gc * 32 + 255) / 256, 256, 0, st>>>(cm, obs, a->obs_stride, N, gc, a->ctrl_mode, ws.idx, ws.count);
       gather_kernel<<<rows, 128, 0, st>>>(ws.idx, ws.count, ws.x0, hid, ws.x1, HC, ws.x2, HC, ws.z);
+      mls_count_launch(2);
     } else {
       pool_kernel<<<gc, 128, 0, st>>>(ws.x1, HC, obs, a->obs_stride, N, HC, d->pool, ws.z);
+      mls_count_launch();
     }
     const int head_rows = hl ? gc : rows;
     const int* m_dev = hl ? nullptr : ws.count;
     // dueling head: Q = MLP(latent->hh->hh->2), V = MLP(latent->hh->hh->1)
+    prof_begin(MLS_PROF_HEAD0);
     sgemm(st, ws.z, latent, nullptr, 0, N, w->q_w0, latent, w->q_b0, ws.hid1, 2 * hh, head_rows, m_dev, hh, latent, 1);
+    prof_end(MLS_PROF_HEAD0);
     sgemm(st, ws.z, latent, nullptr, 0, N, w->v_w0, latent, w->v_b0, ws.hid1 + hh, 2 * hh, head_rows, m_dev, hh, latent, 1);
     sgemm(st, ws.hid1, 2 * hh, nullptr, 0, N, w->q_w1, hh, w->q_b1, ws.hid2, 2 * hh, head_rows, m_dev, hh, hh, 1);
     sgemm(st, ws.hid1 + hh, 2 * hh, nullptr, 0, N, w->v_w1, hh, w->v_b1, ws.hid2 + hh, 2 * hh, head_rows, m_dev, hh, hh, 1);
     if (!hl) {
       head_out_kernel<<<(rows * 32 + 255) / 256, 256, 0, st>>>(ws.hid2, hh, ws.idx, ws.count, rows, w->q_w2, w->q_b2, w->v_w2,
                                                                w->v_b2, (int64_t)g0 * N, N, a->q, a->act, a->ctrl_mode, aa);
+      mls_count_launch();
     } else {
       head_out_kernel<<<(gc * 32 + 255) / 256, 256, 0, st>>>(ws.hid2, hh, nullptr, nullptr, gc, w->q_w2, w->q_b2, w->v_w2,
                                                              w->v_b2, 0, N, ws.qg, nullptr, 2, aa);
       const long long nthr = a->ctrl_mode == 1 ? gc : (long long)gc * N;
       hl_scatter_kernel<<<(unsigned)((nthr + 255) / 256), 256, 0, st>>>(ws.qg, cm, N, gc, g0, a->ctrl_mode, a->q, a->act, aa);
+      mls_count_launch(2);
     }
     MLS_LAUNCH_CHECK();
+    first_chunk = false;
   }
   return MLS_OK;
 }

@@ -665,6 +665,7 @@ int launch_env(const EnvParams& p, cudaStream_t stream) {
                 sizeof(uint32_t) * M_COUNT * G * W + sizeof(int) * (G * 4 + 1);
   if (blocks == 0) return MLS_OK;
   env_round_kernel<W><<<blocks, threads, smem, stream>>>(p);
+  mls_count_launch();
   MLS_LAUNCH_CHECK();
   return MLS_OK;
 }

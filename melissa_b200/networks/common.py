@@ -180,8 +180,20 @@ class DGNBase(nn.Module):
         wsp = self._ws.get(nbytes, obs.device)
         args = _lib.MlsForwardArgs(obs.data_ptr(), stride, n_graphs, ctrl_mode, _lib.ptr(ctrl_mask), q.data_ptr(),
                                    _lib.ptr(act), float(eps), 0, int(seed), int(offset), _lib.ptr(rand3),
-                                   wsp.data_ptr(), wsp.numel())
+                                   wsp.data_ptr(), wsp.numel(), None, None, 0, 0)
+        prof = getattr(self, "_prof", None)
+        if prof is not None:          # (cudaEvent start, cudaEvent stop, kernel id), see set_profile_events
+            args.prof_start, args.prof_stop, args.prof_kernel = prof[0].cuda_event, prof[1].cuda_event, prof[2]
         _lib.check(L.mls_dgn_forward(C.byref(desc), C.byref(ws), C.byref(args), _lib.current_stream_ptr()))
+
+    def set_profile_events(self, kernel: Optional[str], start=None, stop=None):
+        """Record ``start``/``stop`` (torch.cuda.Event with timing) around one launch of the named
+        kernel class in every forward call (bench.py roofline line).  ``None`` switches it off."""
+        if kernel is None:
+            self._prof = None
+        else:
+            start.record(); stop.record()      # materialise the underlying cudaEvent_t handles
+            self._prof = (start, stop, _lib.PROF_KERNELS[kernel])
 
     # ------------------------------------------------------------------ public
     def forward(self, obs, state=None, info={}):

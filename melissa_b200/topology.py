@@ -43,6 +43,32 @@ def make_connected_graph(n_nodes: int, graph_seed: int, side: float | None = Non
             return g
 
 
+def _is_connected(adj: np.ndarray) -> bool:
+    n = adj.shape[0]
+    seen = np.zeros(n, dtype=bool)
+    seen[0] = True
+    frontier = seen.copy()
+    while frontier.any():
+        nxt = adj[frontier].any(axis=0) & ~seen
+        seen |= nxt
+        frontier = nxt
+    return bool(seen.all())
+
+
+def connected_geometric_arrays(n_nodes: int, graph_seed: int, side: float | None = None,
+                               radius: float = RADIUS_OF_INFLUENCE):
+    """numpy twin of :func:`make_connected_graph`: -> (adj bool [N,N], pos float64 [N,2])."""
+    side = default_square_side(n_nodes) if side is None else side
+    rng = np.random.default_rng(graph_seed)
+    eye = np.eye(n_nodes, dtype=bool)
+    while True:
+        p = rng.uniform(0.0, side, size=(n_nodes, 2))
+        d = p[:, None, :] - p[None, :, :]
+        adj = ((d * d).sum(-1) <= radius * radius) & ~eye
+        if _is_connected(adj):
+            return adj, p
+
+
 def graph_to_arrays(g: nx.Graph, n_nodes: int | None = None):
     """-> (adj bool [N,N], pos float64 [N,2]).  Node labels must be 0..N-1."""
     n = g.number_of_nodes() if n_nodes is None else n_nodes
@@ -127,7 +153,10 @@ class GraphPool:
 
     @classmethod
     def synthetic(cls, n_nodes: int, count: int, first_seed: int = 0, side: float | None = None):
-        arrs = [graph_to_arrays(make_connected_graph(n_nodes, s, side)) for s in range(first_seed, first_seed + count)]
+        """``count`` connected random geometric graphs, graph k from ``graph_seed = first_seed + k``.
+        Same draws and same graphs as :func:`make_connected_graph` (checked in
+        tests/test_host_logic.py), without building networkx objects."""
+        arrs = [connected_geometric_arrays(n_nodes, s, side) for s in range(first_seed, first_seed + count)]
         return cls(np.stack([a for a, _ in arrs]), np.stack([p for _, p in arrs]))
 
     @classmethod
