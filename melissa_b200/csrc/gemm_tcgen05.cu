@@ -1,0 +1,302 @@
+// tcgen05 / TMEM / TMA bf16 GEMM for the dense projections of the DGN networks (sm_100a).
+// See gemm_tcgen05.cuh for the contract.  Replaces the cuBLAS sgemm calls behind
+// torch.nn.Linear in PyG GATv2Conv / TransformerConv and tianshou MLP
+// (reference l_dgn.py:125,133,142-149; dgn_r.py:105,113; hl_dgn.py:101,111-117).
+#include "gemm_tcgen05.cuh"
+
+namespace mls {
+
+// ------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tm) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128B-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart
+// (cute::UMMA::SmemDescriptor: start>>4 | LBO>>4 @16 | SBO>>4 @32 | version=1 @46 | layout SWIZZLE_128B=2 @61)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// cute::UMMA::InstrDescriptor for kind::f16: D=F32 (bit4), A=B=BF16 (bits 7,10), K-major both, N>>3 @17, M>>4 @24
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+template <int BN>
+struct GemmSmem {
+  static constexpr int kABytes = kBM * kBK * 2;      // 16 KiB
+  static constexpr int kBBytes = BN * kBK * 2;       // 16 / 32 KiB
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kBarOffset = kStages * kStageBytes;
+  static constexpr int kTotal = kBarOffset + 256 + 1024;   // barriers + alignment slack
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                         const GemmShape shape, const GemmEpilogue epi) {
+  using S = GemmSmem<BN>;
+  extern __shared__ unsigned char smem_raw[];
+  // SWIZZLE_128B tiles need 1024-byte alignment
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kBarOffset);
+  // bars[0..S) full, [S..2S) empty, [2S..2S+2) tmem_full, [2S+2..2S+4) tmem_empty
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+  const uint32_t bar0 = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (kStages + s); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * kStages + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * kStages + 2 + a); };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int M = shape.M;
+  if (shape.m_dev) M = min(M, *shape.m_dev);
+  const int n_m = (M + kBM - 1) / kBM, n_n = shape.N / BN;
+  const int n_tiles = n_m * n_n;
+  const int n_kb = shape.K / kBK;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(smem_u32(tmem_slot), 2 * BN);      // 2 accumulator stages of BN fp32 columns
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int m0 = (tile / n_n) * kBM, n0 = (tile % n_n) * BN;
+        for (int kb = 0; kb < n_kb; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t sa = smem_u32(smem + stage * S::kStageBytes);
+          mbar_expect_tx(full_bar(stage), S::kStageBytes);
+          tma_load_2d(sa, &tmA, full_bar(stage), kb * kBK, m0);
+          tma_load_2d(sa + S::kABytes, &tmB, full_bar(stage), kb * kBK, n0);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer (one thread)
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(kBM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1);          // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < n_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase);                // TMA bytes have landed
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * S::kStageBytes);
+          const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + S::kABytes);
+#pragma unroll
+          for (int k = 0; k < kBK / kUmmaK; ++k)            // +32 B per K=16 step inside the swizzle atom
+            umma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+          umma_commit(empty_bar(stage));                    // frees the smem slot when these MMAs retire
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(tfull_bar(acc));                        // accumulator complete -> epilogue
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================================================================== epilogue (TMEM -> regs -> global)
+    const int ew = warp - 4;                                // == warp % 4: the TMEM lane quarter this warp may read
+    int it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int m0 = (tile / n_n) * kBM, n0 = (tile % n_n) * BN;
+      const int r = m0 + ew * 32 + lane;
+      float scale = 1.0f;
+      if (epi.obs && r < M) {
+        const int g = r / epi.nodes, i = r - g * epi.nodes;
+        scale = epi.obs[(long long)g * epi.obs_stride + i * 8 + 7];
+      }
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN + c0), v);
+        if (r < M) {
+          uint32_t packed[16];
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            float x0 = __uint_as_float(v[j]) * scale, x1 = __uint_as_float(v[j + 1]) * scale;
+            if (epi.bias) { x0 += __ldg(epi.bias + n0 + c0 + j); x1 += __ldg(epi.bias + n0 + c0 + j + 1); }
+            if (epi.relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
+            __nv_bfloat162 b2 = __floats2bfloat162_rn(x0, x1);
+            packed[j >> 1] = *reinterpret_cast<uint32_t*>(&b2);
+          }
+          uint4* dst = reinterpret_cast<uint4*>(epi.C + (size_t)r * epi.ldc + n0 + c0);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) dst[q] = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(acc));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 2 * BN);
+}
+
+// ------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+static int make_tmap(CUtensorMap* tm, const void* base, int rows, int cols, int ld_elems, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { mls_set_error("cuTensorMapEncodeTiled not available from the driver"); return MLS_ERR_CUDA; }
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld_elems * 2};
+  cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { mls_set_error("cuTensorMapEncodeTiled failed with %d (rows=%d cols=%d ld=%d)", (int)r, rows, cols, ld_elems); return MLS_ERR_CUDA; }
+  return MLS_OK;
+}
+
+size_t gemm_smem_bytes(int BN) { return BN == 256 ? GemmSmem<256>::kTotal : GemmSmem<128>::kTotal; }
+
+template <int BN>
+static int launch_bn(const CUtensorMap& ta, const CUtensorMap& tb, GemmShape shape, GemmEpilogue epi, int sm_count, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    MLS_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN>::kTotal));
+    configured = true;
+  }
+  const int n_tiles = ((shape.M + kBM - 1) / kBM) * (shape.N / BN);
+  const int grid = n_tiles < sm_count ? n_tiles : sm_count;
+  if (grid <= 0) return MLS_OK;
+  gemm_bf16_tcgen05_kernel<BN><<<grid, kGemmThreads, GemmSmem<BN>::kTotal, st>>>(ta, tb, shape, epi);
+  mls_count_launch();
+  MLS_LAUNCH_CHECK();
+  return MLS_OK;
+}
+
+int gemm_bf16_launch(const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, int ldb, GemmShape shape, GemmEpilogue epi,
+                     int sm_count, cudaStream_t st) {
+  MLS_CHECK_ARG(shape.K % kBK == 0 && shape.K >= kBK, "GEMM K must be a multiple of %d (got %d)", kBK, shape.K);
+  MLS_CHECK_ARG(shape.N % 128 == 0, "GEMM N must be a multiple of 128 (got %d)", shape.N);
+  MLS_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0 && epi.ldc % 8 == 0, "GEMM leading dimensions must be multiples of 8 elements");
+  if (shape.M <= 0) return MLS_OK;
+  const int BN = (shape.N % 256 == 0) ? 256 : 128;
+  CUtensorMap ta, tb;
+  int rc = make_tmap(&ta, A, shape.M, shape.K, lda, kBM);
+  if (rc) return rc;
+  rc = make_tmap(&tb, B, shape.N, shape.K, ldb, BN);
+  if (rc) return rc;
+  return BN == 256 ? launch_bn<256>(ta, tb, shape, epi, sm_count, st) : launch_bn<128>(ta, tb, shape, epi, sm_count, st);
+}
+
+}  // namespace mls
+
+// Standalone entry for the GEMM unit test (tests/test_gemm_gpu.py); not part of the reference-facing ABI.
+extern "C" int mls_test_gemm_bf16(const void* A, const void* B, const float* bias, const float* obs, long long obs_stride,
+                                  int nodes, void* C, int M, int N, int K, int relu, const int* m_dev, void* stream) {
+  int dev = 0, sms = 0;
+  MLS_CUDA(cudaGetDevice(&dev));
+  MLS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  mls::GemmShape shape{M, N, K, m_dev};
+  mls::GemmEpilogue epi{reinterpret_cast<__nv_bfloat16*>(C), N, bias, obs, obs_stride, nodes, relu};
+  return mls::gemm_bf16_launch(reinterpret_cast<const __nv_bfloat16*>(A), K, reinterpret_cast<const __nv_bfloat16*>(B), K, shape,
+                               epi, sms, reinterpret_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,39 @@
+// Persistent warp-specialised bf16 GEMM on the 5th-gen tensor cores (sm_100a):
+//     C[M, N] (bf16) = act( rowscale[m] * (A[M, K] @ B[N, K]^T) + bias[n] )
+// A and B are K-major bf16 in global memory, moved by TMA (128B swizzle) into a 4-stage
+// shared-memory ring; one thread issues tcgen05.mma (M=128, N=BN, K=16) into a double
+// buffered fp32 accumulator in TMEM; four epilogue warps drain TMEM with tcgen05.ld, apply
+// the fused epilogue and store bf16 rows.  One CTA per SM, static round-robin tile order
+// with the N tiles of one M tile adjacent (A tile stays hot in L2).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace mls {
+
+constexpr int kBM = 128, kBK = 64, kUmmaK = 16, kStages = 4;
+constexpr int kGemmThreads = 256;
+
+struct GemmEpilogue {
+  __nv_bfloat16* C;      // [M, ldc]
+  int ldc;
+  const float* bias;     // [N] or NULL
+  const float* obs;      // row scale = obs[(m / nodes) * obs_stride + (m % nodes) * 8 + 7], or NULL
+  long long obs_stride;
+  int nodes;
+  int relu;
+};
+
+struct GemmShape {
+  int M, N, K;
+  const int* m_dev;      // optional device-side row count (clamped to M)
+};
+
+size_t gemm_smem_bytes(int BN);
+// host: build the two TMA descriptors + launch.  A: [M, K] row stride lda; B: [N, K] row stride ldb.
+int gemm_bf16_launch(const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, int ldb, GemmShape shape,
+                     GemmEpilogue epi, int sm_count, cudaStream_t st);
+
+}  // namespace mls
