@@ -274,7 +274,7 @@ def run_ours(args):
         flops_round = algorithmic_flops(args.model, N, deg + N, A)
         # dominant kernel: projection GEMM launch that was bracketed with events (first chunk of every forward)
         HC, hid = 512, 128
-        chunk_rows = min(B, max(1, 8192 // N)) * N
+        chunk_rows = min(B, max(1, (8192 if args.precision == "fp32" else 148 * 128) // N)) * N
         K = HC if prof_name == "proj2" else hid
         kern_flops = 2.0 * chunk_rows * HC * K
         kern_ms = float(np.mean(prof_ms)) if prof_ms else None

@@ -433,6 +433,7 @@ void launch_tr_edge(cudaStream_t st, const float* P, int ldp, const float* obs, 
 
 extern "C" size_t mls_dgn_workspace_bytes(const MlsNetDesc* desc, int32_t n_graphs) {
   if (!desc || n_graphs <= 0 || desc->n_nodes <= 0) return 0;
+  if (desc->precision == MLS_PREC_BF16) return dgn_workspace_bytes_bf16(desc, n_graphs);
   return carve(desc, chunk_graphs(desc, n_graphs), nullptr, nullptr);
 }
 
@@ -448,11 +449,12 @@ extern "C" int mls_dgn_forward(const MlsNetDesc* d, const MlsNetWeights* w, cons
   MLS_CHECK_ARG(a->ctrl_mode == 1 || a->ctrl_mask, "ctrl_mask missing");
   MLS_CHECK_ARG(a->obs_stride >= (int64_t)d->n_nodes * 8 + (a->ctrl_mode == 1 ? 1 : 0),
                 "Expected %d feature cols for nodes, got %lld", d->n_nodes * 8, (long long)a->obs_stride - 1);
+  if (a->n_graphs == 0) return MLS_OK;
+  if (d->precision == MLS_PREC_BF16) return dgn_forward_bf16(d, w, a, stream);
   if (d->precision != MLS_PREC_FP32) {
-    mls_set_error("precision %d not available in this build", d->precision);
+    mls_set_error("unknown precision %d", d->precision);
     return MLS_ERR_UNSUPPORTED;
   }
-  if (a->n_graphs == 0) return MLS_OK;
   const int N = d->n_nodes, hid = d->hidden, H = d->heads, HC = hid * H, hh = d->head_hidden;
   const int Gc = chunk_graphs(d, a->n_graphs);
   MLS_CHECK_ARG(a->workspace && a->workspace_bytes >= carve(d, Gc, nullptr, nullptr), "workspace too small");

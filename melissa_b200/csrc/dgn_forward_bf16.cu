@@ -1,0 +1,607 @@
+// bf16 tensor-core forward of DGN-R / L-DGN / HL-DGN (sm_100a).
+//
+// Dense layers run on the tcgen05 GEMM (gemm_tcgen05.cu) with fused bias / ReLU /
+// decision-maker row mask; the attention convolutions run one CTA per graph with the
+// neighbour operand of one head staged in shared memory (every x_l / k / v row is read from
+// L2 once per head instead of once per edge); controlling-node snapshots and the HL-DGN
+// graph pooling are written by the same kernels, so the only activations that ever exist
+// in global memory are bf16 and live in an L2-sized, chunk-reused workspace.
+//
+// Accumulation is fp32 everywhere; activations and weights are rounded to bf16
+// (tolerance stated in tests/test_networks_gpu.py).  Reference math: see dgn_forward.cu.
+#include "dgn_kernels.cuh"
+#include "gemm_tcgen05.cuh"
+
+namespace mls {
+
+typedef __nv_bfloat16 bf16;
+
+__device__ __forceinline__ float4 ld_bf16x4(const bf16* p) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ void st_bf16x4(bf16* p, float4 v) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+  uint2 u;
+  u.x = *reinterpret_cast<uint32_t*>(&a);
+  u.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+
+// ------------------------------------------------------------------------------ weight preparation
+struct CvtJob {
+  const float* src;   // [rows, cols] fp32 row major
+  bf16* dst;          // destination matrix base
+  int rows, cols, ld_dst, row_off, col_off;
+};
+struct CvtJobs {
+  CvtJob j[8];
+  int n;
+};
+__global__ void cvt_weights_kernel(const CvtJobs jobs) {
+  const CvtJob jb = jobs.j[blockIdx.y];
+  const long long total = (long long)jb.rows * jb.cols;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(t / jb.cols), c = (int)(t - (long long)r * jb.cols);
+    jb.dst[(size_t)(r + jb.row_off) * jb.ld_dst + c + jb.col_off] = __float2bfloat16_rn(jb.src[t]);
+  }
+}
+struct CatJobs {
+  const float* src[8];
+  float* dst[8];
+  int n[8];
+  int count;
+};
+__global__ void cat_bias_kernel(const CatJobs jobs) {
+  const int k = blockIdx.y;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < jobs.n[k]; t += gridDim.x * blockDim.x) jobs.dst[k][t] = jobs.src[k][t];
+}
+
+// ------------------------------------------------------------------------------ encoder layer 0
+__global__ void enc0_bf16_kernel(const float* __restrict__ obs, int64_t obs_stride, int N, int rows, int in_dim,
+                                 const float* __restrict__ w0, const float* __restrict__ b0, int hidden, bf16* __restrict__ h) {
+  const int r = blockIdx.x * blockDim.y + threadIdx.y;
+  if (r >= rows) return;
+  const int g = r / N, i = r - g * N;
+  const float* f = obs + (int64_t)g * obs_stride + i * 8 + 2;
+  for (int c = threadIdx.x; c < hidden; c += blockDim.x) {
+    float acc = b0[c];
+    for (int k = 0; k < in_dim; ++k) acc = fmaf(w0[c * in_dim + k], f[k], acc);
+    h[(size_t)r * hidden + c] = __float2bfloat16_rn(fmaxf(acc, 0.0f));
+  }
+}
+
+// ------------------------------------------------------------------------------ neighbour masks from smem positions
+template <int W>
+__device__ __forceinline__ void radius_neighbours_xy(const float2* __restrict__ pos, int N, int i, int lane, uint32_t (&nb)[W]) {
+  const float2 pi = pos[i];
+  const float thr = r2_threshold();
+  int total = 0;
+#pragma unroll
+  for (int w = 0; w < W; ++w) {
+    const int j = w * 32 + lane;
+    bool hit = false;
+    if (j < N) {
+      const float dx = pos[j].x - pi.x, dy = pos[j].y - pi.y;
+      hit = __fmaf_rn(dy, dy, __fmul_rn(dx, dx)) < thr;
+    }
+    nb[w] = __ballot_sync(0xffffffffu, hit);
+    total += __popc(nb[w]);
+  }
+  if (total > kMaxNbr + 1) {
+    int keep = kMaxNbr + 1;
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+      const int c = __popc(nb[w]);
+      if (c <= keep) keep -= c;
+      else {
+        uint32_t m = nb[w], out = 0;
+        for (int t = 0; t < keep; ++t) { out |= m & (0u - m); m &= m - 1; }
+        nb[w] = out;
+        keep = 0;
+      }
+    }
+  }
+#pragma unroll
+  for (int w = 0; w < W; ++w) if (w == (i >> 5)) nb[w] &= ~(1u << (i & 31));
+}
+
+// ------------------------------------------------------------------------------ attention convolutions
+struct EdgeArgs {
+  const bf16* P;          // [rows, ldp] projections: GATv2 [x_l | x_r], Transformer [q | k | v]
+  int ldp;
+  const float* obs;       // chunk base
+  int64_t obs_stride;
+  int N, H, n_graphs;
+  const float* att;       // GATv2 [H*C]
+  const float* bias;      // GATv2 [H*C]
+  bf16* x_out;            // [rows, H*C] relu(conv) for every node, or NULL
+  const int* slot;        // [rows] index of the node in the controlling list, -1 if none; or NULL
+  bf16* z;                // snapshot destination rows [*, ldz], written at column z_col for slot >= 0; or NULL
+  int ldz, z_col;
+  int ctrl_only;          // compute only nodes with slot >= 0
+  int pool_mode;          // >= 0: HL-DGN pooling of relu(conv)*dm into z[g][H*C] (enum MlsPool); -1 none
+};
+
+constexpr int kEdgeThreads = 256, kEdgeWarps = 8;
+
+template <int W, bool TRANSFORMER>
+__global__ void __launch_bounds__(kEdgeThreads) edge_bf16_kernel(const EdgeArgs a) {
+  extern __shared__ __align__(16) unsigned char esm[];
+  const int N = a.N, H = a.H, HC = H * kC;
+  float2* pos = reinterpret_cast<float2*>(esm);                                  // [N]
+  bf16* stA = reinterpret_cast<bf16*>(esm + ((N * 8 + 15) & ~15));               // [N][kC]  x_l or k
+  bf16* stB = stA + (size_t)N * kC;                                              // [N][kC]  v (Transformer)
+  float* poolbuf = reinterpret_cast<float*>(stB + (TRANSFORMER ? (size_t)N * kC : 0));   // [warps][kC]
+  const int g = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* g_obs = a.obs + (int64_t)g * a.obs_stride;
+  const size_t base = (size_t)g * N;
+  for (int j = threadIdx.x; j < N; j += kEdgeThreads) pos[j] = make_float2(g_obs[j * 8 + 0], g_obs[j * 8 + 1]);
+  const float inv_sqrt_c = 1.0f / sqrtf((float)kC);
+
+  for (int h = 0; h < H; ++h) {
+    __syncthreads();                                   // previous head fully consumed (and pos visible)
+    // stage the neighbour-side operand of head h: N rows x 256 B
+    const int src_col = TRANSFORMER ? HC + h * kC : h * kC;
+    for (int t = threadIdx.x; t < N * (kC / 8); t += kEdgeThreads) {
+      const int j = t / (kC / 8), q = t - j * (kC / 8);
+      reinterpret_cast<uint4*>(stA)[t] = *reinterpret_cast<const uint4*>(a.P + (base + j) * a.ldp + src_col + q * 8);
+      if (TRANSFORMER)
+        reinterpret_cast<uint4*>(stB)[t] = *reinterpret_cast<const uint4*>(a.P + (base + j) * a.ldp + 2 * HC + h * kC + q * 8);
+    }
+    __syncthreads();
+    float4 att4 = make_float4(0.f, 0.f, 0.f, 0.f), bias4 = att4;
+    if (!TRANSFORMER) {
+      att4 = *reinterpret_cast<const float4*>(a.att + h * kC + lane * 4);
+      bias4 = *reinterpret_cast<const float4*>(a.bias + h * kC + lane * 4);
+    }
+    float4 pool = a.pool_mode == MLS_POOL_MAX ? make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY)
+                                              : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = warp; i < N; i += kEdgeWarps) {
+      int sl = -1;
+      if (a.slot) sl = a.slot[base + i];
+      if (a.ctrl_only && sl < 0) continue;
+      uint32_t nb[W];
+      radius_neighbours_xy<W>(pos, N, i, lane, nb);
+      if (!TRANSFORMER) {
+#pragma unroll
+        for (int w = 0; w < W; ++w) if (w == (i >> 5)) nb[w] |= 1u << (i & 31);          // add_self_loops
+      }
+      // target-side operand: x_r[i] (GATv2) / q[i] (Transformer)
+      const float4 ti = ld_bf16x4(a.P + (base + i) * a.ldp + (TRANSFORMER ? 0 : HC) + h * kC + lane * 4);
+      float e_loc[W];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int w = 0; w < W; ++w) {
+        e_loc[w] = -INFINITY;
+        uint32_t bits = nb[w];
+        while (bits) {
+          const int jl = __ffs(bits) - 1;
+          bits &= bits - 1;
+          const float4 xj = ld_bf16x4(stA + (size_t)(w * 32 + jl) * kC + lane * 4);
+          float part;
+          if (TRANSFORMER) {
+            part = ti.x * xj.x + ti.y * xj.y + ti.z * xj.z + ti.w * xj.w;
+          } else {
+            float s0 = xj.x + ti.x, s1 = xj.y + ti.y, s2 = xj.z + ti.z, s3 = xj.w + ti.w;
+            s0 = s0 > 0.f ? s0 : 0.2f * s0; s1 = s1 > 0.f ? s1 : 0.2f * s1;
+            s2 = s2 > 0.f ? s2 : 0.2f * s2; s3 = s3 > 0.f ? s3 : 0.2f * s3;
+            part = s0 * att4.x + s1 * att4.y + s2 * att4.z + s3 * att4.w;
+          }
+          float e = warp_sum(part);
+          if (TRANSFORMER) e *= inv_sqrt_c;
+          if (lane == jl) e_loc[w] = e;
+          mx = fmaxf(mx, e);
+        }
+      }
+      float den = 0.f;
+#pragma unroll
+      for (int w = 0; w < W; ++w) {
+        const float ex = (nb[w] >> lane) & 1u ? __expf(e_loc[w] - mx) : 0.f;
+        e_loc[w] = ex;
+        den += warp_sum(ex);
+      }
+      const float inv_den = 1.0f / (den + 1e-16f);
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int w = 0; w < W; ++w) {
+        uint32_t bits = nb[w];
+        while (bits) {
+          const int jl = __ffs(bits) - 1;
+          bits &= bits - 1;
+          const float al = __shfl_sync(0xffffffffu, e_loc[w], jl) * inv_den;
+          const float4 vj = ld_bf16x4((TRANSFORMER ? stB : stA) + (size_t)(w * 32 + jl) * kC + lane * 4);
+          acc.x = fmaf(al, vj.x, acc.x); acc.y = fmaf(al, vj.y, acc.y); acc.z = fmaf(al, vj.z, acc.z); acc.w = fmaf(al, vj.w, acc.w);
+        }
+      }
+      float4 o;
+      o.x = fmaxf(acc.x + bias4.x, 0.f); o.y = fmaxf(acc.y + bias4.y, 0.f);
+      o.z = fmaxf(acc.z + bias4.z, 0.f); o.w = fmaxf(acc.w + bias4.w, 0.f);
+      if (a.x_out) st_bf16x4(a.x_out + (base + i) * HC + h * kC + lane * 4, o);
+      if (a.z && sl >= 0 && a.pool_mode < 0) st_bf16x4(a.z + (size_t)sl * a.ldz + a.z_col + h * kC + lane * 4, o);
+      if (a.pool_mode >= 0) {
+        const float dm = g_obs[i * 8 + 7];
+        const float4 v = make_float4(o.x * dm, o.y * dm, o.z * dm, o.w * dm);
+        if (a.pool_mode == MLS_POOL_MAX) { pool.x = fmaxf(pool.x, v.x); pool.y = fmaxf(pool.y, v.y); pool.z = fmaxf(pool.z, v.z); pool.w = fmaxf(pool.w, v.w); }
+        else { pool.x += v.x; pool.y += v.y; pool.z += v.z; pool.w += v.w; }
+      }
+    }
+    if (a.pool_mode >= 0) {      // HL-DGN: z[g] = pool_i(relu(conv)[i] * dm[i])  (hl_dgn.py:103-108)
+      *reinterpret_cast<float4*>(poolbuf + warp * kC + lane * 4) = pool;
+      __syncthreads();
+      if (threadIdx.x < kC) {
+        const int used = N < kEdgeWarps ? N : kEdgeWarps;      // warps that own at least one node
+        float r = poolbuf[threadIdx.x];
+        for (int w2 = 1; w2 < used; ++w2) {
+          const float v = poolbuf[w2 * kC + threadIdx.x];
+          r = a.pool_mode == MLS_POOL_MAX ? fmaxf(r, v) : r + v;
+        }
+        if (a.pool_mode == MLS_POOL_MEAN) r = r / (float)N;
+        a.z[(size_t)g * a.ldz + a.z_col + h * kC + threadIdx.x] = __float2bfloat16_rn(r);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------ controlling nodes
+__global__ void ctrl_list_slot_kernel(const uint8_t* __restrict__ ctrl_mask, const float* __restrict__ obs, int64_t obs_stride,
+                                      int N, int n_graphs, int mode, int* __restrict__ idx, int* __restrict__ slot,
+                                      int* __restrict__ count) {
+  const int lane = threadIdx.x & 31;
+  const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (g >= n_graphs) return;
+  if (mode == 1) {
+    if (lane == 0) {
+      float c = obs[(int64_t)g * obs_stride + (int64_t)N * 8];
+      c = fminf(fmaxf(c, 0.f), (float)(N - 1));
+      const int r = g * N + (int)(long long)c;
+      idx[g] = r;
+      slot[r] = g;
+      if (g == 0) *count = n_graphs;
+    }
+    return;
+  }
+  for (int i0 = 0; i0 < N; i0 += 32) {
+    const int i = i0 + lane;
+    const bool c = i < N && ctrl_mask[(size_t)g * N + i] != 0;
+    const uint32_t bal = __ballot_sync(0xffffffffu, c);
+    const int n = __popc(bal);
+    int s = 0;
+    if (lane == 0 && n) s = atomicAdd(count, n);
+    s = __shfl_sync(0xffffffffu, s, 0);
+    if (c) {
+      const int t = s + __popc(bal & ((1u << lane) - 1));
+      idx[t] = g * N + i;
+      slot[g * N + i] = t;
+    }
+  }
+}
+
+// z[t][0:hidden] = x0[idx[t]]  (encoder snapshot, l_dgn.py:121-122)
+__global__ void gather_x0_kernel(const int* __restrict__ idx, const int* __restrict__ count, const bf16* __restrict__ x0,
+                                 int hidden, bf16* __restrict__ z, int ldz) {
+  const int t = blockIdx.x * blockDim.y + threadIdx.y;
+  if (t >= *count) return;
+  const int r = idx[t];
+  for (int c = threadIdx.x * 8; c < hidden; c += blockDim.x * 8)
+    *reinterpret_cast<uint4*>(z + (size_t)t * ldz + c) = *reinterpret_cast<const uint4*>(x0 + (size_t)r * hidden + c);
+}
+
+struct ActArgsB {
+  float eps;
+  uint64_t seed, offset;
+  const double* rand3;
+};
+__device__ __forceinline__ int select_action_b(float q0, float q1, const ActArgsB& a, uint64_t row) {
+  int act = q1 > q0 ? 1 : 0;
+  if (fabsf(a.eps) > 1e-8f) {
+    double ue, u0, u1;
+    if (a.rand3) { ue = a.rand3[row * 3 + 0]; u0 = a.rand3[row * 3 + 1]; u1 = a.rand3[row * 3 + 2]; }
+    else {
+      Philox4 r = philox4x32_10(a.seed, row, a.offset);
+      ue = u01_from_u32x2(r.v[0], r.v[1]);
+      u0 = (double)r.v[2] * (1.0 / 4294967296.0);
+      u1 = (double)r.v[3] * (1.0 / 4294967296.0);
+    }
+    if (ue < (double)a.eps) act = (u1 + 1.0) > (u0 + 1.0) ? 1 : 0;
+  }
+  return act;
+}
+
+// last head layer + dueling + action; hid row = [Q hidden (hh) | V hidden (hh)] in bf16
+__global__ void head_out_bf16_kernel(const bf16* __restrict__ hid, int hh, const int* __restrict__ idx, const int* __restrict__ count,
+                                     int max_rows, const float* __restrict__ wq, const float* __restrict__ bq,
+                                     const float* __restrict__ wv, const float* __restrict__ bv, int64_t row0, int per_graph_N,
+                                     float* __restrict__ q_out, int8_t* __restrict__ act_out, int out_mode, ActArgsB aa) {
+  const int lane = threadIdx.x & 31;
+  const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int n = count ? min(*count, max_rows) : max_rows;
+  if (t >= n) return;
+  const bf16* hq = hid + (size_t)t * 2 * hh;
+  const bf16* hv = hq + hh;
+  float s0 = 0.f, s1 = 0.f, sv = 0.f;
+  for (int c = lane; c < hh; c += 32) {
+    const float q = __bfloat162float(hq[c]), v = __bfloat162float(hv[c]);
+    s0 = fmaf(q, wq[c], s0);
+    s1 = fmaf(q, wq[hh + c], s1);
+    sv = fmaf(v, wv[c], sv);
+  }
+  s0 = warp_sum(s0) + bq[0]; s1 = warp_sum(s1) + bq[1]; sv = warp_sum(sv) + bv[0];
+  if (lane == 0) {
+    const float mean = (s0 + s1) / 2.0f;
+    const float o0 = (s0 - mean) + sv, o1 = (s1 - mean) + sv;
+    int64_t orow;
+    if (out_mode == 0) orow = row0 + idx[t];
+    else if (out_mode == 1) orow = row0 / per_graph_N + idx[t] / per_graph_N;
+    else orow = t;
+    q_out[orow * 2 + 0] = o0;
+    q_out[orow * 2 + 1] = o1;
+    if (act_out && out_mode != 2) act_out[orow] = (int8_t)select_action_b(o0, o1, aa, (uint64_t)orow);
+  }
+}
+
+__global__ void hl_scatter_b_kernel(const float* __restrict__ qg, const uint8_t* __restrict__ ctrl_mask, int N, int n_graphs,
+                                    int64_t graph0, int mode, float* __restrict__ q_out, int8_t* __restrict__ act_out, ActArgsB aa) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (mode == 1) {
+    if (t >= n_graphs) return;
+    const float o0 = qg[t * 2], o1 = qg[t * 2 + 1];
+    const int64_t orow = graph0 + t;
+    q_out[orow * 2] = o0; q_out[orow * 2 + 1] = o1;
+    if (act_out) act_out[orow] = (int8_t)select_action_b(o0, o1, aa, (uint64_t)orow);
+    return;
+  }
+  if (t >= (int64_t)n_graphs * N) return;
+  if (!ctrl_mask[t]) return;
+  const int64_t g = t / N, orow = graph0 * N + t;
+  const float o0 = qg[g * 2], o1 = qg[g * 2 + 1];
+  q_out[orow * 2] = o0; q_out[orow * 2 + 1] = o1;
+  if (act_out) act_out[orow] = (int8_t)select_action_b(o0, o1, aa, (uint64_t)orow);
+}
+
+}  // namespace mls
+
+// ================================================================================== host
+namespace {
+using namespace mls;
+
+size_t al(size_t v, size_t a = 1024) { return (v + a - 1) / a * a; }
+
+struct WsB {
+  bf16 *w_enc1, *w_c1, *w_c2, *w_h0, *w_h1;
+  float *b_c1, *b_c2, *b_h0, *b_h1;
+  bf16 *h, *x0, *P, *x1, *z, *hid1, *hid2;
+  float* qg;
+  int *idx, *slot, *count;
+};
+
+size_t carve_b(const MlsNetDesc* d, int Gc, unsigned char* base, WsB* ws) {
+  const size_t R = al((size_t)Gc * d->n_nodes, 128);
+  const int hid = d->hidden, HC = d->hidden * d->heads, hh2 = 2 * d->head_hidden;
+  const bool hl = d->kind == MLS_NET_HL_DGN;
+  const int nproj = d->kind == MLS_NET_DGN_R ? 3 : 2;
+  const int latent = hl ? HC : hid + 2 * HC;
+  const size_t T = hl ? al((size_t)Gc, 128) : R;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = al(off + bytes); return o; };
+  const size_t o_we = take((size_t)hid * hid * 2), o_wc1 = take((size_t)nproj * HC * hid * 2);
+  const size_t o_wc2 = take(hl ? 0 : (size_t)nproj * HC * HC * 2), o_wh0 = take((size_t)hh2 * latent * 2);
+  const size_t o_wh1 = take((size_t)hh2 * hh2 * 2);
+  const size_t o_bc1 = take((size_t)nproj * HC * 4), o_bc2 = take((size_t)nproj * HC * 4), o_bh0 = take(hh2 * 4), o_bh1 = take(hh2 * 4);
+  const size_t o_h = take(R * hid * 2), o_x0 = take(R * hid * 2), o_P = take(R * nproj * HC * 2);
+  const size_t o_x1 = take(hl ? 0 : R * HC * 2), o_z = take(T * latent * 2), o_h1 = take(T * hh2 * 2), o_h2 = take(T * hh2 * 2);
+  const size_t o_qg = take((size_t)Gc * 8), o_idx = take(R * 4), o_slot = take(R * 4), o_cnt = take(4);
+  if (ws) {
+    auto B = [&](size_t o) { return reinterpret_cast<bf16*>(base + o); };
+    auto F = [&](size_t o) { return reinterpret_cast<float*>(base + o); };
+    ws->w_enc1 = B(o_we); ws->w_c1 = B(o_wc1); ws->w_c2 = B(o_wc2); ws->w_h0 = B(o_wh0); ws->w_h1 = B(o_wh1);
+    ws->b_c1 = F(o_bc1); ws->b_c2 = F(o_bc2); ws->b_h0 = F(o_bh0); ws->b_h1 = F(o_bh1);
+    ws->h = B(o_h); ws->x0 = B(o_x0); ws->P = B(o_P); ws->x1 = B(o_x1); ws->z = B(o_z); ws->hid1 = B(o_h1); ws->hid2 = B(o_h2);
+    ws->qg = F(o_qg);
+    ws->idx = reinterpret_cast<int*>(base + o_idx); ws->slot = reinterpret_cast<int*>(base + o_slot);
+    ws->count = reinterpret_cast<int*>(base + o_cnt);
+  }
+  return off;
+}
+
+template <int W, bool TR>
+int launch_edge(cudaStream_t st, const EdgeArgs& ea) {
+  const size_t smem = ((ea.N * 8 + 15) & ~15) + (size_t)ea.N * kC * 2 * (TR ? 2 : 1) + kEdgeWarps * kC * 4;
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    MLS_CUDA(cudaFuncSetAttribute(edge_bf16_kernel<W, TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  edge_bf16_kernel<W, TR><<<ea.n_graphs, kEdgeThreads, smem, st>>>(ea);
+  mls_count_launch();
+  MLS_LAUNCH_CHECK();
+  return MLS_OK;
+}
+
+int edge_dispatch(cudaStream_t st, const EdgeArgs& ea, bool tr, int Wn) {
+  if (tr) {
+    switch (Wn) {
+      case 1: return launch_edge<1, true>(st, ea);
+      case 2: return launch_edge<2, true>(st, ea);
+      case 4: return launch_edge<4, true>(st, ea);
+      default: return launch_edge<8, true>(st, ea);
+    }
+  }
+  switch (Wn) {
+    case 1: return launch_edge<1, false>(st, ea);
+    case 2: return launch_edge<2, false>(st, ea);
+    case 4: return launch_edge<4, false>(st, ea);
+    default: return launch_edge<8, false>(st, ea);
+  }
+}
+
+}  // namespace
+
+int bf16_chunk_graphs(const MlsNetDesc* d, int n_graphs) {
+  int gc = (148 * 128) / d->n_nodes;      // one full wave of 128-row GEMM tiles per N tile
+  if (gc < 1) gc = 1;
+  return n_graphs < gc ? n_graphs : gc;
+}
+
+size_t dgn_workspace_bytes_bf16(const MlsNetDesc* d, int n_graphs) {
+  return carve_b(d, bf16_chunk_graphs(d, n_graphs), nullptr, nullptr);
+}
+
+int dgn_forward_bf16(const MlsNetDesc* d, const MlsNetWeights* w, const MlsForwardArgs* a, void* stream) {
+  const int N = d->n_nodes, hid = d->hidden, H = d->heads, HC = hid * H, hh = d->head_hidden, hh2 = 2 * hh;
+  MLS_CHECK_ARG(hid % 64 == 0 && hh % 64 == 0, "bf16 path needs hidden sizes that are multiples of 64");
+  const int Gc = bf16_chunk_graphs(d, a->n_graphs);
+  MLS_CHECK_ARG(a->workspace && a->workspace_bytes >= carve_b(d, Gc, nullptr, nullptr), "workspace too small");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int dev = 0, sms = 0;
+  MLS_CUDA(cudaGetDevice(&dev));
+  MLS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  WsB ws;
+  carve_b(d, Gc, (unsigned char*)a->workspace, &ws);
+  const int Wn = mls_words_per_row(N);
+  const bool hl = d->kind == MLS_NET_HL_DGN, tr = d->kind == MLS_NET_DGN_R;
+  const int nproj = tr ? 3 : 2;
+  const int latent = hl ? HC : hid + 2 * HC;
+  ActArgsB aa{a->eps, a->philox_seed, a->philox_offset, a->rand3};
+  if (a->ctrl_mode == 0) {
+    MLS_CUDA(cudaMemsetAsync(a->q, 0, (size_t)a->n_graphs * N * 2 * sizeof(float), st));
+    if (a->act) MLS_CUDA(cudaMemsetAsync(a->act, 0xFF, (size_t)a->n_graphs * N, st));
+  }
+  // ---- weights -> bf16 (stacked the way the GEMMs consume them); biases stay fp32
+  {
+    CvtJobs cj{};
+    int n = 0;
+    auto add = [&](const float* src, bf16* dst, int rows, int cols, int ld, int ro, int co) { cj.j[n++] = CvtJob{src, dst, rows, cols, ld, ro, co}; };
+    add(w->enc_w1, ws.w_enc1, hid, hid, hid, 0, 0);
+    add(w->c1_wa, ws.w_c1, HC, hid, hid, 0, 0);
+    add(w->c1_wb, ws.w_c1, HC, hid, hid, HC, 0);
+    if (tr) add(w->c1_wc, ws.w_c1, HC, hid, hid, 2 * HC, 0);
+    cj.n = n;
+    cvt_weights_kernel<<<dim3(64, n), 256, 0, st>>>(cj);
+    CvtJobs c2{};
+    n = 0;
+    auto add2 = [&](const float* src, bf16* dst, int rows, int cols, int ld, int ro, int co) { c2.j[n++] = CvtJob{src, dst, rows, cols, ld, ro, co}; };
+    if (!hl) {
+      add2(w->c2_wa, ws.w_c2, HC, HC, HC, 0, 0);
+      add2(w->c2_wb, ws.w_c2, HC, HC, HC, HC, 0);
+      if (tr) add2(w->c2_wc, ws.w_c2, HC, HC, HC, 2 * HC, 0);
+    }
+    MLS_CUDA(cudaMemsetAsync(ws.w_h1, 0, (size_t)hh2 * hh2 * 2, st));
+    add2(w->q_w0, ws.w_h0, hh, latent, latent, 0, 0);
+    add2(w->v_w0, ws.w_h0, hh, latent, latent, hh, 0);
+    add2(w->q_w1, ws.w_h1, hh, hh, hh2, 0, 0);         // block diagonal: Q and V hidden layers in one GEMM
+    add2(w->v_w1, ws.w_h1, hh, hh, hh2, hh, hh);
+    c2.n = n;
+    cvt_weights_kernel<<<dim3(128, n), 256, 0, st>>>(c2);
+    CatJobs bj{};
+    int m = 0;
+    auto addb = [&](const float* src, float* dst, int cnt) { bj.src[m] = src; bj.dst[m] = dst; bj.n[m] = cnt; ++m; };
+    if (tr) { addb(w->c1_ba, ws.b_c1, HC); addb(w->c1_bb, ws.b_c1 + HC, HC); addb(w->c1_bc, ws.b_c1 + 2 * HC, HC); }
+    else { addb(w->c1_ba, ws.b_c1, HC); addb(w->c1_bb, ws.b_c1 + HC, HC); }
+    addb(w->q_b0, ws.b_h0, hh); addb(w->v_b0, ws.b_h0 + hh, hh);
+    addb(w->q_b1, ws.b_h1, hh); addb(w->v_b1, ws.b_h1 + hh, hh);
+    bj.count = m;
+    cat_bias_kernel<<<dim3(2, m), 256, 0, st>>>(bj);
+    if (!hl) {
+      CatJobs b2{};
+      m = 0;
+      auto addc = [&](const float* src, float* dst, int cnt) { b2.src[m] = src; b2.dst[m] = dst; b2.n[m] = cnt; ++m; };
+      addc(w->c2_ba, ws.b_c2, HC); addc(w->c2_bb, ws.b_c2 + HC, HC);
+      if (tr) addc(w->c2_bc, ws.b_c2 + 2 * HC, HC);
+      b2.count = m;
+      cat_bias_kernel<<<dim3(2, m), 256, 0, st>>>(b2);
+      mls_count_launch();
+    }
+    mls_count_launch(3);
+    MLS_LAUNCH_CHECK();
+  }
+  cudaEvent_t ev0 = reinterpret_cast<cudaEvent_t>(a->prof_start), ev1 = reinterpret_cast<cudaEvent_t>(a->prof_stop);
+  bool first_chunk = true;
+  auto prof_begin = [&](int which) { if (first_chunk && ev0 && ev1 && a->prof_kernel == which) cudaEventRecord(ev0, st); };
+  auto prof_end = [&](int which) { if (first_chunk && ev0 && ev1 && a->prof_kernel == which) cudaEventRecord(ev1, st); };
+  int rc;
+  for (int g0 = 0; g0 < a->n_graphs; g0 += Gc) {
+    const int gc = (a->n_graphs - g0) < Gc ? (a->n_graphs - g0) : Gc;
+    const int rows = gc * N;
+    const float* obs = a->obs + (int64_t)g0 * a->obs_stride;
+    const uint8_t* cm = a->ctrl_mode == 0 ? a->ctrl_mask + (size_t)g0 * N : nullptr;
+    // controlling-node list first: the conv kernels scatter their snapshots through `slot`
+    if (!hl) {
+      MLS_CUDA(cudaMemsetAsync(ws.count, 0, sizeof(int), st));
+      MLS_CUDA(cudaMemsetAsync(ws.slot, 0xFF, (size_t)rows * sizeof(int), st));
+      ctrl_list_slot_kernel<<<(gc * 32 + 255) / 256, 256, 0, st>>>(cm, obs, a->obs_stride, N, gc, a->ctrl_mode, ws.idx, ws.slot, ws.count);
+      mls_count_launch();
+    }
+    // encoder
+    {
+      dim3 blk(32, 8);
+      enc0_bf16_kernel<<<(rows + 7) / 8, blk, 0, st>>>(obs, a->obs_stride, N, rows, d->input_dim, w->enc_w0, w->enc_b0, hid, ws.h);
+      mls_count_launch();
+      GemmEpilogue e{ws.x0, hid, w->enc_b1, nullptr, 0, N, 1};
+      if ((rc = gemm_bf16_launch(ws.h, hid, ws.w_enc1, hid, GemmShape{rows, hid, hid, nullptr}, e, sms, st))) return rc;
+    }
+    // conv1 projections
+    {
+      GemmEpilogue e{ws.P, nproj * HC, ws.b_c1, nullptr, 0, N, 0};
+      prof_begin(MLS_PROF_PROJ1);
+      if ((rc = gemm_bf16_launch(ws.x0, hid, ws.w_c1, hid, GemmShape{rows, nproj * HC, hid, nullptr}, e, sms, st))) return rc;
+      prof_end(MLS_PROF_PROJ1);
+    }
+    // conv1 attention (+ReLU); snapshot x1[ctrl] (pre-mask) or HL-DGN pooling
+    {
+      EdgeArgs ea{};
+      ea.P = ws.P; ea.ldp = nproj * HC; ea.obs = obs; ea.obs_stride = a->obs_stride; ea.N = N; ea.H = H; ea.n_graphs = gc;
+      ea.att = w->c1_att; ea.bias = w->c1_bias;
+      if (hl) { ea.x_out = nullptr; ea.slot = nullptr; ea.z = ws.z; ea.ldz = latent; ea.z_col = 0; ea.ctrl_only = 0; ea.pool_mode = d->pool; }
+      else { ea.x_out = ws.x1; ea.slot = ws.slot; ea.z = ws.z; ea.ldz = latent; ea.z_col = hid; ea.ctrl_only = 0; ea.pool_mode = -1; }
+      prof_begin(MLS_PROF_EDGE1);
+      if ((rc = edge_dispatch(st, ea, tr, Wn))) return rc;
+      prof_end(MLS_PROF_EDGE1);
+    }
+    if (!hl) {
+      // conv2 projections on x1 * dm: the row mask commutes with the GEMM, applied in its epilogue
+      GemmEpilogue e{ws.P, nproj * HC, ws.b_c2, obs, a->obs_stride, N, 0};
+      prof_begin(MLS_PROF_PROJ2);
+      if ((rc = gemm_bf16_launch(ws.x1, HC, ws.w_c2, HC, GemmShape{rows, nproj * HC, HC, nullptr}, e, sms, st))) return rc;
+      prof_end(MLS_PROF_PROJ2);
+      // conv2 attention only where a controlling agent needs it; result goes straight into z
+      EdgeArgs ea{};
+      ea.P = ws.P; ea.ldp = nproj * HC; ea.obs = obs; ea.obs_stride = a->obs_stride; ea.N = N; ea.H = H; ea.n_graphs = gc;
+      ea.att = w->c2_att; ea.bias = w->c2_bias; ea.x_out = nullptr; ea.slot = ws.slot; ea.z = ws.z; ea.ldz = latent;
+      ea.z_col = hid + HC; ea.ctrl_only = 1; ea.pool_mode = -1;
+      prof_begin(MLS_PROF_EDGE2);
+      if ((rc = edge_dispatch(st, ea, tr, Wn))) return rc;
+      prof_end(MLS_PROF_EDGE2);
+      dim3 blk(16, 16);
+      gather_x0_kernel<<<(rows + 15) / 16, blk, 0, st>>>(ws.idx, ws.count, ws.x0, hid, ws.z, latent);
+      mls_count_launch();
+    }
+    // dueling head on the tensor cores: [Q0;V0] stacked, then block-diagonal [Q1 0; 0 V1]
+    const int head_rows = hl ? gc : rows;
+    const int* m_dev = hl ? nullptr : ws.count;
+    {
+      GemmEpilogue e0{ws.hid1, hh2, ws.b_h0, nullptr, 0, N, 1};
+      prof_begin(MLS_PROF_HEAD0);
+      if ((rc = gemm_bf16_launch(ws.z, latent, ws.w_h0, latent, GemmShape{head_rows, hh2, latent, m_dev}, e0, sms, st))) return rc;
+      prof_end(MLS_PROF_HEAD0);
+      GemmEpilogue e1{ws.hid2, hh2, ws.b_h1, nullptr, 0, N, 1};
+      if ((rc = gemm_bf16_launch(ws.hid1, hh2, ws.w_h1, hh2, GemmShape{head_rows, hh2, hh2, m_dev}, e1, sms, st))) return rc;
+    }
+    if (!hl) {
+      head_out_bf16_kernel<<<(rows * 32 + 255) / 256, 256, 0, st>>>(ws.hid2, hh, ws.idx, ws.count, rows, w->q_w2, w->q_b2, w->v_w2,
+                                                                     w->v_b2, (int64_t)g0 * N, N, a->q, a->act, a->ctrl_mode, aa);
+      mls_count_launch();
+    } else {
+      head_out_bf16_kernel<<<(gc * 32 + 255) / 256, 256, 0, st>>>(ws.hid2, hh, nullptr, nullptr, gc, w->q_w2, w->q_b2, w->v_w2,
+                                                                   w->v_b2, 0, N, ws.qg, nullptr, 2, aa);
+      const long long nthr = a->ctrl_mode == 1 ? gc : (long long)gc * N;
+      hl_scatter_b_kernel<<<(unsigned)((nthr + 255) / 256), 256, 0, st>>>(ws.qg, cm, N, gc, g0, a->ctrl_mode, a->q, a->act, aa);
+      mls_count_launch(2);
+    }
+    MLS_LAUNCH_CHECK();
+    first_chunk = false;
+  }
+  return MLS_OK;
+}

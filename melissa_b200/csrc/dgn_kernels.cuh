@@ -10,6 +10,10 @@
 
 #include "common.cuh"
 
+// bf16 tensor-core path (dgn_forward_bf16.cu)
+size_t dgn_workspace_bytes_bf16(const MlsNetDesc* d, int n_graphs);
+int dgn_forward_bf16(const MlsNetDesc* d, const MlsNetWeights* w, const MlsForwardArgs* a, void* stream);
+
 namespace mls {
 
 constexpr int kC = 128;                 // channels per head the edge kernels are written for
