@@ -276,12 +276,14 @@ def run_ours(args):
         HC, hid = 512, 128
         chunk_rows = min(B, max(1, (8192 if args.precision == "fp32" else 148 * 128) // N)) * N
         K = HC if prof_name == "proj2" else hid
-        kern_flops = 2.0 * chunk_rows * HC * K
+        nproj = 3 if args.model == "dgn_r" else 2
+        n_out = HC if args.precision == "fp32" else nproj * HC     # bf16: all projections of a conv in one GEMM
+        kern_flops = 2.0 * chunk_rows * n_out * K
         kern_ms = float(np.mean(prof_ms)) if prof_ms else None
         roofline = None
         if kern_ms:
             ach = kern_flops / (kern_ms * 1e-3) / 1e12
-            roofline = {"kernel": f"{args.precision} projection GEMM ({prof_name}, [{chunk_rows}x{K}]x[{K}x{HC}])",
+            roofline = {"kernel": f"{args.precision} projection GEMM ({prof_name}, [{chunk_rows}x{K}]x[{K}x{n_out}])",
                         "bound": "tensor", "achieved": round(ach, 3), "peak": tensor_peak, "unit": "TFLOP/s",
                         "frac": round(ach / tensor_peak, 5), "traffic": None, "peak_source": f"{peak_src} (sustained bf16)",
                         "kernel_ms": round(kern_ms, 5), "launch_flops": kern_flops}

@@ -73,39 +73,22 @@ __global__ void enc0_bf16_kernel(const float* __restrict__ obs, int64_t obs_stri
   }
 }
 
-// ------------------------------------------------------------------------------ neighbour masks from smem positions
+// ------------------------------------------------------------------------------ neighbour masks
+// radius_graph(pos, r=0.2, loop=False, max_num_neighbors=32) once per chunk: nbr[row][W] (bit j = edge j -> row)
 template <int W>
-__device__ __forceinline__ void radius_neighbours_xy(const float2* __restrict__ pos, int N, int i, int lane, uint32_t (&nb)[W]) {
-  const float2 pi = pos[i];
-  const float thr = r2_threshold();
-  int total = 0;
+__global__ void nbr_mask_kernel(const float* __restrict__ obs, int64_t obs_stride, int N, int rows, uint32_t* __restrict__ nbr) {
+  const int lane = threadIdx.x & 31;
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (r >= rows) return;
+  const int g = r / N, i = r - g * N;
+  uint32_t nb[W];
+  radius_neighbours<W>(obs + (int64_t)g * obs_stride, N, i, lane, nb);
+  if (lane < W) {
+    uint32_t v = 0;
 #pragma unroll
-  for (int w = 0; w < W; ++w) {
-    const int j = w * 32 + lane;
-    bool hit = false;
-    if (j < N) {
-      const float dx = pos[j].x - pi.x, dy = pos[j].y - pi.y;
-      hit = __fmaf_rn(dy, dy, __fmul_rn(dx, dx)) < thr;
-    }
-    nb[w] = __ballot_sync(0xffffffffu, hit);
-    total += __popc(nb[w]);
+    for (int w = 0; w < W; ++w) if (w == lane) v = nb[w];
+    nbr[(size_t)r * W + lane] = v;
   }
-  if (total > kMaxNbr + 1) {
-    int keep = kMaxNbr + 1;
-#pragma unroll
-    for (int w = 0; w < W; ++w) {
-      const int c = __popc(nb[w]);
-      if (c <= keep) keep -= c;
-      else {
-        uint32_t m = nb[w], out = 0;
-        for (int t = 0; t < keep; ++t) { out |= m & (0u - m); m &= m - 1; }
-        nb[w] = out;
-        keep = 0;
-      }
-    }
-  }
-#pragma unroll
-  for (int w = 0; w < W; ++w) if (w == (i >> 5)) nb[w] &= ~(1u << (i & 31));
 }
 
 // ------------------------------------------------------------------------------ attention convolutions
@@ -115,6 +98,7 @@ struct EdgeArgs {
   const float* obs;       // chunk base
   int64_t obs_stride;
   int N, H, n_graphs;
+  const uint32_t* nbr;    // [rows][W] neighbour masks
   const float* att;       // GATv2 [H*C]
   const float* bias;      // GATv2 [H*C]
   bf16* x_out;            // [rows, H*C] relu(conv) for every node, or NULL
@@ -125,25 +109,43 @@ struct EdgeArgs {
   int pool_mode;          // >= 0: HL-DGN pooling of relu(conv)*dm into z[g][H*C] (enum MlsPool); -1 none
 };
 
-constexpr int kEdgeThreads = 256, kEdgeWarps = 8;
+constexpr int kEdgeThreads = 128, kEdgeWarps = 4;
 
+// sum four per-lane values over the warp with 6 shuffles (pairs are folded while halving), then
+// broadcast: returns the four totals to every lane
+__device__ __forceinline__ void warp_sum4(float& p0, float& p1, float& p2, float& p3, int lane) {
+  const bool h16 = lane & 16, h8 = lane & 8;
+  float a = h16 ? p1 : p0, sa = h16 ? p0 : p1;
+  a += __shfl_xor_sync(0xffffffffu, sa, 16);
+  float b = h16 ? p3 : p2, sb = h16 ? p2 : p3;
+  b += __shfl_xor_sync(0xffffffffu, sb, 16);
+  float c = h8 ? b : a, sc = h8 ? a : b;
+  c += __shfl_xor_sync(0xffffffffu, sc, 8);
+  c += __shfl_xor_sync(0xffffffffu, c, 4);
+  c += __shfl_xor_sync(0xffffffffu, c, 2);
+  c += __shfl_xor_sync(0xffffffffu, c, 1);
+  p0 = __shfl_sync(0xffffffffu, c, 0);      // value index = 2*bit3 + bit4 of the holding lane
+  p1 = __shfl_sync(0xffffffffu, c, 16);
+  p2 = __shfl_sync(0xffffffffu, c, 8);
+  p3 = __shfl_sync(0xffffffffu, c, 24);
+}
+
+// One CTA per (graph, head): the neighbour-side operand of that head is staged in shared
+// memory once; each warp walks targets, neighbours in batches of four, single-pass softmax
+// (running max / denominator, identical to exp(e - max) / (sum + 1e-16) up to rounding).
 template <int W, bool TRANSFORMER>
 __global__ void __launch_bounds__(kEdgeThreads) edge_bf16_kernel(const EdgeArgs a) {
   extern __shared__ __align__(16) unsigned char esm[];
   const int N = a.N, H = a.H, HC = H * kC;
-  float2* pos = reinterpret_cast<float2*>(esm);                                  // [N]
-  bf16* stA = reinterpret_cast<bf16*>(esm + ((N * 8 + 15) & ~15));               // [N][kC]  x_l or k
+  bf16* stA = reinterpret_cast<bf16*>(esm);                                      // [N][kC]  x_l or k
   bf16* stB = stA + (size_t)N * kC;                                              // [N][kC]  v (Transformer)
   float* poolbuf = reinterpret_cast<float*>(stB + (TRANSFORMER ? (size_t)N * kC : 0));   // [warps][kC]
-  const int g = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = blockIdx.x / H, h = blockIdx.x - g * H;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float* g_obs = a.obs + (int64_t)g * a.obs_stride;
   const size_t base = (size_t)g * N;
-  for (int j = threadIdx.x; j < N; j += kEdgeThreads) pos[j] = make_float2(g_obs[j * 8 + 0], g_obs[j * 8 + 1]);
   const float inv_sqrt_c = 1.0f / sqrtf((float)kC);
-
-  for (int h = 0; h < H; ++h) {
-    __syncthreads();                                   // previous head fully consumed (and pos visible)
-    // stage the neighbour-side operand of head h: N rows x 256 B
+  {
     const int src_col = TRANSFORMER ? HC + h * kC : h * kC;
     for (int t = threadIdx.x; t < N * (kC / 8); t += kEdgeThreads) {
       const int j = t / (kC / 8), q = t - j * (kC / 8);
@@ -151,96 +153,111 @@ __global__ void __launch_bounds__(kEdgeThreads) edge_bf16_kernel(const EdgeArgs 
       if (TRANSFORMER)
         reinterpret_cast<uint4*>(stB)[t] = *reinterpret_cast<const uint4*>(a.P + (base + j) * a.ldp + 2 * HC + h * kC + q * 8);
     }
-    __syncthreads();
-    float4 att4 = make_float4(0.f, 0.f, 0.f, 0.f), bias4 = att4;
+  }
+  __syncthreads();
+  float4 att4 = make_float4(0.f, 0.f, 0.f, 0.f), bias4 = att4;
+  if (!TRANSFORMER) {
+    att4 = *reinterpret_cast<const float4*>(a.att + h * kC + lane * 4);
+    bias4 = *reinterpret_cast<const float4*>(a.bias + h * kC + lane * 4);
+  }
+  float4 pool = a.pool_mode == MLS_POOL_MAX ? make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY)
+                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = warp; i < N; i += kEdgeWarps) {
+    int sl = -1;
+    if (a.slot) sl = a.slot[base + i];
+    if (a.ctrl_only && sl < 0) continue;
+    uint32_t nb[W];
+#pragma unroll
+    for (int w = 0; w < W; ++w) nb[w] = a.nbr[(base + i) * W + w];
     if (!TRANSFORMER) {
-      att4 = *reinterpret_cast<const float4*>(a.att + h * kC + lane * 4);
-      bias4 = *reinterpret_cast<const float4*>(a.bias + h * kC + lane * 4);
+#pragma unroll
+      for (int w = 0; w < W; ++w) if (w == (i >> 5)) nb[w] |= 1u << (i & 31);          // add_self_loops
     }
-    float4 pool = a.pool_mode == MLS_POOL_MAX ? make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY)
-                                              : make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int i = warp; i < N; i += kEdgeWarps) {
-      int sl = -1;
-      if (a.slot) sl = a.slot[base + i];
-      if (a.ctrl_only && sl < 0) continue;
-      uint32_t nb[W];
-      radius_neighbours_xy<W>(pos, N, i, lane, nb);
-      if (!TRANSFORMER) {
+    // target-side operand: x_r[i] (GATv2) / q[i] (Transformer)
+    const float4 ti = ld_bf16x4(a.P + (base + i) * a.ldp + (TRANSFORMER ? 0 : HC) + h * kC + lane * 4);
+    float mx = -INFINITY, den = 0.f;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int wcur = 0;
+    uint32_t bits = nb[0];
+    auto next = [&](int& j) -> bool {       // warp-uniform walk over the set bits of nb[0..W)
+      while (bits == 0) {
+        if (++wcur >= W) return false;
 #pragma unroll
-        for (int w = 0; w < W; ++w) if (w == (i >> 5)) nb[w] |= 1u << (i & 31);          // add_self_loops
+        for (int w = 1; w < W; ++w) if (w == wcur) bits = nb[w];
       }
-      // target-side operand: x_r[i] (GATv2) / q[i] (Transformer)
-      const float4 ti = ld_bf16x4(a.P + (base + i) * a.ldp + (TRANSFORMER ? 0 : HC) + h * kC + lane * 4);
-      float e_loc[W];
-      float mx = -INFINITY;
+      j = wcur * 32 + __ffs(bits) - 1;
+      bits &= bits - 1;
+      return true;
+    };
+    for (;;) {
+      int j[4];
+      bool ok[4];
 #pragma unroll
-      for (int w = 0; w < W; ++w) {
-        e_loc[w] = -INFINITY;
-        uint32_t bits = nb[w];
-        while (bits) {
-          const int jl = __ffs(bits) - 1;
-          bits &= bits - 1;
-          const float4 xj = ld_bf16x4(stA + (size_t)(w * 32 + jl) * kC + lane * 4);
-          float part;
-          if (TRANSFORMER) {
-            part = ti.x * xj.x + ti.y * xj.y + ti.z * xj.z + ti.w * xj.w;
-          } else {
-            float s0 = xj.x + ti.x, s1 = xj.y + ti.y, s2 = xj.z + ti.z, s3 = xj.w + ti.w;
-            s0 = s0 > 0.f ? s0 : 0.2f * s0; s1 = s1 > 0.f ? s1 : 0.2f * s1;
-            s2 = s2 > 0.f ? s2 : 0.2f * s2; s3 = s3 > 0.f ? s3 : 0.2f * s3;
-            part = s0 * att4.x + s1 * att4.y + s2 * att4.z + s3 * att4.w;
-          }
-          float e = warp_sum(part);
-          if (TRANSFORMER) e *= inv_sqrt_c;
-          if (lane == jl) e_loc[w] = e;
-          mx = fmaxf(mx, e);
+      for (int u = 0; u < 4; ++u) { j[u] = i; ok[u] = (wcur < W) && next(j[u]); }
+      if (!ok[0]) break;
+      float4 xj[4];
+      float e[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        xj[u] = ld_bf16x4(stA + (size_t)j[u] * kC + lane * 4);
+        if (TRANSFORMER) {
+          e[u] = ti.x * xj[u].x + ti.y * xj[u].y + ti.z * xj[u].z + ti.w * xj[u].w;
+        } else {
+          float s0 = xj[u].x + ti.x, s1 = xj[u].y + ti.y, s2 = xj[u].z + ti.z, s3 = xj[u].w + ti.w;
+          s0 = fmaxf(s0, 0.2f * s0); s1 = fmaxf(s1, 0.2f * s1); s2 = fmaxf(s2, 0.2f * s2); s3 = fmaxf(s3, 0.2f * s3);
+          e[u] = s0 * att4.x + s1 * att4.y + s2 * att4.z + s3 * att4.w;
         }
       }
-      float den = 0.f;
+      warp_sum4(e[0], e[1], e[2], e[3], lane);
+      float m_new = mx;
 #pragma unroll
-      for (int w = 0; w < W; ++w) {
-        const float ex = (nb[w] >> lane) & 1u ? __expf(e_loc[w] - mx) : 0.f;
-        e_loc[w] = ex;
-        den += warp_sum(ex);
+      for (int u = 0; u < 4; ++u) {
+        if (TRANSFORMER) e[u] *= inv_sqrt_c;
+        if (!ok[u]) e[u] = -INFINITY;
+        m_new = fmaxf(m_new, e[u]);
       }
-      const float inv_den = 1.0f / (den + 1e-16f);
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float resc = __expf(mx - m_new);        // first batch: exp(-inf) = 0
+      den *= resc;
+      acc.x *= resc; acc.y *= resc; acc.z *= resc; acc.w *= resc;
+      if (TRANSFORMER) {
 #pragma unroll
-      for (int w = 0; w < W; ++w) {
-        uint32_t bits = nb[w];
-        while (bits) {
-          const int jl = __ffs(bits) - 1;
-          bits &= bits - 1;
-          const float al = __shfl_sync(0xffffffffu, e_loc[w], jl) * inv_den;
-          const float4 vj = ld_bf16x4((TRANSFORMER ? stB : stA) + (size_t)(w * 32 + jl) * kC + lane * 4);
-          acc.x = fmaf(al, vj.x, acc.x); acc.y = fmaf(al, vj.y, acc.y); acc.z = fmaf(al, vj.z, acc.z); acc.w = fmaf(al, vj.w, acc.w);
-        }
+        for (int u = 0; u < 4; ++u) xj[u] = ld_bf16x4(stB + (size_t)j[u] * kC + lane * 4);
       }
-      float4 o;
-      o.x = fmaxf(acc.x + bias4.x, 0.f); o.y = fmaxf(acc.y + bias4.y, 0.f);
-      o.z = fmaxf(acc.z + bias4.z, 0.f); o.w = fmaxf(acc.w + bias4.w, 0.f);
-      if (a.x_out) st_bf16x4(a.x_out + (base + i) * HC + h * kC + lane * 4, o);
-      if (a.z && sl >= 0 && a.pool_mode < 0) st_bf16x4(a.z + (size_t)sl * a.ldz + a.z_col + h * kC + lane * 4, o);
-      if (a.pool_mode >= 0) {
-        const float dm = g_obs[i * 8 + 7];
-        const float4 v = make_float4(o.x * dm, o.y * dm, o.z * dm, o.w * dm);
-        if (a.pool_mode == MLS_POOL_MAX) { pool.x = fmaxf(pool.x, v.x); pool.y = fmaxf(pool.y, v.y); pool.z = fmaxf(pool.z, v.z); pool.w = fmaxf(pool.w, v.w); }
-        else { pool.x += v.x; pool.y += v.y; pool.z += v.z; pool.w += v.w; }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float p = __expf(e[u] - m_new);       // 0 for padded entries
+        den += p;
+        acc.x = fmaf(p, xj[u].x, acc.x); acc.y = fmaf(p, xj[u].y, acc.y);
+        acc.z = fmaf(p, xj[u].z, acc.z); acc.w = fmaf(p, xj[u].w, acc.w);
       }
+      mx = m_new;
+      if (!ok[3]) break;
     }
-    if (a.pool_mode >= 0) {      // HL-DGN: z[g] = pool_i(relu(conv)[i] * dm[i])  (hl_dgn.py:103-108)
-      *reinterpret_cast<float4*>(poolbuf + warp * kC + lane * 4) = pool;
-      __syncthreads();
-      if (threadIdx.x < kC) {
-        const int used = N < kEdgeWarps ? N : kEdgeWarps;      // warps that own at least one node
-        float r = poolbuf[threadIdx.x];
-        for (int w2 = 1; w2 < used; ++w2) {
-          const float v = poolbuf[w2 * kC + threadIdx.x];
-          r = a.pool_mode == MLS_POOL_MAX ? fmaxf(r, v) : r + v;
-        }
-        if (a.pool_mode == MLS_POOL_MEAN) r = r / (float)N;
-        a.z[(size_t)g * a.ldz + a.z_col + h * kC + threadIdx.x] = __float2bfloat16_rn(r);
+    const float inv_den = 1.0f / (den + 1e-16f);    // isolated Transformer node: acc = 0 -> output 0
+    float4 o;
+    o.x = fmaxf(fmaf(acc.x, inv_den, bias4.x), 0.f); o.y = fmaxf(fmaf(acc.y, inv_den, bias4.y), 0.f);
+    o.z = fmaxf(fmaf(acc.z, inv_den, bias4.z), 0.f); o.w = fmaxf(fmaf(acc.w, inv_den, bias4.w), 0.f);
+    if (a.x_out) st_bf16x4(a.x_out + (base + i) * HC + h * kC + lane * 4, o);
+    if (a.z && sl >= 0 && a.pool_mode < 0) st_bf16x4(a.z + (size_t)sl * a.ldz + a.z_col + h * kC + lane * 4, o);
+    if (a.pool_mode >= 0) {
+      const float dm = g_obs[i * 8 + 7];
+      const float4 v = make_float4(o.x * dm, o.y * dm, o.z * dm, o.w * dm);
+      if (a.pool_mode == MLS_POOL_MAX) { pool.x = fmaxf(pool.x, v.x); pool.y = fmaxf(pool.y, v.y); pool.z = fmaxf(pool.z, v.z); pool.w = fmaxf(pool.w, v.w); }
+      else { pool.x += v.x; pool.y += v.y; pool.z += v.z; pool.w += v.w; }
+    }
+  }
+  if (a.pool_mode >= 0) {      // HL-DGN: z[g] = pool_i(relu(conv)[i] * dm[i])  (hl_dgn.py:103-108)
+    *reinterpret_cast<float4*>(poolbuf + warp * kC + lane * 4) = pool;
+    __syncthreads();
+    if (threadIdx.x < kC) {
+      const int used = N < kEdgeWarps ? N : kEdgeWarps;        // warps that own at least one node
+      float r = poolbuf[threadIdx.x];
+      for (int w2 = 1; w2 < used; ++w2) {
+        const float v = poolbuf[w2 * kC + threadIdx.x];
+        r = a.pool_mode == MLS_POOL_MAX ? fmaxf(r, v) : r + v;
       }
+      if (a.pool_mode == MLS_POOL_MEAN) r = r / (float)N;
+      a.z[(size_t)g * a.ldz + a.z_col + h * kC + threadIdx.x] = __float2bfloat16_rn(r);
     }
   }
 }
@@ -375,6 +392,7 @@ struct WsB {
   bf16 *h, *x0, *P, *x1, *z, *hid1, *hid2;
   float* qg;
   int *idx, *slot, *count;
+  uint32_t* nbr;
 };
 
 size_t carve_b(const MlsNetDesc* d, int Gc, unsigned char* base, WsB* ws) {
@@ -393,6 +411,7 @@ size_t carve_b(const MlsNetDesc* d, int Gc, unsigned char* base, WsB* ws) {
   const size_t o_h = take(R * hid * 2), o_x0 = take(R * hid * 2), o_P = take(R * nproj * HC * 2);
   const size_t o_x1 = take(hl ? 0 : R * HC * 2), o_z = take(T * latent * 2), o_h1 = take(T * hh2 * 2), o_h2 = take(T * hh2 * 2);
   const size_t o_qg = take((size_t)Gc * 8), o_idx = take(R * 4), o_slot = take(R * 4), o_cnt = take(4);
+  const size_t o_nbr = take(R * 8 * 4);
   if (ws) {
     auto B = [&](size_t o) { return reinterpret_cast<bf16*>(base + o); };
     auto F = [&](size_t o) { return reinterpret_cast<float*>(base + o); };
@@ -402,19 +421,20 @@ size_t carve_b(const MlsNetDesc* d, int Gc, unsigned char* base, WsB* ws) {
     ws->qg = F(o_qg);
     ws->idx = reinterpret_cast<int*>(base + o_idx); ws->slot = reinterpret_cast<int*>(base + o_slot);
     ws->count = reinterpret_cast<int*>(base + o_cnt);
+    ws->nbr = reinterpret_cast<uint32_t*>(base + o_nbr);
   }
   return off;
 }
 
 template <int W, bool TR>
 int launch_edge(cudaStream_t st, const EdgeArgs& ea) {
-  const size_t smem = ((ea.N * 8 + 15) & ~15) + (size_t)ea.N * kC * 2 * (TR ? 2 : 1) + kEdgeWarps * kC * 4;
+  const size_t smem = (size_t)ea.N * kC * 2 * (TR ? 2 : 1) + kEdgeWarps * kC * 4;
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
     MLS_CUDA(cudaFuncSetAttribute(edge_bf16_kernel<W, TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  edge_bf16_kernel<W, TR><<<ea.n_graphs, kEdgeThreads, smem, st>>>(ea);
+  edge_bf16_kernel<W, TR><<<ea.n_graphs * ea.H, kEdgeThreads, smem, st>>>(ea);
   mls_count_launch();
   MLS_LAUNCH_CHECK();
   return MLS_OK;
@@ -534,6 +554,13 @@ int dgn_forward_bf16(const MlsNetDesc* d, const MlsNetWeights* w, const MlsForwa
       ctrl_list_slot_kernel<<<(gc * 32 + 255) / 256, 256, 0, st>>>(cm, obs, a->obs_stride, N, gc, a->ctrl_mode, ws.idx, ws.slot, ws.count);
       mls_count_launch();
     }
+    switch (Wn) {
+      case 1: nbr_mask_kernel<1><<<(rows * 32 + 255) / 256, 256, 0, st>>>(obs, a->obs_stride, N, rows, ws.nbr); break;
+      case 2: nbr_mask_kernel<2><<<(rows * 32 + 255) / 256, 256, 0, st>>>(obs, a->obs_stride, N, rows, ws.nbr); break;
+      case 4: nbr_mask_kernel<4><<<(rows * 32 + 255) / 256, 256, 0, st>>>(obs, a->obs_stride, N, rows, ws.nbr); break;
+      default: nbr_mask_kernel<8><<<(rows * 32 + 255) / 256, 256, 0, st>>>(obs, a->obs_stride, N, rows, ws.nbr); break;
+    }
+    mls_count_launch();
     // encoder
     {
       dim3 blk(32, 8);
@@ -553,7 +580,7 @@ int dgn_forward_bf16(const MlsNetDesc* d, const MlsNetWeights* w, const MlsForwa
     {
       EdgeArgs ea{};
       ea.P = ws.P; ea.ldp = nproj * HC; ea.obs = obs; ea.obs_stride = a->obs_stride; ea.N = N; ea.H = H; ea.n_graphs = gc;
-      ea.att = w->c1_att; ea.bias = w->c1_bias;
+      ea.att = w->c1_att; ea.bias = w->c1_bias; ea.nbr = ws.nbr;
       if (hl) { ea.x_out = nullptr; ea.slot = nullptr; ea.z = ws.z; ea.ldz = latent; ea.z_col = 0; ea.ctrl_only = 0; ea.pool_mode = d->pool; }
       else { ea.x_out = ws.x1; ea.slot = ws.slot; ea.z = ws.z; ea.ldz = latent; ea.z_col = hid; ea.ctrl_only = 0; ea.pool_mode = -1; }
       prof_begin(MLS_PROF_EDGE1);
@@ -569,7 +596,7 @@ int dgn_forward_bf16(const MlsNetDesc* d, const MlsNetWeights* w, const MlsForwa
       // conv2 attention only where a controlling agent needs it; result goes straight into z
       EdgeArgs ea{};
       ea.P = ws.P; ea.ldp = nproj * HC; ea.obs = obs; ea.obs_stride = a->obs_stride; ea.N = N; ea.H = H; ea.n_graphs = gc;
-      ea.att = w->c2_att; ea.bias = w->c2_bias; ea.x_out = nullptr; ea.slot = ws.slot; ea.z = ws.z; ea.ldz = latent;
+      ea.att = w->c2_att; ea.bias = w->c2_bias; ea.nbr = ws.nbr; ea.x_out = nullptr; ea.slot = ws.slot; ea.z = ws.z; ea.ldz = latent;
       ea.z_col = hid + HC; ea.ctrl_only = 1; ea.pool_mode = -1;
       prof_begin(MLS_PROF_EDGE2);
       if ((rc = edge_dispatch(st, ea, tr, Wn))) return rc;
