@@ -89,10 +89,16 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
 
 template <int BN>
 struct GemmSmem {
+  static constexpr int kNumStages = BN == 256 ? 3 : 4;
   static constexpr int kABytes = kBM * kBK * 2;      // 16 KiB
   static constexpr int kBBytes = BN * kBK * 2;       // 16 / 32 KiB
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kBarOffset = kStages * kStageBytes;
+  // epilogue staging: per warp 32 rows of BN bf16 (+16 B pad: conflict-free 16 B stores by row-owning lanes)
+  static constexpr int kOutRowBytes = BN * 2 + 16;
+  static constexpr int kOutWarpBytes = 32 * kOutRowBytes;
+  static constexpr int kOutOffset = kNumStages * kStageBytes;
+  static constexpr int kBiasOffset = kOutOffset + 4 * kOutWarpBytes;      // BN floats
+  static constexpr int kBarOffset = kBiasOffset + BN * 4;
   static constexpr int kTotal = kBarOffset + 256 + 1024;   // barriers + alignment slack
 };
 
@@ -106,6 +112,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kBarOffset);
   // bars[0..S) full, [S..2S) empty, [2S..2S+2) tmem_full, [2S+2..2S+4) tmem_empty
+  constexpr int kStages = S::kNumStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
   const uint32_t bar0 = smem_u32(bars);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
@@ -180,8 +187,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       }
     }
   } else if (warp >= 4) {
-    // ===================================================================== epilogue (TMEM -> regs -> global)
+    // ===================================================================== epilogue
+    // TMEM -> registers (lane = row) -> scale/bias/ReLU -> bf16 -> per-warp smem tile -> coalesced row stores
     const int ew = warp - 4;                                // == warp % 4: the TMEM lane quarter this warp may read
+    unsigned char* stage_out = smem + S::kOutOffset + ew * S::kOutWarpBytes;
+    float* bias_s = reinterpret_cast<float*>(smem + S::kBiasOffset);
+    const int et = threadIdx.x - 128;                       // 0..127 within the epilogue warps
     int it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -193,29 +204,47 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         const int g = r / epi.nodes, i = r - g * epi.nodes;
         scale = epi.obs[(long long)g * epi.obs_stride + i * 8 + 7];
       }
+      // bias slice of this tile -> smem (all four epilogue warps; named barrier 1 keeps the other warps out of it)
+      asm volatile("bar.sync 1, 128;" ::: "memory");        // previous tile's readers are done with bias_s
+      for (int c = et; c < BN; c += 128) bias_s[c] = epi.bias ? __ldg(epi.bias + n0 + c) : 0.0f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN + c0), v);
-        if (r < M) {
-          uint32_t packed[16];
+        uint32_t packed[16];
 #pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            float x0 = __uint_as_float(v[j]) * scale, x1 = __uint_as_float(v[j + 1]) * scale;
-            if (epi.bias) { x0 += __ldg(epi.bias + n0 + c0 + j); x1 += __ldg(epi.bias + n0 + c0 + j + 1); }
-            if (epi.relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
-            __nv_bfloat162 b2 = __floats2bfloat162_rn(x0, x1);
-            packed[j >> 1] = *reinterpret_cast<uint32_t*>(&b2);
-          }
-          uint4* dst = reinterpret_cast<uint4*>(epi.C + (size_t)r * epi.ldc + n0 + c0);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) dst[q] = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+        for (int j = 0; j < 32; j += 4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c0 + j);
+          float x0 = fmaf(__uint_as_float(v[j]), scale, b4.x), x1 = fmaf(__uint_as_float(v[j + 1]), scale, b4.y);
+          float x2 = fmaf(__uint_as_float(v[j + 2]), scale, b4.z), x3 = fmaf(__uint_as_float(v[j + 3]), scale, b4.w);
+          if (epi.relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f); }
+          __nv_bfloat162 p0 = __floats2bfloat162_rn(x0, x1), p1 = __floats2bfloat162_rn(x2, x3);
+          packed[j >> 1] = *reinterpret_cast<uint32_t*>(&p0);
+          packed[(j >> 1) + 1] = *reinterpret_cast<uint32_t*>(&p1);
         }
+        uint4* dst = reinterpret_cast<uint4*>(stage_out + lane * S::kOutRowBytes + c0 * 2);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) dst[q] = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
       }
+      // accumulator drained: hand it back to the MMA warp before the global stores
       tc_fence_before();
       mbar_arrive(tempty_bar(acc));
+      __syncwarp();
+      // each instruction now writes one full row segment of BN bf16 (BN*2 bytes contiguous)
+      constexpr int kLanesPerRow = BN * 2 / 16;             // 16 (BN=128) or 32 (BN=256) lanes cover one row
+      constexpr int kRowsPerIter = 32 / kLanesPerRow;
+      const int sub = lane / kLanesPerRow, cl = lane % kLanesPerRow;
+#pragma unroll 4
+      for (int rr = 0; rr < 32; rr += kRowsPerIter) {
+        const int row = rr + sub;
+        const int gr = m0 + ew * 32 + row;
+        const uint4 val = *reinterpret_cast<const uint4*>(stage_out + row * S::kOutRowBytes + cl * 16);
+        if (gr < M) *reinterpret_cast<uint4*>(epi.C + (size_t)gr * epi.ldc + n0 + cl * 8) = val;
+      }
+      __syncwarp();
     }
   }
   tc_fence_before();

@@ -1,6 +1,6 @@
 // Persistent warp-specialised bf16 GEMM on the 5th-gen tensor cores (sm_100a):
 //     C[M, N] (bf16) = act( rowscale[m] * (A[M, K] @ B[N, K]^T) + bias[n] )
-// A and B are K-major bf16 in global memory, moved by TMA (128B swizzle) into a 4-stage
+// A and B are K-major bf16 in global memory, moved by TMA (128B swizzle) into a 3/4-stage
 // shared-memory ring; one thread issues tcgen05.mma (M=128, N=BN, K=16) into a double
 // buffered fp32 accumulator in TMEM; four epilogue warps drain TMEM with tcgen05.ld, apply
 // the fused epilogue and store bf16 rows.  One CTA per SM, static round-robin tile order
@@ -13,7 +13,7 @@
 
 namespace mls {
 
-constexpr int kBM = 128, kBK = 64, kUmmaK = 16, kStages = 4;
+constexpr int kBM = 128, kBK = 64, kUmmaK = 16;
 constexpr int kGemmThreads = 256;
 
 struct GemmEpilogue {
