@@ -42,7 +42,8 @@ def parse_args():
     ap.add_argument("--episodes", type=int, default=32768, help="episodes per GPU")
     ap.add_argument("--graphs", type=int, default=1024)
     ap.add_argument("--eps", type=float, default=0.05)
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--precision", default="bf16", choices=["fp32", "bf16"])
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     ap.add_argument("--preroll", type=int, default=32, help="untimed rounds so episodes are spread over their lifetime")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -185,8 +186,9 @@ def run_ours(args):
                                    device=str(dev), **kw).to(dev)
         net.set_precision(args.precision)
     ro = Rollout(env, net, eps=args.eps, seed=9 + rank)
-    ro.start(ResetTuplesDevice(gi, src, inter, scr, N, dev))
+    tuples_dev = ResetTuplesDevice(gi, src, inter, scr, N, dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    use_graph = not args.no_graph
 
     def sync_all():
         torch.cuda.synchronize()
@@ -194,20 +196,26 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    if net is None:
-        ro.act.copy_(torch.randint(0, 2, ro.act.shape, device=dev, dtype=torch.int8))
-    for _ in range(args.preroll):
-        ro.round()
-    for _ in range(args.warmup):
-        ro.round()
-    sync_all()
+    def prepare(graph):
+        """Identical starting point for every measured phase: same tuples, same Philox stream,
+        `preroll` untimed rounds so the episodes are spread over their lifetime, then W warm-up rounds."""
+        ro.graph = None
+        ro.start(tuples_dev)
+        if net is None:
+            ro.act.copy_(torch.randint(0, 2, ro.act.shape, device=dev, dtype=torch.int8))
+        n_pre = args.preroll - (2 if graph else 0)
+        for _ in range(max(0, n_pre)):
+            ro.round()
+        if graph:
+            ro.capture(warmup_rounds=2)
+        for _ in range(args.warmup):
+            ro.round()
+        sync_all()
 
     prof_name = args.prof_kernel or ("proj2" if args.model in ("l_dgn", "dgn_r") else "proj1")
     pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    if net is not None:
-        net.set_profile_events(prof_name, pe0, pe1)
 
-    def timed(fn, steps):
+    def timed(fn, steps, with_prof=False):
         """K steps, L2 flushed between steps (outside the per-step event pairs)."""
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         t_before = ro.transitions()
@@ -219,19 +227,31 @@ def run_ours(args):
             evs[s][0].record()
             extra.append(fn())
             evs[s][1].record()
-            if net is not None:
+            if with_prof:
                 evs[s][1].synchronize()
                 prof_ms.append(pe0.elapsed_time(pe1))
         sync_all()
         ms = sum(a.elapsed_time(b) for a, b in evs)
         return ms, ro.transitions() - t_before, _lib.lib().mls_launch_count() - l_before, prof_ms, extra
 
+    # ---- phase 1: the product path (CUDA-graph replay of the whole round unless --no-graph)
+    prepare(use_graph)
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
-    ms, trans, launches, prof_ms, _ = timed(ro.round, args.steps)
+    ms, trans, launches, _, _ = timed(ro.round, args.steps)
     clk = clocks.stop() if rank == 0 else None
-
+    launches_per_step = None
+    # ---- phase 2: same rounds launched eagerly with an event pair around the dominant kernel
+    prof_ms, eager_ms = [], None
+    if net is not None:
+        prepare(False)
+        net.set_profile_events(prof_name, pe0, pe1)
+        eager_ms, _, launches_eager, prof_ms, _ = timed(ro.round, args.steps, with_prof=True)
+        net.set_profile_events(None)
+        launches_per_step = launches_eager / args.steps
+        if use_graph:
+            launches = launches_eager          # a graph replay launches the same kernels; they are counted at capture
     # env kernel alone (HBM roofline of the environment round)
     env_evs = []
     for s in range(min(args.steps, 10)):
@@ -244,10 +264,12 @@ def run_ours(args):
 
     e2e = None
     if not args.no_e2e:
-        if net is not None:
-            net.set_profile_events(None)
-        for _ in range(2):
-            ro.round_host()
+        prepare(False)
+        ro.round_host()          # allocates the pinned mirrors
+        prepare(False)
+        ro._host["obs"].copy_(env.obs)
+        ro._host["active"].copy_(env.active)
+        torch.cuda.synchronize()
         e_ms, e_trans, _, _, ex = timed(ro.round_host, args.steps)
         e2e = (e_ms, e_trans, ex[0])
 
@@ -301,6 +323,9 @@ def run_ours(args):
                             f"{B} episodes per GPU (BASELINE config 3 per-GPU shard)",
                 "episodes_per_gpu": B, "n_nodes": N, "graph_pool": len(pool), "eps": args.eps, "precision": args.precision,
                 "preroll_rounds": args.preroll, "l2": "flushed between timed steps (256 MiB memset outside the timed events)",
+                "launch_mode": "cuda-graph replay of the whole round" if use_graph else "eager",
+                "eager_ms_per_step": (eager_ms / steps) if eager_ms else None,
+                "kernel_timing": "event pair around one launch per step in an eager pass over the same rounds",
                 "active_agents_per_graph_round": round(A, 3), "graph_rounds_per_s": world * B * steps / (ms_max / 1e3),
                 "model_tflops_algorithmic": round(flops_round * B * steps / (ms / 1e3) / 1e12, 3),
             },

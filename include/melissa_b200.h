@@ -215,6 +215,9 @@ typedef struct MlsForwardArgs {
   void* prof_stop;
   int32_t prof_kernel;
   int32_t pad2_;
+  /* optional device-side uint64 added to philox_offset (a round counter the caller bumps on
+   * the stream; lets a captured CUDA graph draw fresh exploration noise on every replay) */
+  const void* philox_offset_dev;
 } MlsForwardArgs;
 
 enum MlsProfKernel {

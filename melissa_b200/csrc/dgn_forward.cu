@@ -289,6 +289,7 @@ struct ActArgs {
   float eps;
   uint64_t seed, offset;
   const double* rand3;
+  const unsigned long long* offset_dev;   // optional device-side addend (round counter under CUDA-graph replay)
 };
 
 __device__ __forceinline__ int select_action(float q0, float q1, const ActArgs& a, uint64_t row) {
@@ -299,7 +300,7 @@ __device__ __forceinline__ int select_action(float q0, float q1, const ActArgs& 
     double ue, u0, u1;
     if (a.rand3) { ue = a.rand3[row * 3 + 0]; u0 = a.rand3[row * 3 + 1]; u1 = a.rand3[row * 3 + 2]; }
     else {
-      Philox4 r = philox4x32_10(a.seed, row, a.offset);
+      Philox4 r = philox4x32_10(a.seed, row, a.offset + (a.offset_dev ? *a.offset_dev : 0ull));
       ue = u01_from_u32x2(r.v[0], r.v[1]);
       u0 = (double)r.v[2] * (1.0 / 4294967296.0);
       u1 = (double)r.v[3] * (1.0 / 4294967296.0);
@@ -465,7 +466,7 @@ extern "C" int mls_dgn_forward(const MlsNetDesc* d, const MlsNetWeights* w, cons
   const bool hl = d->kind == MLS_NET_HL_DGN, tr = d->kind == MLS_NET_DGN_R;
   const int nproj = tr ? 3 : 2;
   const int latent = hl ? HC : hid + 2 * HC;
-  ActArgs aa{a->eps, a->philox_seed, a->philox_offset, a->rand3};
+  ActArgs aa{a->eps, a->philox_seed, a->philox_offset, a->rand3, reinterpret_cast<const unsigned long long*>(a->philox_offset_dev)};
   if (a->ctrl_mode == 0) {
     MLS_CUDA(cudaMemsetAsync(a->q, 0, (size_t)a->n_graphs * N * 2 * sizeof(float), st));
     if (a->act) MLS_CUDA(cudaMemsetAsync(a->act, 0xFF, (size_t)a->n_graphs * N, st));

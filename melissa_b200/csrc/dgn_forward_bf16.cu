@@ -109,7 +109,7 @@ struct EdgeArgs {
   int pool_mode;          // >= 0: HL-DGN pooling of relu(conv)*dm into z[g][H*C] (enum MlsPool); -1 none
 };
 
-constexpr int kEdgeThreads = 128, kEdgeWarps = 4;
+constexpr int kEdgeThreads = 256, kEdgeWarps = 8;
 
 // sum four per-lane values over the warp with 6 shuffles (pairs are folded while halving), then
 // broadcast: returns the four totals to every lane
@@ -137,9 +137,13 @@ template <int W, bool TRANSFORMER>
 __global__ void __launch_bounds__(kEdgeThreads) edge_bf16_kernel(const EdgeArgs a) {
   extern __shared__ __align__(16) unsigned char esm[];
   const int N = a.N, H = a.H, HC = H * kC;
-  bf16* stA = reinterpret_cast<bf16*>(esm);                                      // [N][kC]  x_l or k
-  bf16* stB = stA + (size_t)N * kC;                                              // [N][kC]  v (Transformer)
+  bf16* stA = reinterpret_cast<bf16*>(esm);                                      // [N][kC]  x_l or k   (neighbour side)
+  bf16* stT = stA + (size_t)N * kC;                                              // [N][kC]  x_r or q   (target side)
+  bf16* stB = stT + (size_t)N * kC;                                              // [N][kC]  v (Transformer)
   float* poolbuf = reinterpret_cast<float*>(stB + (TRANSFORMER ? (size_t)N * kC : 0));   // [warps][kC]
+  uint32_t* s_nbr = reinterpret_cast<uint32_t*>(poolbuf + kEdgeWarps * kC);      // [N][W]
+  int* s_slot = reinterpret_cast<int*>(s_nbr + (size_t)N * W);                   // [N]
+  float* s_dm = reinterpret_cast<float*>(s_slot + N);                            // [N]
   const int g = blockIdx.x / H, h = blockIdx.x - g * H;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float* g_obs = a.obs + (int64_t)g * a.obs_stride;
@@ -147,11 +151,18 @@ __global__ void __launch_bounds__(kEdgeThreads) edge_bf16_kernel(const EdgeArgs 
   const float inv_sqrt_c = 1.0f / sqrtf((float)kC);
   {
     const int src_col = TRANSFORMER ? HC + h * kC : h * kC;
+    const int tgt_col = (TRANSFORMER ? 0 : HC) + h * kC;
     for (int t = threadIdx.x; t < N * (kC / 8); t += kEdgeThreads) {
       const int j = t / (kC / 8), q = t - j * (kC / 8);
-      reinterpret_cast<uint4*>(stA)[t] = *reinterpret_cast<const uint4*>(a.P + (base + j) * a.ldp + src_col + q * 8);
-      if (TRANSFORMER)
-        reinterpret_cast<uint4*>(stB)[t] = *reinterpret_cast<const uint4*>(a.P + (base + j) * a.ldp + 2 * HC + h * kC + q * 8);
+      const bf16* row = a.P + (base + j) * a.ldp;
+      reinterpret_cast<uint4*>(stA)[t] = *reinterpret_cast<const uint4*>(row + src_col + q * 8);
+      reinterpret_cast<uint4*>(stT)[t] = *reinterpret_cast<const uint4*>(row + tgt_col + q * 8);
+      if (TRANSFORMER) reinterpret_cast<uint4*>(stB)[t] = *reinterpret_cast<const uint4*>(row + 2 * HC + h * kC + q * 8);
+    }
+    for (int t = threadIdx.x; t < N * W; t += kEdgeThreads) s_nbr[t] = a.nbr[base * W + t];
+    for (int t = threadIdx.x; t < N; t += kEdgeThreads) {
+      s_slot[t] = a.slot ? a.slot[base + t] : -1;
+      s_dm[t] = g_obs[t * 8 + 7];
     }
   }
   __syncthreads();
@@ -163,18 +174,17 @@ __global__ void __launch_bounds__(kEdgeThreads) edge_bf16_kernel(const EdgeArgs 
   float4 pool = a.pool_mode == MLS_POOL_MAX ? make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY)
                                             : make_float4(0.f, 0.f, 0.f, 0.f);
   for (int i = warp; i < N; i += kEdgeWarps) {
-    int sl = -1;
-    if (a.slot) sl = a.slot[base + i];
+    const int sl = s_slot[i];
     if (a.ctrl_only && sl < 0) continue;
     uint32_t nb[W];
 #pragma unroll
-    for (int w = 0; w < W; ++w) nb[w] = a.nbr[(base + i) * W + w];
+    for (int w = 0; w < W; ++w) nb[w] = s_nbr[i * W + w];
     if (!TRANSFORMER) {
 #pragma unroll
       for (int w = 0; w < W; ++w) if (w == (i >> 5)) nb[w] |= 1u << (i & 31);          // add_self_loops
     }
     // target-side operand: x_r[i] (GATv2) / q[i] (Transformer)
-    const float4 ti = ld_bf16x4(a.P + (base + i) * a.ldp + (TRANSFORMER ? 0 : HC) + h * kC + lane * 4);
+    const float4 ti = ld_bf16x4(stT + (size_t)i * kC + lane * 4);
     float mx = -INFINITY, den = 0.f;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     int wcur = 0;
@@ -240,7 +250,7 @@ __global__ void __launch_bounds__(kEdgeThreads) edge_bf16_kernel(const EdgeArgs 
     if (a.x_out) st_bf16x4(a.x_out + (base + i) * HC + h * kC + lane * 4, o);
     if (a.z && sl >= 0 && a.pool_mode < 0) st_bf16x4(a.z + (size_t)sl * a.ldz + a.z_col + h * kC + lane * 4, o);
     if (a.pool_mode >= 0) {
-      const float dm = g_obs[i * 8 + 7];
+      const float dm = s_dm[i];
       const float4 v = make_float4(o.x * dm, o.y * dm, o.z * dm, o.w * dm);
       if (a.pool_mode == MLS_POOL_MAX) { pool.x = fmaxf(pool.x, v.x); pool.y = fmaxf(pool.y, v.y); pool.z = fmaxf(pool.z, v.z); pool.w = fmaxf(pool.w, v.w); }
       else { pool.x += v.x; pool.y += v.y; pool.z += v.z; pool.w += v.w; }
@@ -310,6 +320,7 @@ struct ActArgsB {
   float eps;
   uint64_t seed, offset;
   const double* rand3;
+  const unsigned long long* offset_dev;   // optional device-side addend (round counter under CUDA-graph replay)
 };
 __device__ __forceinline__ int select_action_b(float q0, float q1, const ActArgsB& a, uint64_t row) {
   int act = q1 > q0 ? 1 : 0;
@@ -317,7 +328,7 @@ __device__ __forceinline__ int select_action_b(float q0, float q1, const ActArgs
     double ue, u0, u1;
     if (a.rand3) { ue = a.rand3[row * 3 + 0]; u0 = a.rand3[row * 3 + 1]; u1 = a.rand3[row * 3 + 2]; }
     else {
-      Philox4 r = philox4x32_10(a.seed, row, a.offset);
+      Philox4 r = philox4x32_10(a.seed, row, a.offset + (a.offset_dev ? *a.offset_dev : 0ull));
       ue = u01_from_u32x2(r.v[0], r.v[1]);
       u0 = (double)r.v[2] * (1.0 / 4294967296.0);
       u1 = (double)r.v[3] * (1.0 / 4294967296.0);
@@ -428,7 +439,7 @@ size_t carve_b(const MlsNetDesc* d, int Gc, unsigned char* base, WsB* ws) {
 
 template <int W, bool TR>
 int launch_edge(cudaStream_t st, const EdgeArgs& ea) {
-  const size_t smem = (size_t)ea.N * kC * 2 * (TR ? 2 : 1) + kEdgeWarps * kC * 4;
+  const size_t smem = (size_t)ea.N * kC * 2 * (TR ? 3 : 2) + kEdgeWarps * kC * 4 + (size_t)ea.N * (W + 2) * 4;
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
     MLS_CUDA(cudaFuncSetAttribute(edge_bf16_kernel<W, TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -484,7 +495,7 @@ int dgn_forward_bf16(const MlsNetDesc* d, const MlsNetWeights* w, const MlsForwa
   const bool hl = d->kind == MLS_NET_HL_DGN, tr = d->kind == MLS_NET_DGN_R;
   const int nproj = tr ? 3 : 2;
   const int latent = hl ? HC : hid + 2 * HC;
-  ActArgsB aa{a->eps, a->philox_seed, a->philox_offset, a->rand3};
+  ActArgsB aa{a->eps, a->philox_seed, a->philox_offset, a->rand3, reinterpret_cast<const unsigned long long*>(a->philox_offset_dev)};
   if (a->ctrl_mode == 0) {
     MLS_CUDA(cudaMemsetAsync(a->q, 0, (size_t)a->n_graphs * N * 2 * sizeof(float), st));
     if (a->act) MLS_CUDA(cudaMemsetAsync(a->act, 0xFF, (size_t)a->n_graphs * N, st));

@@ -172,7 +172,7 @@ class DGNBase(nn.Module):
             raise ValueError(f"Expected {expected} feature cols for nodes, got {dim - 1}")
         return bs
 
-    def _call(self, obs, stride, n_graphs, ctrl_mode, ctrl_mask, q, act, eps, seed, offset, rand3):
+    def _call(self, obs, stride, n_graphs, ctrl_mode, ctrl_mask, q, act, eps, seed, offset, rand3, offset_dev=None):
         L = _lib.lib()
         desc = self._desc()
         ws, keep = self.weights_struct()
@@ -180,7 +180,7 @@ class DGNBase(nn.Module):
         wsp = self._ws.get(nbytes, obs.device)
         args = _lib.MlsForwardArgs(obs.data_ptr(), stride, n_graphs, ctrl_mode, _lib.ptr(ctrl_mask), q.data_ptr(),
                                    _lib.ptr(act), float(eps), 0, int(seed), int(offset), _lib.ptr(rand3),
-                                   wsp.data_ptr(), wsp.numel(), None, None, 0, 0)
+                                   wsp.data_ptr(), wsp.numel(), None, None, 0, 0, _lib.ptr(offset_dev))
         prof = getattr(self, "_prof", None)
         if prof is not None:          # (cudaEvent start, cudaEvent stop, kernel id), see set_profile_events
             args.prof_start, args.prof_stop, args.prof_kernel = prof[0].cuda_event, prof[1].cuda_event, prof[2]
@@ -215,7 +215,8 @@ class DGNBase(nn.Module):
     @torch.no_grad()
     def forward_graphs(self, obs_matrix: torch.Tensor, ctrl_mask: torch.Tensor, *, eps: float = 0.0,
                        philox_seed: int = 0, philox_offset: int = 0, rand3: Optional[torch.Tensor] = None,
-                       q_out: Optional[torch.Tensor] = None, act_out: Optional[torch.Tensor] = None):
+                       q_out: Optional[torch.Tensor] = None, act_out: Optional[torch.Tensor] = None,
+                       philox_offset_dev: Optional[torch.Tensor] = None):
         """Rollout form: obs_matrix f32 [B, N, 8] (what ``BatchedGraphEnv`` emits), ctrl_mask
         u8 [B, N] (the active set).  One GNN pass per graph; returns (q f32 [B,N,2] -- zero
         where not controlling, act i8 [B,N] -- -1 where not controlling)."""
@@ -227,5 +228,5 @@ class DGNBase(nn.Module):
         act = act_out if act_out is not None else torch.empty(B, N, dtype=torch.int8, device=dev)
         if B:
             self._call(obs_matrix.contiguous(), N * F, B, 0, ctrl_mask.contiguous(), q, act, eps, philox_seed,
-                       philox_offset, rand3)
+                       philox_offset, rand3, philox_offset_dev)
         return q, act

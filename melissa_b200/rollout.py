@@ -24,6 +24,10 @@ class Rollout:
         B, N, dev = env.B, env.N, env.device
         self.q = torch.zeros(B, N, 2, dtype=torch.float32, device=dev)
         self.act = torch.full((B, N), -1, dtype=torch.int8, device=dev)
+        # device-side round counter: Philox offset of the exploration draws (so a captured CUDA
+        # graph draws fresh noise on every replay)
+        self.round_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.graph = None
         # host mirrors for the end-to-end (host buffer) path
         self._host = None
 
@@ -42,16 +46,45 @@ class Rollout:
         self.env.reset(first)
         self.env.set_recycling(tuples if recycle else None)
         self.round_index = 0
+        self.round_dev.zero_()
+        self.env.transitions.zero_()
 
     # ---------------------------------------------------------------- device loop
-    def round(self):
-        """forward (one GNN pass per graph for all its active agents) -> eps-greedy -> env round."""
+    def _round_eager(self, obs, active):
         env = self.env
         if self.net is not None:
-            self.net.forward_graphs(env.obs, env.active, eps=self.eps, philox_seed=self.seed,
-                                    philox_offset=self.round_index, q_out=self.q, act_out=self.act)
+            self.net.forward_graphs(obs, active, eps=self.eps, philox_seed=self.seed, philox_offset=0,
+                                    philox_offset_dev=self.round_dev, q_out=self.q, act_out=self.act)
         env.step_device(self.act)
+        self.round_dev.add_(1)
+
+    def round(self):
+        """forward (one GNN pass per graph for all its active agents) -> eps-greedy -> env round.
+        Replays the captured CUDA graph when :meth:`capture` was called."""
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._round_eager(self.env.obs, self.env.active)
         self.round_index += 1
+
+    def capture(self, warmup_rounds: int = 2):
+        """Capture one round (every kernel of forward + env step) into a CUDA graph.  All buffers
+        are fixed device tensors and the exploration stream is keyed by a device-side counter,
+        so a replay is exactly the eager round without the per-launch host cost."""
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup_rounds):
+                self._round_eager(self.env.obs, self.env.active)
+                self.round_index += 1
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._round_eager(self.env.obs, self.env.active)
+        self.round_index += 1
+        self.graph = g
+        return self
 
     def transitions(self) -> int:
         return int(self.env.transitions.item())
@@ -76,10 +109,7 @@ class Rollout:
         env = self.env
         self._dev_in["obs"].copy_(h["obs"], non_blocking=True)
         self._dev_in["active"].copy_(h["active"], non_blocking=True)
-        if self.net is not None:
-            self.net.forward_graphs(self._dev_in["obs"], self._dev_in["active"], eps=self.eps, philox_seed=self.seed,
-                                    philox_offset=self.round_index, q_out=self.q, act_out=self.act)
-        env.step_device(self.act)
+        self._round_eager(self._dev_in["obs"], self._dev_in["active"])
         self.round_index += 1
         h["act"].copy_(self.act, non_blocking=True)
         h["obs"].copy_(env.obs, non_blocking=True)
