@@ -130,34 +130,40 @@ __device__ __forceinline__ void warp_sum4(float& p0, float& p1, float& p2, float
   p3 = __shfl_sync(0xffffffffu, c, 24);
 }
 
-// One CTA per (graph, head): the neighbour-side operand of that head is staged in shared
-// memory once; each warp walks targets, neighbours in batches of four, single-pass softmax
-// (running max / denominator, identical to exp(e - max) / (sum + 1e-16) up to rounding).
+// One CTA per (graph, head).  The operands of that head are converted to fp32 once while they
+// are staged in shared memory; each warp walks targets, neighbours in batches of four, with a
+// single-pass softmax (running max / denominator: identical to exp(e - max) / (sum + 1e-16) up
+// to rounding) in base 2.
+// GATv2 logits use leaky_relu(s, 0.2) = 0.6 s + 0.4 |s|:
+//     e_ij = 0.6 (a_j + b_i) + 0.4 sum_c att_c |x_l[j,c] + x_r[i,c]|,  a_j = <att, x_l[j]>, b_i = <att, x_r[i]>
+// so the per-edge, per-channel work is one add and one FMA; a_j and b_i are computed once per node.
 template <int W, bool TRANSFORMER>
 __global__ void __launch_bounds__(kEdgeThreads) edge_bf16_kernel(const EdgeArgs a) {
   extern __shared__ __align__(16) unsigned char esm[];
   const int N = a.N, H = a.H, HC = H * kC;
-  bf16* stA = reinterpret_cast<bf16*>(esm);                                      // [N][kC]  x_l or k   (neighbour side)
-  bf16* stT = stA + (size_t)N * kC;                                              // [N][kC]  x_r or q   (target side)
-  bf16* stB = stT + (size_t)N * kC;                                              // [N][kC]  v (Transformer)
-  float* poolbuf = reinterpret_cast<float*>(stB + (TRANSFORMER ? (size_t)N * kC : 0));   // [warps][kC]
-  uint32_t* s_nbr = reinterpret_cast<uint32_t*>(poolbuf + kEdgeWarps * kC);      // [N][W]
+  float* stA = reinterpret_cast<float*>(esm);                                    // [N][kC]  x_l or k   (neighbour side)
+  float* stT = stA + (size_t)N * kC;                                             // [N][kC]  x_r or q   (target side)
+  float* stB = stT + (size_t)N * kC;                                             // [N][kC]  v (Transformer)
+  float* poolbuf = stB + (TRANSFORMER ? (size_t)N * kC : 0);                     // [warps][kC]
+  float* s_a = poolbuf + kEdgeWarps * kC;                                        // [N] a_j (GATv2)
+  float* s_b = s_a + N;                                                          // [N] b_i (GATv2)
+  float* s_dm = s_b + N;                                                         // [N]
+  uint32_t* s_nbr = reinterpret_cast<uint32_t*>(s_dm + N);                       // [N][W]
   int* s_slot = reinterpret_cast<int*>(s_nbr + (size_t)N * W);                   // [N]
-  float* s_dm = reinterpret_cast<float*>(s_slot + N);                            // [N]
   const int g = blockIdx.x / H, h = blockIdx.x - g * H;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float* g_obs = a.obs + (int64_t)g * a.obs_stride;
   const size_t base = (size_t)g * N;
-  const float inv_sqrt_c = 1.0f / sqrtf((float)kC);
+  constexpr float kLog2e = 1.4426950408889634f;
   {
     const int src_col = TRANSFORMER ? HC + h * kC : h * kC;
     const int tgt_col = (TRANSFORMER ? 0 : HC) + h * kC;
-    for (int t = threadIdx.x; t < N * (kC / 8); t += kEdgeThreads) {
-      const int j = t / (kC / 8), q = t - j * (kC / 8);
+    for (int t = threadIdx.x; t < N * (kC / 4); t += kEdgeThreads) {
+      const int j = t / (kC / 4), q = t - j * (kC / 4);
       const bf16* row = a.P + (base + j) * a.ldp;
-      reinterpret_cast<uint4*>(stA)[t] = *reinterpret_cast<const uint4*>(row + src_col + q * 8);
-      reinterpret_cast<uint4*>(stT)[t] = *reinterpret_cast<const uint4*>(row + tgt_col + q * 8);
-      if (TRANSFORMER) reinterpret_cast<uint4*>(stB)[t] = *reinterpret_cast<const uint4*>(row + 2 * HC + h * kC + q * 8);
+      reinterpret_cast<float4*>(stA)[t] = ld_bf16x4(row + src_col + q * 4);
+      reinterpret_cast<float4*>(stT)[t] = ld_bf16x4(row + tgt_col + q * 4);
+      if (TRANSFORMER) reinterpret_cast<float4*>(stB)[t] = ld_bf16x4(row + 2 * HC + h * kC + q * 4);
     }
     for (int t = threadIdx.x; t < N * W; t += kEdgeThreads) s_nbr[t] = a.nbr[base * W + t];
     for (int t = threadIdx.x; t < N; t += kEdgeThreads) {
@@ -170,7 +176,20 @@ __global__ void __launch_bounds__(kEdgeThreads) edge_bf16_kernel(const EdgeArgs 
   if (!TRANSFORMER) {
     att4 = *reinterpret_cast<const float4*>(a.att + h * kC + lane * 4);
     bias4 = *reinterpret_cast<const float4*>(a.bias + h * kC + lane * 4);
+    for (int j = warp; j < N; j += kEdgeWarps) {            // per-node linear parts of the logit
+      const float4 xl = *reinterpret_cast<const float4*>(stA + (size_t)j * kC + lane * 4);
+      const float4 xr = *reinterpret_cast<const float4*>(stT + (size_t)j * kC + lane * 4);
+      float pa = xl.x * att4.x + xl.y * att4.y + xl.z * att4.z + xl.w * att4.w;
+      float pb = xr.x * att4.x + xr.y * att4.y + xr.z * att4.z + xr.w * att4.w;
+      pa = warp_sum(pa); pb = warp_sum(pb);
+      if (lane == 0) { s_a[j] = pa; s_b[j] = pb; }
+    }
+    __syncthreads();
   }
+  // logits are produced directly in the base-2 domain: softmax_2(e * log2 e) == softmax_e(e)
+  const float lin_scale = 0.6f * kLog2e;
+  const float4 attn = make_float4(att4.x * 0.4f * kLog2e, att4.y * 0.4f * kLog2e, att4.z * 0.4f * kLog2e, att4.w * 0.4f * kLog2e);
+  const float tr_scale = kLog2e / sqrtf((float)kC);
   float4 pool = a.pool_mode == MLS_POOL_MAX ? make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY)
                                             : make_float4(0.f, 0.f, 0.f, 0.f);
   for (int i = warp; i < N; i += kEdgeWarps) {
@@ -184,7 +203,8 @@ __global__ void __launch_bounds__(kEdgeThreads) edge_bf16_kernel(const EdgeArgs 
       for (int w = 0; w < W; ++w) if (w == (i >> 5)) nb[w] |= 1u << (i & 31);          // add_self_loops
     }
     // target-side operand: x_r[i] (GATv2) / q[i] (Transformer)
-    const float4 ti = ld_bf16x4(stT + (size_t)i * kC + lane * 4);
+    const float4 ti = *reinterpret_cast<const float4*>(stT + (size_t)i * kC + lane * 4);
+    const float b_i = TRANSFORMER ? 0.f : s_b[i];
     float mx = -INFINITY, den = 0.f;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     int wcur = 0;
@@ -209,33 +229,35 @@ __global__ void __launch_bounds__(kEdgeThreads) edge_bf16_kernel(const EdgeArgs 
       float e[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        xj[u] = ld_bf16x4(stA + (size_t)j[u] * kC + lane * 4);
+        xj[u] = *reinterpret_cast<const float4*>(stA + (size_t)j[u] * kC + lane * 4);
         if (TRANSFORMER) {
           e[u] = ti.x * xj[u].x + ti.y * xj[u].y + ti.z * xj[u].z + ti.w * xj[u].w;
         } else {
-          float s0 = xj[u].x + ti.x, s1 = xj[u].y + ti.y, s2 = xj[u].z + ti.z, s3 = xj[u].w + ti.w;
-          s0 = fmaxf(s0, 0.2f * s0); s1 = fmaxf(s1, 0.2f * s1); s2 = fmaxf(s2, 0.2f * s2); s3 = fmaxf(s3, 0.2f * s3);
-          e[u] = s0 * att4.x + s1 * att4.y + s2 * att4.z + s3 * att4.w;
+          e[u] = attn.x * fabsf(xj[u].x + ti.x);
+          e[u] = fmaf(attn.y, fabsf(xj[u].y + ti.y), e[u]);
+          e[u] = fmaf(attn.z, fabsf(xj[u].z + ti.z), e[u]);
+          e[u] = fmaf(attn.w, fabsf(xj[u].w + ti.w), e[u]);
         }
       }
       warp_sum4(e[0], e[1], e[2], e[3], lane);
       float m_new = mx;
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        if (TRANSFORMER) e[u] *= inv_sqrt_c;
+        if (TRANSFORMER) e[u] *= tr_scale;
+        else e[u] = fmaf(lin_scale, s_a[j[u]] + b_i, e[u]);
         if (!ok[u]) e[u] = -INFINITY;
         m_new = fmaxf(m_new, e[u]);
       }
-      const float resc = __expf(mx - m_new);        // first batch: exp(-inf) = 0
+      const float resc = exp2f(mx - m_new);         // first batch: 2^-inf = 0
       den *= resc;
       acc.x *= resc; acc.y *= resc; acc.z *= resc; acc.w *= resc;
       if (TRANSFORMER) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) xj[u] = ld_bf16x4(stB + (size_t)j[u] * kC + lane * 4);
+        for (int u = 0; u < 4; ++u) xj[u] = *reinterpret_cast<const float4*>(stB + (size_t)j[u] * kC + lane * 4);
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const float p = __expf(e[u] - m_new);       // 0 for padded entries
+        const float p = exp2f(e[u] - m_new);        // 0 for padded entries
         den += p;
         acc.x = fmaf(p, xj[u].x, acc.x); acc.y = fmaf(p, xj[u].y, acc.y);
         acc.z = fmaf(p, xj[u].z, acc.z); acc.w = fmaf(p, xj[u].w, acc.w);
@@ -439,8 +461,12 @@ size_t carve_b(const MlsNetDesc* d, int Gc, unsigned char* base, WsB* ws) {
 
 template <int W, bool TR>
 int launch_edge(cudaStream_t st, const EdgeArgs& ea) {
-  const size_t smem = (size_t)ea.N * kC * 2 * (TR ? 3 : 2) + kEdgeWarps * kC * 4 + (size_t)ea.N * (W + 2) * 4;
+  const size_t smem = (size_t)ea.N * kC * 4 * (TR ? 3 : 2) + kEdgeWarps * kC * 4 + (size_t)ea.N * (W + 4) * 4;
   static size_t configured = 0;
+  if (smem > 227 * 1024) {
+    mls_set_error("bf16 attention kernel needs %zu bytes of shared memory for %d nodes (max 232448): use precision fp32", smem, ea.N);
+    return MLS_ERR_UNSUPPORTED;
+  }
   if (smem > 48 * 1024 && smem > configured) {
     MLS_CUDA(cudaFuncSetAttribute(edge_bf16_kernel<W, TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
@@ -470,8 +496,17 @@ int edge_dispatch(cudaStream_t st, const EdgeArgs& ea, bool tr, int Wn) {
 
 }  // namespace
 
+#include <stdlib.h>
 int bf16_chunk_graphs(const MlsNetDesc* d, int n_graphs) {
-  int gc = (148 * 128) / d->n_nodes;      // one full wave of 128-row GEMM tiles per N tile
+  // one full wave of 128-row GEMM tiles per N tile by default: the bf16 intermediates of a chunk
+  // (about 5.3 KB per node) then stay L2 resident; MLS_BF16_CHUNK_TILES overrides (experiments)
+  static int tiles = 0;
+  if (!tiles) {
+    const char* e = getenv("MLS_BF16_CHUNK_TILES");
+    tiles = e ? atoi(e) : 148;
+    if (tiles < 1) tiles = 148;
+  }
+  int gc = (tiles * 128) / d->n_nodes;
   if (gc < 1) gc = 1;
   return n_graphs < gc ? n_graphs : gc;
 }
