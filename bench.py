@@ -296,7 +296,8 @@ def run_ours(args):
         flops_round = algorithmic_flops(args.model, N, deg + N, A)
         # dominant kernel: projection GEMM launch that was bracketed with events (first chunk of every forward)
         HC, hid = 512, 128
-        chunk_rows = min(B, max(1, (8192 if args.precision == "fp32" else 148 * 128) // N)) * N
+        import ctypes
+        chunk_rows = (_lib.lib().mls_dgn_chunk_graphs(ctypes.byref(net._desc()), B) if net is not None else B) * N
         K = HC if prof_name == "proj2" else hid
         nproj = 3 if args.model == "dgn_r" else 2
         n_out = HC if args.precision == "fp32" else nproj * HC     # bf16: all projections of a conv in one GEMM

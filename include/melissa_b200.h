@@ -230,6 +230,8 @@ enum MlsProfKernel {
 };
 
 size_t mls_dgn_workspace_bytes(const MlsNetDesc* desc, int32_t n_graphs);
+/* graphs processed per internal pass (kernel launches cover this many graphs at a time). */
+int mls_dgn_chunk_graphs(const MlsNetDesc* desc, int32_t n_graphs);
 int mls_dgn_forward(const MlsNetDesc* desc, const MlsNetWeights* w, const MlsForwardArgs* args,
                     void* stream);
 

@@ -84,7 +84,7 @@ PROF_KERNELS = {None: 0, "proj1": 1, "proj2": 2, "edge1": 3, "edge2": 4, "head0"
 
 
 EXPORTS = ["mls_version", "mls_last_error", "mls_device_info", "mls_words_per_row", "mls_launch_count", "mls_env_reset", "mls_env_step",
-           "mls_env_info", "mls_dgn_workspace_bytes", "mls_dgn_forward"]
+           "mls_env_info", "mls_dgn_workspace_bytes", "mls_dgn_chunk_graphs", "mls_dgn_forward"]
 
 _lib = None
 
@@ -116,6 +116,7 @@ def lib():
     L.mls_env_info.argtypes = [P(MlsEnvDesc), P(MlsEnvState), vp, vp]
     L.mls_dgn_workspace_bytes.argtypes = [P(MlsNetDesc), C.c_int32]
     L.mls_dgn_workspace_bytes.restype = C.c_size_t
+    L.mls_dgn_chunk_graphs.argtypes = [P(MlsNetDesc), C.c_int32]
     L.mls_dgn_forward.argtypes = [P(MlsNetDesc), P(MlsNetWeights), P(MlsForwardArgs), vp]
     for name in EXPORTS:
         getattr(L, name)

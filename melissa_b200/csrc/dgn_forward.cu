@@ -432,6 +432,12 @@ void launch_tr_edge(cudaStream_t st, const float* P, int ldp, const float* obs, 
 
 }  // namespace
 
+int bf16_chunk_graphs(const MlsNetDesc* d, int n_graphs);
+extern "C" int mls_dgn_chunk_graphs(const MlsNetDesc* desc, int32_t n_graphs) {
+  if (!desc || n_graphs <= 0 || desc->n_nodes <= 0) return 0;
+  return desc->precision == MLS_PREC_BF16 ? bf16_chunk_graphs(desc, n_graphs) : chunk_graphs(desc, n_graphs);
+}
+
 extern "C" size_t mls_dgn_workspace_bytes(const MlsNetDesc* desc, int32_t n_graphs) {
   if (!desc || n_graphs <= 0 || desc->n_nodes <= 0) return 0;
   if (desc->precision == MLS_PREC_BF16) return dgn_workspace_bytes_bf16(desc, n_graphs);

@@ -498,13 +498,15 @@ int edge_dispatch(cudaStream_t st, const EdgeArgs& ea, bool tr, int Wn) {
 
 #include <stdlib.h>
 int bf16_chunk_graphs(const MlsNetDesc* d, int n_graphs) {
-  // one full wave of 128-row GEMM tiles per N tile by default: the bf16 intermediates of a chunk
-  // (about 5.3 KB per node) then stay L2 resident; MLS_BF16_CHUNK_TILES overrides (experiments)
+  // 32 waves of 128-row GEMM tiles per chunk (about 600 K node rows, ~6 GB of bf16 workspace).
+  // Measured on B200 (profiles/r01_chunk_sweep.txt): L2-sized chunks (148 tiles) cost 35 % more
+  // per round than big ones -- launch ramp/drain of ~12 kernels per chunk outweighs the HBM
+  // round trip of the intermediates.  MLS_BF16_CHUNK_TILES overrides.
   static int tiles = 0;
   if (!tiles) {
     const char* e = getenv("MLS_BF16_CHUNK_TILES");
-    tiles = e ? atoi(e) : 148;
-    if (tiles < 1) tiles = 148;
+    tiles = e ? atoi(e) : 4736;
+    if (tiles < 1) tiles = 4736;
   }
   int gc = (tiles * 128) / d->n_nodes;
   if (gc < 1) gc = 1;
