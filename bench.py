@@ -176,7 +176,8 @@ def run_ours(args):
         dist.barrier()
     if rank != 0:
         tup = load_tuples(N, G, P)
-    gi, src, inter, scr = [np.roll(a, -rank * (B // 2), axis=0) for a in tup]   # each rank starts elsewhere in the pool
+    from melissa_b200.sharding import reduce_job, shard_tuples
+    gi, src, inter, scr = shard_tuples(tup, rank, B)   # each rank starts elsewhere in the pool
     env = BatchedGraphEnv(B, N, pool, device=dev, want_obs=True)
     net = None
     if args.model != "none":
@@ -280,12 +281,10 @@ def run_ours(args):
         dist.all_reduce(t, op=op)
         return float(t.item())
 
-    ms_max = reduce(ms, dist.ReduceOp.MAX if world > 1 else None)
-    trans_sum = reduce(trans, dist.ReduceOp.SUM if world > 1 else None)
+    ms_max, trans_sum = reduce_job(ms, trans, dev)
     launches_sum = reduce(launches, dist.ReduceOp.SUM if world > 1 else None)
     if e2e is not None:
-        e_ms_max = reduce(e2e[0], dist.ReduceOp.MAX if world > 1 else None)
-        e_trans_sum = reduce(e2e[1], dist.ReduceOp.SUM if world > 1 else None)
+        e_ms_max, e_trans_sum = reduce_job(e2e[0], e2e[1], dev)
 
     out = None
     if rank == 0:
