@@ -110,163 +110,171 @@ struct EdgeArgs {
 };
 
 constexpr int kEdgeThreads = 256, kEdgeWarps = 8;
+constexpr int kLD = kC + 4;             // staged row pitch in floats (528 B: 16 B aligned, rows 4 banks apart)
+constexpr int kMaxDeg = kMaxNbr + 1;    // 32 neighbours + self loop
 
-// sum four per-lane values over the warp with 6 shuffles (pairs are folded while halving), then
-// broadcast: returns the four totals to every lane
-__device__ __forceinline__ void warp_sum4(float& p0, float& p1, float& p2, float& p3, int lane) {
-  const bool h16 = lane & 16, h8 = lane & 8;
-  float a = h16 ? p1 : p0, sa = h16 ? p0 : p1;
-  a += __shfl_xor_sync(0xffffffffu, sa, 16);
-  float b = h16 ? p3 : p2, sb = h16 ? p2 : p3;
-  b += __shfl_xor_sync(0xffffffffu, sb, 16);
-  float c = h8 ? b : a, sc = h8 ? a : b;
-  c += __shfl_xor_sync(0xffffffffu, sc, 8);
-  c += __shfl_xor_sync(0xffffffffu, c, 4);
-  c += __shfl_xor_sync(0xffffffffu, c, 2);
-  c += __shfl_xor_sync(0xffffffffu, c, 1);
-  p0 = __shfl_sync(0xffffffffu, c, 0);      // value index = 2*bit3 + bit4 of the holding lane
-  p1 = __shfl_sync(0xffffffffu, c, 16);
-  p2 = __shfl_sync(0xffffffffu, c, 8);
-  p3 = __shfl_sync(0xffffffffu, c, 24);
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
 }
 
-// One CTA per (graph, head).  The operands of that head are converted to fp32 once while they
-// are staged in shared memory; each warp walks targets, neighbours in batches of four, with a
-// single-pass softmax (running max / denominator: identical to exp(e - max) / (sum + 1e-16) up
-// to rounding) in base 2.
-// GATv2 logits use leaky_relu(s, 0.2) = 0.6 s + 0.4 |s|:
-//     e_ij = 0.6 (a_j + b_i) + 0.4 sum_c att_c |x_l[j,c] + x_r[i,c]|,  a_j = <att, x_l[j]>, b_i = <att, x_r[i]>
-// so the per-edge, per-channel work is one add and one FMA; a_j and b_i are computed once per node.
+// One CTA per (graph, head).
+//   phase 0  stage the head's operands in shared memory as fp32 (converted once, not per edge)
+//   phase 1  CSR edge list of the graph from the neighbour masks (targets x sources, self loop for GATv2)
+//   phase 2  logits, FOUR LANES PER EDGE (32 channels each, interleaved float4s): no warp-wide
+//            reductions and no padding -- every issued lane does useful work
+//              GATv2:       e_ij = 0.6 (a_j + b_i) + 0.4 sum_c att_c |x_l[j,c] + x_r[i,c]|   (leaky_relu(s,.2) = .6 s + .4 |s|)
+//              Transformer: e_ij = <q_i, k_j> / sqrt(C)
+//   phase 3  one warp per target: softmax over its segment (exp2, PyG's +1e-16) and the weighted sum of
+//            x_l / v rows; writes relu(conv + bias) to x_out, the controlling-node snapshot, or the HL-DGN pool
 template <int W, bool TRANSFORMER>
 __global__ void __launch_bounds__(kEdgeThreads) edge_bf16_kernel(const EdgeArgs a) {
   extern __shared__ __align__(16) unsigned char esm[];
   const int N = a.N, H = a.H, HC = H * kC;
-  float* stA = reinterpret_cast<float*>(esm);                                    // [N][kC]  x_l or k   (neighbour side)
-  float* stT = stA + (size_t)N * kC;                                             // [N][kC]  x_r or q   (target side)
-  float* stB = stT + (size_t)N * kC;                                             // [N][kC]  v (Transformer)
-  float* poolbuf = stB + (TRANSFORMER ? (size_t)N * kC : 0);                     // [warps][kC]
-  float* s_a = poolbuf + kEdgeWarps * kC;                                        // [N] a_j (GATv2)
-  float* s_b = s_a + N;                                                          // [N] b_i (GATv2)
+  const int emax = N * kMaxDeg;
+  float* stA = reinterpret_cast<float*>(esm);                                    // [N][kLD]  x_l or k   (source side)
+  float* stT = stA + (size_t)N * kLD;                                            // [N][kLD]  x_r or q   (target side)
+  float* stB = stT + (size_t)N * kLD;                                            // [N][kLD]  v (Transformer)
+  float* poolbuf = stB + (TRANSFORMER ? (size_t)N * kLD : 0);                    // [warps][kC]
+  float* s_a = poolbuf + kEdgeWarps * kC;                                        // [N] <att, x_l[j]>
+  float* s_b = s_a + N;                                                          // [N] <att, x_r[i]>
   float* s_dm = s_b + N;                                                         // [N]
-  uint32_t* s_nbr = reinterpret_cast<uint32_t*>(s_dm + N);                       // [N][W]
-  int* s_slot = reinterpret_cast<int*>(s_nbr + (size_t)N * W);                   // [N]
+  float* e_val = s_dm + N;                                                       // [emax] logits (base-2 domain)
+  int* row_ptr = reinterpret_cast<int*>(e_val + emax);                           // [N+1]
+  int* s_deg = row_ptr + N + 1;                                                  // [N]
+  int* s_slot = s_deg + N;                                                       // [N]
+  uint32_t* s_nbr = reinterpret_cast<uint32_t*>(s_slot + N);                     // [N][W]
+  uint8_t* e_src = reinterpret_cast<uint8_t*>(s_nbr + (size_t)N * W);            // [emax]
+  uint8_t* e_dst = e_src + emax;                                                 // [emax]
   const int g = blockIdx.x / H, h = blockIdx.x - g * H;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const float* g_obs = a.obs + (int64_t)g * a.obs_stride;
   const size_t base = (size_t)g * N;
   constexpr float kLog2e = 1.4426950408889634f;
+  // ---------------------------------------------------------------- phase 0
   {
     const int src_col = TRANSFORMER ? HC + h * kC : h * kC;
     const int tgt_col = (TRANSFORMER ? 0 : HC) + h * kC;
-    for (int t = threadIdx.x; t < N * (kC / 4); t += kEdgeThreads) {
+    for (int t = tid; t < N * (kC / 4); t += kEdgeThreads) {
       const int j = t / (kC / 4), q = t - j * (kC / 4);
       const bf16* row = a.P + (base + j) * a.ldp;
-      reinterpret_cast<float4*>(stA)[t] = ld_bf16x4(row + src_col + q * 4);
-      reinterpret_cast<float4*>(stT)[t] = ld_bf16x4(row + tgt_col + q * 4);
-      if (TRANSFORMER) reinterpret_cast<float4*>(stB)[t] = ld_bf16x4(row + 2 * HC + h * kC + q * 4);
+      *reinterpret_cast<float4*>(stA + (size_t)j * kLD + q * 4) = ld_bf16x4(row + src_col + q * 4);
+      *reinterpret_cast<float4*>(stT + (size_t)j * kLD + q * 4) = ld_bf16x4(row + tgt_col + q * 4);
+      if (TRANSFORMER) *reinterpret_cast<float4*>(stB + (size_t)j * kLD + q * 4) = ld_bf16x4(row + 2 * HC + h * kC + q * 4);
     }
-    for (int t = threadIdx.x; t < N * W; t += kEdgeThreads) s_nbr[t] = a.nbr[base * W + t];
-    for (int t = threadIdx.x; t < N; t += kEdgeThreads) {
-      s_slot[t] = a.slot ? a.slot[base + t] : -1;
+    for (int t = tid; t < N; t += kEdgeThreads) {
+      const int sl = a.slot ? a.slot[base + t] : -1;
+      s_slot[t] = sl;
       s_dm[t] = g_obs[t * 8 + 7];
+      int deg = 0;
+#pragma unroll
+      for (int w = 0; w < W; ++w) {
+        uint32_t m = a.nbr[(base + t) * W + w];
+        if (!TRANSFORMER && w == (t >> 5)) m |= 1u << (t & 31);                  // add_self_loops
+        if (a.ctrl_only && sl < 0) m = 0;                                        // nobody reads this target
+        s_nbr[t * W + w] = m;
+        deg += __popc(m);
+      }
+      s_deg[t] = deg;
     }
   }
   __syncthreads();
+  // ---------------------------------------------------------------- phase 1
+  for (int t = tid; t <= N; t += kEdgeThreads) {
+    int acc = 0;
+    for (int k = 0; k < t; ++k) acc += s_deg[k];
+    row_ptr[t] = acc;
+  }
   float4 att4 = make_float4(0.f, 0.f, 0.f, 0.f), bias4 = att4;
   if (!TRANSFORMER) {
     att4 = *reinterpret_cast<const float4*>(a.att + h * kC + lane * 4);
     bias4 = *reinterpret_cast<const float4*>(a.bias + h * kC + lane * 4);
-    for (int j = warp; j < N; j += kEdgeWarps) {            // per-node linear parts of the logit
-      const float4 xl = *reinterpret_cast<const float4*>(stA + (size_t)j * kC + lane * 4);
-      const float4 xr = *reinterpret_cast<const float4*>(stT + (size_t)j * kC + lane * 4);
+  }
+  __syncthreads();
+  for (int i = warp; i < N; i += kEdgeWarps) {
+    int off = row_ptr[i];
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+      const uint32_t m = s_nbr[i * W + w];
+      const int c = __popc(m);
+      if (lane < c) {
+        e_src[off + lane] = (uint8_t)(w * 32 + __fns(m, 0, lane + 1));
+        e_dst[off + lane] = (uint8_t)i;
+      }
+      off += c;
+    }
+    if (!TRANSFORMER) {                                     // per-node linear parts of the logit
+      const float4 xl = *reinterpret_cast<const float4*>(stA + (size_t)i * kLD + lane * 4);
+      const float4 xr = *reinterpret_cast<const float4*>(stT + (size_t)i * kLD + lane * 4);
       float pa = xl.x * att4.x + xl.y * att4.y + xl.z * att4.z + xl.w * att4.w;
       float pb = xr.x * att4.x + xr.y * att4.y + xr.z * att4.z + xr.w * att4.w;
       pa = warp_sum(pa); pb = warp_sum(pb);
-      if (lane == 0) { s_a[j] = pa; s_b[j] = pb; }
+      if (lane == 0) { s_a[i] = pa; s_b[i] = pb; }
     }
-    __syncthreads();
   }
-  // logits are produced directly in the base-2 domain: softmax_2(e * log2 e) == softmax_e(e)
-  const float lin_scale = 0.6f * kLog2e;
-  const float4 attn = make_float4(att4.x * 0.4f * kLog2e, att4.y * 0.4f * kLog2e, att4.z * 0.4f * kLog2e, att4.w * 0.4f * kLog2e);
-  const float tr_scale = kLog2e / sqrtf((float)kC);
+  __syncthreads();
+  // ---------------------------------------------------------------- phase 2: logits, 4 lanes per edge
+  {
+    const int E = row_ptr[N];
+    const int sub = tid & 3;
+    float4 attn[8];
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      attn[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (!TRANSFORMER) {
+        const float4 v = *reinterpret_cast<const float4*>(a.att + h * kC + (it * 4 + sub) * 4);
+        const float sc = 0.4f * kLog2e;
+        attn[it] = make_float4(v.x * sc, v.y * sc, v.z * sc, v.w * sc);
+      }
+    }
+    const float lin_scale = 0.6f * kLog2e, tr_scale = kLog2e / sqrtf((float)kC);
+    for (int e0 = 0; e0 < E; e0 += kEdgeThreads / 4) {
+      const int eidx = e0 + (tid >> 2);
+      const bool valid = eidx < E;
+      const int i = valid ? e_dst[eidx] : 0, j = valid ? e_src[eidx] : 0;
+      const float* pj = stA + (size_t)j * kLD + sub * 4;
+      const float* pi = stT + (size_t)i * kLD + sub * 4;
+      float acc = 0.f;
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const float4 x = *reinterpret_cast<const float4*>(pj + it * 16);
+        const float4 y = *reinterpret_cast<const float4*>(pi + it * 16);
+        if (TRANSFORMER) {
+          acc = fmaf(x.x, y.x, acc); acc = fmaf(x.y, y.y, acc); acc = fmaf(x.z, y.z, acc); acc = fmaf(x.w, y.w, acc);
+        } else {
+          acc = fmaf(attn[it].x, fabsf(x.x + y.x), acc); acc = fmaf(attn[it].y, fabsf(x.y + y.y), acc);
+          acc = fmaf(attn[it].z, fabsf(x.z + y.z), acc); acc = fmaf(attn[it].w, fabsf(x.w + y.w), acc);
+        }
+      }
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      if (valid && sub == 0) e_val[eidx] = TRANSFORMER ? acc * tr_scale : fmaf(lin_scale, s_a[j] + s_b[i], acc);
+    }
+  }
+  __syncthreads();
+  // ---------------------------------------------------------------- phase 3: softmax + aggregation
   float4 pool = a.pool_mode == MLS_POOL_MAX ? make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY)
                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float* stV = TRANSFORMER ? stB : stA;
   for (int i = warp; i < N; i += kEdgeWarps) {
     const int sl = s_slot[i];
     if (a.ctrl_only && sl < 0) continue;
-    uint32_t nb[W];
-#pragma unroll
-    for (int w = 0; w < W; ++w) nb[w] = s_nbr[i * W + w];
-    if (!TRANSFORMER) {
-#pragma unroll
-      for (int w = 0; w < W; ++w) if (w == (i >> 5)) nb[w] |= 1u << (i & 31);          // add_self_loops
-    }
-    // target-side operand: x_r[i] (GATv2) / q[i] (Transformer)
-    const float4 ti = *reinterpret_cast<const float4*>(stT + (size_t)i * kC + lane * 4);
-    const float b_i = TRANSFORMER ? 0.f : s_b[i];
-    float mx = -INFINITY, den = 0.f;
+    const int r0 = row_ptr[i], d = row_ptr[i + 1] - r0;     // d <= 33, warp uniform
+    const float ev0 = lane < d ? e_val[r0 + lane] : -INFINITY;
+    const float ev1 = lane + 32 < d ? e_val[r0 + 32 + lane] : -INFINITY;
+    const float mx = warp_max(fmaxf(ev0, ev1));
+    const float p0 = lane < d ? exp2f(ev0 - mx) : 0.f;
+    const float p1 = lane + 32 < d ? exp2f(ev1 - mx) : 0.f;
+    const float inv_den = 1.0f / (warp_sum(p0 + p1) + 1e-16f);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    int wcur = 0;
-    uint32_t bits = nb[0];
-    auto next = [&](int& j) -> bool {       // warp-uniform walk over the set bits of nb[0..W)
-      while (bits == 0) {
-        if (++wcur >= W) return false;
-#pragma unroll
-        for (int w = 1; w < W; ++w) if (w == wcur) bits = nb[w];
-      }
-      j = wcur * 32 + __ffs(bits) - 1;
-      bits &= bits - 1;
-      return true;
-    };
-    for (;;) {
-      int j[4];
-      bool ok[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) { j[u] = i; ok[u] = (wcur < W) && next(j[u]); }
-      if (!ok[0]) break;
-      float4 xj[4];
-      float e[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        xj[u] = *reinterpret_cast<const float4*>(stA + (size_t)j[u] * kC + lane * 4);
-        if (TRANSFORMER) {
-          e[u] = ti.x * xj[u].x + ti.y * xj[u].y + ti.z * xj[u].z + ti.w * xj[u].w;
-        } else {
-          e[u] = attn.x * fabsf(xj[u].x + ti.x);
-          e[u] = fmaf(attn.y, fabsf(xj[u].y + ti.y), e[u]);
-          e[u] = fmaf(attn.z, fabsf(xj[u].z + ti.z), e[u]);
-          e[u] = fmaf(attn.w, fabsf(xj[u].w + ti.w), e[u]);
-        }
-      }
-      warp_sum4(e[0], e[1], e[2], e[3], lane);
-      float m_new = mx;
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (TRANSFORMER) e[u] *= tr_scale;
-        else e[u] = fmaf(lin_scale, s_a[j[u]] + b_i, e[u]);
-        if (!ok[u]) e[u] = -INFINITY;
-        m_new = fmaxf(m_new, e[u]);
-      }
-      const float resc = exp2f(mx - m_new);         // first batch: 2^-inf = 0
-      den *= resc;
-      acc.x *= resc; acc.y *= resc; acc.z *= resc; acc.w *= resc;
-      if (TRANSFORMER) {
-#pragma unroll
-        for (int u = 0; u < 4; ++u) xj[u] = *reinterpret_cast<const float4*>(stB + (size_t)j[u] * kC + lane * 4);
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const float p = exp2f(e[u] - m_new);        // 0 for padded entries
-        den += p;
-        acc.x = fmaf(p, xj[u].x, acc.x); acc.y = fmaf(p, xj[u].y, acc.y);
-        acc.z = fmaf(p, xj[u].z, acc.z); acc.w = fmaf(p, xj[u].w, acc.w);
-      }
-      mx = m_new;
-      if (!ok[3]) break;
+    for (int k = 0; k < d; ++k) {
+      const float pk = __shfl_sync(0xffffffffu, k < 32 ? p0 : p1, k & 31);
+      const int j = e_src[r0 + k];
+      const float4 v = *reinterpret_cast<const float4*>(stV + (size_t)j * kLD + lane * 4);
+      acc.x = fmaf(pk, v.x, acc.x); acc.y = fmaf(pk, v.y, acc.y); acc.z = fmaf(pk, v.z, acc.z); acc.w = fmaf(pk, v.w, acc.w);
     }
-    const float inv_den = 1.0f / (den + 1e-16f);    // isolated Transformer node: acc = 0 -> output 0
-    float4 o;
+    float4 o;                                               // isolated Transformer node: acc = 0 -> output 0
     o.x = fmaxf(fmaf(acc.x, inv_den, bias4.x), 0.f); o.y = fmaxf(fmaf(acc.y, inv_den, bias4.y), 0.f);
     o.z = fmaxf(fmaf(acc.z, inv_den, bias4.z), 0.f); o.w = fmaxf(fmaf(acc.w, inv_den, bias4.w), 0.f);
     if (a.x_out) st_bf16x4(a.x_out + (base + i) * HC + h * kC + lane * 4, o);
@@ -281,15 +289,15 @@ __global__ void __launch_bounds__(kEdgeThreads) edge_bf16_kernel(const EdgeArgs 
   if (a.pool_mode >= 0) {      // HL-DGN: z[g] = pool_i(relu(conv)[i] * dm[i])  (hl_dgn.py:103-108)
     *reinterpret_cast<float4*>(poolbuf + warp * kC + lane * 4) = pool;
     __syncthreads();
-    if (threadIdx.x < kC) {
+    if (tid < kC) {
       const int used = N < kEdgeWarps ? N : kEdgeWarps;        // warps that own at least one node
-      float r = poolbuf[threadIdx.x];
+      float r = poolbuf[tid];
       for (int w2 = 1; w2 < used; ++w2) {
-        const float v = poolbuf[w2 * kC + threadIdx.x];
+        const float v = poolbuf[w2 * kC + tid];
         r = a.pool_mode == MLS_POOL_MAX ? fmaxf(r, v) : r + v;
       }
       if (a.pool_mode == MLS_POOL_MEAN) r = r / (float)N;
-      a.z[(size_t)g * a.ldz + a.z_col + h * kC + threadIdx.x] = __float2bfloat16_rn(r);
+      a.z[(size_t)g * a.ldz + a.z_col + h * kC + tid] = __float2bfloat16_rn(r);
     }
   }
 }
@@ -461,7 +469,9 @@ size_t carve_b(const MlsNetDesc* d, int Gc, unsigned char* base, WsB* ws) {
 
 template <int W, bool TR>
 int launch_edge(cudaStream_t st, const EdgeArgs& ea) {
-  const size_t smem = (size_t)ea.N * kC * 4 * (TR ? 3 : 2) + kEdgeWarps * kC * 4 + (size_t)ea.N * (W + 4) * 4;
+  const size_t emax = (size_t)ea.N * kMaxDeg;
+  const size_t smem = (size_t)ea.N * kLD * 4 * (TR ? 3 : 2) + kEdgeWarps * kC * 4 + (size_t)ea.N * 3 * 4 + emax * 4 +
+                      ((size_t)ea.N * 3 + 1) * 4 + (size_t)ea.N * W * 4 + emax * 2 + 16;
   static size_t configured = 0;
   if (smem > 227 * 1024) {
     mls_set_error("bf16 attention kernel needs %zu bytes of shared memory for %d nodes (max 232448): use precision fp32", smem, ea.N);
