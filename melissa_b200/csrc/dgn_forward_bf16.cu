@@ -110,24 +110,21 @@ struct EdgeArgs {
 };
 
 constexpr int kEdgeThreads = 256, kEdgeWarps = 8;
-constexpr int kLD = kC + 4;             // staged row pitch in floats (528 B: 16 B aligned, rows 4 banks apart)
+constexpr int kLD = kC;                 // staged row pitch in floats (a warp reads 4 x 128 B row segments = the 4-wavefront minimum)
 constexpr int kMaxDeg = kMaxNbr + 1;    // 32 neighbours + self loop
-
-__device__ __forceinline__ float warp_max(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-  return v;
-}
 
 // One CTA per (graph, head).
 //   phase 0  stage the head's operands in shared memory as fp32 (converted once, not per edge)
-//   phase 1  CSR edge list of the graph from the neighbour masks (targets x sources, self loop for GATv2)
-//   phase 2  logits, FOUR LANES PER EDGE (32 channels each, interleaved float4s): no warp-wide
-//            reductions and no padding -- every issued lane does useful work
+//   phase 1  CSR source lists per target from the neighbour masks (self loop for GATv2); per-node
+//            linear parts of the GATv2 logit
+//   phase 2  one warp per target, FOUR neighbours per round, EIGHT lanes per neighbour (16 channels
+//            each): the target row lives in registers, every neighbour row is read from shared
+//            memory exactly once and serves both its logit and its contribution to the output
+//            (single-pass softmax in base 2: running max / denominator, same value as PyG's
+//            exp(e - max) / (sum + 1e-16) up to rounding); the four lane groups are combined with a
+//            reduce-scatter (12 shuffles) so that lane l ends up owning channels 4l..4l+3.
 //              GATv2:       e_ij = 0.6 (a_j + b_i) + 0.4 sum_c att_c |x_l[j,c] + x_r[i,c]|   (leaky_relu(s,.2) = .6 s + .4 |s|)
 //              Transformer: e_ij = <q_i, k_j> / sqrt(C)
-//   phase 3  one warp per target: softmax over its segment (exp2, PyG's +1e-16) and the weighted sum of
-//            x_l / v rows; writes relu(conv + bias) to x_out, the controlling-node snapshot, or the HL-DGN pool
 template <int W, bool TRANSFORMER>
 __global__ void __launch_bounds__(kEdgeThreads) edge_bf16_kernel(const EdgeArgs a) {
   extern __shared__ __align__(16) unsigned char esm[];
@@ -136,17 +133,15 @@ __global__ void __launch_bounds__(kEdgeThreads) edge_bf16_kernel(const EdgeArgs 
   float* stA = reinterpret_cast<float*>(esm);                                    // [N][kLD]  x_l or k   (source side)
   float* stT = stA + (size_t)N * kLD;                                            // [N][kLD]  x_r or q   (target side)
   float* stB = stT + (size_t)N * kLD;                                            // [N][kLD]  v (Transformer)
-  float* poolbuf = stB + (TRANSFORMER ? (size_t)N * kLD : 0);                    // [warps][kC]
-  float* s_a = poolbuf + kEdgeWarps * kC;                                        // [N] <att, x_l[j]>
+  float* s_a = stB + (TRANSFORMER ? (size_t)N * kLD : 0);                        // [N] <att, x_l[j]>
   float* s_b = s_a + N;                                                          // [N] <att, x_r[i]>
   float* s_dm = s_b + N;                                                         // [N]
-  float* e_val = s_dm + N;                                                       // [emax] logits (base-2 domain)
-  int* row_ptr = reinterpret_cast<int*>(e_val + emax);                           // [N+1]
+  int* row_ptr = reinterpret_cast<int*>(s_dm + N);                               // [N+1]
   int* s_deg = row_ptr + N + 1;                                                  // [N]
   int* s_slot = s_deg + N;                                                       // [N]
   uint32_t* s_nbr = reinterpret_cast<uint32_t*>(s_slot + N);                     // [N][W]
   uint8_t* e_src = reinterpret_cast<uint8_t*>(s_nbr + (size_t)N * W);            // [emax]
-  uint8_t* e_dst = e_src + emax;                                                 // [emax]
+  float* poolbuf = reinterpret_cast<float*>(e_src + ((emax + 15) & ~15));        // [warps][kC], HL-DGN pooling only
   const int g = blockIdx.x / H, h = blockIdx.x - g * H;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const float* g_obs = a.obs + (int64_t)g * a.obs_stride;
@@ -198,10 +193,7 @@ __global__ void __launch_bounds__(kEdgeThreads) edge_bf16_kernel(const EdgeArgs 
     for (int w = 0; w < W; ++w) {
       const uint32_t m = s_nbr[i * W + w];
       const int c = __popc(m);
-      if (lane < c) {
-        e_src[off + lane] = (uint8_t)(w * 32 + __fns(m, 0, lane + 1));
-        e_dst[off + lane] = (uint8_t)i;
-      }
+      if (lane < c) e_src[off + lane] = (uint8_t)(w * 32 + __fns(m, 0, lane + 1));
       off += c;
     }
     if (!TRANSFORMER) {                                     // per-node linear parts of the logit
@@ -214,69 +206,102 @@ __global__ void __launch_bounds__(kEdgeThreads) edge_bf16_kernel(const EdgeArgs 
     }
   }
   __syncthreads();
-  // ---------------------------------------------------------------- phase 2: logits, 4 lanes per edge
-  {
-    const int E = row_ptr[N];
-    const int sub = tid & 3;
-    float4 attn[8];
+  // ---------------------------------------------------------------- phase 2
+  const int grp = lane >> 3, sub = lane & 7;                // neighbour slot of the round / channel slice
+  float4 attn[4];
 #pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      attn[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (!TRANSFORMER) {
-        const float4 v = *reinterpret_cast<const float4*>(a.att + h * kC + (it * 4 + sub) * 4);
-        const float sc = 0.4f * kLog2e;
-        attn[it] = make_float4(v.x * sc, v.y * sc, v.z * sc, v.w * sc);
-      }
-    }
-    const float lin_scale = 0.6f * kLog2e, tr_scale = kLog2e / sqrtf((float)kC);
-    for (int e0 = 0; e0 < E; e0 += kEdgeThreads / 4) {
-      const int eidx = e0 + (tid >> 2);
-      const bool valid = eidx < E;
-      const int i = valid ? e_dst[eidx] : 0, j = valid ? e_src[eidx] : 0;
-      const float* pj = stA + (size_t)j * kLD + sub * 4;
-      const float* pi = stT + (size_t)i * kLD + sub * 4;
-      float acc = 0.f;
-#pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const float4 x = *reinterpret_cast<const float4*>(pj + it * 16);
-        const float4 y = *reinterpret_cast<const float4*>(pi + it * 16);
-        if (TRANSFORMER) {
-          acc = fmaf(x.x, y.x, acc); acc = fmaf(x.y, y.y, acc); acc = fmaf(x.z, y.z, acc); acc = fmaf(x.w, y.w, acc);
-        } else {
-          acc = fmaf(attn[it].x, fabsf(x.x + y.x), acc); acc = fmaf(attn[it].y, fabsf(x.y + y.y), acc);
-          acc = fmaf(attn[it].z, fabsf(x.z + y.z), acc); acc = fmaf(attn[it].w, fabsf(x.w + y.w), acc);
-        }
-      }
-      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-      if (valid && sub == 0) e_val[eidx] = TRANSFORMER ? acc * tr_scale : fmaf(lin_scale, s_a[j] + s_b[i], acc);
+  for (int it = 0; it < 4; ++it) {
+    attn[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!TRANSFORMER) {
+      const float4 v = *reinterpret_cast<const float4*>(a.att + h * kC + (it * 8 + sub) * 4);
+      const float sc = 0.4f * kLog2e;
+      attn[it] = make_float4(v.x * sc, v.y * sc, v.z * sc, v.w * sc);
     }
   }
-  __syncthreads();
-  // ---------------------------------------------------------------- phase 3: softmax + aggregation
+  const float lin_scale = 0.6f * kLog2e, tr_scale = kLog2e / sqrtf((float)kC);
+  const float* stV = TRANSFORMER ? stB : stA;
   float4 pool = a.pool_mode == MLS_POOL_MAX ? make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY)
                                             : make_float4(0.f, 0.f, 0.f, 0.f);
-  const float* stV = TRANSFORMER ? stB : stA;
   for (int i = warp; i < N; i += kEdgeWarps) {
     const int sl = s_slot[i];
     if (a.ctrl_only && sl < 0) continue;
-    const int r0 = row_ptr[i], d = row_ptr[i + 1] - r0;     // d <= 33, warp uniform
-    const float ev0 = lane < d ? e_val[r0 + lane] : -INFINITY;
-    const float ev1 = lane + 32 < d ? e_val[r0 + 32 + lane] : -INFINITY;
-    const float mx = warp_max(fmaxf(ev0, ev1));
-    const float p0 = lane < d ? exp2f(ev0 - mx) : 0.f;
-    const float p1 = lane + 32 < d ? exp2f(ev1 - mx) : 0.f;
-    const float inv_den = 1.0f / (warp_sum(p0 + p1) + 1e-16f);
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int k = 0; k < d; ++k) {
-      const float pk = __shfl_sync(0xffffffffu, k < 32 ? p0 : p1, k & 31);
-      const int j = e_src[r0 + k];
-      const float4 v = *reinterpret_cast<const float4*>(stV + (size_t)j * kLD + lane * 4);
-      acc.x = fmaf(pk, v.x, acc.x); acc.y = fmaf(pk, v.y, acc.y); acc.z = fmaf(pk, v.z, acc.z); acc.w = fmaf(pk, v.w, acc.w);
+    const int r0 = row_ptr[i], r1 = row_ptr[i + 1];         // warp uniform
+    float4 tr[4];
+#pragma unroll
+    for (int it = 0; it < 4; ++it) tr[it] = *reinterpret_cast<const float4*>(stT + (size_t)i * kLD + (it * 8 + sub) * 4);
+    const float b_i = TRANSFORMER ? 0.f : s_b[i];
+    float mx = -INFINITY, den = 0.f;
+    float4 acc[4];
+#pragma unroll
+    for (int it = 0; it < 4; ++it) acc[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int kb = r0; kb < r1; kb += 4) {
+      const int k = kb + grp;
+      const bool valid = k < r1;
+      const int j = valid ? (int)e_src[k] : i;
+      float4 x[4];
+      float part = 0.f;
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        x[it] = *reinterpret_cast<const float4*>(stA + (size_t)j * kLD + (it * 8 + sub) * 4);
+        if (TRANSFORMER) {
+          part = fmaf(x[it].x, tr[it].x, part); part = fmaf(x[it].y, tr[it].y, part);
+          part = fmaf(x[it].z, tr[it].z, part); part = fmaf(x[it].w, tr[it].w, part);
+        } else {
+          part = fmaf(attn[it].x, fabsf(x[it].x + tr[it].x), part); part = fmaf(attn[it].y, fabsf(x[it].y + tr[it].y), part);
+          part = fmaf(attn[it].z, fabsf(x[it].z + tr[it].z), part); part = fmaf(attn[it].w, fabsf(x[it].w + tr[it].w), part);
+        }
+      }
+      part += __shfl_xor_sync(0xffffffffu, part, 1);
+      part += __shfl_xor_sync(0xffffffffu, part, 2);
+      part += __shfl_xor_sync(0xffffffffu, part, 4);        // all 8 lanes of the group hold the dot product
+      float e = TRANSFORMER ? part * tr_scale : fmaf(lin_scale, s_a[j] + b_i, part);
+      if (!valid) e = -INFINITY;
+      float m_r = fmaxf(e, __shfl_xor_sync(0xffffffffu, e, 8));
+      m_r = fmaxf(m_r, __shfl_xor_sync(0xffffffffu, m_r, 16));
+      if (m_r > mx) {                                       // warp uniform
+        const float resc = exp2f(mx - m_r);                 // first round: 2^-inf = 0
+        den *= resc;
+#pragma unroll
+        for (int it = 0; it < 4; ++it) { acc[it].x *= resc; acc[it].y *= resc; acc[it].z *= resc; acc[it].w *= resc; }
+        mx = m_r;
+      }
+      const float p = exp2f(e - mx);                        // 0 for padded slots
+      den += p;                                             // per-group partial
+      if (TRANSFORMER) {
+#pragma unroll
+        for (int it = 0; it < 4; ++it) x[it] = *reinterpret_cast<const float4*>(stV + (size_t)j * kLD + (it * 8 + sub) * 4);
+      }
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        acc[it].x = fmaf(p, x[it].x, acc[it].x); acc[it].y = fmaf(p, x[it].y, acc[it].y);
+        acc[it].z = fmaf(p, x[it].z, acc[it].z); acc[it].w = fmaf(p, x[it].w, acc[it].w);
+      }
     }
-    float4 o;                                               // isolated Transformer node: acc = 0 -> output 0
-    o.x = fmaxf(fmaf(acc.x, inv_den, bias4.x), 0.f); o.y = fmaxf(fmaf(acc.y, inv_den, bias4.y), 0.f);
-    o.z = fmaxf(fmaf(acc.z, inv_den, bias4.z), 0.f); o.w = fmaxf(fmaf(acc.w, inv_den, bias4.w), 0.f);
+    // combine the four lane groups: reduce-scatter so that group g keeps float4 slice it == g,
+    // i.e. lane l = 8g + sub owns channels 4l .. 4l+3
+    den += __shfl_xor_sync(0xffffffffu, den, 8);
+    den += __shfl_xor_sync(0xffffffffu, den, 16);
+    float4 lo, hi;                                          // step 1 (xor 16): keep slices {0,1} or {2,3}
+    {
+      const bool up = grp >= 2;
+      const float4 k0 = up ? acc[2] : acc[0], k1 = up ? acc[3] : acc[1];
+      const float4 s0 = up ? acc[0] : acc[2], s1 = up ? acc[1] : acc[3];
+      lo.x = k0.x + __shfl_xor_sync(0xffffffffu, s0.x, 16); lo.y = k0.y + __shfl_xor_sync(0xffffffffu, s0.y, 16);
+      lo.z = k0.z + __shfl_xor_sync(0xffffffffu, s0.z, 16); lo.w = k0.w + __shfl_xor_sync(0xffffffffu, s0.w, 16);
+      hi.x = k1.x + __shfl_xor_sync(0xffffffffu, s1.x, 16); hi.y = k1.y + __shfl_xor_sync(0xffffffffu, s1.y, 16);
+      hi.z = k1.z + __shfl_xor_sync(0xffffffffu, s1.z, 16); hi.w = k1.w + __shfl_xor_sync(0xffffffffu, s1.w, 16);
+    }
+    float4 mine;                                            // step 2 (xor 8): keep the slice of this group
+    {
+      const bool odd = grp & 1;
+      const float4 kp = odd ? hi : lo, sd = odd ? lo : hi;
+      mine.x = kp.x + __shfl_xor_sync(0xffffffffu, sd.x, 8); mine.y = kp.y + __shfl_xor_sync(0xffffffffu, sd.y, 8);
+      mine.z = kp.z + __shfl_xor_sync(0xffffffffu, sd.z, 8); mine.w = kp.w + __shfl_xor_sync(0xffffffffu, sd.w, 8);
+    }
+    const float inv_den = 1.0f / (den + 1e-16f);            // isolated Transformer node: acc = 0 -> output 0
+    float4 o;
+    o.x = fmaxf(fmaf(mine.x, inv_den, bias4.x), 0.f); o.y = fmaxf(fmaf(mine.y, inv_den, bias4.y), 0.f);
+    o.z = fmaxf(fmaf(mine.z, inv_den, bias4.z), 0.f); o.w = fmaxf(fmaf(mine.w, inv_den, bias4.w), 0.f);
     if (a.x_out) st_bf16x4(a.x_out + (base + i) * HC + h * kC + lane * 4, o);
     if (a.z && sl >= 0 && a.pool_mode < 0) st_bf16x4(a.z + (size_t)sl * a.ldz + a.z_col + h * kC + lane * 4, o);
     if (a.pool_mode >= 0) {
@@ -470,8 +495,8 @@ size_t carve_b(const MlsNetDesc* d, int Gc, unsigned char* base, WsB* ws) {
 template <int W, bool TR>
 int launch_edge(cudaStream_t st, const EdgeArgs& ea) {
   const size_t emax = (size_t)ea.N * kMaxDeg;
-  const size_t smem = (size_t)ea.N * kLD * 4 * (TR ? 3 : 2) + kEdgeWarps * kC * 4 + (size_t)ea.N * 3 * 4 + emax * 4 +
-                      ((size_t)ea.N * 3 + 1) * 4 + (size_t)ea.N * W * 4 + emax * 2 + 16;
+  const size_t smem = (size_t)ea.N * kLD * 4 * (TR ? 3 : 2) + (size_t)ea.N * 3 * 4 + ((size_t)ea.N * 3 + 1) * 4 +
+                      (size_t)ea.N * W * 4 + ((emax + 15) & ~(size_t)15) + (ea.pool_mode >= 0 ? kEdgeWarps * kC * 4 : 0) + 16;
   static size_t configured = 0;
   if (smem > 227 * 1024) {
     mls_set_error("bf16 attention kernel needs %zu bytes of shared memory for %d nodes (max 232448): use precision fp32", smem, ea.N);
