@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(kEdgeThreads) edge_bf16_kernel(const EdgeArgs 
   int* s_slot = s_deg + N;                                                       // [N]
   uint32_t* s_nbr = reinterpret_cast<uint32_t*>(s_slot + N);                     // [N][W]
   uint8_t* e_src = reinterpret_cast<uint8_t*>(s_nbr + (size_t)N * W);            // [emax]
-  float* poolbuf = reinterpret_cast<float*>(e_src + ((emax + 15) & ~15));        // [warps][kC], HL-DGN pooling only
+  float* poolbuf = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(e_src + emax) + 15) & ~(uintptr_t)15);   // [warps][kC], HL-DGN pooling only
   const int g = blockIdx.x / H, h = blockIdx.x - g * H;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const float* g_obs = a.obs + (int64_t)g * a.obs_stride;
@@ -496,7 +496,7 @@ template <int W, bool TR>
 int launch_edge(cudaStream_t st, const EdgeArgs& ea) {
   const size_t emax = (size_t)ea.N * kMaxDeg;
   const size_t smem = (size_t)ea.N * kLD * 4 * (TR ? 3 : 2) + (size_t)ea.N * 3 * 4 + ((size_t)ea.N * 3 + 1) * 4 +
-                      (size_t)ea.N * W * 4 + ((emax + 15) & ~(size_t)15) + (ea.pool_mode >= 0 ? kEdgeWarps * kC * 4 : 0) + 16;
+                      (size_t)ea.N * W * 4 + emax + 32 + (ea.pool_mode >= 0 ? kEdgeWarps * kC * 4 : 0);
   static size_t configured = 0;
   if (smem > 227 * 1024) {
     mls_set_error("bf16 attention kernel needs %zu bytes of shared memory for %d nodes (max 232448): use precision fp32", smem, ea.N);
