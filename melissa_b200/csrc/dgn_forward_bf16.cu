@@ -73,21 +73,58 @@ __global__ void enc0_bf16_kernel(const float* __restrict__ obs, int64_t obs_stri
   }
 }
 
-// ------------------------------------------------------------------------------ neighbour masks
-// radius_graph(pos, r=0.2, loop=False, max_num_neighbors=32) once per chunk: nbr[row][W] (bit j = edge j -> row)
+// ------------------------------------------------------------------------------ graph CSR
+// radius_graph(pos, r=0.2, loop=False, max_num_neighbors=32) once per chunk and graph, as source
+// lists per target: csr_ptr[g][N+1] (uint16 offsets into the graph's list), csr_src[g][N*32] (uint8
+// source node ids, index order).  Self loops are NOT stored (GATv2 adds its own).  The lists are
+// shared by all heads and by both conv layers.  One CTA per graph.
 template <int W>
-__global__ void nbr_mask_kernel(const float* __restrict__ obs, int64_t obs_stride, int N, int rows, uint32_t* __restrict__ nbr) {
-  const int lane = threadIdx.x & 31;
-  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (r >= rows) return;
-  const int g = r / N, i = r - g * N;
-  uint32_t nb[W];
-  radius_neighbours<W>(obs + (int64_t)g * obs_stride, N, i, lane, nb);
-  if (lane < W) {
-    uint32_t v = 0;
+__global__ void __launch_bounds__(256) graph_csr_kernel(const float* __restrict__ obs, int64_t obs_stride, int N, int n_graphs,
+                                                        uint16_t* __restrict__ csr_ptr, uint8_t* __restrict__ csr_src) {
+  extern __shared__ __align__(16) unsigned char csm[];
+  uint32_t* s_mask = reinterpret_cast<uint32_t*>(csm);      // [N][W]
+  int* s_ptr = reinterpret_cast<int*>(s_mask + (size_t)N * W);   // [N+1]
+  const int g = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* g_obs = obs + (int64_t)g * obs_stride;
+  for (int i = warp; i < N; i += 8) {
+    uint32_t nb[W];
+    radius_neighbours<W>(g_obs, N, i, lane, nb);
+    int deg = 0;
 #pragma unroll
-    for (int w = 0; w < W; ++w) if (w == lane) v = nb[w];
-    nbr[(size_t)r * W + lane] = v;
+    for (int w = 0; w < W; ++w) {
+      deg += __popc(nb[w]);
+      if (lane == w) s_mask[i * W + w] = nb[w];
+    }
+    if (lane == 0) s_ptr[i + 1] = deg;
+  }
+  __syncthreads();
+  if (warp == 0) {                                          // exclusive scan of the degrees
+    int run = 0;
+    for (int c0 = 0; c0 < N; c0 += 32) {
+      const int idx = c0 + lane;
+      int v = idx < N ? s_ptr[idx + 1] : 0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+      }
+      if (idx < N) s_ptr[idx + 1] = run + v;
+      run += __shfl_sync(0xffffffffu, v, 31);
+    }
+    if (lane == 0) s_ptr[0] = 0;
+  }
+  __syncthreads();
+  uint16_t* gp = csr_ptr + (size_t)g * (N + 1);
+  uint8_t* gs = csr_src + (size_t)g * N * kMaxNbr;
+  for (int t = threadIdx.x; t <= N; t += 256) gp[t] = (uint16_t)s_ptr[t];
+  for (int i = warp; i < N; i += 8) {
+    int off = s_ptr[i];
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+      const uint32_t m = s_mask[i * W + w];
+      if ((m >> lane) & 1u) gs[off + __popc(m & ((1u << lane) - 1u))] = (uint8_t)(w * 32 + lane);
+      off += __popc(m);
+    }
   }
 }
 
@@ -98,7 +135,9 @@ struct EdgeArgs {
   const float* obs;       // chunk base
   int64_t obs_stride;
   int N, H, n_graphs;
-  const uint32_t* nbr;    // [rows][W] neighbour masks
+  const uint16_t* csr_ptr; // [graphs][N+1]
+  const uint8_t* csr_src;  // [graphs][N*32]
+  const float* ab;        // GATv2: [rows][2H] = (<att_h, x_l[row,h]>, <att_h, x_r[row,h]>) from the projection GEMM
   const float* att;       // GATv2 [H*C]
   const float* bias;      // GATv2 [H*C]
   bf16* x_out;            // [rows, H*C] relu(conv) for every node, or NULL
@@ -111,13 +150,22 @@ struct EdgeArgs {
 
 constexpr int kEdgeThreads = 256, kEdgeWarps = 8;
 constexpr int kLD = kC;                 // staged row pitch in floats (a warp reads 4 x 128 B row segments = the 4-wavefront minimum)
-constexpr int kMaxDeg = kMaxNbr + 1;    // 32 neighbours + self loop
+
+__device__ __forceinline__ float fast_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fast_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 // One CTA per (graph, head).
-//   phase 0  stage the head's operands in shared memory as fp32 (converted once, not per edge)
-//   phase 1  CSR source lists per target from the neighbour masks (self loop for GATv2); per-node
-//            linear parts of the GATv2 logit
-//   phase 2  one warp per target, FOUR neighbours per round, EIGHT lanes per neighbour (16 channels
+//   phase 0  stage the head's operands in shared memory as fp32 (converted once, not per edge) together
+//            with the graph's CSR lists and the per-node scalars
+//   phase 1  one warp per target, FOUR neighbours per round, EIGHT lanes per neighbour (16 channels
 //            each): the target row lives in registers, every neighbour row is read from shared
 //            memory exactly once and serves both its logit and its contribution to the output
 //            (single-pass softmax in base 2: running max / denominator, same value as PyG's
@@ -125,23 +173,20 @@ constexpr int kMaxDeg = kMaxNbr + 1;    // 32 neighbours + self loop
 //            reduce-scatter (12 shuffles) so that lane l ends up owning channels 4l..4l+3.
 //              GATv2:       e_ij = 0.6 (a_j + b_i) + 0.4 sum_c att_c |x_l[j,c] + x_r[i,c]|   (leaky_relu(s,.2) = .6 s + .4 |s|)
 //              Transformer: e_ij = <q_i, k_j> / sqrt(C)
-template <int W, bool TRANSFORMER>
+template <bool TRANSFORMER>
 __global__ void __launch_bounds__(kEdgeThreads) edge_bf16_kernel(const EdgeArgs a) {
   extern __shared__ __align__(16) unsigned char esm[];
   const int N = a.N, H = a.H, HC = H * kC;
-  const int emax = N * kMaxDeg;
   float* stA = reinterpret_cast<float*>(esm);                                    // [N][kLD]  x_l or k   (source side)
-  float* stT = stA + (size_t)N * kLD;                                            // [N][kLD]  x_r or q   (target side)
-  float* stB = stT + (size_t)N * kLD;                                            // [N][kLD]  v (Transformer)
-  float* s_a = stB + (TRANSFORMER ? (size_t)N * kLD : 0);                        // [N] <att, x_l[j]>
-  float* s_b = s_a + N;                                                          // [N] <att, x_r[i]>
+  float* stT = stA + N * kLD;                                                    // [N][kLD]  x_r or q   (target side)
+  float* stB = stT + N * kLD;                                                    // [N][kLD]  v (Transformer)
+  float* s_a = stB + (TRANSFORMER ? N * kLD : 0);                                // [N] <att, x_l[j]> * 0.6 log2e
+  float* s_b = s_a + N;                                                          // [N] <att, x_r[i]> * 0.6 log2e
   float* s_dm = s_b + N;                                                         // [N]
-  int* row_ptr = reinterpret_cast<int*>(s_dm + N);                               // [N+1]
-  int* s_deg = row_ptr + N + 1;                                                  // [N]
-  int* s_slot = s_deg + N;                                                       // [N]
-  uint32_t* s_nbr = reinterpret_cast<uint32_t*>(s_slot + N);                     // [N][W]
-  uint8_t* e_src = reinterpret_cast<uint8_t*>(s_nbr + (size_t)N * W);            // [emax]
-  float* poolbuf = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(e_src + emax) + 15) & ~(uintptr_t)15);   // [warps][kC], HL-DGN pooling only
+  int* s_slot = reinterpret_cast<int*>(s_dm + N);                                // [N]
+  float* poolbuf = reinterpret_cast<float*>(s_slot + N);                         // [warps][kC]  (16 B aligned: 4N floats before it)
+  uint16_t* s_ptr = reinterpret_cast<uint16_t*>(poolbuf + (a.pool_mode >= 0 ? kEdgeWarps * kC : 0));   // [N+1]
+  uint8_t* s_src = reinterpret_cast<uint8_t*>(s_ptr + N + 1);                    // [E]
   const int g = blockIdx.x / H, h = blockIdx.x - g * H;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const float* g_obs = a.obs + (int64_t)g * a.obs_stride;
@@ -152,61 +197,28 @@ __global__ void __launch_bounds__(kEdgeThreads) edge_bf16_kernel(const EdgeArgs 
     const int src_col = TRANSFORMER ? HC + h * kC : h * kC;
     const int tgt_col = (TRANSFORMER ? 0 : HC) + h * kC;
     for (int t = tid; t < N * (kC / 4); t += kEdgeThreads) {
-      const int j = t / (kC / 4), q = t - j * (kC / 4);
+      const int j = t >> 5, q = t & 31;                     // kC / 4 == 32 float4 per row
       const bf16* row = a.P + (base + j) * a.ldp;
-      *reinterpret_cast<float4*>(stA + (size_t)j * kLD + q * 4) = ld_bf16x4(row + src_col + q * 4);
-      *reinterpret_cast<float4*>(stT + (size_t)j * kLD + q * 4) = ld_bf16x4(row + tgt_col + q * 4);
-      if (TRANSFORMER) *reinterpret_cast<float4*>(stB + (size_t)j * kLD + q * 4) = ld_bf16x4(row + 2 * HC + h * kC + q * 4);
+      *reinterpret_cast<float4*>(stA + j * kLD + q * 4) = ld_bf16x4(row + src_col + q * 4);
+      *reinterpret_cast<float4*>(stT + j * kLD + q * 4) = ld_bf16x4(row + tgt_col + q * 4);
+      if (TRANSFORMER) *reinterpret_cast<float4*>(stB + j * kLD + q * 4) = ld_bf16x4(row + 2 * HC + h * kC + q * 4);
     }
+    const uint16_t* gp = a.csr_ptr + (size_t)g * (N + 1);
+    const uint8_t* gs = a.csr_src + (size_t)g * N * kMaxNbr;
     for (int t = tid; t < N; t += kEdgeThreads) {
-      const int sl = a.slot ? a.slot[base + t] : -1;
-      s_slot[t] = sl;
+      s_slot[t] = a.slot ? a.slot[base + t] : -1;
       s_dm[t] = g_obs[t * 8 + 7];
-      int deg = 0;
-#pragma unroll
-      for (int w = 0; w < W; ++w) {
-        uint32_t m = a.nbr[(base + t) * W + w];
-        if (!TRANSFORMER && w == (t >> 5)) m |= 1u << (t & 31);                  // add_self_loops
-        if (a.ctrl_only && sl < 0) m = 0;                                        // nobody reads this target
-        s_nbr[t * W + w] = m;
-        deg += __popc(m);
+      if (!TRANSFORMER) {
+        s_a[t] = a.ab[(base + t) * (2 * H) + h] * (0.6f * kLog2e);
+        s_b[t] = a.ab[(base + t) * (2 * H) + H + h] * (0.6f * kLog2e);
       }
-      s_deg[t] = deg;
     }
+    for (int t = tid; t <= N; t += kEdgeThreads) s_ptr[t] = gp[t];
+    const int E = gp[N];
+    for (int t = tid; t < E; t += kEdgeThreads) s_src[t] = gs[t];
   }
-  __syncthreads();
-  // ---------------------------------------------------------------- phase 1
-  for (int t = tid; t <= N; t += kEdgeThreads) {
-    int acc = 0;
-    for (int k = 0; k < t; ++k) acc += s_deg[k];
-    row_ptr[t] = acc;
-  }
-  float4 att4 = make_float4(0.f, 0.f, 0.f, 0.f), bias4 = att4;
-  if (!TRANSFORMER) {
-    att4 = *reinterpret_cast<const float4*>(a.att + h * kC + lane * 4);
-    bias4 = *reinterpret_cast<const float4*>(a.bias + h * kC + lane * 4);
-  }
-  __syncthreads();
-  for (int i = warp; i < N; i += kEdgeWarps) {
-    int off = row_ptr[i];
-#pragma unroll
-    for (int w = 0; w < W; ++w) {
-      const uint32_t m = s_nbr[i * W + w];
-      const int c = __popc(m);
-      if (lane < c) e_src[off + lane] = (uint8_t)(w * 32 + __fns(m, 0, lane + 1));
-      off += c;
-    }
-    if (!TRANSFORMER) {                                     // per-node linear parts of the logit
-      const float4 xl = *reinterpret_cast<const float4*>(stA + (size_t)i * kLD + lane * 4);
-      const float4 xr = *reinterpret_cast<const float4*>(stT + (size_t)i * kLD + lane * 4);
-      float pa = xl.x * att4.x + xl.y * att4.y + xl.z * att4.z + xl.w * att4.w;
-      float pb = xr.x * att4.x + xr.y * att4.y + xr.z * att4.z + xr.w * att4.w;
-      pa = warp_sum(pa); pb = warp_sum(pb);
-      if (lane == 0) { s_a[i] = pa; s_b[i] = pb; }
-    }
-  }
-  __syncthreads();
-  // ---------------------------------------------------------------- phase 2
+  float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (!TRANSFORMER) bias4 = *reinterpret_cast<const float4*>(a.bias + h * kC + lane * 4);
   const int grp = lane >> 3, sub = lane & 7;                // neighbour slot of the round / channel slice
   float4 attn[4];
 #pragma unroll
@@ -218,31 +230,37 @@ __global__ void __launch_bounds__(kEdgeThreads) edge_bf16_kernel(const EdgeArgs 
       attn[it] = make_float4(v.x * sc, v.y * sc, v.z * sc, v.w * sc);
     }
   }
-  const float lin_scale = 0.6f * kLog2e, tr_scale = kLog2e / sqrtf((float)kC);
+  __syncthreads();
+  // ---------------------------------------------------------------- phase 1
+  const float tr_scale = kLog2e / sqrtf((float)kC);
   const float* stV = TRANSFORMER ? stB : stA;
+  const int self = TRANSFORMER ? 0 : 1;                     // GATv2: slot 0 of every target is its self loop
   float4 pool = a.pool_mode == MLS_POOL_MAX ? make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY)
                                             : make_float4(0.f, 0.f, 0.f, 0.f);
   for (int i = warp; i < N; i += kEdgeWarps) {
     const int sl = s_slot[i];
     if (a.ctrl_only && sl < 0) continue;
-    const int r0 = row_ptr[i], r1 = row_ptr[i + 1];         // warp uniform
+    const int r0 = s_ptr[i];
+    const int d = (int)s_ptr[i + 1] - r0 + self;            // warp uniform, <= 33
     float4 tr[4];
 #pragma unroll
-    for (int it = 0; it < 4; ++it) tr[it] = *reinterpret_cast<const float4*>(stT + (size_t)i * kLD + (it * 8 + sub) * 4);
+    for (int it = 0; it < 4; ++it) tr[it] = *reinterpret_cast<const float4*>(stT + i * kLD + (it * 8 + sub) * 4);
     const float b_i = TRANSFORMER ? 0.f : s_b[i];
     float mx = -INFINITY, den = 0.f;
     float4 acc[4];
 #pragma unroll
     for (int it = 0; it < 4; ++it) acc[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int kb = r0; kb < r1; kb += 4) {
+    for (int kb = 0; kb < d; kb += 4) {
       const int k = kb + grp;
-      const bool valid = k < r1;
-      const int j = valid ? (int)e_src[k] : i;
+      const bool valid = k < d;
+      int j = i;
+      if (valid && k >= self) j = s_src[r0 + k - self];
+      const float* xrow = stA + j * kLD + sub * 4;
       float4 x[4];
       float part = 0.f;
 #pragma unroll
       for (int it = 0; it < 4; ++it) {
-        x[it] = *reinterpret_cast<const float4*>(stA + (size_t)j * kLD + (it * 8 + sub) * 4);
+        x[it] = *reinterpret_cast<const float4*>(xrow + it * 32);
         if (TRANSFORMER) {
           part = fmaf(x[it].x, tr[it].x, part); part = fmaf(x[it].y, tr[it].y, part);
           part = fmaf(x[it].z, tr[it].z, part); part = fmaf(x[it].w, tr[it].w, part);
@@ -254,22 +272,23 @@ __global__ void __launch_bounds__(kEdgeThreads) edge_bf16_kernel(const EdgeArgs 
       part += __shfl_xor_sync(0xffffffffu, part, 1);
       part += __shfl_xor_sync(0xffffffffu, part, 2);
       part += __shfl_xor_sync(0xffffffffu, part, 4);        // all 8 lanes of the group hold the dot product
-      float e = TRANSFORMER ? part * tr_scale : fmaf(lin_scale, s_a[j] + b_i, part);
+      float e = TRANSFORMER ? part * tr_scale : part + (s_a[j] + b_i);
       if (!valid) e = -INFINITY;
       float m_r = fmaxf(e, __shfl_xor_sync(0xffffffffu, e, 8));
       m_r = fmaxf(m_r, __shfl_xor_sync(0xffffffffu, m_r, 16));
       if (m_r > mx) {                                       // warp uniform
-        const float resc = exp2f(mx - m_r);                 // first round: 2^-inf = 0
+        const float resc = fast_ex2(mx - m_r);              // first round: 2^-inf = 0
         den *= resc;
 #pragma unroll
         for (int it = 0; it < 4; ++it) { acc[it].x *= resc; acc[it].y *= resc; acc[it].z *= resc; acc[it].w *= resc; }
         mx = m_r;
       }
-      const float p = exp2f(e - mx);                        // 0 for padded slots
+      const float p = fast_ex2(e - mx);                     // 0 for padded slots
       den += p;                                             // per-group partial
       if (TRANSFORMER) {
+        const float* vrow = stV + j * kLD + sub * 4;
 #pragma unroll
-        for (int it = 0; it < 4; ++it) x[it] = *reinterpret_cast<const float4*>(stV + (size_t)j * kLD + (it * 8 + sub) * 4);
+        for (int it = 0; it < 4; ++it) x[it] = *reinterpret_cast<const float4*>(vrow + it * 32);
       }
 #pragma unroll
       for (int it = 0; it < 4; ++it) {
@@ -298,7 +317,7 @@ __global__ void __launch_bounds__(kEdgeThreads) edge_bf16_kernel(const EdgeArgs 
       mine.x = kp.x + __shfl_xor_sync(0xffffffffu, sd.x, 8); mine.y = kp.y + __shfl_xor_sync(0xffffffffu, sd.y, 8);
       mine.z = kp.z + __shfl_xor_sync(0xffffffffu, sd.z, 8); mine.w = kp.w + __shfl_xor_sync(0xffffffffu, sd.w, 8);
     }
-    const float inv_den = 1.0f / (den + 1e-16f);            // isolated Transformer node: acc = 0 -> output 0
+    const float inv_den = fast_rcp(den + 1e-16f);           // isolated Transformer node: acc = 0 -> output 0
     float4 o;
     o.x = fmaxf(fmaf(mine.x, inv_den, bias4.x), 0.f); o.y = fmaxf(fmaf(mine.y, inv_den, bias4.y), 0.f);
     o.z = fmaxf(fmaf(mine.z, inv_den, bias4.z), 0.f); o.w = fmaxf(fmaf(mine.w, inv_den, bias4.w), 0.f);
@@ -458,7 +477,9 @@ struct WsB {
   bf16 *h, *x0, *P, *x1, *z, *hid1, *hid2;
   float* qg;
   int *idx, *slot, *count;
-  uint32_t* nbr;
+  uint16_t* csr_ptr;
+  uint8_t* csr_src;
+  float *ab, *att1, *att2;
 };
 
 size_t carve_b(const MlsNetDesc* d, int Gc, unsigned char* base, WsB* ws) {
@@ -477,7 +498,8 @@ size_t carve_b(const MlsNetDesc* d, int Gc, unsigned char* base, WsB* ws) {
   const size_t o_h = take(R * hid * 2), o_x0 = take(R * hid * 2), o_P = take(R * nproj * HC * 2);
   const size_t o_x1 = take(hl ? 0 : R * HC * 2), o_z = take(T * latent * 2), o_h1 = take(T * hh2 * 2), o_h2 = take(T * hh2 * 2);
   const size_t o_qg = take((size_t)Gc * 8), o_idx = take(R * 4), o_slot = take(R * 4), o_cnt = take(4);
-  const size_t o_nbr = take(R * 8 * 4);
+  const size_t o_cptr = take(((size_t)Gc * (d->n_nodes + 1) + 64) * 2), o_csrc = take((size_t)Gc * d->n_nodes * kMaxNbr + 64);
+  const size_t o_ab = take(R * 2 * d->heads * 4), o_att1 = take((size_t)2 * HC * 4), o_att2 = take((size_t)2 * HC * 4);
   if (ws) {
     auto B = [&](size_t o) { return reinterpret_cast<bf16*>(base + o); };
     auto F = [&](size_t o) { return reinterpret_cast<float*>(base + o); };
@@ -487,46 +509,34 @@ size_t carve_b(const MlsNetDesc* d, int Gc, unsigned char* base, WsB* ws) {
     ws->qg = F(o_qg);
     ws->idx = reinterpret_cast<int*>(base + o_idx); ws->slot = reinterpret_cast<int*>(base + o_slot);
     ws->count = reinterpret_cast<int*>(base + o_cnt);
-    ws->nbr = reinterpret_cast<uint32_t*>(base + o_nbr);
+    ws->csr_ptr = reinterpret_cast<uint16_t*>(base + o_cptr); ws->csr_src = base + o_csrc;
+    ws->ab = F(o_ab); ws->att1 = F(o_att1); ws->att2 = F(o_att2);
   }
   return off;
 }
 
-template <int W, bool TR>
+template <bool TR>
 int launch_edge(cudaStream_t st, const EdgeArgs& ea) {
-  const size_t emax = (size_t)ea.N * kMaxDeg;
-  const size_t smem = (size_t)ea.N * kLD * 4 * (TR ? 3 : 2) + (size_t)ea.N * 3 * 4 + ((size_t)ea.N * 3 + 1) * 4 +
-                      (size_t)ea.N * W * 4 + emax + 32 + (ea.pool_mode >= 0 ? kEdgeWarps * kC * 4 : 0);
+  const size_t smem = (size_t)ea.N * kLD * 4 * (TR ? 3 : 2) + (size_t)ea.N * 4 * 4 + (ea.pool_mode >= 0 ? kEdgeWarps * kC * 4 : 0) +
+                      ((size_t)ea.N + 1) * 2 + (size_t)ea.N * kMaxNbr + 16;
   static size_t configured = 0;
   if (smem > 227 * 1024) {
     mls_set_error("bf16 attention kernel needs %zu bytes of shared memory for %d nodes (max 232448): use precision fp32", smem, ea.N);
     return MLS_ERR_UNSUPPORTED;
   }
   if (smem > 48 * 1024 && smem > configured) {
-    MLS_CUDA(cudaFuncSetAttribute(edge_bf16_kernel<W, TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MLS_CUDA(cudaFuncSetAttribute(edge_bf16_kernel<TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  edge_bf16_kernel<W, TR><<<ea.n_graphs * ea.H, kEdgeThreads, smem, st>>>(ea);
+  edge_bf16_kernel<TR><<<ea.n_graphs * ea.H, kEdgeThreads, smem, st>>>(ea);
   mls_count_launch();
   MLS_LAUNCH_CHECK();
   return MLS_OK;
 }
 
 int edge_dispatch(cudaStream_t st, const EdgeArgs& ea, bool tr, int Wn) {
-  if (tr) {
-    switch (Wn) {
-      case 1: return launch_edge<1, true>(st, ea);
-      case 2: return launch_edge<2, true>(st, ea);
-      case 4: return launch_edge<4, true>(st, ea);
-      default: return launch_edge<8, true>(st, ea);
-    }
-  }
-  switch (Wn) {
-    case 1: return launch_edge<1, false>(st, ea);
-    case 2: return launch_edge<2, false>(st, ea);
-    case 4: return launch_edge<4, false>(st, ea);
-    default: return launch_edge<8, false>(st, ea);
-  }
+  (void)Wn;
+  return tr ? launch_edge<true>(st, ea) : launch_edge<false>(st, ea);
 }
 
 }  // namespace
@@ -603,6 +613,7 @@ int dgn_forward_bf16(const MlsNetDesc* d, const MlsNetWeights* w, const MlsForwa
     auto addb = [&](const float* src, float* dst, int cnt) { bj.src[m] = src; bj.dst[m] = dst; bj.n[m] = cnt; ++m; };
     if (tr) { addb(w->c1_ba, ws.b_c1, HC); addb(w->c1_bb, ws.b_c1 + HC, HC); addb(w->c1_bc, ws.b_c1 + 2 * HC, HC); }
     else { addb(w->c1_ba, ws.b_c1, HC); addb(w->c1_bb, ws.b_c1 + HC, HC); }
+    if (!tr) { addb(w->c1_att, ws.att1, HC); addb(w->c1_att, ws.att1 + HC, HC); }
     addb(w->q_b0, ws.b_h0, hh); addb(w->v_b0, ws.b_h0 + hh, hh);
     addb(w->q_b1, ws.b_h1, hh); addb(w->v_b1, ws.b_h1 + hh, hh);
     bj.count = m;
@@ -612,6 +623,7 @@ int dgn_forward_bf16(const MlsNetDesc* d, const MlsNetWeights* w, const MlsForwa
       m = 0;
       auto addc = [&](const float* src, float* dst, int cnt) { b2.src[m] = src; b2.dst[m] = dst; b2.n[m] = cnt; ++m; };
       addc(w->c2_ba, ws.b_c2, HC); addc(w->c2_bb, ws.b_c2 + HC, HC);
+      if (!tr) { addc(w->c2_att, ws.att2, HC); addc(w->c2_att, ws.att2 + HC, HC); }
       if (tr) addc(w->c2_bc, ws.b_c2 + 2 * HC, HC);
       b2.count = m;
       cat_bias_kernel<<<dim3(2, m), 256, 0, st>>>(b2);
@@ -637,11 +649,14 @@ int dgn_forward_bf16(const MlsNetDesc* d, const MlsNetWeights* w, const MlsForwa
       ctrl_list_slot_kernel<<<(gc * 32 + 255) / 256, 256, 0, st>>>(cm, obs, a->obs_stride, N, gc, a->ctrl_mode, ws.idx, ws.slot, ws.count);
       mls_count_launch();
     }
-    switch (Wn) {
-      case 1: nbr_mask_kernel<1><<<(rows * 32 + 255) / 256, 256, 0, st>>>(obs, a->obs_stride, N, rows, ws.nbr); break;
-      case 2: nbr_mask_kernel<2><<<(rows * 32 + 255) / 256, 256, 0, st>>>(obs, a->obs_stride, N, rows, ws.nbr); break;
-      case 4: nbr_mask_kernel<4><<<(rows * 32 + 255) / 256, 256, 0, st>>>(obs, a->obs_stride, N, rows, ws.nbr); break;
-      default: nbr_mask_kernel<8><<<(rows * 32 + 255) / 256, 256, 0, st>>>(obs, a->obs_stride, N, rows, ws.nbr); break;
+    {
+      const size_t csm = (size_t)N * Wn * 4 + ((size_t)N + 1) * 4;
+      switch (Wn) {
+        case 1: graph_csr_kernel<1><<<gc, 256, csm, st>>>(obs, a->obs_stride, N, gc, ws.csr_ptr, ws.csr_src); break;
+        case 2: graph_csr_kernel<2><<<gc, 256, csm, st>>>(obs, a->obs_stride, N, gc, ws.csr_ptr, ws.csr_src); break;
+        case 4: graph_csr_kernel<4><<<gc, 256, csm, st>>>(obs, a->obs_stride, N, gc, ws.csr_ptr, ws.csr_src); break;
+        default: graph_csr_kernel<8><<<gc, 256, csm, st>>>(obs, a->obs_stride, N, gc, ws.csr_ptr, ws.csr_src); break;
+      }
     }
     mls_count_launch();
     // encoder
@@ -649,12 +664,12 @@ int dgn_forward_bf16(const MlsNetDesc* d, const MlsNetWeights* w, const MlsForwa
       dim3 blk(32, 8);
       enc0_bf16_kernel<<<(rows + 7) / 8, blk, 0, st>>>(obs, a->obs_stride, N, rows, d->input_dim, w->enc_w0, w->enc_b0, hid, ws.h);
       mls_count_launch();
-      GemmEpilogue e{ws.x0, hid, w->enc_b1, nullptr, 0, N, 1};
+      GemmEpilogue e{ws.x0, hid, w->enc_b1, nullptr, 0, N, 1, nullptr, nullptr};
       if ((rc = gemm_bf16_launch(ws.h, hid, ws.w_enc1, hid, GemmShape{rows, hid, hid, nullptr}, e, sms, st))) return rc;
     }
     // conv1 projections
     {
-      GemmEpilogue e{ws.P, nproj * HC, ws.b_c1, nullptr, 0, N, 0};
+      GemmEpilogue e{ws.P, nproj * HC, ws.b_c1, nullptr, 0, N, 0, tr ? nullptr : ws.att1, tr ? nullptr : ws.ab};
       prof_begin(MLS_PROF_PROJ1);
       if ((rc = gemm_bf16_launch(ws.x0, hid, ws.w_c1, hid, GemmShape{rows, nproj * HC, hid, nullptr}, e, sms, st))) return rc;
       prof_end(MLS_PROF_PROJ1);
@@ -663,7 +678,7 @@ int dgn_forward_bf16(const MlsNetDesc* d, const MlsNetWeights* w, const MlsForwa
     {
       EdgeArgs ea{};
       ea.P = ws.P; ea.ldp = nproj * HC; ea.obs = obs; ea.obs_stride = a->obs_stride; ea.N = N; ea.H = H; ea.n_graphs = gc;
-      ea.att = w->c1_att; ea.bias = w->c1_bias; ea.nbr = ws.nbr;
+      ea.att = w->c1_att; ea.bias = w->c1_bias; ea.csr_ptr = ws.csr_ptr; ea.csr_src = ws.csr_src; ea.ab = ws.ab;
       if (hl) { ea.x_out = nullptr; ea.slot = nullptr; ea.z = ws.z; ea.ldz = latent; ea.z_col = 0; ea.ctrl_only = 0; ea.pool_mode = d->pool; }
       else { ea.x_out = ws.x1; ea.slot = ws.slot; ea.z = ws.z; ea.ldz = latent; ea.z_col = hid; ea.ctrl_only = 0; ea.pool_mode = -1; }
       prof_begin(MLS_PROF_EDGE1);
@@ -672,14 +687,14 @@ int dgn_forward_bf16(const MlsNetDesc* d, const MlsNetWeights* w, const MlsForwa
     }
     if (!hl) {
       // conv2 projections on x1 * dm: the row mask commutes with the GEMM, applied in its epilogue
-      GemmEpilogue e{ws.P, nproj * HC, ws.b_c2, obs, a->obs_stride, N, 0};
+      GemmEpilogue e{ws.P, nproj * HC, ws.b_c2, obs, a->obs_stride, N, 0, tr ? nullptr : ws.att2, tr ? nullptr : ws.ab};
       prof_begin(MLS_PROF_PROJ2);
       if ((rc = gemm_bf16_launch(ws.x1, HC, ws.w_c2, HC, GemmShape{rows, nproj * HC, HC, nullptr}, e, sms, st))) return rc;
       prof_end(MLS_PROF_PROJ2);
       // conv2 attention only where a controlling agent needs it; result goes straight into z
       EdgeArgs ea{};
       ea.P = ws.P; ea.ldp = nproj * HC; ea.obs = obs; ea.obs_stride = a->obs_stride; ea.N = N; ea.H = H; ea.n_graphs = gc;
-      ea.att = w->c2_att; ea.bias = w->c2_bias; ea.nbr = ws.nbr; ea.x_out = nullptr; ea.slot = ws.slot; ea.z = ws.z; ea.ldz = latent;
+      ea.att = w->c2_att; ea.bias = w->c2_bias; ea.csr_ptr = ws.csr_ptr; ea.csr_src = ws.csr_src; ea.ab = ws.ab; ea.x_out = nullptr; ea.slot = ws.slot; ea.z = ws.z; ea.ldz = latent;
       ea.z_col = hid + HC; ea.ctrl_only = 1; ea.pool_mode = -1;
       prof_begin(MLS_PROF_EDGE2);
       if ((rc = edge_dispatch(st, ea, tr, Wn))) return rc;
@@ -692,11 +707,11 @@ int dgn_forward_bf16(const MlsNetDesc* d, const MlsNetWeights* w, const MlsForwa
     const int head_rows = hl ? gc : rows;
     const int* m_dev = hl ? nullptr : ws.count;
     {
-      GemmEpilogue e0{ws.hid1, hh2, ws.b_h0, nullptr, 0, N, 1};
+      GemmEpilogue e0{ws.hid1, hh2, ws.b_h0, nullptr, 0, N, 1, nullptr, nullptr};
       prof_begin(MLS_PROF_HEAD0);
       if ((rc = gemm_bf16_launch(ws.z, latent, ws.w_h0, latent, GemmShape{head_rows, hh2, latent, m_dev}, e0, sms, st))) return rc;
       prof_end(MLS_PROF_HEAD0);
-      GemmEpilogue e1{ws.hid2, hh2, ws.b_h1, nullptr, 0, N, 1};
+      GemmEpilogue e1{ws.hid2, hh2, ws.b_h1, nullptr, 0, N, 1, nullptr, nullptr};
       if ((rc = gemm_bf16_launch(ws.hid1, hh2, ws.w_h1, hh2, GemmShape{head_rows, hh2, hh2, m_dev}, e1, sms, st))) return rc;
     }
     if (!hl) {

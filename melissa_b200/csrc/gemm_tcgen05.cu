@@ -98,7 +98,8 @@ struct GemmSmem {
   static constexpr int kOutWarpBytes = 32 * kOutRowBytes;
   static constexpr int kOutOffset = kNumStages * kStageBytes;
   static constexpr int kBiasOffset = kOutOffset + 4 * kOutWarpBytes;      // BN floats
-  static constexpr int kBarOffset = kBiasOffset + BN * 4;
+  static constexpr int kDotOffset = kBiasOffset + BN * 4;                 // BN floats
+  static constexpr int kBarOffset = kDotOffset + BN * 4;
   static constexpr int kTotal = kBarOffset + 256 + 1024;   // barriers + alignment slack
 };
 
@@ -192,6 +193,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     const int ew = warp - 4;                                // == warp % 4: the TMEM lane quarter this warp may read
     unsigned char* stage_out = smem + S::kOutOffset + ew * S::kOutWarpBytes;
     float* bias_s = reinterpret_cast<float*>(smem + S::kBiasOffset);
+    float* dot_s = reinterpret_cast<float*>(smem + S::kDotOffset);
     const int et = threadIdx.x - 128;                       // 0..127 within the epilogue warps
     int it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
@@ -206,10 +208,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       }
       // bias slice of this tile -> smem (all four epilogue warps; named barrier 1 keeps the other warps out of it)
       asm volatile("bar.sync 1, 128;" ::: "memory");        // previous tile's readers are done with bias_s
-      for (int c = et; c < BN; c += 128) bias_s[c] = epi.bias ? __ldg(epi.bias + n0 + c) : 0.0f;
+      for (int c = et; c < BN; c += 128) {
+        bias_s[c] = epi.bias ? __ldg(epi.bias + n0 + c) : 0.0f;
+        if (epi.dotvec) dot_s[c] = __ldg(epi.dotvec + n0 + c);
+      }
       asm volatile("bar.sync 1, 128;" ::: "memory");
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
+      float dot = 0.f;
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t v[32];
@@ -220,6 +226,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c0 + j);
           float x0 = fmaf(__uint_as_float(v[j]), scale, b4.x), x1 = fmaf(__uint_as_float(v[j + 1]), scale, b4.y);
           float x2 = fmaf(__uint_as_float(v[j + 2]), scale, b4.z), x3 = fmaf(__uint_as_float(v[j + 3]), scale, b4.w);
+          if (epi.dotvec) {
+            const float4 d4 = *reinterpret_cast<const float4*>(dot_s + c0 + j);
+            dot = fmaf(x0, d4.x, dot); dot = fmaf(x1, d4.y, dot); dot = fmaf(x2, d4.z, dot); dot = fmaf(x3, d4.w, dot);
+          }
           if (epi.relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f); }
           __nv_bfloat162 p0 = __floats2bfloat162_rn(x0, x1), p1 = __floats2bfloat162_rn(x2, x3);
           packed[j >> 1] = *reinterpret_cast<uint32_t*>(&p0);
@@ -228,6 +238,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         uint4* dst = reinterpret_cast<uint4*>(stage_out + lane * S::kOutRowBytes + c0 * 2);
 #pragma unroll
         for (int q = 0; q < 4; ++q) dst[q] = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+        if (epi.dotvec && (c0 & 96) == 96) {                 // end of a 128-column group
+          if (r < M) epi.dots[(size_t)r * (shape.N >> 7) + ((n0 + c0) >> 7)] = dot;
+          dot = 0.f;
+        }
       }
       // accumulator drained: hand it back to the MMA warp before the global stores
       tc_fence_before();
@@ -325,7 +339,7 @@ extern "C" int mls_test_gemm_bf16(const void* A, const void* B, const float* bia
   MLS_CUDA(cudaGetDevice(&dev));
   MLS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   mls::GemmShape shape{M, N, K, m_dev};
-  mls::GemmEpilogue epi{reinterpret_cast<__nv_bfloat16*>(C), N, bias, obs, obs_stride, nodes, relu};
+  mls::GemmEpilogue epi{reinterpret_cast<__nv_bfloat16*>(C), N, bias, obs, obs_stride, nodes, relu, nullptr, nullptr};
   return mls::gemm_bf16_launch(reinterpret_cast<const __nv_bfloat16*>(A), K, reinterpret_cast<const __nv_bfloat16*>(B), K, shape,
                                epi, sms, reinterpret_cast<cudaStream_t>(stream));
 }

@@ -24,6 +24,10 @@ struct GemmEpilogue {
   long long obs_stride;
   int nodes;
   int relu;
+  // optional: dots[m][n / 128] = sum over the 128-column group of dotvec[n] * (value before bf16 rounding / ReLU).
+  // Used for the per-node linear part of the GATv2 logits (<att_h, x_l[j,h,:]>, <att_h, x_r[i,h,:]>).
+  const float* dotvec;   // [N] or NULL
+  float* dots;           // [M, N / 128]
 };
 
 struct GemmShape {
