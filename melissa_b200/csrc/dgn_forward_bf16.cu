@@ -174,7 +174,7 @@ __device__ __forceinline__ float fast_rcp(float x) {
 //              GATv2:       e_ij = 0.6 (a_j + b_i) + 0.4 sum_c att_c |x_l[j,c] + x_r[i,c]|   (leaky_relu(s,.2) = .6 s + .4 |s|)
 //              Transformer: e_ij = <q_i, k_j> / sqrt(C)
 template <bool TRANSFORMER>
-__global__ void __launch_bounds__(kEdgeThreads) edge_bf16_kernel(const EdgeArgs a) {
+__global__ void __launch_bounds__(kEdgeThreads, 3) edge_bf16_kernel(const EdgeArgs a) {
   extern __shared__ __align__(16) unsigned char esm[];
   const int N = a.N, H = a.H, HC = H * kC;
   float* stA = reinterpret_cast<float*>(esm);                                    // [N][kLD]  x_l or k   (source side)
@@ -242,9 +242,7 @@ __global__ void __launch_bounds__(kEdgeThreads) edge_bf16_kernel(const EdgeArgs 
     if (a.ctrl_only && sl < 0) continue;
     const int r0 = s_ptr[i];
     const int d = (int)s_ptr[i + 1] - r0 + self;            // warp uniform, <= 33
-    float4 tr[4];
-#pragma unroll
-    for (int it = 0; it < 4; ++it) tr[it] = *reinterpret_cast<const float4*>(stT + i * kLD + (it * 8 + sub) * 4);
+    const float* trow = stT + i * kLD + sub * 4;           // target row, re-read per round (multicast, 1 wavefront) to save 16 registers
     const float b_i = TRANSFORMER ? 0.f : s_b[i];
     float mx = -INFINITY, den = 0.f;
     float4 acc[4];
@@ -261,12 +259,13 @@ __global__ void __launch_bounds__(kEdgeThreads) edge_bf16_kernel(const EdgeArgs 
 #pragma unroll
       for (int it = 0; it < 4; ++it) {
         x[it] = *reinterpret_cast<const float4*>(xrow + it * 32);
+        const float4 t4 = *reinterpret_cast<const float4*>(trow + it * 32);
         if (TRANSFORMER) {
-          part = fmaf(x[it].x, tr[it].x, part); part = fmaf(x[it].y, tr[it].y, part);
-          part = fmaf(x[it].z, tr[it].z, part); part = fmaf(x[it].w, tr[it].w, part);
+          part = fmaf(x[it].x, t4.x, part); part = fmaf(x[it].y, t4.y, part);
+          part = fmaf(x[it].z, t4.z, part); part = fmaf(x[it].w, t4.w, part);
         } else {
-          part = fmaf(attn[it].x, fabsf(x[it].x + tr[it].x), part); part = fmaf(attn[it].y, fabsf(x[it].y + tr[it].y), part);
-          part = fmaf(attn[it].z, fabsf(x[it].z + tr[it].z), part); part = fmaf(attn[it].w, fabsf(x[it].w + tr[it].w), part);
+          part = fmaf(attn[it].x, fabsf(x[it].x + t4.x), part); part = fmaf(attn[it].y, fabsf(x[it].y + t4.y), part);
+          part = fmaf(attn[it].z, fabsf(x[it].z + t4.z), part); part = fmaf(attn[it].w, fabsf(x[it].w + t4.w), part);
         }
       }
       part += __shfl_xor_sync(0xffffffffu, part, 1);
@@ -524,8 +523,11 @@ int launch_edge(cudaStream_t st, const EdgeArgs& ea) {
     mls_set_error("bf16 attention kernel needs %zu bytes of shared memory for %d nodes (max 232448): use precision fp32", smem, ea.N);
     return MLS_ERR_UNSUPPORTED;
   }
-  if (smem > 48 * 1024 && smem > configured) {
-    MLS_CUDA(cudaFuncSetAttribute(edge_bf16_kernel<TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (smem > configured) {
+    if (smem > 48 * 1024)
+      MLS_CUDA(cudaFuncSetAttribute(edge_bf16_kernel<TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // ask for the largest shared-memory carveout: the default split only fits 2 of these CTAs per SM
+    MLS_CUDA(cudaFuncSetAttribute(edge_bf16_kernel<TR>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     configured = smem;
   }
   edge_bf16_kernel<TR><<<ea.n_graphs * ea.H, kEdgeThreads, smem, st>>>(ea);
