@@ -174,7 +174,7 @@ __device__ __forceinline__ float fast_rcp(float x) {
 //              GATv2:       e_ij = 0.6 (a_j + b_i) + 0.4 sum_c att_c |x_l[j,c] + x_r[i,c]|   (leaky_relu(s,.2) = .6 s + .4 |s|)
 //              Transformer: e_ij = <q_i, k_j> / sqrt(C)
 template <bool TRANSFORMER>
-__global__ void __launch_bounds__(kEdgeThreads, 3) edge_bf16_kernel(const EdgeArgs a) {
+__global__ void __launch_bounds__(kEdgeThreads, 2) edge_bf16_kernel(const EdgeArgs a) {
   extern __shared__ __align__(16) unsigned char esm[];
   const int N = a.N, H = a.H, HC = H * kC;
   float* stA = reinterpret_cast<float*>(esm);                                    // [N][kLD]  x_l or k   (source side)
@@ -248,51 +248,64 @@ __global__ void __launch_bounds__(kEdgeThreads, 3) edge_bf16_kernel(const EdgeAr
     float4 acc[4];
 #pragma unroll
     for (int it = 0; it < 4; ++it) acc[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int kb = 0; kb < d; kb += 4) {
-      const int k = kb + grp;
-      const bool valid = k < d;
-      int j = i;
-      if (valid && k >= self) j = s_src[r0 + k - self];
-      const float* xrow = stA + j * kLD + sub * 4;
-      float4 x[4];
-      float part = 0.f;
+    for (int kb = 0; kb < d; kb += 8) {                     // up to 8 neighbours per pass: two independent chains
+      const int k0 = kb + grp, k1 = kb + 4 + grp;
+      const bool v0 = k0 < d, v1 = k1 < d;
+      int j0 = i, j1 = i;
+      if (v0 && k0 >= self) j0 = s_src[r0 + k0 - self];
+      if (v1) j1 = s_src[r0 + k1 - self];                   // k1 >= 4 > self
+      const float* xr0 = stA + j0 * kLD + sub * 4;
+      const float* xr1 = stA + j1 * kLD + sub * 4;
+      float4 x0[4], x1[4];
+      float pa0 = 0.f, pb0 = 0.f, pa1 = 0.f, pb1 = 0.f;     // two partial sums per chain: shorter FFMA dependency
 #pragma unroll
       for (int it = 0; it < 4; ++it) {
-        x[it] = *reinterpret_cast<const float4*>(xrow + it * 32);
+        x0[it] = *reinterpret_cast<const float4*>(xr0 + it * 32);
+        x1[it] = *reinterpret_cast<const float4*>(xr1 + it * 32);
         const float4 t4 = *reinterpret_cast<const float4*>(trow + it * 32);
         if (TRANSFORMER) {
-          part = fmaf(x[it].x, t4.x, part); part = fmaf(x[it].y, t4.y, part);
-          part = fmaf(x[it].z, t4.z, part); part = fmaf(x[it].w, t4.w, part);
+          pa0 = fmaf(x0[it].x, t4.x, pa0); pb0 = fmaf(x0[it].y, t4.y, pb0); pa0 = fmaf(x0[it].z, t4.z, pa0); pb0 = fmaf(x0[it].w, t4.w, pb0);
+          pa1 = fmaf(x1[it].x, t4.x, pa1); pb1 = fmaf(x1[it].y, t4.y, pb1); pa1 = fmaf(x1[it].z, t4.z, pa1); pb1 = fmaf(x1[it].w, t4.w, pb1);
         } else {
-          part = fmaf(attn[it].x, fabsf(x[it].x + t4.x), part); part = fmaf(attn[it].y, fabsf(x[it].y + t4.y), part);
-          part = fmaf(attn[it].z, fabsf(x[it].z + t4.z), part); part = fmaf(attn[it].w, fabsf(x[it].w + t4.w), part);
+          pa0 = fmaf(attn[it].x, fabsf(x0[it].x + t4.x), pa0); pb0 = fmaf(attn[it].y, fabsf(x0[it].y + t4.y), pb0);
+          pa0 = fmaf(attn[it].z, fabsf(x0[it].z + t4.z), pa0); pb0 = fmaf(attn[it].w, fabsf(x0[it].w + t4.w), pb0);
+          pa1 = fmaf(attn[it].x, fabsf(x1[it].x + t4.x), pa1); pb1 = fmaf(attn[it].y, fabsf(x1[it].y + t4.y), pb1);
+          pa1 = fmaf(attn[it].z, fabsf(x1[it].z + t4.z), pa1); pb1 = fmaf(attn[it].w, fabsf(x1[it].w + t4.w), pb1);
         }
       }
-      part += __shfl_xor_sync(0xffffffffu, part, 1);
-      part += __shfl_xor_sync(0xffffffffu, part, 2);
-      part += __shfl_xor_sync(0xffffffffu, part, 4);        // all 8 lanes of the group hold the dot product
-      float e = TRANSFORMER ? part * tr_scale : part + (s_a[j] + b_i);
-      if (!valid) e = -INFINITY;
-      float m_r = fmaxf(e, __shfl_xor_sync(0xffffffffu, e, 8));
+      float e0 = pa0 + pb0, e1 = pa1 + pb1;
+      e0 += __shfl_xor_sync(0xffffffffu, e0, 1); e1 += __shfl_xor_sync(0xffffffffu, e1, 1);
+      e0 += __shfl_xor_sync(0xffffffffu, e0, 2); e1 += __shfl_xor_sync(0xffffffffu, e1, 2);
+      e0 += __shfl_xor_sync(0xffffffffu, e0, 4); e1 += __shfl_xor_sync(0xffffffffu, e1, 4);
+      e0 = TRANSFORMER ? e0 * tr_scale : e0 + (s_a[j0] + b_i);
+      e1 = TRANSFORMER ? e1 * tr_scale : e1 + (s_a[j1] + b_i);
+      if (!v0) e0 = -INFINITY;
+      if (!v1) e1 = -INFINITY;
+      float m_r = fmaxf(e0, e1);
+      m_r = fmaxf(m_r, __shfl_xor_sync(0xffffffffu, m_r, 8));
       m_r = fmaxf(m_r, __shfl_xor_sync(0xffffffffu, m_r, 16));
-      if (m_r > mx) {                                       // warp uniform
-        const float resc = fast_ex2(mx - m_r);              // first round: 2^-inf = 0
+      if (kb > 0 && m_r > mx) {                             // only targets with more than 8 entries get here (warp uniform)
+        const float resc = fast_ex2(mx - m_r);
         den *= resc;
 #pragma unroll
         for (int it = 0; it < 4; ++it) { acc[it].x *= resc; acc[it].y *= resc; acc[it].z *= resc; acc[it].w *= resc; }
-        mx = m_r;
       }
-      const float p = fast_ex2(e - mx);                     // 0 for padded slots
-      den += p;                                             // per-group partial
+      mx = fmaxf(mx, m_r);
+      const float p0 = fast_ex2(e0 - mx), p1 = fast_ex2(e1 - mx);   // 0 for padded slots
+      den += p0 + p1;                                       // per-group partial
       if (TRANSFORMER) {
-        const float* vrow = stV + j * kLD + sub * 4;
+        const float* vr0 = stV + j0 * kLD + sub * 4;
+        const float* vr1 = stV + j1 * kLD + sub * 4;
 #pragma unroll
-        for (int it = 0; it < 4; ++it) x[it] = *reinterpret_cast<const float4*>(vrow + it * 32);
+        for (int it = 0; it < 4; ++it) {
+          x0[it] = *reinterpret_cast<const float4*>(vr0 + it * 32);
+          x1[it] = *reinterpret_cast<const float4*>(vr1 + it * 32);
+        }
       }
 #pragma unroll
       for (int it = 0; it < 4; ++it) {
-        acc[it].x = fmaf(p, x[it].x, acc[it].x); acc[it].y = fmaf(p, x[it].y, acc[it].y);
-        acc[it].z = fmaf(p, x[it].z, acc[it].z); acc[it].w = fmaf(p, x[it].w, acc[it].w);
+        acc[it].x = fmaf(p1, x1[it].x, fmaf(p0, x0[it].x, acc[it].x)); acc[it].y = fmaf(p1, x1[it].y, fmaf(p0, x0[it].y, acc[it].y));
+        acc[it].z = fmaf(p1, x1[it].z, fmaf(p0, x0[it].z, acc[it].z)); acc[it].w = fmaf(p1, x1[it].w, fmaf(p0, x0[it].w, acc[it].w));
       }
     }
     // combine the four lane groups: reduce-scatter so that group g keeps float4 slice it == g,
