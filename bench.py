@@ -213,7 +213,8 @@ def run_ours(args):
             ro.round()
         sync_all()
 
-    prof_name = args.prof_kernel or ("proj2" if args.model in ("l_dgn", "dgn_r") else "proj1")
+    prof_name = args.prof_kernel or ("edge1" if args.precision == "bf16" else ("proj2" if args.model in ("l_dgn", "dgn_r") else "proj1"))
+    gemm_name = "proj2" if args.model in ("l_dgn", "dgn_r") else "proj1"
     pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
     def timed(fn, steps, with_prof=False):
@@ -243,16 +244,24 @@ def run_ours(args):
     ms, trans, launches, _, _ = timed(ro.round, args.steps)
     clk = clocks.stop() if rank == 0 else None
     launches_per_step = None
-    # ---- phase 2: same rounds launched eagerly with an event pair around the dominant kernel
-    prof_ms, eager_ms = [], None
+    # ---- phase 2: same rounds launched eagerly with an event pair around one launch per step of
+    #      (a) the attention kernel of conv1 -- the kernel with the largest share of the step -- and
+    #      (b) the conv2 projection GEMM (the tensor-core kernel)
+    prof_ms, prof_ms_gemm, eager_ms = [], [], None
     if net is not None:
         prepare(False)
         net.set_profile_events(prof_name, pe0, pe1)
         eager_ms, _, launches_eager, prof_ms, _ = timed(ro.round, args.steps, with_prof=True)
-        net.set_profile_events(None)
         launches_per_step = launches_eager / args.steps
         if use_graph:
             launches = launches_eager          # a graph replay launches the same kernels; they are counted at capture
+        if prof_name != gemm_name:
+            prepare(False)
+            net.set_profile_events(gemm_name, pe0, pe1)
+            _, _, _, prof_ms_gemm, _ = timed(ro.round, args.steps, with_prof=True)
+        else:
+            prof_ms_gemm = prof_ms
+        net.set_profile_events(None)
     # env kernel alone (HBM roofline of the environment round)
     env_evs = []
     for s in range(min(args.steps, 10)):
@@ -293,25 +302,49 @@ def run_ours(args):
         A = trans / (steps * B)                                   # mean active agents per graph-round (this rank)
         deg = float(pool.adj.sum()) / len(pool)                   # directed edges per graph
         flops_round = algorithmic_flops(args.model, N, deg + N, A)
-        # dominant kernel: projection GEMM launch that was bracketed with events (first chunk of every forward)
+        # kernels bracketed with events (first chunk of every forward)
         HC, hid = 512, 128
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
+        # (profiles/r01_traffic.json), valid for the default workload only
+        traffic = {}
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+            if tj.get("model") == args.model and tj.get("episodes") == B and tj.get("nodes") == N and tj.get("precision") == args.precision:
+                traffic = tj.get("traffic", {})
+        except (OSError, ValueError):
+            pass
         import ctypes
-        chunk_rows = (_lib.lib().mls_dgn_chunk_graphs(ctypes.byref(net._desc()), B) if net is not None else B) * N
-        K = HC if prof_name == "proj2" else hid
+        chunk_graphs = _lib.lib().mls_dgn_chunk_graphs(ctypes.byref(net._desc()), B) if net is not None else B
+        chunk_rows = chunk_graphs * N
         nproj = 3 if args.model == "dgn_r" else 2
         n_out = HC if args.precision == "fp32" else nproj * HC     # bf16: all projections of a conv in one GEMM
-        kern_flops = 2.0 * chunk_rows * n_out * K
+        gk = HC if gemm_name == "proj2" else hid
+        gemm_flops = 2.0 * chunk_rows * n_out * gk
+        gemm_ms = float(np.mean(prof_ms_gemm)) if prof_ms_gemm else None
+        roof_gemm = None
+        if gemm_ms:
+            ach = gemm_flops / (gemm_ms * 1e-3) / 1e12
+            roof_gemm = {"kernel": f"{args.precision} projection GEMM ({gemm_name}, [{chunk_rows}x{gk}]x[{gk}x{n_out}])",
+                         "bound": "tensor", "achieved": round(ach, 3), "peak": tensor_peak, "unit": "TFLOP/s",
+                         "frac": round(ach / tensor_peak, 5), "traffic": traffic.get(gemm_name),
+                         "peak_source": f"{peak_src} (sustained bf16)", "kernel_ms": round(gemm_ms, 5), "launch_flops": gemm_flops}
+        roofline = roof_gemm
         kern_ms = float(np.mean(prof_ms)) if prof_ms else None
-        roofline = None
-        if kern_ms:
-            ach = kern_flops / (kern_ms * 1e-3) / 1e12
-            roofline = {"kernel": f"{args.precision} projection GEMM ({prof_name}, [{chunk_rows}x{K}]x[{K}x{n_out}])",
-                        "bound": "tensor", "achieved": round(ach, 3), "peak": tensor_peak, "unit": "TFLOP/s",
-                        "frac": round(ach / tensor_peak, 5), "traffic": None, "peak_source": f"{peak_src} (sustained bf16)",
-                        "kernel_ms": round(kern_ms, 5), "launch_flops": kern_flops}
+        if kern_ms and prof_name.startswith("edge"):
+            # attention kernel: reads the projection rows once (nproj*HC bf16), writes relu(conv) (HC bf16),
+            # reads the CSR lists (~(E + 2N) bytes per graph and head) and the per-node scalars
+            esz = 2
+            row_bytes = nproj * HC * esz + (HC * esz if args.model != "hl_dgn" else 0) + (8 * 4 if args.model != "dgn_r" else 0)
+            csr_bytes = 4 * (deg + 2 * (N + 1))
+            edge_bytes = chunk_rows * row_bytes + chunk_graphs * csr_bytes
+            ach = edge_bytes / (kern_ms * 1e-3) / 1e9
+            roofline = {"kernel": f"edge_bf16_kernel ({prof_name}: attention conv over {chunk_graphs} graphs x 4 heads)",
+                        "bound": "hbm", "achieved": round(ach, 1), "peak": hbm_peak, "unit": "GB/s", "frac": round(ach / hbm_peak, 4),
+                        "traffic": traffic.get(prof_name), "peak_source": peak_src, "kernel_ms": round(kern_ms, 5), "launch_bytes": int(edge_bytes),
+                        "note": "largest share of the step; SIMT issue/latency bound (ncu: profiles/), not bandwidth bound"}
         W = _lib.words_per_row(N)
         env_bytes = B * (N * (4 * W + 4 + 4 + 2 + 2 + 1 + 32 + 8 + 1 + 1) + 8 * 4 + 8 + 1)   # adj+pos(pool, L2) not counted
-        env_roof = {"kernel": "env_round_kernel", "bound": "hbm", "achieved": round(env_bytes / (env_ms * 1e-3) / 1e9, 1),
+        env_roof = {"kernel": "env_round_kernel", "bound": "hbm", "traffic": traffic.get("env"), "achieved": round(env_bytes / (env_ms * 1e-3) / 1e9, 1),
                     "peak": hbm_peak, "unit": "GB/s", "frac": round(env_bytes / (env_ms * 1e-3) / 1e9 / hbm_peak, 4),
                     "kernel_ms": round(env_ms, 5), "launch_bytes": env_bytes, "peak_source": peak_src}
         out = {
@@ -332,6 +365,7 @@ def run_ours(args):
             "gpu_launches": int(launches_sum),
             "clocks": clk,
             "roofline": roofline if roofline else env_roof,
+            "roofline_tensor": roof_gemm,
             "roofline_env": env_roof,
         }
         if e2e is not None:

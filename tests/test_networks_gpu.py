@@ -219,3 +219,27 @@ def test_bf16_agent_rows_and_chunking(kind):
     scale = max(1.0, float(np.abs(want).max()))
     assert float(np.abs(q[sel] - want).max()) <= BF16_TOL * scale
     assert np.isfinite(q).all()
+
+
+def test_large_graphs_200_nodes():
+    """BASELINE config 5 stress: 200-node graphs (mean degree ~21, max > 32 -> the 32-neighbour cap of
+    radius_graph is exercised).  fp32 path for every model; bf16 path for the GATv2 models (the bf16
+    Transformer kernel needs more shared memory than one CTA has at N = 200 and must say so)."""
+    from melissa_b200 import _lib
+    N, B = 200, 3
+    om = _obs_matrix(N, B, 71)
+    cm = np.random.default_rng(8).random((B, N)) < 0.1
+    for kind, kw in (("l_dgn", {}), ("dgn_r", {}), ("hl_dgn", {"aggregator": "max"})):
+        sd = _random_sd(kind, 73)
+        want = no.forward_graphs(kind, sd, torch.as_tensor(om), torch.as_tensor(cm), N, **kw).numpy()
+        m = _module(kind, N, sd, **kw)
+        q, _ = m.forward_graphs(torch.as_tensor(om, device="cuda"), torch.as_tensor(cm, device="cuda").to(torch.uint8))
+        _assert_q(q.cpu().numpy(), want, f"{kind} N=200 fp32")
+        m.set_precision("bf16")
+        if kind == "dgn_r":
+            with pytest.raises(_lib.MelissaLibraryError):
+                m.forward_graphs(torch.as_tensor(om, device="cuda"), torch.as_tensor(cm, device="cuda").to(torch.uint8))
+        else:
+            q, _ = m.forward_graphs(torch.as_tensor(om, device="cuda"), torch.as_tensor(cm, device="cuda").to(torch.uint8))
+            scale = max(1.0, float(np.abs(want).max()))
+            assert float(np.abs(q.cpu().numpy() - want).max()) <= BF16_TOL * scale
