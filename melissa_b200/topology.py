@@ -83,6 +83,17 @@ def graph_to_arrays(g: nx.Graph, n_nodes: int | None = None):
     return adj, pos
 
 
+def arrays_to_graph(adj: np.ndarray, pos: np.ndarray) -> nx.Graph:
+    """Inverse of :func:`graph_to_arrays`: networkx graph with nodes 0..N-1 and ``pos=[x, y]``."""
+    n = adj.shape[0]
+    g = nx.Graph()
+    for i in range(n):
+        g.add_node(i, pos=[float(pos[i, 0]), float(pos[i, 1])])
+    iu, ju = np.nonzero(np.triu(adj, 1))
+    g.add_edges_from(zip(iu.tolist(), ju.tolist()))
+    return g
+
+
 def pack_adjacency(adj: np.ndarray) -> np.ndarray:
     """bool [..., N, N] -> uint32 [..., N, W] bitmask rows (bit j of word j//32)."""
     n = adj.shape[-1]
