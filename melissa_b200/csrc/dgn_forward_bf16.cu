@@ -60,17 +60,37 @@ __global__ void cat_bias_kernel(const CatJobs jobs) {
 }
 
 // ------------------------------------------------------------------------------ encoder layer 0
-__global__ void enc0_bf16_kernel(const float* __restrict__ obs, int64_t obs_stride, int N, int rows, int in_dim,
-                                 const float* __restrict__ w0, const float* __restrict__ b0, int hidden, bf16* __restrict__ h) {
-  const int r = blockIdx.x * blockDim.y + threadIdx.y;
+// h = relu(W0 f + b0), f = obs cols 2..6.  16 threads per node row (8 channels each, one 16 B store),
+// W0 / b0 in shared memory.
+__global__ void __launch_bounds__(256) enc0_bf16_kernel(const float* __restrict__ obs, int64_t obs_stride, int N, int rows, int in_dim,
+                                                        const float* __restrict__ w0, const float* __restrict__ b0, int hidden,
+                                                        bf16* __restrict__ h) {
+  __shared__ float w_s[kC * 5 + kC];
+  for (int t = threadIdx.x; t < hidden * in_dim; t += 256) w_s[t] = w0[t];
+  for (int t = threadIdx.x; t < hidden; t += 256) w_s[kC * 5 + t] = b0[t];
+  __syncthreads();
+  const int per_row = hidden / 8;                      // threads per row
+  const int rows_per_cta = 256 / per_row;
+  const int r = blockIdx.x * rows_per_cta + threadIdx.x / per_row;
   if (r >= rows) return;
+  const int c0 = (threadIdx.x % per_row) * 8;
   const int g = r / N, i = r - g * N;
   const float* f = obs + (int64_t)g * obs_stride + i * 8 + 2;
-  for (int c = threadIdx.x; c < hidden; c += blockDim.x) {
-    float acc = b0[c];
-    for (int k = 0; k < in_dim; ++k) acc = fmaf(w0[c * in_dim + k], f[k], acc);
-    h[(size_t)r * hidden + c] = __float2bfloat16_rn(fmaxf(acc, 0.0f));
+  float fv[5];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) fv[k] = k < in_dim ? f[k] : 0.f;
+  uint32_t packed[4];
+#pragma unroll
+  for (int c = 0; c < 8; c += 2) {
+    float a0 = w_s[kC * 5 + c0 + c], a1 = w_s[kC * 5 + c0 + c + 1];
+    for (int k = 0; k < in_dim; ++k) {
+      a0 = fmaf(w_s[(c0 + c) * in_dim + k], fv[k], a0);
+      a1 = fmaf(w_s[(c0 + c + 1) * in_dim + k], fv[k], a1);
+    }
+    __nv_bfloat162 p = __floats2bfloat162_rn(fmaxf(a0, 0.f), fmaxf(a1, 0.f));
+    packed[c >> 1] = *reinterpret_cast<uint32_t*>(&p);
   }
+  *reinterpret_cast<uint4*>(h + (size_t)r * hidden + c0) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
 }
 
 // ------------------------------------------------------------------------------ graph CSR
@@ -676,8 +696,9 @@ int dgn_forward_bf16(const MlsNetDesc* d, const MlsNetWeights* w, const MlsForwa
     mls_count_launch();
     // encoder
     {
-      dim3 blk(32, 8);
-      enc0_bf16_kernel<<<(rows + 7) / 8, blk, 0, st>>>(obs, a->obs_stride, N, rows, d->input_dim, w->enc_w0, w->enc_b0, hid, ws.h);
+      const int rows_per_cta = 256 / (hid / 8);
+      enc0_bf16_kernel<<<(rows + rows_per_cta - 1) / rows_per_cta, 256, 0, st>>>(obs, a->obs_stride, N, rows, d->input_dim, w->enc_w0,
+                                                                                  w->enc_b0, hid, ws.h);
       mls_count_launch();
       GemmEpilogue e{ws.x0, hid, w->enc_b1, nullptr, 0, N, 1, nullptr, nullptr};
       if ((rc = gemm_bf16_launch(ws.h, hid, ws.w_enc1, hid, GemmShape{rows, hid, hid, nullptr}, e, sms, st))) return rc;

@@ -93,11 +93,11 @@ struct GemmSmem {
   static constexpr int kABytes = kBM * kBK * 2;      // 16 KiB
   static constexpr int kBBytes = BN * kBK * 2;       // 16 / 32 KiB
   static constexpr int kStageBytes = kABytes + kBBytes;
-  // epilogue staging: per warp 32 rows of BN bf16 (+16 B pad: conflict-free 16 B stores by row-owning lanes)
-  static constexpr int kOutRowBytes = BN * 2 + 16;
+  // epilogue staging: 8 warps, each 32 rows x BN/2 bf16 (+16 B pad: conflict-free 16 B stores by row-owning lanes)
+  static constexpr int kOutRowBytes = BN + 16;
   static constexpr int kOutWarpBytes = 32 * kOutRowBytes;
   static constexpr int kOutOffset = kNumStages * kStageBytes;
-  static constexpr int kBiasOffset = kOutOffset + 4 * kOutWarpBytes;      // BN floats
+  static constexpr int kBiasOffset = kOutOffset + 8 * kOutWarpBytes;      // BN floats
   static constexpr int kDotOffset = kBiasOffset + BN * 4;                 // BN floats
   static constexpr int kBarOffset = kDotOffset + BN * 4;
   static constexpr int kTotal = kBarOffset + 256 + 1024;   // barriers + alignment slack
@@ -134,7 +134,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 256); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(smem_u32(tmem_slot), 2 * BN);      // 2 accumulator stages of BN fp32 columns
@@ -190,11 +190,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   } else if (warp >= 4) {
     // ===================================================================== epilogue
     // TMEM -> registers (lane = row) -> scale/bias/ReLU -> bf16 -> per-warp smem tile -> coalesced row stores
-    const int ew = warp - 4;                                // == warp % 4: the TMEM lane quarter this warp may read
-    unsigned char* stage_out = smem + S::kOutOffset + ew * S::kOutWarpBytes;
+    // eight warps: warp % 4 selects the TMEM lane quarter (rows) a warp may read, (warp - 4) / 4 the column half
+    const int ew = (warp - 4) & 3, half = (warp - 4) >> 2;
+    constexpr int HN = BN / 2;
+    const int cb = half * HN;
+    unsigned char* stage_out = smem + S::kOutOffset + (warp - 4) * S::kOutWarpBytes;
     float* bias_s = reinterpret_cast<float*>(smem + S::kBiasOffset);
     float* dot_s = reinterpret_cast<float*>(smem + S::kDotOffset);
-    const int et = threadIdx.x - 128;                       // 0..127 within the epilogue warps
+    const int et = threadIdx.x - 128;                       // 0..255 within the epilogue warps
     int it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -207,17 +210,17 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         scale = epi.obs[(long long)g * epi.obs_stride + i * 8 + 7];
       }
       // bias slice of this tile -> smem (all four epilogue warps; named barrier 1 keeps the other warps out of it)
-      asm volatile("bar.sync 1, 128;" ::: "memory");        // previous tile's readers are done with bias_s
-      for (int c = et; c < BN; c += 128) {
+      asm volatile("bar.sync 1, 256;" ::: "memory");        // previous tile's readers are done with bias_s
+      for (int c = et; c < BN; c += 256) {
         bias_s[c] = epi.bias ? __ldg(epi.bias + n0 + c) : 0.0f;
         if (epi.dotvec) dot_s[c] = __ldg(epi.dotvec + n0 + c);
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       float dot = 0.f;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = cb; c0 < cb + HN; c0 += 32) {
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN + c0), v);
         uint32_t packed[16];
@@ -235,7 +238,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           packed[j >> 1] = *reinterpret_cast<uint32_t*>(&p0);
           packed[(j >> 1) + 1] = *reinterpret_cast<uint32_t*>(&p1);
         }
-        uint4* dst = reinterpret_cast<uint4*>(stage_out + lane * S::kOutRowBytes + c0 * 2);
+        uint4* dst = reinterpret_cast<uint4*>(stage_out + lane * S::kOutRowBytes + (c0 - cb) * 2);
 #pragma unroll
         for (int q = 0; q < 4; ++q) dst[q] = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
         if (epi.dotvec && (c0 & 96) == 96) {                 // end of a 128-column group
@@ -247,8 +250,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       tc_fence_before();
       mbar_arrive(tempty_bar(acc));
       __syncwarp();
-      // each instruction now writes one full row segment of BN bf16 (BN*2 bytes contiguous)
-      constexpr int kLanesPerRow = BN * 2 / 16;             // 16 (BN=128) or 32 (BN=256) lanes cover one row
+      // each instruction now writes whole row segments of BN/2 bf16 (BN bytes contiguous each)
+      constexpr int kLanesPerRow = HN * 2 / 16;             // 8 (BN=128) or 16 (BN=256) lanes cover one row segment
       constexpr int kRowsPerIter = 32 / kLanesPerRow;
       const int sub = lane / kLanesPerRow, cl = lane % kLanesPerRow;
 #pragma unroll 4
@@ -256,7 +259,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         const int row = rr + sub;
         const int gr = m0 + ew * 32 + row;
         const uint4 val = *reinterpret_cast<const uint4*>(stage_out + row * S::kOutRowBytes + cl * 16);
-        if (gr < M) *reinterpret_cast<uint4*>(epi.C + (size_t)gr * epi.ldc + n0 + cl * 8) = val;
+        if (gr < M) *reinterpret_cast<uint4*>(epi.C + (size_t)gr * epi.ldc + n0 + cb + cl * 8) = val;
       }
       __syncwarp();
     }
@@ -320,6 +323,7 @@ int gemm_bf16_launch(const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, in
   MLS_CHECK_ARG(shape.K % kBK == 0 && shape.K >= kBK, "GEMM K must be a multiple of %d (got %d)", kBK, shape.K);
   MLS_CHECK_ARG(shape.N % 128 == 0, "GEMM N must be a multiple of 128 (got %d)", shape.N);
   MLS_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0 && epi.ldc % 8 == 0, "GEMM leading dimensions must be multiples of 8 elements");
+  MLS_CHECK_ARG(!epi.dotvec || shape.N % 256 == 0, "the fused per-group dot products need N to be a multiple of 256");
   if (shape.M <= 0) return MLS_OK;
   const int BN = (shape.N % 256 == 0) ? 256 : 128;
   CUtensorMap ta, tb;

@@ -14,7 +14,7 @@
 namespace mls {
 
 constexpr int kBM = 128, kBK = 64, kUmmaK = 16;
-constexpr int kGemmThreads = 256;
+constexpr int kGemmThreads = 384;      // 4 control warps (TMA, MMA, TMEM alloc, spare) + 8 epilogue warps
 
 struct GemmEpilogue {
   __nv_bfloat16* C;      // [M, ldc]
