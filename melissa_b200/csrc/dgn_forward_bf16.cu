@@ -168,7 +168,10 @@ struct EdgeArgs {
   int pool_mode;          // >= 0: HL-DGN pooling of relu(conv)*dm into z[g][H*C] (enum MlsPool); -1 none
 };
 
-constexpr int kEdgeThreads = 256, kEdgeWarps = 8;
+#ifndef MLS_EDGE_THREADS
+#define MLS_EDGE_THREADS 128
+#endif
+constexpr int kEdgeThreads = MLS_EDGE_THREADS, kEdgeWarps = kEdgeThreads / 32;
 constexpr int kLD = kC;                 // staged row pitch in floats (a warp reads 4 x 128 B row segments = the 4-wavefront minimum)
 
 __device__ __forceinline__ float fast_ex2(float x) {
@@ -194,7 +197,7 @@ __device__ __forceinline__ float fast_rcp(float x) {
 //              GATv2:       e_ij = 0.6 (a_j + b_i) + 0.4 sum_c att_c |x_l[j,c] + x_r[i,c]|   (leaky_relu(s,.2) = .6 s + .4 |s|)
 //              Transformer: e_ij = <q_i, k_j> / sqrt(C)
 template <bool TRANSFORMER>
-__global__ void __launch_bounds__(kEdgeThreads, 2) edge_bf16_kernel(const EdgeArgs a) {
+__global__ void __launch_bounds__(kEdgeThreads, 512 / kEdgeThreads) edge_bf16_kernel(const EdgeArgs a) {
   extern __shared__ __align__(16) unsigned char esm[];
   const int N = a.N, H = a.H, HC = H * kC;
   float* stA = reinterpret_cast<float*>(esm);                                    // [N][kLD]  x_l or k   (source side)
