@@ -168,10 +168,10 @@ struct EdgeArgs {
   int pool_mode;          // >= 0: HL-DGN pooling of relu(conv)*dm into z[g][H*C] (enum MlsPool); -1 none
 };
 
-#ifndef MLS_EDGE_THREADS
-#define MLS_EDGE_THREADS 128
-#endif
-constexpr int kEdgeThreads = MLS_EDGE_THREADS, kEdgeWarps = kEdgeThreads / 32;
+// CTA size per variant: what matters is how many CTAs fit an SM (shared memory: 2 staged operands for
+// GATv2 -> 4 CTAs of 128 threads; 3 for the Transformer conv -> 2 CTAs of 256 threads), so that staging of
+// one CTA overlaps the compute of the others at the same number of resident warps.
+template <bool TRANSFORMER> struct EdgeCfg { static constexpr int kThreads = TRANSFORMER ? 256 : 128; };
 constexpr int kLD = kC;                 // staged row pitch in floats (a warp reads 4 x 128 B row segments = the 4-wavefront minimum)
 
 __device__ __forceinline__ float fast_ex2(float x) {
@@ -197,7 +197,8 @@ __device__ __forceinline__ float fast_rcp(float x) {
 //              GATv2:       e_ij = 0.6 (a_j + b_i) + 0.4 sum_c att_c |x_l[j,c] + x_r[i,c]|   (leaky_relu(s,.2) = .6 s + .4 |s|)
 //              Transformer: e_ij = <q_i, k_j> / sqrt(C)
 template <bool TRANSFORMER>
-__global__ void __launch_bounds__(kEdgeThreads, 512 / kEdgeThreads) edge_bf16_kernel(const EdgeArgs a) {
+__global__ void __launch_bounds__(EdgeCfg<TRANSFORMER>::kThreads, 512 / EdgeCfg<TRANSFORMER>::kThreads) edge_bf16_kernel(const EdgeArgs a) {
+  constexpr int kEdgeThreads = EdgeCfg<TRANSFORMER>::kThreads, kEdgeWarps = kEdgeThreads / 32;
   extern __shared__ __align__(16) unsigned char esm[];
   const int N = a.N, H = a.H, HC = H * kC;
   float* stA = reinterpret_cast<float*>(esm);                                    // [N][kLD]  x_l or k   (source side)
@@ -552,6 +553,7 @@ size_t carve_b(const MlsNetDesc* d, int Gc, unsigned char* base, WsB* ws) {
 
 template <bool TR>
 int launch_edge(cudaStream_t st, const EdgeArgs& ea) {
+  constexpr int kEdgeThreads = EdgeCfg<TR>::kThreads, kEdgeWarps = kEdgeThreads / 32;
   const size_t smem = (size_t)ea.N * kLD * 4 * (TR ? 3 : 2) + (size_t)ea.N * 4 * 4 + (ea.pool_mode >= 0 ? kEdgeWarps * kC * 4 : 0) +
                       ((size_t)ea.N + 1) * 2 + (size_t)ea.N * kMaxNbr + 16;
   static size_t configured = 0;
