@@ -49,6 +49,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-episodes", type=int, default=8, help="episodes per CPU process in the CPU arm")
     ap.add_argument("--prof-kernel", default=None)
+    ap.add_argument("--dynamic", action="store_true", help="dynamic_graph=True: nodes move every round (Philox stream on the device)")
     return ap.parse_args()
 
 
@@ -178,7 +179,7 @@ def run_ours(args):
         tup = load_tuples(N, G, P)
     from melissa_b200.sharding import reduce_job, shard_tuples
     gi, src, inter, scr = shard_tuples(tup, rank, B)   # each rank starts elsewhere in the pool
-    env = BatchedGraphEnv(B, N, pool, device=dev, want_obs=True)
+    env = BatchedGraphEnv(B, N, pool, device=dev, want_obs=True, dynamic_graph=args.dynamic)
     net = None
     if args.model != "none":
         torch.manual_seed(9)
@@ -354,7 +355,7 @@ def run_ours(args):
             "config": {
                 "workload": f"{args.model} rollout round (env round + forward + eps-greedy), {N}-node graphs, "
                             f"{B} episodes per GPU (BASELINE config 3 per-GPU shard)",
-                "episodes_per_gpu": B, "n_nodes": N, "graph_pool": len(pool), "eps": args.eps, "precision": args.precision,
+                "episodes_per_gpu": B, "n_nodes": N, "dynamic_graph": bool(args.dynamic), "graph_pool": len(pool), "eps": args.eps, "precision": args.precision,
                 "preroll_rounds": args.preroll, "l2": "flushed between timed steps (256 MiB memset outside the timed events)",
                 "launch_mode": "cuda-graph replay of the whole round" if use_graph else "eager",
                 "eager_ms_per_step": (eager_ms / steps) if eager_ms else None,

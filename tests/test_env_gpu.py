@@ -184,3 +184,40 @@ def test_invalid_arguments_raise_value_error():
     env = _env(4, 20, pool)
     with pytest.raises(ValueError):
         env.step(np.zeros((4, 19), dtype=np.int8))
+
+
+def test_dynamic_philox_movement_is_consistent_and_deterministic():
+    """dynamic_graph=True without host-fed offsets: the device draws 0.06*U(-1,1) from Philox4x32-10.
+    Every round each coordinate moves by at most 0.06, the adjacency is exactly the d^2 <= r^2 graph of
+    the moved positions (fp64), the same seed reproduces the trajectory, another seed does not."""
+    N, B = 50, 64
+    pool = GraphPool.synthetic(N, 8, first_seed=11)
+    gi, src, inter, scr, _ = reset_chain.episode_pool(21, B, N, 8)
+    from melissa_b200.topology import unpack_adjacency
+
+    def run(seed):
+        env = _env(B, N, pool, dynamic_graph=True)
+        env.philox_seed = seed
+        env.reset(_tuples(gi, src, inter, scr, N))
+        traj = []
+        prev = env.pos.cpu().numpy().copy()
+        rng = np.random.default_rng(0)
+        for r in range(6):
+            env.step(rng.integers(0, 2, size=(B, N)).astype(np.int8))
+            pos = env.pos.cpu().numpy()
+            adj = unpack_adjacency(env.adj.cpu().numpy().view(np.uint32), N)
+            assert np.abs(pos - prev).max() <= 0.06 + 1e-12 and np.abs(pos - prev).max() > 0.03
+            d = pos[:, :, None, :] - pos[:, None, :, :]
+            want = ((d * d).sum(-1) <= 0.2 * 0.2) & ~np.eye(N, dtype=bool)
+            np.testing.assert_array_equal(adj, want)
+            obs = env.obs.cpu().numpy()
+            np.testing.assert_array_equal(obs[:, :, 0], pos[:, :, 0].astype(np.float32))
+            np.testing.assert_array_equal(obs[:, :, 2], want.sum(2).astype(np.float32))
+            traj.append(pos.copy())
+            prev = pos.copy()
+        return np.stack(traj)
+
+    a, b, c = run(5), run(5), run(6)
+    assert np.array_equal(a, b) and not np.array_equal(a, c)
+    moves = np.diff(np.concatenate([a[:1] * 0 + pool.pos[gi][None], a]), axis=0)[1:]
+    assert abs(moves.mean()) < 2e-3 and 0.03 < moves.std() < 0.04      # U(-0.06, 0.06): std = 0.0346
