@@ -352,6 +352,29 @@ __device__ __forceinline__ void write_obs(const EnvParams& p, const Th<W>& th, i
   o[1] = c;
 }
 
+// adjacency row + position of this node: from the episode's own copy (dynamic graphs, mid-episode) or
+// from the topology pool (static graphs, and every reset)
+template <int W>
+__device__ __forceinline__ void load_topology(const EnvParams& p, const Smem<W>& sm, Th<W>& th, int graph, bool valid,
+                                              bool do_reset, size_t row, int N, int le, int i) {
+  if (!valid) return;
+  if (p.d.dynamic && !do_reset) {
+#pragma unroll
+    for (int w = 0; w < W; ++w) th.adj[w] = p.s.adj[row * W + w];
+    th.px = p.s.pos[row * 2 + 0];
+    th.py = p.s.pos[row * 2 + 1];
+  } else {
+    const size_t gr = (size_t)graph * N + i;
+#pragma unroll
+    for (int w = 0; w < W; ++w) th.adj[w] = p.s.pool_adj[gr * W + w];
+    th.px = p.s.pool_pos[gr * 2 + 0];
+    th.py = p.s.pool_pos[gr * 2 + 1];
+  }
+  uint32_t* mine = sm.adj_row(le, i);
+#pragma unroll
+  for (int w = 0; w < W; ++w) mine[w] = th.adj[w];
+}
+
 template <int W>
 __global__ void __launch_bounds__(kThreads) env_round_kernel(const EnvParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -392,25 +415,6 @@ __global__ void __launch_bounds__(kThreads) env_round_kernel(const EnvParams p) 
   if (i < 4 && le < G) sm.cnt[le * 4 + i] = 0;
   if (threadIdx.x == 0) sm.cnt[G * 4] = 0;
 
-  auto load_topology = [&]() {
-    if (!valid) return;
-    if (p.d.dynamic && !do_reset) {
-#pragma unroll
-      for (int w = 0; w < W; ++w) th.adj[w] = p.s.adj[row * W + w];
-      th.px = p.s.pos[row * 2 + 0];
-      th.py = p.s.pos[row * 2 + 1];
-    } else {
-      const size_t gr = (size_t)ep.graph * N + i;
-#pragma unroll
-      for (int w = 0; w < W; ++w) th.adj[w] = p.s.pool_adj[gr * W + w];
-      th.px = p.s.pool_pos[gr * 2 + 0];
-      th.py = p.s.pool_pos[gr * 2 + 1];
-    }
-    uint32_t* mine = sm.adj_row(le, i);
-#pragma unroll
-    for (int w = 0; w < W; ++w) mine[w] = th.adj[w];
-  };
-
   if (p.mode != 1) {
     // ------------------------------------------------------------ load state
     if (ep_valid) {
@@ -427,7 +431,7 @@ __global__ void __launch_bounds__(kThreads) env_round_kernel(const EnvParams p) 
         for (int w = 0; w < W; ++w) th.rfrom[w] = p.s.recv_from[row * W + w];
       }
     }
-    load_topology();
+    load_topology<W>(p, sm, th, ep.graph, valid, do_reset, row, N, le, i);
     publish<W>(sm, M_I, le, wq, valid && (th.node & MLS_F_INTERESTED));
     __syncthreads();
   }
@@ -514,36 +518,31 @@ __global__ void __launch_bounds__(kThreads) env_round_kernel(const EnvParams p) 
     const bool done = !any_w<W>(A);
     const int n_acted = popc_w<W>(ACT);
     if (ep_valid && i == 0) {
-      // episode_rewards_sum += reward, agents in id order (graph.py:378-389)
+      // episode_rewards_sum += reward, agents in id order (graph.py:378-389): walk the acted bits only
       double s = ep.rsum;
-      for (int n = 0; n < N; ++n) {
-        uint32_t av = 0;
 #pragma unroll
-        for (int w = 0; w < W; ++w) if (w == (n >> 5)) av = ACT[w];
-        if (av & (1u << (n & 31))) s = __dadd_rn(s, sm.rew[(size_t)le * NP + n]);
+      for (int w = 0; w < W; ++w) {
+        uint32_t bits = ACT[w];
+        while (bits) {
+          const int n = w * 32 + __ffs(bits) - 1;
+          bits &= bits - 1;
+          s = __dadd_rn(s, sm.rew[(size_t)le * NP + n]);
+        }
       }
       ep.rsum = s;
       ep.num_moves += 1;
       if (p.out.done) p.out.done[b] = done ? 1 : 0;
       if (p.out.info) {
-        MlsInfo inf;
-        inf.total_messages_transmitted = ep.world_msgs;
-        inf.covered = popc_w<W>(M);
-        inf.messages_sent = sm.cnt[le * 4 + 0];
-        inf.messages_received = sm.cnt[le * 4 + 1];
-        inf.n_neighbours = sm.cnt[le * 4 + 2];
         int ni = 0, ci = 0, um = 0;
 #pragma unroll
         for (int w = 0; w < W; ++w) { ni += __popc(I[w]); ci += __popc(M[w] & I[w]); um += __popc(M[w] & ~I[w]); }
-        inf.interested_agents = ni;
-        inf.coverage_interested_count = ci;
-        inf.uninterested_with_message = um;
-        inf.num_moves = ep.num_moves;
-        inf.n_acted = n_acted;
-        inf.episodes_started = ep.n_resets;
-        inf.reserved = 0;
-        inf.episode_rewards_sum = ep.rsum;
-        p.out.info[b] = inf;
+        int4* o4 = reinterpret_cast<int4*>(p.out.info + b);          // MlsInfo = 12 x int32 + double (56 bytes, 8-aligned)
+        int* o = reinterpret_cast<int*>(p.out.info + b);
+        o[0] = ep.world_msgs; o[1] = popc_w<W>(M); o[2] = sm.cnt[le * 4 + 0]; o[3] = sm.cnt[le * 4 + 1];
+        o[4] = sm.cnt[le * 4 + 2]; o[5] = ni; o[6] = ci; o[7] = um;
+        o[8] = ep.num_moves; o[9] = n_acted; o[10] = ep.n_resets; o[11] = 0;
+        p.out.info[b].episode_rewards_sum = ep.rsum;
+        (void)o4;
       }
       if (p.out.transitions && n_acted) atomicAdd(&sm.cnt[G * 4], n_acted);
     }
@@ -610,7 +609,7 @@ __global__ void __launch_bounds__(kThreads) env_round_kernel(const EnvParams p) 
 #pragma unroll
         for (int w = 0; w < W; ++w) th.rfrom[w] = 0;
       }
-      load_topology();
+      load_topology<W>(p, sm, th, ep.graph, valid, do_reset, row, N, le, i);
     }
     // (threads of episodes that do not reset keep their interest mask slot untouched)
     if (do_reset) publish<W>(sm, M_I, le, wq, valid && (th.node & MLS_F_INTERESTED));
