@@ -656,7 +656,9 @@ template <int W>
 int launch_env(const EnvParams& p, cudaStream_t stream) {
   const int N = p.d.n_nodes;
   const int NP = ((N + 31) / 32) * 32;
-  int G = kThreads / NP;
+  // small CTAs (2 episodes of up to 64 nodes): more independent CTAs per SM overlap each other's load latency and barriers
+  const int target = NP <= 64 ? 64 : kThreads;
+  int G = target / NP;
   if (G < 1) G = 1;
   const int threads = G * NP;
   const int blocks = (p.n_work + G - 1) / G;
