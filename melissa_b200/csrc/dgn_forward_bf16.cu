@@ -1,11 +1,12 @@
 // bf16 tensor-core forward of DGN-R / L-DGN / HL-DGN (sm_100a).
 //
-// Dense layers run on the tcgen05 GEMM (gemm_tcgen05.cu) with fused bias / ReLU /
-// decision-maker row mask; the attention convolutions run one CTA per graph with the
-// neighbour operand of one head staged in shared memory (every x_l / k / v row is read from
-// L2 once per head instead of once per edge); controlling-node snapshots and the HL-DGN
-// graph pooling are written by the same kernels, so the only activations that ever exist
-// in global memory are bf16 and live in an L2-sized, chunk-reused workspace.
+// Dense layers run on the tcgen05 GEMM (gemm_tcgen05.cu) with fused bias / ReLU / decision-maker
+// row mask (and the linear parts of the GATv2 logits); the attention convolutions run one CTA per
+// (graph, head) with that head's operands staged in shared memory (every x_l / x_r / k / v row is
+// read from global memory once per head instead of once per edge) over CSR neighbour lists built
+// once per pass; controlling-node snapshots and the HL-DGN graph pooling are written by the same
+// kernels.  The only activations in global memory are bf16 rows in a workspace that is reused
+// pass after pass (a pass = mls_dgn_chunk_graphs() graphs).
 //
 // Accumulation is fp32 everywhere; activations and weights are rounded to bf16
 // (tolerance stated in tests/test_networks_gpu.py).  Reference math: see dgn_forward.cu.
