@@ -12,6 +12,7 @@
 // (tolerance stated in tests/test_networks_gpu.py).  Reference math: see dgn_forward.cu.
 #include "dgn_kernels.cuh"
 #include "gemm_tcgen05.cuh"
+#include "conv_fused.cuh"
 
 namespace mls {
 
@@ -678,6 +679,8 @@ int dgn_forward_bf16(const MlsNetDesc* d, const MlsNetWeights* w, const MlsForwa
   auto prof_begin = [&](int which) { if (first_chunk && ev0 && ev1 && a->prof_kernel == which) cudaEventRecord(ev0, st); };
   auto prof_end = [&](int which) { if (first_chunk && ev0 && ev1 && a->prof_kernel == which) cudaEventRecord(ev1, st); };
   int rc;
+  static int use_fused = -1;
+  if (use_fused < 0) { const char* e = getenv("MLS_FUSED_CONV"); use_fused = e ? atoi(e) : 0; }
   for (int g0 = 0; g0 < a->n_graphs; g0 += Gc) {
     const int gc = (a->n_graphs - g0) < Gc ? (a->n_graphs - g0) : Gc;
     const int rows = gc * N;
@@ -709,38 +712,62 @@ int dgn_forward_bf16(const MlsNetDesc* d, const MlsNetWeights* w, const MlsForwa
       GemmEpilogue e{ws.x0, hid, w->enc_b1, nullptr, 0, N, 1, nullptr, nullptr};
       if ((rc = gemm_bf16_launch(ws.h, hid, ws.w_enc1, hid, GemmShape{rows, hid, hid, nullptr}, e, sms, st))) return rc;
     }
-    // conv1 projections
-    {
-      GemmEpilogue e{ws.P, nproj * HC, ws.b_c1, nullptr, 0, N, 0, tr ? nullptr : ws.att1, tr ? nullptr : ws.ab};
-      prof_begin(MLS_PROF_PROJ1);
-      if ((rc = gemm_bf16_launch(ws.x0, hid, ws.w_c1, hid, GemmShape{rows, nproj * HC, hid, nullptr}, e, sms, st))) return rc;
-      prof_end(MLS_PROF_PROJ1);
-    }
-    // conv1 attention (+ReLU); snapshot x1[ctrl] (pre-mask) or HL-DGN pooling
-    {
-      EdgeArgs ea{};
-      ea.P = ws.P; ea.ldp = nproj * HC; ea.obs = obs; ea.obs_stride = a->obs_stride; ea.N = N; ea.H = H; ea.n_graphs = gc;
-      ea.att = w->c1_att; ea.bias = w->c1_bias; ea.csr_ptr = ws.csr_ptr; ea.csr_src = ws.csr_src; ea.ab = ws.ab;
-      if (hl) { ea.x_out = nullptr; ea.slot = nullptr; ea.z = ws.z; ea.ldz = latent; ea.z_col = 0; ea.ctrl_only = 0; ea.pool_mode = d->pool; }
-      else { ea.x_out = ws.x1; ea.slot = ws.slot; ea.z = ws.z; ea.ldz = latent; ea.z_col = hid; ea.ctrl_only = 0; ea.pool_mode = -1; }
+    // fused GATv2 conv (projection GEMM + attention in one kernel) for L-DGN when the graphs fit a 128-row tile
+    const int fusedG = (!tr && !hl && use_fused && N <= 100) ? 100 / N : 0;
+    if (fusedG) {
+      FusedConvArgs fa{};
+      fa.rows = rows; fa.K = hid; fa.N = N; fa.H = H; fa.n_graphs = gc; fa.G = fusedG;
+      fa.proj_bias = ws.b_c1; fa.att = w->c1_att; fa.conv_bias = w->c1_bias; fa.obs = obs; fa.obs_stride = a->obs_stride;
+      fa.scale_rows = 0; fa.csr_ptr = ws.csr_ptr; fa.csr_src = ws.csr_src; fa.slot = ws.slot; fa.ctrl_only = 0;
+      fa.x_out = ws.x1; fa.z = ws.z; fa.ldz = latent; fa.z_col = hid;
       prof_begin(MLS_PROF_EDGE1);
-      if ((rc = edge_dispatch(st, ea, tr, Wn))) return rc;
+      if ((rc = fused_gatv2_conv_launch(ws.x0, ws.w_c1, fa, sms, st))) return rc;
       prof_end(MLS_PROF_EDGE1);
+    } else {
+    // conv1 projections
+      {
+        GemmEpilogue e{ws.P, nproj * HC, ws.b_c1, nullptr, 0, N, 0, tr ? nullptr : ws.att1, tr ? nullptr : ws.ab};
+        prof_begin(MLS_PROF_PROJ1);
+        if ((rc = gemm_bf16_launch(ws.x0, hid, ws.w_c1, hid, GemmShape{rows, nproj * HC, hid, nullptr}, e, sms, st))) return rc;
+        prof_end(MLS_PROF_PROJ1);
+      }
+      // conv1 attention (+ReLU); snapshot x1[ctrl] (pre-mask) or HL-DGN pooling
+      {
+        EdgeArgs ea{};
+        ea.P = ws.P; ea.ldp = nproj * HC; ea.obs = obs; ea.obs_stride = a->obs_stride; ea.N = N; ea.H = H; ea.n_graphs = gc;
+        ea.att = w->c1_att; ea.bias = w->c1_bias; ea.csr_ptr = ws.csr_ptr; ea.csr_src = ws.csr_src; ea.ab = ws.ab;
+        if (hl) { ea.x_out = nullptr; ea.slot = nullptr; ea.z = ws.z; ea.ldz = latent; ea.z_col = 0; ea.ctrl_only = 0; ea.pool_mode = d->pool; }
+        else { ea.x_out = ws.x1; ea.slot = ws.slot; ea.z = ws.z; ea.ldz = latent; ea.z_col = hid; ea.ctrl_only = 0; ea.pool_mode = -1; }
+        prof_begin(MLS_PROF_EDGE1);
+        if ((rc = edge_dispatch(st, ea, tr, Wn))) return rc;
+        prof_end(MLS_PROF_EDGE1);
+      }
     }
     if (!hl) {
+      if (fusedG) {
+        FusedConvArgs fa{};
+        fa.rows = rows; fa.K = HC; fa.N = N; fa.H = H; fa.n_graphs = gc; fa.G = fusedG;
+        fa.proj_bias = ws.b_c2; fa.att = w->c2_att; fa.conv_bias = w->c2_bias; fa.obs = obs; fa.obs_stride = a->obs_stride;
+        fa.scale_rows = 1; fa.csr_ptr = ws.csr_ptr; fa.csr_src = ws.csr_src; fa.slot = ws.slot; fa.ctrl_only = 1;
+        fa.x_out = nullptr; fa.z = ws.z; fa.ldz = latent; fa.z_col = hid + HC;
+        prof_begin(MLS_PROF_EDGE2);
+        if ((rc = fused_gatv2_conv_launch(ws.x1, ws.w_c2, fa, sms, st))) return rc;
+        prof_end(MLS_PROF_EDGE2);
+      } else {
       // conv2 projections on x1 * dm: the row mask commutes with the GEMM, applied in its epilogue
-      GemmEpilogue e{ws.P, nproj * HC, ws.b_c2, obs, a->obs_stride, N, 0, tr ? nullptr : ws.att2, tr ? nullptr : ws.ab};
-      prof_begin(MLS_PROF_PROJ2);
-      if ((rc = gemm_bf16_launch(ws.x1, HC, ws.w_c2, HC, GemmShape{rows, nproj * HC, HC, nullptr}, e, sms, st))) return rc;
-      prof_end(MLS_PROF_PROJ2);
-      // conv2 attention only where a controlling agent needs it; result goes straight into z
-      EdgeArgs ea{};
-      ea.P = ws.P; ea.ldp = nproj * HC; ea.obs = obs; ea.obs_stride = a->obs_stride; ea.N = N; ea.H = H; ea.n_graphs = gc;
-      ea.att = w->c2_att; ea.bias = w->c2_bias; ea.csr_ptr = ws.csr_ptr; ea.csr_src = ws.csr_src; ea.ab = ws.ab; ea.x_out = nullptr; ea.slot = ws.slot; ea.z = ws.z; ea.ldz = latent;
-      ea.z_col = hid + HC; ea.ctrl_only = 1; ea.pool_mode = -1;
-      prof_begin(MLS_PROF_EDGE2);
-      if ((rc = edge_dispatch(st, ea, tr, Wn))) return rc;
-      prof_end(MLS_PROF_EDGE2);
+        GemmEpilogue e{ws.P, nproj * HC, ws.b_c2, obs, a->obs_stride, N, 0, tr ? nullptr : ws.att2, tr ? nullptr : ws.ab};
+        prof_begin(MLS_PROF_PROJ2);
+        if ((rc = gemm_bf16_launch(ws.x1, HC, ws.w_c2, HC, GemmShape{rows, nproj * HC, HC, nullptr}, e, sms, st))) return rc;
+        prof_end(MLS_PROF_PROJ2);
+        // conv2 attention only where a controlling agent needs it; result goes straight into z
+        EdgeArgs ea{};
+        ea.P = ws.P; ea.ldp = nproj * HC; ea.obs = obs; ea.obs_stride = a->obs_stride; ea.N = N; ea.H = H; ea.n_graphs = gc;
+        ea.att = w->c2_att; ea.bias = w->c2_bias; ea.csr_ptr = ws.csr_ptr; ea.csr_src = ws.csr_src; ea.ab = ws.ab; ea.x_out = nullptr; ea.slot = ws.slot; ea.z = ws.z; ea.ldz = latent;
+        ea.z_col = hid + HC; ea.ctrl_only = 1; ea.pool_mode = -1;
+        prof_begin(MLS_PROF_EDGE2);
+        if ((rc = edge_dispatch(st, ea, tr, Wn))) return rc;
+        prof_end(MLS_PROF_EDGE2);
+      }
       dim3 blk(16, 16);
       gather_x0_kernel<<<(rows + 15) / 16, blk, 0, st>>>(ws.idx, ws.count, ws.x0, hid, ws.z, latent);
       mls_count_launch();

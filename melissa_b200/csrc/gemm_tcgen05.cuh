@@ -36,6 +36,8 @@ struct GemmShape {
 };
 
 size_t gemm_smem_bytes(int BN);
+// K-major bf16 matrix [rows, cols] with row stride ld_elems -> TMA descriptor with a 64 x box_rows box, 128B swizzle
+int make_tmap_bf16(CUtensorMap* tm, const void* base, int rows, int cols, int ld_elems, int box_rows);
 // host: build the two TMA descriptors + launch.  A: [M, K] row stride lda; B: [N, K] row stride ldb.
 int gemm_bf16_launch(const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, int ldb, GemmShape shape,
                      GemmEpilogue epi, int sm_count, cudaStream_t st);
