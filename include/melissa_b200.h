@@ -38,6 +38,10 @@ const char* mls_last_error(void);
 int mls_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);
 /* words per bitmask row for N nodes: 1 (N<=32), 2 (<=64), 4 (<=128), 8 (<=256). */
 int mls_words_per_row(int n_nodes);
+/* process-wide tuning options; "fused_conv" = 1 selects the experimental fused projection+attention kernel
+ * for the GATv2 convolutions of L-DGN (bf16 precision).  get returns -1 for an unknown key. */
+int mls_set_option(const char* key, int value);
+int mls_get_option(const char* key);
 /* kernels launched by this library since it was loaded (process wide; for bench accounting). */
 unsigned long long mls_launch_count(void);
 

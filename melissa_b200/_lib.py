@@ -83,7 +83,7 @@ class MlsForwardArgs(C.Structure):
 PROF_KERNELS = {None: 0, "proj1": 1, "proj2": 2, "edge1": 3, "edge2": 4, "head0": 5}
 
 
-EXPORTS = ["mls_version", "mls_last_error", "mls_device_info", "mls_words_per_row", "mls_launch_count", "mls_env_reset", "mls_env_step",
+EXPORTS = ["mls_version", "mls_last_error", "mls_device_info", "mls_words_per_row", "mls_launch_count", "mls_set_option", "mls_get_option", "mls_env_reset", "mls_env_step",
            "mls_env_info", "mls_dgn_workspace_bytes", "mls_dgn_chunk_graphs", "mls_dgn_forward"]
 
 _lib = None
@@ -108,6 +108,8 @@ def lib():
     L.mls_device_info.argtypes = [C.POINTER(C.c_int32)] * 3
     L.mls_words_per_row.argtypes = [C.c_int]
     L.mls_launch_count.restype = C.c_ulonglong
+    L.mls_set_option.argtypes = [C.c_char_p, C.c_int]
+    L.mls_get_option.argtypes = [C.c_char_p]
     P = C.POINTER
     L.mls_env_reset.argtypes = [P(MlsEnvDesc), P(MlsEnvState), vp, P(MlsResetTuples), P(MlsRoundInputs),
                                 P(MlsRoundOutputs), vp]
@@ -149,3 +151,11 @@ def ptr(t):
 def current_stream_ptr():
     import torch
     return torch.cuda.current_stream().cuda_stream
+
+
+def set_option(key: str, value: int) -> None:
+    check(lib().mls_set_option(key.encode(), int(value)))
+
+
+def get_option(key: str) -> int:
+    return lib().mls_get_option(key.encode())

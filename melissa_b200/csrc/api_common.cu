@@ -29,3 +29,22 @@ extern "C" int mls_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc
   if (cc_minor) *cc_minor = prop.minor;
   return MLS_OK;
 }
+
+// ---- tuning options (process wide).  "fused_conv": 1 = run the GATv2 convolutions of L-DGN with the fused
+// projection+attention kernel (conv_fused.cu; experimental, slower than the two-kernel path in round 1).
+// Initial values come from the environment (MLS_FUSED_CONV).
+#include <stdlib.h>
+#include <string.h>
+static int g_fused_conv = -1;
+extern "C" int mls_get_option(const char* key) {
+  if (key && !strcmp(key, "fused_conv")) {
+    if (g_fused_conv < 0) { const char* e = getenv("MLS_FUSED_CONV"); g_fused_conv = e ? atoi(e) : 0; }
+    return g_fused_conv;
+  }
+  return -1;
+}
+extern "C" int mls_set_option(const char* key, int value) {
+  if (key && !strcmp(key, "fused_conv")) { g_fused_conv = value ? 1 : 0; return MLS_OK; }
+  mls_set_error("unknown option %s", key ? key : "(null)");
+  return MLS_ERR_INVALID;
+}

@@ -8,6 +8,7 @@
 
 void mls_set_error(const char* fmt, ...);
 void mls_count_launch(int n = 1);
+extern "C" int mls_get_option(const char* key);
 
 #define MLS_CHECK_ARG(cond, ...)          \
   do {                                    \

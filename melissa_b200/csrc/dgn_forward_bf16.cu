@@ -679,8 +679,7 @@ int dgn_forward_bf16(const MlsNetDesc* d, const MlsNetWeights* w, const MlsForwa
   auto prof_begin = [&](int which) { if (first_chunk && ev0 && ev1 && a->prof_kernel == which) cudaEventRecord(ev0, st); };
   auto prof_end = [&](int which) { if (first_chunk && ev0 && ev1 && a->prof_kernel == which) cudaEventRecord(ev1, st); };
   int rc;
-  static int use_fused = -1;
-  if (use_fused < 0) { const char* e = getenv("MLS_FUSED_CONV"); use_fused = e ? atoi(e) : 0; }
+  const int use_fused = mls_get_option("fused_conv");
   for (int g0 = 0; g0 < a->n_graphs; g0 += Gc) {
     const int gc = (a->n_graphs - g0) < Gc ? (a->n_graphs - g0) : Gc;
     const int rows = gc * N;

@@ -243,3 +243,28 @@ def test_large_graphs_200_nodes():
             q, _ = m.forward_graphs(torch.as_tensor(om, device="cuda"), torch.as_tensor(cm, device="cuda").to(torch.uint8))
             scale = max(1.0, float(np.abs(want).max()))
             assert float(np.abs(q.cpu().numpy() - want).max()) <= BF16_TOL * scale
+
+
+def test_experimental_fused_conv_kernel_matches_two_kernel_path():
+    """conv_fused.cu (projection GEMM + attention in one kernel, opt-in): same Q-values as the default
+    two-kernel bf16 path up to bf16 rounding of the intermediate projections, and within the stated
+    tolerance of the fp32 oracle."""
+    from melissa_b200 import _lib
+    for N, B in ((50, 40), (20, 64), (12, 9)):
+        sd = _random_sd("l_dgn", 81)
+        om = _obs_matrix(N, B, 31)
+        cm = np.random.default_rng(9).random((B, N)) < 0.3
+        want = no.forward_graphs("l_dgn", sd, torch.as_tensor(om), torch.as_tensor(cm), N).numpy()
+        m = _module("l_dgn", N, sd).set_precision("bf16")
+        args = (torch.as_tensor(om, device="cuda"), torch.as_tensor(cm, device="cuda").to(torch.uint8))
+        q0, _ = m.forward_graphs(*args)
+        assert _lib.get_option("fused_conv") == 0
+        _lib.set_option("fused_conv", 1)
+        try:
+            q1, a1 = m.forward_graphs(*args)
+        finally:
+            _lib.set_option("fused_conv", 0)
+        scale = max(1.0, float(np.abs(want).max()))
+        assert float(np.abs(q1.cpu().numpy() - want).max()) <= BF16_TOL * scale
+        assert float((q1 - q0).abs().max()) <= BF16_TOL * scale
+        assert not torch.equal(q0, q1) or N == 12          # really a different code path
