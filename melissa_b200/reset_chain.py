@@ -136,3 +136,26 @@ def episode_pool(base_seed: int, count: int, n_nodes: int, n_graphs: int,
         gi[i] = (i % n_graphs) if n_graphs > 0 else -1
         src[i], inter[i], scr[i], mv[i] = t.source, t.interested, t.scripted, t.movement_seed
     return gi, src, inter, scr, mv
+
+
+def testing_episode_pool(count: int, n_nodes: int, n_graphs: int, num_test_episodes: int, *, seed: int | None = None,
+                         scripted_agents_ratio: float = 0.0, skip: int = 2):
+    """Reset tuples of ONE testing-mode environment (``is_testing=True``, reference core.py:182-187,348-370)
+    for its next ``count`` episodes: episode seeds from ``RandomState(17)`` used cyclically, graph drawn
+    by the episode RNG from the sorted test graphs, interest density ladder 0.1 .. 1.0.
+    ``skip`` = resets already consumed by the reference constructor (core.py:190, graph.py:117).
+    Returns the same arrays as :func:`episode_pool` plus the densities."""
+    stream = TestingResetStream(n_nodes, num_test_episodes, n_graphs)
+    rng, _ = make_np_random(seed)
+    for _ in range(skip):
+        stream.next(rng, scripted_agents_ratio)
+    gi = np.zeros(count, dtype=np.int32)
+    src = np.zeros(count, dtype=np.int32)
+    inter = np.zeros((count, n_nodes), dtype=bool)
+    scr = np.zeros((count, n_nodes), dtype=bool)
+    mv = np.zeros(count, dtype=np.int64)
+    dens = np.zeros(count, dtype=np.float64)
+    for k in range(count):
+        t = stream.next(rng, scripted_agents_ratio)
+        gi[k], src[k], inter[k], scr[k], mv[k], dens[k] = t.graph_index, t.source, t.interested, t.scripted, t.movement_seed, t.interest_density
+    return gi, src, inter, scr, mv, dens

@@ -157,3 +157,19 @@ def test_world_size_2_gloo_sharding_and_reduction(tmp_path):
     assert r0[0] == 0 and r1[0] == 16 and r1[1] == 32        # rank 1 starts half a shard further into the pool
     for r in (r0, r1):
         assert r[2] == 20.0 and r[3] == 4000.0 and r[4] == 4000.0 / 0.020   # max over ranks, sum over ranks
+
+
+def test_testing_episode_pool_follows_the_test_stream():
+    gi, src, inter, scr, mv, dens = reset_chain.testing_episode_pool(25, 20, 7, num_test_episodes=10, seed=3)
+    # the seeds are used cyclically: episode k and k+10 draw the same graph / source / movement seed ...
+    assert np.array_equal(gi[:15], gi[10:25]) and np.array_equal(src[:15], src[10:25]) and np.array_equal(mv[:15], mv[10:25])
+    # ... and, the ladder having period 10 as well, the same interest density
+    assert np.allclose(dens[:15], dens[10:25])
+    assert set(np.round(dens, 1)) == {0.1, 0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.8, 0.9, 1.0}
+    assert np.array_equal(inter.sum(1), (dens * 20).astype(int))
+    assert ((gi >= 0) & (gi < 7)).all() and not scr.any()
+    s = reset_chain.TestingResetStream(20, 10, 7)
+    rng, _ = reset_chain.make_np_random(3)
+    s.next(rng); s.next(rng)
+    t = s.next(rng)
+    assert t.graph_index == gi[0] and t.source == src[0] and np.array_equal(t.interested, inter[0])

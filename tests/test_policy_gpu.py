@@ -105,3 +105,21 @@ def test_collect_n_episode_and_n_step():
         col.collect()
     st3 = col.collect(n_step=200, random=True)
     assert st3.n_collected_steps >= 200
+
+
+def test_evaluation_collect_in_testing_mode():
+    """C5 "eval": is_testing=True environment, reset tuples from the reference's test stream
+    (RandomState(17) seeds, density ladder), greedy policy (eps_test ~ 0), n_episode collection."""
+    from melissa_b200.batched_env import BatchedGraphEnv, ResetTuplesDevice
+    from melissa_b200.networks import HLDGNNetwork
+    from melissa_b200.policy import BatchedCollector, DQNPolicy
+    N, B = 20, 16
+    pool = GraphPool.synthetic(N, 6, first_seed=900)
+    gi, src, inter, scr, mv, dens = reset_chain.testing_episode_pool(64, N, 6, num_test_episodes=10, seed=1)
+    net = HLDGNNetwork(5, 128, 2, 4, N, aggregator="max", dueling_param=DUELING(), device="cuda").cuda()
+    env = BatchedGraphEnv(B, N, pool, is_testing=True, want_info=True)
+    col = BatchedCollector(DQNPolicy(net, eps=0.001), env, ResetTuplesDevice(gi, src, inter, scr, N, "cuda"))
+    st = col.collect(n_episode=40)
+    assert st.n_collected_episodes >= 40 and (st.lens >= 1).all()
+    assert 0.0 < st.info["coverage"].mean <= 1.0
+    assert set(np.unique(st.info and np.round(dens, 1))) <= {0.1, 0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.8, 0.9, 1.0}
