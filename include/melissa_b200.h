@@ -208,7 +208,7 @@ typedef struct MlsForwardArgs {
   float* q;                  /* out */
   int8_t* act;               /* out, NULL ok: greedy / epsilon-greedy action, -1 where not controlling */
   float eps;                 /* exploration rate (tianshou DQNPolicy.exploration_noise)      */
-  int32_t pad_;
+  int32_t flags;             /* MLS_FWD_* bits                                               */
   uint64_t philox_seed, philox_offset;
   const double* rand3;       /* optional host-fed uniforms [rows][3] = (u_eps, u_act0, u_act1) */
   void* workspace;           /* mls_dgn_workspace_bytes() bytes                              */
@@ -222,7 +222,16 @@ typedef struct MlsForwardArgs {
   /* optional device-side uint64 added to philox_offset (a round counter the caller bumps on
    * the stream; lets a captured CUDA graph draw fresh exploration noise on every replay) */
   const void* philox_offset_dev;
+  /* with MLS_FWD_DISCRETE_FEATURES: device int32, set to the number of node rows whose features were not
+   * small non-negative integers (those rows are evaluated with key 0); NULL ok */
+  void* feature_errors;
 } MlsForwardArgs;
+
+/* The caller guarantees that obs columns 2..6 (degree, messages transmitted, last action, interested,
+ * has-message) hold small non-negative integers -- always true for observations produced by
+ * mls_env_reset / mls_env_step (graph.py:263-269): degree < 2^ceil(log2 N), messages < 64, flags 0/1.
+ * bf16 precision only: encoder + conv1 projections are then evaluated once per distinct feature key. */
+#define MLS_FWD_DISCRETE_FEATURES 1
 
 enum MlsProfKernel {
   MLS_PROF_NONE = 0,

@@ -74,12 +74,13 @@ class MlsNetWeights(C.Structure):
 
 class MlsForwardArgs(C.Structure):
     _fields_ = [("obs", vp), ("obs_stride", C.c_int64), ("n_graphs", C.c_int32), ("ctrl_mode", C.c_int32),
-                ("ctrl_mask", vp), ("q", vp), ("act", vp), ("eps", C.c_float), ("pad_", C.c_int32),
+                ("ctrl_mask", vp), ("q", vp), ("act", vp), ("eps", C.c_float), ("flags", C.c_int32),
                 ("philox_seed", C.c_uint64), ("philox_offset", C.c_uint64), ("rand3", vp), ("workspace", vp),
                 ("workspace_bytes", C.c_size_t), ("prof_start", vp), ("prof_stop", vp), ("prof_kernel", C.c_int32),
-                ("pad2_", C.c_int32), ("philox_offset_dev", vp)]
+                ("pad2_", C.c_int32), ("philox_offset_dev", vp), ("feature_errors", vp)]
 
 
+FWD_DISCRETE_FEATURES = 1
 PROF_KERNELS = {None: 0, "proj1": 1, "proj2": 2, "edge1": 3, "edge2": 4, "head0": 5}
 
 

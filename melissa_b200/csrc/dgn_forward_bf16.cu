@@ -95,6 +95,57 @@ __global__ void __launch_bounds__(256) enc0_bf16_kernel(const float* __restrict_
   *reinterpret_cast<uint4*>(h + (size_t)r * hidden + c0) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
 }
 
+// ------------------------------------------------------------------------------ discrete-feature table
+// The encoder input of a node is five small integers (obs cols 2..6: degree, messages transmitted, last
+// action, interested, has-message; reference graph.py:263-269), so x0 = encoder(f) and the conv1
+// projections [x_l | x_r] (or [q | k | v]) take only a few thousand distinct values.  In "discrete
+// features" mode they are computed ONCE per forward for every possible key and the conv1 attention
+// kernel gathers its rows from that table (L2 resident) instead of a per-node GEMM result in HBM.
+//   key = ((((deg << 6) | msgs) << 1 | action) << 1 | interested) << 1 | has_message
+__device__ __forceinline__ void key_decode(uint32_t key, float (&f)[5]) {
+  f[4] = (float)(key & 1u); f[3] = (float)((key >> 1) & 1u); f[2] = (float)((key >> 2) & 1u);
+  f[1] = (float)((key >> 3) & 63u); f[0] = (float)(key >> 9);
+}
+__global__ void feature_key_kernel(const float* __restrict__ obs, int64_t obs_stride, int N, int rows, int degbits,
+                                   uint32_t* __restrict__ key, int* __restrict__ errors) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  const int g = r / N, i = r - g * N;
+  const float* f = obs + (int64_t)g * obs_stride + i * 8 + 2;
+  const float deg = f[0], msgs = f[1], act = f[2], intr = f[3], hm = f[4];
+  const bool ok = deg >= 0.f && deg < (float)(1 << degbits) && deg == floorf(deg) && msgs >= 0.f && msgs < 64.f &&
+                  msgs == floorf(msgs) && (act == 0.f || act == 1.f) && (intr == 0.f || intr == 1.f) && (hm == 0.f || hm == 1.f);
+  uint32_t k = 0;
+  if (ok) k = (((((uint32_t)deg << 6) | (uint32_t)msgs) << 1 | (uint32_t)act) << 1 | (uint32_t)intr) << 1 | (uint32_t)hm;
+  else if (errors) atomicAdd(errors, 1);
+  key[r] = k;
+}
+__global__ void __launch_bounds__(256) enc0_keys_kernel(int n_keys, int in_dim, const float* __restrict__ w0,
+                                                        const float* __restrict__ b0, int hidden, bf16* __restrict__ h) {
+  __shared__ float w_s[kC * 5 + kC];
+  for (int t = threadIdx.x; t < hidden * in_dim; t += 256) w_s[t] = w0[t];
+  for (int t = threadIdx.x; t < hidden; t += 256) w_s[kC * 5 + t] = b0[t];
+  __syncthreads();
+  const int per_row = hidden / 8, rows_per_cta = 256 / per_row;
+  const int r = blockIdx.x * rows_per_cta + threadIdx.x / per_row;
+  if (r >= n_keys) return;
+  const int c0 = (threadIdx.x % per_row) * 8;
+  float fv[5];
+  key_decode((uint32_t)r, fv);
+  uint32_t packed[4];
+#pragma unroll
+  for (int c = 0; c < 8; c += 2) {
+    float a0 = w_s[kC * 5 + c0 + c], a1 = w_s[kC * 5 + c0 + c + 1];
+    for (int k = 0; k < in_dim; ++k) {
+      a0 = fmaf(w_s[(c0 + c) * in_dim + k], fv[k], a0);
+      a1 = fmaf(w_s[(c0 + c + 1) * in_dim + k], fv[k], a1);
+    }
+    __nv_bfloat162 p = __floats2bfloat162_rn(fmaxf(a0, 0.f), fmaxf(a1, 0.f));
+    packed[c >> 1] = *reinterpret_cast<uint32_t*>(&p);
+  }
+  *reinterpret_cast<uint4*>(h + (size_t)r * hidden + c0) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+}
+
 // ------------------------------------------------------------------------------ graph CSR
 // radius_graph(pos, r=0.2, loop=False, max_num_neighbors=32) once per chunk and graph, as source
 // lists per target: csr_ptr[g][N+1] (uint16 offsets into the graph's list), csr_src[g][N*32] (uint8
@@ -160,6 +211,7 @@ struct EdgeArgs {
   const uint16_t* csr_ptr; // [graphs][N+1]
   const uint8_t* csr_src;  // [graphs][N*32]
   const float* ab;        // GATv2: [rows][2H] = (<att_h, x_l[row,h]>, <att_h, x_r[row,h]>) from the projection GEMM
+  const uint32_t* row_key; // optional [rows]: P / ab are tables indexed by row_key[row] (discrete-feature mode), else by row
   const float* att;       // GATv2 [H*C]
   const float* bias;      // GATv2 [H*C]
   bf16* x_out;            // [rows, H*C] relu(conv) for every node, or NULL
@@ -224,7 +276,7 @@ __global__ void __launch_bounds__(EdgeCfg<TRANSFORMER>::kThreads, 512 / EdgeCfg<
     const int tgt_col = (TRANSFORMER ? 0 : HC) + h * kC;
     for (int t = tid; t < N * (kC / 4); t += kEdgeThreads) {
       const int j = t >> 5, q = t & 31;                     // kC / 4 == 32 float4 per row
-      const bf16* row = a.P + (base + j) * a.ldp;
+      const bf16* row = a.P + (a.row_key ? (size_t)a.row_key[base + j] : base + j) * a.ldp;
       *reinterpret_cast<float4*>(stA + j * kLD + q * 4) = ld_bf16x4(row + src_col + q * 4);
       *reinterpret_cast<float4*>(stT + j * kLD + q * 4) = ld_bf16x4(row + tgt_col + q * 4);
       if (TRANSFORMER) *reinterpret_cast<float4*>(stB + j * kLD + q * 4) = ld_bf16x4(row + 2 * HC + h * kC + q * 4);
@@ -235,8 +287,9 @@ __global__ void __launch_bounds__(EdgeCfg<TRANSFORMER>::kThreads, 512 / EdgeCfg<
       s_slot[t] = a.slot ? a.slot[base + t] : -1;
       s_dm[t] = g_obs[t * 8 + 7];
       if (!TRANSFORMER) {
-        s_a[t] = a.ab[(base + t) * (2 * H) + h] * (0.6f * kLog2e);
-        s_b[t] = a.ab[(base + t) * (2 * H) + H + h] * (0.6f * kLog2e);
+        const size_t pr = a.row_key ? (size_t)a.row_key[base + t] : base + t;
+        s_a[t] = a.ab[pr * (2 * H) + h] * (0.6f * kLog2e);
+        s_b[t] = a.ab[pr * (2 * H) + H + h] * (0.6f * kLog2e);
       }
     }
     for (int t = tid; t <= N; t += kEdgeThreads) s_ptr[t] = gp[t];
@@ -420,10 +473,10 @@ __global__ void ctrl_list_slot_kernel(const uint8_t* __restrict__ ctrl_mask, con
 
 // z[t][0:hidden] = x0[idx[t]]  (encoder snapshot, l_dgn.py:121-122)
 __global__ void gather_x0_kernel(const int* __restrict__ idx, const int* __restrict__ count, const bf16* __restrict__ x0,
-                                 int hidden, bf16* __restrict__ z, int ldz) {
+                                 const uint32_t* __restrict__ row_key, int hidden, bf16* __restrict__ z, int ldz) {
   const int t = blockIdx.x * blockDim.y + threadIdx.y;
   if (t >= *count) return;
-  const int r = idx[t];
+  const size_t r = row_key ? (size_t)row_key[idx[t]] : (size_t)idx[t];
   for (int c = threadIdx.x * 8; c < hidden; c += blockDim.x * 8)
     *reinterpret_cast<uint4*>(z + (size_t)t * ldz + c) = *reinterpret_cast<const uint4*>(x0 + (size_t)r * hidden + c);
 }
@@ -509,6 +562,9 @@ using namespace mls;
 
 size_t al(size_t v, size_t a = 1024) { return (v + a - 1) / a * a; }
 
+int degree_bits(int n_nodes) { int b = 1; while ((1 << b) < n_nodes) ++b; return b; }
+int table_keys(int n_nodes) { return (1 << degree_bits(n_nodes)) * 512; }     // deg | 6 bits msgs | 3 flag bits
+
 struct WsB {
   bf16 *w_enc1, *w_c1, *w_c2, *w_h0, *w_h1;
   float *b_c1, *b_c2, *b_h0, *b_h1;
@@ -518,6 +574,9 @@ struct WsB {
   uint16_t* csr_ptr;
   uint8_t* csr_src;
   float *ab, *att1, *att2;
+  bf16 *t_h, *t_x0, *t_P;     // discrete-feature tables: [n_keys][hid], [n_keys][hid], [n_keys][nproj*HC]
+  float* t_ab;                // [n_keys][2H]
+  uint32_t* key;              // [R]
 };
 
 size_t carve_b(const MlsNetDesc* d, int Gc, unsigned char* base, WsB* ws) {
@@ -538,6 +597,9 @@ size_t carve_b(const MlsNetDesc* d, int Gc, unsigned char* base, WsB* ws) {
   const size_t o_qg = take((size_t)Gc * 8), o_idx = take(R * 4), o_slot = take(R * 4), o_cnt = take(4);
   const size_t o_cptr = take(((size_t)Gc * (d->n_nodes + 1) + 64) * 2), o_csrc = take((size_t)Gc * d->n_nodes * kMaxNbr + 64);
   const size_t o_ab = take(R * 2 * d->heads * 4), o_att1 = take((size_t)2 * HC * 4), o_att2 = take((size_t)2 * HC * 4);
+  const size_t KT = (size_t)table_keys(d->n_nodes);
+  const size_t o_th = take(KT * hid * 2), o_tx0 = take(KT * hid * 2), o_tP = take(KT * nproj * HC * 2), o_tab = take(KT * 2 * d->heads * 4);
+  const size_t o_key = take(R * 4);
   if (ws) {
     auto B = [&](size_t o) { return reinterpret_cast<bf16*>(base + o); };
     auto F = [&](size_t o) { return reinterpret_cast<float*>(base + o); };
@@ -549,6 +611,7 @@ size_t carve_b(const MlsNetDesc* d, int Gc, unsigned char* base, WsB* ws) {
     ws->count = reinterpret_cast<int*>(base + o_cnt);
     ws->csr_ptr = reinterpret_cast<uint16_t*>(base + o_cptr); ws->csr_src = base + o_csrc;
     ws->ab = F(o_ab); ws->att1 = F(o_att1); ws->att2 = F(o_att2);
+    ws->t_h = B(o_th); ws->t_x0 = B(o_tx0); ws->t_P = B(o_tP); ws->t_ab = F(o_tab); ws->key = reinterpret_cast<uint32_t*>(base + o_key);
   }
   return off;
 }
@@ -676,10 +739,23 @@ int dgn_forward_bf16(const MlsNetDesc* d, const MlsNetWeights* w, const MlsForwa
   }
   cudaEvent_t ev0 = reinterpret_cast<cudaEvent_t>(a->prof_start), ev1 = reinterpret_cast<cudaEvent_t>(a->prof_stop);
   bool first_chunk = true;
+  int rc;
   auto prof_begin = [&](int which) { if (first_chunk && ev0 && ev1 && a->prof_kernel == which) cudaEventRecord(ev0, st); };
   auto prof_end = [&](int which) { if (first_chunk && ev0 && ev1 && a->prof_kernel == which) cudaEventRecord(ev1, st); };
-  int rc;
   const int use_fused = mls_get_option("fused_conv");
+  // discrete-feature mode: encoder + conv1 projections as a table over all feature keys, built once per call
+  const bool use_table = (a->flags & MLS_FWD_DISCRETE_FEATURES) && !(use_fused && !tr && !hl && N <= 100);
+  const int degbits = degree_bits(N), n_keys = table_keys(N);
+  if (use_table) {
+    const int rows_per_cta = 256 / (hid / 8);
+    enc0_keys_kernel<<<(n_keys + rows_per_cta - 1) / rows_per_cta, 256, 0, st>>>(n_keys, d->input_dim, w->enc_w0, w->enc_b0, hid, ws.t_h);
+    mls_count_launch();
+    GemmEpilogue e0{ws.t_x0, hid, w->enc_b1, nullptr, 0, N, 1, nullptr, nullptr};
+    if ((rc = gemm_bf16_launch(ws.t_h, hid, ws.w_enc1, hid, GemmShape{n_keys, hid, hid, nullptr}, e0, sms, st))) return rc;
+    GemmEpilogue e1{ws.t_P, nproj * HC, ws.b_c1, nullptr, 0, N, 0, tr ? nullptr : ws.att1, tr ? nullptr : ws.t_ab};
+    if ((rc = gemm_bf16_launch(ws.t_x0, hid, ws.w_c1, hid, GemmShape{n_keys, nproj * HC, hid, nullptr}, e1, sms, st))) return rc;
+    if (a->feature_errors) MLS_CUDA(cudaMemsetAsync(a->feature_errors, 0, sizeof(int), st));
+  }
   for (int g0 = 0; g0 < a->n_graphs; g0 += Gc) {
     const int gc = (a->n_graphs - g0) < Gc ? (a->n_graphs - g0) : Gc;
     const int rows = gc * N;
@@ -702,8 +778,12 @@ int dgn_forward_bf16(const MlsNetDesc* d, const MlsNetWeights* w, const MlsForwa
       }
     }
     mls_count_launch();
-    // encoder
-    {
+    // encoder (or, in discrete-feature mode, just the table keys of this pass)
+    if (use_table) {
+      feature_key_kernel<<<(rows + 255) / 256, 256, 0, st>>>(obs, a->obs_stride, N, rows, degbits, ws.key,
+                                                           reinterpret_cast<int*>(a->feature_errors));
+      mls_count_launch();
+    } else {
       const int rows_per_cta = 256 / (hid / 8);
       enc0_bf16_kernel<<<(rows + rows_per_cta - 1) / rows_per_cta, 256, 0, st>>>(obs, a->obs_stride, N, rows, d->input_dim, w->enc_w0,
                                                                                   w->enc_b0, hid, ws.h);
@@ -723,8 +803,8 @@ int dgn_forward_bf16(const MlsNetDesc* d, const MlsNetWeights* w, const MlsForwa
       if ((rc = fused_gatv2_conv_launch(ws.x0, ws.w_c1, fa, sms, st))) return rc;
       prof_end(MLS_PROF_EDGE1);
     } else {
-    // conv1 projections
-      {
+    // conv1 projections (table mode: already in ws.t_P for every feature key)
+      if (!use_table) {
         GemmEpilogue e{ws.P, nproj * HC, ws.b_c1, nullptr, 0, N, 0, tr ? nullptr : ws.att1, tr ? nullptr : ws.ab};
         prof_begin(MLS_PROF_PROJ1);
         if ((rc = gemm_bf16_launch(ws.x0, hid, ws.w_c1, hid, GemmShape{rows, nproj * HC, hid, nullptr}, e, sms, st))) return rc;
@@ -733,8 +813,9 @@ int dgn_forward_bf16(const MlsNetDesc* d, const MlsNetWeights* w, const MlsForwa
       // conv1 attention (+ReLU); snapshot x1[ctrl] (pre-mask) or HL-DGN pooling
       {
         EdgeArgs ea{};
-        ea.P = ws.P; ea.ldp = nproj * HC; ea.obs = obs; ea.obs_stride = a->obs_stride; ea.N = N; ea.H = H; ea.n_graphs = gc;
-        ea.att = w->c1_att; ea.bias = w->c1_bias; ea.csr_ptr = ws.csr_ptr; ea.csr_src = ws.csr_src; ea.ab = ws.ab;
+        ea.P = use_table ? ws.t_P : ws.P; ea.ldp = nproj * HC; ea.obs = obs; ea.obs_stride = a->obs_stride; ea.N = N; ea.H = H;
+        ea.n_graphs = gc; ea.row_key = use_table ? ws.key : nullptr;
+        ea.att = w->c1_att; ea.bias = w->c1_bias; ea.csr_ptr = ws.csr_ptr; ea.csr_src = ws.csr_src; ea.ab = use_table ? ws.t_ab : ws.ab;
         if (hl) { ea.x_out = nullptr; ea.slot = nullptr; ea.z = ws.z; ea.ldz = latent; ea.z_col = 0; ea.ctrl_only = 0; ea.pool_mode = d->pool; }
         else { ea.x_out = ws.x1; ea.slot = ws.slot; ea.z = ws.z; ea.ldz = latent; ea.z_col = hid; ea.ctrl_only = 0; ea.pool_mode = -1; }
         prof_begin(MLS_PROF_EDGE1);
@@ -768,7 +849,7 @@ int dgn_forward_bf16(const MlsNetDesc* d, const MlsNetWeights* w, const MlsForwa
         prof_end(MLS_PROF_EDGE2);
       }
       dim3 blk(16, 16);
-      gather_x0_kernel<<<(rows + 15) / 16, blk, 0, st>>>(ws.idx, ws.count, ws.x0, hid, ws.z, latent);
+      gather_x0_kernel<<<(rows + 15) / 16, blk, 0, st>>>(ws.idx, ws.count, use_table ? ws.t_x0 : ws.x0, use_table ? ws.key : nullptr, hid, ws.z, latent);
       mls_count_launch();
     }
     // dueling head on the tensor cores: [Q0;V0] stacked, then block-diagonal [Q1 0; 0 V1]

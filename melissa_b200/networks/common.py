@@ -172,15 +172,16 @@ class DGNBase(nn.Module):
             raise ValueError(f"Expected {expected} feature cols for nodes, got {dim - 1}")
         return bs
 
-    def _call(self, obs, stride, n_graphs, ctrl_mode, ctrl_mask, q, act, eps, seed, offset, rand3, offset_dev=None):
+    def _call(self, obs, stride, n_graphs, ctrl_mode, ctrl_mask, q, act, eps, seed, offset, rand3, offset_dev=None,
+              flags=0, feature_errors=None):
         L = _lib.lib()
         desc = self._desc()
         ws, keep = self.weights_struct()
         nbytes = L.mls_dgn_workspace_bytes(C.byref(desc), n_graphs)
         wsp = self._ws.get(nbytes, obs.device)
         args = _lib.MlsForwardArgs(obs.data_ptr(), stride, n_graphs, ctrl_mode, _lib.ptr(ctrl_mask), q.data_ptr(),
-                                   _lib.ptr(act), float(eps), 0, int(seed), int(offset), _lib.ptr(rand3),
-                                   wsp.data_ptr(), wsp.numel(), None, None, 0, 0, _lib.ptr(offset_dev))
+                                   _lib.ptr(act), float(eps), int(flags), int(seed), int(offset), _lib.ptr(rand3),
+                                   wsp.data_ptr(), wsp.numel(), None, None, 0, 0, _lib.ptr(offset_dev), _lib.ptr(feature_errors))
         prof = getattr(self, "_prof", None)
         if prof is not None:          # (cudaEvent start, cudaEvent stop, kernel id), see set_profile_events
             args.prof_start, args.prof_stop, args.prof_kernel = prof[0].cuda_event, prof[1].cuda_event, prof[2]
@@ -216,10 +217,16 @@ class DGNBase(nn.Module):
     def forward_graphs(self, obs_matrix: torch.Tensor, ctrl_mask: torch.Tensor, *, eps: float = 0.0,
                        philox_seed: int = 0, philox_offset: int = 0, rand3: Optional[torch.Tensor] = None,
                        q_out: Optional[torch.Tensor] = None, act_out: Optional[torch.Tensor] = None,
-                       philox_offset_dev: Optional[torch.Tensor] = None):
+                       philox_offset_dev: Optional[torch.Tensor] = None, discrete_features: bool = False,
+                       feature_errors: Optional[torch.Tensor] = None):
         """Rollout form: obs_matrix f32 [B, N, 8] (what ``BatchedGraphEnv`` emits), ctrl_mask
         u8 [B, N] (the active set).  One GNN pass per graph; returns (q f32 [B,N,2] -- zero
-        where not controlling, act i8 [B,N] -- -1 where not controlling)."""
+        where not controlling, act i8 [B,N] -- -1 where not controlling).
+
+        ``discrete_features=True`` (bf16 precision): the caller guarantees that the feature columns hold the
+        small integers the environment writes (always true for ``BatchedGraphEnv.obs``); encoder and conv1
+        projections are then evaluated once per distinct feature vector instead of once per node.
+        ``feature_errors`` (int32[1] device tensor) receives the number of rows violating that promise."""
         B, N, F = obs_matrix.shape
         if N != self.agents_num or F != self.input_dim + 3:
             raise ValueError(f"Expected obs_matrix [B, {self.agents_num}, {self.input_dim + 3}], got {tuple(obs_matrix.shape)}")
@@ -227,6 +234,7 @@ class DGNBase(nn.Module):
         q = q_out if q_out is not None else torch.empty(B, N, 2, dtype=torch.float32, device=dev)
         act = act_out if act_out is not None else torch.empty(B, N, dtype=torch.int8, device=dev)
         if B:
+            flags = _lib.FWD_DISCRETE_FEATURES if (discrete_features and self.precision == "bf16") else 0
             self._call(obs_matrix.contiguous(), N * F, B, 0, ctrl_mask.contiguous(), q, act, eps, philox_seed,
-                       philox_offset, rand3, philox_offset_dev)
+                       philox_offset, rand3, philox_offset_dev, flags, feature_errors)
         return q, act

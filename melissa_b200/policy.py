@@ -140,6 +140,7 @@ class BatchedCollector:
         B, N = env.B, env.N
         self.q = torch.zeros(B, N, 2, dtype=torch.float32, device=env.device)
         self.act = torch.full((B, N), -1, dtype=torch.int8, device=env.device)
+        self.feature_errors = torch.zeros(1, dtype=torch.int32, device=env.device)
         self.reset()
 
     def reset(self):
@@ -158,7 +159,8 @@ class BatchedCollector:
             self.act.copy_(torch.randint(0, 2, self.act.shape, device=env.device, dtype=torch.int8))
         else:
             self.policy.model.forward_graphs(env.obs, env.active, eps=eps, philox_seed=self.policy.seed,
-                                             philox_offset=self._round, q_out=self.q, act_out=self.act)
+                                             philox_offset=self._round, q_out=self.q, act_out=self.act,
+                                             discrete_features=True, feature_errors=self.feature_errors)
         env.step_device(self.act)
         self._round += 1
 

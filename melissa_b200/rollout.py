@@ -27,6 +27,10 @@ class Rollout:
         # device-side round counter: Philox offset of the exploration draws (so a captured CUDA
         # graph draws fresh noise on every replay)
         self.round_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+        # observations come from the environment kernel, whose feature columns are small integers:
+        # encoder + conv1 projections are evaluated per distinct feature vector (bf16 path)
+        self.discrete_features = True
+        self.feature_errors = torch.zeros(1, dtype=torch.int32, device=dev)
         self.graph = None
         # host mirrors for the end-to-end (host buffer) path
         self._host = None
@@ -54,7 +58,8 @@ class Rollout:
         env = self.env
         if self.net is not None:
             self.net.forward_graphs(obs, active, eps=self.eps, philox_seed=self.seed, philox_offset=0,
-                                    philox_offset_dev=self.round_dev, q_out=self.q, act_out=self.act)
+                                    philox_offset_dev=self.round_dev, q_out=self.q, act_out=self.act,
+                                    discrete_features=self.discrete_features, feature_errors=self.feature_errors)
         env.step_device(self.act)
         self.round_dev.add_(1)
 

@@ -268,3 +268,28 @@ def test_experimental_fused_conv_kernel_matches_two_kernel_path():
         assert float(np.abs(q1.cpu().numpy() - want).max()) <= BF16_TOL * scale
         assert float((q1 - q0).abs().max()) <= BF16_TOL * scale
         assert not torch.equal(q0, q1) or N == 12          # really a different code path
+
+
+@pytest.mark.parametrize("kind,kw", [("l_dgn", {}), ("dgn_r", {}), ("hl_dgn", {"aggregator": "max"}),
+                                     ("hl_dgn", {"aggregator": "mean"})])
+@pytest.mark.parametrize("N,B", [(50, 40), (20, 64), (12, 9), (200, 6)])
+def test_discrete_feature_table_path_is_bit_identical(kind, kw, N, B):
+    """MLS_FWD_DISCRETE_FEATURES: encoder + conv1 projections looked up per distinct feature vector.  The
+    table rows are produced by the same kernels on the same inputs, so Q-values and actions must equal the
+    per-node bf16 path bit for bit; the violation counter stays 0 on environment observations."""
+    sd = _random_sd(kind, 5)
+    om = _obs_matrix(N, B, 77)
+    cm = np.random.default_rng(3).random((B, N)) < 0.4
+    m = _module(kind, N, sd, **kw).set_precision("bf16")
+    args = (torch.as_tensor(om, device="cuda"), torch.as_tensor(cm, device="cuda").to(torch.uint8))
+    q0, a0 = m.forward_graphs(*args, eps=0.2, philox_seed=4, philox_offset=1)
+    err = torch.full((1,), 7, dtype=torch.int32, device="cuda")
+    q1, a1 = m.forward_graphs(*args, eps=0.2, philox_seed=4, philox_offset=1, discrete_features=True, feature_errors=err)
+    assert int(err.item()) == 0
+    assert torch.equal(q0, q1) and torch.equal(a0, a1)
+    # a non-integer feature is counted (and that row evaluated with key 0), never silently accepted
+    bad = om.copy()
+    bad[0, 0, 3] = 0.5
+    bad[B - 1, N - 1, 2] = -1.0
+    m.forward_graphs(torch.as_tensor(bad, device="cuda"), args[1], discrete_features=True, feature_errors=err)
+    assert int(err.item()) == 2
