@@ -36,7 +36,14 @@ extern "C" int mls_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc
 #include <stdlib.h>
 #include <string.h>
 static int g_fused_conv = -1;
+// "attn_mma": 1 (default) = in discrete-feature mode run conv1's attention through the pair-logit table and
+// the tensor-core aggregation kernel (attn_table.cu); 0 = gather kernel only.  Environment: MLS_ATTN_MMA.
+static int g_attn_mma = -1;
 extern "C" int mls_get_option(const char* key) {
+  if (key && !strcmp(key, "attn_mma")) {
+    if (g_attn_mma < 0) { const char* e = getenv("MLS_ATTN_MMA"); g_attn_mma = e ? atoi(e) : 1; }
+    return g_attn_mma;
+  }
   if (key && !strcmp(key, "fused_conv")) {
     if (g_fused_conv < 0) { const char* e = getenv("MLS_FUSED_CONV"); g_fused_conv = e ? atoi(e) : 0; }
     return g_fused_conv;
@@ -45,6 +52,7 @@ extern "C" int mls_get_option(const char* key) {
 }
 extern "C" int mls_set_option(const char* key, int value) {
   if (key && !strcmp(key, "fused_conv")) { g_fused_conv = value ? 1 : 0; return MLS_OK; }
+  if (key && !strcmp(key, "attn_mma")) { g_attn_mma = value ? 1 : 0; return MLS_OK; }
   mls_set_error("unknown option %s", key ? key : "(null)");
   return MLS_ERR_INVALID;
 }

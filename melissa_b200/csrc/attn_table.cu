@@ -1,0 +1,455 @@
+// Attention convolution in discrete-feature mode, on the tensor cores (sm_100a).
+//
+// With MLS_FWD_DISCRETE_FEATURES every node's encoder output and conv1 projections are rows of small
+// tables indexed by the node's feature key (dgn_forward_bf16.cu).  The attention logit of an edge then
+// depends only on the pair (target key, source key):
+//
+//   compact_keys_kernel   keys present in this pass -> dense ids 0..U-1
+//   pair_logit_kernel     E[ci][cj][h] = base-2 logit of head h for target key ci, source key cj
+//                           GATv2:       0.6 (a_j + b_i) + 0.4 sum_c att_c |x_l[j,c] + x_r[i,c]|
+//                           Transformer: <q_i, k_j> / sqrt(C)
+//   attn_table_mma_kernel per tile of G graphs (G*N <= 64 node rows), per head:
+//       producers (SIMT)   softmax weights p_ij = 2^(e_ij - max_i) from E, written as a bf16 matrix
+//                          W_h[target][source] (K-major, 128B swizzle); value rows x_l[key_j] / v[key_j]
+//                          gathered from the table into a [source][channel] operand (MN-major, 128B swizzle)
+//       tcgen05.mma        out_h[target][0..127] = W_h x V_h, fp32 accumulators in TMEM (one per head)
+//       epilogue warps     tcgen05.ld, x 1/sum_j p_ij, + bias, ReLU, bf16 -> x1 rows and controlling-node snapshots
+//     The weight matrix is block diagonal over the graphs of a tile; the aggregation over (at most 33)
+//     neighbours is done densely because the tensor core does the 64-wide row in one instruction.
+//
+// Reference math: PyG GATv2Conv / TransformerConv as used by l_dgn.py:125,133 and dgn_r.py; softmax
+// exp(e - max) / (sum + 1e-16).  Same results as edge_bf16_kernel up to bf16 rounding of the weights.
+#include "attn_table.cuh"
+
+#include "dgn_kernels.cuh"
+#include "tcgen05_ptx.cuh"
+
+namespace mls {
+
+namespace {
+
+typedef __nv_bfloat16 bf16;
+
+// cute::UMMA::SmemDescriptor, SWIZZLE_128B, explicit LBO / SBO (both in 16-byte units)
+__device__ __forceinline__ uint64_t make_smem_desc_ex(uint32_t smem_addr, uint32_t lbo16, uint32_t sbo16) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(lbo16 & 0x3FFFu) << 16;
+  d |= (uint64_t)(sbo16 & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// kind::f16 instruction descriptor with B MN-major (bit 16)
+__host__ __device__ constexpr uint32_t make_idesc_bmn(int M, int N) { return make_idesc(M, N) | (1u << 16); }
+
+__global__ void __launch_bounds__(128) umma_mn_probe_kernel(const bf16* __restrict__ A, const bf16* __restrict__ B, float* __restrict__ D,
+                                                            int rows_a, int kt, uint32_t lbo16, uint32_t sbo16, uint32_t kadv16) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char* sA = smem;                 // 128 rows x 128 B
+  unsigned char* sB = smem + 16384;         // 2 panels x 64 rows x 128 B
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 32768);
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(bar + 1);
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  for (int u = t; u < 128 * 8; u += 128) {
+    const int r = u >> 3, c = u & 7;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (r < rows_a) v = *reinterpret_cast<const uint4*>(A + (size_t)r * 64 + c * 8);
+    *reinterpret_cast<uint4*>(sA + r * 128 + ((c ^ (r & 7)) << 4)) = v;
+  }
+  for (int u = t; u < 64 * 16; u += 128) {
+    const int k = u >> 4, c = u & 15;       // node row k, 16-byte chunk c of its 128 channels
+    const int pn = c >> 3, ch = c & 7;
+    const uint4 v = *reinterpret_cast<const uint4*>(B + (size_t)k * 128 + c * 8);
+    *reinterpret_cast<uint4*>(sB + pn * 8192 + k * 128 + ((ch ^ (k & 7)) << 4)) = v;
+  }
+  fence_proxy_async();
+  if (t == 0) { mbar_init(smem_u32(bar), 1); fence_barrier_init(); }
+  if (warp == 0) tmem_alloc(smem_u32(tslot), 128);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tslot;
+  if (t == 0) {
+    const uint32_t idesc = make_idesc_bmn(128, 128);
+    const uint64_t da = make_smem_desc(smem_u32(sA)), db = make_smem_desc_ex(smem_u32(sB), lbo16, sbo16);
+    for (int k = 0; k < kt / 16; ++k) umma_bf16(tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * kadv16), idesc, k ? 1u : 0u);
+    umma_commit(smem_u32(bar));
+  }
+  mbar_wait(smem_u32(bar), 0);
+  tc_fence_after();
+  for (int c0 = 0; c0 < 128; c0 += 32) {
+    uint32_t v[32];
+    tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+    for (int j = 0; j < 32; ++j) D[(size_t)(warp * 32 + lane) * 128 + c0 + j] = __uint_as_float(v[j]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 128);
+}
+
+
+// ------------------------------------------------------------------------------ key compaction
+__global__ void __launch_bounds__(1024) compact_keys_kernel(uint8_t* __restrict__ used, int n_keys, uint16_t* __restrict__ cid_of_key,
+                                                            uint32_t* __restrict__ key_of_cid, int* __restrict__ n_used) {
+  __shared__ int s_warp[32];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int per = (n_keys + 1023) / 1024;
+  const int k0 = t * per, k1 = min(n_keys, k0 + per);
+  int cnt = 0;
+  for (int k = k0; k < k1; ++k) cnt += used[k] ? 1 : 0;
+  int incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int w = s_warp[lane], wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, wi, o);
+      if (lane >= o) wi += v;
+    }
+    s_warp[lane] = wi - w;
+    if (lane == 31) *n_used = wi;
+  }
+  __syncthreads();
+  int id = s_warp[warp] + incl - cnt;
+  for (int k = k0; k < k1; ++k) {
+    uint16_t c = 0xFFFF;
+    if (used[k]) {
+      if (id < kAttnUcap) { c = (uint16_t)id; key_of_cid[id] = (uint32_t)k; }
+      ++id;
+      used[k] = 0;
+    }
+    cid_of_key[k] = c;
+  }
+}
+
+__global__ void row_cid_kernel(const uint32_t* __restrict__ key, const uint16_t* __restrict__ cid_of_key, int rows,
+                               uint16_t* __restrict__ row_cid) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < rows) row_cid[r] = cid_of_key[key[r]];
+}
+
+__device__ __forceinline__ void unpack8(const uint4 u, float* f) {
+  const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { const float2 v = __bfloat1622float2(p[i]); f[2 * i] = v.x; f[2 * i + 1] = v.y; }
+}
+
+// ------------------------------------------------------------------------------ pair logits
+// One warp per (target key, 32 source keys); lane = (head, 16-channel slice).
+__global__ void __launch_bounds__(256) pair_logit_kernel(const AttnTableArgs a) {
+  const int U = *a.n_used;
+  if (U > kAttnUcap) return;
+  constexpr float kLog2e = 1.4426950408889634f;
+  const int H = a.H, HC = H * kC;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int h = lane >> 3, sub = lane & 7;
+  const int src_col = (a.transformer ? HC : 0) + h * kC + sub * 16;
+  const int tgt_col = (a.transformer ? 0 : HC) + h * kC + sub * 16;
+  float attn[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) attn[c] = a.transformer ? 1.f : a.att[h * kC + sub * 16 + c] * (0.4f * kLog2e);
+  const float tr_scale = kLog2e / sqrtf((float)kC);
+  const int nchunk = (U + 31) / 32;
+  const int tasks = U * nchunk;
+  for (int task = blockIdx.x * 8 + warp; task < tasks; task += gridDim.x * 8) {
+    const int ci = task / nchunk, cj0 = (task - ci * nchunk) * 32;
+    const uint32_t ki = a.key_of_cid[ci];
+    float tg[16];
+    {
+      const uint4* p = reinterpret_cast<const uint4*>(a.t_P + (size_t)ki * a.ldp + tgt_col);
+      unpack8(p[0], tg); unpack8(p[1], tg + 8);
+    }
+    const float b_i = a.transformer ? 0.f : a.t_ab[(size_t)ki * (2 * H) + H + h] * (0.6f * kLog2e);
+    const int cj1 = min(U, cj0 + 32);
+    for (int cj = cj0; cj < cj1; ++cj) {
+      const uint32_t kj = a.key_of_cid[cj];
+      float x[16];
+      const uint4* p = reinterpret_cast<const uint4*>(a.t_P + (size_t)kj * a.ldp + src_col);
+      unpack8(p[0], x); unpack8(p[1], x + 8);
+      float pa = 0.f, pb = 0.f;
+      if (a.transformer) {
+#pragma unroll
+        for (int c = 0; c < 16; c += 2) { pa = fmaf(x[c], tg[c], pa); pb = fmaf(x[c + 1], tg[c + 1], pb); }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 16; c += 2) { pa = fmaf(attn[c], fabsf(x[c] + tg[c]), pa); pb = fmaf(attn[c + 1], fabsf(x[c + 1] + tg[c + 1]), pb); }
+      }
+      float e = pa + pb;
+      e += __shfl_xor_sync(0xffffffffu, e, 1);
+      e += __shfl_xor_sync(0xffffffffu, e, 2);
+      e += __shfl_xor_sync(0xffffffffu, e, 4);
+      if (a.transformer) e *= tr_scale;
+      else e += a.t_ab[(size_t)kj * (2 * H) + h] * (0.6f * kLog2e) + b_i;
+      float4 o;
+      o.x = __shfl_sync(0xffffffffu, e, 0); o.y = __shfl_sync(0xffffffffu, e, 8);
+      o.z = __shfl_sync(0xffffffffu, e, 16); o.w = __shfl_sync(0xffffffffu, e, 24);
+      if (lane == 0) reinterpret_cast<float4*>(a.E)[(size_t)ci * kAttnUcap + cj] = o;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------ aggregation on the tensor cores
+constexpr int kTThreads = 640;                 // 20 warps: w & 3 = TMEM lane quarter, w >> 2 = group
+constexpr int kProducers = 320;                // warps with quarter 2, 3
+constexpr int kAHead = 64 * 128;               // weight matrix of one head: 64 targets x 64 sources bf16
+constexpr int kBPanel = 64 * 128;              // value panel: 64 sources x 64 channels bf16
+constexpr int kStageA = 4 * kAHead;            // 32 KiB
+constexpr int kStageB = 8 * kBPanel;           // 64 KiB
+constexpr int kStage = kStageA + kStageB;      // 96 KiB
+constexpr int kMetaSrc = 64 * kMaxNbr;         // CSR source lists of a tile
+constexpr int kMeta = kMetaSrc + 64 * 4 /*keys*/ + 64 * 2 /*ids*/ + 128 * 2 /*CSR row pointers*/;
+constexpr int kTSmem = 2 * kStage + 4 * 64 * 4 * 4 /*inv_den ring*/ + 2 * kMeta + 512 * 4 /*bias*/ + 256 /*barriers*/ + 1024;
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+__device__ __forceinline__ float f_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float f_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ void bar_producers() { asm volatile("bar.sync 1, 320;" ::: "memory"); }
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+
+__global__ void __launch_bounds__(kTThreads, 1) attn_table_mma_kernel(const AttnTableArgs a, const int G) {
+  if (*a.n_used > kAttnUcap) return;            // uniform: the gather kernel handles this pass
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  // 1024-byte alignment by offset (not by integer round trip): the compiler keeps the shared address space -> LDS / STS
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  float* inv_den = reinterpret_cast<float*>(smem + 2 * kStage);                  // [4][64][4]
+  unsigned char* meta = reinterpret_cast<unsigned char*>(inv_den + 4 * 64 * 4);    // [2][kMeta]
+  float* bias_s = reinterpret_cast<float*>(meta + 2 * kMeta);                     // [512]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + 512);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  const uint32_t bar0 = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (2 + s); };
+  auto tfull_bar = [&](int h) { return bar0 + 8u * (4 + h); };
+  auto tempty_bar = [&](int h) { return bar0 + 8u * (8 + h); };
+
+  const int N = a.N, HC = 4 * kC;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int quarter = warp & 3, grp = warp >> 2;
+  const int n_tiles = (a.n_graphs + G - 1) / G;
+
+  // value panels start out finite (rows beyond a tile's node count are multiplied by zero weights)
+  for (int u = threadIdx.x; u < 2 * kStage / 16; u += kTThreads) reinterpret_cast<uint4*>(smem)[u] = make_uint4(0, 0, 0, 0);
+  for (int u = threadIdx.x; u < 512; u += kTThreads) bias_s[u] = a.bias ? a.bias[u] : 0.f;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 2; ++s) { mbar_init(full_bar(s), kProducers); mbar_init(empty_bar(s), 1); }
+    for (int h = 0; h < 4; ++h) { mbar_init(tfull_bar(h), 1); mbar_init(tempty_bar(h), 64); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (quarter >= 2) {
+    // ===================================================================== producers
+    const int pt = (grp * 2 + (quarter - 2)) * 32 + lane;          // 0..319
+    const int vcol = a.transformer ? 2 * HC : 0;
+    const int self = a.transformer ? 0 : 1;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const int s = it & 1;
+      const int g0 = tile * G, gt = min(G, a.n_graphs - g0), rt = gt * N;
+      const size_t m0 = (size_t)g0 * N;
+      unsigned char* sA = smem + s * kStage;
+      unsigned char* sB = sA + kStageA;
+      const uint8_t* src_s = meta + s * kMeta;                                 // [gt][N*32]
+      const uint32_t* key_s = reinterpret_cast<const uint32_t*>(src_s + kMetaSrc);   // [64]
+      const uint16_t* cid = reinterpret_cast<const uint16_t*>(key_s + 64);     // [64]
+      const uint16_t* ptr_s = cid + 64;                                        // [gt][N+1]
+      mbar_wait(empty_bar(s), ((it >> 1) & 1) ^ 1);
+      // ---- phase A: tile metadata (all global loads issued before the first dependent store) and the cleared weight matrices
+      {
+        uint32_t kv = 0, pv = 0;
+        uint16_t cv = 0;
+        uint4 sv = make_uint4(0, 0, 0, 0);
+        if (pt < rt) { kv = __ldg(a.key + m0 + pt); cv = __ldg(a.row_cid + m0 + pt); }
+        if (pt < gt * (N + 1)) pv = __ldg(a.csr_ptr + (size_t)g0 * (N + 1) + pt);                    // gt * (N + 1) <= 128
+        if (pt < rt * 2) sv = __ldg(reinterpret_cast<const uint4*>(a.csr_src + (size_t)g0 * N * kMaxNbr) + pt);   // N*32 bytes per graph
+        for (int u = pt; u < kStageA / 16; u += kProducers) reinterpret_cast<uint4*>(sA)[u] = make_uint4(0, 0, 0, 0);
+        if (pt < rt) { const_cast<uint32_t*>(key_s)[pt] = kv; const_cast<uint16_t*>(cid)[pt] = cv; }
+        if (pt < gt * (N + 1)) const_cast<uint16_t*>(ptr_s)[pt] = (uint16_t)pv;
+        if (pt < rt * 2) reinterpret_cast<uint4*>(const_cast<uint8_t*>(src_s))[pt] = sv;
+      }
+      bar_producers();
+      // ---- phase B: value rows of the tile's nodes (64 x 16 B per node -> 8 panels: head, channel half), asynchronously
+      {
+        const uint32_t sB32 = smem_u32(sB);
+        for (int u = pt; u < rt * 64; u += kProducers) {
+          const int j = u >> 6, c = u & 63;
+          cp_async16(sB32 + (c >> 3) * kBPanel + j * 128 + (((c & 7) ^ (j & 7)) << 4),
+                     reinterpret_cast<const uint4*>(a.t_P + (size_t)key_s[j] * a.ldp + vcol) + c);
+        }
+      }
+      // ---- softmax weights of (target i, head h)
+      float* inv = inv_den + (it & 3) * 256;
+      for (int tt = pt; tt < rt * 4; tt += kProducers) {
+        const int i = tt >> 2, h = tt & 3;
+        const int gl = i / N, il = i - gl * N, rbase = gl * N;
+        const uint16_t* ptr = ptr_s + gl * (N + 1);
+        const int r0 = ptr[il], d = (int)ptr[il + 1] - r0;
+        const uint8_t* src = src_s + gl * N * kMaxNbr + r0;
+        const float* Erow = a.E + (size_t)cid[i] * kAttnUcap * 4 + h;
+        // entry 0 = the self loop (GATv2), then the CSR neighbours; batches of 8 independent table reads
+        const int cnt = d + self;
+        unsigned char* arow = sA + h * kAHead + i * 128;
+        const int sw = i & 7;
+        float ev[8];
+        int jv[8];
+        float mx = -INFINITY;
+        for (int k0 = 0; k0 < cnt; k0 += 8) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const int k = k0 + q;
+            jv[q] = (k < cnt && k >= self) ? rbase + src[k - self] : i;
+            ev[q] = __ldg(Erow + (int)cid[jv[q]] * 4);
+          }
+#pragma unroll
+          for (int q = 0; q < 8; ++q) if (k0 + q < cnt) mx = fmaxf(mx, ev[q]);
+        }
+        float sum = 0.f;
+        for (int k0 = 0; k0 < cnt; k0 += 8) {
+          if (cnt > 8) {                                     // more than one batch: read the logits again (L1)
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const int k = k0 + q;
+              jv[q] = (k < cnt && k >= self) ? rbase + src[k - self] : i;
+              ev[q] = __ldg(Erow + (int)cid[jv[q]] * 4);
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            if (k0 + q < cnt) {
+              const int j = jv[q];
+              const __nv_bfloat16 pb = __float2bfloat16_rn(f_ex2(ev[q] - mx));
+              sum += __bfloat162float(pb);
+              *reinterpret_cast<__nv_bfloat16*>(arow + (((j >> 3) ^ sw) << 4) + (j & 7) * 2) = pb;
+            }
+          }
+        }
+        inv[i * 4 + h] = f_rcp(sum + 1e-16f);
+      }
+      cp_async_wait_all();
+      fence_proxy_async();
+      mbar_arrive(full_bar(s));
+    }
+  } else if (warp == 0) {
+    // ===================================================================== MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bmn(128, 128);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int s = it & 1;
+        const int g0 = tile * G, gt = min(G, a.n_graphs - g0), rt = gt * N;
+        const int ksteps = (rt + 15) >> 4;
+        const uint32_t sA = smem_u32(smem + s * kStage), sB = sA + kStageA;
+        mbar_wait(full_bar(s), (it >> 1) & 1);
+        tc_fence_after();
+        for (int h = 0; h < 4; ++h) {
+          mbar_wait(tempty_bar(h), (it & 1) ^ 1);
+          tc_fence_after();
+          const uint64_t da = make_smem_desc(sA + h * kAHead);
+          const uint64_t db = make_smem_desc_ex(sB + h * 2 * kBPanel, kBPanel >> 4, 1024 >> 4);
+          for (int k = 0; k < ksteps; ++k) umma_bf16(tmem_base + (uint32_t)(h * 128), da + (uint64_t)(k * 2), db + (uint64_t)(k * 128), idesc, k ? 1u : 0u);
+          umma_commit(tfull_bar(h));
+        }
+        umma_commit(empty_bar(s));
+      }
+    }
+  } else if (grp >= 1) {
+    // ===================================================================== epilogue (quarter 0, 1; head = grp - 1)
+    const int h = grp - 1;
+    const int r = quarter * 32 + lane;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const int g0 = tile * G, gt = min(G, a.n_graphs - g0), rt = gt * N;
+      const size_t row = (size_t)g0 * N + r;
+      const bool valid = r < rt;
+      const int sl = (valid && a.slot) ? a.slot[row] : -1;
+      mbar_wait(tfull_bar(h), it & 1);
+      tc_fence_after();
+      const float inv = valid ? inv_den[(it & 3) * 256 + r * 4 + h] : 0.f;
+      bf16* xo = a.x_out ? a.x_out + row * HC + h * kC : nullptr;
+      bf16* zo = (a.z && sl >= 0) ? a.z + (size_t)sl * a.ldz + a.z_col + h * kC : nullptr;
+#pragma unroll 1
+      for (int c0 = 0; c0 < kC; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(h * 128 + c0), v);
+        if (c0 == kC - 32) { tc_fence_before(); mbar_arrive(tempty_bar(h)); }
+        if (valid) {
+          const float* bs = bias_s + h * kC + c0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            const float4 b0 = *reinterpret_cast<const float4*>(bs + j), b1 = *reinterpret_cast<const float4*>(bs + j + 4);
+            uint4 o;
+            o.x = pack_bf16x2(fmaxf(fmaf(__uint_as_float(v[j]), inv, b0.x), 0.f), fmaxf(fmaf(__uint_as_float(v[j + 1]), inv, b0.y), 0.f));
+            o.y = pack_bf16x2(fmaxf(fmaf(__uint_as_float(v[j + 2]), inv, b0.z), 0.f), fmaxf(fmaf(__uint_as_float(v[j + 3]), inv, b0.w), 0.f));
+            o.z = pack_bf16x2(fmaxf(fmaf(__uint_as_float(v[j + 4]), inv, b1.x), 0.f), fmaxf(fmaf(__uint_as_float(v[j + 5]), inv, b1.y), 0.f));
+            o.w = pack_bf16x2(fmaxf(fmaf(__uint_as_float(v[j + 6]), inv, b1.z), 0.f), fmaxf(fmaf(__uint_as_float(v[j + 7]), inv, b1.w), 0.f));
+            if (xo) *reinterpret_cast<uint4*>(xo + c0 + j) = o;
+            if (zo) *reinterpret_cast<uint4*>(zo + c0 + j) = o;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace
+
+int attn_table_conv_launch(const AttnTableArgs& a, int sm_count, cudaStream_t st) {
+  if (!attn_table_supported(a.N, a.H)) {
+    mls_set_error("table-mode attention: unsupported shape (N=%d, H=%d)", a.N, a.H);
+    return MLS_ERR_UNSUPPORTED;
+  }
+  static bool configured = false;
+  if (!configured) {
+    MLS_CUDA(cudaFuncSetAttribute(attn_table_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTSmem));
+    configured = true;
+  }
+  compact_keys_kernel<<<1, 1024, 0, st>>>(a.used, a.n_keys, a.cid_of_key, a.key_of_cid, a.n_used);
+  const int rows = a.n_graphs * a.N;
+  row_cid_kernel<<<(rows + 255) / 256, 256, 0, st>>>(a.key, a.cid_of_key, rows, a.row_cid);
+  pair_logit_kernel<<<sm_count * 2, 256, 0, st>>>(a);
+  const int G = kAttnMaxRows / a.N;
+  const int n_tiles = (a.n_graphs + G - 1) / G;
+  const int grid = n_tiles < sm_count ? n_tiles : sm_count;
+  if (grid > 0) attn_table_mma_kernel<<<grid, kTThreads, kTSmem, st>>>(a, G);
+  mls_count_launch(4);
+  MLS_LAUNCH_CHECK();
+  return MLS_OK;
+}
+
+}  // namespace mls
+
+// Standalone entry for tests/test_gemm_gpu.py: D[128 x 128] = A[rows_a x 64] (K-major) x B[64 x 128] (MN-major), K = kt.
+extern "C" int mls_test_umma_mn(const void* A, const void* B, float* D, int rows_a, int kt, unsigned lbo16, unsigned sbo16,
+                                unsigned kadv16, void* stream) {
+  static bool configured = false;
+  if (!configured) {
+    MLS_CUDA(cudaFuncSetAttribute(mls::umma_mn_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 40 * 1024));
+    configured = true;
+  }
+  mls::umma_mn_probe_kernel<<<1, 128, 40 * 1024, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const mls::bf16*>(A), reinterpret_cast<const mls::bf16*>(B), D, rows_a, kt, lbo16, sbo16, kadv16);
+  MLS_LAUNCH_CHECK();
+  return MLS_OK;
+}

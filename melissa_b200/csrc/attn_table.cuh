@@ -1,0 +1,48 @@
+// Table-mode attention convolution on the tensor cores (discrete node features), see attn_table.cu.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace mls {
+
+constexpr int kAttnUcap = 1024;      // distinct feature keys per pass the pair-logit table is sized for
+constexpr int kAttnMaxRows = 64;     // node rows per tile (one 64-wide K panel of the weight matrix)
+
+struct AttnTableArgs {
+  // projection tables over all feature keys (MLS_FWD_DISCRETE_FEATURES)
+  const __nv_bfloat16* t_P;  // [n_keys][ldp]  GATv2 [x_l | x_r], Transformer [q | k | v]
+  int ldp;
+  const float* t_ab;         // GATv2 [n_keys][2H]: <att_h, x_l>, <att_h, x_r>
+  const float* att;          // GATv2 [H*C]
+  const float* bias;         // GATv2 conv bias [H*C]; NULL for the Transformer conv
+  int transformer;
+  // this pass
+  const uint32_t* key;       // [rows] feature key of every node row
+  int N, H, n_graphs;
+  const uint16_t* csr_ptr;   // [graphs][N+1]
+  const uint8_t* csr_src;    // [graphs][N*32]
+  const int* slot;           // [rows] controlling-list slot or -1
+  __nv_bfloat16* x_out;      // [rows][H*C] relu(conv)
+  __nv_bfloat16* z;          // snapshot rows
+  int ldz, z_col;
+  // scratch (workspace)
+  uint8_t* used;             // [n_keys] marked by feature_key_kernel, cleared here
+  int n_keys;
+  uint16_t* cid_of_key;      // [n_keys] compact id of a key present in this pass (0xFFFF otherwise)
+  uint32_t* key_of_cid;      // [kAttnUcap]
+  uint16_t* row_cid;         // [rows] compact id of every node row
+  int* n_used;               // [1] number of distinct keys; > kAttnUcap: the caller's gather kernel runs instead
+  float* E;                  // [kAttnUcap][kAttnUcap][4] base-2 logits of (target key, source key) for the 4 heads
+};
+
+// scratch bytes behind `E`
+inline size_t attn_table_pair_bytes() { return (size_t)kAttnUcap * kAttnUcap * 4 * sizeof(float); }
+// true when this (N, H) can take the tensor-core path at all
+inline bool attn_table_supported(int N, int H) { return N >= 1 && N <= kAttnMaxRows && H == 4; }
+
+int attn_table_conv_launch(const AttnTableArgs& a, int sm_count, cudaStream_t st);
+
+}  // namespace mls

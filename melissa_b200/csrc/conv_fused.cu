@@ -65,8 +65,9 @@ __host__ __device__ inline FSmem fused_layout(int rt, int G, int N) {
 
 __global__ void __launch_bounds__(kFThreads, 1)
 fused_gatv2_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const FusedConvArgs a) {
-  extern __shared__ unsigned char smem_raw[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  // aligned by offset so that the compiler keeps the shared address space (LDS / STS instead of generic LD / ST)
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int N = a.N, H = a.H, HC = H * kC, G = a.G;
   const int rt_max = G * N;
   const FSmem L = fused_layout(rt_max, G, N);

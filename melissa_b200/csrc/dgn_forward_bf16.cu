@@ -12,6 +12,7 @@
 // (tolerance stated in tests/test_networks_gpu.py).  Reference math: see dgn_forward.cu.
 #include "dgn_kernels.cuh"
 #include "gemm_tcgen05.cuh"
+#include "attn_table.cuh"
 #include "conv_fused.cuh"
 
 namespace mls {
@@ -107,7 +108,7 @@ __device__ __forceinline__ void key_decode(uint32_t key, float (&f)[5]) {
   f[1] = (float)((key >> 3) & 63u); f[0] = (float)(key >> 9);
 }
 __global__ void feature_key_kernel(const float* __restrict__ obs, int64_t obs_stride, int N, int rows, int degbits,
-                                   uint32_t* __restrict__ key, int* __restrict__ errors) {
+                                   uint32_t* __restrict__ key, int* __restrict__ errors, uint8_t* __restrict__ used) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= rows) return;
   const int g = r / N, i = r - g * N;
@@ -119,6 +120,7 @@ __global__ void feature_key_kernel(const float* __restrict__ obs, int64_t obs_st
   if (ok) k = (((((uint32_t)deg << 6) | (uint32_t)msgs) << 1 | (uint32_t)act) << 1 | (uint32_t)intr) << 1 | (uint32_t)hm;
   else if (errors) atomicAdd(errors, 1);
   key[r] = k;
+  if (used && !used[k]) used[k] = 1;   // keys present in this pass (attn_table.cu compacts them); benign race, few distinct keys
 }
 __global__ void __launch_bounds__(256) enc0_keys_kernel(int n_keys, int in_dim, const float* __restrict__ w0,
                                                         const float* __restrict__ b0, int hidden, bf16* __restrict__ h) {
@@ -220,6 +222,8 @@ struct EdgeArgs {
   int ldz, z_col;
   int ctrl_only;          // compute only nodes with slot >= 0
   int pool_mode;          // >= 0: HL-DGN pooling of relu(conv)*dm into z[g][H*C] (enum MlsPool); -1 none
+  const int* run_if_gt;   // optional device int: the kernel only runs when *run_if_gt > run_thresh
+  int run_thresh;         // (fallback behind the tensor-core table kernel, attn_table.cu)
 };
 
 // CTA size per variant: what matters is how many CTAs fit an SM (shared memory: 2 staged operands for
@@ -265,8 +269,12 @@ __global__ void __launch_bounds__(EdgeCfg<TRANSFORMER>::kThreads, 512 / EdgeCfg<
   float* poolbuf = reinterpret_cast<float*>(s_slot + N);                         // [warps][kC]  (16 B aligned: 4N floats before it)
   uint16_t* s_ptr = reinterpret_cast<uint16_t*>(poolbuf + (a.pool_mode >= 0 ? kEdgeWarps * kC : 0));   // [N+1]
   uint8_t* s_src = reinterpret_cast<uint8_t*>(s_ptr + N + 1);                    // [E]
-  const int g = blockIdx.x / H, h = blockIdx.x - g * H;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (a.run_if_gt && *a.run_if_gt <= a.run_thresh) return;
+  // one (graph, head) per CTA; the fallback launch behind the table kernel uses a small grid and strides
+  for (int blk = blockIdx.x; blk < a.n_graphs * H; blk += gridDim.x) {
+  if (blk != (int)blockIdx.x) __syncthreads();
+  const int g = blk / H, h = blk - g * H;
   const float* g_obs = a.obs + (int64_t)g * a.obs_stride;
   const size_t base = (size_t)g * N;
   constexpr float kLog2e = 1.4426950408889634f;
@@ -435,6 +443,7 @@ __global__ void __launch_bounds__(EdgeCfg<TRANSFORMER>::kThreads, 512 / EdgeCfg<
       a.z[(size_t)g * a.ldz + a.z_col + h * kC + tid] = __float2bfloat16_rn(r);
     }
   }
+  }
 }
 
 // ------------------------------------------------------------------------------ controlling nodes
@@ -577,6 +586,13 @@ struct WsB {
   bf16 *t_h, *t_x0, *t_P;     // discrete-feature tables: [n_keys][hid], [n_keys][hid], [n_keys][nproj*HC]
   float* t_ab;                // [n_keys][2H]
   uint32_t* key;              // [R]
+  // tensor-core table attention (attn_table.cu)
+  uint8_t* used;              // [n_keys]
+  uint16_t* cid_of_key;       // [n_keys]
+  uint32_t* key_of_cid;       // [kAttnUcap]
+  int* n_used;
+  uint16_t* row_cid;          // [R]
+  float* pairE;               // [kAttnUcap][kAttnUcap][4]
 };
 
 size_t carve_b(const MlsNetDesc* d, int Gc, unsigned char* base, WsB* ws) {
@@ -600,6 +616,9 @@ size_t carve_b(const MlsNetDesc* d, int Gc, unsigned char* base, WsB* ws) {
   const size_t KT = (size_t)table_keys(d->n_nodes);
   const size_t o_th = take(KT * hid * 2), o_tx0 = take(KT * hid * 2), o_tP = take(KT * nproj * HC * 2), o_tab = take(KT * 2 * d->heads * 4);
   const size_t o_key = take(R * 4);
+  const bool mma_ok = attn_table_supported(d->n_nodes, d->heads) && !hl;
+  const size_t o_used = take(KT), o_cok = take(KT * 2), o_koc = take(kAttnUcap * 4), o_nu = take(4);
+  const size_t o_pe = take(mma_ok ? attn_table_pair_bytes() : 0), o_rcid = take(R * 2);
   if (ws) {
     auto B = [&](size_t o) { return reinterpret_cast<bf16*>(base + o); };
     auto F = [&](size_t o) { return reinterpret_cast<float*>(base + o); };
@@ -612,6 +631,9 @@ size_t carve_b(const MlsNetDesc* d, int Gc, unsigned char* base, WsB* ws) {
     ws->csr_ptr = reinterpret_cast<uint16_t*>(base + o_cptr); ws->csr_src = base + o_csrc;
     ws->ab = F(o_ab); ws->att1 = F(o_att1); ws->att2 = F(o_att2);
     ws->t_h = B(o_th); ws->t_x0 = B(o_tx0); ws->t_P = B(o_tP); ws->t_ab = F(o_tab); ws->key = reinterpret_cast<uint32_t*>(base + o_key);
+    ws->used = base + o_used; ws->cid_of_key = reinterpret_cast<uint16_t*>(base + o_cok);
+    ws->key_of_cid = reinterpret_cast<uint32_t*>(base + o_koc); ws->n_used = reinterpret_cast<int*>(base + o_nu);
+    ws->pairE = F(o_pe); ws->row_cid = reinterpret_cast<uint16_t*>(base + o_rcid);
   }
   return off;
 }
@@ -633,7 +655,9 @@ int launch_edge(cudaStream_t st, const EdgeArgs& ea) {
     MLS_CUDA(cudaFuncSetAttribute(edge_bf16_kernel<TR>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     configured = smem;
   }
-  edge_bf16_kernel<TR><<<ea.n_graphs * ea.H, kEdgeThreads, smem, st>>>(ea);
+  int grid = ea.n_graphs * ea.H;
+  if (ea.run_if_gt && grid > 148 * 4) grid = 148 * 4;      // normally exits at once
+  edge_bf16_kernel<TR><<<grid, kEdgeThreads, smem, st>>>(ea);
   mls_count_launch();
   MLS_LAUNCH_CHECK();
   return MLS_OK;
@@ -755,7 +779,10 @@ int dgn_forward_bf16(const MlsNetDesc* d, const MlsNetWeights* w, const MlsForwa
     GemmEpilogue e1{ws.t_P, nproj * HC, ws.b_c1, nullptr, 0, N, 0, tr ? nullptr : ws.att1, tr ? nullptr : ws.t_ab};
     if ((rc = gemm_bf16_launch(ws.t_x0, hid, ws.w_c1, hid, GemmShape{n_keys, nproj * HC, hid, nullptr}, e1, sms, st))) return rc;
     if (a->feature_errors) MLS_CUDA(cudaMemsetAsync(a->feature_errors, 0, sizeof(int), st));
+    MLS_CUDA(cudaMemsetAsync(ws.used, 0, (size_t)n_keys, st));
   }
+  // conv1 attention through the pair-logit table + tensor-core aggregation (L-DGN / DGN-R, graphs of <= 64 nodes)
+  const bool use_mma = use_table && !hl && attn_table_supported(N, H) && mls_get_option("attn_mma");
   for (int g0 = 0; g0 < a->n_graphs; g0 += Gc) {
     const int gc = (a->n_graphs - g0) < Gc ? (a->n_graphs - g0) : Gc;
     const int rows = gc * N;
@@ -781,7 +808,7 @@ int dgn_forward_bf16(const MlsNetDesc* d, const MlsNetWeights* w, const MlsForwa
     // encoder (or, in discrete-feature mode, just the table keys of this pass)
     if (use_table) {
       feature_key_kernel<<<(rows + 255) / 256, 256, 0, st>>>(obs, a->obs_stride, N, rows, degbits, ws.key,
-                                                           reinterpret_cast<int*>(a->feature_errors));
+                                                           reinterpret_cast<int*>(a->feature_errors), use_mma ? ws.used : nullptr);
       mls_count_launch();
     } else {
       const int rows_per_cta = 256 / (hid / 8);
@@ -819,6 +846,16 @@ int dgn_forward_bf16(const MlsNetDesc* d, const MlsNetWeights* w, const MlsForwa
         if (hl) { ea.x_out = nullptr; ea.slot = nullptr; ea.z = ws.z; ea.ldz = latent; ea.z_col = 0; ea.ctrl_only = 0; ea.pool_mode = d->pool; }
         else { ea.x_out = ws.x1; ea.slot = ws.slot; ea.z = ws.z; ea.ldz = latent; ea.z_col = hid; ea.ctrl_only = 0; ea.pool_mode = -1; }
         prof_begin(MLS_PROF_EDGE1);
+        if (use_mma) {
+          AttnTableArgs ta{};
+          ta.t_P = ws.t_P; ta.ldp = nproj * HC; ta.t_ab = ws.t_ab; ta.att = w->c1_att; ta.bias = tr ? nullptr : w->c1_bias;
+          ta.transformer = tr ? 1 : 0; ta.key = ws.key; ta.N = N; ta.H = H; ta.n_graphs = gc; ta.csr_ptr = ws.csr_ptr;
+          ta.csr_src = ws.csr_src; ta.slot = ws.slot; ta.x_out = ws.x1; ta.z = ws.z; ta.ldz = latent; ta.z_col = hid;
+          ta.used = ws.used; ta.n_keys = n_keys; ta.cid_of_key = ws.cid_of_key; ta.key_of_cid = ws.key_of_cid;
+          ta.n_used = ws.n_used; ta.E = ws.pairE; ta.row_cid = ws.row_cid;
+          if ((rc = attn_table_conv_launch(ta, sms, st))) return rc;
+          ea.run_if_gt = ws.n_used; ea.run_thresh = kAttnUcap;      // more distinct keys than the table holds: gather kernel
+        }
         if ((rc = edge_dispatch(st, ea, tr, Wn))) return rc;
         prof_end(MLS_PROF_EDGE1);
       }

@@ -28,9 +28,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          const GemmShape shape, const GemmEpilogue epi) {
   using S = GemmSmem<BN>;
-  extern __shared__ unsigned char smem_raw[];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // aligned by offset so that the compiler keeps the shared address space (LDS / STS instead of generic LD / ST)
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kBarOffset);
   // bars[0..S) full, [S..2S) empty, [2S..2S+2) tmem_full, [2S+2..2S+4) tmem_empty
   constexpr int kStages = S::kNumStages;

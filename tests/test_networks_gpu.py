@@ -270,13 +270,25 @@ def test_experimental_fused_conv_kernel_matches_two_kernel_path():
         assert not torch.equal(q0, q1) or N == 12          # really a different code path
 
 
+@pytest.fixture
+def gather_attention():
+    """Discrete-feature mode with the gather kernel only (no pair-logit table / tensor-core aggregation)."""
+    from melissa_b200 import _lib
+    old = _lib.get_option("attn_mma")
+    _lib.set_option("attn_mma", 0)
+    yield
+    _lib.set_option("attn_mma", old)
+
+
 @pytest.mark.parametrize("kind,kw", [("l_dgn", {}), ("dgn_r", {}), ("hl_dgn", {"aggregator": "max"}),
                                      ("hl_dgn", {"aggregator": "mean"})])
 @pytest.mark.parametrize("N,B", [(50, 40), (20, 64), (12, 9), (200, 6)])
-def test_discrete_feature_table_path_is_bit_identical(kind, kw, N, B):
+def test_discrete_feature_table_path_is_bit_identical(kind, kw, N, B, gather_attention):
     """MLS_FWD_DISCRETE_FEATURES: encoder + conv1 projections looked up per distinct feature vector.  The
     table rows are produced by the same kernels on the same inputs, so Q-values and actions must equal the
     per-node bf16 path bit for bit; the violation counter stays 0 on environment observations."""
+    if kind == "dgn_r" and N == 200:
+        pytest.skip("bf16 Transformer attention stages 3 operands: 200-node graphs exceed shared memory (fp32 path)")
     sd = _random_sd(kind, 5)
     om = _obs_matrix(N, B, 77)
     cm = np.random.default_rng(3).random((B, N)) < 0.4
@@ -293,3 +305,50 @@ def test_discrete_feature_table_path_is_bit_identical(kind, kw, N, B):
     bad[B - 1, N - 1, 2] = -1.0
     m.forward_graphs(torch.as_tensor(bad, device="cuda"), args[1], discrete_features=True, feature_errors=err)
     assert int(err.item()) == 2
+
+
+@pytest.mark.parametrize("kind", ["l_dgn", "dgn_r"])
+@pytest.mark.parametrize("N,B", [(50, 300), (20, 64), (12, 9), (64, 33), (7, 1000)])
+def test_tensor_core_table_attention_within_tolerance(kind, N, B):
+    """attn_table.cu (default in discrete-feature mode, graphs of <= 64 nodes): softmax weights from the
+    pair-logit table, aggregation on tcgen05.  Differs from the gather kernel only by bf16 rounding of the
+    softmax weights: within the stated bf16 tolerance of the fp32 oracle, and close to the gather path."""
+    from melissa_b200 import _lib
+    assert _lib.get_option("attn_mma") == 1
+    sd = _random_sd(kind, 6)
+    om = _obs_matrix(N, B, 78)
+    cm = np.random.default_rng(4).random((B, N)) < 0.4
+    want = no.forward_graphs(kind, sd, torch.as_tensor(om), torch.as_tensor(cm), N).numpy()
+    m = _module(kind, N, sd).set_precision("bf16")
+    args = (torch.as_tensor(om, device="cuda"), torch.as_tensor(cm, device="cuda").to(torch.uint8))
+    q0, _ = m.forward_graphs(*args)
+    err = torch.zeros(1, dtype=torch.int32, device="cuda")
+    q1, a1 = m.forward_graphs(*args, discrete_features=True, feature_errors=err)
+    assert int(err.item()) == 0
+    scale = max(1.0, float(np.abs(want).max()))
+    e_or = float(np.abs(q1.cpu().numpy() - want).max())
+    e_g = float((q1 - q0).abs().max())
+    assert e_or <= BF16_TOL * scale, (e_or, scale)
+    assert e_g <= 0.5 * BF16_TOL * scale, (e_g, scale)
+    assert not torch.equal(q0, q1)                          # really the other kernel
+    assert torch.equal(a1 >= 0, torch.as_tensor(cm, device="cuda"))
+    # same call again (scratch state such as the used-key flags is left clean)
+    q2, _ = m.forward_graphs(*args, discrete_features=True)
+    assert torch.equal(q1, q2)
+
+
+def test_tensor_core_table_attention_falls_back_when_keys_overflow():
+    """More than 1024 distinct feature keys in one pass: the pair-logit table cannot hold them, the gather
+    kernel takes the pass (decided on the device) -- bit-identical to the per-node path."""
+    N, B = 50, 200
+    sd = _random_sd("l_dgn", 8)
+    om = _obs_matrix(N, B, 79)
+    rng = np.random.default_rng(0)
+    om[:, :, 2] = rng.integers(0, 64, size=(B, N))
+    om[:, :, 3] = rng.integers(0, 64, size=(B, N))
+    cm = rng.random((B, N)) < 0.4
+    m = _module("l_dgn", N, sd).set_precision("bf16")
+    args = (torch.as_tensor(om, device="cuda"), torch.as_tensor(cm, device="cuda").to(torch.uint8))
+    q0, a0 = m.forward_graphs(*args)
+    q1, a1 = m.forward_graphs(*args, discrete_features=True)
+    assert torch.equal(q0, q1) and torch.equal(a0, a1)
