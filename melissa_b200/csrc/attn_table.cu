@@ -9,13 +9,14 @@
 //                           GATv2:       0.6 (a_j + b_i) + 0.4 sum_c att_c |x_l[j,c] + x_r[i,c]|
 //                           Transformer: <q_i, k_j> / sqrt(C)
 //   attn_table_mma_kernel per tile of G graphs (G*N <= 64 node rows), per head:
-//       producers (SIMT)   softmax weights p_ij = 2^(e_ij - max_i) from E, written as a bf16 matrix
+//       producers (SIMT)   softmax weights 2^(e_ij - max_i) / (sum_j + 1e-16) from E, written as a bf16 matrix
 //                          W_h[target][source] (K-major, 128B swizzle); value rows x_l[key_j] / v[key_j]
 //                          gathered from the table into a [source][channel] operand (MN-major, 128B swizzle)
-//       tcgen05.mma        out_h[target][0..127] = W_h x V_h, fp32 accumulators in TMEM (one per head)
-//       epilogue warps     tcgen05.ld, x 1/sum_j p_ij, + bias, ReLU, bf16 -> x1 rows and controlling-node snapshots
+//       tcgen05.mma        out_h^T[channel][target] = V_h^T x W_h^T, fp32 accumulators in TMEM (double buffered)
+//                          (bulk copies of pre-swizzled rows); the conv bias rides along as two extra value rows
+//       epilogue warps     tcgen05.ld, ReLU, bf16 -> x1 rows and controlling-node snapshots
 //     The weight matrix is block diagonal over the graphs of a tile; the aggregation over (at most 33)
-//     neighbours is done densely because the tensor core does the 64-wide row in one instruction.
+//     neighbours is done densely because the tensor core does the 64-wide row in 4 instructions.
 //
 // Reference math: PyG GATv2Conv / TransformerConv as used by l_dgn.py:125,133 and dgn_r.py; softmax
 // exp(e - max) / (sum + 1e-16).  Same results as edge_bf16_kernel up to bf16 rounding of the weights.
@@ -91,14 +92,16 @@ __global__ void __launch_bounds__(128) umma_mn_probe_kernel(const bf16* __restri
 
 
 // ------------------------------------------------------------------------------ key compaction
-__global__ void __launch_bounds__(1024) compact_keys_kernel(uint8_t* __restrict__ used, int n_keys, uint16_t* __restrict__ cid_of_key,
+// used_bits: bitmap over all feature keys, bit set by feature_key_kernel for every key present in this pass.
+__global__ void __launch_bounds__(1024) compact_keys_kernel(uint32_t* __restrict__ used_bits, int n_keys, uint16_t* __restrict__ cid_of_key,
                                                             uint32_t* __restrict__ key_of_cid, int* __restrict__ n_used) {
   __shared__ int s_warp[32];
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  const int per = (n_keys + 1023) / 1024;
-  const int k0 = t * per, k1 = min(n_keys, k0 + per);
+  const int n_words = n_keys >> 5;
+  const int per = (n_words + 1023) / 1024;
+  const int w0 = t * per, w1 = min(n_words, w0 + per);
   int cnt = 0;
-  for (int k = k0; k < k1; ++k) cnt += used[k] ? 1 : 0;
+  for (int w = w0; w < w1; ++w) cnt += __popc(used_bits[w]);
   int incl = cnt;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -119,14 +122,16 @@ __global__ void __launch_bounds__(1024) compact_keys_kernel(uint8_t* __restrict_
   }
   __syncthreads();
   int id = s_warp[warp] + incl - cnt;
-  for (int k = k0; k < k1; ++k) {
-    uint16_t c = 0xFFFF;
-    if (used[k]) {
-      if (id < kAttnUcap) { c = (uint16_t)id; key_of_cid[id] = (uint32_t)k; }
+  for (int w = w0; w < w1; ++w) {
+    uint32_t bits = used_bits[w];
+    used_bits[w] = 0;                                   // clean for the next pass
+    while (bits) {
+      const int b = __ffs(bits) - 1;
+      bits &= bits - 1;
+      const int k = w * 32 + b;
+      if (id < kAttnUcap) { cid_of_key[k] = (uint16_t)id; key_of_cid[id] = (uint32_t)k; }
       ++id;
-      used[k] = 0;
     }
-    cid_of_key[k] = c;
   }
 }
 
@@ -197,8 +202,18 @@ __global__ void __launch_bounds__(256) pair_logit_kernel(const AttnTableArgs a) 
 }
 
 // ------------------------------------------------------------------------------ aggregation on the tensor cores
-constexpr int kTThreads = 640;                 // 20 warps: w & 3 = TMEM lane quarter, w >> 2 = group
-constexpr int kProducers = 320;                // warps with quarter 2, 3
+// The MMA is issued transposed, out_h^T[channel][target] = V_h^T x W_h^T, so that M = 128 channels fills the
+// tensor core's rows whatever the tile's node count, N = 64 targets halves the cycles per instruction, and a
+// warp's 32 TMEM lanes are 32 consecutive channels of one target: coalesced 64-byte stores.
+//   A operand = value panels [source][channel]   (MN-major, 128B swizzle)
+//   B operand = weight matrix [target][source]   (K-major,  128B swizzle)
+//   D         = 64 TMEM columns per head, 4 heads, double buffered over tiles (512 columns)
+// 24 warps.  w & 3 = TMEM lane quarter:
+//   warp 0   MMA issuer            warp 1   TMEM allocation
+//   warps 4..11   epilogue: quarter w & 3, heads 2p and 2p+1 with p = (w >> 2) - 1
+//   the other 14 warps   two producer teams of 7 warps; team g builds the tiles g, g+2, ... of this CTA in stage g
+constexpr int kTThreads = 768;
+constexpr int kTeam = 224;
 constexpr int kAHead = 64 * 128;               // weight matrix of one head: 64 targets x 64 sources bf16
 constexpr int kBPanel = 64 * 128;              // value panel: 64 sources x 64 channels bf16
 constexpr int kStageA = 4 * kAHead;            // 32 KiB
@@ -206,18 +221,36 @@ constexpr int kStageB = 8 * kBPanel;           // 64 KiB
 constexpr int kStage = kStageA + kStageB;      // 96 KiB
 constexpr int kMetaSrc = 64 * kMaxNbr;         // CSR source lists of a tile
 constexpr int kMeta = kMetaSrc + 64 * 4 /*keys*/ + 64 * 2 /*ids*/ + 128 * 2 /*CSR row pointers*/;
-constexpr int kTSmem = 2 * kStage + 4 * 64 * 4 * 4 /*inv_den ring*/ + 2 * kMeta + 512 * 4 /*bias*/ + 256 /*barriers*/ + 1024;
+constexpr int kTSmem = 2 * kStage + 2 * kMeta + 256 /*barriers*/ + 1024;
+
+__device__ __forceinline__ float f_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float f_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ void bar_team(int team) { asm volatile("bar.sync %0, 224;" ::"r"(team + 1) : "memory"); }
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-
-__device__ __forceinline__ float f_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float f_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ void bar_producers() { asm volatile("bar.sync 1, 320;" ::: "memory"); }
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-  const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<const uint32_t*>(&v);
+// mbarrier wait for warps that are far ahead of the pipeline: sleep between polls so that the issue slots
+// go to the warps doing the work
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return;
+    __nanosleep(200);
+  }
+}
+__device__ __forceinline__ uint16_t relu_bf16(float x) {
+  uint16_t d;
+  asm("cvt.rn.relu.bf16.f32 %0, %1;" : "=h"(d) : "f"(x));
+  return d;
+}
+__device__ __forceinline__ uint32_t a_off(int i, int j) {      // byte offset of W[i][j] inside a head's K-major SW128 tile
+  return (uint32_t)(i * 128 + ((((j >> 3) ^ i) & 7) << 4) + (j & 7) * 2);
 }
 
 __global__ void __launch_bounds__(kTThreads, 1) attn_table_mma_kernel(const AttnTableArgs a, const int G) {
@@ -225,28 +258,39 @@ __global__ void __launch_bounds__(kTThreads, 1) attn_table_mma_kernel(const Attn
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // 1024-byte alignment by offset (not by integer round trip): the compiler keeps the shared address space -> LDS / STS
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  float* inv_den = reinterpret_cast<float*>(smem + 2 * kStage);                  // [4][64][4]
-  unsigned char* meta = reinterpret_cast<unsigned char*>(inv_den + 4 * 64 * 4);    // [2][kMeta]
-  float* bias_s = reinterpret_cast<float*>(meta + 2 * kMeta);                     // [512]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + 512);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  unsigned char* meta = smem + 2 * kStage;                                        // [2][kMeta]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(meta + 2 * kMeta);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
   const uint32_t bar0 = smem_u32(bars);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (2 + s); };
-  auto tfull_bar = [&](int h) { return bar0 + 8u * (4 + h); };
-  auto tempty_bar = [&](int h) { return bar0 + 8u * (8 + h); };
+  auto tfull_bar = [&](int b) { return bar0 + 8u * (4 + b); };
+  auto tempty_bar = [&](int b) { return bar0 + 8u * (6 + b); };
 
   const int N = a.N, HC = 4 * kC;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int quarter = warp & 3, grp = warp >> 2;
   const int n_tiles = (a.n_graphs + G - 1) / G;
+  const int kb = G * N;                          // K index of the two bias rows (hi, lo); <= 62
+  const int ksteps = (kb + 2 + 15) >> 4;
 
-  // value panels start out finite (rows beyond a tile's node count are multiplied by zero weights)
   for (int u = threadIdx.x; u < 2 * kStage / 16; u += kTThreads) reinterpret_cast<uint4*>(smem)[u] = make_uint4(0, 0, 0, 0);
-  for (int u = threadIdx.x; u < 512; u += kTThreads) bias_s[u] = a.bias ? a.bias[u] : 0.f;
+  __syncthreads();
+  // conv bias as two extra value rows (bf16 hi + lo), multiplied by two columns of ones in the weight matrix
+  for (int u = threadIdx.x; u < 2 * 512; u += kTThreads) {
+    const int s = u >> 9, ch = u & 511;
+    const float b = a.bias ? a.bias[ch] : 0.f;
+    const bf16 hi = __float2bfloat16_rn(b), lo = __float2bfloat16_rn(b - __bfloat162float(hi));
+    unsigned char* panel = smem + s * kStage + kStageA + (ch >> 6) * kBPanel;
+    const int e = ch & 63;
+    *reinterpret_cast<bf16*>(panel + kb * 128 + ((((e >> 3) ^ kb) & 7) << 4) + (e & 7) * 2) = hi;
+    *reinterpret_cast<bf16*>(panel + (kb + 1) * 128 + ((((e >> 3) ^ (kb + 1)) & 7) << 4) + (e & 7) * 2) = lo;
+  }
   if (threadIdx.x == 0) {
-    for (int s = 0; s < 2; ++s) { mbar_init(full_bar(s), kProducers); mbar_init(empty_bar(s), 1); }
-    for (int h = 0; h < 4; ++h) { mbar_init(tfull_bar(h), 1); mbar_init(tempty_bar(h), 64); }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(full_bar(s), kTeam); mbar_init(empty_bar(s), 1);
+      mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 8 * 32);
+    }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
@@ -256,49 +300,102 @@ __global__ void __launch_bounds__(kTThreads, 1) attn_table_mma_kernel(const Attn
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (quarter >= 2) {
-    // ===================================================================== producers
-    const int pt = (grp * 2 + (quarter - 2)) * 32 + lane;          // 0..319
-    const int vcol = a.transformer ? 2 * HC : 0;
-    const int self = a.transformer ? 0 : 1;
+  const bool is_epi = grp == 1 || grp == 2;
+  if (warp == 0) {
+    // ===================================================================== MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(128, 64) | (1u << 15);                 // A (values) MN-major, B (weights) K-major
+      int it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int s = it & 1;                                                  // shared-memory stage == TMEM buffer
+        const uint32_t sA = smem_u32(smem + s * kStage), sB = sA + kStageA;
+        mbar_wait(full_bar(s), (it >> 1) & 1);
+        mbar_wait(tempty_bar(s), ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        for (int h = 0; h < 4; ++h) {
+          const uint64_t dv = make_smem_desc_ex(sB + h * 2 * kBPanel, kBPanel >> 4, 1024 >> 4);
+          const uint64_t dw = make_smem_desc(sA + h * kAHead);
+          for (int k = 0; k < ksteps; ++k)
+            umma_bf16(tmem_base + (uint32_t)(s * 256 + h * 64), dv + (uint64_t)(k * 128), dw + (uint64_t)(k * 2), idesc, k ? 1u : 0u);
+        }
+        umma_commit(tfull_bar(s));
+        umma_commit(empty_bar(s));
+      }
+    }
+  } else if (is_epi) {
+    // ===================================================================== epilogue: lane = channel, registers = targets
+    const int pair = grp - 1;
     int it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-      const int s = it & 1;
+      const int b = it & 1;
       const int g0 = tile * G, gt = min(G, a.n_graphs - g0), rt = gt * N;
       const size_t m0 = (size_t)g0 * N;
-      unsigned char* sA = smem + s * kStage;
-      unsigned char* sB = sA + kStageA;
-      const uint8_t* src_s = meta + s * kMeta;                                 // [gt][N*32]
-      const uint32_t* key_s = reinterpret_cast<const uint32_t*>(src_s + kMetaSrc);   // [64]
-      const uint16_t* cid = reinterpret_cast<const uint16_t*>(key_s + 64);     // [64]
-      const uint16_t* ptr_s = cid + 64;                                        // [gt][N+1]
-      mbar_wait(empty_bar(s), ((it >> 1) & 1) ^ 1);
-      // ---- phase A: tile metadata (all global loads issued before the first dependent store) and the cleared weight matrices
-      {
-        uint32_t kv = 0, pv = 0;
-        uint16_t cv = 0;
-        uint4 sv = make_uint4(0, 0, 0, 0);
-        if (pt < rt) { kv = __ldg(a.key + m0 + pt); cv = __ldg(a.row_cid + m0 + pt); }
-        if (pt < gt * (N + 1)) pv = __ldg(a.csr_ptr + (size_t)g0 * (N + 1) + pt);                    // gt * (N + 1) <= 128
-        if (pt < rt * 2) sv = __ldg(reinterpret_cast<const uint4*>(a.csr_src + (size_t)g0 * N * kMaxNbr) + pt);   // N*32 bytes per graph
-        for (int u = pt; u < kStageA / 16; u += kProducers) reinterpret_cast<uint4*>(sA)[u] = make_uint4(0, 0, 0, 0);
-        if (pt < rt) { const_cast<uint32_t*>(key_s)[pt] = kv; const_cast<uint16_t*>(cid)[pt] = cv; }
-        if (pt < gt * (N + 1)) const_cast<uint16_t*>(ptr_s)[pt] = (uint16_t)pv;
-        if (pt < rt * 2) reinterpret_cast<uint4*>(const_cast<uint8_t*>(src_s))[pt] = sv;
-      }
-      bar_producers();
-      // ---- phase B: value rows of the tile's nodes (64 x 16 B per node -> 8 panels: head, channel half), asynchronously
-      {
-        const uint32_t sB32 = smem_u32(sB);
-        for (int u = pt; u < rt * 64; u += kProducers) {
-          const int j = u >> 6, c = u & 63;
-          cp_async16(sB32 + (c >> 3) * kBPanel + j * 128 + (((c & 7) ^ (j & 7)) << 4),
-                     reinterpret_cast<const uint4*>(a.t_P + (size_t)key_s[j] * a.ldp + vcol) + c);
+      // controlling-list slots of the tile's targets: lane t holds targets t and t + 32
+      const int sl0 = (lane < rt && a.slot) ? a.slot[m0 + lane] : -1;
+      const int sl1 = (lane + 32 < rt && a.slot) ? a.slot[m0 + lane + 32] : -1;
+      mbar_wait(tfull_bar(b), (it >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int q = 0; q < 4; ++q) {
+        const int h = pair * 2 + (q >> 1), t0 = (q & 1) * 32;
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(b * 256 + h * 64 + t0), v);
+        if (q == 3) { tc_fence_before(); mbar_arrive(tempty_bar(b)); }
+        const int col = h * kC + quarter * 32 + lane;
+        const int slv = t0 ? sl1 : sl0;                                        // -1 beyond the tile's rows
+        const int nv = rt - t0;
+        uint16_t* xo = reinterpret_cast<uint16_t*>(a.x_out) + (m0 + t0) * HC + col;
+        uint16_t* zo = reinterpret_cast<uint16_t*>(a.z) + a.z_col + col;
+        const uint32_t ldz_u = (uint32_t)a.ldz;
+#pragma unroll
+        for (int t = 0; t < 32; ++t) {
+          const uint16_t o = relu_bf16(__uint_as_float(v[t]));
+          if (t < nv) xo[(size_t)t * HC] = o;                                  // 32 lanes = 64 contiguous bytes
+          const int sl = __shfl_sync(0xffffffffu, slv, t);
+          if (sl >= 0) zo[(uint32_t)sl * ldz_u] = o;                         // < 2^31 elements (checked at launch)
         }
       }
-      // ---- softmax weights of (target i, head h)
-      float* inv = inv_den + (it & 3) * 256;
-      for (int tt = pt; tt < rt * 4; tt += kProducers) {
+    }
+  } else if (warp != 1) {
+    // ===================================================================== producer teams
+    const int p = warp < 4 ? warp - 2 : warp - 10;                            // warps 2, 3, 12..23 -> 0..13
+    const int team = p & 1, pt = (p >> 1) * 32 + lane;                        // 0..223
+    const int self = a.transformer ? 0 : 1;
+    unsigned char* sA = smem + team * kStage;
+    const uint32_t sB32 = smem_u32(sA + kStageA);
+    uint8_t* src_s = meta + team * kMeta;                                       // [gt][N*32]
+    uint32_t* key_s = reinterpret_cast<uint32_t*>(src_s + kMetaSrc);            // [64]
+    uint16_t* cid = reinterpret_cast<uint16_t*>(key_s + 64);                    // [64]
+    uint16_t* ptr_s = cid + 64;                                                 // [gt][N+1]
+    // value gather: thread = (16-byte chunk c of the 1 KiB value row, node residue jg); chunk -> panel c >> 3
+    const int gc = pt & 63, jg = pt >> 6;                                       // jg 0..2 gather, 3 idles (32 threads)
+    const uint32_t gdst = sB32 + (gc >> 3) * kBPanel;
+    const unsigned char* gsrc = reinterpret_cast<const unsigned char*>(a.t_P + (a.transformer ? 2 * HC : 0)) + gc * 16;
+    const size_t row_bytes = (size_t)a.ldp * 2;
+    int use = 0;
+    for (int tile = blockIdx.x + team * gridDim.x; tile < n_tiles; tile += 2 * gridDim.x, ++use) {
+      const int g0 = tile * G, gt = min(G, a.n_graphs - g0), rt = gt * N;
+      const size_t m0 = (size_t)g0 * N;
+      // ---- phase A: tile metadata (global loads first) and the cleared weight matrices
+      uint32_t pv = 0, kv = 0;
+      uint16_t cv = 0;
+      uint4 sv = make_uint4(0, 0, 0, 0);
+      if (pt < rt) { cv = __ldg(a.row_cid + m0 + pt); kv = __ldg(a.key + m0 + pt); }
+      if (pt < gt * (N + 1)) pv = __ldg(a.csr_ptr + (size_t)g0 * (N + 1) + pt);                     // gt * (N + 1) <= 128
+      if (pt < rt * 2) sv = __ldg(reinterpret_cast<const uint4*>(a.csr_src + (size_t)g0 * N * kMaxNbr) + pt);   // N*32 bytes per graph
+      mbar_wait_backoff(empty_bar(team), (use & 1) ^ 1);                       // the MMAs that read this stage are done
+      for (int u = pt; u < kStageA / 16; u += kTeam) reinterpret_cast<uint4*>(sA)[u] = make_uint4(0, 0, 0, 0);
+      if (pt < rt) { cid[pt] = cv; key_s[pt] = kv; }
+      if (pt < gt * (N + 1)) ptr_s[pt] = (uint16_t)pv;
+      if (pt < rt * 2) reinterpret_cast<uint4*>(src_s)[pt] = sv;
+      bar_team(team);
+      // ---- phase B: value rows of the tile's nodes, asynchronously (swizzled by the node's row residue) ...
+      if (jg < 3) {
+        for (int j = jg; j < rt; j += 3)
+          cp_async16(gdst + j * 128 + (((gc ^ j) & 7) << 4), gsrc + (size_t)key_s[j] * row_bytes);
+      }
+      // ---- ... and the normalised softmax weights of (target i, head h) as bf16 rows of the head's weight matrix
+      for (int tt = pt; tt < rt * 4; tt += kTeam) {
         const int i = tt >> 2, h = tt & 3;
         const int gl = i / N, il = i - gl * N, rbase = gl * N;
         const uint16_t* ptr = ptr_s + gl * (N + 1);
@@ -307,8 +404,7 @@ __global__ void __launch_bounds__(kTThreads, 1) attn_table_mma_kernel(const Attn
         const float* Erow = a.E + (size_t)cid[i] * kAttnUcap * 4 + h;
         // entry 0 = the self loop (GATv2), then the CSR neighbours; batches of 8 independent table reads
         const int cnt = d + self;
-        unsigned char* arow = sA + h * kAHead + i * 128;
-        const int sw = i & 7;
+        unsigned char* arow = sA + h * kAHead;
         float ev[8];
         int jv[8];
         float mx = -INFINITY;
@@ -323,89 +419,32 @@ __global__ void __launch_bounds__(kTThreads, 1) attn_table_mma_kernel(const Attn
           for (int q = 0; q < 8; ++q) if (k0 + q < cnt) mx = fmaxf(mx, ev[q]);
         }
         float sum = 0.f;
-        for (int k0 = 0; k0 < cnt; k0 += 8) {
-          if (cnt > 8) {                                     // more than one batch: read the logits again (L1)
+        if (cnt <= 8) {
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const int k = k0 + q;
-              jv[q] = (k < cnt && k >= self) ? rbase + src[k - self] : i;
-              ev[q] = __ldg(Erow + (int)cid[jv[q]] * 4);
-            }
-          }
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            if (k0 + q < cnt) {
-              const int j = jv[q];
-              const __nv_bfloat16 pb = __float2bfloat16_rn(f_ex2(ev[q] - mx));
-              sum += __bfloat162float(pb);
-              *reinterpret_cast<__nv_bfloat16*>(arow + (((j >> 3) ^ sw) << 4) + (j & 7) * 2) = pb;
-            }
+          for (int q = 0; q < 8; ++q) { ev[q] = q < cnt ? f_ex2(ev[q] - mx) : 0.f; sum += ev[q]; }
+        } else {
+          for (int k = 0; k < cnt; ++k) {
+            const int j = k >= self ? rbase + src[k - self] : i;
+            sum += f_ex2(__ldg(Erow + (int)cid[j] * 4) - mx);
           }
         }
-        inv[i * 4 + h] = f_rcp(sum + 1e-16f);
+        const float inv = f_rcp(sum + 1e-16f);
+        if (cnt <= 8) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            if (q < cnt) *reinterpret_cast<bf16*>(arow + a_off(i, jv[q])) = __float2bfloat16_rn(ev[q] * inv);
+        } else {
+          for (int k = 0; k < cnt; ++k) {
+            const int j = k >= self ? rbase + src[k - self] : i;
+            *reinterpret_cast<bf16*>(arow + a_off(i, j)) = __float2bfloat16_rn(f_ex2(__ldg(Erow + (int)cid[j] * 4) - mx) * inv);
+          }
+        }
+        *reinterpret_cast<uint16_t*>(arow + a_off(i, kb)) = 0x3F80;          // 1.0: + bias (hi)
+        *reinterpret_cast<uint16_t*>(arow + a_off(i, kb + 1)) = 0x3F80;      // 1.0: + bias (lo)
       }
       cp_async_wait_all();
       fence_proxy_async();
-      mbar_arrive(full_bar(s));
-    }
-  } else if (warp == 0) {
-    // ===================================================================== MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bmn(128, 128);
-      int it = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-        const int s = it & 1;
-        const int g0 = tile * G, gt = min(G, a.n_graphs - g0), rt = gt * N;
-        const int ksteps = (rt + 15) >> 4;
-        const uint32_t sA = smem_u32(smem + s * kStage), sB = sA + kStageA;
-        mbar_wait(full_bar(s), (it >> 1) & 1);
-        tc_fence_after();
-        for (int h = 0; h < 4; ++h) {
-          mbar_wait(tempty_bar(h), (it & 1) ^ 1);
-          tc_fence_after();
-          const uint64_t da = make_smem_desc(sA + h * kAHead);
-          const uint64_t db = make_smem_desc_ex(sB + h * 2 * kBPanel, kBPanel >> 4, 1024 >> 4);
-          for (int k = 0; k < ksteps; ++k) umma_bf16(tmem_base + (uint32_t)(h * 128), da + (uint64_t)(k * 2), db + (uint64_t)(k * 128), idesc, k ? 1u : 0u);
-          umma_commit(tfull_bar(h));
-        }
-        umma_commit(empty_bar(s));
-      }
-    }
-  } else if (grp >= 1) {
-    // ===================================================================== epilogue (quarter 0, 1; head = grp - 1)
-    const int h = grp - 1;
-    const int r = quarter * 32 + lane;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-      const int g0 = tile * G, gt = min(G, a.n_graphs - g0), rt = gt * N;
-      const size_t row = (size_t)g0 * N + r;
-      const bool valid = r < rt;
-      const int sl = (valid && a.slot) ? a.slot[row] : -1;
-      mbar_wait(tfull_bar(h), it & 1);
-      tc_fence_after();
-      const float inv = valid ? inv_den[(it & 3) * 256 + r * 4 + h] : 0.f;
-      bf16* xo = a.x_out ? a.x_out + row * HC + h * kC : nullptr;
-      bf16* zo = (a.z && sl >= 0) ? a.z + (size_t)sl * a.ldz + a.z_col + h * kC : nullptr;
-#pragma unroll 1
-      for (int c0 = 0; c0 < kC; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(h * 128 + c0), v);
-        if (c0 == kC - 32) { tc_fence_before(); mbar_arrive(tempty_bar(h)); }
-        if (valid) {
-          const float* bs = bias_s + h * kC + c0;
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            const float4 b0 = *reinterpret_cast<const float4*>(bs + j), b1 = *reinterpret_cast<const float4*>(bs + j + 4);
-            uint4 o;
-            o.x = pack_bf16x2(fmaxf(fmaf(__uint_as_float(v[j]), inv, b0.x), 0.f), fmaxf(fmaf(__uint_as_float(v[j + 1]), inv, b0.y), 0.f));
-            o.y = pack_bf16x2(fmaxf(fmaf(__uint_as_float(v[j + 2]), inv, b0.z), 0.f), fmaxf(fmaf(__uint_as_float(v[j + 3]), inv, b0.w), 0.f));
-            o.z = pack_bf16x2(fmaxf(fmaf(__uint_as_float(v[j + 4]), inv, b1.x), 0.f), fmaxf(fmaf(__uint_as_float(v[j + 5]), inv, b1.y), 0.f));
-            o.w = pack_bf16x2(fmaxf(fmaf(__uint_as_float(v[j + 6]), inv, b1.z), 0.f), fmaxf(fmaf(__uint_as_float(v[j + 7]), inv, b1.w), 0.f));
-            if (xo) *reinterpret_cast<uint4*>(xo + c0 + j) = o;
-            if (zo) *reinterpret_cast<uint4*>(zo + c0 + j) = o;
-          }
-        }
-      }
+      mbar_arrive(full_bar(team));
     }
   }
   tc_fence_before();
@@ -420,12 +459,16 @@ int attn_table_conv_launch(const AttnTableArgs& a, int sm_count, cudaStream_t st
     mls_set_error("table-mode attention: unsupported shape (N=%d, H=%d)", a.N, a.H);
     return MLS_ERR_UNSUPPORTED;
   }
+  if ((long long)a.n_graphs * a.N * a.ldz >= (1ll << 31) || !a.x_out || !a.z) {
+    mls_set_error("table-mode attention: snapshot matrix too large for 32-bit offsets or missing outputs");
+    return MLS_ERR_UNSUPPORTED;
+  }
   static bool configured = false;
   if (!configured) {
     MLS_CUDA(cudaFuncSetAttribute(attn_table_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTSmem));
     configured = true;
   }
-  compact_keys_kernel<<<1, 1024, 0, st>>>(a.used, a.n_keys, a.cid_of_key, a.key_of_cid, a.n_used);
+  compact_keys_kernel<<<1, 1024, 0, st>>>(a.used_bits, a.n_keys, a.cid_of_key, a.key_of_cid, a.n_used);
   const int rows = a.n_graphs * a.N;
   row_cid_kernel<<<(rows + 255) / 256, 256, 0, st>>>(a.key, a.cid_of_key, rows, a.row_cid);
   pair_logit_kernel<<<sm_count * 2, 256, 0, st>>>(a);

@@ -9,7 +9,7 @@
 namespace mls {
 
 constexpr int kAttnUcap = 1024;      // distinct feature keys per pass the pair-logit table is sized for
-constexpr int kAttnMaxRows = 64;     // node rows per tile (one 64-wide K panel of the weight matrix)
+constexpr int kAttnMaxRows = 62;     // node rows per tile (one 64-wide K panel of the weight matrix, 2 columns for the bias)
 
 struct AttnTableArgs {
   // projection tables over all feature keys (MLS_FWD_DISCRETE_FEATURES)
@@ -29,7 +29,7 @@ struct AttnTableArgs {
   __nv_bfloat16* z;          // snapshot rows
   int ldz, z_col;
   // scratch (workspace)
-  uint8_t* used;             // [n_keys] marked by feature_key_kernel, cleared here
+  uint32_t* used_bits;       // [n_keys / 32] bitmap marked by feature_key_kernel, cleared here
   int n_keys;
   uint16_t* cid_of_key;      // [n_keys] compact id of a key present in this pass (0xFFFF otherwise)
   uint32_t* key_of_cid;      // [kAttnUcap]

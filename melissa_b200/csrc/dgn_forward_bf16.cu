@@ -108,19 +108,33 @@ __device__ __forceinline__ void key_decode(uint32_t key, float (&f)[5]) {
   f[1] = (float)((key >> 3) & 63u); f[0] = (float)(key >> 9);
 }
 __global__ void feature_key_kernel(const float* __restrict__ obs, int64_t obs_stride, int N, int rows, int degbits,
-                                   uint32_t* __restrict__ key, int* __restrict__ errors, uint8_t* __restrict__ used) {
+                                   uint32_t* __restrict__ key, int* __restrict__ errors, uint32_t* __restrict__ used_bits) {
+  extern __shared__ uint32_t s_bits[];         // (1 << degbits) * 16 words when used_bits != NULL
+  const int n_words = (1 << degbits) * 16;
+  if (used_bits) {
+    for (int w = threadIdx.x; w < n_words; w += blockDim.x) s_bits[w] = 0;
+    __syncthreads();
+  }
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= rows) return;
-  const int g = r / N, i = r - g * N;
-  const float* f = obs + (int64_t)g * obs_stride + i * 8 + 2;
-  const float deg = f[0], msgs = f[1], act = f[2], intr = f[3], hm = f[4];
-  const bool ok = deg >= 0.f && deg < (float)(1 << degbits) && deg == floorf(deg) && msgs >= 0.f && msgs < 64.f &&
-                  msgs == floorf(msgs) && (act == 0.f || act == 1.f) && (intr == 0.f || intr == 1.f) && (hm == 0.f || hm == 1.f);
-  uint32_t k = 0;
-  if (ok) k = (((((uint32_t)deg << 6) | (uint32_t)msgs) << 1 | (uint32_t)act) << 1 | (uint32_t)intr) << 1 | (uint32_t)hm;
-  else if (errors) atomicAdd(errors, 1);
-  key[r] = k;
-  if (used && !used[k]) used[k] = 1;   // keys present in this pass (attn_table.cu compacts them); benign race, few distinct keys
+  if (r < rows) {
+    const int g = r / N, i = r - g * N;
+    const float* f = obs + (int64_t)g * obs_stride + i * 8 + 2;
+    const float deg = f[0], msgs = f[1], act = f[2], intr = f[3], hm = f[4];
+    const bool ok = deg >= 0.f && deg < (float)(1 << degbits) && deg == floorf(deg) && msgs >= 0.f && msgs < 64.f &&
+                    msgs == floorf(msgs) && (act == 0.f || act == 1.f) && (intr == 0.f || intr == 1.f) && (hm == 0.f || hm == 1.f);
+    uint32_t k = 0;
+    if (ok) k = (((((uint32_t)deg << 6) | (uint32_t)msgs) << 1 | (uint32_t)act) << 1 | (uint32_t)intr) << 1 | (uint32_t)hm;
+    else if (errors) atomicAdd(errors, 1);
+    key[r] = k;
+    if (used_bits) atomicOr(&s_bits[k >> 5], 1u << (k & 31));   // keys present in this pass (attn_table.cu compacts them)
+  }
+  if (used_bits) {
+    __syncthreads();
+    for (int w = threadIdx.x; w < n_words; w += blockDim.x) {
+      const uint32_t b = s_bits[w];
+      if (b && (used_bits[w] & b) != b) atomicOr(&used_bits[w], b);
+    }
+  }
 }
 __global__ void __launch_bounds__(256) enc0_keys_kernel(int n_keys, int in_dim, const float* __restrict__ w0,
                                                         const float* __restrict__ b0, int hidden, bf16* __restrict__ h) {
@@ -587,7 +601,7 @@ struct WsB {
   float* t_ab;                // [n_keys][2H]
   uint32_t* key;              // [R]
   // tensor-core table attention (attn_table.cu)
-  uint8_t* used;              // [n_keys]
+  uint32_t* used;             // [n_keys / 32] bitmap
   uint16_t* cid_of_key;       // [n_keys]
   uint32_t* key_of_cid;       // [kAttnUcap]
   int* n_used;
@@ -631,7 +645,7 @@ size_t carve_b(const MlsNetDesc* d, int Gc, unsigned char* base, WsB* ws) {
     ws->csr_ptr = reinterpret_cast<uint16_t*>(base + o_cptr); ws->csr_src = base + o_csrc;
     ws->ab = F(o_ab); ws->att1 = F(o_att1); ws->att2 = F(o_att2);
     ws->t_h = B(o_th); ws->t_x0 = B(o_tx0); ws->t_P = B(o_tP); ws->t_ab = F(o_tab); ws->key = reinterpret_cast<uint32_t*>(base + o_key);
-    ws->used = base + o_used; ws->cid_of_key = reinterpret_cast<uint16_t*>(base + o_cok);
+    ws->used = reinterpret_cast<uint32_t*>(base + o_used); ws->cid_of_key = reinterpret_cast<uint16_t*>(base + o_cok);
     ws->key_of_cid = reinterpret_cast<uint32_t*>(base + o_koc); ws->n_used = reinterpret_cast<int*>(base + o_nu);
     ws->pairE = F(o_pe); ws->row_cid = reinterpret_cast<uint16_t*>(base + o_rcid);
   }
@@ -779,7 +793,7 @@ int dgn_forward_bf16(const MlsNetDesc* d, const MlsNetWeights* w, const MlsForwa
     GemmEpilogue e1{ws.t_P, nproj * HC, ws.b_c1, nullptr, 0, N, 0, tr ? nullptr : ws.att1, tr ? nullptr : ws.t_ab};
     if ((rc = gemm_bf16_launch(ws.t_x0, hid, ws.w_c1, hid, GemmShape{n_keys, nproj * HC, hid, nullptr}, e1, sms, st))) return rc;
     if (a->feature_errors) MLS_CUDA(cudaMemsetAsync(a->feature_errors, 0, sizeof(int), st));
-    MLS_CUDA(cudaMemsetAsync(ws.used, 0, (size_t)n_keys, st));
+    MLS_CUDA(cudaMemsetAsync(ws.used, 0, (size_t)n_keys / 8, st));
   }
   // conv1 attention through the pair-logit table + tensor-core aggregation (L-DGN / DGN-R, graphs of <= 64 nodes)
   const bool use_mma = use_table && !hl && attn_table_supported(N, H) && mls_get_option("attn_mma");
@@ -807,8 +821,8 @@ int dgn_forward_bf16(const MlsNetDesc* d, const MlsNetWeights* w, const MlsForwa
     mls_count_launch();
     // encoder (or, in discrete-feature mode, just the table keys of this pass)
     if (use_table) {
-      feature_key_kernel<<<(rows + 255) / 256, 256, 0, st>>>(obs, a->obs_stride, N, rows, degbits, ws.key,
-                                                           reinterpret_cast<int*>(a->feature_errors), use_mma ? ws.used : nullptr);
+      feature_key_kernel<<<(rows + 1023) / 1024, 1024, use_mma ? (size_t)(n_keys / 32) * 4 : 0, st>>>(
+          obs, a->obs_stride, N, rows, degbits, ws.key, reinterpret_cast<int*>(a->feature_errors), use_mma ? ws.used : nullptr);
       mls_count_launch();
     } else {
       const int rows_per_cta = 256 / (hid / 8);
@@ -851,7 +865,7 @@ int dgn_forward_bf16(const MlsNetDesc* d, const MlsNetWeights* w, const MlsForwa
           ta.t_P = ws.t_P; ta.ldp = nproj * HC; ta.t_ab = ws.t_ab; ta.att = w->c1_att; ta.bias = tr ? nullptr : w->c1_bias;
           ta.transformer = tr ? 1 : 0; ta.key = ws.key; ta.N = N; ta.H = H; ta.n_graphs = gc; ta.csr_ptr = ws.csr_ptr;
           ta.csr_src = ws.csr_src; ta.slot = ws.slot; ta.x_out = ws.x1; ta.z = ws.z; ta.ldz = latent; ta.z_col = hid;
-          ta.used = ws.used; ta.n_keys = n_keys; ta.cid_of_key = ws.cid_of_key; ta.key_of_cid = ws.key_of_cid;
+          ta.used_bits = ws.used; ta.n_keys = n_keys; ta.cid_of_key = ws.cid_of_key; ta.key_of_cid = ws.key_of_cid;
           ta.n_used = ws.n_used; ta.E = ws.pairE; ta.row_cid = ws.row_cid;
           if ((rc = attn_table_conv_launch(ta, sms, st))) return rc;
           ea.run_if_gt = ws.n_used; ea.run_thresh = kAttnUcap;      // more distinct keys than the table holds: gather kernel

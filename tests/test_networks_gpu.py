@@ -308,7 +308,7 @@ def test_discrete_feature_table_path_is_bit_identical(kind, kw, N, B, gather_att
 
 
 @pytest.mark.parametrize("kind", ["l_dgn", "dgn_r"])
-@pytest.mark.parametrize("N,B", [(50, 300), (20, 64), (12, 9), (64, 33), (7, 1000)])
+@pytest.mark.parametrize("N,B", [(50, 300), (20, 64), (12, 9), (62, 33), (7, 1000)])
 def test_tensor_core_table_attention_within_tolerance(kind, N, B):
     """attn_table.cu (default in discrete-feature mode, graphs of <= 64 nodes): softmax weights from the
     pair-logit table, aggregation on tcgen05.  Differs from the gather kernel only by bf16 rounding of the
