@@ -333,6 +333,13 @@ __global__ void __launch_bounds__(kTThreads, 1) attn_table_mma_kernel(const Attn
       // controlling-list slots of the tile's targets: lane t holds targets t and t + 32
       const int sl0 = (lane < rt && a.slot) ? a.slot[m0 + lane] : -1;
       const int sl1 = (lane + 32 < rt && a.slot) ? a.slot[m0 + lane + 32] : -1;
+      // a graph's slots are consecutive in node order (ctrl_list_slot_kernel): with one graph per tile the
+      // snapshot rows are walked with a running pointer instead of a shuffle per target
+      const uint32_t zm0 = __ballot_sync(0xffffffffu, sl0 >= 0), zm1 = __ballot_sync(0xffffffffu, sl1 >= 0);
+      int zfirst = 0;
+      if (zm0) zfirst = __shfl_sync(0xffffffffu, sl0, __ffs(zm0) - 1);
+      else if (zm1) zfirst = __shfl_sync(0xffffffffu, sl1, __ffs(zm1) - 1);
+      const uint32_t ldz_u = (uint32_t)a.ldz;
       mbar_wait(tfull_bar(b), (it >> 1) & 1);
       tc_fence_after();
 #pragma unroll 1
@@ -342,17 +349,27 @@ __global__ void __launch_bounds__(kTThreads, 1) attn_table_mma_kernel(const Attn
         tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(b * 256 + h * 64 + t0), v);
         if (q == 3) { tc_fence_before(); mbar_arrive(tempty_bar(b)); }
         const int col = h * kC + quarter * 32 + lane;
-        const int slv = t0 ? sl1 : sl0;                                        // -1 beyond the tile's rows
         const int nv = rt - t0;
         uint16_t* xo = reinterpret_cast<uint16_t*>(a.x_out) + (m0 + t0) * HC + col;
         uint16_t* zo = reinterpret_cast<uint16_t*>(a.z) + a.z_col + col;
-        const uint32_t ldz_u = (uint32_t)a.ldz;
+        if (G == 1) {
+          const uint32_t zm = t0 ? zm1 : zm0;
+          uint16_t* zp = zo + (uint32_t)(zfirst + (t0 ? __popc(zm0) : 0)) * ldz_u;   // < 2^31 elements (checked at launch)
 #pragma unroll
-        for (int t = 0; t < 32; ++t) {
-          const uint16_t o = relu_bf16(__uint_as_float(v[t]));
-          if (t < nv) xo[(size_t)t * HC] = o;                                  // 32 lanes = 64 contiguous bytes
-          const int sl = __shfl_sync(0xffffffffu, slv, t);
-          if (sl >= 0) zo[(uint32_t)sl * ldz_u] = o;                         // < 2^31 elements (checked at launch)
+          for (int t = 0; t < 32; ++t) {
+            const uint16_t o = relu_bf16(__uint_as_float(v[t]));
+            if (t < nv) xo[(size_t)t * HC] = o;                                // 32 lanes = 64 contiguous bytes
+            if ((zm >> t) & 1u) { *zp = o; zp += ldz_u; }
+          }
+        } else {
+          const int slv = t0 ? sl1 : sl0;                                      // -1 beyond the tile's rows
+#pragma unroll
+          for (int t = 0; t < 32; ++t) {
+            const uint16_t o = relu_bf16(__uint_as_float(v[t]));
+            if (t < nv) xo[(size_t)t * HC] = o;
+            const int sl = __shfl_sync(0xffffffffu, slv, t);
+            if (sl >= 0) zo[(uint32_t)sl * ldz_u] = o;
+          }
         }
       }
     }

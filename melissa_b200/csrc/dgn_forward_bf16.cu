@@ -478,19 +478,26 @@ __global__ void ctrl_list_slot_kernel(const uint8_t* __restrict__ ctrl_mask, con
     }
     return;
   }
+  // one reservation per graph: the slots of a graph's controlling nodes are consecutive, in node order
+  // (attn_table.cu walks them with a running pointer)
+  int total = 0;
+  for (int i0 = 0; i0 < N; i0 += 32) {
+    const int i = i0 + lane;
+    total += __popc(__ballot_sync(0xffffffffu, i < N && ctrl_mask[(size_t)g * N + i] != 0));
+  }
+  int s = 0;
+  if (lane == 0 && total) s = atomicAdd(count, total);
+  s = __shfl_sync(0xffffffffu, s, 0);
   for (int i0 = 0; i0 < N; i0 += 32) {
     const int i = i0 + lane;
     const bool c = i < N && ctrl_mask[(size_t)g * N + i] != 0;
     const uint32_t bal = __ballot_sync(0xffffffffu, c);
-    const int n = __popc(bal);
-    int s = 0;
-    if (lane == 0 && n) s = atomicAdd(count, n);
-    s = __shfl_sync(0xffffffffu, s, 0);
     if (c) {
       const int t = s + __popc(bal & ((1u << lane) - 1));
       idx[t] = g * N + i;
       slot[g * N + i] = t;
     }
+    s += __popc(bal);
   }
 }
 
