@@ -318,7 +318,9 @@ def run_ours(args):
         chunk_graphs = _lib.lib().mls_dgn_chunk_graphs(ctypes.byref(net._desc()), B) if net is not None else B
         chunk_rows = chunk_graphs * N
         nproj = 3 if args.model == "dgn_r" else 2
-        n_out = HC if args.precision == "fp32" else nproj * HC     # bf16: all projections of a conv in one GEMM
+        # bf16: conv1 = all projections in one GEMM; conv2 = source-side projections on every node (the target
+        # side runs on the controlling nodes only, in a second, smaller GEMM)
+        n_out = HC if args.precision == "fp32" else (nproj * HC if gemm_name == "proj1" else (nproj - 1) * HC)
         gk = HC if gemm_name == "proj2" else hid
         gemm_flops = 2.0 * chunk_rows * n_out * gk
         gemm_ms = float(np.mean(prof_ms_gemm)) if prof_ms_gemm else None

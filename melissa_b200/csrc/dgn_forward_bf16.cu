@@ -236,6 +236,15 @@ struct EdgeArgs {
   int ldz, z_col;
   int ctrl_only;          // compute only nodes with slot >= 0
   int pool_mode;          // >= 0: HL-DGN pooling of relu(conv)*dm into z[g][H*C] (enum MlsPool); -1 none
+  // optional compact target side (conv2: only controlling nodes are targets).  Pt row (slot of node i) holds the
+  // target projection (GATv2 x_r, Transformer q) of node i, bt[slot][H] the <att, x_r> dots; the slots of graph g
+  // are gfirst[g] .. gfirst[g] + gcnt[g] - 1 in node order.  P then holds only the source side:
+  // GATv2 [x_l] (ab = [rows][H]), Transformer [k | v].
+  const bf16* Pt;
+  int ldpt;
+  const float* bt;
+  const int* gfirst;
+  const int* gcnt;
   const int* run_if_gt;   // optional device int: the kernel only runs when *run_if_gt > run_thresh
   int run_thresh;         // (fallback behind the tensor-core table kernel, attn_table.cu)
 };
@@ -294,14 +303,25 @@ __global__ void __launch_bounds__(EdgeCfg<TRANSFORMER>::kThreads, 512 / EdgeCfg<
   constexpr float kLog2e = 1.4426950408889634f;
   // ---------------------------------------------------------------- phase 0
   {
-    const int src_col = TRANSFORMER ? HC + h * kC : h * kC;
+    const bool compact = a.Pt != nullptr;
+    const int src_col = (TRANSFORMER && !compact ? HC : 0) + h * kC;
+    const int val_col = (compact ? HC : 2 * HC) + h * kC;  // Transformer values
     const int tgt_col = (TRANSFORMER ? 0 : HC) + h * kC;
     for (int t = tid; t < N * (kC / 4); t += kEdgeThreads) {
       const int j = t >> 5, q = t & 31;                     // kC / 4 == 32 float4 per row
       const bf16* row = a.P + (a.row_key ? (size_t)a.row_key[base + j] : base + j) * a.ldp;
       *reinterpret_cast<float4*>(stA + j * kLD + q * 4) = ld_bf16x4(row + src_col + q * 4);
-      *reinterpret_cast<float4*>(stT + j * kLD + q * 4) = ld_bf16x4(row + tgt_col + q * 4);
-      if (TRANSFORMER) *reinterpret_cast<float4*>(stB + j * kLD + q * 4) = ld_bf16x4(row + 2 * HC + h * kC + q * 4);
+      if (!compact) *reinterpret_cast<float4*>(stT + j * kLD + q * 4) = ld_bf16x4(row + tgt_col + q * 4);
+      if (TRANSFORMER) *reinterpret_cast<float4*>(stB + j * kLD + q * 4) = ld_bf16x4(row + val_col + q * 4);
+    }
+    if (compact) {                                          // target rows of the graph's controlling nodes: consecutive slots
+      const int first = a.gfirst[g], cnt = a.gcnt[g];
+      for (int t = tid; t < cnt * (kC / 4); t += kEdgeThreads) {
+        const int k = t >> 5, q = t & 31;
+        *reinterpret_cast<float4*>(stT + k * kLD + q * 4) = ld_bf16x4(a.Pt + (size_t)(first + k) * a.ldpt + h * kC + q * 4);
+      }
+      if (!TRANSFORMER)
+        for (int k = tid; k < cnt; k += kEdgeThreads) s_b[k] = a.bt[(size_t)(first + k) * H + h] * (0.6f * kLog2e);
     }
     const uint16_t* gp = a.csr_ptr + (size_t)g * (N + 1);
     const uint8_t* gs = a.csr_src + (size_t)g * N * kMaxNbr;
@@ -310,8 +330,11 @@ __global__ void __launch_bounds__(EdgeCfg<TRANSFORMER>::kThreads, 512 / EdgeCfg<
       s_dm[t] = g_obs[t * 8 + 7];
       if (!TRANSFORMER) {
         const size_t pr = a.row_key ? (size_t)a.row_key[base + t] : base + t;
-        s_a[t] = a.ab[pr * (2 * H) + h] * (0.6f * kLog2e);
-        s_b[t] = a.ab[pr * (2 * H) + H + h] * (0.6f * kLog2e);
+        if (a.Pt) s_a[t] = a.ab[pr * H + h] * (0.6f * kLog2e);
+        else {
+          s_a[t] = a.ab[pr * (2 * H) + h] * (0.6f * kLog2e);
+          s_b[t] = a.ab[pr * (2 * H) + H + h] * (0.6f * kLog2e);
+        }
       }
     }
     for (int t = tid; t <= N; t += kEdgeThreads) s_ptr[t] = gp[t];
@@ -343,8 +366,9 @@ __global__ void __launch_bounds__(EdgeCfg<TRANSFORMER>::kThreads, 512 / EdgeCfg<
     if (a.ctrl_only && sl < 0) continue;
     const int r0 = s_ptr[i];
     const int d = (int)s_ptr[i + 1] - r0 + self;            // warp uniform, <= 33
-    const float* trow = stT + i * kLD + sub * 4;           // target row, re-read per round (multicast, 1 wavefront) to save 16 registers
-    const float b_i = TRANSFORMER ? 0.f : s_b[i];
+    const int ti = a.Pt ? sl - a.gfirst[g] : i;            // row of the target side in stT / s_b
+    const float* trow = stT + ti * kLD + sub * 4;          // target row, re-read per round (multicast, 1 wavefront) to save 16 registers
+    const float b_i = TRANSFORMER ? 0.f : s_b[ti];
     float mx = -INFINITY, den = 0.f;
     float4 acc[4];
 #pragma unroll
@@ -463,7 +487,7 @@ __global__ void __launch_bounds__(EdgeCfg<TRANSFORMER>::kThreads, 512 / EdgeCfg<
 // ------------------------------------------------------------------------------ controlling nodes
 __global__ void ctrl_list_slot_kernel(const uint8_t* __restrict__ ctrl_mask, const float* __restrict__ obs, int64_t obs_stride,
                                       int N, int n_graphs, int mode, int* __restrict__ idx, int* __restrict__ slot,
-                                      int* __restrict__ count) {
+                                      int* __restrict__ count, int* __restrict__ gfirst, int* __restrict__ gcnt) {
   const int lane = threadIdx.x & 31;
   const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (g >= n_graphs) return;
@@ -474,6 +498,8 @@ __global__ void ctrl_list_slot_kernel(const uint8_t* __restrict__ ctrl_mask, con
       const int r = g * N + (int)(long long)c;
       idx[g] = r;
       slot[r] = g;
+      gfirst[g] = g;
+      gcnt[g] = 1;
       if (g == 0) *count = n_graphs;
     }
     return;
@@ -488,6 +514,7 @@ __global__ void ctrl_list_slot_kernel(const uint8_t* __restrict__ ctrl_mask, con
   int s = 0;
   if (lane == 0 && total) s = atomicAdd(count, total);
   s = __shfl_sync(0xffffffffu, s, 0);
+  if (lane == 0) { gfirst[g] = s; gcnt[g] = total; }
   for (int i0 = 0; i0 < N; i0 += 32) {
     const int i = i0 + lane;
     const bool c = i < N && ctrl_mask[(size_t)g * N + i] != 0;
@@ -600,7 +627,7 @@ struct WsB {
   float *b_c1, *b_c2, *b_h0, *b_h1;
   bf16 *h, *x0, *P, *x1, *z, *hid1, *hid2;
   float* qg;
-  int *idx, *slot, *count;
+  int *idx, *slot, *count, *gfirst, *gcnt;
   uint16_t* csr_ptr;
   uint8_t* csr_src;
   float *ab, *att1, *att2;
@@ -632,6 +659,7 @@ size_t carve_b(const MlsNetDesc* d, int Gc, unsigned char* base, WsB* ws) {
   const size_t o_h = take(R * hid * 2), o_x0 = take(R * hid * 2), o_P = take(R * nproj * HC * 2);
   const size_t o_x1 = take(hl ? 0 : R * HC * 2), o_z = take(T * latent * 2), o_h1 = take(T * hh2 * 2), o_h2 = take(T * hh2 * 2);
   const size_t o_qg = take((size_t)Gc * 8), o_idx = take(R * 4), o_slot = take(R * 4), o_cnt = take(4);
+  const size_t o_gf = take((size_t)Gc * 4), o_gc = take((size_t)Gc * 4);
   const size_t o_cptr = take(((size_t)Gc * (d->n_nodes + 1) + 64) * 2), o_csrc = take((size_t)Gc * d->n_nodes * kMaxNbr + 64);
   const size_t o_ab = take(R * 2 * d->heads * 4), o_att1 = take((size_t)2 * HC * 4), o_att2 = take((size_t)2 * HC * 4);
   const size_t KT = (size_t)table_keys(d->n_nodes);
@@ -649,6 +677,7 @@ size_t carve_b(const MlsNetDesc* d, int Gc, unsigned char* base, WsB* ws) {
     ws->qg = F(o_qg);
     ws->idx = reinterpret_cast<int*>(base + o_idx); ws->slot = reinterpret_cast<int*>(base + o_slot);
     ws->count = reinterpret_cast<int*>(base + o_cnt);
+    ws->gfirst = reinterpret_cast<int*>(base + o_gf); ws->gcnt = reinterpret_cast<int*>(base + o_gc);
     ws->csr_ptr = reinterpret_cast<uint16_t*>(base + o_cptr); ws->csr_src = base + o_csrc;
     ws->ab = F(o_ab); ws->att1 = F(o_att1); ws->att2 = F(o_att2);
     ws->t_h = B(o_th); ws->t_x0 = B(o_tx0); ws->t_P = B(o_tP); ws->t_ab = F(o_tab); ws->key = reinterpret_cast<uint32_t*>(base + o_key);
@@ -813,7 +842,8 @@ int dgn_forward_bf16(const MlsNetDesc* d, const MlsNetWeights* w, const MlsForwa
     if (!hl) {
       MLS_CUDA(cudaMemsetAsync(ws.count, 0, sizeof(int), st));
       MLS_CUDA(cudaMemsetAsync(ws.slot, 0xFF, (size_t)rows * sizeof(int), st));
-      ctrl_list_slot_kernel<<<(gc * 32 + 255) / 256, 256, 0, st>>>(cm, obs, a->obs_stride, N, gc, a->ctrl_mode, ws.idx, ws.slot, ws.count);
+      ctrl_list_slot_kernel<<<(gc * 32 + 255) / 256, 256, 0, st>>>(cm, obs, a->obs_stride, N, gc, a->ctrl_mode, ws.idx, ws.slot, ws.count,
+                                                                   ws.gfirst, ws.gcnt);
       mls_count_launch();
     }
     {
@@ -892,14 +922,27 @@ int dgn_forward_bf16(const MlsNetDesc* d, const MlsNetWeights* w, const MlsForwa
         if ((rc = fused_gatv2_conv_launch(ws.x1, ws.w_c2, fa, sms, st))) return rc;
         prof_end(MLS_PROF_EDGE2);
       } else {
-      // conv2 projections on x1 * dm: the row mask commutes with the GEMM, applied in its epilogue
-        GemmEpilogue e{ws.P, nproj * HC, ws.b_c2, obs, a->obs_stride, N, 0, tr ? nullptr : ws.att2, tr ? nullptr : ws.ab};
+      // conv2 projections on x1 * dm (the row mask commutes with the GEMM, applied in its epilogue).  Only the
+      // controlling nodes are conv2 targets, and their x1 rows already sit compacted in z (snapshot): the target
+      // projection (GATv2 x_r, Transformer q) runs on those rows only, the source side on every node.
+        const int nsrc = nproj - 1;                           // GATv2: x_l; Transformer: k | v
+        bf16* Psrc = ws.P;                                    // [rows][nsrc*HC]
+        bf16* Ptgt = ws.P + (size_t)rows * nsrc * HC;         // [count][HC]
+        float* dots_t = ws.ab + (size_t)rows * H;             // [count][H]
+        const bf16* w_src = tr ? ws.w_c2 + (size_t)HC * HC : ws.w_c2;            // weight rows: Transformer [q; k; v], GATv2 [l; r]
+        const bf16* w_tgt = tr ? ws.w_c2 : ws.w_c2 + (size_t)HC * HC;
+        const float* b_src = tr ? ws.b_c2 + HC : ws.b_c2;
+        const float* b_tgt = tr ? ws.b_c2 : ws.b_c2 + HC;
+        GemmEpilogue e{Psrc, nsrc * HC, b_src, obs, a->obs_stride, N, 0, tr ? nullptr : ws.att2, tr ? nullptr : ws.ab, nullptr};
         prof_begin(MLS_PROF_PROJ2);
-        if ((rc = gemm_bf16_launch(ws.x1, HC, ws.w_c2, HC, GemmShape{rows, nproj * HC, HC, nullptr}, e, sms, st))) return rc;
+        if ((rc = gemm_bf16_launch(ws.x1, HC, w_src, HC, GemmShape{rows, nsrc * HC, HC, nullptr}, e, sms, st))) return rc;
         prof_end(MLS_PROF_PROJ2);
+        GemmEpilogue et{Ptgt, HC, b_tgt, obs, a->obs_stride, N, 0, tr ? nullptr : ws.att2, tr ? nullptr : dots_t, ws.idx};
+        if ((rc = gemm_bf16_launch(ws.z + hid, latent, w_tgt, HC, GemmShape{rows, HC, HC, ws.count}, et, sms, st))) return rc;
         // conv2 attention only where a controlling agent needs it; result goes straight into z
         EdgeArgs ea{};
-        ea.P = ws.P; ea.ldp = nproj * HC; ea.obs = obs; ea.obs_stride = a->obs_stride; ea.N = N; ea.H = H; ea.n_graphs = gc;
+        ea.P = Psrc; ea.ldp = nsrc * HC; ea.obs = obs; ea.obs_stride = a->obs_stride; ea.N = N; ea.H = H; ea.n_graphs = gc;
+        ea.Pt = Ptgt; ea.ldpt = HC; ea.bt = dots_t; ea.gfirst = ws.gfirst; ea.gcnt = ws.gcnt;
         ea.att = w->c2_att; ea.bias = w->c2_bias; ea.csr_ptr = ws.csr_ptr; ea.csr_src = ws.csr_src; ea.ab = ws.ab; ea.x_out = nullptr; ea.slot = ws.slot; ea.z = ws.z; ea.ldz = latent;
         ea.z_col = hid + HC; ea.ctrl_only = 1; ea.pool_mode = -1;
         prof_begin(MLS_PROF_EDGE2);

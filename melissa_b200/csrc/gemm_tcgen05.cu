@@ -127,7 +127,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       const int r = m0 + ew * 32 + lane;
       float scale = 1.0f;
       if (epi.obs && r < M) {
-        const int g = r / epi.nodes, i = r - g * epi.nodes;
+        const int nr = epi.row_index ? __ldg(epi.row_index + r) : r;
+        const int g = nr / epi.nodes, i = nr - g * epi.nodes;
         scale = epi.obs[(long long)g * epi.obs_stride + i * 8 + 7];
       }
       // bias slice of this tile -> smem (all four epilogue warps; named barrier 1 keeps the other warps out of it)

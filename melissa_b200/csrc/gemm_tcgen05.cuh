@@ -28,6 +28,8 @@ struct GemmEpilogue {
   // Used for the per-node linear part of the GATv2 logits (<att_h, x_l[j,h,:]>, <att_h, x_r[i,h,:]>).
   const float* dotvec;   // [N] or NULL
   float* dots;           // [M, N / 128]
+  // optional: output row m is node row row_index[m] for the row scale (compacted row sets)
+  const int* row_index;
 };
 
 struct GemmShape {
