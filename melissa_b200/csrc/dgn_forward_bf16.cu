@@ -245,6 +245,7 @@ struct EdgeArgs {
   const float* bt;
   const int* gfirst;
   const int* gcnt;
+  const int* idx;         // [slots] node row of every slot (compact mode: the warps walk the target list, evenly split)
   const int* run_if_gt;   // optional device int: the kernel only runs when *run_if_gt > run_thresh
   int run_thresh;         // (fallback behind the tensor-core table kernel, attn_table.cu)
 };
@@ -320,14 +321,17 @@ __global__ void __launch_bounds__(EdgeCfg<TRANSFORMER>::kThreads, 512 / EdgeCfg<
         const int k = t >> 5, q = t & 31;
         *reinterpret_cast<float4*>(stT + k * kLD + q * 4) = ld_bf16x4(a.Pt + (size_t)(first + k) * a.ldpt + h * kC + q * 4);
       }
-      if (!TRANSFORMER)
-        for (int k = tid; k < cnt; k += kEdgeThreads) s_b[k] = a.bt[(size_t)(first + k) * H + h] * (0.6f * kLog2e);
+      int* s_tl = reinterpret_cast<int*>(s_dm);            // target list (s_dm is only read by the pooling variant)
+      for (int k = tid; k < cnt; k += kEdgeThreads) {
+        s_tl[k] = a.idx[first + k] - (int)base;
+        if (!TRANSFORMER) s_b[k] = a.bt[(size_t)(first + k) * H + h] * (0.6f * kLog2e);
+      }
     }
     const uint16_t* gp = a.csr_ptr + (size_t)g * (N + 1);
     const uint8_t* gs = a.csr_src + (size_t)g * N * kMaxNbr;
     for (int t = tid; t < N; t += kEdgeThreads) {
       s_slot[t] = a.slot ? a.slot[base + t] : -1;
-      s_dm[t] = g_obs[t * 8 + 7];
+      if (!a.Pt) s_dm[t] = g_obs[t * 8 + 7];
       if (!TRANSFORMER) {
         const size_t pr = a.row_key ? (size_t)a.row_key[base + t] : base + t;
         if (a.Pt) s_a[t] = a.ab[pr * H + h] * (0.6f * kLog2e);
@@ -361,12 +365,14 @@ __global__ void __launch_bounds__(EdgeCfg<TRANSFORMER>::kThreads, 512 / EdgeCfg<
   const int self = TRANSFORMER ? 0 : 1;                     // GATv2: slot 0 of every target is its self loop
   float4 pool = a.pool_mode == MLS_POOL_MAX ? make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY)
                                             : make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int i = warp; i < N; i += kEdgeWarps) {
+  const int n_targets = a.Pt ? a.gcnt[g] : N;               // compact mode: only the controlling nodes, split evenly over the warps
+  for (int tk = warp; tk < n_targets; tk += kEdgeWarps) {
+    const int i = a.Pt ? reinterpret_cast<const int*>(s_dm)[tk] : tk;
     const int sl = s_slot[i];
     if (a.ctrl_only && sl < 0) continue;
     const int r0 = s_ptr[i];
     const int d = (int)s_ptr[i + 1] - r0 + self;            // warp uniform, <= 33
-    const int ti = a.Pt ? sl - a.gfirst[g] : i;            // row of the target side in stT / s_b
+    const int ti = a.Pt ? tk : i;                           // row of the target side in stT / s_b
     const float* trow = stT + ti * kLD + sub * 4;          // target row, re-read per round (multicast, 1 wavefront) to save 16 registers
     const float b_i = TRANSFORMER ? 0.f : s_b[ti];
     float mx = -INFINITY, den = 0.f;
@@ -722,15 +728,15 @@ int edge_dispatch(cudaStream_t st, const EdgeArgs& ea, bool tr, int Wn) {
 
 #include <stdlib.h>
 int bf16_chunk_graphs(const MlsNetDesc* d, int n_graphs) {
-  // 32 waves of 128-row GEMM tiles per chunk (about 600 K node rows, ~6 GB of bf16 workspace).
-  // Measured on B200 (profiles/r01_chunk_sweep.txt): L2-sized chunks (148 tiles) cost 35 % more
-  // per round than big ones -- launch ramp/drain of ~12 kernels per chunk outweighs the HBM
-  // round trip of the intermediates.  MLS_BF16_CHUNK_TILES overrides.
+  // Up to 12800 128-row GEMM tiles (1.64 M node rows, ~16 GB of bf16 workspace) per pass: 32768 episodes of
+  // 50 nodes go through in one pass.  Measured on B200 (profiles/r01_chunk_sweep.txt): every pass costs the
+  // ramp/drain of ~20 kernels, so fewer, larger passes win (one pass 6.36 ms/round, three passes 6.56 ms),
+  // and L2-sized chunks (148 tiles) are 35 % slower.  MLS_BF16_CHUNK_TILES overrides.
   static int tiles = 0;
   if (!tiles) {
     const char* e = getenv("MLS_BF16_CHUNK_TILES");
-    tiles = e ? atoi(e) : 4736;
-    if (tiles < 1) tiles = 4736;
+    tiles = e ? atoi(e) : 12800;
+    if (tiles < 1) tiles = 12800;
   }
   int gc = (tiles * 128) / d->n_nodes;
   if (gc < 1) gc = 1;
@@ -942,7 +948,7 @@ int dgn_forward_bf16(const MlsNetDesc* d, const MlsNetWeights* w, const MlsForwa
         // conv2 attention only where a controlling agent needs it; result goes straight into z
         EdgeArgs ea{};
         ea.P = Psrc; ea.ldp = nsrc * HC; ea.obs = obs; ea.obs_stride = a->obs_stride; ea.N = N; ea.H = H; ea.n_graphs = gc;
-        ea.Pt = Ptgt; ea.ldpt = HC; ea.bt = dots_t; ea.gfirst = ws.gfirst; ea.gcnt = ws.gcnt;
+        ea.Pt = Ptgt; ea.ldpt = HC; ea.bt = dots_t; ea.gfirst = ws.gfirst; ea.gcnt = ws.gcnt; ea.idx = ws.idx;
         ea.att = w->c2_att; ea.bias = w->c2_bias; ea.csr_ptr = ws.csr_ptr; ea.csr_src = ws.csr_src; ea.ab = ws.ab; ea.x_out = nullptr; ea.slot = ws.slot; ea.z = ws.z; ea.ldz = latent;
         ea.z_col = hid + HC; ea.ctrl_only = 1; ea.pool_mode = -1;
         prof_begin(MLS_PROF_EDGE2);
