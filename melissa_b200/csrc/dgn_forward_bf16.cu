@@ -52,9 +52,9 @@ __global__ void cvt_weights_kernel(const CvtJobs jobs) {
   }
 }
 struct CatJobs {
-  const float* src[8];
-  float* dst[8];
-  int n[8];
+  const float* src[12];
+  float* dst[12];
+  int n[12];
   int count;
 };
 __global__ void cat_bias_kernel(const CatJobs jobs) {
@@ -173,11 +173,14 @@ __global__ void __launch_bounds__(256) graph_csr_kernel(const float* __restrict_
   extern __shared__ __align__(16) unsigned char csm[];
   uint32_t* s_mask = reinterpret_cast<uint32_t*>(csm);      // [N][W]
   int* s_ptr = reinterpret_cast<int*>(s_mask + (size_t)N * W);   // [N+1]
+  float* s_pos = reinterpret_cast<float*>(s_ptr + N + 1);   // [N][2]: one trip to global memory for the positions
   const int g = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float* g_obs = obs + (int64_t)g * obs_stride;
+  for (int t = threadIdx.x; t < 2 * N; t += 256) s_pos[t] = g_obs[(t >> 1) * 8 + (t & 1)];
+  __syncthreads();
   for (int i = warp; i < N; i += 8) {
     uint32_t nb[W];
-    radius_neighbours<W>(g_obs, N, i, lane, nb);
+    radius_neighbours<W>(s_pos, N, i, lane, nb, 2);
     int deg = 0;
 #pragma unroll
     for (int w = 0; w < W; ++w) {
@@ -256,6 +259,18 @@ struct EdgeArgs {
 template <bool TRANSFORMER> struct EdgeCfg { static constexpr int kThreads = TRANSFORMER ? 256 : 128; };
 constexpr int kLD = kC;                 // staged row pitch in floats (a warp reads 4 x 128 B row segments = the 4-wavefront minimum)
 
+__device__ __forceinline__ void edge_cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void edge_cp_async_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// 8 bf16 -> two float4 (exact: a bf16 is the upper half of an fp32)
+__device__ __forceinline__ void bf16x8_to_f32(const uint4 u, float4& lo, float4& hi) {
+  lo = make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u), __uint_as_float(u.y << 16), __uint_as_float(u.y & 0xffff0000u));
+  hi = make_float4(__uint_as_float(u.z << 16), __uint_as_float(u.z & 0xffff0000u), __uint_as_float(u.w << 16), __uint_as_float(u.w & 0xffff0000u));
+}
+// Channel slices of a lane: sub = lane & 7 owns channels [8 sub, 8 sub + 8) and [64 + 8 sub, 64 + 8 sub + 8) of the head, as
+// four float4 "it" = 0..3 (two 16-byte chunks of the bf16 row: 8 lanes read 128 contiguous bytes).
+__device__ __forceinline__ int edge_chan(int it, int sub) { return (it >> 1) * 64 + sub * 8 + (it & 1) * 4; }
 __device__ __forceinline__ float fast_ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -283,10 +298,10 @@ __global__ void __launch_bounds__(EdgeCfg<TRANSFORMER>::kThreads, 512 / EdgeCfg<
   constexpr int kEdgeThreads = EdgeCfg<TRANSFORMER>::kThreads, kEdgeWarps = kEdgeThreads / 32;
   extern __shared__ __align__(16) unsigned char esm[];
   const int N = a.N, H = a.H, HC = H * kC;
-  float* stA = reinterpret_cast<float*>(esm);                                    // [N][kLD]  x_l or k   (source side)
-  float* stT = stA + N * kLD;                                                    // [N][kLD]  x_r or q   (target side)
-  float* stB = stT + N * kLD;                                                    // [N][kLD]  v (Transformer)
-  float* s_a = stB + (TRANSFORMER ? N * kLD : 0);                                // [N] <att, x_l[j]> * 0.6 log2e
+  float* stT = reinterpret_cast<float*>(esm);                                    // [N][kLD] fp32  x_r or q (target side), float4 (it*8+sub) = channels edge_chan(it, sub)
+  bf16* stA = reinterpret_cast<bf16*>(stT + N * kLD);                            // [N][kC]  bf16  x_l or k (source side), raw rows
+  bf16* stB = stA + N * kC;                                                      // [N][kC]  bf16  v (Transformer)
+  float* s_a = reinterpret_cast<float*>(stB + (TRANSFORMER ? N * kC : 0));       // [N] <att, x_l[j]> * 0.6 log2e
   float* s_b = s_a + N;                                                          // [N] <att, x_r[i]> * 0.6 log2e
   float* s_dm = s_b + N;                                                         // [N]
   int* s_slot = reinterpret_cast<int*>(s_dm + N);                                // [N]
@@ -308,23 +323,32 @@ __global__ void __launch_bounds__(EdgeCfg<TRANSFORMER>::kThreads, 512 / EdgeCfg<
     const int src_col = (TRANSFORMER && !compact ? HC : 0) + h * kC;
     const int val_col = (compact ? HC : 2 * HC) + h * kC;  // Transformer values
     const int tgt_col = (TRANSFORMER ? 0 : HC) + h * kC;
-    for (int t = tid; t < N * (kC / 4); t += kEdgeThreads) {
-      const int j = t >> 5, q = t & 31;                     // kC / 4 == 32 float4 per row
-      const bf16* row = a.P + (a.row_key ? (size_t)a.row_key[base + j] : base + j) * a.ldp;
-      *reinterpret_cast<float4*>(stA + j * kLD + q * 4) = ld_bf16x4(row + src_col + q * 4);
-      if (!compact) *reinterpret_cast<float4*>(stT + j * kLD + q * 4) = ld_bf16x4(row + tgt_col + q * 4);
-      if (TRANSFORMER) *reinterpret_cast<float4*>(stB + j * kLD + q * 4) = ld_bf16x4(row + val_col + q * 4);
-    }
-    if (compact) {                                          // target rows of the graph's controlling nodes: consecutive slots
-      const int first = a.gfirst[g], cnt = a.gcnt[g];
-      for (int t = tid; t < cnt * (kC / 4); t += kEdgeThreads) {
-        const int k = t >> 5, q = t & 31;
-        *reinterpret_cast<float4*>(stT + k * kLD + q * 4) = ld_bf16x4(a.Pt + (size_t)(first + k) * a.ldpt + h * kC + q * 4);
+    // source side: raw bf16 rows, copied asynchronously (no registers, all loads in flight at once)
+    {
+      const uint32_t sA32 = (uint32_t)__cvta_generic_to_shared(stA), sB32 = (uint32_t)__cvta_generic_to_shared(stB);
+      for (int t = tid; t < N * 16; t += kEdgeThreads) {
+        const int j = t >> 4, c = t & 15;                   // 16 chunks of 16 B per 128-channel row
+        const bf16* row = a.P + (a.row_key ? (size_t)a.row_key[base + j] : base + j) * a.ldp;
+        edge_cp_async16(sA32 + j * (kC * 2) + c * 16, row + src_col + c * 8);
+        if (TRANSFORMER) edge_cp_async16(sB32 + j * (kC * 2) + c * 16, row + val_col + c * 8);
       }
-      int* s_tl = reinterpret_cast<int*>(s_dm);            // target list (s_dm is only read by the pooling variant)
-      for (int k = tid; k < cnt; k += kEdgeThreads) {
-        s_tl[k] = a.idx[first + k] - (int)base;
-        if (!TRANSFORMER) s_b[k] = a.bt[(size_t)(first + k) * H + h] * (0.6f * kLog2e);
+    }
+    // target side: fp32, in the lanes' channel order
+    {
+      const int first = compact ? a.gfirst[g] : 0, cnt = compact ? a.gcnt[g] : N;
+      for (int t = tid; t < cnt * (kC / 4); t += kEdgeThreads) {
+        const int k = t >> 5, q = t & 31;                   // float4 q of the row = channels 4q .. 4q+3
+        const int c = q * 4, pos = ((((c >> 6) << 1) | ((c >> 2) & 1)) * 8 + ((c & 63) >> 3)) * 4;
+        const bf16* src = compact ? a.Pt + (size_t)(first + k) * a.ldpt + h * kC
+                                  : a.P + (a.row_key ? (size_t)a.row_key[base + k] : base + k) * a.ldp + tgt_col;
+        *reinterpret_cast<float4*>(stT + k * kLD + pos) = ld_bf16x4(src + c);
+      }
+      if (compact) {
+        int* s_tl = reinterpret_cast<int*>(s_dm);          // target list (s_dm is only read by the pooling variant)
+        for (int k = tid; k < cnt; k += kEdgeThreads) {
+          s_tl[k] = a.idx[first + k] - (int)base;
+          if (!TRANSFORMER) s_b[k] = a.bt[(size_t)(first + k) * H + h] * (0.6f * kLog2e);
+        }
       }
     }
     const uint16_t* gp = a.csr_ptr + (size_t)g * (N + 1);
@@ -345,23 +369,25 @@ __global__ void __launch_bounds__(EdgeCfg<TRANSFORMER>::kThreads, 512 / EdgeCfg<
     const int E = gp[N];
     for (int t = tid; t < E; t += kEdgeThreads) s_src[t] = gs[t];
   }
-  float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (!TRANSFORMER) bias4 = *reinterpret_cast<const float4*>(a.bias + h * kC + lane * 4);
   const int grp = lane >> 3, sub = lane & 7;                // neighbour slot of the round / channel slice
+  const int och = edge_chan(grp, sub);                      // channels this lane owns after the reduce-scatter
+  float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (!TRANSFORMER) bias4 = *reinterpret_cast<const float4*>(a.bias + h * kC + och);
   float4 attn[4];
 #pragma unroll
   for (int it = 0; it < 4; ++it) {
     attn[it] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (!TRANSFORMER) {
-      const float4 v = *reinterpret_cast<const float4*>(a.att + h * kC + (it * 8 + sub) * 4);
+      const float4 v = *reinterpret_cast<const float4*>(a.att + h * kC + edge_chan(it, sub));
       const float sc = 0.4f * kLog2e;
       attn[it] = make_float4(v.x * sc, v.y * sc, v.z * sc, v.w * sc);
     }
   }
+  edge_cp_async_wait();
   __syncthreads();
   // ---------------------------------------------------------------- phase 1
   const float tr_scale = kLog2e / sqrtf((float)kC);
-  const float* stV = TRANSFORMER ? stB : stA;
+  const bf16* stV = TRANSFORMER ? stB : stA;
   const int self = TRANSFORMER ? 0 : 1;                     // GATv2: slot 0 of every target is its self loop
   float4 pool = a.pool_mode == MLS_POOL_MAX ? make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY)
                                             : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -385,14 +411,14 @@ __global__ void __launch_bounds__(EdgeCfg<TRANSFORMER>::kThreads, 512 / EdgeCfg<
       int j0 = i, j1 = i;
       if (v0 && k0 >= self) j0 = s_src[r0 + k0 - self];
       if (v1) j1 = s_src[r0 + k1 - self];                   // k1 >= 4 > self
-      const float* xr0 = stA + j0 * kLD + sub * 4;
-      const float* xr1 = stA + j1 * kLD + sub * 4;
+      const uint4* xr0 = reinterpret_cast<const uint4*>(stA + j0 * kC);
+      const uint4* xr1 = reinterpret_cast<const uint4*>(stA + j1 * kC);
       float4 x0[4], x1[4];
+      bf16x8_to_f32(xr0[sub], x0[0], x0[1]); bf16x8_to_f32(xr0[sub + 8], x0[2], x0[3]);
+      bf16x8_to_f32(xr1[sub], x1[0], x1[1]); bf16x8_to_f32(xr1[sub + 8], x1[2], x1[3]);
       float pa0 = 0.f, pb0 = 0.f, pa1 = 0.f, pb1 = 0.f;     // two partial sums per chain: shorter FFMA dependency
 #pragma unroll
       for (int it = 0; it < 4; ++it) {
-        x0[it] = *reinterpret_cast<const float4*>(xr0 + it * 32);
-        x1[it] = *reinterpret_cast<const float4*>(xr1 + it * 32);
         const float4 t4 = *reinterpret_cast<const float4*>(trow + it * 32);
         if (TRANSFORMER) {
           pa0 = fmaf(x0[it].x, t4.x, pa0); pb0 = fmaf(x0[it].y, t4.y, pb0); pa0 = fmaf(x0[it].z, t4.z, pa0); pb0 = fmaf(x0[it].w, t4.w, pb0);
@@ -425,13 +451,10 @@ __global__ void __launch_bounds__(EdgeCfg<TRANSFORMER>::kThreads, 512 / EdgeCfg<
       const float p0 = fast_ex2(e0 - mx), p1 = fast_ex2(e1 - mx);   // 0 for padded slots
       den += p0 + p1;                                       // per-group partial
       if (TRANSFORMER) {
-        const float* vr0 = stV + j0 * kLD + sub * 4;
-        const float* vr1 = stV + j1 * kLD + sub * 4;
-#pragma unroll
-        for (int it = 0; it < 4; ++it) {
-          x0[it] = *reinterpret_cast<const float4*>(vr0 + it * 32);
-          x1[it] = *reinterpret_cast<const float4*>(vr1 + it * 32);
-        }
+        const uint4* vr0 = reinterpret_cast<const uint4*>(stV + j0 * kC);
+        const uint4* vr1 = reinterpret_cast<const uint4*>(stV + j1 * kC);
+        bf16x8_to_f32(vr0[sub], x0[0], x0[1]); bf16x8_to_f32(vr0[sub + 8], x0[2], x0[3]);
+        bf16x8_to_f32(vr1[sub], x1[0], x1[1]); bf16x8_to_f32(vr1[sub + 8], x1[2], x1[3]);
       }
 #pragma unroll
       for (int it = 0; it < 4; ++it) {
@@ -464,8 +487,8 @@ __global__ void __launch_bounds__(EdgeCfg<TRANSFORMER>::kThreads, 512 / EdgeCfg<
     float4 o;
     o.x = fmaxf(fmaf(mine.x, inv_den, bias4.x), 0.f); o.y = fmaxf(fmaf(mine.y, inv_den, bias4.y), 0.f);
     o.z = fmaxf(fmaf(mine.z, inv_den, bias4.z), 0.f); o.w = fmaxf(fmaf(mine.w, inv_den, bias4.w), 0.f);
-    if (a.x_out) st_bf16x4(a.x_out + (base + i) * HC + h * kC + lane * 4, o);
-    if (a.z && sl >= 0 && a.pool_mode < 0) st_bf16x4(a.z + (size_t)sl * a.ldz + a.z_col + h * kC + lane * 4, o);
+    if (a.x_out) st_bf16x4(a.x_out + (base + i) * HC + h * kC + och, o);
+    if (a.z && sl >= 0 && a.pool_mode < 0) st_bf16x4(a.z + (size_t)sl * a.ldz + a.z_col + h * kC + och, o);
     if (a.pool_mode >= 0) {
       const float dm = s_dm[i];
       const float4 v = make_float4(o.x * dm, o.y * dm, o.z * dm, o.w * dm);
@@ -474,7 +497,7 @@ __global__ void __launch_bounds__(EdgeCfg<TRANSFORMER>::kThreads, 512 / EdgeCfg<
     }
   }
   if (a.pool_mode >= 0) {      // HL-DGN: z[g] = pool_i(relu(conv)[i] * dm[i])  (hl_dgn.py:103-108)
-    *reinterpret_cast<float4*>(poolbuf + warp * kC + lane * 4) = pool;
+    *reinterpret_cast<float4*>(poolbuf + warp * kC + och) = pool;
     __syncthreads();
     if (tid < kC) {
       const int used = N < kEdgeWarps ? N : kEdgeWarps;        // warps that own at least one node
@@ -598,6 +621,27 @@ __global__ void head_out_bf16_kernel(const bf16* __restrict__ hid, int hh, const
   }
 }
 
+// Output layer of the dueling heads from the three dot products the last hidden-layer GEMM left per row
+// (dots[t] = (<relu(hq), wq[0]>, <relu(hv), wv>), dots2[t] = (<relu(hq), wq[1]>, -)); same outputs as head_out_bf16_kernel.
+__global__ void head_final_kernel(const float* __restrict__ dots, const float* __restrict__ dots2, const int* __restrict__ idx,
+                                  const int* __restrict__ count, int max_rows, const float* __restrict__ bq, const float* __restrict__ bv,
+                                  int64_t row0, int per_graph_N, float* __restrict__ q_out, int8_t* __restrict__ act_out, int out_mode,
+                                  ActArgsB aa) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = count ? min(*count, max_rows) : max_rows;
+  if (t >= n) return;
+  const float s0 = dots[t * 2] + bq[0], sv = dots[t * 2 + 1] + bv[0], s1 = dots2[t * 2] + bq[1];
+  const float mean = (s0 + s1) / 2.0f;
+  const float o0 = (s0 - mean) + sv, o1 = (s1 - mean) + sv;
+  int64_t orow;
+  if (out_mode == 0) orow = row0 + idx[t];
+  else if (out_mode == 1) orow = row0 / per_graph_N + idx[t] / per_graph_N;
+  else orow = t;
+  q_out[orow * 2 + 0] = o0;
+  q_out[orow * 2 + 1] = o1;
+  if (act_out && out_mode != 2) act_out[orow] = (int8_t)select_action_b(o0, o1, aa, (uint64_t)orow);
+}
+
 __global__ void hl_scatter_b_kernel(const float* __restrict__ qg, const uint8_t* __restrict__ ctrl_mask, int N, int n_graphs,
                                     int64_t graph0, int mode, float* __restrict__ q_out, int8_t* __restrict__ act_out, ActArgsB aa) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -631,6 +675,7 @@ int table_keys(int n_nodes) { return (1 << degree_bits(n_nodes)) * 512; }     //
 struct WsB {
   bf16 *w_enc1, *w_c1, *w_c2, *w_h0, *w_h1;
   float *b_c1, *b_c2, *b_h0, *b_h1;
+  float *hv1, *hv2, *hd;      // output-layer dot vectors [2*hh] each; per-row dots [T][4]
   bf16 *h, *x0, *P, *x1, *z, *hid1, *hid2;
   float* qg;
   int *idx, *slot, *count, *gfirst, *gcnt;
@@ -662,8 +707,10 @@ size_t carve_b(const MlsNetDesc* d, int Gc, unsigned char* base, WsB* ws) {
   const size_t o_wc2 = take(hl ? 0 : (size_t)nproj * HC * HC * 2), o_wh0 = take((size_t)hh2 * latent * 2);
   const size_t o_wh1 = take((size_t)hh2 * hh2 * 2);
   const size_t o_bc1 = take((size_t)nproj * HC * 4), o_bc2 = take((size_t)nproj * HC * 4), o_bh0 = take(hh2 * 4), o_bh1 = take(hh2 * 4);
+  const size_t o_hv1 = take(hh2 * 4), o_hv2 = take(hh2 * 4);
   const size_t o_h = take(R * hid * 2), o_x0 = take(R * hid * 2), o_P = take(R * nproj * HC * 2);
   const size_t o_x1 = take(hl ? 0 : R * HC * 2), o_z = take(T * latent * 2), o_h1 = take(T * hh2 * 2), o_h2 = take(T * hh2 * 2);
+  const size_t o_hd = take(T * 4 * 4);
   const size_t o_qg = take((size_t)Gc * 8), o_idx = take(R * 4), o_slot = take(R * 4), o_cnt = take(4);
   const size_t o_gf = take((size_t)Gc * 4), o_gc = take((size_t)Gc * 4);
   const size_t o_cptr = take(((size_t)Gc * (d->n_nodes + 1) + 64) * 2), o_csrc = take((size_t)Gc * d->n_nodes * kMaxNbr + 64);
@@ -679,6 +726,7 @@ size_t carve_b(const MlsNetDesc* d, int Gc, unsigned char* base, WsB* ws) {
     auto F = [&](size_t o) { return reinterpret_cast<float*>(base + o); };
     ws->w_enc1 = B(o_we); ws->w_c1 = B(o_wc1); ws->w_c2 = B(o_wc2); ws->w_h0 = B(o_wh0); ws->w_h1 = B(o_wh1);
     ws->b_c1 = F(o_bc1); ws->b_c2 = F(o_bc2); ws->b_h0 = F(o_bh0); ws->b_h1 = F(o_bh1);
+    ws->hv1 = F(o_hv1); ws->hv2 = F(o_hv2); ws->hd = F(o_hd);
     ws->h = B(o_h); ws->x0 = B(o_x0); ws->P = B(o_P); ws->x1 = B(o_x1); ws->z = B(o_z); ws->hid1 = B(o_h1); ws->hid2 = B(o_h2);
     ws->qg = F(o_qg);
     ws->idx = reinterpret_cast<int*>(base + o_idx); ws->slot = reinterpret_cast<int*>(base + o_slot);
@@ -697,7 +745,7 @@ size_t carve_b(const MlsNetDesc* d, int Gc, unsigned char* base, WsB* ws) {
 template <bool TR>
 int launch_edge(cudaStream_t st, const EdgeArgs& ea) {
   constexpr int kEdgeThreads = EdgeCfg<TR>::kThreads, kEdgeWarps = kEdgeThreads / 32;
-  const size_t smem = (size_t)ea.N * kLD * 4 * (TR ? 3 : 2) + (size_t)ea.N * 4 * 4 + (ea.pool_mode >= 0 ? kEdgeWarps * kC * 4 : 0) +
+  const size_t smem = (size_t)ea.N * kLD * 4 + (size_t)ea.N * kC * 2 * (TR ? 2 : 1) + (size_t)ea.N * 4 * 4 + (ea.pool_mode >= 0 ? kEdgeWarps * kC * 4 : 0) +
                       ((size_t)ea.N + 1) * 2 + (size_t)ea.N * kMaxNbr + 16;
   static size_t configured = 0;
   if (smem > 227 * 1024) {
@@ -801,6 +849,9 @@ int dgn_forward_bf16(const MlsNetDesc* d, const MlsNetWeights* w, const MlsForwa
     if (!tr) { addb(w->c1_att, ws.att1, HC); addb(w->c1_att, ws.att1 + HC, HC); }
     addb(w->q_b0, ws.b_h0, hh); addb(w->v_b0, ws.b_h0 + hh, hh);
     addb(w->q_b1, ws.b_h1, hh); addb(w->v_b1, ws.b_h1 + hh, hh);
+    // output layer as dot vectors for the epilogue of the last hidden-layer GEMM: [wq[0] | wv], [wq[1] | 0]
+    MLS_CUDA(cudaMemsetAsync(ws.hv2, 0, (size_t)hh2 * 4, st));
+    addb(w->q_w2, ws.hv1, hh); addb(w->v_w2, ws.hv1 + hh, hh); addb(w->q_w2 + hh, ws.hv2, hh);
     bj.count = m;
     cat_bias_kernel<<<dim3(2, m), 256, 0, st>>>(bj);
     if (!hl) {
@@ -853,7 +904,7 @@ int dgn_forward_bf16(const MlsNetDesc* d, const MlsNetWeights* w, const MlsForwa
       mls_count_launch();
     }
     {
-      const size_t csm = (size_t)N * Wn * 4 + ((size_t)N + 1) * 4;
+      const size_t csm = (size_t)N * Wn * 4 + ((size_t)N + 1) * 4 + (size_t)N * 8;
       switch (Wn) {
         case 1: graph_csr_kernel<1><<<gc, 256, csm, st>>>(obs, a->obs_stride, N, gc, ws.csr_ptr, ws.csr_src); break;
         case 2: graph_csr_kernel<2><<<gc, 256, csm, st>>>(obs, a->obs_stride, N, gc, ws.csr_ptr, ws.csr_src); break;
@@ -967,19 +1018,32 @@ int dgn_forward_bf16(const MlsNetDesc* d, const MlsNetWeights* w, const MlsForwa
       prof_begin(MLS_PROF_HEAD0);
       if ((rc = gemm_bf16_launch(ws.z, latent, ws.w_h0, latent, GemmShape{head_rows, hh2, latent, m_dev}, e0, sms, st))) return rc;
       prof_end(MLS_PROF_HEAD0);
-      GemmEpilogue e1{ws.hid2, hh2, ws.b_h1, nullptr, 0, N, 1, nullptr, nullptr};
+      // last hidden layer: with 128-wide heads the output layer rides in the epilogue as three dot products per
+      // row and the hidden activations are never written
+      const bool fuse_out = hh == 128;
+      GemmEpilogue e1{fuse_out ? nullptr : ws.hid2, hh2, ws.b_h1, nullptr, 0, N, 1, nullptr, nullptr, nullptr, nullptr, nullptr, 0};
+      if (fuse_out) { e1.dotvec = ws.hv1; e1.dots = ws.hd; e1.dotvec2 = ws.hv2; e1.dots2 = ws.hd + (size_t)head_rows * 2; e1.dot_relu = 1; }
       if ((rc = gemm_bf16_launch(ws.hid1, hh2, ws.w_h1, hh2, GemmShape{head_rows, hh2, hh2, m_dev}, e1, sms, st))) return rc;
-    }
-    if (!hl) {
-      head_out_bf16_kernel<<<(rows * 32 + 255) / 256, 256, 0, st>>>(ws.hid2, hh, ws.idx, ws.count, rows, w->q_w2, w->q_b2, w->v_w2,
-                                                                     w->v_b2, (int64_t)g0 * N, N, a->q, a->act, a->ctrl_mode, aa);
-      mls_count_launch();
-    } else {
-      head_out_bf16_kernel<<<(gc * 32 + 255) / 256, 256, 0, st>>>(ws.hid2, hh, nullptr, nullptr, gc, w->q_w2, w->q_b2, w->v_w2,
-                                                                   w->v_b2, 0, N, ws.qg, nullptr, 2, aa);
-      const long long nthr = a->ctrl_mode == 1 ? gc : (long long)gc * N;
-      hl_scatter_b_kernel<<<(unsigned)((nthr + 255) / 256), 256, 0, st>>>(ws.qg, cm, N, gc, g0, a->ctrl_mode, a->q, a->act, aa);
-      mls_count_launch(2);
+      const float* d1 = ws.hd;
+      const float* d2 = ws.hd + (size_t)head_rows * 2;
+      if (!hl) {
+        if (fuse_out)
+          head_final_kernel<<<(rows + 255) / 256, 256, 0, st>>>(d1, d2, ws.idx, ws.count, rows, w->q_b2, w->v_b2, (int64_t)g0 * N, N, a->q,
+                                                               a->act, a->ctrl_mode, aa);
+        else
+          head_out_bf16_kernel<<<(rows * 32 + 255) / 256, 256, 0, st>>>(ws.hid2, hh, ws.idx, ws.count, rows, w->q_w2, w->q_b2, w->v_w2,
+                                                                         w->v_b2, (int64_t)g0 * N, N, a->q, a->act, a->ctrl_mode, aa);
+        mls_count_launch();
+      } else {
+        if (fuse_out)
+          head_final_kernel<<<(gc + 255) / 256, 256, 0, st>>>(d1, d2, nullptr, nullptr, gc, w->q_b2, w->v_b2, 0, N, ws.qg, nullptr, 2, aa);
+        else
+          head_out_bf16_kernel<<<(gc * 32 + 255) / 256, 256, 0, st>>>(ws.hid2, hh, nullptr, nullptr, gc, w->q_w2, w->q_b2, w->v_w2,
+                                                                       w->v_b2, 0, N, ws.qg, nullptr, 2, aa);
+        const long long nthr = a->ctrl_mode == 1 ? gc : (long long)gc * N;
+        hl_scatter_b_kernel<<<(unsigned)((nthr + 255) / 256), 256, 0, st>>>(ws.qg, cm, N, gc, g0, a->ctrl_mode, a->q, a->act, aa);
+        mls_count_launch(2);
+      }
     }
     MLS_LAUNCH_CHECK();
     first_chunk = false;

@@ -32,8 +32,9 @@ __device__ __forceinline__ float warp_sum(float v) {
 // included), self dropped.  Warp-cooperative; result words are warp-uniform.
 template <int W>
 __device__ __forceinline__ void radius_neighbours(const float* __restrict__ g_obs, int N, int i, int lane,
-                                                  uint32_t (&nb)[W]) {
-  const float xi = g_obs[i * 8 + 0], yi = g_obs[i * 8 + 1];
+                                                  uint32_t (&nb)[W], const int stride = 8) {
+  // `stride` floats between node rows: 8 for observation rows, 2 for a staged (x, y) array
+  const float xi = g_obs[i * stride + 0], yi = g_obs[i * stride + 1];
   const float thr = r2_threshold();
   int total = 0;
 #pragma unroll
@@ -41,7 +42,7 @@ __device__ __forceinline__ void radius_neighbours(const float* __restrict__ g_ob
     const int j = w * 32 + lane;
     bool hit = false;
     if (j < N) {
-      const float dx = g_obs[j * 8 + 0] - xi, dy = g_obs[j * 8 + 1] - yi;
+      const float dx = g_obs[j * stride + 0] - xi, dy = g_obs[j * stride + 1] - yi;
       const float d2 = __fmaf_rn(dy, dy, __fmul_rn(dx, dx));
       hit = d2 < thr;
     }

@@ -19,7 +19,8 @@ struct GemmSmem {
   static constexpr int kOutOffset = kNumStages * kStageBytes;
   static constexpr int kBiasOffset = kOutOffset + 8 * kOutWarpBytes;      // BN floats
   static constexpr int kDotOffset = kBiasOffset + BN * 4;                 // BN floats
-  static constexpr int kBarOffset = kDotOffset + BN * 4;
+  static constexpr int kDot2Offset = kDotOffset + BN * 4;                 // BN floats
+  static constexpr int kBarOffset = kDot2Offset + BN * 4;
   static constexpr int kTotal = kBarOffset + 256 + 1024;   // barriers + alignment slack
 };
 
@@ -118,6 +119,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     unsigned char* stage_out = smem + S::kOutOffset + (warp - 4) * S::kOutWarpBytes;
     float* bias_s = reinterpret_cast<float*>(smem + S::kBiasOffset);
     float* dot_s = reinterpret_cast<float*>(smem + S::kDotOffset);
+    float* dot2_s = reinterpret_cast<float*>(smem + S::kDot2Offset);
     const int et = threadIdx.x - 128;                       // 0..255 within the epilogue warps
     int it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
@@ -136,11 +138,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       for (int c = et; c < BN; c += 256) {
         bias_s[c] = epi.bias ? __ldg(epi.bias + n0 + c) : 0.0f;
         if (epi.dotvec) dot_s[c] = __ldg(epi.dotvec + n0 + c);
+        if (epi.dotvec2) dot2_s[c] = __ldg(epi.dotvec2 + n0 + c);
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      float dot = 0.f;
+      float dot = 0.f, dot2 = 0.f;
 #pragma unroll 1
       for (int c0 = cb; c0 < cb + HN; c0 += 32) {
         uint32_t v[32];
@@ -153,19 +156,30 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           float x2 = fmaf(__uint_as_float(v[j + 2]), scale, b4.z), x3 = fmaf(__uint_as_float(v[j + 3]), scale, b4.w);
           if (epi.dotvec) {
             const float4 d4 = *reinterpret_cast<const float4*>(dot_s + c0 + j);
-            dot = fmaf(x0, d4.x, dot); dot = fmaf(x1, d4.y, dot); dot = fmaf(x2, d4.z, dot); dot = fmaf(x3, d4.w, dot);
+            const float y0 = epi.dot_relu ? fmaxf(x0, 0.f) : x0, y1 = epi.dot_relu ? fmaxf(x1, 0.f) : x1;
+            const float y2 = epi.dot_relu ? fmaxf(x2, 0.f) : x2, y3 = epi.dot_relu ? fmaxf(x3, 0.f) : x3;
+            dot = fmaf(y0, d4.x, dot); dot = fmaf(y1, d4.y, dot); dot = fmaf(y2, d4.z, dot); dot = fmaf(y3, d4.w, dot);
+            if (epi.dotvec2) {
+              const float4 e4 = *reinterpret_cast<const float4*>(dot2_s + c0 + j);
+              dot2 = fmaf(y0, e4.x, dot2); dot2 = fmaf(y1, e4.y, dot2); dot2 = fmaf(y2, e4.z, dot2); dot2 = fmaf(y3, e4.w, dot2);
+            }
           }
           if (epi.relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f); }
           __nv_bfloat162 p0 = __floats2bfloat162_rn(x0, x1), p1 = __floats2bfloat162_rn(x2, x3);
           packed[j >> 1] = *reinterpret_cast<uint32_t*>(&p0);
           packed[(j >> 1) + 1] = *reinterpret_cast<uint32_t*>(&p1);
         }
-        uint4* dst = reinterpret_cast<uint4*>(stage_out + lane * S::kOutRowBytes + (c0 - cb) * 2);
+        if (epi.C) {
+          uint4* dst = reinterpret_cast<uint4*>(stage_out + lane * S::kOutRowBytes + (c0 - cb) * 2);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) dst[q] = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+          for (int q = 0; q < 4; ++q) dst[q] = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+        }
         if (epi.dotvec && (c0 & 96) == 96) {                 // end of a 128-column group
-          if (r < M) epi.dots[(size_t)r * (shape.N >> 7) + ((n0 + c0) >> 7)] = dot;
-          dot = 0.f;
+          if (r < M) {
+            epi.dots[(size_t)r * (shape.N >> 7) + ((n0 + c0) >> 7)] = dot;
+            if (epi.dotvec2) epi.dots2[(size_t)r * (shape.N >> 7) + ((n0 + c0) >> 7)] = dot2;
+          }
+          dot = 0.f; dot2 = 0.f;
         }
       }
       // accumulator drained: hand it back to the MMA warp before the global stores
@@ -176,12 +190,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       constexpr int kLanesPerRow = HN * 2 / 16;             // 8 (BN=128) or 16 (BN=256) lanes cover one row segment
       constexpr int kRowsPerIter = 32 / kLanesPerRow;
       const int sub = lane / kLanesPerRow, cl = lane % kLanesPerRow;
+      if (epi.C) {
 #pragma unroll 4
-      for (int rr = 0; rr < 32; rr += kRowsPerIter) {
-        const int row = rr + sub;
-        const int gr = m0 + ew * 32 + row;
-        const uint4 val = *reinterpret_cast<const uint4*>(stage_out + row * S::kOutRowBytes + cl * 16);
-        if (gr < M) *reinterpret_cast<uint4*>(epi.C + (size_t)gr * epi.ldc + n0 + cb + cl * 8) = val;
+        for (int rr = 0; rr < 32; rr += kRowsPerIter) {
+          const int row = rr + sub;
+          const int gr = m0 + ew * 32 + row;
+          const uint4 val = *reinterpret_cast<const uint4*>(stage_out + row * S::kOutRowBytes + cl * 16);
+          if (gr < M) *reinterpret_cast<uint4*>(epi.C + (size_t)gr * epi.ldc + n0 + cb + cl * 8) = val;
+        }
       }
       __syncwarp();
     }

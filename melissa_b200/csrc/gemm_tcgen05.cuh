@@ -30,6 +30,12 @@ struct GemmEpilogue {
   float* dots;           // [M, N / 128]
   // optional: output row m is node row row_index[m] for the row scale (compacted row sets)
   const int* row_index;
+  // optional second dot vector (dots2 laid out like dots); dot_relu: the dots use max(value, 0).
+  // C may be NULL when only the dots are wanted (last hidden layer of the dueling heads: the output
+  // layer is three dot products per row, the hidden activations themselves are never needed).
+  const float* dotvec2;
+  float* dots2;
+  int dot_relu;
 };
 
 struct GemmShape {
