@@ -253,10 +253,9 @@ struct EdgeArgs {
   int run_thresh;         // (fallback behind the tensor-core table kernel, attn_table.cu)
 };
 
-// CTA size per variant: what matters is how many CTAs fit an SM (shared memory: 2 staged operands for
-// GATv2 -> 4 CTAs of 128 threads; 3 for the Transformer conv -> 2 CTAs of 256 threads), so that staging of
-// one CTA overlaps the compute of the others at the same number of resident warps.
-template <bool TRANSFORMER> struct EdgeCfg { static constexpr int kThreads = TRANSFORMER ? 256 : 128; };
+// CTA size: 128 threads, 4 CTAs per SM (register bound), so that the staging of one CTA overlaps the compute of the
+// others.  The operands are staged as bf16 (2-3 x 12.8 KB for 50-node graphs), shared memory is no longer the limit.
+template <bool TRANSFORMER> struct EdgeCfg { static constexpr int kThreads = 128; };
 constexpr int kLD = kC;                 // staged row pitch in floats (a warp reads 4 x 128 B row segments = the 4-wavefront minimum)
 
 __device__ __forceinline__ void edge_cp_async16(uint32_t dst, const void* src) {
@@ -298,16 +297,17 @@ __global__ void __launch_bounds__(EdgeCfg<TRANSFORMER>::kThreads, 512 / EdgeCfg<
   constexpr int kEdgeThreads = EdgeCfg<TRANSFORMER>::kThreads, kEdgeWarps = kEdgeThreads / 32;
   extern __shared__ __align__(16) unsigned char esm[];
   const int N = a.N, H = a.H, HC = H * kC;
-  float* stT = reinterpret_cast<float*>(esm);                                    // [N][kLD] fp32  x_r or q (target side), float4 (it*8+sub) = channels edge_chan(it, sub)
-  bf16* stA = reinterpret_cast<bf16*>(stT + N * kLD);                            // [N][kC]  bf16  x_l or k (source side), raw rows
-  bf16* stB = stA + N * kC;                                                      // [N][kC]  bf16  v (Transformer)
+  // operands staged as raw bf16 rows (cp.async, converted at use: a bf16 is the upper half of an fp32)
+  bf16* stT = reinterpret_cast<bf16*>(esm);                                      // [N][kC]  x_r or q (target side)
+  bf16* stA = stT + N * kC;                                                      // [N][kC]  x_l or k (source side)
+  bf16* stB = stA + N * kC;                                                      // [N][kC]  v (Transformer)
   float* s_a = reinterpret_cast<float*>(stB + (TRANSFORMER ? N * kC : 0));       // [N] <att, x_l[j]> * 0.6 log2e
   float* s_b = s_a + N;                                                          // [N] <att, x_r[i]> * 0.6 log2e
   float* s_dm = s_b + N;                                                         // [N]
   int* s_slot = reinterpret_cast<int*>(s_dm + N);                                // [N]
   float* poolbuf = reinterpret_cast<float*>(s_slot + N);                         // [warps][kC]  (16 B aligned: 4N floats before it)
-  uint16_t* s_ptr = reinterpret_cast<uint16_t*>(poolbuf + (a.pool_mode >= 0 ? kEdgeWarps * kC : 0));   // [N+1]
-  uint8_t* s_src = reinterpret_cast<uint8_t*>(s_ptr + N + 1);                    // [E]
+  uint8_t* s_src = reinterpret_cast<uint8_t*>(poolbuf + (a.pool_mode >= 0 ? kEdgeWarps * kC : 0));     // [N*32] (16 B aligned)
+  uint16_t* s_ptr = reinterpret_cast<uint16_t*>(s_src + N * kMaxNbr);            // [N+1]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (a.run_if_gt && *a.run_if_gt <= a.run_thresh) return;
   // one (graph, head) per CTA; the fallback launch behind the table kernel uses a small grid and strides
@@ -323,51 +323,49 @@ __global__ void __launch_bounds__(EdgeCfg<TRANSFORMER>::kThreads, 512 / EdgeCfg<
     const int src_col = (TRANSFORMER && !compact ? HC : 0) + h * kC;
     const int val_col = (compact ? HC : 2 * HC) + h * kC;  // Transformer values
     const int tgt_col = (TRANSFORMER ? 0 : HC) + h * kC;
-    // source side: raw bf16 rows, copied asynchronously (no registers, all loads in flight at once)
-    {
-      const uint32_t sA32 = (uint32_t)__cvta_generic_to_shared(stA), sB32 = (uint32_t)__cvta_generic_to_shared(stB);
-      for (int t = tid; t < N * 16; t += kEdgeThreads) {
-        const int j = t >> 4, c = t & 15;                   // 16 chunks of 16 B per 128-channel row
-        const bf16* row = a.P + (a.row_key ? (size_t)a.row_key[base + j] : base + j) * a.ldp;
-        edge_cp_async16(sA32 + j * (kC * 2) + c * 16, row + src_col + c * 8);
-        if (TRANSFORMER) edge_cp_async16(sB32 + j * (kC * 2) + c * 16, row + val_col + c * 8);
-      }
+    // everything big is copied asynchronously (no registers, all loads in flight at once); the only chained
+    // global access is (first, cnt) -> the compact target rows, and it overlaps the rest
+    int first = 0, cnt = N;
+    if (compact) { first = a.gfirst[g]; cnt = a.gcnt[g]; }
+    const uint32_t sT32 = (uint32_t)__cvta_generic_to_shared(stT), sA32 = (uint32_t)__cvta_generic_to_shared(stA);
+    const uint32_t sB32 = (uint32_t)__cvta_generic_to_shared(stB);
+    for (int t = tid; t < N * 16; t += kEdgeThreads) {
+      const int j = t >> 4, c = t & 15;                     // 16 chunks of 16 B per 128-channel row
+      const bf16* row = a.P + (a.row_key ? (size_t)a.row_key[base + j] : base + j) * a.ldp;
+      edge_cp_async16(sA32 + j * (kC * 2) + c * 16, row + src_col + c * 8);
+      if (TRANSFORMER) edge_cp_async16(sB32 + j * (kC * 2) + c * 16, row + val_col + c * 8);
+      if (!compact) edge_cp_async16(sT32 + j * (kC * 2) + c * 16, row + tgt_col + c * 8);
     }
-    // target side: fp32, in the lanes' channel order
     {
-      const int first = compact ? a.gfirst[g] : 0, cnt = compact ? a.gcnt[g] : N;
-      for (int t = tid; t < cnt * (kC / 4); t += kEdgeThreads) {
-        const int k = t >> 5, q = t & 31;                   // float4 q of the row = channels 4q .. 4q+3
-        const int c = q * 4, pos = ((((c >> 6) << 1) | ((c >> 2) & 1)) * 8 + ((c & 63) >> 3)) * 4;
-        const bf16* src = compact ? a.Pt + (size_t)(first + k) * a.ldpt + h * kC
-                                  : a.P + (a.row_key ? (size_t)a.row_key[base + k] : base + k) * a.ldp + tgt_col;
-        *reinterpret_cast<float4*>(stT + k * kLD + pos) = ld_bf16x4(src + c);
-      }
-      if (compact) {
-        int* s_tl = reinterpret_cast<int*>(s_dm);          // target list (s_dm is only read by the pooling variant)
-        for (int k = tid; k < cnt; k += kEdgeThreads) {
-          s_tl[k] = a.idx[first + k] - (int)base;
-          if (!TRANSFORMER) s_b[k] = a.bt[(size_t)(first + k) * H + h] * (0.6f * kLog2e);
-        }
-      }
+      const uint32_t sS32 = (uint32_t)__cvta_generic_to_shared(s_src);      // the graph's whole list block (N*32 bytes, 32 B aligned)
+      const uint8_t* gs = a.csr_src + (size_t)g * N * kMaxNbr;
+      for (int t = tid; t < N * 2; t += kEdgeThreads) edge_cp_async16(sS32 + t * 16, gs + t * 16);
     }
     const uint16_t* gp = a.csr_ptr + (size_t)g * (N + 1);
-    const uint8_t* gs = a.csr_src + (size_t)g * N * kMaxNbr;
+    for (int t = tid; t <= N; t += kEdgeThreads) s_ptr[t] = gp[t];
     for (int t = tid; t < N; t += kEdgeThreads) {
       s_slot[t] = a.slot ? a.slot[base + t] : -1;
-      if (!a.Pt) s_dm[t] = g_obs[t * 8 + 7];
+      if (!compact) s_dm[t] = g_obs[t * 8 + 7];
       if (!TRANSFORMER) {
         const size_t pr = a.row_key ? (size_t)a.row_key[base + t] : base + t;
-        if (a.Pt) s_a[t] = a.ab[pr * H + h] * (0.6f * kLog2e);
+        if (compact) s_a[t] = a.ab[pr * H + h] * (0.6f * kLog2e);
         else {
           s_a[t] = a.ab[pr * (2 * H) + h] * (0.6f * kLog2e);
           s_b[t] = a.ab[pr * (2 * H) + H + h] * (0.6f * kLog2e);
         }
       }
     }
-    for (int t = tid; t <= N; t += kEdgeThreads) s_ptr[t] = gp[t];
-    const int E = gp[N];
-    for (int t = tid; t < E; t += kEdgeThreads) s_src[t] = gs[t];
+    if (compact) {                                          // target rows of the graph's controlling nodes: consecutive slots
+      for (int t = tid; t < cnt * 16; t += kEdgeThreads) {
+        const int k = t >> 4, c = t & 15;
+        edge_cp_async16(sT32 + k * (kC * 2) + c * 16, a.Pt + (size_t)(first + k) * a.ldpt + h * kC + c * 8);
+      }
+      int* s_tl = reinterpret_cast<int*>(s_dm);            // target list (s_dm is only read by the pooling variant)
+      for (int k = tid; k < cnt; k += kEdgeThreads) {
+        s_tl[k] = a.idx[first + k] - (int)base;
+        if (!TRANSFORMER) s_b[k] = a.bt[(size_t)(first + k) * H + h] * (0.6f * kLog2e);
+      }
+    }
   }
   const int grp = lane >> 3, sub = lane & 7;                // neighbour slot of the round / channel slice
   const int och = edge_chan(grp, sub);                      // channels this lane owns after the reduce-scatter
@@ -399,7 +397,7 @@ __global__ void __launch_bounds__(EdgeCfg<TRANSFORMER>::kThreads, 512 / EdgeCfg<
     const int r0 = s_ptr[i];
     const int d = (int)s_ptr[i + 1] - r0 + self;            // warp uniform, <= 33
     const int ti = a.Pt ? tk : i;                           // row of the target side in stT / s_b
-    const float* trow = stT + ti * kLD + sub * 4;          // target row, re-read per round (multicast, 1 wavefront) to save 16 registers
+    const uint4* trow = reinterpret_cast<const uint4*>(stT + ti * kC);   // target row, re-read per round (multicast, 1 wavefront) to save 16 registers
     const float b_i = TRANSFORMER ? 0.f : s_b[ti];
     float mx = -INFINITY, den = 0.f;
     float4 acc[4];
@@ -417,9 +415,11 @@ __global__ void __launch_bounds__(EdgeCfg<TRANSFORMER>::kThreads, 512 / EdgeCfg<
       bf16x8_to_f32(xr0[sub], x0[0], x0[1]); bf16x8_to_f32(xr0[sub + 8], x0[2], x0[3]);
       bf16x8_to_f32(xr1[sub], x1[0], x1[1]); bf16x8_to_f32(xr1[sub + 8], x1[2], x1[3]);
       float pa0 = 0.f, pb0 = 0.f, pa1 = 0.f, pb1 = 0.f;     // two partial sums per chain: shorter FFMA dependency
+      float4 tg[4];
+      bf16x8_to_f32(trow[sub], tg[0], tg[1]); bf16x8_to_f32(trow[sub + 8], tg[2], tg[3]);
 #pragma unroll
       for (int it = 0; it < 4; ++it) {
-        const float4 t4 = *reinterpret_cast<const float4*>(trow + it * 32);
+        const float4 t4 = tg[it];
         if (TRANSFORMER) {
           pa0 = fmaf(x0[it].x, t4.x, pa0); pb0 = fmaf(x0[it].y, t4.y, pb0); pa0 = fmaf(x0[it].z, t4.z, pa0); pb0 = fmaf(x0[it].w, t4.w, pb0);
           pa1 = fmaf(x1[it].x, t4.x, pa1); pb1 = fmaf(x1[it].y, t4.y, pb1); pa1 = fmaf(x1[it].z, t4.z, pa1); pb1 = fmaf(x1[it].w, t4.w, pb1);
@@ -745,7 +745,7 @@ size_t carve_b(const MlsNetDesc* d, int Gc, unsigned char* base, WsB* ws) {
 template <bool TR>
 int launch_edge(cudaStream_t st, const EdgeArgs& ea) {
   constexpr int kEdgeThreads = EdgeCfg<TR>::kThreads, kEdgeWarps = kEdgeThreads / 32;
-  const size_t smem = (size_t)ea.N * kLD * 4 + (size_t)ea.N * kC * 2 * (TR ? 2 : 1) + (size_t)ea.N * 4 * 4 + (ea.pool_mode >= 0 ? kEdgeWarps * kC * 4 : 0) +
+  const size_t smem = (size_t)ea.N * kC * 2 * (TR ? 3 : 2) + (size_t)ea.N * 4 * 4 + (ea.pool_mode >= 0 ? kEdgeWarps * kC * 4 : 0) +
                       ((size_t)ea.N + 1) * 2 + (size_t)ea.N * kMaxNbr + 16;
   static size_t configured = 0;
   if (smem > 227 * 1024) {
