@@ -105,30 +105,43 @@ class ClockSampler:
 
     def __init__(self, gpu_index):
         self.gpu, self.rows, self.proc = gpu_index, [], None
+        self.t0 = self.t1 = None
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "20", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
             self.proc = None
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        # samples that arrived inside the timed region; a region shorter than nvidia-smi's reporting period
+        # falls back to every sample since the sampler started (the warm-up rounds are the same load)
+        inside = [r for t, r in self.rows if self.t0 is not None and self.t0 <= t <= (self.t1 or t) + 0.02]
+        window = "timed region"
+        if not inside:
+            inside, window = [r for _, r in self.rows], "warm-up + timed region (same load)"
+        sm = [float(r[1]) for r in inside if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in inside if len(r) >= 9 and r[2].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v.lower().startswith("active")})
+        reasons = sorted({n for r in inside if len(r) >= 9 for n, v in zip(names, r[5:9]) if v.lower().startswith("active")})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "window": window}
 
 
 # ------------------------------------------------------------------------------ our arm
@@ -214,8 +227,10 @@ def run_ours(args):
             ro.round()
         sync_all()
 
-    prof_name = args.prof_kernel or ("edge1" if args.precision == "bf16" else ("proj2" if args.model in ("l_dgn", "dgn_r") else "proj1"))
-    gemm_name = "proj2" if args.model in ("l_dgn", "dgn_r") else "proj1"
+    two_convs = args.model in ("l_dgn", "dgn_r")
+    # dominant kernel of the step: the conv2 attention pass (bf16, two-conv models), else the conv1 attention
+    prof_name = args.prof_kernel or (("edge2" if two_convs else "edge1") if args.precision == "bf16" else ("proj2" if two_convs else "proj1"))
+    gemm_name = "proj2" if two_convs else "proj1"
     pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
     def timed(fn, steps, with_prof=False):
@@ -238,17 +253,21 @@ def run_ours(args):
         return ms, ro.transitions() - t_before, _lib.lib().mls_launch_count() - l_before, prof_ms, extra
 
     # ---- phase 1: the product path (CUDA-graph replay of the whole round unless --no-graph)
-    prepare(use_graph)
     clocks = ClockSampler(local_rank)
     if rank == 0:
-        clocks.start()
+        clocks.start()                      # before the pre-roll / warm-up rounds: nvidia-smi needs ~0.2 s to report
+    prepare(use_graph)
+    clocks.mark_begin()
     ms, trans, launches, _, _ = timed(ro.round, args.steps)
+    clocks.mark_end()
     clk = clocks.stop() if rank == 0 else None
+    if net is not None and ro.feature_violations() != 0:
+        raise RuntimeError("discrete-feature mode: the environment produced non-integer feature columns")
     launches_per_step = None
     # ---- phase 2: same rounds launched eagerly with an event pair around one launch per step of
-    #      (a) the attention kernel of conv1 -- the kernel with the largest share of the step -- and
-    #      (b) the conv2 projection GEMM (the tensor-core kernel)
-    prof_ms, prof_ms_gemm, eager_ms = [], [], None
+    #      (a) the conv2 attention kernel -- the single kernel with the largest share of the step --,
+    #      (b) the conv2 source-side projection GEMM (the tensor-core kernel) and (c) the conv1 attention stage
+    prof_ms, prof_ms_gemm, prof_ms_conv1, eager_ms = [], [], [], None
     if net is not None:
         prepare(False)
         net.set_profile_events(prof_name, pe0, pe1)
@@ -262,6 +281,10 @@ def run_ours(args):
             _, _, _, prof_ms_gemm, _ = timed(ro.round, args.steps, with_prof=True)
         else:
             prof_ms_gemm = prof_ms
+        if args.precision == "bf16" and prof_name != "edge1":
+            prepare(False)
+            net.set_profile_events("edge1", pe0, pe1)
+            _, _, _, prof_ms_conv1, _ = timed(ro.round, args.steps, with_prof=True)
         net.set_profile_events(None)
     # env kernel alone (HBM roofline of the environment round)
     env_evs = []
@@ -333,18 +356,41 @@ def run_ours(args):
                          "peak_source": f"{peak_src} (sustained bf16)", "kernel_ms": round(gemm_ms, 5), "launch_flops": gemm_flops}
         roofline = roof_gemm
         kern_ms = float(np.mean(prof_ms)) if prof_ms else None
-        if kern_ms and prof_name.startswith("edge"):
-            # attention kernel: reads the projection rows once (nproj*HC bf16), writes relu(conv) (HC bf16),
-            # reads the CSR lists (~(E + 2N) bytes per graph and head) and the per-node scalars
-            esz = 2
-            row_bytes = nproj * HC * esz + (HC * esz if args.model != "hl_dgn" else 0) + (8 * 4 if args.model != "dgn_r" else 0)
-            csr_bytes = 4 * (deg + 2 * (N + 1))
-            edge_bytes = chunk_rows * row_bytes + chunk_graphs * csr_bytes
-            ach = edge_bytes / (kern_ms * 1e-3) / 1e9
-            roofline = {"kernel": f"edge_bf16_kernel ({prof_name}: attention conv over {chunk_graphs} graphs x 4 heads)",
-                        "bound": "hbm", "achieved": round(ach, 1), "peak": hbm_peak, "unit": "GB/s", "frac": round(ach / hbm_peak, 4),
-                        "traffic": traffic.get(prof_name), "peak_source": peak_src, "kernel_ms": round(kern_ms, 5), "launch_bytes": int(edge_bytes),
-                        "note": "largest share of the step; SIMT issue/latency bound (ncu: profiles/), not bandwidth bound"}
+        esz = 2
+        ctrl_rows = A * chunk_graphs                                # controlling nodes (= agent transitions) per launch
+        csr_bytes = chunk_graphs * (deg + 2 * (N + 1))              # neighbour lists + row pointers, once per graph
+
+        def hbm_line(kernel, ms_k, nbytes, key, note):
+            ach = nbytes / (ms_k * 1e-3) / 1e9
+            return {"kernel": kernel, "bound": "hbm", "achieved": round(ach, 1), "peak": hbm_peak, "unit": "GB/s",
+                    "frac": round(ach / hbm_peak, 4), "traffic": traffic.get(key), "peak_source": peak_src,
+                    "kernel_ms": round(ms_k, 5), "launch_bytes": int(nbytes), "note": note}
+
+        def conv1_bytes():
+            # discrete-feature mode: the projections come from an L2-resident table; the kernel reads the keys
+            # (4 B/node) and lists and writes relu(conv) (HC bf16 per node) + the controlling-node snapshot
+            if args.model == "hl_dgn":                              # gather kernel + pooling: reads keys, writes one row per graph
+                return chunk_rows * 4 + csr_bytes + chunk_graphs * HC * esz
+            return chunk_rows * (4 + HC * esz) + csr_bytes + ctrl_rows * HC * esz
+
+        roof_conv1 = None
+        if kern_ms and prof_name == "edge2":
+            # conv2 attention (edge_bf16_kernel, compact targets): reads the source-side projections of every node
+            # ((nproj-1)*HC bf16), the target-side projection of the controlling nodes (HC bf16), the per-node dots,
+            # slots and lists; writes the conv2 snapshot of the controlling nodes (HC bf16)
+            nb = (chunk_rows * ((nproj - 1) * HC * esz + 4 * 4 + 4) + ctrl_rows * (HC * esz + 4 * 4 + 4) + csr_bytes +
+                  ctrl_rows * HC * esz)
+            roofline = hbm_line(f"edge_bf16_kernel (conv2 attention, {chunk_graphs} graphs x 4 heads, {int(ctrl_rows)} targets)", kern_ms, nb,
+                                "edge2", "largest single-kernel share of the step; SIMT issue/latency bound (ncu: profiles/), not bandwidth bound")
+            if prof_ms_conv1:
+                c1_ms = float(np.mean(prof_ms_conv1))
+                name = ("attn_table_mma_kernel + key compaction + pair-logit table (conv1 attention on tcgen05"
+                        if N <= 62 and args.model != "hl_dgn" else "edge_bf16_kernel (conv1 attention, gather from the feature table")
+                roof_conv1 = hbm_line(f"{name}, {chunk_graphs} graphs)", c1_ms, conv1_bytes(), "edge1",
+                                      "event pair spans the whole conv1 attention stage")
+        elif kern_ms and prof_name == "edge1":
+            roofline = hbm_line(f"conv1 attention stage ({chunk_graphs} graphs x 4 heads)", kern_ms, conv1_bytes(), "edge1",
+                                "largest share of the step")
         W = _lib.words_per_row(N)
         env_bytes = B * (N * (4 * W + 4 + 4 + 2 + 2 + 1 + 32 + 8 + 1 + 1) + 8 * 4 + 8 + 1)   # adj+pos(pool, L2) not counted
         env_roof = {"kernel": "env_round_kernel", "bound": "hbm", "traffic": traffic.get("env"), "achieved": round(env_bytes / (env_ms * 1e-3) / 1e9, 1),
@@ -360,6 +406,8 @@ def run_ours(args):
                 "episodes_per_gpu": B, "n_nodes": N, "dynamic_graph": bool(args.dynamic), "graph_pool": len(pool), "eps": args.eps, "precision": args.precision,
                 "preroll_rounds": args.preroll, "l2": "flushed between timed steps (256 MiB memset outside the timed events)",
                 "launch_mode": "cuda-graph replay of the whole round" if use_graph else "eager",
+                "forward_mode": ("discrete-feature tables (MLS_FWD_DISCRETE_FEATURES)" if args.precision == "bf16" else "per-node"),
+                "graphs_per_pass": int(chunk_graphs),
                 "eager_ms_per_step": (eager_ms / steps) if eager_ms else None,
                 "kernel_timing": "event pair around one launch per step in an eager pass over the same rounds",
                 "active_agents_per_graph_round": round(A, 3), "graph_rounds_per_s": world * B * steps / (ms_max / 1e3),
@@ -369,6 +417,7 @@ def run_ours(args):
             "clocks": clk,
             "roofline": roofline if roofline else env_roof,
             "roofline_tensor": roof_gemm,
+            "roofline_conv1": roof_conv1,
             "roofline_env": env_roof,
         }
         if e2e is not None:

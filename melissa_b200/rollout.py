@@ -106,6 +106,11 @@ class Rollout:
             self._dev_in = dict(obs=torch.empty_like(env.obs), active=torch.empty_like(env.active))
         return self._host
 
+    def feature_violations(self) -> int:
+        """Node rows of the last forward whose feature columns were not the small integers the environment writes
+        (always 0 for observations produced by the environment kernel; see MLS_FWD_DISCRETE_FEATURES)."""
+        return int(self.feature_errors.item())
+
     def round_host(self):
         """The same round through host buffers, as a caller holding numpy observations would
         drive it: obs/active H2D -> forward + act -> env round -> obs/reward/active/done/act D2H.
