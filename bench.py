@@ -45,6 +45,7 @@ def parse_args():
     ap.add_argument("--precision", default="bf16", choices=["fp32", "bf16"])
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     ap.add_argument("--preroll", type=int, default=32, help="untimed rounds so episodes are spread over their lifetime")
+    ap.add_argument("--e2e-sub-batches", type=int, default=2, help="episode slices per host round (Rollout.round_host)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-episodes", type=int, default=8, help="episodes per CPU process in the CPU arm")
@@ -233,8 +234,9 @@ def run_ours(args):
     gemm_name = "proj2" if two_convs else "proj1"
     pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
-    def timed(fn, steps, with_prof=False):
-        """K steps, L2 flushed between steps (outside the per-step event pairs)."""
+    def timed(fn, steps, with_prof=False, finish=None):
+        """K steps, L2 flushed between steps (outside the per-step event pairs).  ``finish`` (optional) runs after
+        the last step, inside the timed region: work the steps left in flight on other streams."""
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         t_before = ro.transitions()
         l_before = _lib.lib().mls_launch_count()
@@ -248,8 +250,15 @@ def run_ours(args):
             if with_prof:
                 evs[s][1].synchronize()
                 prof_ms.append(pe0.elapsed_time(pe1))
+        ev_fin = None
+        if finish is not None:
+            finish()
+            ev_fin = torch.cuda.Event(enable_timing=True)
+            ev_fin.record()
         sync_all()
         ms = sum(a.elapsed_time(b) for a, b in evs)
+        if ev_fin is not None:
+            ms += evs[-1][1].elapsed_time(ev_fin)
         return ms, ro.transitions() - t_before, _lib.lib().mls_launch_count() - l_before, prof_ms, extra
 
     # ---- phase 1: the product path (CUDA-graph replay of the whole round unless --no-graph)
@@ -299,12 +308,18 @@ def run_ours(args):
     e2e = None
     if not args.no_e2e:
         prepare(False)
-        ro.round_host()          # allocates the pinned mirrors
+        ro.round_host(args.e2e_sub_batches)          # allocates the pinned mirrors
+        if args.e2e_sub_batches > 1 and use_graph:
+            ro.capture_host(args.e2e_sub_batches)    # one CUDA graph per episode slice
         prepare(False)
         ro._host["obs"].copy_(env.obs)
         ro._host["active"].copy_(env.active)
         torch.cuda.synchronize()
-        e_ms, e_trans, _, _, ex = timed(ro.round_host, args.steps)
+        # rounds are issued back to back: slice i of round k+1 waits only for slice i of round k to be back on the
+        # host (the dependency of a caller feeding observations back); the timed region ends when the last copy lands
+        pipelined = args.e2e_sub_batches > 1
+        e_ms, e_trans, _, _, ex = timed(lambda: ro.round_host(args.e2e_sub_batches, wait=not pipelined), args.steps,
+                                        finish=ro.host_drain if pipelined else None)
         e2e = (e_ms, e_trans, ex[0])
 
     def reduce(v, op):
@@ -422,7 +437,12 @@ def run_ours(args):
         }
         if e2e is not None:
             out["e2e"] = {"value": e_trans_sum / (e_ms_max / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(e2e[2][0]),
-                          "d2h_bytes_per_step": int(e2e[2][1]), "ms_per_step": e_ms_max / steps}
+                          "d2h_bytes_per_step": int(e2e[2][1]), "ms_per_step": e_ms_max / steps,
+                          "pipeline": (f"{args.e2e_sub_batches} episode slices per round: H2D, compute and D2H of different slices overlap "
+                                       "on three streams, slice i of round k+1 waits for slice i of round k to be back on the host "
+                                       "(pinned host buffers; every byte of every round crosses PCIe inside the timed region, "
+                                       "which ends when the last copy has landed)"
+                                       if args.e2e_sub_batches > 1 else "one stream: H2D -> compute -> D2H")}
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

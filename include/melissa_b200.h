@@ -69,7 +69,14 @@ typedef struct MlsEnvDesc {
   int32_t dynamic;    /* dynamic_graph (graph.py:39)                                     */
   int32_t is_testing; /* graph.py:37: scripted agents are policy-stepped too             */
   int32_t heuristic;  /* enum MlsHeuristic                                               */
-  int32_t reserved[3];
+  /* Sub-batch view (mls_env_step only): the state / output pointers address episodes
+   * [episode_offset, episode_offset + n_episodes) of a batch of batch_episodes episodes, so that a caller can
+   * pipeline a round in slices (H2D / compute / D2H overlap) with exactly the results of one full-batch call:
+   * the recycle-pool row and the device movement stream are keyed by the batch-wide episode index.
+   * batch_episodes == 0: not a view (offset 0, batch = n_episodes). */
+  int32_t episode_offset;
+  int32_t batch_episodes;
+  int32_t reserved;
 } MlsEnvDesc;
 
 /* per-node packed state word (node[b][i]) */

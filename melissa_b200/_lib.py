@@ -25,7 +25,8 @@ vp = C.c_void_p
 
 class MlsEnvDesc(C.Structure):
     _fields_ = [("n_episodes", C.c_int32), ("n_nodes", C.c_int32), ("dynamic", C.c_int32), ("is_testing", C.c_int32),
-                ("heuristic", C.c_int32), ("reserved", C.c_int32 * 3)]
+                ("heuristic", C.c_int32), ("episode_offset", C.c_int32), ("batch_episodes", C.c_int32),
+                ("reserved", C.c_int32)]
 
 
 class MlsEnvState(C.Structure):

@@ -172,6 +172,27 @@ class BatchedGraphEnv:
         _lib.check(self.lib.mls_env_step(C.byref(self.desc), C.byref(self._state), C.byref(inp), C.byref(self._out),
                                          C.byref(rec) if rec is not None else None, _lib.current_stream_ptr()))
 
+    def step_device_slice(self, actions_i8: torch.Tensor, b0: int, b1: int):
+        """One round for episodes ``[b0, b1)`` only (``actions_i8`` = the matching int8 rows).  The slices of
+        a round may be stepped one after the other (pipelined with host copies); together they give exactly
+        the full-batch round: recycling and the device movement stream are keyed by the batch-wide index."""
+        key = (int(b0), int(b1))
+        views = self.__dict__.setdefault("_slice_views", {})
+        if key not in views:
+            sl = lambda t: _lib.ptr(t[b0:b1]) if t is not None else None
+            desc = _lib.MlsEnvDesc(b1 - b0, self.N, int(self.dynamic), int(self.is_testing), _lib.HEURISTIC_IDS[self.heuristic],
+                                   b0, self.B, 0)
+            state = _lib.MlsEnvState(sl(self.node), sl(self.recv_count), sl(self.recv_from), sl(self.episode), sl(self.rewards_sum),
+                                     sl(self.adj), sl(self.pos), _lib.ptr(self.pool_adj), _lib.ptr(self.pool_pos), len(self.pool), 0)
+            out = _lib.MlsRoundOutputs(sl(self.obs), sl(self.reward), sl(self.active), sl(self.terminated), sl(self.done),
+                                       sl(self.info_buf), _lib.ptr(self.transitions))
+            views[key] = (desc, state, out)
+        desc, state, out = views[key]
+        inp = _lib.MlsRoundInputs(actions_i8.data_ptr(), None, None, None, self.philox_seed)
+        rec = self.recycle.c_struct() if self.recycle is not None else None
+        _lib.check(self.lib.mls_env_step(C.byref(desc), C.byref(state), C.byref(inp), C.byref(out),
+                                         C.byref(rec) if rec is not None else None, _lib.current_stream_ptr()))
+
     def info(self):
         """``get_info`` counters for every episode (reference graph.py:149-179) as a dict of numpy arrays."""
         buf = torch.zeros(self.B, C.sizeof(_lib.MlsInfo) // 4, dtype=torch.int32, device=self.device)

@@ -293,7 +293,9 @@ __device__ __forceinline__ int world_step(const EnvParams& p, const Smem<W>& sm,
         ox = p.in.move_offsets[(in_row * 2 + 0) * N + i];
         oy = p.in.move_offsets[(in_row * 2 + 1) * N + i];
       } else {
-        Philox4 r = philox4x32_10(p.in.philox_seed, ((uint64_t)(uint32_t)in_row << 32) | (uint32_t)i,
+        // keyed by the batch-wide episode index (sub-batch views draw what the full-batch call draws)
+        const uint32_t rng_row = (uint32_t)in_row + (uint32_t)((p.mode == 0 && p.d.batch_episodes > 0) ? p.d.episode_offset : 0);
+        Philox4 r = philox4x32_10(p.in.philox_seed, ((uint64_t)rng_row << 32) | (uint32_t)i,
                                   ((uint64_t)(uint32_t)ep.n_resets << 32) | (uint32_t)ep.num_moves);
         ox = kMoveStep * (-1.0 + 2.0 * u01_from_u32x2(r.v[0], r.v[1]));
         oy = kMoveStep * (-1.0 + 2.0 * u01_from_u32x2(r.v[2], r.v[3]));
@@ -401,7 +403,8 @@ __global__ void __launch_bounds__(kThreads) env_round_kernel(const EnvParams p) 
   const int b = ep_valid ? ((p.mode == 1 && p.env_ids) ? p.env_ids[k] : k) : 0;
   const bool valid = ep_valid && i < N;
   const size_t row = (size_t)b * N + i;
-  const int B = p.d.n_episodes;
+  const int B = p.d.batch_episodes > 0 ? p.d.batch_episodes : p.d.n_episodes;   // batch-wide count (sub-batch views)
+  const int b_off = p.d.batch_episodes > 0 ? p.d.episode_offset : 0;
 
   Th<W> th;
 #pragma unroll
@@ -594,7 +597,7 @@ __global__ void __launch_bounds__(kThreads) env_round_kernel(const EnvParams p) 
     size_t trow = 0;
     if (do_reset) {
       // World.reset (core.py:388-437) + GraphEnv.reset (graph.py:227-248)
-      trow = (p.mode == 1) ? (size_t)k : (size_t)(((long long)b + (long long)ep.n_resets * B) % p.tup.count);
+      trow = (p.mode == 1) ? (size_t)k : (size_t)(((long long)b + b_off + (long long)ep.n_resets * B) % p.tup.count);
       ep.graph = p.tup.graph_index[trow];
       ep.source = p.tup.source[trow];
       ep.world_msgs = 0; ep.num_moves = 0; ep.rsum = 0.0;

@@ -47,6 +47,7 @@ class Rollout:
         first.count = self.env.B
         first.graph_index, first.source = tuples.graph_index[: self.env.B], tuples.source[: self.env.B]
         first.interested, first.scripted = tuples.interested[: self.env.B], tuples.scripted[: self.env.B]
+        self.env.episode.zero_()            # restart counters too: the recycle pool is walked from its beginning again
         self.env.reset(first)
         self.env.set_recycling(tuples if recycle else None)
         self.round_index = 0
@@ -106,25 +107,124 @@ class Rollout:
             self._dev_in = dict(obs=torch.empty_like(env.obs), active=torch.empty_like(env.active))
         return self._host
 
+    def host_drain(self):
+        """Make the calling stream wait for every outstanding copy of :meth:`round_host` (``wait=False``)."""
+        if getattr(self, "_pipe", None) is not None:
+            torch.cuda.current_stream().wait_stream(self._pipe["d2h"])
+            torch.cuda.current_stream().wait_stream(self._pipe["h2d"])
+
+    def sync_host(self):
+        """Load the pinned host mirrors with the environment's current observations / active sets."""
+        h = self._host_buffers()
+        h["obs"].copy_(self.env.obs)
+        h["active"].copy_(self.env.active)
+        torch.cuda.synchronize()
+
+    def _compute_slice(self, i: int, b0: int, b1: int):
+        """forward + eps-greedy + env round for episodes [b0, b1) of the host-fed observations."""
+        if self.net is not None:
+            self.net.forward_graphs(self._dev_in["obs"][b0:b1], self._dev_in["active"][b0:b1], eps=self.eps,
+                                    philox_seed=self.seed + 7919 * i, philox_offset=0, philox_offset_dev=self.round_dev,
+                                    q_out=self.q[b0:b1], act_out=self.act[b0:b1],
+                                    discrete_features=self.discrete_features, feature_errors=self.feature_errors)
+        self.env.step_device_slice(self.act[b0:b1], b0, b1)
+
+    def capture_host(self, sub_batches: int):
+        """Capture the compute of every episode slice of :meth:`round_host` into its own CUDA graph (the slices
+        are 1/sub_batches of a round: without graphs the ~24 launches per slice cost more host time than the
+        kernels run).  Runs one untimed round; call before :meth:`start`."""
+        self._host_buffers()
+        env = self.env
+        S = max(1, min(int(sub_batches), env.B))
+        bounds = [(env.B * i // S, env.B * (i + 1) // S) for i in range(S)]
+        self._dev_in["obs"].copy_(env.obs)
+        self._dev_in["active"].copy_(env.active)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for i, (b0, b1) in enumerate(bounds):
+                self._compute_slice(i, b0, b1)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graphs = []
+        for i, (b0, b1) in enumerate(bounds):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._compute_slice(i, b0, b1)
+            graphs.append(g)
+        self._host_graphs = (S, graphs)
+        return self
+
     def feature_violations(self) -> int:
         """Node rows of the last forward whose feature columns were not the small integers the environment writes
         (always 0 for observations produced by the environment kernel; see MLS_FWD_DISCRETE_FEATURES)."""
         return int(self.feature_errors.item())
 
-    def round_host(self):
+    def round_host(self, sub_batches: int = 1, wait: bool = True):
         """The same round through host buffers, as a caller holding numpy observations would
         drive it: obs/active H2D -> forward + act -> env round -> obs/reward/active/done/act D2H.
-        Returns (h2d_bytes, d2h_bytes)."""
+        With ``sub_batches`` > 1 the batch is processed in that many slices of episodes: the H2D copy of
+        slice i+1 and the D2H copy of slice i-1 run on their own streams while slice i computes (same
+        results as one full-batch round up to the exploration draws, which are keyed per slice).
+        ``wait=False`` does not make the calling stream wait for the round's last D2H copy: the slices of
+        consecutive rounds then overlap too (slice i of round k+1 only waits for slice i of round k to be back
+        on the host, exactly the dependency a caller feeding observations back has); call :meth:`host_drain`
+        before reading the host buffers.  Returns (h2d_bytes, d2h_bytes)."""
         h = self._host_buffers()
         env = self.env
-        self._dev_in["obs"].copy_(h["obs"], non_blocking=True)
-        self._dev_in["active"].copy_(h["active"], non_blocking=True)
-        self._round_eager(self._dev_in["obs"], self._dev_in["active"])
-        self.round_index += 1
-        h["act"].copy_(self.act, non_blocking=True)
-        h["obs"].copy_(env.obs, non_blocking=True)
-        h["reward"].copy_(env.reward, non_blocking=True)
-        h["active"].copy_(env.active, non_blocking=True)
-        h["done"].copy_(env.done, non_blocking=True)
         nb = lambda t: t.numel() * t.element_size()
-        return nb(h["obs"]) + nb(h["active"]), nb(h["act"]) + nb(h["obs"]) + nb(h["reward"]) + nb(h["active"]) + nb(h["done"])
+        nbytes = (nb(h["obs"]) + nb(h["active"]), nb(h["act"]) + nb(h["obs"]) + nb(h["reward"]) + nb(h["active"]) + nb(h["done"]))
+        S = max(1, min(int(sub_batches), env.B))
+        if S == 1:
+            self._dev_in["obs"].copy_(h["obs"], non_blocking=True)
+            self._dev_in["active"].copy_(h["active"], non_blocking=True)
+            self._round_eager(self._dev_in["obs"], self._dev_in["active"])
+            self.round_index += 1
+            h["act"].copy_(self.act, non_blocking=True)
+            h["obs"].copy_(env.obs, non_blocking=True)
+            h["reward"].copy_(env.reward, non_blocking=True)
+            h["active"].copy_(env.active, non_blocking=True)
+            h["done"].copy_(env.done, non_blocking=True)
+            return nbytes
+        if getattr(self, "_pipe", None) is None or self._pipe["S"] != S:
+            self._pipe = dict(S=S, h2d=torch.cuda.Stream(), d2h=torch.cuda.Stream(),
+                              ev_h=[torch.cuda.Event() for _ in range(S)], ev_c=[torch.cuda.Event() for _ in range(S)],
+                              ev_d=[torch.cuda.Event() for _ in range(S)], rounds=0,
+                              ev_start=torch.cuda.Event(), ev_end=torch.cuda.Event())
+        P = self._pipe
+        cur = torch.cuda.current_stream()
+        bounds = [(env.B * i // S, env.B * (i + 1) // S) for i in range(S)]
+        if P["rounds"] == 0 or wait:
+            P["ev_start"].record(cur)               # the copies of this round start after everything queued before it
+            P["h2d"].wait_event(P["ev_start"])
+            P["d2h"].wait_event(P["ev_start"])
+        with torch.cuda.stream(P["h2d"]):
+            for i, (b0, b1) in enumerate(bounds):
+                if P["rounds"] > 0:
+                    P["h2d"].wait_event(P["ev_d"][i])   # slice i of the previous round is back on the host (and off _dev_in)
+                self._dev_in["obs"][b0:b1].copy_(h["obs"][b0:b1], non_blocking=True)
+                self._dev_in["active"][b0:b1].copy_(h["active"][b0:b1], non_blocking=True)
+                P["ev_h"][i].record(P["h2d"])
+        graphs = self._host_graphs[1] if getattr(self, "_host_graphs", None) and self._host_graphs[0] == S else None
+        for i, (b0, b1) in enumerate(bounds):
+            cur.wait_event(P["ev_h"][i])
+            if graphs is not None:
+                graphs[i].replay()
+            else:
+                self._compute_slice(i, b0, b1)
+            P["ev_c"][i].record(cur)
+            with torch.cuda.stream(P["d2h"]):
+                P["d2h"].wait_event(P["ev_c"][i])
+                h["act"][b0:b1].copy_(self.act[b0:b1], non_blocking=True)
+                h["obs"][b0:b1].copy_(env.obs[b0:b1], non_blocking=True)
+                h["reward"][b0:b1].copy_(env.reward[b0:b1], non_blocking=True)
+                h["active"][b0:b1].copy_(env.active[b0:b1], non_blocking=True)
+                h["done"][b0:b1].copy_(env.done[b0:b1], non_blocking=True)
+                P["ev_d"][i].record(P["d2h"])
+        P["rounds"] += 1
+        if wait:
+            P["ev_end"].record(P["d2h"])
+            cur.wait_event(P["ev_end"])             # the round is over when its last result is on the host
+        self.round_dev.add_(1)
+        self.round_index += 1
+        return nbytes

@@ -123,3 +123,51 @@ def test_evaluation_collect_in_testing_mode():
     assert st.n_collected_episodes >= 40 and (st.lens >= 1).all()
     assert 0.0 < st.info["coverage"].mean <= 1.0
     assert set(np.unique(st.info and np.round(dens, 1))) <= {0.1, 0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.8, 0.9, 1.0}
+
+
+@pytest.mark.parametrize("precision,dynamic", [("bf16", False), ("fp32", True)])
+def test_pipelined_host_round_equals_single_shot_round(precision, dynamic):
+    """Rollout.round_host(sub_batches=4): H2D / compute / D2H of episode slices overlap on three streams.
+    Greedy policy -> deterministic: the host buffers after every round equal those of the single-shot
+    host round (the sliced environment step keys recycling and the device movement stream by the batch-wide
+    episode index, include/melissa_b200.h MlsEnvDesc.episode_offset)."""
+    from melissa_b200.batched_env import BatchedGraphEnv, ResetTuplesDevice
+    from melissa_b200.networks import LDGNNetwork
+    from melissa_b200.rollout import Rollout
+    N, B, P, seed = 20, 50, 160, 5
+    pool = GraphPool.synthetic(N, 8, first_seed=seed)
+    tup = reset_chain.episode_pool(seed, P, N, 8)
+    sd = no.init_state_dict("l_dgn", seed=seed)
+    outs = []
+    for sub in (1, 4, -4, -3):                   # negative: slices replayed from CUDA graphs, rounds issued without waiting
+        net = LDGNNetwork(5, 128, 2, 4, N, dueling_param=DUELING(), device="cuda")
+        net.load_state_dict(sd)
+        net = net.cuda().set_precision(precision)
+        env = BatchedGraphEnv(B, N, pool, dynamic_graph=dynamic)
+        ro = Rollout(env, net, eps=0.0, seed=9)
+        nowait = sub < 0
+        if sub < 0:
+            sub = -sub
+            ro.start(ResetTuplesDevice(*tup[:4], N, "cuda"))
+            ro.capture_host(sub)
+        ro.start(ResetTuplesDevice(*tup[:4], N, "cuda"))
+        ro.sync_host()                           # pinned mirrors <- reset state
+        ro.round_host(sub)
+        trace = []
+        for _ in range(14):                      # several episode lifetimes: restarts from the recycle pool included
+            if nowait:
+                ro.round_host(sub, wait=False)
+                ro.host_drain()
+            else:
+                ro.round_host(sub)
+            torch.cuda.synchronize()
+            trace.append({k: v.clone() for k, v in ro._host.items()})
+        outs.append((trace, ro.transitions()))
+        assert ro.feature_violations() == 0
+    (t1, n1) = outs[0]
+    assert n1 > 0
+    for t4, n4 in outs[1:]:
+        assert n1 == n4
+        for r, (a, b) in enumerate(zip(t1, t4)):
+            for k in a:
+                assert torch.equal(a[k], b[k]), (r, k)
