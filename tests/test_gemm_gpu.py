@@ -62,3 +62,22 @@ def test_fused_epilogue_bias_rowscale_relu_and_device_row_count():
     out = _gemm(A, B, bias=bias, m_dev=m_dev)
     _check(out, A.float() @ B.float().T + bias, rows=333)
     assert torch.isnan(out[384:].float()).all()      # tiles past the device-side row count are never written
+
+
+@pytest.mark.parametrize("rows_a,kt", [(128, 64), (50, 64), (50, 48), (60, 16)])
+def test_umma_mn_major_operand_layout(rows_a, kt):
+    """The MN-major, 128B-swizzled operand image the table-mode attention kernel builds by hand (attn_table.cu:
+    rows of 128 B per K index, 8-row groups 1024 B apart = SBO, the next 64 columns 8 KiB further = LBO, K-step
+    2048 B): one CTA, D[128 x 128] = A[rows_a x 64] (K-major) x B[64 x 128] (MN-major) over the first kt of K."""
+    from melissa_b200 import _lib
+    L = _lib.lib()
+    L.mls_test_umma_mn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint, C.c_uint, C.c_uint, C.c_void_p]
+    L.mls_test_umma_mn.restype = C.c_int
+    torch.manual_seed(rows_a + kt)
+    A = torch.randn(rows_a, 64, device="cuda").to(torch.bfloat16)
+    B = torch.randn(64, 128, device="cuda").to(torch.bfloat16)
+    D = torch.full((128, 128), float("nan"), device="cuda")
+    _lib.check(L.mls_test_umma_mn(A.data_ptr(), B.data_ptr(), D.data_ptr(), rows_a, kt, 8192 >> 4, 1024 >> 4, 2048 >> 4, None))
+    torch.cuda.synchronize()
+    want = A.float()[:, :kt] @ B.float()[:kt]
+    assert float((D[:rows_a] - want).abs().max()) < 1e-3
