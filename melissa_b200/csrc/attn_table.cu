@@ -10,7 +10,7 @@
 //                           Transformer: <q_i, k_j> / sqrt(C)
 //   attn_table_mma_kernel per tile of G graphs (G*N <= 64 node rows), per head:
 //       producers (SIMT)   softmax weights 2^(e_ij - max_i) / (sum_j + 1e-16) from E, written as a bf16 matrix
-//                          W_h[target][source] (K-major, 128B swizzle); value rows x_l[key_j] / v[key_j]
+//                          W_h[target][source] (fp16, K-major, 128B swizzle); value rows x_l[key_j] / v[key_j] (fp16)
 //                          gathered from the table into a [source][channel] operand (MN-major, 128B swizzle)
 //       tcgen05.mma        out_h^T[channel][target] = V_h^T x W_h^T, fp32 accumulators in TMEM (double buffered)
 //                          (bulk copies of pre-swizzled rows); the conv bias rides along as two extra value rows
@@ -21,6 +21,8 @@
 // Reference math: PyG GATv2Conv / TransformerConv as used by l_dgn.py:125,133 and dgn_r.py; softmax
 // exp(e - max) / (sum + 1e-16).  Same results as edge_bf16_kernel up to bf16 rounding of the weights.
 #include "attn_table.cuh"
+
+#include <cuda_fp16.h>
 
 #include "dgn_kernels.cuh"
 #include "tcgen05_ptx.cuh"
@@ -141,6 +143,29 @@ __global__ void row_cid_kernel(const uint32_t* __restrict__ key, const uint16_t*
   if (r < rows) row_cid[r] = cid_of_key[key[r]];
 }
 
+// Value rows (GATv2 x_l, Transformer v) of the keys present in this pass as fp16, indexed by compact id: exact for
+// every bf16 value inside fp16's normal range (saturated beyond +-65504, flushed below 2^-24).
+__global__ void values_fp16_kernel(const AttnTableArgs a) {
+  const int U = *a.n_used;
+  if (U > kAttnUcap) return;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int cid = t >> 6, c = t & 63;                       // 64 chunks of 8 channels per row
+  if (cid >= U) return;
+  const int vcol = a.transformer ? 2 * a.H * kC : 0;
+  const uint4 v = __ldg(reinterpret_cast<const uint4*>(a.t_P + (size_t)a.key_of_cid[cid] * a.ldp + vcol) + c);
+  const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&v);
+  uint4 o;
+  uint32_t* op = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 f = __bfloat1622float2(p[i]);
+    f.x = fminf(fmaxf(f.x, -65504.f), 65504.f); f.y = fminf(fmaxf(f.y, -65504.f), 65504.f);
+    const __half2 h2 = __floats2half2_rn(f.x, f.y);
+    op[i] = *reinterpret_cast<const uint32_t*>(&h2);
+  }
+  reinterpret_cast<uint4*>(a.Vh)[(size_t)cid * 64 + c] = o;
+}
+
 __device__ __forceinline__ void unpack8(const uint4 u, float* f) {
   const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
@@ -220,7 +245,7 @@ constexpr int kStageA = 4 * kAHead;            // 32 KiB
 constexpr int kStageB = 8 * kBPanel;           // 64 KiB
 constexpr int kStage = kStageA + kStageB;      // 96 KiB
 constexpr int kMetaSrc = 64 * kMaxNbr;         // CSR source lists of a tile
-constexpr int kMeta = kMetaSrc + 64 * 4 /*keys*/ + 64 * 2 /*ids*/ + 128 * 2 /*CSR row pointers*/;
+constexpr int kMeta = kMetaSrc + 64 * 4 /*keys*/ + 64 * 2 /*ids*/ + 128 * 2 /*CSR row pointers*/ + 64 * 4 /*dm*/;
 constexpr int kTSmem = 2 * kStage + 2 * kMeta + 256 /*barriers*/ + 1024;
 
 __device__ __forceinline__ float f_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -276,15 +301,15 @@ __global__ void __launch_bounds__(kTThreads, 1) attn_table_mma_kernel(const Attn
 
   for (int u = threadIdx.x; u < 2 * kStage / 16; u += kTThreads) reinterpret_cast<uint4*>(smem)[u] = make_uint4(0, 0, 0, 0);
   __syncthreads();
-  // conv bias as two extra value rows (bf16 hi + lo), multiplied by two columns of ones in the weight matrix
+  // conv bias as two extra value rows (fp16 hi + lo), multiplied by two columns of ones in the weight matrix
   for (int u = threadIdx.x; u < 2 * 512; u += kTThreads) {
     const int s = u >> 9, ch = u & 511;
     const float b = a.bias ? a.bias[ch] : 0.f;
-    const bf16 hi = __float2bfloat16_rn(b), lo = __float2bfloat16_rn(b - __bfloat162float(hi));
+    const __half hi = __float2half_rn(b), lo = __float2half_rn(b - __half2float(hi));
     unsigned char* panel = smem + s * kStage + kStageA + (ch >> 6) * kBPanel;
     const int e = ch & 63;
-    *reinterpret_cast<bf16*>(panel + kb * 128 + ((((e >> 3) ^ kb) & 7) << 4) + (e & 7) * 2) = hi;
-    *reinterpret_cast<bf16*>(panel + (kb + 1) * 128 + ((((e >> 3) ^ (kb + 1)) & 7) << 4) + (e & 7) * 2) = lo;
+    *reinterpret_cast<__half*>(panel + kb * 128 + ((((e >> 3) ^ kb) & 7) << 4) + (e & 7) * 2) = hi;
+    *reinterpret_cast<__half*>(panel + (kb + 1) * 128 + ((((e >> 3) ^ (kb + 1)) & 7) << 4) + (e & 7) * 2) = lo;
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < 2; ++s) {
@@ -304,7 +329,10 @@ __global__ void __launch_bounds__(kTThreads, 1) attn_table_mma_kernel(const Attn
   if (warp == 0) {
     // ===================================================================== MMA issuer
     if (lane == 0) {
-      const uint32_t idesc = make_idesc(128, 64) | (1u << 15);                 // A (values) MN-major, B (weights) K-major
+      // both operands fp16 (format fields of the kind::f16 descriptor: bits 7-9 A, 10-12 B; 0 = F16; mixing F16 with
+      // BF16 is an illegal instruction): the softmax weights live in [0, 1], where fp16 carries 11 significant bits
+      // against bf16's 8, and the bf16 value rows convert to fp16 exactly (values_fp16_kernel).  A (values) MN-major.
+      const uint32_t idesc = (make_idesc(128, 64) & ~((7u << 7) | (7u << 10))) | (1u << 15);
       int it = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
         const int s = it & 1;                                                  // shared-memory stage == TMEM buffer
@@ -342,6 +370,7 @@ __global__ void __launch_bounds__(kTThreads, 1) attn_table_mma_kernel(const Attn
       const uint32_t ldz_u = (uint32_t)a.ldz;
       mbar_wait(tfull_bar(b), (it >> 1) & 1);
       tc_fence_after();
+      float pool = 0.f;                          // relu(conv) * dm >= 0: 0 is the identity of max and add here
 #pragma unroll 1
       for (int q = 0; q < 4; ++q) {
         const int h = pair * 2 + (q >> 1), t0 = (q & 1) * 32;
@@ -349,6 +378,23 @@ __global__ void __launch_bounds__(kTThreads, 1) attn_table_mma_kernel(const Attn
         tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(b * 256 + h * 64 + t0), v);
         if (q == 3) { tc_fence_before(); mbar_arrive(tempty_bar(b)); }
         const int col = h * kC + quarter * 32 + lane;
+        if (a.pool_mode >= 0) {
+          // lane = channel, registers = the graph's nodes (rows of scripted nodes and rows beyond the graph are
+          // all-zero weight rows -> exactly 0): the pooling is a reduction over this lane's registers
+          if (a.pool_mode == MLS_POOL_MAX) {
+#pragma unroll
+            for (int t = 0; t < 32; ++t) pool = fmaxf(pool, __uint_as_float(v[t]));
+          } else {
+#pragma unroll
+            for (int t = 0; t < 32; ++t) pool += fmaxf(__uint_as_float(v[t]), 0.f);
+          }
+          if (q & 1) {
+            if (a.pool_mode == MLS_POOL_MEAN) pool = pool / (float)N;
+            a.z[(size_t)g0 * a.ldz + a.z_col + col] = __float2bfloat16_rn(pool);
+            pool = 0.f;
+          }
+          continue;
+        }
         const int nv = rt - t0;
         uint16_t* xo = reinterpret_cast<uint16_t*>(a.x_out) + (m0 + t0) * HC + col;
         uint16_t* zo = reinterpret_cast<uint16_t*>(a.z) + a.z_col + col;
@@ -384,11 +430,12 @@ __global__ void __launch_bounds__(kTThreads, 1) attn_table_mma_kernel(const Attn
     uint32_t* key_s = reinterpret_cast<uint32_t*>(src_s + kMetaSrc);            // [64]
     uint16_t* cid = reinterpret_cast<uint16_t*>(key_s + 64);                    // [64]
     uint16_t* ptr_s = cid + 64;                                                 // [gt][N+1]
+    float* dm_s = reinterpret_cast<float*>(ptr_s + 128);                        // [64] decision-maker flag (pooling variant)
     // value gather: thread = (16-byte chunk c of the 1 KiB value row, node residue jg); chunk -> panel c >> 3
     const int gc = pt & 63, jg = pt >> 6;                                       // jg 0..2 gather, 3 idles (32 threads)
     const uint32_t gdst = sB32 + (gc >> 3) * kBPanel;
-    const unsigned char* gsrc = reinterpret_cast<const unsigned char*>(a.t_P + (a.transformer ? 2 * HC : 0)) + gc * 16;
-    const size_t row_bytes = (size_t)a.ldp * 2;
+    const unsigned char* gsrc = reinterpret_cast<const unsigned char*>(a.Vh) + gc * 16;   // fp16 value rows of the present keys
+    const size_t row_bytes = (size_t)HC * 2;
     int use = 0;
     for (int tile = blockIdx.x + team * gridDim.x; tile < n_tiles; tile += 2 * gridDim.x, ++use) {
       const int g0 = tile * G, gt = min(G, a.n_graphs - g0), rt = gt * N;
@@ -397,23 +444,28 @@ __global__ void __launch_bounds__(kTThreads, 1) attn_table_mma_kernel(const Attn
       uint32_t pv = 0, kv = 0;
       uint16_t cv = 0;
       uint4 sv = make_uint4(0, 0, 0, 0);
-      if (pt < rt) { cv = __ldg(a.row_cid + m0 + pt); kv = __ldg(a.key + m0 + pt); }
+      float dmv = 1.f;
+      if (pt < rt) {
+        cv = __ldg(a.row_cid + m0 + pt); kv = __ldg(a.key + m0 + pt);
+        if (a.pool_mode >= 0) dmv = __ldg(a.obs + (long long)(g0 + pt / N) * a.obs_stride + (pt % N) * 8 + 7);
+      }
       if (pt < gt * (N + 1)) pv = __ldg(a.csr_ptr + (size_t)g0 * (N + 1) + pt);                     // gt * (N + 1) <= 128
       if (pt < rt * 2) sv = __ldg(reinterpret_cast<const uint4*>(a.csr_src + (size_t)g0 * N * kMaxNbr) + pt);   // N*32 bytes per graph
       mbar_wait_backoff(empty_bar(team), (use & 1) ^ 1);                       // the MMAs that read this stage are done
       for (int u = pt; u < kStageA / 16; u += kTeam) reinterpret_cast<uint4*>(sA)[u] = make_uint4(0, 0, 0, 0);
-      if (pt < rt) { cid[pt] = cv; key_s[pt] = kv; }
+      if (pt < rt) { cid[pt] = cv; key_s[pt] = kv; dm_s[pt] = dmv; }
       if (pt < gt * (N + 1)) ptr_s[pt] = (uint16_t)pv;
       if (pt < rt * 2) reinterpret_cast<uint4*>(src_s)[pt] = sv;
       bar_team(team);
       // ---- phase B: value rows of the tile's nodes, asynchronously (swizzled by the node's row residue) ...
       if (jg < 3) {
         for (int j = jg; j < rt; j += 3)
-          cp_async16(gdst + j * 128 + (((gc ^ j) & 7) << 4), gsrc + (size_t)key_s[j] * row_bytes);
+          cp_async16(gdst + j * 128 + (((gc ^ j) & 7) << 4), gsrc + (size_t)cid[j] * row_bytes);
       }
       // ---- ... and the normalised softmax weights of (target i, head h) as bf16 rows of the head's weight matrix
       for (int tt = pt; tt < rt * 4; tt += kTeam) {
         const int i = tt >> 2, h = tt & 3;
+        if (a.pool_mode >= 0 && dm_s[i] == 0.f) continue;                       // relu(conv) * 0: the row stays all zero
         const int gl = i / N, il = i - gl * N, rbase = gl * N;
         const uint16_t* ptr = ptr_s + gl * (N + 1);
         const int r0 = ptr[il], d = (int)ptr[il + 1] - r0;
@@ -449,15 +501,15 @@ __global__ void __launch_bounds__(kTThreads, 1) attn_table_mma_kernel(const Attn
         if (cnt <= 8) {
 #pragma unroll
           for (int q = 0; q < 8; ++q)
-            if (q < cnt) *reinterpret_cast<bf16*>(arow + a_off(i, jv[q])) = __float2bfloat16_rn(ev[q] * inv);
+            if (q < cnt) *reinterpret_cast<__half*>(arow + a_off(i, jv[q])) = __float2half_rn(ev[q] * inv);
         } else {
           for (int k = 0; k < cnt; ++k) {
             const int j = k >= self ? rbase + src[k - self] : i;
-            *reinterpret_cast<bf16*>(arow + a_off(i, j)) = __float2bfloat16_rn(f_ex2(__ldg(Erow + (int)cid[j] * 4) - mx) * inv);
+            *reinterpret_cast<__half*>(arow + a_off(i, j)) = __float2half_rn(f_ex2(__ldg(Erow + (int)cid[j] * 4) - mx) * inv);
           }
         }
-        *reinterpret_cast<uint16_t*>(arow + a_off(i, kb)) = 0x3F80;          // 1.0: + bias (hi)
-        *reinterpret_cast<uint16_t*>(arow + a_off(i, kb + 1)) = 0x3F80;      // 1.0: + bias (lo)
+        *reinterpret_cast<uint16_t*>(arow + a_off(i, kb)) = 0x3C00;          // 1.0 (fp16): + bias (hi)
+        *reinterpret_cast<uint16_t*>(arow + a_off(i, kb + 1)) = 0x3C00;      // 1.0 (fp16): + bias (lo)
       }
       cp_async_wait_all();
       fence_proxy_async();
@@ -476,7 +528,7 @@ int attn_table_conv_launch(const AttnTableArgs& a, int sm_count, cudaStream_t st
     mls_set_error("table-mode attention: unsupported shape (N=%d, H=%d)", a.N, a.H);
     return MLS_ERR_UNSUPPORTED;
   }
-  if ((long long)a.n_graphs * a.N * a.ldz >= (1ll << 31) || !a.x_out || !a.z) {
+  if (!a.z || (a.pool_mode < 0 && (!a.x_out || (long long)a.n_graphs * a.N * a.ldz >= (1ll << 31))) || (a.pool_mode >= 0 && !a.obs)) {
     mls_set_error("table-mode attention: snapshot matrix too large for 32-bit offsets or missing outputs");
     return MLS_ERR_UNSUPPORTED;
   }
@@ -488,12 +540,13 @@ int attn_table_conv_launch(const AttnTableArgs& a, int sm_count, cudaStream_t st
   compact_keys_kernel<<<1, 1024, 0, st>>>(a.used_bits, a.n_keys, a.cid_of_key, a.key_of_cid, a.n_used);
   const int rows = a.n_graphs * a.N;
   row_cid_kernel<<<(rows + 255) / 256, 256, 0, st>>>(a.key, a.cid_of_key, rows, a.row_cid);
+  values_fp16_kernel<<<kAttnUcap * 64 / 256, 256, 0, st>>>(a);
   pair_logit_kernel<<<sm_count * 2, 256, 0, st>>>(a);
-  const int G = kAttnMaxRows / a.N;
+  const int G = a.pool_mode >= 0 ? 1 : kAttnMaxRows / a.N;     // pooling: one graph per tile
   const int n_tiles = (a.n_graphs + G - 1) / G;
   const int grid = n_tiles < sm_count ? n_tiles : sm_count;
   if (grid > 0) attn_table_mma_kernel<<<grid, kTThreads, kTSmem, st>>>(a, G);
-  mls_count_launch(4);
+  mls_count_launch(5);
   MLS_LAUNCH_CHECK();
   return MLS_OK;
 }

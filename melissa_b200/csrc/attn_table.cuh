@@ -28,6 +28,11 @@ struct AttnTableArgs {
   __nv_bfloat16* x_out;      // [rows][H*C] relu(conv)
   __nv_bfloat16* z;          // snapshot rows
   int ldz, z_col;
+  // HL-DGN: pool_mode >= 0 (enum MlsPool): instead of x_out / snapshots, z[graph][z_col + H*C] = pool over the graph's
+  // nodes of relu(conv) * dm, dm = obs column 7 (one graph per tile)
+  int pool_mode;
+  const float* obs;
+  long long obs_stride;
   // scratch (workspace)
   uint32_t* used_bits;       // [n_keys / 32] bitmap marked by feature_key_kernel, cleared here
   int n_keys;
@@ -35,11 +40,13 @@ struct AttnTableArgs {
   uint32_t* key_of_cid;      // [kAttnUcap]
   uint16_t* row_cid;         // [rows] compact id of every node row
   int* n_used;               // [1] number of distinct keys; > kAttnUcap: the caller's gather kernel runs instead
+  void* Vh;                  // [kAttnUcap][H*C] fp16 value rows of the present keys (by compact id)
   float* E;                  // [kAttnUcap][kAttnUcap][4] base-2 logits of (target key, source key) for the 4 heads
 };
 
 // scratch bytes behind `E`
 inline size_t attn_table_pair_bytes() { return (size_t)kAttnUcap * kAttnUcap * 4 * sizeof(float); }
+inline size_t attn_table_value_bytes() { return (size_t)kAttnUcap * 512 * 2; }
 // true when this (N, H) can take the tensor-core path at all
 inline bool attn_table_supported(int N, int H) { return N >= 1 && N <= kAttnMaxRows && H == 4; }
 

@@ -692,6 +692,7 @@ struct WsB {
   int* n_used;
   uint16_t* row_cid;          // [R]
   float* pairE;               // [kAttnUcap][kAttnUcap][4]
+  void* Vh;                   // [kAttnUcap][512] fp16
 };
 
 size_t carve_b(const MlsNetDesc* d, int Gc, unsigned char* base, WsB* ws) {
@@ -718,9 +719,9 @@ size_t carve_b(const MlsNetDesc* d, int Gc, unsigned char* base, WsB* ws) {
   const size_t KT = (size_t)table_keys(d->n_nodes);
   const size_t o_th = take(KT * hid * 2), o_tx0 = take(KT * hid * 2), o_tP = take(KT * nproj * HC * 2), o_tab = take(KT * 2 * d->heads * 4);
   const size_t o_key = take(R * 4);
-  const bool mma_ok = attn_table_supported(d->n_nodes, d->heads) && !hl;
+  const bool mma_ok = attn_table_supported(d->n_nodes, d->heads);
   const size_t o_used = take(KT), o_cok = take(KT * 2), o_koc = take(kAttnUcap * 4), o_nu = take(4);
-  const size_t o_pe = take(mma_ok ? attn_table_pair_bytes() : 0), o_rcid = take(R * 2);
+  const size_t o_pe = take(mma_ok ? attn_table_pair_bytes() : 0), o_rcid = take(R * 2), o_vh = take(mma_ok ? attn_table_value_bytes() : 0);
   if (ws) {
     auto B = [&](size_t o) { return reinterpret_cast<bf16*>(base + o); };
     auto F = [&](size_t o) { return reinterpret_cast<float*>(base + o); };
@@ -737,7 +738,7 @@ size_t carve_b(const MlsNetDesc* d, int Gc, unsigned char* base, WsB* ws) {
     ws->t_h = B(o_th); ws->t_x0 = B(o_tx0); ws->t_P = B(o_tP); ws->t_ab = F(o_tab); ws->key = reinterpret_cast<uint32_t*>(base + o_key);
     ws->used = reinterpret_cast<uint32_t*>(base + o_used); ws->cid_of_key = reinterpret_cast<uint16_t*>(base + o_cok);
     ws->key_of_cid = reinterpret_cast<uint32_t*>(base + o_koc); ws->n_used = reinterpret_cast<int*>(base + o_nu);
-    ws->pairE = F(o_pe); ws->row_cid = reinterpret_cast<uint16_t*>(base + o_rcid);
+    ws->pairE = F(o_pe); ws->row_cid = reinterpret_cast<uint16_t*>(base + o_rcid); ws->Vh = base + o_vh;
   }
   return off;
 }
@@ -889,7 +890,7 @@ int dgn_forward_bf16(const MlsNetDesc* d, const MlsNetWeights* w, const MlsForwa
     MLS_CUDA(cudaMemsetAsync(ws.used, 0, (size_t)n_keys / 8, st));
   }
   // conv1 attention through the pair-logit table + tensor-core aggregation (L-DGN / DGN-R, graphs of <= 64 nodes)
-  const bool use_mma = use_table && !hl && attn_table_supported(N, H) && mls_get_option("attn_mma");
+  const bool use_mma = use_table && attn_table_supported(N, H) && mls_get_option("attn_mma");
   for (int g0 = 0; g0 < a->n_graphs; g0 += Gc) {
     const int gc = (a->n_graphs - g0) < Gc ? (a->n_graphs - g0) : Gc;
     const int rows = gc * N;
@@ -959,8 +960,10 @@ int dgn_forward_bf16(const MlsNetDesc* d, const MlsNetWeights* w, const MlsForwa
           ta.t_P = ws.t_P; ta.ldp = nproj * HC; ta.t_ab = ws.t_ab; ta.att = w->c1_att; ta.bias = tr ? nullptr : w->c1_bias;
           ta.transformer = tr ? 1 : 0; ta.key = ws.key; ta.N = N; ta.H = H; ta.n_graphs = gc; ta.csr_ptr = ws.csr_ptr;
           ta.csr_src = ws.csr_src; ta.slot = ws.slot; ta.x_out = ws.x1; ta.z = ws.z; ta.ldz = latent; ta.z_col = hid;
+          ta.pool_mode = -1;
+          if (hl) { ta.slot = nullptr; ta.x_out = nullptr; ta.z_col = 0; ta.pool_mode = d->pool; ta.obs = obs; ta.obs_stride = a->obs_stride; }
           ta.used_bits = ws.used; ta.n_keys = n_keys; ta.cid_of_key = ws.cid_of_key; ta.key_of_cid = ws.key_of_cid;
-          ta.n_used = ws.n_used; ta.E = ws.pairE; ta.row_cid = ws.row_cid;
+          ta.n_used = ws.n_used; ta.E = ws.pairE; ta.row_cid = ws.row_cid; ta.Vh = ws.Vh;
           if ((rc = attn_table_conv_launch(ta, sms, st))) return rc;
           ea.run_if_gt = ws.n_used; ea.run_thresh = kAttnUcap;      // more distinct keys than the table holds: gather kernel
         }

@@ -301,19 +301,21 @@ def test_discrete_feature_table_path_is_bit_identical(kind, kw, N, B, gather_att
     assert int(err.item()) == 2
 
 
-@pytest.mark.parametrize("kind", ["l_dgn", "dgn_r"])
+@pytest.mark.parametrize("kind,kw", [("l_dgn", {}), ("dgn_r", {}), ("hl_dgn", {"aggregator": "max"}),
+                                     ("hl_dgn", {"aggregator": "mean"}), ("hl_dgn", {"aggregator": "add"})])
 @pytest.mark.parametrize("N,B", [(50, 300), (20, 64), (12, 9), (62, 33), (7, 1000)])
-def test_tensor_core_table_attention_within_tolerance(kind, N, B):
-    """attn_table.cu (default in discrete-feature mode, graphs of <= 64 nodes): softmax weights from the
-    pair-logit table, aggregation on tcgen05.  Differs from the gather kernel only by bf16 rounding of the
-    softmax weights: within the stated bf16 tolerance of the fp32 oracle, and close to the gather path."""
+def test_tensor_core_table_attention_within_tolerance(kind, kw, N, B):
+    """attn_table.cu (default in discrete-feature mode, graphs of <= 62 nodes): softmax weights from the
+    pair-logit table, aggregation on tcgen05 (HL-DGN: graph pooling in the epilogue).  Differs from the gather
+    kernel only by bf16 rounding of the softmax weights: within the stated bf16 tolerance of the fp32 oracle,
+    and close to the gather path."""
     from melissa_b200 import _lib
     assert _lib.get_option("attn_mma") == 1
     sd = _random_sd(kind, 6)
     om = _obs_matrix(N, B, 78)
     cm = np.random.default_rng(4).random((B, N)) < 0.4
-    want = no.forward_graphs(kind, sd, torch.as_tensor(om), torch.as_tensor(cm), N).numpy()
-    m = _module(kind, N, sd).set_precision("bf16")
+    want = no.forward_graphs(kind, sd, torch.as_tensor(om), torch.as_tensor(cm), N, **kw).numpy()
+    m = _module(kind, N, sd, **kw).set_precision("bf16")
     args = (torch.as_tensor(om, device="cuda"), torch.as_tensor(cm, device="cuda").to(torch.uint8))
     q0, _ = m.forward_graphs(*args)
     err = torch.zeros(1, dtype=torch.int32, device="cuda")
