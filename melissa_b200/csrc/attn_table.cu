@@ -431,36 +431,39 @@ __global__ void __launch_bounds__(kTThreads, 1) attn_table_mma_kernel(const Attn
     uint16_t* cid = reinterpret_cast<uint16_t*>(key_s + 64);                    // [64]
     uint16_t* ptr_s = cid + 64;                                                 // [gt][N+1]
     float* dm_s = reinterpret_cast<float*>(ptr_s + 128);                        // [64] decision-maker flag (pooling variant)
-    // value gather: thread = (16-byte chunk c of the 1 KiB value row, node residue jg); chunk -> panel c >> 3
-    const int gc = pt & 63, jg = pt >> 6;                                       // jg 0..2 gather, 3 idles (32 threads)
-    const uint32_t gdst = sB32 + (gc >> 3) * kBPanel;
-    const unsigned char* gsrc = reinterpret_cast<const unsigned char*>(a.Vh) + gc * 16;   // fp16 value rows of the present keys
-    const size_t row_bytes = (size_t)HC * 2;
+    // value gather: 4 lanes per node, lane part p copies the 16-byte chunks 4i + p (i = 0..15) of the node's 1 KiB
+    // fp16 row: a warp instruction reads 64 contiguous bytes of each of 8 rows; chunk c lands in panel c >> 3 at
+    // 16-byte slot (c & 7) ^ (row & 7) -- all offsets but two per-thread registers are immediates
+    const int gp = pt & 3;
+    const unsigned char* gsrc = reinterpret_cast<const unsigned char*>(a.Vh) + gp * 16;   // fp16 value rows of the present keys
     int use = 0;
     for (int tile = blockIdx.x + team * gridDim.x; tile < n_tiles; tile += 2 * gridDim.x, ++use) {
       const int g0 = tile * G, gt = min(G, a.n_graphs - g0), rt = gt * N;
       const size_t m0 = (size_t)g0 * N;
       // ---- phase A: tile metadata (global loads first) and the cleared weight matrices
-      uint32_t pv = 0, kv = 0;
+      uint32_t pv = 0;
       uint16_t cv = 0;
       uint4 sv = make_uint4(0, 0, 0, 0);
       float dmv = 1.f;
       if (pt < rt) {
-        cv = __ldg(a.row_cid + m0 + pt); kv = __ldg(a.key + m0 + pt);
+        cv = __ldg(a.row_cid + m0 + pt);
         if (a.pool_mode >= 0) dmv = __ldg(a.obs + (long long)(g0 + pt / N) * a.obs_stride + (pt % N) * 8 + 7);
       }
       if (pt < gt * (N + 1)) pv = __ldg(a.csr_ptr + (size_t)g0 * (N + 1) + pt);                     // gt * (N + 1) <= 128
       if (pt < rt * 2) sv = __ldg(reinterpret_cast<const uint4*>(a.csr_src + (size_t)g0 * N * kMaxNbr) + pt);   // N*32 bytes per graph
       mbar_wait_backoff(empty_bar(team), (use & 1) ^ 1);                       // the MMAs that read this stage are done
       for (int u = pt; u < kStageA / 16; u += kTeam) reinterpret_cast<uint4*>(sA)[u] = make_uint4(0, 0, 0, 0);
-      if (pt < rt) { cid[pt] = cv; key_s[pt] = kv; dm_s[pt] = dmv; }
+      if (pt < rt) { cid[pt] = cv; dm_s[pt] = dmv; }
       if (pt < gt * (N + 1)) ptr_s[pt] = (uint16_t)pv;
       if (pt < rt * 2) reinterpret_cast<uint4*>(src_s)[pt] = sv;
       bar_team(team);
       // ---- phase B: value rows of the tile's nodes, asynchronously (swizzled by the node's row residue) ...
-      if (jg < 3) {
-        for (int j = jg; j < rt; j += 3)
-          cp_async16(gdst + j * 128 + (((gc ^ j) & 7) << 4), gsrc + (size_t)cid[j] * row_bytes);
+      for (int j = pt >> 2; j < rt; j += kTeam / 4) {
+        const unsigned char* src = gsrc + (size_t)cid[j] * (HC * 2);
+        const uint32_t row = sB32 + j * 128;
+        const uint32_t d0 = row + ((gp ^ (j & 7)) << 4), d1 = row + (((gp + 4) ^ (j & 7)) << 4);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) cp_async16(((i & 1) ? d1 : d0) + (i >> 1) * kBPanel, src + i * 64);
       }
       // ---- ... and the normalised softmax weights of (target i, head h) as bf16 rows of the head's weight matrix
       for (int tt = pt; tt < rt * 4; tt += kTeam) {
