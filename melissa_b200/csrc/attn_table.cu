@@ -257,7 +257,7 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 // mbarrier wait for warps that are far ahead of the pipeline: sleep between polls so that the issue slots
 // go to the warps doing the work
-__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity, unsigned ns = 200) {
   for (;;) {
     uint32_t ok;
     asm volatile(
@@ -266,7 +266,7 @@ __device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity)
         : "r"(bar), "r"(parity)
         : "memory");
     if (ok) return;
-    __nanosleep(200);
+    __nanosleep(ns);
   }
 }
 __device__ __forceinline__ uint16_t relu_bf16(float x) {
@@ -337,8 +337,8 @@ __global__ void __launch_bounds__(kTThreads, 1) attn_table_mma_kernel(const Attn
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
         const int s = it & 1;                                                  // shared-memory stage == TMEM buffer
         const uint32_t sA = smem_u32(smem + s * kStage), sB = sA + kStageA;
-        mbar_wait(full_bar(s), (it >> 1) & 1);
-        mbar_wait(tempty_bar(s), ((it >> 1) & 1) ^ 1);
+        mbar_wait_backoff(full_bar(s), (it >> 1) & 1, 32);
+        mbar_wait_backoff(tempty_bar(s), ((it >> 1) & 1) ^ 1, 32);
         tc_fence_after();
         for (int h = 0; h < 4; ++h) {
           const uint64_t dv = make_smem_desc_ex(sB + h * 2 * kBPanel, kBPanel >> 4, 1024 >> 4);
@@ -368,7 +368,7 @@ __global__ void __launch_bounds__(kTThreads, 1) attn_table_mma_kernel(const Attn
       if (zm0) zfirst = __shfl_sync(0xffffffffu, sl0, __ffs(zm0) - 1);
       else if (zm1) zfirst = __shfl_sync(0xffffffffu, sl1, __ffs(zm1) - 1);
       const uint32_t ldz_u = (uint32_t)a.ldz;
-      mbar_wait(tfull_bar(b), (it >> 1) & 1);
+      mbar_wait_backoff(tfull_bar(b), (it >> 1) & 1, 64);
       tc_fence_after();
       float pool = 0.f;                          // relu(conv) * dm >= 0: 0 is the identity of max and add here
 #pragma unroll 1
