@@ -253,10 +253,13 @@ struct EdgeArgs {
   int run_thresh;         // (fallback behind the tensor-core table kernel, attn_table.cu)
 };
 
-// CTA size: 128 threads, 4 CTAs per SM (register bound), so that the staging of one CTA overlaps the compute of the
+// CTA size: 128 threads, 5-6 CTAs per SM (register bound), so that the staging of one CTA overlaps the compute of the
 // others.  The operands are staged as bf16 (2-3 x 12.8 KB for 50-node graphs), shared memory is no longer the limit.
-template <bool TRANSFORMER> struct EdgeCfg { static constexpr int kThreads = 128; };
-constexpr int kLD = kC;                 // staged row pitch in floats (a warp reads 4 x 128 B row segments = the 4-wavefront minimum)
+template <bool TRANSFORMER> struct EdgeCfg {
+  static constexpr int kThreads = 128;
+  static constexpr int kMinCtas = TRANSFORMER ? 6 : 5;      // measured: 5 CTAs (96 registers) beat 4 by 9 % for GATv2, 6 spill
+};
+
 
 __device__ __forceinline__ void edge_cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
@@ -270,6 +273,10 @@ __device__ __forceinline__ void bf16x8_to_f32(const uint4 u, float4& lo, float4&
 // Channel slices of a lane: sub = lane & 7 owns channels [8 sub, 8 sub + 8) and [64 + 8 sub, 64 + 8 sub + 8) of the head, as
 // four float4 "it" = 0..3 (two 16-byte chunks of the bf16 row: 8 lanes read 128 contiguous bytes).
 __device__ __forceinline__ int edge_chan(int it, int sub) { return (it >> 1) * 64 + sub * 8 + (it & 1) * 4; }
+__device__ __forceinline__ uint32_t pack_bf16x2_rn(float lo, float hi) {
+  const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
 __device__ __forceinline__ float fast_ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -282,18 +289,18 @@ __device__ __forceinline__ float fast_rcp(float x) {
 }
 
 // One CTA per (graph, head).
-//   phase 0  stage the head's operands in shared memory as fp32 (converted once, not per edge) together
-//            with the graph's CSR lists and the per-node scalars
-//   phase 1  one warp per target, FOUR neighbours per round, EIGHT lanes per neighbour (16 channels
-//            each): the target row lives in registers, every neighbour row is read from shared
-//            memory exactly once and serves both its logit and its contribution to the output
-//            (single-pass softmax in base 2: running max / denominator, same value as PyG's
-//            exp(e - max) / (sum + 1e-16) up to rounding); the four lane groups are combined with a
-//            reduce-scatter (12 shuffles) so that lane l ends up owning channels 4l..4l+3.
+//   phase 0  stage the head's operands in shared memory as raw bf16 rows with cp.async, together with the graph's
+//            CSR block and the per-node scalars
+//   phase 1  one warp per target, FOUR neighbours per round (two lane groups x two independent chains), SIXTEEN
+//            lanes per neighbour (8 channels each); the target's 8 channels stay in registers, every neighbour
+//            row is read from shared memory exactly once and serves both its logit and its contribution to the
+//            output (single-pass softmax in base 2: running max / denominator, same value as PyG's
+//            exp(e - max) / (sum + 1e-16) up to rounding); the two lane groups are combined with 9 shuffles and
+//            group 0 writes 256 contiguous bytes per target.
 //              GATv2:       e_ij = 0.6 (a_j + b_i) + 0.4 sum_c att_c |x_l[j,c] + x_r[i,c]|   (leaky_relu(s,.2) = .6 s + .4 |s|)
 //              Transformer: e_ij = <q_i, k_j> / sqrt(C)
 template <bool TRANSFORMER>
-__global__ void __launch_bounds__(EdgeCfg<TRANSFORMER>::kThreads, 512 / EdgeCfg<TRANSFORMER>::kThreads) edge_bf16_kernel(const EdgeArgs a) {
+__global__ void __launch_bounds__(EdgeCfg<TRANSFORMER>::kThreads, EdgeCfg<TRANSFORMER>::kMinCtas) edge_bf16_kernel(const EdgeArgs a) {
   constexpr int kEdgeThreads = EdgeCfg<TRANSFORMER>::kThreads, kEdgeWarps = kEdgeThreads / 32;
   extern __shared__ __align__(16) unsigned char esm[];
   const int N = a.N, H = a.H, HC = H * kC;
@@ -367,19 +374,13 @@ __global__ void __launch_bounds__(EdgeCfg<TRANSFORMER>::kThreads, 512 / EdgeCfg<
       }
     }
   }
-  const int grp = lane >> 3, sub = lane & 7;                // neighbour slot of the round / channel slice
-  const int och = edge_chan(grp, sub);                      // channels this lane owns after the reduce-scatter
-  float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (!TRANSFORMER) bias4 = *reinterpret_cast<const float4*>(a.bias + h * kC + och);
-  float4 attn[4];
+  const int grp = lane >> 4, sub = lane & 15;               // neighbour slot of the round / 8-channel slice of the head
+  const int och = sub * 8;
+  float bias8[8], attn[8];
 #pragma unroll
-  for (int it = 0; it < 4; ++it) {
-    attn[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (!TRANSFORMER) {
-      const float4 v = *reinterpret_cast<const float4*>(a.att + h * kC + edge_chan(it, sub));
-      const float sc = 0.4f * kLog2e;
-      attn[it] = make_float4(v.x * sc, v.y * sc, v.z * sc, v.w * sc);
-    }
+  for (int c = 0; c < 8; ++c) {
+    bias8[c] = TRANSFORMER ? 0.f : a.bias[h * kC + och + c];
+    attn[c] = TRANSFORMER ? 0.f : a.att[h * kC + och + c] * (0.4f * kLog2e);
   }
   edge_cp_async_wait();
   __syncthreads();
@@ -387,8 +388,9 @@ __global__ void __launch_bounds__(EdgeCfg<TRANSFORMER>::kThreads, 512 / EdgeCfg<
   const float tr_scale = kLog2e / sqrtf((float)kC);
   const bf16* stV = TRANSFORMER ? stB : stA;
   const int self = TRANSFORMER ? 0 : 1;                     // GATv2: slot 0 of every target is its self loop
-  float4 pool = a.pool_mode == MLS_POOL_MAX ? make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY)
-                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+  float pool[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) pool[c] = a.pool_mode == MLS_POOL_MAX ? -INFINITY : 0.f;
   const int n_targets = a.Pt ? a.gcnt[g] : N;               // compact mode: only the controlling nodes, split evenly over the warps
   for (int tk = warp; tk < n_targets; tk += kEdgeWarps) {
     const int i = a.Pt ? reinterpret_cast<const int*>(s_dm)[tk] : tk;
@@ -397,107 +399,101 @@ __global__ void __launch_bounds__(EdgeCfg<TRANSFORMER>::kThreads, 512 / EdgeCfg<
     const int r0 = s_ptr[i];
     const int d = (int)s_ptr[i + 1] - r0 + self;            // warp uniform, <= 33
     const int ti = a.Pt ? tk : i;                           // row of the target side in stT / s_b
-    const uint4* trow = reinterpret_cast<const uint4*>(stT + ti * kC);   // target row, re-read per round (multicast, 1 wavefront) to save 16 registers
+    float tg[8];                                            // the target's 8 channels stay in registers
+    {
+      float4 lo4, hi4;
+      bf16x8_to_f32(reinterpret_cast<const uint4*>(stT + ti * kC)[sub], lo4, hi4);
+      tg[0] = lo4.x; tg[1] = lo4.y; tg[2] = lo4.z; tg[3] = lo4.w; tg[4] = hi4.x; tg[5] = hi4.y; tg[6] = hi4.z; tg[7] = hi4.w;
+    }
     const float b_i = TRANSFORMER ? 0.f : s_b[ti];
     float mx = -INFINITY, den = 0.f;
-    float4 acc[4];
+    float acc[8];
 #pragma unroll
-    for (int it = 0; it < 4; ++it) acc[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int kb = 0; kb < d; kb += 8) {                     // up to 8 neighbours per pass: two independent chains
-      const int k0 = kb + grp, k1 = kb + 4 + grp;
+    for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+    for (int kb = 0; kb < d; kb += 4) {                     // 4 neighbours per pass: two lane groups x two independent chains
+      const int k0 = kb + grp, k1 = kb + 2 + grp;
       const bool v0 = k0 < d, v1 = k1 < d;
       int j0 = i, j1 = i;
       if (v0 && k0 >= self) j0 = s_src[r0 + k0 - self];
-      if (v1) j1 = s_src[r0 + k1 - self];                   // k1 >= 4 > self
-      const uint4* xr0 = reinterpret_cast<const uint4*>(stA + j0 * kC);
-      const uint4* xr1 = reinterpret_cast<const uint4*>(stA + j1 * kC);
-      float4 x0[4], x1[4];
-      bf16x8_to_f32(xr0[sub], x0[0], x0[1]); bf16x8_to_f32(xr0[sub + 8], x0[2], x0[3]);
-      bf16x8_to_f32(xr1[sub], x1[0], x1[1]); bf16x8_to_f32(xr1[sub + 8], x1[2], x1[3]);
+      if (v1) j1 = s_src[r0 + k1 - self];                   // k1 >= 2 > self
+      float x0[8], x1[8];
+      {
+        float4 l0, h0, l1, h1;
+        bf16x8_to_f32(reinterpret_cast<const uint4*>(stA + j0 * kC)[sub], l0, h0);
+        bf16x8_to_f32(reinterpret_cast<const uint4*>(stA + j1 * kC)[sub], l1, h1);
+        x0[0] = l0.x; x0[1] = l0.y; x0[2] = l0.z; x0[3] = l0.w; x0[4] = h0.x; x0[5] = h0.y; x0[6] = h0.z; x0[7] = h0.w;
+        x1[0] = l1.x; x1[1] = l1.y; x1[2] = l1.z; x1[3] = l1.w; x1[4] = h1.x; x1[5] = h1.y; x1[6] = h1.z; x1[7] = h1.w;
+      }
       float pa0 = 0.f, pb0 = 0.f, pa1 = 0.f, pb1 = 0.f;     // two partial sums per chain: shorter FFMA dependency
-      float4 tg[4];
-      bf16x8_to_f32(trow[sub], tg[0], tg[1]); bf16x8_to_f32(trow[sub + 8], tg[2], tg[3]);
 #pragma unroll
-      for (int it = 0; it < 4; ++it) {
-        const float4 t4 = tg[it];
+      for (int c = 0; c < 8; c += 2) {
         if (TRANSFORMER) {
-          pa0 = fmaf(x0[it].x, t4.x, pa0); pb0 = fmaf(x0[it].y, t4.y, pb0); pa0 = fmaf(x0[it].z, t4.z, pa0); pb0 = fmaf(x0[it].w, t4.w, pb0);
-          pa1 = fmaf(x1[it].x, t4.x, pa1); pb1 = fmaf(x1[it].y, t4.y, pb1); pa1 = fmaf(x1[it].z, t4.z, pa1); pb1 = fmaf(x1[it].w, t4.w, pb1);
+          pa0 = fmaf(x0[c], tg[c], pa0); pb0 = fmaf(x0[c + 1], tg[c + 1], pb0);
+          pa1 = fmaf(x1[c], tg[c], pa1); pb1 = fmaf(x1[c + 1], tg[c + 1], pb1);
         } else {
-          pa0 = fmaf(attn[it].x, fabsf(x0[it].x + t4.x), pa0); pb0 = fmaf(attn[it].y, fabsf(x0[it].y + t4.y), pb0);
-          pa0 = fmaf(attn[it].z, fabsf(x0[it].z + t4.z), pa0); pb0 = fmaf(attn[it].w, fabsf(x0[it].w + t4.w), pb0);
-          pa1 = fmaf(attn[it].x, fabsf(x1[it].x + t4.x), pa1); pb1 = fmaf(attn[it].y, fabsf(x1[it].y + t4.y), pb1);
-          pa1 = fmaf(attn[it].z, fabsf(x1[it].z + t4.z), pa1); pb1 = fmaf(attn[it].w, fabsf(x1[it].w + t4.w), pb1);
+          pa0 = fmaf(attn[c], fabsf(x0[c] + tg[c]), pa0); pb0 = fmaf(attn[c + 1], fabsf(x0[c + 1] + tg[c + 1]), pb0);
+          pa1 = fmaf(attn[c], fabsf(x1[c] + tg[c]), pa1); pb1 = fmaf(attn[c + 1], fabsf(x1[c + 1] + tg[c + 1]), pb1);
         }
       }
       float e0 = pa0 + pb0, e1 = pa1 + pb1;
-      e0 += __shfl_xor_sync(0xffffffffu, e0, 1); e1 += __shfl_xor_sync(0xffffffffu, e1, 1);
-      e0 += __shfl_xor_sync(0xffffffffu, e0, 2); e1 += __shfl_xor_sync(0xffffffffu, e1, 2);
-      e0 += __shfl_xor_sync(0xffffffffu, e0, 4); e1 += __shfl_xor_sync(0xffffffffu, e1, 4);
+#pragma unroll
+      for (int o = 1; o < 16; o <<= 1) {
+        e0 += __shfl_xor_sync(0xffffffffu, e0, o);
+        e1 += __shfl_xor_sync(0xffffffffu, e1, o);
+      }
       e0 = TRANSFORMER ? e0 * tr_scale : e0 + (s_a[j0] + b_i);
       e1 = TRANSFORMER ? e1 * tr_scale : e1 + (s_a[j1] + b_i);
       if (!v0) e0 = -INFINITY;
       if (!v1) e1 = -INFINITY;
       float m_r = fmaxf(e0, e1);
-      m_r = fmaxf(m_r, __shfl_xor_sync(0xffffffffu, m_r, 8));
       m_r = fmaxf(m_r, __shfl_xor_sync(0xffffffffu, m_r, 16));
-      if (kb > 0 && m_r > mx) {                             // only targets with more than 8 entries get here (warp uniform)
+      if (kb > 0 && m_r > mx) {                             // only targets with more than 4 entries get here (warp uniform)
         const float resc = fast_ex2(mx - m_r);
         den *= resc;
 #pragma unroll
-        for (int it = 0; it < 4; ++it) { acc[it].x *= resc; acc[it].y *= resc; acc[it].z *= resc; acc[it].w *= resc; }
+        for (int c = 0; c < 8; ++c) acc[c] *= resc;
       }
       mx = fmaxf(mx, m_r);
       const float p0 = fast_ex2(e0 - mx), p1 = fast_ex2(e1 - mx);   // 0 for padded slots
       den += p0 + p1;                                       // per-group partial
       if (TRANSFORMER) {
-        const uint4* vr0 = reinterpret_cast<const uint4*>(stV + j0 * kC);
-        const uint4* vr1 = reinterpret_cast<const uint4*>(stV + j1 * kC);
-        bf16x8_to_f32(vr0[sub], x0[0], x0[1]); bf16x8_to_f32(vr0[sub + 8], x0[2], x0[3]);
-        bf16x8_to_f32(vr1[sub], x1[0], x1[1]); bf16x8_to_f32(vr1[sub + 8], x1[2], x1[3]);
+        float4 l0, h0, l1, h1;
+        bf16x8_to_f32(reinterpret_cast<const uint4*>(stV + j0 * kC)[sub], l0, h0);
+        bf16x8_to_f32(reinterpret_cast<const uint4*>(stV + j1 * kC)[sub], l1, h1);
+        x0[0] = l0.x; x0[1] = l0.y; x0[2] = l0.z; x0[3] = l0.w; x0[4] = h0.x; x0[5] = h0.y; x0[6] = h0.z; x0[7] = h0.w;
+        x1[0] = l1.x; x1[1] = l1.y; x1[2] = l1.z; x1[3] = l1.w; x1[4] = h1.x; x1[5] = h1.y; x1[6] = h1.z; x1[7] = h1.w;
       }
 #pragma unroll
-      for (int it = 0; it < 4; ++it) {
-        acc[it].x = fmaf(p1, x1[it].x, fmaf(p0, x0[it].x, acc[it].x)); acc[it].y = fmaf(p1, x1[it].y, fmaf(p0, x0[it].y, acc[it].y));
-        acc[it].z = fmaf(p1, x1[it].z, fmaf(p0, x0[it].z, acc[it].z)); acc[it].w = fmaf(p1, x1[it].w, fmaf(p0, x0[it].w, acc[it].w));
-      }
+      for (int c = 0; c < 8; ++c) acc[c] = fmaf(p1, x1[c], fmaf(p0, x0[c], acc[c]));
     }
-    // combine the four lane groups: reduce-scatter so that group g keeps float4 slice it == g,
-    // i.e. lane l = 8g + sub owns channels 4l .. 4l+3
-    den += __shfl_xor_sync(0xffffffffu, den, 8);
+    // combine the two lane groups (both end up with the full sums; group 0 writes)
     den += __shfl_xor_sync(0xffffffffu, den, 16);
-    float4 lo, hi;                                          // step 1 (xor 16): keep slices {0,1} or {2,3}
-    {
-      const bool up = grp >= 2;
-      const float4 k0 = up ? acc[2] : acc[0], k1 = up ? acc[3] : acc[1];
-      const float4 s0 = up ? acc[0] : acc[2], s1 = up ? acc[1] : acc[3];
-      lo.x = k0.x + __shfl_xor_sync(0xffffffffu, s0.x, 16); lo.y = k0.y + __shfl_xor_sync(0xffffffffu, s0.y, 16);
-      lo.z = k0.z + __shfl_xor_sync(0xffffffffu, s0.z, 16); lo.w = k0.w + __shfl_xor_sync(0xffffffffu, s0.w, 16);
-      hi.x = k1.x + __shfl_xor_sync(0xffffffffu, s1.x, 16); hi.y = k1.y + __shfl_xor_sync(0xffffffffu, s1.y, 16);
-      hi.z = k1.z + __shfl_xor_sync(0xffffffffu, s1.z, 16); hi.w = k1.w + __shfl_xor_sync(0xffffffffu, s1.w, 16);
-    }
-    float4 mine;                                            // step 2 (xor 8): keep the slice of this group
-    {
-      const bool odd = grp & 1;
-      const float4 kp = odd ? hi : lo, sd = odd ? lo : hi;
-      mine.x = kp.x + __shfl_xor_sync(0xffffffffu, sd.x, 8); mine.y = kp.y + __shfl_xor_sync(0xffffffffu, sd.y, 8);
-      mine.z = kp.z + __shfl_xor_sync(0xffffffffu, sd.z, 8); mine.w = kp.w + __shfl_xor_sync(0xffffffffu, sd.w, 8);
-    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], 16);
     const float inv_den = fast_rcp(den + 1e-16f);           // isolated Transformer node: acc = 0 -> output 0
-    float4 o;
-    o.x = fmaxf(fmaf(mine.x, inv_den, bias4.x), 0.f); o.y = fmaxf(fmaf(mine.y, inv_den, bias4.y), 0.f);
-    o.z = fmaxf(fmaf(mine.z, inv_den, bias4.z), 0.f); o.w = fmaxf(fmaf(mine.w, inv_den, bias4.w), 0.f);
-    if (a.x_out) st_bf16x4(a.x_out + (base + i) * HC + h * kC + och, o);
-    if (a.z && sl >= 0 && a.pool_mode < 0) st_bf16x4(a.z + (size_t)sl * a.ldz + a.z_col + h * kC + och, o);
+    float o[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) o[c] = fmaxf(fmaf(acc[c], inv_den, bias8[c]), 0.f);
+    if (grp == 0) {
+      uint4 ov;
+      ov.x = pack_bf16x2_rn(o[0], o[1]); ov.y = pack_bf16x2_rn(o[2], o[3]); ov.z = pack_bf16x2_rn(o[4], o[5]); ov.w = pack_bf16x2_rn(o[6], o[7]);
+      if (a.x_out) *reinterpret_cast<uint4*>(a.x_out + (base + i) * HC + h * kC + och) = ov;      // 16 lanes: 256 contiguous bytes
+      if (a.z && sl >= 0 && a.pool_mode < 0) *reinterpret_cast<uint4*>(a.z + (size_t)sl * a.ldz + a.z_col + h * kC + och) = ov;
+    }
     if (a.pool_mode >= 0) {
       const float dm = s_dm[i];
-      const float4 v = make_float4(o.x * dm, o.y * dm, o.z * dm, o.w * dm);
-      if (a.pool_mode == MLS_POOL_MAX) { pool.x = fmaxf(pool.x, v.x); pool.y = fmaxf(pool.y, v.y); pool.z = fmaxf(pool.z, v.z); pool.w = fmaxf(pool.w, v.w); }
-      else { pool.x += v.x; pool.y += v.y; pool.z += v.z; pool.w += v.w; }
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const float v = o[c] * dm;
+        pool[c] = a.pool_mode == MLS_POOL_MAX ? fmaxf(pool[c], v) : pool[c] + v;
+      }
     }
   }
   if (a.pool_mode >= 0) {      // HL-DGN: z[g] = pool_i(relu(conv)[i] * dm[i])  (hl_dgn.py:103-108)
-    *reinterpret_cast<float4*>(poolbuf + warp * kC + och) = pool;
+    if (grp == 0) {
+      *reinterpret_cast<float4*>(poolbuf + warp * kC + och) = make_float4(pool[0], pool[1], pool[2], pool[3]);
+      *reinterpret_cast<float4*>(poolbuf + warp * kC + och + 4) = make_float4(pool[4], pool[5], pool[6], pool[7]);
+    }
     __syncthreads();
     if (tid < kC) {
       const int used = N < kEdgeWarps ? N : kEdgeWarps;        // warps that own at least one node
