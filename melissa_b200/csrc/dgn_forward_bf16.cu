@@ -19,20 +19,6 @@ namespace mls {
 
 typedef __nv_bfloat16 bf16;
 
-__device__ __forceinline__ float4 ld_bf16x4(const bf16* p) {
-  const uint2 u = *reinterpret_cast<const uint2*>(p);
-  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
-  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
-  return make_float4(a.x, a.y, b.x, b.y);
-}
-__device__ __forceinline__ void st_bf16x4(bf16* p, float4 v) {
-  __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
-  uint2 u;
-  u.x = *reinterpret_cast<uint32_t*>(&a);
-  u.y = *reinterpret_cast<uint32_t*>(&b);
-  *reinterpret_cast<uint2*>(p) = u;
-}
-
 // ------------------------------------------------------------------------------ weight preparation
 struct CvtJob {
   const float* src;   // [rows, cols] fp32 row major
@@ -270,9 +256,6 @@ __device__ __forceinline__ void bf16x8_to_f32(const uint4 u, float4& lo, float4&
   lo = make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u), __uint_as_float(u.y << 16), __uint_as_float(u.y & 0xffff0000u));
   hi = make_float4(__uint_as_float(u.z << 16), __uint_as_float(u.z & 0xffff0000u), __uint_as_float(u.w << 16), __uint_as_float(u.w & 0xffff0000u));
 }
-// Channel slices of a lane: sub = lane & 7 owns channels [8 sub, 8 sub + 8) and [64 + 8 sub, 64 + 8 sub + 8) of the head, as
-// four float4 "it" = 0..3 (two 16-byte chunks of the bf16 row: 8 lanes read 128 contiguous bytes).
-__device__ __forceinline__ int edge_chan(int it, int sub) { return (it >> 1) * 64 + sub * 8 + (it & 1) * 4; }
 __device__ __forceinline__ uint32_t pack_bf16x2_rn(float lo, float hi) {
   const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<const uint32_t*>(&v);
