@@ -417,6 +417,14 @@ __global__ void __launch_bounds__(kThreads) env_round_kernel(const EnvParams p) 
   int act_post = 0;
   if (i < 4 && le < G) sm.cnt[le * 4 + i] = 0;
   if (threadIdx.x == 0) sm.cnt[G * 4] = 0;
+  // mask words beyond the episode's warps (W is a power of two, NP / 32 need not be: N = 65..96, 129..224) are never
+  // written by publish(): clear them once, or stale shared memory shows up as phantom nodes in every mask
+  {
+    const int wpn = NP >> 5;
+    if (wpn < W)
+      for (int t = threadIdx.x; t < M_COUNT * G * (W - wpn); t += blockDim.x)
+        sm.mask[(t / (W - wpn)) * W + wpn + t % (W - wpn)] = 0u;
+  }
 
   if (p.mode != 1) {
     // ------------------------------------------------------------ load state

@@ -221,3 +221,25 @@ def test_dynamic_philox_movement_is_consistent_and_deterministic():
     assert np.array_equal(a, b) and not np.array_equal(a, c)
     moves = np.diff(np.concatenate([a[:1] * 0 + pool.pos[gi][None], a]), axis=0)[1:]
     assert abs(moves.mean()) < 2e-3 and 0.03 < moves.std() < 0.04      # U(-0.06, 0.06): std = 0.0346
+
+
+@pytest.mark.parametrize("N,B", [(200, 8), (72, 16), (150, 8)])
+def test_phantom_nodes_from_stale_shared_memory(N, B):
+    """N = 65..96 and 129..224: the episode's bitmask rows have more words (W = 4 / 8) than the episode has warps.
+    The unused words must read as zero whatever an earlier kernel left in shared memory (they used to be
+    uninitialised: phantom acting nodes, wrong reward sums, episodes that never finish).  A tcgen05 GEMM with random
+    operands dirties ~200 KB of every SM's shared memory first."""
+    import ctypes as C
+    from melissa_b200 import _lib
+    L = _lib.lib()
+    L.mls_test_gemm_bf16.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p,
+                                     C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    M, K, Nn = 148 * 128 * 2, 512, 256
+    A = (torch.randn(M, K, device="cuda") * 1e4).to(torch.bfloat16)
+    Bm = (torch.randn(Nn, K, device="cuda") * 1e4).to(torch.bfloat16)
+    out = torch.empty(M, Nn, dtype=torch.bfloat16, device="cuda")
+    for _ in range(2):
+        _lib.check(L.mls_test_gemm_bf16(A.data_ptr(), Bm.data_ptr(), None, None, 0, 1, out.data_ptr(), M, Nn, K, 0, None,
+                                        _lib.current_stream_ptr()))
+    torch.cuda.synchronize()
+    assert _rollout_vs_oracle(N, B, min(B, 8), 10) > 0
