@@ -285,3 +285,18 @@ extern "C" int mls_test_gemm_bf16(const void* A, const void* B, const float* bia
   return mls::gemm_bf16_launch(reinterpret_cast<const __nv_bfloat16*>(A), K, reinterpret_cast<const __nv_bfloat16*>(B), K, shape,
                                epi, sms, reinterpret_cast<cudaStream_t>(stream));
 }
+
+// Same, with every epilogue option (tests/test_gemm_gpu.py): compacted row scale, one or two dot vectors per
+// 128-column group (optionally on max(value, 0)), C optional.
+extern "C" int mls_test_gemm_bf16_ex(const void* A, const void* B, const float* bias, const float* obs, long long obs_stride, int nodes,
+                                     const int* row_index, const float* dotvec, const float* dotvec2, float* dots, float* dots2,
+                                     int dot_relu, void* C, int M, int N, int K, int relu, const int* m_dev, void* stream) {
+  int dev = 0, sms = 0;
+  MLS_CUDA(cudaGetDevice(&dev));
+  MLS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  mls::GemmShape shape{M, N, K, m_dev};
+  mls::GemmEpilogue epi{reinterpret_cast<__nv_bfloat16*>(C), N, bias, obs, obs_stride, nodes, relu, dotvec, dots, row_index, dotvec2, dots2,
+                        dot_relu};
+  return mls::gemm_bf16_launch(reinterpret_cast<const __nv_bfloat16*>(A), K, reinterpret_cast<const __nv_bfloat16*>(B), K, shape,
+                               epi, sms, reinterpret_cast<cudaStream_t>(stream));
+}

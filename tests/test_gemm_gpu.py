@@ -81,3 +81,49 @@ def test_umma_mn_major_operand_layout(rows_a, kt):
     torch.cuda.synchronize()
     want = A.float()[:, :kt] @ B.float()[:kt]
     assert float((D[:rows_a] - want).abs().max()) < 1e-3
+
+
+@pytest.mark.parametrize("with_c,dot_relu,two,compact", [(True, False, False, False), (True, True, True, True), (False, True, True, False)])
+def test_epilogue_dots_row_index_and_dots_only(with_c, dot_relu, two, compact):
+    """Epilogue extras: per-128-column dot products with one or two vectors (linear parts of the GATv2 logits; the
+    dueling heads' output layer), optionally on max(value, 0); row scale through a row index (compacted
+    controlling-node rows); C = NULL (dots only); device-side row count."""
+    from melissa_b200 import _lib
+    L = _lib.lib()
+    vp = C.c_void_p
+    L.mls_test_gemm_bf16_ex.argtypes = [vp, vp, vp, vp, C.c_longlong, C.c_int, vp, vp, vp, vp, vp, C.c_int, vp,
+                                        C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]
+    L.mls_test_gemm_bf16_ex.restype = C.c_int
+    torch.manual_seed(3)
+    M, N, K, nodes = 700, 256, 192, 10
+    A = torch.randn(M, K, device="cuda").to(torch.bfloat16)
+    B = (torch.randn(N, K, device="cuda") / 8).to(torch.bfloat16)
+    bias = torch.randn(N, device="cuda")
+    n_src = 130                                                 # node rows = 130 graphs x 10 nodes
+    obs = torch.zeros(n_src, nodes, 8, device="cuda")
+    obs[:, :, 7] = (torch.rand(n_src, nodes, device="cuda") > 0.3).float()
+    row_index = torch.randint(0, n_src * nodes, (M,), device="cuda", dtype=torch.int32) if compact else None
+    dv = torch.randn(N, device="cuda")
+    dv2 = torch.randn(N, device="cuda") if two else None
+    dots = torch.full((M, N // 128), float("nan"), device="cuda")
+    dots2 = torch.full((M, N // 128), float("nan"), device="cuda") if two else None
+    Cout = torch.full((M, N), float("nan"), dtype=torch.bfloat16, device="cuda") if with_c else None
+    m_dev = torch.tensor([650], dtype=torch.int32, device="cuda")
+    _lib.check(L.mls_test_gemm_bf16_ex(A.data_ptr(), B.data_ptr(), bias.data_ptr(), obs.data_ptr(), nodes * 8, nodes, _lib.ptr(row_index),
+                                       dv.data_ptr(), _lib.ptr(dv2), dots.data_ptr(), _lib.ptr(dots2), int(dot_relu), _lib.ptr(Cout),
+                                       M, N, K, 0, m_dev.data_ptr(), _lib.current_stream_ptr()))
+    torch.cuda.synchronize()
+    rows = row_index.long() if compact else torch.arange(M, device="cuda")
+    scale = obs.reshape(-1, 8)[rows, 7]
+    x = (A.float() @ B.float().T) * scale[:, None] + bias[None, :]
+    xd = x.clamp_min(0) if dot_relu else x
+    live = slice(0, 650)
+    want = (xd * dv[None, :]).reshape(M, N // 128, 128).sum(2)
+    assert torch.allclose(dots[live], want[live], rtol=2e-3, atol=2e-2)
+    assert torch.isnan(dots[650:]).all()                        # rows beyond the device-side count are untouched
+    if two:
+        want2 = (xd * dv2[None, :]).reshape(M, N // 128, 128).sum(2)
+        assert torch.allclose(dots2[live], want2[live], rtol=2e-3, atol=2e-2)
+    if with_c:
+        _check(Cout[live], x[live])
+        assert torch.isnan(Cout[650:].float()).all()
