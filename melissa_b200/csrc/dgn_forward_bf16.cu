@@ -160,11 +160,11 @@ __global__ void __launch_bounds__(256) graph_csr_kernel(const float* __restrict_
   uint32_t* s_mask = reinterpret_cast<uint32_t*>(csm);      // [N][W]
   int* s_ptr = reinterpret_cast<int*>(s_mask + (size_t)N * W);   // [N+1]
   float* s_pos = reinterpret_cast<float*>(s_ptr + N + 1);   // [N][2]: one trip to global memory for the positions
-  const int g = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const float* g_obs = obs + (int64_t)g * obs_stride;
-  for (int t = threadIdx.x; t < 2 * N; t += 256) s_pos[t] = g_obs[(t >> 1) * 8 + (t & 1)];
+  for (int t = threadIdx.x; t < 2 * N; t += blockDim.x) s_pos[t] = g_obs[(t >> 1) * 8 + (t & 1)];
   __syncthreads();
-  for (int i = warp; i < N; i += 8) {
+  for (int i = warp; i < N; i += nwarps) {
     uint32_t nb[W];
     radius_neighbours<W>(s_pos, N, i, lane, nb, 2);
     int deg = 0;
@@ -194,8 +194,8 @@ __global__ void __launch_bounds__(256) graph_csr_kernel(const float* __restrict_
   __syncthreads();
   uint16_t* gp = csr_ptr + (size_t)g * (N + 1);
   uint8_t* gs = csr_src + (size_t)g * N * kMaxNbr;
-  for (int t = threadIdx.x; t <= N; t += 256) gp[t] = (uint16_t)s_ptr[t];
-  for (int i = warp; i < N; i += 8) {
+  for (int t = threadIdx.x; t <= N; t += blockDim.x) gp[t] = (uint16_t)s_ptr[t];
+  for (int i = warp; i < N; i += nwarps) {
     int off = s_ptr[i];
 #pragma unroll
     for (int w = 0; w < W; ++w) {
@@ -885,11 +885,12 @@ int dgn_forward_bf16(const MlsNetDesc* d, const MlsNetWeights* w, const MlsForwa
     }
     {
       const size_t csm = (size_t)N * Wn * 4 + ((size_t)N + 1) * 4 + (size_t)N * 8;
+      const int kCsrThreads = N <= 64 ? 64 : 256;           // small graphs: more, smaller CTAs (fewer threads idle at the barriers)
       switch (Wn) {
-        case 1: graph_csr_kernel<1><<<gc, 256, csm, st>>>(obs, a->obs_stride, N, gc, ws.csr_ptr, ws.csr_src); break;
-        case 2: graph_csr_kernel<2><<<gc, 256, csm, st>>>(obs, a->obs_stride, N, gc, ws.csr_ptr, ws.csr_src); break;
-        case 4: graph_csr_kernel<4><<<gc, 256, csm, st>>>(obs, a->obs_stride, N, gc, ws.csr_ptr, ws.csr_src); break;
-        default: graph_csr_kernel<8><<<gc, 256, csm, st>>>(obs, a->obs_stride, N, gc, ws.csr_ptr, ws.csr_src); break;
+        case 1: graph_csr_kernel<1><<<gc, kCsrThreads, csm, st>>>(obs, a->obs_stride, N, gc, ws.csr_ptr, ws.csr_src); break;
+        case 2: graph_csr_kernel<2><<<gc, kCsrThreads, csm, st>>>(obs, a->obs_stride, N, gc, ws.csr_ptr, ws.csr_src); break;
+        case 4: graph_csr_kernel<4><<<gc, kCsrThreads, csm, st>>>(obs, a->obs_stride, N, gc, ws.csr_ptr, ws.csr_src); break;
+        default: graph_csr_kernel<8><<<gc, kCsrThreads, csm, st>>>(obs, a->obs_stride, N, gc, ws.csr_ptr, ws.csr_src); break;
       }
     }
     mls_count_launch();
