@@ -75,20 +75,20 @@ def _tuple_shard(args):
     return reset_chain.episode_pool(base, count, N, G)
 
 
-def load_tuples(N, G, count, base_seed=9):
+def load_tuples(N, G, count, base_seed=9, first_index=0):
     """Reset tuples drawn with the reference's RNG chain, env seed = base_seed + k (tianshou
-    seeds vector env k with seed + k); graph k % G."""
+    seeds vector env k with seed + k); graph (first_index + k) % G."""
     path = os.path.join(CACHE_DIR, f"tuples_n{N}_g{G}_c{count}_s{base_seed}.npz")
     if os.path.exists(path):
         z = np.load(path)
-        return z["gi"], z["src"], z["inter"], z["scr"]
+        return ((first_index + np.arange(count)) % G).astype(np.int32), z["src"], z["inter"], z["scr"]
     import multiprocessing as mp
-    procs = max(1, min(os.cpu_count() or 1, 16))
+    procs = max(1, min((os.cpu_count() or 1) // max(1, int(os.environ.get("WORLD_SIZE", "1"))), 16))
     per = (count + procs - 1) // procs
     jobs = [(base_seed + p * per, min(per, count - p * per), N, G) for p in range(procs) if p * per < count]
     with mp.get_context("spawn").Pool(len(jobs)) as pool:
         parts = pool.map(_tuple_shard, jobs)
-    gi = (np.arange(count) % G).astype(np.int32)
+    gi = ((first_index + np.arange(count)) % G).astype(np.int32)
     src = np.concatenate([p[1] for p in parts])
     inter = np.concatenate([p[2] for p in parts])
     scr = np.concatenate([p[3] for p in parts])
@@ -185,14 +185,11 @@ def run_ours(args):
     N, B, G = args.nodes, args.episodes, args.graphs
     pool = load_pool(N, G)
     P = 2 * B
-    if rank == 0:
-        tup = load_tuples(N, G, P)
-    if world > 1:
-        dist.barrier()
-    if rank != 0:
-        tup = load_tuples(N, G, P)
-    from melissa_b200.sharding import reduce_job, shard_tuples
-    gi, src, inter, scr = shard_tuples(tup, rank, B)   # each rank starts elsewhere in the pool
+    from melissa_b200.sharding import rank_seed_range, reduce_job
+    # every rank draws its own pool: env seeds 9 + rank*P + k (global env index, tianshou seeds env i with seed + i),
+    # graphs (rank*P + k) % G -- disjoint across ranks
+    seed0, first = rank_seed_range(9, rank, P)
+    gi, src, inter, scr = load_tuples(N, G, P, base_seed=seed0, first_index=first)
     env = BatchedGraphEnv(B, N, pool, device=dev, want_obs=True, dynamic_graph=args.dynamic)
     net = None
     if args.model != "none":

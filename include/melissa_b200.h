@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define MLS_VERSION 100
+#define MLS_VERSION 200
 #define MLS_MAX_NODES 256
 
 /* ---- errors ------------------------------------------------------------------------- */
@@ -38,8 +38,10 @@ const char* mls_last_error(void);
 int mls_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);
 /* words per bitmask row for N nodes: 1 (N<=32), 2 (<=64), 4 (<=128), 8 (<=256). */
 int mls_words_per_row(int n_nodes);
-/* process-wide tuning options; "fused_conv" = 1 selects the experimental fused projection+attention kernel
- * for the GATv2 convolutions of L-DGN (bf16 precision).  get returns -1 for an unknown key. */
+/* process-wide tuning options (A/B switches for benchmarking; defaults are the fast paths):
+ *   "attn_mma"  1 = conv1 attention through the pair-logit table + tcgen05 aggregation (discrete-feature mode)
+ *   "conv2_mma" 1 = conv2 attention with half2 logits + tcgen05 aggregation (graphs of <= 64 nodes)
+ * get returns -1 for an unknown key. */
 int mls_set_option(const char* key, int value);
 int mls_get_option(const char* key);
 /* kernels launched by this library since it was loaded (process wide; for bench accounting). */
@@ -232,6 +234,14 @@ typedef struct MlsForwardArgs {
   /* with MLS_FWD_DISCRETE_FEATURES: device int32, set to the number of node rows whose features were not
    * small non-negative integers (those rows are evaluated with key 0); NULL ok */
   void* feature_errors;
+  /* optional topology cache (static graph pools; bf16 precision): graph g of this call has the node positions of
+   * pool graph graph_ids[g * graph_id_stride], whose radius_graph lists are in csr_cache (mls_dgn_csr_cache_build);
+   * the per-call radius_graph pass is then skipped.  The caller guarantees that obs columns 0..1 of graph g equal
+   * the positions the cache was built from.  NULL: lists are rebuilt from obs on every call (dynamic graphs). */
+  const int32_t* graph_ids;
+  int32_t graph_id_stride;   /* in int32 elements (MLS_EP_STRIDE when pointing at episode[b][MLS_EP_GRAPH]) */
+  int32_t csr_cache_graphs;  /* pool size the cache was built for */
+  const void* csr_cache;
 } MlsForwardArgs;
 
 /* The caller guarantees that obs columns 2..6 (degree, messages transmitted, last action, interested,
@@ -239,6 +249,10 @@ typedef struct MlsForwardArgs {
  * mls_env_reset / mls_env_step (graph.py:263-269): degree < 2^ceil(log2 N), messages < 64, flags 0/1.
  * bf16 precision only: encoder + conv1 projections are then evaluated once per distinct feature key. */
 #define MLS_FWD_DISCRETE_FEATURES 1
+/* bf16 precision: the workspace already holds the packed bf16 weights (and, with MLS_FWD_DISCRETE_FEATURES, the
+ * feature tables) of exactly these parameters, left there by mls_dgn_prepare with the same desc / flags on the same
+ * workspace; the forward skips re-packing them (weights only change on an optimiser step). */
+#define MLS_FWD_PREPARED 2
 
 enum MlsProfKernel {
   MLS_PROF_NONE = 0,
@@ -254,6 +268,17 @@ size_t mls_dgn_workspace_bytes(const MlsNetDesc* desc, int32_t n_graphs);
 int mls_dgn_chunk_graphs(const MlsNetDesc* desc, int32_t n_graphs);
 int mls_dgn_forward(const MlsNetDesc* desc, const MlsNetWeights* w, const MlsForwardArgs* args,
                     void* stream);
+/* Pack the parameters into the workspace (bf16 weight matrices, stacked biases, feature tables when flags has
+ * MLS_FWD_DISCRETE_FEATURES) for later mls_dgn_forward calls with MLS_FWD_PREPARED.  The packed region's layout does
+ * not depend on the number of graphs.  fp32 precision: no-op. */
+int mls_dgn_prepare(const MlsNetDesc* desc, const MlsNetWeights* w, int32_t flags, void* workspace,
+                    size_t workspace_bytes, void* stream);
+/* Topology cache of a static graph pool: radius_graph(pos, r=0.2, loop=False, max_num_neighbors=32)
+ * (networks/common.py:47-48) of every pool graph, built once.  pos_obs: graph k's node i has its position at
+ * pos_obs[k*obs_stride + i*8 + {0,1}] (fp32, the values the environment writes into obs columns 0..1). */
+size_t mls_dgn_csr_cache_bytes(const MlsNetDesc* desc, int32_t n_pool_graphs);
+int mls_dgn_csr_cache_build(const MlsNetDesc* desc, const float* pos_obs, int64_t obs_stride,
+                            int32_t n_pool_graphs, void* cache, size_t cache_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -78,15 +78,18 @@ class MlsForwardArgs(C.Structure):
                 ("ctrl_mask", vp), ("q", vp), ("act", vp), ("eps", C.c_float), ("flags", C.c_int32),
                 ("philox_seed", C.c_uint64), ("philox_offset", C.c_uint64), ("rand3", vp), ("workspace", vp),
                 ("workspace_bytes", C.c_size_t), ("prof_start", vp), ("prof_stop", vp), ("prof_kernel", C.c_int32),
-                ("pad2_", C.c_int32), ("philox_offset_dev", vp), ("feature_errors", vp)]
+                ("pad2_", C.c_int32), ("philox_offset_dev", vp), ("feature_errors", vp),
+                ("graph_ids", vp), ("graph_id_stride", C.c_int32), ("csr_cache_graphs", C.c_int32), ("csr_cache", vp)]
 
 
 FWD_DISCRETE_FEATURES = 1
+FWD_PREPARED = 2
 PROF_KERNELS = {None: 0, "proj1": 1, "proj2": 2, "edge1": 3, "edge2": 4, "head0": 5}
 
 
 EXPORTS = ["mls_version", "mls_last_error", "mls_device_info", "mls_words_per_row", "mls_launch_count", "mls_set_option", "mls_get_option", "mls_env_reset", "mls_env_step",
-           "mls_env_info", "mls_dgn_workspace_bytes", "mls_dgn_chunk_graphs", "mls_dgn_forward"]
+           "mls_env_info", "mls_dgn_workspace_bytes", "mls_dgn_chunk_graphs", "mls_dgn_forward", "mls_dgn_prepare",
+           "mls_dgn_csr_cache_bytes", "mls_dgn_csr_cache_build"]
 
 _lib = None
 
@@ -122,6 +125,10 @@ def lib():
     L.mls_dgn_workspace_bytes.restype = C.c_size_t
     L.mls_dgn_chunk_graphs.argtypes = [P(MlsNetDesc), C.c_int32]
     L.mls_dgn_forward.argtypes = [P(MlsNetDesc), P(MlsNetWeights), P(MlsForwardArgs), vp]
+    L.mls_dgn_prepare.argtypes = [P(MlsNetDesc), P(MlsNetWeights), C.c_int32, vp, C.c_size_t, vp]
+    L.mls_dgn_csr_cache_bytes.argtypes = [P(MlsNetDesc), C.c_int32]
+    L.mls_dgn_csr_cache_bytes.restype = C.c_size_t
+    L.mls_dgn_csr_cache_build.argtypes = [P(MlsNetDesc), vp, C.c_int64, C.c_int32, vp, C.c_size_t, vp]
     for name in EXPORTS:
         getattr(L, name)
     _lib = L

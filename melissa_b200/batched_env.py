@@ -40,9 +40,15 @@ def pack_bits(mask: np.ndarray, W: int) -> np.ndarray:
 class ResetTuplesDevice:
     """Reset tuples (graph index, source, interested set, scripted set) resident on the device."""
 
-    def __init__(self, graph_index, source, interested, scripted, n_nodes, device):
+    def __init__(self, graph_index, source, interested, scripted, n_nodes, device, pool_size=None):
         W = _lib.words_per_row(n_nodes)
         self.count = int(len(source))
+        gi_np, src_np = np.asarray(graph_index, dtype=np.int64), np.asarray(source, dtype=np.int64)
+        if self.count and (gi_np.min() < 0 or (pool_size is not None and gi_np.max() >= pool_size)):
+            raise ValueError("reset tuples: graph_index outside the topology pool")
+        if self.count and (src_np.min() < 0 or src_np.max() >= n_nodes):
+            raise ValueError("reset tuples: source node outside the graph")
+        self.max_graph = int(gi_np.max()) if self.count else -1
         self.graph_index = torch.as_tensor(np.asarray(graph_index, dtype=np.int32), device=device)
         self.source = torch.as_tensor(np.asarray(source, dtype=np.int32), device=device)
         self.interested = torch.as_tensor(_bits_to_i32(pack_bits(np.asarray(interested, dtype=bool), W)), device=device)
@@ -143,6 +149,7 @@ class BatchedGraphEnv:
                 raise ValueError("env_ids and tuples differ in length")
         elif tuples.count > self.B:
             raise ValueError("more tuples than episodes")
+        self._check_tuples(tuples)
         inp, keep = self._inputs(None, move_offsets, gossip_bits, relay_bits)
         tup = tuples.c_struct()
         _lib.check(self.lib.mls_env_reset(C.byref(self.desc), C.byref(self._state), _lib.ptr(ids), C.byref(tup),
@@ -151,7 +158,13 @@ class BatchedGraphEnv:
 
     def set_recycling(self, tuples: ResetTuplesDevice | None):
         """Episodes that finish are restarted inside the step kernel from this pool."""
+        if tuples is not None:
+            self._check_tuples(tuples)
         self.recycle = tuples
+
+    def _check_tuples(self, tuples: ResetTuplesDevice):
+        if getattr(tuples, "max_graph", -1) >= len(self.pool):
+            raise ValueError(f"reset tuples name graph {tuples.max_graph} but the topology pool holds {len(self.pool)} graphs")
 
     def step(self, actions, *, move_offsets=None, gossip_bits=None, relay_bits=None):
         """One round for all episodes.  ``actions`` int8 [B, N] (device tensor or numpy):

@@ -30,28 +30,27 @@ extern "C" int mls_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc
   return MLS_OK;
 }
 
-// ---- tuning options (process wide).  "fused_conv": 1 = run the GATv2 convolutions of L-DGN with the fused
-// projection+attention kernel (conv_fused.cu; experimental, slower than the two-kernel path in round 1).
-// Initial values come from the environment (MLS_FUSED_CONV).
+// ---- tuning options (process wide; A/B switches, defaults = fast paths).  Initial values come from the
+// environment (MLS_ATTN_MMA, MLS_CONV2_MMA).
+//   "attn_mma":  1 = in discrete-feature mode run conv1's attention through the pair-logit table and the tensor-core
+//                aggregation kernel (attn_table.cu); 0 = gather kernel only
+//   "conv2_mma": 1 = conv2 attention with half2 logits + tensor-core aggregation (conv2_attn.cu); 0 = gather kernel
 #include <stdlib.h>
 #include <string.h>
-static int g_fused_conv = -1;
-// "attn_mma": 1 (default) = in discrete-feature mode run conv1's attention through the pair-logit table and
-// the tensor-core aggregation kernel (attn_table.cu); 0 = gather kernel only.  Environment: MLS_ATTN_MMA.
-static int g_attn_mma = -1;
+static int g_attn_mma = -1, g_conv2_mma = -1;
 extern "C" int mls_get_option(const char* key) {
   if (key && !strcmp(key, "attn_mma")) {
     if (g_attn_mma < 0) { const char* e = getenv("MLS_ATTN_MMA"); g_attn_mma = e ? atoi(e) : 1; }
     return g_attn_mma;
   }
-  if (key && !strcmp(key, "fused_conv")) {
-    if (g_fused_conv < 0) { const char* e = getenv("MLS_FUSED_CONV"); g_fused_conv = e ? atoi(e) : 0; }
-    return g_fused_conv;
+  if (key && !strcmp(key, "conv2_mma")) {
+    if (g_conv2_mma < 0) { const char* e = getenv("MLS_CONV2_MMA"); g_conv2_mma = e ? atoi(e) : 1; }
+    return g_conv2_mma;
   }
   return -1;
 }
 extern "C" int mls_set_option(const char* key, int value) {
-  if (key && !strcmp(key, "fused_conv")) { g_fused_conv = value ? 1 : 0; return MLS_OK; }
+  if (key && !strcmp(key, "conv2_mma")) { g_conv2_mma = value ? 1 : 0; return MLS_OK; }
   if (key && !strcmp(key, "attn_mma")) { g_attn_mma = value ? 1 : 0; return MLS_OK; }
   mls_set_error("unknown option %s", key ? key : "(null)");
   return MLS_ERR_INVALID;

@@ -361,6 +361,16 @@ __global__ void __launch_bounds__(kTThreads, 1) attn_table_mma_kernel(const Attn
       // controlling-list slots of the tile's targets: lane t holds targets t and t + 32
       const int sl0 = (lane < rt && a.slot) ? a.slot[m0 + lane] : -1;
       const int sl1 = (lane + 32 < rt && a.slot) ? a.slot[m0 + lane + 32] : -1;
+      // x_out rows of the tile's targets (-1: not needed / beyond the tile)
+      int xr0 = -1, xr1 = -1;
+      if (a.pool_mode < 0) {
+        if (lane < rt) xr0 = a.xrow ? a.xrow[m0 + lane] : (int)m0 + lane;
+        if (lane + 32 < rt) xr1 = a.xrow ? a.xrow[m0 + lane + 32] : (int)m0 + lane + 32;
+      }
+      const uint32_t nm0 = __ballot_sync(0xffffffffu, xr0 >= 0), nm1 = __ballot_sync(0xffffffffu, xr1 >= 0);
+      int xfirst = 0;
+      if (nm0) xfirst = __shfl_sync(0xffffffffu, xr0, __ffs(nm0) - 1);
+      else if (nm1) xfirst = __shfl_sync(0xffffffffu, xr1, __ffs(nm1) - 1);
       // a graph's slots are consecutive in node order (ctrl_list_slot_kernel): with one graph per tile the
       // snapshot rows are walked with a running pointer instead of a shuffle per target
       const uint32_t zm0 = __ballot_sync(0xffffffffu, sl0 >= 0), zm1 = __ballot_sync(0xffffffffu, sl1 >= 0);
@@ -395,26 +405,33 @@ __global__ void __launch_bounds__(kTThreads, 1) attn_table_mma_kernel(const Attn
           }
           continue;
         }
-        const int nv = rt - t0;
-        uint16_t* xo = reinterpret_cast<uint16_t*>(a.x_out) + (m0 + t0) * HC + col;
+        uint16_t* xo = reinterpret_cast<uint16_t*>(a.x_out) + col;
         uint16_t* zo = reinterpret_cast<uint16_t*>(a.z) + a.z_col + col;
         if (G == 1) {
-          const uint32_t zm = t0 ? zm1 : zm0;
+          // one graph per tile: its needed rows and its slots are consecutive in node order -> running pointers
+          const uint32_t zm = t0 ? zm1 : zm0, nm = t0 ? nm1 : nm0;
           uint16_t* zp = zo + (uint32_t)(zfirst + (t0 ? __popc(zm0) : 0)) * ldz_u;   // < 2^31 elements (checked at launch)
+          uint16_t* xp = xo + (size_t)(xfirst + (t0 ? __popc(nm0) : 0)) * HC;
 #pragma unroll
           for (int t = 0; t < 32; ++t) {
-            const uint16_t o = relu_bf16(__uint_as_float(v[t]));
-            if (t < nv) xo[(size_t)t * HC] = o;                                // 32 lanes = 64 contiguous bytes
-            if ((zm >> t) & 1u) { *zp = o; zp += ldz_u; }
+            if ((nm >> t) & 1u) {                                              // warp uniform
+              const uint16_t o = relu_bf16(__uint_as_float(v[t]));
+              *xp = o;                                                         // 32 lanes = 64 contiguous bytes
+              xp += HC;
+              if ((zm >> t) & 1u) { *zp = o; zp += ldz_u; }
+            }
           }
         } else {
-          const int slv = t0 ? sl1 : sl0;                                      // -1 beyond the tile's rows
+          const int slv = t0 ? sl1 : sl0, xrv = t0 ? xr1 : xr0;                // -1 beyond the tile's rows
 #pragma unroll
           for (int t = 0; t < 32; ++t) {
-            const uint16_t o = relu_bf16(__uint_as_float(v[t]));
-            if (t < nv) xo[(size_t)t * HC] = o;
+            const int xr = __shfl_sync(0xffffffffu, xrv, t);
             const int sl = __shfl_sync(0xffffffffu, slv, t);
-            if (sl >= 0) zo[(uint32_t)sl * ldz_u] = o;
+            if (xr >= 0) {
+              const uint16_t o = relu_bf16(__uint_as_float(v[t]));
+              xo[(size_t)xr * HC] = o;
+              if (sl >= 0) zo[(uint32_t)sl * ldz_u] = o;
+            }
           }
         }
       }
@@ -427,8 +444,9 @@ __global__ void __launch_bounds__(kTThreads, 1) attn_table_mma_kernel(const Attn
     unsigned char* sA = smem + team * kStage;
     const uint32_t sB32 = smem_u32(sA + kStageA);
     uint8_t* src_s = meta + team * kMeta;                                       // [gt][N*32]
-    uint32_t* key_s = reinterpret_cast<uint32_t*>(src_s + kMetaSrc);            // [64]
-    uint16_t* cid = reinterpret_cast<uint16_t*>(key_s + 64);                    // [64]
+    uint8_t* need_s = src_s + kMetaSrc;                                         // [64] node rows of the tile whose output is read
+    int* cnt_s = reinterpret_cast<int*>(need_s + 64);                           // [2]
+    uint16_t* cid = reinterpret_cast<uint16_t*>(need_s + 256);                  // [64]
     uint16_t* ptr_s = cid + 64;                                                 // [gt][N+1]
     float* dm_s = reinterpret_cast<float*>(ptr_s + 128);                        // [64] decision-maker flag (pooling variant)
     // value gather: 4 lanes per node, lane part p copies the 16-byte chunks 4i + p (i = 0..15) of the node's 1 KiB
@@ -445,18 +463,32 @@ __global__ void __launch_bounds__(kTThreads, 1) attn_table_mma_kernel(const Attn
       uint16_t cv = 0;
       uint4 sv = make_uint4(0, 0, 0, 0);
       float dmv = 1.f;
+      int xrv = 0;                                                             // >= 0: somebody reads this target's output
       if (pt < rt) {
         cv = __ldg(a.row_cid + m0 + pt);
         if (a.pool_mode >= 0) dmv = __ldg(a.obs + (long long)(g0 + pt / N) * a.obs_stride + (pt % N) * 8 + 7);
+        if (a.xrow) xrv = __ldg(a.xrow + m0 + pt);
       }
-      if (pt < gt * (N + 1)) pv = __ldg(a.csr_ptr + (size_t)g0 * (N + 1) + pt);                     // gt * (N + 1) <= 128
-      if (pt < rt * 2) sv = __ldg(reinterpret_cast<const uint4*>(a.csr_src + (size_t)g0 * N * kMaxNbr) + pt);   // N*32 bytes per graph
+      if (pt < gt * (N + 1)) {                                                 // gt * (N + 1) <= 128
+        const int gl = pt / (N + 1), il = pt - gl * (N + 1);
+        const size_t cg = a.graph_id ? (size_t)__ldg(a.graph_id + (size_t)(g0 + gl) * a.gid_stride) : (size_t)(g0 + gl);
+        pv = __ldg(a.csr_ptr + cg * (N + 1) + il);
+      }
+      if (pt < rt * 2) {                                                       // N*32 bytes (2N chunks of 16 B) per graph
+        const int gl = pt / (2 * N), cl = pt - gl * 2 * N;
+        const size_t cg = a.graph_id ? (size_t)__ldg(a.graph_id + (size_t)(g0 + gl) * a.gid_stride) : (size_t)(g0 + gl);
+        sv = __ldg(reinterpret_cast<const uint4*>(a.csr_src + cg * N * kMaxNbr) + cl);
+      }
+      // the tile's needed targets, compacted (team warps 0 and 1 hold node rows 0..63)
+      const uint32_t nbal = __ballot_sync(0xffffffffu, pt < rt && xrv >= 0);
       mbar_wait_backoff(empty_bar(team), (use & 1) ^ 1);                       // the MMAs that read this stage are done
       for (int u = pt; u < kStageA / 16; u += kTeam) reinterpret_cast<uint4*>(sA)[u] = make_uint4(0, 0, 0, 0);
       if (pt < rt) { cid[pt] = cv; dm_s[pt] = dmv; }
       if (pt < gt * (N + 1)) ptr_s[pt] = (uint16_t)pv;
       if (pt < rt * 2) reinterpret_cast<uint4*>(src_s)[pt] = sv;
+      if (pt < 64 && lane == 0) cnt_s[pt >> 5] = __popc(nbal);
       bar_team(team);
+      if (pt < rt && xrv >= 0) need_s[(pt >= 32 ? cnt_s[0] : 0) + __popc(nbal & ((1u << lane) - 1u))] = (uint8_t)pt;
       // ---- phase B: value rows of the tile's nodes, asynchronously (swizzled by the node's row residue) ...
       for (int j = pt >> 2; j < rt; j += kTeam / 4) {
         const unsigned char* src = gsrc + (size_t)cid[j] * (HC * 2);
@@ -465,9 +497,11 @@ __global__ void __launch_bounds__(kTThreads, 1) attn_table_mma_kernel(const Attn
 #pragma unroll
         for (int i = 0; i < 16; ++i) cp_async16(((i & 1) ? d1 : d0) + (i >> 1) * kBPanel, src + i * 64);
       }
-      // ---- ... and the normalised softmax weights of (target i, head h) as bf16 rows of the head's weight matrix
-      for (int tt = pt; tt < rt * 4; tt += kTeam) {
-        const int i = tt >> 2, h = tt & 3;
+      bar_team(team);                                                          // need_s complete
+      // ---- ... and the normalised softmax weights of (needed target i, head h) as fp16 rows of the head's weight matrix
+      const int n_tasks = (cnt_s[0] + cnt_s[1]) * 4;
+      for (int tt = pt; tt < n_tasks; tt += kTeam) {
+        const int i = need_s[tt >> 2], h = tt & 3;
         if (a.pool_mode >= 0 && dm_s[i] == 0.f) continue;                       // relu(conv) * 0: the row stays all zero
         const int gl = i / N, il = i - gl * N, rbase = gl * N;
         const uint16_t* ptr = ptr_s + gl * (N + 1);

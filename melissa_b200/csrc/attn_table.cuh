@@ -25,7 +25,13 @@ struct AttnTableArgs {
   const uint16_t* csr_ptr;   // [graphs][N+1]
   const uint8_t* csr_src;    // [graphs][N*32]
   const int* slot;           // [rows] controlling-list slot or -1
-  __nv_bfloat16* x_out;      // [rows][H*C] relu(conv)
+  // optional "needed" row map (ctrl_need_list_kernel): x_out row of every node row, -1 = nobody reads this node's
+  // conv output (its softmax weights are not even built); needed rows of a graph are consecutive, in node order
+  const int* xrow;
+  // CSR lists of graph g live at index graph_id[g * gid_stride] (topology cache of a static graph pool), else at g
+  const int* graph_id;
+  int gid_stride;
+  __nv_bfloat16* x_out;      // [rows][H*C] relu(conv)  (or [needed rows][H*C] with xrow)
   __nv_bfloat16* z;          // snapshot rows
   int ldz, z_col;
   // HL-DGN: pool_mode >= 0 (enum MlsPool): instead of x_out / snapshots, z[graph][z_col + H*C] = pool over the graph's

@@ -444,6 +444,37 @@ extern "C" size_t mls_dgn_workspace_bytes(const MlsNetDesc* desc, int32_t n_grap
   return carve(desc, chunk_graphs(desc, n_graphs), nullptr, nullptr);
 }
 
+static int check_desc(const MlsNetDesc* d) {
+  MLS_CHECK_ARG(d->kind >= MLS_NET_DGN_R && d->kind <= MLS_NET_HL_DGN, "unknown network kind %d", d->kind);
+  MLS_CHECK_ARG(d->n_nodes >= 1 && d->n_nodes <= MLS_MAX_NODES, "n_nodes out of range: %d", d->n_nodes);
+  MLS_CHECK_ARG(d->hidden == kC, "hidden_dim must be %d (got %d)", kC, d->hidden);
+  MLS_CHECK_ARG(d->heads >= 1 && d->heads <= 8, "num_heads must be in [1,8]");
+  MLS_CHECK_ARG(d->input_dim >= 1 && d->input_dim <= 5, "input_dim must be <= 5 (obs rows hold 5 features)");
+  MLS_CHECK_ARG(d->head_hidden % 16 == 0 && d->head_hidden >= 16, "head hidden size must be a multiple of 16");
+  return MLS_OK;
+}
+
+extern "C" int mls_dgn_prepare(const MlsNetDesc* d, const MlsNetWeights* w, int32_t flags, void* workspace, size_t workspace_bytes,
+                               void* stream) {
+  MLS_CHECK_ARG(d && w, "NULL argument");
+  if (int rc = check_desc(d)) return rc;
+  if (d->precision != MLS_PREC_BF16) return MLS_OK;        // the fp32 path reads the parameters in place
+  return dgn_prepare_bf16(d, w, flags, workspace, workspace_bytes, stream);
+}
+
+extern "C" size_t mls_dgn_csr_cache_bytes(const MlsNetDesc* d, int32_t n_pool_graphs) {
+  if (!d || n_pool_graphs <= 0 || d->n_nodes <= 0 || d->n_nodes > MLS_MAX_NODES) return 0;
+  return dgn_csr_cache_bytes(d, n_pool_graphs);
+}
+
+extern "C" int mls_dgn_csr_cache_build(const MlsNetDesc* d, const float* pos_obs, int64_t obs_stride, int32_t n_pool_graphs, void* cache,
+                                       size_t cache_bytes, void* stream) {
+  MLS_CHECK_ARG(d && pos_obs && cache && n_pool_graphs > 0, "NULL argument");
+  MLS_CHECK_ARG(d->n_nodes >= 1 && d->n_nodes <= MLS_MAX_NODES, "n_nodes out of range: %d", d->n_nodes);
+  MLS_CHECK_ARG(obs_stride >= (int64_t)d->n_nodes * 8 - 6, "position rows must be 8 floats apart");
+  return dgn_csr_cache_build(d, pos_obs, obs_stride, n_pool_graphs, cache, cache_bytes, stream);
+}
+
 extern "C" int mls_dgn_forward(const MlsNetDesc* d, const MlsNetWeights* w, const MlsForwardArgs* a, void* stream) {
   MLS_CHECK_ARG(d && w && a, "NULL argument");
   MLS_CHECK_ARG(d->kind >= MLS_NET_DGN_R && d->kind <= MLS_NET_HL_DGN, "unknown network kind %d", d->kind);

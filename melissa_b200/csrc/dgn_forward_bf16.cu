@@ -13,7 +13,7 @@
 #include "dgn_kernels.cuh"
 #include "gemm_tcgen05.cuh"
 #include "attn_table.cuh"
-#include "conv_fused.cuh"
+#include "conv2_attn.cuh"
 
 namespace mls {
 
@@ -155,7 +155,8 @@ __global__ void __launch_bounds__(256) enc0_keys_kernel(int n_keys, int in_dim, 
 // shared by all heads and by both conv layers.  One CTA per graph.
 template <int W>
 __global__ void __launch_bounds__(256) graph_csr_kernel(const float* __restrict__ obs, int64_t obs_stride, int N, int n_graphs,
-                                                        uint16_t* __restrict__ csr_ptr, uint8_t* __restrict__ csr_src) {
+                                                        uint16_t* __restrict__ csr_ptr, uint8_t* __restrict__ csr_src,
+                                                        uint32_t* __restrict__ adj_out) {
   extern __shared__ __align__(16) unsigned char csm[];
   uint32_t* s_mask = reinterpret_cast<uint32_t*>(csm);      // [N][W]
   int* s_ptr = reinterpret_cast<int*>(s_mask + (size_t)N * W);   // [N+1]
@@ -195,6 +196,7 @@ __global__ void __launch_bounds__(256) graph_csr_kernel(const float* __restrict_
   uint16_t* gp = csr_ptr + (size_t)g * (N + 1);
   uint8_t* gs = csr_src + (size_t)g * N * kMaxNbr;
   for (int t = threadIdx.x; t <= N; t += blockDim.x) gp[t] = (uint16_t)s_ptr[t];
+  if (adj_out) for (int t = threadIdx.x; t < N * W; t += blockDim.x) adj_out[(size_t)g * N * W + t] = s_mask[t];   // source masks per target
   for (int i = warp; i < N; i += nwarps) {
     int off = s_ptr[i];
 #pragma unroll
@@ -237,6 +239,14 @@ struct EdgeArgs {
   const int* idx;         // [slots] node row of every slot (compact mode: the warps walk the target list, evenly split)
   const int* run_if_gt;   // optional device int: the kernel only runs when *run_if_gt > run_thresh
   int run_thresh;         // (fallback behind the tensor-core table kernel, attn_table.cu)
+  // "needed" row sets (ctrl_need_list_kernel): xrow[node row] = compact row of a node that some later stage reads, -1 else.
+  //   xrow_out: x_out rows are written at xrow_out[row]; targets with -1 are skipped altogether (conv1)
+  //   xrow_src: P / ab hold one row per needed node, indexed by xrow_src[row] (conv2, compact target mode)
+  const int* xrow_out;
+  const int* xrow_src;
+  // CSR lists of graph g live at index graph_id[g * gid_stride] (topology cache of a static graph pool), else at g
+  const int* graph_id;
+  int gid_stride;
 };
 
 // CTA size: 128 threads, 5-6 CTAs per SM (register bound), so that the staging of one CTA overlaps the compute of the
@@ -306,6 +316,7 @@ __global__ void __launch_bounds__(EdgeCfg<TRANSFORMER>::kThreads, EdgeCfg<TRANSF
   const int g = blk / H, h = blk - g * H;
   const float* g_obs = a.obs + (int64_t)g * a.obs_stride;
   const size_t base = (size_t)g * N;
+  const size_t cg = a.graph_id ? (size_t)a.graph_id[(size_t)g * a.gid_stride] : (size_t)g;
   constexpr float kLog2e = 1.4426950408889634f;
   // ---------------------------------------------------------------- phase 0
   {
@@ -321,23 +332,27 @@ __global__ void __launch_bounds__(EdgeCfg<TRANSFORMER>::kThreads, EdgeCfg<TRANSF
     const uint32_t sB32 = (uint32_t)__cvta_generic_to_shared(stB);
     for (int t = tid; t < N * 16; t += kEdgeThreads) {
       const int j = t >> 4, c = t & 15;                     // 16 chunks of 16 B per 128-channel row
-      const bf16* row = a.P + (a.row_key ? (size_t)a.row_key[base + j] : base + j) * a.ldp;
+      size_t pr = base + j;
+      if (a.xrow_src) { const int xr = a.xrow_src[base + j]; if (xr < 0) continue; pr = (size_t)xr; }   // never read: not a source of a target
+      else if (a.row_key) pr = (size_t)a.row_key[base + j];
+      const bf16* row = a.P + pr * a.ldp;
       edge_cp_async16(sA32 + j * (kC * 2) + c * 16, row + src_col + c * 8);
       if (TRANSFORMER) edge_cp_async16(sB32 + j * (kC * 2) + c * 16, row + val_col + c * 8);
       if (!compact) edge_cp_async16(sT32 + j * (kC * 2) + c * 16, row + tgt_col + c * 8);
     }
     {
       const uint32_t sS32 = (uint32_t)__cvta_generic_to_shared(s_src);      // the graph's whole list block (N*32 bytes, 32 B aligned)
-      const uint8_t* gs = a.csr_src + (size_t)g * N * kMaxNbr;
+      const uint8_t* gs = a.csr_src + cg * N * kMaxNbr;
       for (int t = tid; t < N * 2; t += kEdgeThreads) edge_cp_async16(sS32 + t * 16, gs + t * 16);
     }
-    const uint16_t* gp = a.csr_ptr + (size_t)g * (N + 1);
+    const uint16_t* gp = a.csr_ptr + cg * (N + 1);
     for (int t = tid; t <= N; t += kEdgeThreads) s_ptr[t] = gp[t];
     for (int t = tid; t < N; t += kEdgeThreads) {
       s_slot[t] = a.slot ? a.slot[base + t] : -1;
       if (!compact) s_dm[t] = g_obs[t * 8 + 7];
       if (!TRANSFORMER) {
-        const size_t pr = a.row_key ? (size_t)a.row_key[base + t] : base + t;
+        size_t pr = a.row_key ? (size_t)a.row_key[base + t] : base + t;
+        if (a.xrow_src) { const int xr = a.xrow_src[base + t]; pr = xr < 0 ? 0 : (size_t)xr; }
         if (compact) s_a[t] = a.ab[pr * H + h] * (0.6f * kLog2e);
         else {
           s_a[t] = a.ab[pr * (2 * H) + h] * (0.6f * kLog2e);
@@ -379,6 +394,8 @@ __global__ void __launch_bounds__(EdgeCfg<TRANSFORMER>::kThreads, EdgeCfg<TRANSF
     const int i = a.Pt ? reinterpret_cast<const int*>(s_dm)[tk] : tk;
     const int sl = s_slot[i];
     if (a.ctrl_only && sl < 0) continue;
+    long long orow = (long long)(base + i);
+    if (a.xrow_out) { orow = a.xrow_out[base + i]; if (orow < 0) continue; }
     const int r0 = s_ptr[i];
     const int d = (int)s_ptr[i + 1] - r0 + self;            // warp uniform, <= 33
     const int ti = a.Pt ? tk : i;                           // row of the target side in stT / s_b
@@ -460,7 +477,7 @@ __global__ void __launch_bounds__(EdgeCfg<TRANSFORMER>::kThreads, EdgeCfg<TRANSF
     if (grp == 0) {
       uint4 ov;
       ov.x = pack_bf16x2_rn(o[0], o[1]); ov.y = pack_bf16x2_rn(o[2], o[3]); ov.z = pack_bf16x2_rn(o[4], o[5]); ov.w = pack_bf16x2_rn(o[6], o[7]);
-      if (a.x_out) *reinterpret_cast<uint4*>(a.x_out + (base + i) * HC + h * kC + och) = ov;      // 16 lanes: 256 contiguous bytes
+      if (a.x_out) *reinterpret_cast<uint4*>(a.x_out + (size_t)orow * HC + h * kC + och) = ov;     // 16 lanes: 256 contiguous bytes
       if (a.z && sl >= 0 && a.pool_mode < 0) *reinterpret_cast<uint4*>(a.z + (size_t)sl * a.ldz + a.z_col + h * kC + och) = ov;
     }
     if (a.pool_mode >= 0) {
@@ -492,47 +509,95 @@ __global__ void __launch_bounds__(EdgeCfg<TRANSFORMER>::kThreads, EdgeCfg<TRANSF
   }
 }
 
-// ------------------------------------------------------------------------------ controlling nodes
-__global__ void ctrl_list_slot_kernel(const uint8_t* __restrict__ ctrl_mask, const float* __restrict__ obs, int64_t obs_stride,
-                                      int N, int n_graphs, int mode, int* __restrict__ idx, int* __restrict__ slot,
-                                      int* __restrict__ count, int* __restrict__ gfirst, int* __restrict__ gcnt) {
+// ------------------------------------------------------------------------------ controlling nodes + needed rows
+// One warp per graph.
+//   controlling list: idx[slot] = node row, slot[node row] = slot or -1; the slots of a graph's controlling nodes are
+//     consecutive, in node order (gfirst / gcnt; one atomic reservation per graph)
+//   needed rows (two-conv models, adj != NULL): the network reads conv2 only at the controlling nodes
+//     (l_dgn.py:133-139), so conv2's sources -- and therefore the only rows of relu(conv1) anybody reads -- are the
+//     controlling nodes themselves (self loop, snapshot) and their radius-graph sources.  nidx[r] = node row of
+//     needed row r, xrow[node row] = r or -1, consecutive per graph in node order (nfirst / ncnt).
+// mode 1 (agent-observation rows, one controlling node per graph): slot of graph g is g.
+template <int W>
+__global__ void ctrl_need_list_kernel(const uint8_t* __restrict__ ctrl_mask, const float* __restrict__ obs, int64_t obs_stride,
+                                      int N, int n_graphs, int mode, const uint32_t* __restrict__ adj,
+                                      const int* __restrict__ graph_id, int gid_stride, int* __restrict__ idx,
+                                      int* __restrict__ slot, int* __restrict__ count, int* __restrict__ gfirst,
+                                      int* __restrict__ gcnt, int* __restrict__ nidx, int* __restrict__ xrow,
+                                      int* __restrict__ ncount, int* __restrict__ nfirst, int* __restrict__ ncnt) {
   const int lane = threadIdx.x & 31;
   const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (g >= n_graphs) return;
-  if (mode == 1) {
-    if (lane == 0) {
-      float c = obs[(int64_t)g * obs_stride + (int64_t)N * 8];
-      c = fminf(fmaxf(c, 0.f), (float)(N - 1));
-      const int r = g * N + (int)(long long)c;
-      idx[g] = r;
-      slot[r] = g;
-      gfirst[g] = g;
-      gcnt[g] = 1;
-      if (g == 0) *count = n_graphs;
-    }
-    return;
-  }
-  // one reservation per graph: the slots of a graph's controlling nodes are consecutive, in node order
-  // (attn_table.cu walks them with a running pointer)
+  uint32_t cw[W];
   int total = 0;
-  for (int i0 = 0; i0 < N; i0 += 32) {
-    const int i = i0 + lane;
-    total += __popc(__ballot_sync(0xffffffffu, i < N && ctrl_mask[(size_t)g * N + i] != 0));
+  if (mode == 1) {
+    float c = obs[(int64_t)g * obs_stride + (int64_t)N * 8];
+    c = fminf(fmaxf(c, 0.f), (float)(N - 1));
+    const int ci = (int)(long long)c;
+#pragma unroll
+    for (int w = 0; w < W; ++w) cw[w] = (ci >> 5) == w ? 1u << (ci & 31) : 0u;
+    total = 1;
+  } else {
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+      const int i = w * 32 + lane;
+      cw[w] = __ballot_sync(0xffffffffu, i < N && ctrl_mask[(size_t)g * N + i] != 0);
+      total += __popc(cw[w]);
+    }
   }
   int s = 0;
-  if (lane == 0 && total) s = atomicAdd(count, total);
-  s = __shfl_sync(0xffffffffu, s, 0);
+  if (mode == 1) {
+    s = g;
+    if (g == 0 && lane == 0) *count = n_graphs;
+  } else {
+    if (lane == 0 && total) s = atomicAdd(count, total);
+    s = __shfl_sync(0xffffffffu, s, 0);
+  }
   if (lane == 0) { gfirst[g] = s; gcnt[g] = total; }
-  for (int i0 = 0; i0 < N; i0 += 32) {
-    const int i = i0 + lane;
-    const bool c = i < N && ctrl_mask[(size_t)g * N + i] != 0;
-    const uint32_t bal = __ballot_sync(0xffffffffu, c);
-    if (c) {
-      const int t = s + __popc(bal & ((1u << lane) - 1));
-      idx[t] = g * N + i;
-      slot[g * N + i] = t;
+#pragma unroll
+  for (int w = 0; w < W; ++w) {
+    const int i = w * 32 + lane;
+    if (i < N) {
+      const bool c = (cw[w] >> lane) & 1u;
+      const int t = s + __popc(cw[w] & ((1u << lane) - 1));
+      if (c) idx[t] = g * N + i;
+      slot[(size_t)g * N + i] = c ? t : -1;
     }
-    s += __popc(bal);
+    s += __popc(cw[w]);
+  }
+  if (!adj) return;
+  const uint32_t* ga = adj + (graph_id ? (size_t)graph_id[(size_t)g * gid_stride] : (size_t)g) * N * W;
+  uint32_t nw[W];
+#pragma unroll
+  for (int w = 0; w < W; ++w) nw[w] = 0;
+#pragma unroll
+  for (int w = 0; w < W; ++w) {
+    const int i = w * 32 + lane;
+    if ((cw[w] >> lane) & 1u) {
+#pragma unroll
+      for (int v = 0; v < W; ++v) nw[v] |= ga[(size_t)i * W + v];
+    }
+  }
+  int nn = 0;
+#pragma unroll
+  for (int w = 0; w < W; ++w) {
+    nw[w] = __reduce_or_sync(0xffffffffu, nw[w]) | cw[w];
+    nn += __popc(nw[w]);
+  }
+  int ns = 0;
+  if (lane == 0 && nn) ns = atomicAdd(ncount, nn);
+  ns = __shfl_sync(0xffffffffu, ns, 0);
+  if (lane == 0) { nfirst[g] = ns; ncnt[g] = nn; }
+#pragma unroll
+  for (int w = 0; w < W; ++w) {
+    const int i = w * 32 + lane;
+    if (i < N) {
+      const bool c = (nw[w] >> lane) & 1u;
+      const int r = ns + __popc(nw[w] & ((1u << lane) - 1));
+      if (c) nidx[r] = g * N + i;
+      xrow[(size_t)g * N + i] = c ? r : -1;
+    }
+    ns += __popc(nw[w]);
   }
 }
 
@@ -652,17 +717,23 @@ int degree_bits(int n_nodes) { int b = 1; while ((1 << b) < n_nodes) ++b; return
 int table_keys(int n_nodes) { return (1 << degree_bits(n_nodes)) * 512; }     // deg | 6 bits msgs | 3 flag bits
 
 struct WsB {
+  // ---- packed parameters + feature tables (mls_dgn_prepare; offsets independent of the number of graphs)
   bf16 *w_enc1, *w_c1, *w_c2, *w_h0, *w_h1;
   float *b_c1, *b_c2, *b_h0, *b_h1;
-  float *hv1, *hv2, *hd;      // output-layer dot vectors [2*hh] each; per-row dots [T][4]
+  float *hv1, *hv2;           // output-layer dot vectors [2*hh] each
+  float *att1, *att2;
+  bf16 *t_h, *t_x0, *t_P;     // discrete-feature tables: [n_keys][hid], [n_keys][hid], [n_keys][nproj*HC]
+  float* t_ab;                // [n_keys][2H]
+  // ---- per pass
+  float* hd;                  // per-row output dots [T][4]
   bf16 *h, *x0, *P, *x1, *z, *hid1, *hid2;
   float* qg;
   int *idx, *slot, *count, *gfirst, *gcnt;
+  int *nidx, *xrow, *ncount, *nfirst, *ncnt;   // needed rows (conv2 sources)
   uint16_t* csr_ptr;
   uint8_t* csr_src;
-  float *ab, *att1, *att2;
-  bf16 *t_h, *t_x0, *t_P;     // discrete-feature tables: [n_keys][hid], [n_keys][hid], [n_keys][nproj*HC]
-  float* t_ab;                // [n_keys][2H]
+  uint32_t* adjm;             // [graphs][N][W] radius-graph source masks
+  float* ab;
   uint32_t* key;              // [R]
   // tensor-core table attention (attn_table.cu)
   uint32_t* used;             // [n_keys / 32] bitmap
@@ -681,22 +752,28 @@ size_t carve_b(const MlsNetDesc* d, int Gc, unsigned char* base, WsB* ws) {
   const int nproj = d->kind == MLS_NET_DGN_R ? 3 : 2;
   const int latent = hl ? HC : hid + 2 * HC;
   const size_t T = hl ? al((size_t)Gc, 128) : R;
+  const int Wn = mls_words_per_row(d->n_nodes);
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = al(off + bytes); return o; };
+  // parameters and tables first: their offsets must not depend on Gc (MLS_FWD_PREPARED)
   const size_t o_we = take((size_t)hid * hid * 2), o_wc1 = take((size_t)nproj * HC * hid * 2);
   const size_t o_wc2 = take(hl ? 0 : (size_t)nproj * HC * HC * 2), o_wh0 = take((size_t)hh2 * latent * 2);
   const size_t o_wh1 = take((size_t)hh2 * hh2 * 2);
   const size_t o_bc1 = take((size_t)nproj * HC * 4), o_bc2 = take((size_t)nproj * HC * 4), o_bh0 = take(hh2 * 4), o_bh1 = take(hh2 * 4);
   const size_t o_hv1 = take(hh2 * 4), o_hv2 = take(hh2 * 4);
+  const size_t o_att1 = take((size_t)2 * HC * 4), o_att2 = take((size_t)2 * HC * 4);
+  const size_t KT = (size_t)table_keys(d->n_nodes);
+  const size_t o_th = take(KT * hid * 2), o_tx0 = take(KT * hid * 2), o_tP = take(KT * nproj * HC * 2), o_tab = take(KT * 2 * d->heads * 4);
+  // per pass
   const size_t o_h = take(R * hid * 2), o_x0 = take(R * hid * 2), o_P = take(R * nproj * HC * 2);
   const size_t o_x1 = take(hl ? 0 : R * HC * 2), o_z = take(T * latent * 2), o_h1 = take(T * hh2 * 2), o_h2 = take(T * hh2 * 2);
   const size_t o_hd = take(T * 4 * 4);
-  const size_t o_qg = take((size_t)Gc * 8), o_idx = take(R * 4), o_slot = take(R * 4), o_cnt = take(4);
+  const size_t o_qg = take((size_t)Gc * 8), o_idx = take(R * 4), o_slot = take(R * 4), o_cnt = take(8);
   const size_t o_gf = take((size_t)Gc * 4), o_gc = take((size_t)Gc * 4);
+  const size_t o_nidx = take(hl ? 0 : R * 4), o_xrow = take(hl ? 0 : R * 4), o_nf = take(hl ? 0 : (size_t)Gc * 4), o_nc = take(hl ? 0 : (size_t)Gc * 4);
   const size_t o_cptr = take(((size_t)Gc * (d->n_nodes + 1) + 64) * 2), o_csrc = take((size_t)Gc * d->n_nodes * kMaxNbr + 64);
-  const size_t o_ab = take(R * 2 * d->heads * 4), o_att1 = take((size_t)2 * HC * 4), o_att2 = take((size_t)2 * HC * 4);
-  const size_t KT = (size_t)table_keys(d->n_nodes);
-  const size_t o_th = take(KT * hid * 2), o_tx0 = take(KT * hid * 2), o_tP = take(KT * nproj * HC * 2), o_tab = take(KT * 2 * d->heads * 4);
+  const size_t o_adjm = take(hl ? 0 : (size_t)Gc * d->n_nodes * Wn * 4);
+  const size_t o_ab = take(R * 2 * d->heads * 4);
   const size_t o_key = take(R * 4);
   const bool mma_ok = attn_table_supported(d->n_nodes, d->heads);
   const size_t o_used = take(KT), o_cok = take(KT * 2), o_koc = take(kAttnUcap * 4), o_nu = take(4);
@@ -704,15 +781,17 @@ size_t carve_b(const MlsNetDesc* d, int Gc, unsigned char* base, WsB* ws) {
   if (ws) {
     auto B = [&](size_t o) { return reinterpret_cast<bf16*>(base + o); };
     auto F = [&](size_t o) { return reinterpret_cast<float*>(base + o); };
+    auto I = [&](size_t o) { return reinterpret_cast<int*>(base + o); };
     ws->w_enc1 = B(o_we); ws->w_c1 = B(o_wc1); ws->w_c2 = B(o_wc2); ws->w_h0 = B(o_wh0); ws->w_h1 = B(o_wh1);
     ws->b_c1 = F(o_bc1); ws->b_c2 = F(o_bc2); ws->b_h0 = F(o_bh0); ws->b_h1 = F(o_bh1);
     ws->hv1 = F(o_hv1); ws->hv2 = F(o_hv2); ws->hd = F(o_hd);
     ws->h = B(o_h); ws->x0 = B(o_x0); ws->P = B(o_P); ws->x1 = B(o_x1); ws->z = B(o_z); ws->hid1 = B(o_h1); ws->hid2 = B(o_h2);
     ws->qg = F(o_qg);
-    ws->idx = reinterpret_cast<int*>(base + o_idx); ws->slot = reinterpret_cast<int*>(base + o_slot);
-    ws->count = reinterpret_cast<int*>(base + o_cnt);
-    ws->gfirst = reinterpret_cast<int*>(base + o_gf); ws->gcnt = reinterpret_cast<int*>(base + o_gc);
+    ws->idx = I(o_idx); ws->slot = I(o_slot); ws->count = I(o_cnt); ws->ncount = I(o_cnt) + 1;
+    ws->gfirst = I(o_gf); ws->gcnt = I(o_gc);
+    ws->nidx = I(o_nidx); ws->xrow = I(o_xrow); ws->nfirst = I(o_nf); ws->ncnt = I(o_nc);
     ws->csr_ptr = reinterpret_cast<uint16_t*>(base + o_cptr); ws->csr_src = base + o_csrc;
+    ws->adjm = reinterpret_cast<uint32_t*>(base + o_adjm);
     ws->ab = F(o_ab); ws->att1 = F(o_att1); ws->att2 = F(o_att2);
     ws->t_h = B(o_th); ws->t_x0 = B(o_tx0); ws->t_P = B(o_tP); ws->t_ab = F(o_tab); ws->key = reinterpret_cast<uint32_t*>(base + o_key);
     ws->used = reinterpret_cast<uint32_t*>(base + o_used); ws->cid_of_key = reinterpret_cast<uint16_t*>(base + o_cok);
@@ -747,9 +826,117 @@ int launch_edge(cudaStream_t st, const EdgeArgs& ea) {
   return MLS_OK;
 }
 
-int edge_dispatch(cudaStream_t st, const EdgeArgs& ea, bool tr, int Wn) {
-  (void)Wn;
+int edge_dispatch(cudaStream_t st, const EdgeArgs& ea, bool tr) {
   return tr ? launch_edge<true>(st, ea) : launch_edge<false>(st, ea);
+}
+
+// radius_graph lists (+ source bitmasks) of n_graphs graphs whose positions sit in obs-style rows
+int launch_csr(cudaStream_t st, const float* obs, int64_t obs_stride, int N, int n_graphs, uint16_t* csr_ptr, uint8_t* csr_src,
+               uint32_t* adjm) {
+  const int Wn = mls_words_per_row(N);
+  const size_t csm = (size_t)N * Wn * 4 + ((size_t)N + 1) * 4 + (size_t)N * 8;
+  const int thr = N <= 64 ? 64 : 256;           // small graphs: more, smaller CTAs (fewer threads idle at the barriers)
+  switch (Wn) {
+    case 1: graph_csr_kernel<1><<<n_graphs, thr, csm, st>>>(obs, obs_stride, N, n_graphs, csr_ptr, csr_src, adjm); break;
+    case 2: graph_csr_kernel<2><<<n_graphs, thr, csm, st>>>(obs, obs_stride, N, n_graphs, csr_ptr, csr_src, adjm); break;
+    case 4: graph_csr_kernel<4><<<n_graphs, thr, csm, st>>>(obs, obs_stride, N, n_graphs, csr_ptr, csr_src, adjm); break;
+    default: graph_csr_kernel<8><<<n_graphs, thr, csm, st>>>(obs, obs_stride, N, n_graphs, csr_ptr, csr_src, adjm); break;
+  }
+  mls_count_launch();
+  MLS_LAUNCH_CHECK();
+  return MLS_OK;
+}
+
+struct CsrCache {          // layout of the topology cache buffer
+  uint16_t* ptr;
+  uint8_t* src;
+  uint32_t* adjm;
+};
+size_t carve_cache(int N, int G, unsigned char* base, CsrCache* c) {
+  const int Wn = mls_words_per_row(N);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = al(off + bytes); return o; };
+  const size_t o_p = take(((size_t)G * (N + 1) + 64) * 2), o_s = take((size_t)G * N * kMaxNbr + 64), o_a = take((size_t)G * N * Wn * 4);
+  if (c) { c->ptr = reinterpret_cast<uint16_t*>(base + o_p); c->src = base + o_s; c->adjm = reinterpret_cast<uint32_t*>(base + o_a); }
+  return off;
+}
+
+// weights -> bf16 (stacked the way the GEMMs consume them), biases stay fp32; with `tables` the discrete-feature
+// tables (encoder output + conv1 projections of every feature key)
+int pack_parameters(const MlsNetDesc* d, const MlsNetWeights* w, const WsB& ws, bool tables, int sms, cudaStream_t st) {
+  const int N = d->n_nodes, hid = d->hidden, H = d->heads, HC = hid * H, hh = d->head_hidden, hh2 = 2 * hh;
+  const bool hl = d->kind == MLS_NET_HL_DGN, tr = d->kind == MLS_NET_DGN_R;
+  const int nproj = tr ? 3 : 2;
+  const int latent = hl ? HC : hid + 2 * HC;
+  CvtJobs cj{};
+  int n = 0;
+  auto add = [&](const float* src, bf16* dst, int rows, int cols, int ld, int ro, int co) { cj.j[n++] = CvtJob{src, dst, rows, cols, ld, ro, co}; };
+  add(w->enc_w1, ws.w_enc1, hid, hid, hid, 0, 0);
+  add(w->c1_wa, ws.w_c1, HC, hid, hid, 0, 0);
+  add(w->c1_wb, ws.w_c1, HC, hid, hid, HC, 0);
+  if (tr) add(w->c1_wc, ws.w_c1, HC, hid, hid, 2 * HC, 0);
+  cj.n = n;
+  cvt_weights_kernel<<<dim3(64, n), 256, 0, st>>>(cj);
+  CvtJobs c2{};
+  n = 0;
+  auto add2 = [&](const float* src, bf16* dst, int rows, int cols, int ld, int ro, int co) { c2.j[n++] = CvtJob{src, dst, rows, cols, ld, ro, co}; };
+  if (!hl) {
+    add2(w->c2_wa, ws.w_c2, HC, HC, HC, 0, 0);
+    add2(w->c2_wb, ws.w_c2, HC, HC, HC, HC, 0);
+    if (tr) add2(w->c2_wc, ws.w_c2, HC, HC, HC, 2 * HC, 0);
+  }
+  MLS_CUDA(cudaMemsetAsync(ws.w_h1, 0, (size_t)hh2 * hh2 * 2, st));
+  add2(w->q_w0, ws.w_h0, hh, latent, latent, 0, 0);
+  add2(w->v_w0, ws.w_h0, hh, latent, latent, hh, 0);
+  add2(w->q_w1, ws.w_h1, hh, hh, hh2, 0, 0);         // block diagonal: Q and V hidden layers in one GEMM
+  add2(w->v_w1, ws.w_h1, hh, hh, hh2, hh, hh);
+  c2.n = n;
+  cvt_weights_kernel<<<dim3(128, n), 256, 0, st>>>(c2);
+  CatJobs bj{};
+  int m = 0;
+  auto addb = [&](const float* src, float* dst, int cnt) { bj.src[m] = src; bj.dst[m] = dst; bj.n[m] = cnt; ++m; };
+  addb(w->c1_ba, ws.b_c1, HC); addb(w->c1_bb, ws.b_c1 + HC, HC);
+  if (tr) addb(w->c1_bc, ws.b_c1 + 2 * HC, HC);
+  if (!tr) { addb(w->c1_att, ws.att1, HC); addb(w->c1_att, ws.att1 + HC, HC); }
+  addb(w->q_b0, ws.b_h0, hh); addb(w->v_b0, ws.b_h0 + hh, hh);
+  addb(w->q_b1, ws.b_h1, hh); addb(w->v_b1, ws.b_h1 + hh, hh);
+  // output layer as dot vectors for the epilogue of the last hidden-layer GEMM: [wq[0] | wv], [wq[1] | 0]
+  MLS_CUDA(cudaMemsetAsync(ws.hv2, 0, (size_t)hh2 * 4, st));
+  addb(w->q_w2, ws.hv1, hh); addb(w->v_w2, ws.hv1 + hh, hh); addb(w->q_w2 + hh, ws.hv2, hh);
+  bj.count = m;
+  cat_bias_kernel<<<dim3(2, m), 256, 0, st>>>(bj);
+  if (!hl) {
+    CatJobs b2{};
+    m = 0;
+    auto addc = [&](const float* src, float* dst, int cnt) { b2.src[m] = src; b2.dst[m] = dst; b2.n[m] = cnt; ++m; };
+    addc(w->c2_ba, ws.b_c2, HC); addc(w->c2_bb, ws.b_c2 + HC, HC);
+    if (!tr) { addc(w->c2_att, ws.att2, HC); addc(w->c2_att, ws.att2 + HC, HC); }
+    if (tr) addc(w->c2_bc, ws.b_c2 + 2 * HC, HC);
+    b2.count = m;
+    cat_bias_kernel<<<dim3(2, m), 256, 0, st>>>(b2);
+    mls_count_launch();
+  }
+  mls_count_launch(3);
+  MLS_LAUNCH_CHECK();
+  if (tables) {
+    int rc;
+    const int n_keys = table_keys(N);
+    const int rows_per_cta = 256 / (hid / 8);
+    enc0_keys_kernel<<<(n_keys + rows_per_cta - 1) / rows_per_cta, 256, 0, st>>>(n_keys, d->input_dim, w->enc_w0, w->enc_b0, hid, ws.t_h);
+    mls_count_launch();
+    GemmEpilogue e0{ws.t_x0, hid, w->enc_b1, nullptr, 0, N, 1, nullptr, nullptr};
+    if ((rc = gemm_bf16_launch(ws.t_h, hid, ws.w_enc1, hid, GemmShape{n_keys, hid, hid, nullptr}, e0, sms, st))) return rc;
+    GemmEpilogue e1{ws.t_P, nproj * HC, ws.b_c1, nullptr, 0, N, 0, tr ? nullptr : ws.att1, tr ? nullptr : ws.t_ab};
+    if ((rc = gemm_bf16_launch(ws.t_x0, hid, ws.w_c1, hid, GemmShape{n_keys, nproj * HC, hid, nullptr}, e1, sms, st))) return rc;
+  }
+  return MLS_OK;
+}
+
+int sm_count_of_current_device(int* sms) {
+  int dev = 0;
+  MLS_CUDA(cudaGetDevice(&dev));
+  MLS_CUDA(cudaDeviceGetAttribute(sms, cudaDevAttrMultiProcessorCount, dev));
+  return MLS_OK;
 }
 
 }  // namespace
@@ -775,15 +962,34 @@ size_t dgn_workspace_bytes_bf16(const MlsNetDesc* d, int n_graphs) {
   return carve_b(d, bf16_chunk_graphs(d, n_graphs), nullptr, nullptr);
 }
 
+int dgn_prepare_bf16(const MlsNetDesc* d, const MlsNetWeights* w, int flags, void* workspace, size_t workspace_bytes, void* stream) {
+  MLS_CHECK_ARG(d->hidden % 64 == 0 && d->head_hidden % 64 == 0, "bf16 path needs hidden sizes that are multiples of 64");
+  MLS_CHECK_ARG(workspace && workspace_bytes >= carve_b(d, 1, nullptr, nullptr), "workspace too small");
+  int sms = 0, rc;
+  if ((rc = sm_count_of_current_device(&sms))) return rc;
+  WsB ws;
+  carve_b(d, 1, (unsigned char*)workspace, &ws);           // the packed region does not depend on the graph count
+  return pack_parameters(d, w, ws, (flags & MLS_FWD_DISCRETE_FEATURES) != 0, sms, reinterpret_cast<cudaStream_t>(stream));
+}
+
+size_t dgn_csr_cache_bytes(const MlsNetDesc* d, int n_pool_graphs) { return carve_cache(d->n_nodes, n_pool_graphs, nullptr, nullptr); }
+
+int dgn_csr_cache_build(const MlsNetDesc* d, const float* pos_obs, int64_t obs_stride, int n_pool_graphs, void* cache, size_t cache_bytes,
+                        void* stream) {
+  MLS_CHECK_ARG(cache && cache_bytes >= carve_cache(d->n_nodes, n_pool_graphs, nullptr, nullptr), "topology cache buffer too small");
+  CsrCache c;
+  carve_cache(d->n_nodes, n_pool_graphs, (unsigned char*)cache, &c);
+  return launch_csr(reinterpret_cast<cudaStream_t>(stream), pos_obs, obs_stride, d->n_nodes, n_pool_graphs, c.ptr, c.src, c.adjm);
+}
+
 int dgn_forward_bf16(const MlsNetDesc* d, const MlsNetWeights* w, const MlsForwardArgs* a, void* stream) {
   const int N = d->n_nodes, hid = d->hidden, H = d->heads, HC = hid * H, hh = d->head_hidden, hh2 = 2 * hh;
   MLS_CHECK_ARG(hid % 64 == 0 && hh % 64 == 0, "bf16 path needs hidden sizes that are multiples of 64");
   const int Gc = bf16_chunk_graphs(d, a->n_graphs);
   MLS_CHECK_ARG(a->workspace && a->workspace_bytes >= carve_b(d, Gc, nullptr, nullptr), "workspace too small");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  int dev = 0, sms = 0;
-  MLS_CUDA(cudaGetDevice(&dev));
-  MLS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  int sms = 0, rc;
+  if ((rc = sm_count_of_current_device(&sms))) return rc;
   WsB ws;
   carve_b(d, Gc, (unsigned char*)a->workspace, &ws);
   const int Wn = mls_words_per_row(N);
@@ -795,105 +1001,50 @@ int dgn_forward_bf16(const MlsNetDesc* d, const MlsNetWeights* w, const MlsForwa
     MLS_CUDA(cudaMemsetAsync(a->q, 0, (size_t)a->n_graphs * N * 2 * sizeof(float), st));
     if (a->act) MLS_CUDA(cudaMemsetAsync(a->act, 0xFF, (size_t)a->n_graphs * N, st));
   }
-  // ---- weights -> bf16 (stacked the way the GEMMs consume them); biases stay fp32
-  {
-    CvtJobs cj{};
-    int n = 0;
-    auto add = [&](const float* src, bf16* dst, int rows, int cols, int ld, int ro, int co) { cj.j[n++] = CvtJob{src, dst, rows, cols, ld, ro, co}; };
-    add(w->enc_w1, ws.w_enc1, hid, hid, hid, 0, 0);
-    add(w->c1_wa, ws.w_c1, HC, hid, hid, 0, 0);
-    add(w->c1_wb, ws.w_c1, HC, hid, hid, HC, 0);
-    if (tr) add(w->c1_wc, ws.w_c1, HC, hid, hid, 2 * HC, 0);
-    cj.n = n;
-    cvt_weights_kernel<<<dim3(64, n), 256, 0, st>>>(cj);
-    CvtJobs c2{};
-    n = 0;
-    auto add2 = [&](const float* src, bf16* dst, int rows, int cols, int ld, int ro, int co) { c2.j[n++] = CvtJob{src, dst, rows, cols, ld, ro, co}; };
-    if (!hl) {
-      add2(w->c2_wa, ws.w_c2, HC, HC, HC, 0, 0);
-      add2(w->c2_wb, ws.w_c2, HC, HC, HC, HC, 0);
-      if (tr) add2(w->c2_wc, ws.w_c2, HC, HC, HC, 2 * HC, 0);
-    }
-    MLS_CUDA(cudaMemsetAsync(ws.w_h1, 0, (size_t)hh2 * hh2 * 2, st));
-    add2(w->q_w0, ws.w_h0, hh, latent, latent, 0, 0);
-    add2(w->v_w0, ws.w_h0, hh, latent, latent, hh, 0);
-    add2(w->q_w1, ws.w_h1, hh, hh, hh2, 0, 0);         // block diagonal: Q and V hidden layers in one GEMM
-    add2(w->v_w1, ws.w_h1, hh, hh, hh2, hh, hh);
-    c2.n = n;
-    cvt_weights_kernel<<<dim3(128, n), 256, 0, st>>>(c2);
-    CatJobs bj{};
-    int m = 0;
-    auto addb = [&](const float* src, float* dst, int cnt) { bj.src[m] = src; bj.dst[m] = dst; bj.n[m] = cnt; ++m; };
-    if (tr) { addb(w->c1_ba, ws.b_c1, HC); addb(w->c1_bb, ws.b_c1 + HC, HC); addb(w->c1_bc, ws.b_c1 + 2 * HC, HC); }
-    else { addb(w->c1_ba, ws.b_c1, HC); addb(w->c1_bb, ws.b_c1 + HC, HC); }
-    if (!tr) { addb(w->c1_att, ws.att1, HC); addb(w->c1_att, ws.att1 + HC, HC); }
-    addb(w->q_b0, ws.b_h0, hh); addb(w->v_b0, ws.b_h0 + hh, hh);
-    addb(w->q_b1, ws.b_h1, hh); addb(w->v_b1, ws.b_h1 + hh, hh);
-    // output layer as dot vectors for the epilogue of the last hidden-layer GEMM: [wq[0] | wv], [wq[1] | 0]
-    MLS_CUDA(cudaMemsetAsync(ws.hv2, 0, (size_t)hh2 * 4, st));
-    addb(w->q_w2, ws.hv1, hh); addb(w->v_w2, ws.hv1 + hh, hh); addb(w->q_w2 + hh, ws.hv2, hh);
-    bj.count = m;
-    cat_bias_kernel<<<dim3(2, m), 256, 0, st>>>(bj);
-    if (!hl) {
-      CatJobs b2{};
-      m = 0;
-      auto addc = [&](const float* src, float* dst, int cnt) { b2.src[m] = src; b2.dst[m] = dst; b2.n[m] = cnt; ++m; };
-      addc(w->c2_ba, ws.b_c2, HC); addc(w->c2_bb, ws.b_c2 + HC, HC);
-      if (!tr) { addc(w->c2_att, ws.att2, HC); addc(w->c2_att, ws.att2 + HC, HC); }
-      if (tr) addc(w->c2_bc, ws.b_c2 + 2 * HC, HC);
-      b2.count = m;
-      cat_bias_kernel<<<dim3(2, m), 256, 0, st>>>(b2);
-      mls_count_launch();
-    }
-    mls_count_launch(3);
-    MLS_LAUNCH_CHECK();
-  }
+  // discrete-feature mode: encoder + conv1 projections as a table over all feature keys
+  const bool use_table = (a->flags & MLS_FWD_DISCRETE_FEATURES) != 0;
+  if (!(a->flags & MLS_FWD_PREPARED) && (rc = pack_parameters(d, w, ws, use_table, sms, st))) return rc;
   cudaEvent_t ev0 = reinterpret_cast<cudaEvent_t>(a->prof_start), ev1 = reinterpret_cast<cudaEvent_t>(a->prof_stop);
   bool first_chunk = true;
-  int rc;
   auto prof_begin = [&](int which) { if (first_chunk && ev0 && ev1 && a->prof_kernel == which) cudaEventRecord(ev0, st); };
   auto prof_end = [&](int which) { if (first_chunk && ev0 && ev1 && a->prof_kernel == which) cudaEventRecord(ev1, st); };
-  const int use_fused = mls_get_option("fused_conv");
-  // discrete-feature mode: encoder + conv1 projections as a table over all feature keys, built once per call
-  const bool use_table = (a->flags & MLS_FWD_DISCRETE_FEATURES) && !(use_fused && !tr && !hl && N <= 100);
   const int degbits = degree_bits(N), n_keys = table_keys(N);
   if (use_table) {
-    const int rows_per_cta = 256 / (hid / 8);
-    enc0_keys_kernel<<<(n_keys + rows_per_cta - 1) / rows_per_cta, 256, 0, st>>>(n_keys, d->input_dim, w->enc_w0, w->enc_b0, hid, ws.t_h);
-    mls_count_launch();
-    GemmEpilogue e0{ws.t_x0, hid, w->enc_b1, nullptr, 0, N, 1, nullptr, nullptr};
-    if ((rc = gemm_bf16_launch(ws.t_h, hid, ws.w_enc1, hid, GemmShape{n_keys, hid, hid, nullptr}, e0, sms, st))) return rc;
-    GemmEpilogue e1{ws.t_P, nproj * HC, ws.b_c1, nullptr, 0, N, 0, tr ? nullptr : ws.att1, tr ? nullptr : ws.t_ab};
-    if ((rc = gemm_bf16_launch(ws.t_x0, hid, ws.w_c1, hid, GemmShape{n_keys, nproj * HC, hid, nullptr}, e1, sms, st))) return rc;
     if (a->feature_errors) MLS_CUDA(cudaMemsetAsync(a->feature_errors, 0, sizeof(int), st));
     MLS_CUDA(cudaMemsetAsync(ws.used, 0, (size_t)n_keys / 8, st));
   }
-  // conv1 attention through the pair-logit table + tensor-core aggregation (L-DGN / DGN-R, graphs of <= 64 nodes)
+  // conv1 attention through the pair-logit table + tensor-core aggregation (graphs of <= 62 nodes)
   const bool use_mma = use_table && attn_table_supported(N, H) && mls_get_option("attn_mma");
+  // conv2 attention with tensor-core aggregation over the compacted row sets (graphs of <= 64 nodes)
+  const bool use_c2 = !hl && conv2_attn_supported(N, H) && mls_get_option("conv2_mma");
+  // topology cache of a static pool: lists per pool graph, selected by graph id
+  CsrCache cache{};
+  const bool cached = a->csr_cache && a->graph_ids;
+  if (cached) {
+    MLS_CHECK_ARG(a->csr_cache_graphs > 0 && a->graph_id_stride > 0, "topology cache: pool size / graph id stride missing");
+    carve_cache(N, a->csr_cache_graphs, (unsigned char*)const_cast<void*>(a->csr_cache), &cache);
+  }
   for (int g0 = 0; g0 < a->n_graphs; g0 += Gc) {
     const int gc = (a->n_graphs - g0) < Gc ? (a->n_graphs - g0) : Gc;
     const int rows = gc * N;
     const float* obs = a->obs + (int64_t)g0 * a->obs_stride;
     const uint8_t* cm = a->ctrl_mode == 0 ? a->ctrl_mask + (size_t)g0 * N : nullptr;
-    // controlling-node list first: the conv kernels scatter their snapshots through `slot`
+    const int* gid = cached ? a->graph_ids + (size_t)g0 * a->graph_id_stride : nullptr;
+    const int gid_stride = cached ? a->graph_id_stride : 0;
+    const uint16_t* csr_ptr = cached ? cache.ptr : ws.csr_ptr;
+    const uint8_t* csr_src = cached ? cache.src : ws.csr_src;
+    const uint32_t* adjm = cached ? cache.adjm : ws.adjm;
+    // radius graph (unless cached), then the controlling-node list and the needed rows
+    if (!cached && (rc = launch_csr(st, obs, a->obs_stride, N, gc, ws.csr_ptr, ws.csr_src, hl ? nullptr : ws.adjm))) return rc;
     if (!hl) {
-      MLS_CUDA(cudaMemsetAsync(ws.count, 0, sizeof(int), st));
-      MLS_CUDA(cudaMemsetAsync(ws.slot, 0xFF, (size_t)rows * sizeof(int), st));
-      ctrl_list_slot_kernel<<<(gc * 32 + 255) / 256, 256, 0, st>>>(cm, obs, a->obs_stride, N, gc, a->ctrl_mode, ws.idx, ws.slot, ws.count,
-                                                                   ws.gfirst, ws.gcnt);
+      MLS_CUDA(cudaMemsetAsync(ws.count, 0, 2 * sizeof(int), st));
+      const unsigned grid = (unsigned)((gc * 32 + 255) / 256);
+#define MLS_LIST(WW) ctrl_need_list_kernel<WW><<<grid, 256, 0, st>>>(cm, obs, a->obs_stride, N, gc, a->ctrl_mode, adjm, gid, gid_stride, ws.idx, \
+                                                                      ws.slot, ws.count, ws.gfirst, ws.gcnt, ws.nidx, ws.xrow, ws.ncount, ws.nfirst, ws.ncnt)
+      switch (Wn) { case 1: MLS_LIST(1); break; case 2: MLS_LIST(2); break; case 4: MLS_LIST(4); break; default: MLS_LIST(8); break; }
+#undef MLS_LIST
       mls_count_launch();
     }
-    {
-      const size_t csm = (size_t)N * Wn * 4 + ((size_t)N + 1) * 4 + (size_t)N * 8;
-      const int kCsrThreads = N <= 64 ? 64 : 256;           // small graphs: more, smaller CTAs (fewer threads idle at the barriers)
-      switch (Wn) {
-        case 1: graph_csr_kernel<1><<<gc, kCsrThreads, csm, st>>>(obs, a->obs_stride, N, gc, ws.csr_ptr, ws.csr_src); break;
-        case 2: graph_csr_kernel<2><<<gc, kCsrThreads, csm, st>>>(obs, a->obs_stride, N, gc, ws.csr_ptr, ws.csr_src); break;
-        case 4: graph_csr_kernel<4><<<gc, kCsrThreads, csm, st>>>(obs, a->obs_stride, N, gc, ws.csr_ptr, ws.csr_src); break;
-        default: graph_csr_kernel<8><<<gc, kCsrThreads, csm, st>>>(obs, a->obs_stride, N, gc, ws.csr_ptr, ws.csr_src); break;
-      }
-    }
-    mls_count_launch();
     // encoder (or, in discrete-feature mode, just the table keys of this pass)
     if (use_table) {
       feature_key_kernel<<<(rows + 1023) / 1024, 1024, use_mma ? (size_t)(n_keys / 32) * 4 : 0, st>>>(
@@ -906,89 +1057,79 @@ int dgn_forward_bf16(const MlsNetDesc* d, const MlsNetWeights* w, const MlsForwa
       mls_count_launch();
       GemmEpilogue e{ws.x0, hid, w->enc_b1, nullptr, 0, N, 1, nullptr, nullptr};
       if ((rc = gemm_bf16_launch(ws.h, hid, ws.w_enc1, hid, GemmShape{rows, hid, hid, nullptr}, e, sms, st))) return rc;
+      // conv1 projections (table mode: already in ws.t_P for every feature key)
+      GemmEpilogue e1{ws.P, nproj * HC, ws.b_c1, nullptr, 0, N, 0, tr ? nullptr : ws.att1, tr ? nullptr : ws.ab};
+      prof_begin(MLS_PROF_PROJ1);
+      if ((rc = gemm_bf16_launch(ws.x0, hid, ws.w_c1, hid, GemmShape{rows, nproj * HC, hid, nullptr}, e1, sms, st))) return rc;
+      prof_end(MLS_PROF_PROJ1);
     }
-    // fused GATv2 conv (projection GEMM + attention in one kernel) for L-DGN when the graphs fit a 128-row tile
-    const int fusedG = (!tr && !hl && use_fused && N <= 100) ? 100 / N : 0;
-    if (fusedG) {
-      FusedConvArgs fa{};
-      fa.rows = rows; fa.K = hid; fa.N = N; fa.H = H; fa.n_graphs = gc; fa.G = fusedG;
-      fa.proj_bias = ws.b_c1; fa.att = w->c1_att; fa.conv_bias = w->c1_bias; fa.obs = obs; fa.obs_stride = a->obs_stride;
-      fa.scale_rows = 0; fa.csr_ptr = ws.csr_ptr; fa.csr_src = ws.csr_src; fa.slot = ws.slot; fa.ctrl_only = 0;
-      fa.x_out = ws.x1; fa.z = ws.z; fa.ldz = latent; fa.z_col = hid;
+    // conv1 attention (+ReLU): relu(conv1) of the needed rows (compacted, x1), snapshot x1[ctrl] (pre-mask) into z;
+    // HL-DGN: graph pooling into z
+    {
+      EdgeArgs ea{};
+      ea.P = use_table ? ws.t_P : ws.P; ea.ldp = nproj * HC; ea.obs = obs; ea.obs_stride = a->obs_stride; ea.N = N; ea.H = H;
+      ea.n_graphs = gc; ea.row_key = use_table ? ws.key : nullptr;
+      ea.att = w->c1_att; ea.bias = w->c1_bias; ea.csr_ptr = csr_ptr; ea.csr_src = csr_src; ea.ab = use_table ? ws.t_ab : ws.ab;
+      ea.graph_id = gid; ea.gid_stride = gid_stride;
+      if (hl) { ea.x_out = nullptr; ea.slot = nullptr; ea.z = ws.z; ea.ldz = latent; ea.z_col = 0; ea.ctrl_only = 0; ea.pool_mode = d->pool; }
+      else { ea.x_out = ws.x1; ea.slot = ws.slot; ea.z = ws.z; ea.ldz = latent; ea.z_col = hid; ea.ctrl_only = 0; ea.pool_mode = -1; ea.xrow_out = ws.xrow; }
       prof_begin(MLS_PROF_EDGE1);
-      if ((rc = fused_gatv2_conv_launch(ws.x0, ws.w_c1, fa, sms, st))) return rc;
+      if (use_mma) {
+        AttnTableArgs ta{};
+        ta.t_P = ws.t_P; ta.ldp = nproj * HC; ta.t_ab = ws.t_ab; ta.att = w->c1_att; ta.bias = tr ? nullptr : w->c1_bias;
+        ta.transformer = tr ? 1 : 0; ta.key = ws.key; ta.N = N; ta.H = H; ta.n_graphs = gc; ta.csr_ptr = csr_ptr;
+        ta.csr_src = csr_src; ta.graph_id = gid; ta.gid_stride = gid_stride;
+        ta.slot = ws.slot; ta.xrow = ws.xrow; ta.x_out = ws.x1; ta.z = ws.z; ta.ldz = latent; ta.z_col = hid;
+        ta.pool_mode = -1;
+        if (hl) { ta.slot = nullptr; ta.xrow = nullptr; ta.x_out = nullptr; ta.z_col = 0; ta.pool_mode = d->pool; ta.obs = obs; ta.obs_stride = a->obs_stride; }
+        ta.used_bits = ws.used; ta.n_keys = n_keys; ta.cid_of_key = ws.cid_of_key; ta.key_of_cid = ws.key_of_cid;
+        ta.n_used = ws.n_used; ta.E = ws.pairE; ta.row_cid = ws.row_cid; ta.Vh = ws.Vh;
+        if ((rc = attn_table_conv_launch(ta, sms, st))) return rc;
+        ea.run_if_gt = ws.n_used; ea.run_thresh = kAttnUcap;      // more distinct keys than the table holds: gather kernel
+      }
+      if ((rc = edge_dispatch(st, ea, tr))) return rc;
       prof_end(MLS_PROF_EDGE1);
-    } else {
-    // conv1 projections (table mode: already in ws.t_P for every feature key)
-      if (!use_table) {
-        GemmEpilogue e{ws.P, nproj * HC, ws.b_c1, nullptr, 0, N, 0, tr ? nullptr : ws.att1, tr ? nullptr : ws.ab};
-        prof_begin(MLS_PROF_PROJ1);
-        if ((rc = gemm_bf16_launch(ws.x0, hid, ws.w_c1, hid, GemmShape{rows, nproj * HC, hid, nullptr}, e, sms, st))) return rc;
-        prof_end(MLS_PROF_PROJ1);
-      }
-      // conv1 attention (+ReLU); snapshot x1[ctrl] (pre-mask) or HL-DGN pooling
-      {
-        EdgeArgs ea{};
-        ea.P = use_table ? ws.t_P : ws.P; ea.ldp = nproj * HC; ea.obs = obs; ea.obs_stride = a->obs_stride; ea.N = N; ea.H = H;
-        ea.n_graphs = gc; ea.row_key = use_table ? ws.key : nullptr;
-        ea.att = w->c1_att; ea.bias = w->c1_bias; ea.csr_ptr = ws.csr_ptr; ea.csr_src = ws.csr_src; ea.ab = use_table ? ws.t_ab : ws.ab;
-        if (hl) { ea.x_out = nullptr; ea.slot = nullptr; ea.z = ws.z; ea.ldz = latent; ea.z_col = 0; ea.ctrl_only = 0; ea.pool_mode = d->pool; }
-        else { ea.x_out = ws.x1; ea.slot = ws.slot; ea.z = ws.z; ea.ldz = latent; ea.z_col = hid; ea.ctrl_only = 0; ea.pool_mode = -1; }
-        prof_begin(MLS_PROF_EDGE1);
-        if (use_mma) {
-          AttnTableArgs ta{};
-          ta.t_P = ws.t_P; ta.ldp = nproj * HC; ta.t_ab = ws.t_ab; ta.att = w->c1_att; ta.bias = tr ? nullptr : w->c1_bias;
-          ta.transformer = tr ? 1 : 0; ta.key = ws.key; ta.N = N; ta.H = H; ta.n_graphs = gc; ta.csr_ptr = ws.csr_ptr;
-          ta.csr_src = ws.csr_src; ta.slot = ws.slot; ta.x_out = ws.x1; ta.z = ws.z; ta.ldz = latent; ta.z_col = hid;
-          ta.pool_mode = -1;
-          if (hl) { ta.slot = nullptr; ta.x_out = nullptr; ta.z_col = 0; ta.pool_mode = d->pool; ta.obs = obs; ta.obs_stride = a->obs_stride; }
-          ta.used_bits = ws.used; ta.n_keys = n_keys; ta.cid_of_key = ws.cid_of_key; ta.key_of_cid = ws.key_of_cid;
-          ta.n_used = ws.n_used; ta.E = ws.pairE; ta.row_cid = ws.row_cid; ta.Vh = ws.Vh;
-          if ((rc = attn_table_conv_launch(ta, sms, st))) return rc;
-          ea.run_if_gt = ws.n_used; ea.run_thresh = kAttnUcap;      // more distinct keys than the table holds: gather kernel
-        }
-        if ((rc = edge_dispatch(st, ea, tr, Wn))) return rc;
-        prof_end(MLS_PROF_EDGE1);
-      }
     }
     if (!hl) {
-      if (fusedG) {
-        FusedConvArgs fa{};
-        fa.rows = rows; fa.K = HC; fa.N = N; fa.H = H; fa.n_graphs = gc; fa.G = fusedG;
-        fa.proj_bias = ws.b_c2; fa.att = w->c2_att; fa.conv_bias = w->c2_bias; fa.obs = obs; fa.obs_stride = a->obs_stride;
-        fa.scale_rows = 1; fa.csr_ptr = ws.csr_ptr; fa.csr_src = ws.csr_src; fa.slot = ws.slot; fa.ctrl_only = 1;
-        fa.x_out = nullptr; fa.z = ws.z; fa.ldz = latent; fa.z_col = hid + HC;
-        prof_begin(MLS_PROF_EDGE2);
-        if ((rc = fused_gatv2_conv_launch(ws.x1, ws.w_c2, fa, sms, st))) return rc;
-        prof_end(MLS_PROF_EDGE2);
+      // conv2 projections on x1 * dm (the row mask commutes with the GEMM, applied in its epilogue).  Source side
+      // (GATv2 x_l, Transformer k | v) on the needed rows; target side (GATv2 x_r, Transformer q) on the controlling
+      // nodes, whose x1 rows already sit compacted in z (snapshot).  fp16 outputs for the tensor-core attention.
+      const int nsrc = nproj - 1;
+      bf16* Psrc = ws.P;                                    // [needed rows][nsrc*HC]
+      bf16* Ptgt = ws.P + (size_t)rows * nsrc * HC;         // [count][HC]
+      float* dots_t = ws.ab + (size_t)rows * H;             // [count][H]
+      const bf16* w_src = tr ? ws.w_c2 + (size_t)HC * HC : ws.w_c2;            // weight rows: Transformer [q; k; v], GATv2 [l; r]
+      const bf16* w_tgt = tr ? ws.w_c2 : ws.w_c2 + (size_t)HC * HC;
+      const float* b_src = tr ? ws.b_c2 + HC : ws.b_c2;
+      const float* b_tgt = tr ? ws.b_c2 : ws.b_c2 + HC;
+      GemmEpilogue e{Psrc, nsrc * HC, b_src, obs, a->obs_stride, N, 0, tr ? nullptr : ws.att2, tr ? nullptr : ws.ab, ws.nidx};
+      e.c_fp16 = use_c2 ? 1 : 0;
+      prof_begin(MLS_PROF_PROJ2);
+      if ((rc = gemm_bf16_launch(ws.x1, HC, w_src, HC, GemmShape{rows, nsrc * HC, HC, ws.ncount}, e, sms, st))) return rc;
+      prof_end(MLS_PROF_PROJ2);
+      GemmEpilogue et{Ptgt, HC, b_tgt, obs, a->obs_stride, N, 0, tr ? nullptr : ws.att2, tr ? nullptr : dots_t, ws.idx};
+      et.c_fp16 = use_c2 ? 1 : 0;
+      if ((rc = gemm_bf16_launch(ws.z + hid, latent, w_tgt, HC, GemmShape{rows, HC, HC, ws.count}, et, sms, st))) return rc;
+      // conv2 attention only where a controlling agent reads it; the result goes straight into z
+      prof_begin(MLS_PROF_EDGE2);
+      if (use_c2) {
+        Conv2Args ca{};
+        ca.Ps = reinterpret_cast<const __half*>(Psrc); ca.lds = nsrc * HC; ca.Pt = reinterpret_cast<const __half*>(Ptgt); ca.ldt = HC;
+        ca.as = ws.ab; ca.bt = dots_t; ca.att = w->c2_att; ca.bias = tr ? nullptr : w->c2_bias; ca.transformer = tr ? 1 : 0;
+        ca.N = N; ca.H = H; ca.n_graphs = gc; ca.idx = ws.idx; ca.gfirst = ws.gfirst; ca.gcnt = ws.gcnt;
+        ca.nidx = ws.nidx; ca.nfirst = ws.nfirst; ca.ncnt = ws.ncnt; ca.csr_ptr = csr_ptr; ca.csr_src = csr_src;
+        ca.graph_id = gid; ca.gid_stride = gid_stride; ca.z = ws.z; ca.ldz = latent; ca.z_col = hid + HC;
+        if ((rc = conv2_attn_launch(ca, sms, st))) return rc;
       } else {
-      // conv2 projections on x1 * dm (the row mask commutes with the GEMM, applied in its epilogue).  Only the
-      // controlling nodes are conv2 targets, and their x1 rows already sit compacted in z (snapshot): the target
-      // projection (GATv2 x_r, Transformer q) runs on those rows only, the source side on every node.
-        const int nsrc = nproj - 1;                           // GATv2: x_l; Transformer: k | v
-        bf16* Psrc = ws.P;                                    // [rows][nsrc*HC]
-        bf16* Ptgt = ws.P + (size_t)rows * nsrc * HC;         // [count][HC]
-        float* dots_t = ws.ab + (size_t)rows * H;             // [count][H]
-        const bf16* w_src = tr ? ws.w_c2 + (size_t)HC * HC : ws.w_c2;            // weight rows: Transformer [q; k; v], GATv2 [l; r]
-        const bf16* w_tgt = tr ? ws.w_c2 : ws.w_c2 + (size_t)HC * HC;
-        const float* b_src = tr ? ws.b_c2 + HC : ws.b_c2;
-        const float* b_tgt = tr ? ws.b_c2 : ws.b_c2 + HC;
-        GemmEpilogue e{Psrc, nsrc * HC, b_src, obs, a->obs_stride, N, 0, tr ? nullptr : ws.att2, tr ? nullptr : ws.ab, nullptr};
-        prof_begin(MLS_PROF_PROJ2);
-        if ((rc = gemm_bf16_launch(ws.x1, HC, w_src, HC, GemmShape{rows, nsrc * HC, HC, nullptr}, e, sms, st))) return rc;
-        prof_end(MLS_PROF_PROJ2);
-        GemmEpilogue et{Ptgt, HC, b_tgt, obs, a->obs_stride, N, 0, tr ? nullptr : ws.att2, tr ? nullptr : dots_t, ws.idx};
-        if ((rc = gemm_bf16_launch(ws.z + hid, latent, w_tgt, HC, GemmShape{rows, HC, HC, ws.count}, et, sms, st))) return rc;
-        // conv2 attention only where a controlling agent needs it; result goes straight into z
         EdgeArgs ea{};
         ea.P = Psrc; ea.ldp = nsrc * HC; ea.obs = obs; ea.obs_stride = a->obs_stride; ea.N = N; ea.H = H; ea.n_graphs = gc;
         ea.Pt = Ptgt; ea.ldpt = HC; ea.bt = dots_t; ea.gfirst = ws.gfirst; ea.gcnt = ws.gcnt; ea.idx = ws.idx;
-        ea.att = w->c2_att; ea.bias = w->c2_bias; ea.csr_ptr = ws.csr_ptr; ea.csr_src = ws.csr_src; ea.ab = ws.ab; ea.x_out = nullptr; ea.slot = ws.slot; ea.z = ws.z; ea.ldz = latent;
-        ea.z_col = hid + HC; ea.ctrl_only = 1; ea.pool_mode = -1;
-        prof_begin(MLS_PROF_EDGE2);
-        if ((rc = edge_dispatch(st, ea, tr, Wn))) return rc;
-        prof_end(MLS_PROF_EDGE2);
+        ea.att = w->c2_att; ea.bias = w->c2_bias; ea.csr_ptr = csr_ptr; ea.csr_src = csr_src; ea.ab = ws.ab; ea.x_out = nullptr;
+        ea.slot = ws.slot; ea.z = ws.z; ea.ldz = latent; ea.z_col = hid + HC; ea.ctrl_only = 1; ea.pool_mode = -1;
+        ea.xrow_src = ws.xrow; ea.graph_id = gid; ea.gid_stride = gid_stride;
+        if ((rc = edge_dispatch(st, ea, tr))) return rc;
       }
+      prof_end(MLS_PROF_EDGE2);
       dim3 blk(16, 16);
       gather_x0_kernel<<<(rows + 15) / 16, blk, 0, st>>>(ws.idx, ws.count, use_table ? ws.t_x0 : ws.x0, use_table ? ws.key : nullptr, hid, ws.z, latent);
       mls_count_launch();

@@ -13,6 +13,10 @@
 // bf16 tensor-core path (dgn_forward_bf16.cu)
 size_t dgn_workspace_bytes_bf16(const MlsNetDesc* d, int n_graphs);
 int dgn_forward_bf16(const MlsNetDesc* d, const MlsNetWeights* w, const MlsForwardArgs* a, void* stream);
+int dgn_prepare_bf16(const MlsNetDesc* d, const MlsNetWeights* w, int flags, void* workspace, size_t workspace_bytes, void* stream);
+size_t dgn_csr_cache_bytes(const MlsNetDesc* d, int n_pool_graphs);
+int dgn_csr_cache_build(const MlsNetDesc* d, const float* pos_obs, int64_t obs_stride, int n_pool_graphs, void* cache, size_t cache_bytes,
+                        void* stream);
 
 namespace mls {
 

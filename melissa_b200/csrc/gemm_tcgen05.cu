@@ -3,6 +3,9 @@
 // torch.nn.Linear in PyG GATv2Conv / TransformerConv and tianshou MLP
 // (reference l_dgn.py:125,133,142-149; dgn_r.py:105,113; hl_dgn.py:101,111-117).
 #include "gemm_tcgen05.cuh"
+
+#include <cuda_fp16.h>
+
 #include "tcgen05_ptx.cuh"
 
 namespace mls {
@@ -165,9 +168,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             }
           }
           if (epi.relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f); }
-          __nv_bfloat162 p0 = __floats2bfloat162_rn(x0, x1), p1 = __floats2bfloat162_rn(x2, x3);
-          packed[j >> 1] = *reinterpret_cast<uint32_t*>(&p0);
-          packed[(j >> 1) + 1] = *reinterpret_cast<uint32_t*>(&p1);
+          if (epi.c_fp16) {
+            asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(packed[j >> 1]) : "f"(x1), "f"(x0));
+            asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(packed[(j >> 1) + 1]) : "f"(x3), "f"(x2));
+          } else {
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(x0, x1), p1 = __floats2bfloat162_rn(x2, x3);
+            packed[j >> 1] = *reinterpret_cast<uint32_t*>(&p0);
+            packed[(j >> 1) + 1] = *reinterpret_cast<uint32_t*>(&p1);
+          }
         }
         if (epi.C) {
           uint4* dst = reinterpret_cast<uint4*>(stage_out + lane * S::kOutRowBytes + (c0 - cb) * 2);

@@ -36,6 +36,9 @@ struct GemmEpilogue {
   const float* dotvec2;
   float* dots2;
   int dot_relu;
+  // C is written as IEEE fp16 (saturated to +-65504) instead of bf16: 11 significant bits for operands that feed
+  // packed-half math (conv2 attention)
+  int c_fp16;
 };
 
 struct GemmShape {

@@ -76,11 +76,20 @@ class TransformerConvParams(nn.Module):
 
 
 class _Workspace:
+    """Scratch memory of the forward kernels.  Once a CUDA graph has captured a forward (``pinned``), the buffer's
+    address is baked into the graph (and into the TMA descriptors encoded from it), so it must never be replaced:
+    a later call that needs more bytes raises instead of silently freeing memory the graph still replays into."""
+
     def __init__(self):
         self.buf = None
+        self.pinned = False
 
     def get(self, nbytes: int, device):
         if self.buf is None or self.buf.numel() < nbytes or self.buf.device != device:
+            if self.pinned and self.buf is not None:
+                raise _lib.MelissaLibraryError(
+                    f"forward workspace ({self.buf.numel()} bytes) is pinned by a captured CUDA graph but this call needs "
+                    f"{nbytes} bytes: call reserve_workspace(max_graphs) before capturing")
             self.buf = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device)
         return self.buf
 
@@ -102,7 +111,7 @@ class DGNBase(nn.Module):
         self.use_dueling = dueling_param is not None
         self.precision = "fp32"
         self._ws = _Workspace()
-        self._wcache = None
+        self._prepared = None
 
     def _build_heads(self, latent, dueling_param, output_dim):
         if dueling_param is None:
@@ -172,20 +181,86 @@ class DGNBase(nn.Module):
             raise ValueError(f"Expected {expected} feature cols for nodes, got {dim - 1}")
         return bs
 
+    def _param_version(self):
+        """Changes whenever a parameter tensor is written in place or replaced (optimizer step, load_state_dict)."""
+        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def prepare(self, n_graphs: int = 1, *, discrete_features: bool = True):
+        """Pack the parameters into the forward workspace once (bf16 weight matrices, stacked biases and -- with
+        ``discrete_features`` -- the feature tables), so that later forwards skip it (``MLS_FWD_PREPARED``).  Call
+        again after the parameters change (optimizer step / load_state_dict); ``forward_graphs(prepared=True)``
+        checks this with the parameters' version counters and re-packs on its own outside CUDA-graph capture."""
+        if self.precision != "bf16":
+            self._prepared = None
+            return self
+        L = _lib.lib()
+        dev = next(self.parameters()).device
+        desc = self._desc()
+        ws, keep = self.weights_struct()
+        wsp = self.reserve_workspace(max(1, int(n_graphs)), dev) if (self._ws.buf is None or self._ws.buf.device != dev) else self._ws.buf
+        flags = _lib.FWD_DISCRETE_FEATURES if discrete_features else 0
+        _lib.check(L.mls_dgn_prepare(C.byref(desc), C.byref(ws), flags, wsp.data_ptr(), wsp.numel(), _lib.current_stream_ptr()))
+        self._prepared = (self._param_version(), flags, wsp.data_ptr())
+        return self
+
+    def build_topology_cache(self, pool_pos):
+        """radius_graph lists of every graph of a STATIC pool, built once (``mls_dgn_csr_cache_build``).
+        ``pool_pos``: float64/float32 [G, N, 2] node positions (what the environment writes into obs columns 0..1).
+        Returns an opaque cache object for ``forward_graphs(..., graph_ids=, topology_cache=)``."""
+        L = _lib.lib()
+        dev = next(self.parameters()).device
+        pos = torch.as_tensor(pool_pos).to(device=dev)
+        G, N = int(pos.shape[0]), int(pos.shape[1])
+        if N != self.agents_num:
+            raise ValueError("graph pool node count does not match agents_num")
+        rows = torch.zeros(G, N, 8, dtype=torch.float32, device=dev)
+        rows[:, :, 0:2] = pos.to(torch.float32)          # same double -> float rounding as the environment's obs rows
+        desc = self._desc()
+        nbytes = L.mls_dgn_csr_cache_bytes(C.byref(desc), G)
+        buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        _lib.check(L.mls_dgn_csr_cache_build(C.byref(desc), rows.data_ptr(), N * 8, G, buf.data_ptr(), nbytes,
+                                             _lib.current_stream_ptr()))
+        return {"buf": buf, "graphs": G}
+
     def _call(self, obs, stride, n_graphs, ctrl_mode, ctrl_mask, q, act, eps, seed, offset, rand3, offset_dev=None,
-              flags=0, feature_errors=None):
+              flags=0, feature_errors=None, graph_ids=None, graph_id_stride=1, topology_cache=None, prepared=False):
         L = _lib.lib()
         desc = self._desc()
         ws, keep = self.weights_struct()
         nbytes = L.mls_dgn_workspace_bytes(C.byref(desc), n_graphs)
         wsp = self._ws.get(nbytes, obs.device)
+        if prepared and self.precision == "bf16":
+            pf = flags & _lib.FWD_DISCRETE_FEATURES
+            want = (self._param_version(), pf, wsp.data_ptr())
+            if getattr(self, "_prepared", None) != want:
+                if torch.cuda.is_current_stream_capturing():
+                    raise _lib.MelissaLibraryError("parameters changed since prepare(): call prepare() before CUDA-graph capture")
+                _lib.check(L.mls_dgn_prepare(C.byref(desc), C.byref(ws), pf, wsp.data_ptr(), wsp.numel(), _lib.current_stream_ptr()))
+                self._prepared = want
+            flags |= _lib.FWD_PREPARED
         args = _lib.MlsForwardArgs(obs.data_ptr(), stride, n_graphs, ctrl_mode, _lib.ptr(ctrl_mask), q.data_ptr(),
                                    _lib.ptr(act), float(eps), int(flags), int(seed), int(offset), _lib.ptr(rand3),
                                    wsp.data_ptr(), wsp.numel(), None, None, 0, 0, _lib.ptr(offset_dev), _lib.ptr(feature_errors))
+        if topology_cache is not None and graph_ids is not None and self.precision == "bf16":
+            if graph_ids.dtype != torch.int32:
+                raise ValueError("graph_ids must be an int32 tensor")
+            args.graph_ids = graph_ids.data_ptr()
+            args.graph_id_stride = int(graph_id_stride)
+            args.csr_cache_graphs = int(topology_cache["graphs"])
+            args.csr_cache = topology_cache["buf"].data_ptr()
         prof = getattr(self, "_prof", None)
         if prof is not None:          # (cudaEvent start, cudaEvent stop, kernel id), see set_profile_events
             args.prof_start, args.prof_stop, args.prof_kernel = prof[0].cuda_event, prof[1].cuda_event, prof[2]
         _lib.check(L.mls_dgn_forward(C.byref(desc), C.byref(ws), C.byref(args), _lib.current_stream_ptr()))
+
+    def reserve_workspace(self, n_graphs: int, device=None):
+        """Size the forward workspace for passes of up to ``n_graphs`` graphs (call before CUDA-graph capture)."""
+        device = device or next(self.parameters()).device
+        desc = self._desc()
+        return self._ws.get(_lib.lib().mls_dgn_workspace_bytes(C.byref(desc), int(n_graphs)), torch.device(device))
+
+    def pin_workspace(self, pinned: bool = True):
+        self._ws.pinned = bool(pinned)
 
     def set_profile_events(self, kernel: Optional[str], start=None, stop=None):
         """Record ``start``/``stop`` (torch.cuda.Event with timing) around one launch of the named
@@ -218,7 +293,8 @@ class DGNBase(nn.Module):
                        philox_seed: int = 0, philox_offset: int = 0, rand3: Optional[torch.Tensor] = None,
                        q_out: Optional[torch.Tensor] = None, act_out: Optional[torch.Tensor] = None,
                        philox_offset_dev: Optional[torch.Tensor] = None, discrete_features: bool = False,
-                       feature_errors: Optional[torch.Tensor] = None):
+                       feature_errors: Optional[torch.Tensor] = None, graph_ids: Optional[torch.Tensor] = None,
+                       graph_id_stride: int = 1, topology_cache=None, prepared: bool = False):
         """Rollout form: obs_matrix f32 [B, N, 8] (what ``BatchedGraphEnv`` emits), ctrl_mask
         u8 [B, N] (the active set).  One GNN pass per graph; returns (q f32 [B,N,2] -- zero
         where not controlling, act i8 [B,N] -- -1 where not controlling).
@@ -226,7 +302,10 @@ class DGNBase(nn.Module):
         ``discrete_features=True`` (bf16 precision): the caller guarantees that the feature columns hold the
         small integers the environment writes (always true for ``BatchedGraphEnv.obs``); encoder and conv1
         projections are then evaluated once per distinct feature vector instead of once per node.
-        ``feature_errors`` (int32[1] device tensor) receives the number of rows violating that promise."""
+        ``feature_errors`` (int32[1] device tensor) receives the number of rows violating that promise.
+        ``graph_ids`` (int32 device tensor, graph g's pool index at ``graph_ids.flatten()[g * graph_id_stride]``) +
+        ``topology_cache`` (:meth:`build_topology_cache`): static graph pools skip the per-call radius_graph pass.
+        ``prepared=True``: weights / feature tables are packed once per parameter version (:meth:`prepare`)."""
         B, N, F = obs_matrix.shape
         if N != self.agents_num or F != self.input_dim + 3:
             raise ValueError(f"Expected obs_matrix [B, {self.agents_num}, {self.input_dim + 3}], got {tuple(obs_matrix.shape)}")
@@ -236,5 +315,6 @@ class DGNBase(nn.Module):
         if B:
             flags = _lib.FWD_DISCRETE_FEATURES if (discrete_features and self.precision == "bf16") else 0
             self._call(obs_matrix.contiguous(), N * F, B, 0, ctrl_mask.contiguous(), q, act, eps, philox_seed,
-                       philox_offset, rand3, philox_offset_dev, flags, feature_errors)
+                       philox_offset, rand3, philox_offset_dev, flags, feature_errors, graph_ids, graph_id_stride,
+                       topology_cache, prepared)
         return q, act

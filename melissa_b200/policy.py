@@ -144,6 +144,8 @@ class BatchedCollector:
         self.reset()
 
     def reset(self):
+        if self.tuples.count < self.env.B:
+            raise ValueError(f"need at least {self.env.B} reset tuples (one per episode), got {self.tuples.count}")
         first = ResetTuplesDevice.__new__(ResetTuplesDevice)
         first.count = self.env.B
         for k in ("graph_index", "source", "interested", "scripted"):

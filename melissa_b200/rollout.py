@@ -11,6 +11,7 @@ from __future__ import annotations
 import numpy as np
 import torch
 
+from . import _lib
 from .batched_env import BatchedGraphEnv, ResetTuplesDevice
 from .networks.common import DGNBase
 from . import reset_chain
@@ -34,6 +35,15 @@ class Rollout:
         self.graph = None
         # host mirrors for the end-to-end (host buffer) path
         self._host = None
+        # static graph pools: the radius_graph lists of every pool graph are built once and selected per episode by
+        # the graph index the environment keeps on the device (episode[b][MLS_EP_GRAPH])
+        self.topology_cache = None
+        self.graph_ids = None
+        if net is not None:
+            net.reserve_workspace(B, dev)      # full-batch size up front: captured graphs bake the address in
+            if not env.dynamic and net.precision == "bf16":
+                self.topology_cache = net.build_topology_cache(env.pool_pos)
+                self.graph_ids = env.episode.view(-1)[_lib.MLS_EP_GRAPH:]
 
     # ---------------------------------------------------------------- setup helpers
     @staticmethod
@@ -43,6 +53,8 @@ class Rollout:
 
     def start(self, tuples: ResetTuplesDevice, recycle: bool = True):
         """Reset every episode from the first B tuples; finished episodes restart from the pool."""
+        if tuples.count < self.env.B:
+            raise ValueError(f"need at least {self.env.B} reset tuples (one per episode), got {tuples.count}")
         first = ResetTuplesDevice.__new__(ResetTuplesDevice)
         first.count = self.env.B
         first.graph_index, first.source = tuples.graph_index[: self.env.B], tuples.source[: self.env.B]
@@ -60,7 +72,9 @@ class Rollout:
         if self.net is not None:
             self.net.forward_graphs(obs, active, eps=self.eps, philox_seed=self.seed, philox_offset=0,
                                     philox_offset_dev=self.round_dev, q_out=self.q, act_out=self.act,
-                                    discrete_features=self.discrete_features, feature_errors=self.feature_errors)
+                                    discrete_features=self.discrete_features, feature_errors=self.feature_errors,
+                                    graph_ids=self.graph_ids, graph_id_stride=_lib.MLS_EP_STRIDE,
+                                    topology_cache=self.topology_cache, prepared=True)
         env.step_device(self.act)
         self.round_dev.add_(1)
 
@@ -72,6 +86,12 @@ class Rollout:
         else:
             self._round_eager(self.env.obs, self.env.active)
         self.round_index += 1
+
+    def refresh_weights(self):
+        """Re-pack the network parameters after they changed (optimizer step, load_state_dict).  Captured CUDA
+        graphs keep working: they read the packed copies in the (pinned) forward workspace."""
+        if self.net is not None:
+            self.net.prepare(self.env.B, discrete_features=self.discrete_features)
 
     def capture(self, warmup_rounds: int = 2):
         """Capture one round (every kernel of forward + env step) into a CUDA graph.  All buffers
@@ -90,6 +110,8 @@ class Rollout:
             self._round_eager(self.env.obs, self.env.active)
         self.round_index += 1
         self.graph = g
+        if self.net is not None:
+            self.net.pin_workspace()
         return self
 
     def transitions(self) -> int:
@@ -126,7 +148,9 @@ class Rollout:
             self.net.forward_graphs(self._dev_in["obs"][b0:b1], self._dev_in["active"][b0:b1], eps=self.eps,
                                     philox_seed=self.seed + 7919 * i, philox_offset=0, philox_offset_dev=self.round_dev,
                                     q_out=self.q[b0:b1], act_out=self.act[b0:b1],
-                                    discrete_features=self.discrete_features, feature_errors=self.feature_errors)
+                                    discrete_features=self.discrete_features, feature_errors=self.feature_errors,
+                                    graph_ids=None if self.graph_ids is None else self.graph_ids[b0 * _lib.MLS_EP_STRIDE:],
+                                    graph_id_stride=_lib.MLS_EP_STRIDE, topology_cache=self.topology_cache, prepared=True)
         self.env.step_device_slice(self.act[b0:b1], b0, b1)
 
     def capture_host(self, sub_batches: int):
@@ -153,6 +177,8 @@ class Rollout:
                 self._compute_slice(i, b0, b1)
             graphs.append(g)
         self._host_graphs = (S, graphs)
+        if self.net is not None:
+            self.net.pin_workspace()
         return self
 
     def feature_violations(self) -> int:

@@ -9,11 +9,23 @@ import torch
 import torch.distributed as dist
 
 
-def shard_tuples(arrays, rank: int, episodes_per_rank: int):
-    """Every rank reads the same reset-tuple pool but starts at a different offset, so ranks do
-    not replay each other's episodes.  ``arrays``: tuple of numpy arrays with the pool on axis 0."""
-    shift = rank * (episodes_per_rank // 2)
-    return tuple(np.roll(a, -shift, axis=0) for a in arrays)
+def rank_seed_range(base_seed: int, rank: int, pool_count: int):
+    """Env seeds of rank ``rank``'s reset-tuple pool: ``base_seed + rank*pool_count + k`` for k in [0, pool_count).
+    The reference seeds vector env i with ``seed + i`` (tianshou ``venv.seed``); here the global env index runs over
+    all ranks, so the pools of different ranks are disjoint by construction (no rank replays another rank's episodes).
+    -> (first_seed, first_global_index)"""
+    first = int(rank) * int(pool_count)
+    return int(base_seed) + first, first
+
+
+def shard_tuples(arrays, rank: int, episodes_per_rank: int, world: int = 1):
+    """Slice of a SHARED reset-tuple pool owned by ``rank``: rows [rank*P, (rank+1)*P) with
+    P = len(pool) // world >= episodes_per_rank.  Raises when the pool is too small for disjoint slices."""
+    n = len(arrays[0])
+    per = n // max(1, int(world))
+    if per < episodes_per_rank:
+        raise ValueError(f"reset-tuple pool of {n} rows cannot give {world} ranks {episodes_per_rank} disjoint episodes each")
+    return tuple(a[rank * per:(rank + 1) * per] for a in arrays)
 
 
 def reduce_job(ms: float, units: float, device=None):

@@ -17,7 +17,18 @@ import types
 
 import numpy as np
 
-REFERENCE_ROOT = os.environ.get("MELISSA_REFERENCE_ROOT", "/root/reference")
+def _find_reference_root() -> str:
+    """/root/reference in the builder container; on a GPU box the driver may have left an installed copy of the
+    reference under baseline/_ref (git-ignored, travels with the snapshot) -- use it when it holds the env sources."""
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cands = [os.environ.get("MELISSA_REFERENCE_ROOT"), "/root/reference", os.path.join(here, "baseline", "_ref")]
+    for c in cands:
+        if c and os.path.isfile(os.path.join(c, "graph_env", "env", "graph.py")):
+            return c
+    return cands[1]
+
+
+REFERENCE_ROOT = _find_reference_root()
 
 
 def reference_available() -> bool:

@@ -141,7 +141,8 @@ def _gloo_worker(rank, world, port, out_dir):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from melissa_b200.sharding import reduce_job, shard_tuples, whole_job_throughput
     pool = (np.arange(64), np.arange(64) * 2)
-    mine = shard_tuples(pool, rank, 32)
+    mine = shard_tuples(pool, rank, 32, world)
+    assert len(mine[0]) == 32
     ms, units = (10.0, 1000.0) if rank == 0 else (20.0, 3000.0)
     ms_max, total = reduce_job(ms, units)
     thr = whole_job_throughput(ms, units)
@@ -154,7 +155,7 @@ def test_world_size_2_gloo_sharding_and_reduction(tmp_path):
     port = 29500 + (os.getpid() % 1000)
     mp.spawn(_gloo_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     r0, r1 = np.load(tmp_path / "r0.npy"), np.load(tmp_path / "r1.npy")
-    assert r0[0] == 0 and r1[0] == 16 and r1[1] == 32        # rank 1 starts half a shard further into the pool
+    assert r0[0] == 0 and r1[0] == 32 and r1[1] == 64        # disjoint slices of the shared pool
     for r in (r0, r1):
         assert r[2] == 20.0 and r[3] == 4000.0 and r[4] == 4000.0 / 0.020   # max over ranks, sum over ranks
 
