@@ -280,6 +280,43 @@ size_t mls_dgn_csr_cache_bytes(const MlsNetDesc* desc, int32_t n_pool_graphs);
 int mls_dgn_csr_cache_build(const MlsNetDesc* desc, const float* pos_obs, int64_t obs_stride,
                             int32_t n_pool_graphs, void* cache, size_t cache_bytes, void* stream);
 
+/* ===== training step (data-parallel DQN) ================================================
+ * Replaces, for the batched path, the transition bookkeeping of
+ * graph_env/env/utils/collectors/multi_agent_collector.py:240-308 (per-(env, agent) sub-buffers, a transition is
+ * completed by the agent's next observation), tianshou's compute_nstep_return as called by DQNPolicy.process_fn
+ * (estimation_step / discount_factor, l_dgn.py:69-76) and torch.optim.Adam (l_dgn.py:66).  The loss and the
+ * backward pass are host-side torch autograd (melissa_b200/networks/autograd.py); the gradient all-reduce is NCCL
+ * over one flat fp32 buffer (melissa_b200/data_parallel.py). */
+
+/* Observation rows (8 fp32 per node, graph.py:254-271) <-> 12-byte packed nodes {float x, y; uint32 w}:
+ * w bits 0..16 = feature key (has_message | interested << 1 | action << 2 | messages << 3 | degree << 9), bit 31 = dm.
+ * Lossless for observations produced by mls_env_reset / mls_env_step; rows whose feature columns are not the small
+ * integers the environment writes are counted in *errors (device int32, NULL ok) and packed with w = 0. */
+#define MLS_PACKED_NODE_BYTES 12
+int mls_obs_pack(const float* obs /*[rows][8]*/, int64_t n_node_rows, void* packed, int32_t* errors, void* stream);
+/* out row m = frame src_frame[m] (NULL: m) of n_nodes packed nodes expanded to 8 floats each; with `agent`
+ * (device int32 [n_frames]) column 8*n_nodes receives the controlling index (the reference's agent observation). */
+int mls_obs_unpack(const void* packed, const int64_t* src_frame, const int32_t* agent, int32_t n_nodes,
+                   int64_t n_frames, int64_t out_stride /*floats*/, float* out, void* stream);
+
+/* n-step returns over the replay ring rew / flags [ring_rounds][n_episodes][n_nodes] (flags bit 0: the agent acted
+ * in that round, bit 1: terminated after it).  Sample m = (round_index, episode, agent):
+ *   returns[m]    = sum_{k<K} gamma^k rew[(round+k) % ring][episode][agent], K = min(n_step, steps to termination),
+ *                   accumulated in fp64
+ *   boot_round[m] = ring round of the bootstrap observation when the chain is alive after n_step steps, else -1
+ *   boot_gamma[m] = gamma^n_step
+ * The caller samples only transitions whose n-step window is already stored. */
+int mls_nstep_returns(const double* rew, const uint8_t* flags, int32_t ring_rounds, int64_t n_episodes,
+                      int32_t n_nodes, const int32_t* round_index, const int32_t* episode, const int32_t* agent,
+                      int32_t n_samples, int32_t n_step, double gamma, float* returns, int32_t* boot_round,
+                      float* boot_gamma, void* stream);
+
+/* One torch.optim.Adam step (amsgrad = False) over flat fp32 buffers; grad is multiplied by grad_scale first
+ * (1 / world size after the NCCL sum).  step counts from 1. */
+int mls_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                  float beta1, float beta2, float eps, float weight_decay, int64_t step, float grad_scale,
+                  void* stream);
+
 #ifdef __cplusplus
 }
 #endif

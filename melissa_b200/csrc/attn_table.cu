@@ -332,7 +332,6 @@ __global__ void __launch_bounds__(kTThreads, 1) attn_table_mma_kernel(const Attn
       // both operands fp16 (format fields of the kind::f16 descriptor: bits 7-9 A, 10-12 B; 0 = F16; mixing F16 with
       // BF16 is an illegal instruction): the softmax weights live in [0, 1], where fp16 carries 11 significant bits
       // against bf16's 8, and the bf16 value rows convert to fp16 exactly (values_fp16_kernel).  A (values) MN-major.
-      const uint32_t idesc = (make_idesc(128, 64) & ~((7u << 7) | (7u << 10))) | (1u << 15);
       int it = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
         const int s = it & 1;                                                  // shared-memory stage == TMEM buffer
@@ -340,6 +339,11 @@ __global__ void __launch_bounds__(kTThreads, 1) attn_table_mma_kernel(const Attn
         mbar_wait_backoff(full_bar(s), (it >> 1) & 1, 32);
         mbar_wait_backoff(tempty_bar(s), ((it >> 1) & 1) ^ 1, 32);
         tc_fence_after();
+        // the weight matrix holds one row per NEEDED target, compacted (producers): N = their count rounded to 16
+        const int* cnt_s = reinterpret_cast<const int*>(meta + s * kMeta + kMetaSrc + 64);
+        const int nn = cnt_s[0] + cnt_s[1];
+        const int nmma = a.pool_mode >= 0 ? 64 : (nn <= 16 ? 16 : ((nn + 15) & ~15));   // pooling reads all 64 columns
+        const uint32_t idesc = (make_idesc(128, nmma) & ~((7u << 7) | (7u << 10))) | (1u << 15);
         for (int h = 0; h < 4; ++h) {
           const uint64_t dv = make_smem_desc_ex(sB + h * 2 * kBPanel, kBPanel >> 4, 1024 >> 4);
           const uint64_t dw = make_smem_desc(sA + h * kAHead);
@@ -368,15 +372,29 @@ __global__ void __launch_bounds__(kTThreads, 1) attn_table_mma_kernel(const Attn
         if (lane + 32 < rt) xr1 = a.xrow ? a.xrow[m0 + lane + 32] : (int)m0 + lane + 32;
       }
       const uint32_t nm0 = __ballot_sync(0xffffffffu, xr0 >= 0), nm1 = __ballot_sync(0xffffffffu, xr1 >= 0);
-      int xfirst = 0;
-      if (nm0) xfirst = __shfl_sync(0xffffffffu, xr0, __ffs(nm0) - 1);
-      else if (nm1) xfirst = __shfl_sync(0xffffffffu, xr1, __ffs(nm1) - 1);
-      // a graph's slots are consecutive in node order (ctrl_list_slot_kernel): with one graph per tile the
-      // snapshot rows are walked with a running pointer instead of a shuffle per target
+      // TMEM column t = the t-th needed target of the tile (the producers compact the weight rows): lane t gets that
+      // target's x_out row and slot
+      const int n0c = __popc(nm0), nn = a.pool_mode >= 0 ? 64 : n0c + __popc(nm1);
+      int cx0, cx1, cs0, cs1;
+      {
+        auto pick = [&](int v0, int v1, int t) {
+          const bool lo = t < n0c;
+          const unsigned srcl = lo ? __fns(nm0, 0, t + 1) : __fns(nm1, 0, t - n0c + 1);
+          const int a0 = __shfl_sync(0xffffffffu, v0, srcl & 31), a1 = __shfl_sync(0xffffffffu, v1, srcl & 31);
+          return t < nn ? (lo ? a0 : a1) : -1;
+        };
+        cx0 = pick(xr0, xr1, lane); cx1 = pick(xr0, xr1, lane + 32);
+        cs0 = pick(sl0, sl1, lane); cs1 = pick(sl0, sl1, lane + 32);
+      }
+      const uint32_t zc0 = __ballot_sync(0xffffffffu, cs0 >= 0), zc1 = __ballot_sync(0xffffffffu, cs1 >= 0);
+      // a graph's slots are consecutive in node order (ctrl_need_list_kernel): first slot of the tile's first controlling node
       const uint32_t zm0 = __ballot_sync(0xffffffffu, sl0 >= 0), zm1 = __ballot_sync(0xffffffffu, sl1 >= 0);
       int zfirst = 0;
       if (zm0) zfirst = __shfl_sync(0xffffffffu, sl0, __ffs(zm0) - 1);
       else if (zm1) zfirst = __shfl_sync(0xffffffffu, sl1, __ffs(zm1) - 1);
+      int xfirst = 0;
+      if (nm0) xfirst = __shfl_sync(0xffffffffu, xr0, __ffs(nm0) - 1);
+      else if (nm1) xfirst = __shfl_sync(0xffffffffu, xr1, __ffs(nm1) - 1);
       const uint32_t ldz_u = (uint32_t)a.ldz;
       mbar_wait_backoff(tfull_bar(b), (it >> 1) & 1, 64);
       tc_fence_after();
@@ -384,9 +402,11 @@ __global__ void __launch_bounds__(kTThreads, 1) attn_table_mma_kernel(const Attn
 #pragma unroll 1
       for (int q = 0; q < 4; ++q) {
         const int h = pair * 2 + (q >> 1), t0 = (q & 1) * 32;
+        const bool skip = t0 >= nn;                                            // warp uniform: no needed target in this half
         uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(b * 256 + h * 64 + t0), v);
+        if (!skip) tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(b * 256 + h * 64 + t0), v);
         if (q == 3) { tc_fence_before(); mbar_arrive(tempty_bar(b)); }
+        if (skip) continue;
         const int col = h * kC + quarter * 32 + lane;
         if (a.pool_mode >= 0) {
           // lane = channel, registers = the graph's nodes (rows of scripted nodes and rows beyond the graph are
@@ -407,27 +427,28 @@ __global__ void __launch_bounds__(kTThreads, 1) attn_table_mma_kernel(const Attn
         }
         uint16_t* xo = reinterpret_cast<uint16_t*>(a.x_out) + col;
         uint16_t* zo = reinterpret_cast<uint16_t*>(a.z) + a.z_col + col;
+        const int nv = nn - t0;                                                // columns of this half that hold a target
         if (G == 1) {
-          // one graph per tile: its needed rows and its slots are consecutive in node order -> running pointers
-          const uint32_t zm = t0 ? zm1 : zm0, nm = t0 ? nm1 : nm0;
-          uint16_t* zp = zo + (uint32_t)(zfirst + (t0 ? __popc(zm0) : 0)) * ldz_u;   // < 2^31 elements (checked at launch)
-          uint16_t* xp = xo + (size_t)(xfirst + (t0 ? __popc(nm0) : 0)) * HC;
+          // one graph per tile: its needed rows are consecutive (column t -> row xfirst + t: immediate offsets) and so
+          // are its slots (rank among the controlling columns)
+          const uint32_t zc = t0 ? zc1 : zc0;
+          uint16_t* xb = xo + (size_t)(xfirst + t0) * HC;
+          uint16_t* zb = zo + (uint32_t)(zfirst + (t0 ? __popc(zc0) : 0)) * ldz_u;   // < 2^31 elements (checked at launch)
 #pragma unroll
           for (int t = 0; t < 32; ++t) {
-            if ((nm >> t) & 1u) {                                              // warp uniform
+            if (t < nv) {                                                      // warp uniform
               const uint16_t o = relu_bf16(__uint_as_float(v[t]));
-              *xp = o;                                                         // 32 lanes = 64 contiguous bytes
-              xp += HC;
-              if ((zm >> t) & 1u) { *zp = o; zp += ldz_u; }
+              xb[t * HC] = o;                                                  // 32 lanes = 64 contiguous bytes
+              if ((zc >> t) & 1u) zb[(uint32_t)__popc(zc & ((1u << t) - 1u)) * ldz_u] = o;
             }
           }
         } else {
-          const int slv = t0 ? sl1 : sl0, xrv = t0 ? xr1 : xr0;                // -1 beyond the tile's rows
+          const int slv = t0 ? cs1 : cs0, xrv = t0 ? cx1 : cx0;                // -1 beyond the needed columns
 #pragma unroll
           for (int t = 0; t < 32; ++t) {
-            const int xr = __shfl_sync(0xffffffffu, xrv, t);
-            const int sl = __shfl_sync(0xffffffffu, slv, t);
-            if (xr >= 0) {
+            if (t < nv) {
+              const int xr = __shfl_sync(0xffffffffu, xrv, t);
+              const int sl = __shfl_sync(0xffffffffu, slv, t);
               const uint16_t o = relu_bf16(__uint_as_float(v[t]));
               xo[(size_t)xr * HC] = o;
               if (sl >= 0) zo[(uint32_t)sl * ldz_u] = o;
@@ -501,7 +522,7 @@ __global__ void __launch_bounds__(kTThreads, 1) attn_table_mma_kernel(const Attn
       // ---- ... and the normalised softmax weights of (needed target i, head h) as fp16 rows of the head's weight matrix
       const int n_tasks = (cnt_s[0] + cnt_s[1]) * 4;
       for (int tt = pt; tt < n_tasks; tt += kTeam) {
-        const int i = need_s[tt >> 2], h = tt & 3;
+        const int wr = tt >> 2, i = need_s[wr], h = tt & 3;                    // weight row = rank among the needed targets
         if (a.pool_mode >= 0 && dm_s[i] == 0.f) continue;                       // relu(conv) * 0: the row stays all zero
         const int gl = i / N, il = i - gl * N, rbase = gl * N;
         const uint16_t* ptr = ptr_s + gl * (N + 1);
@@ -538,15 +559,15 @@ __global__ void __launch_bounds__(kTThreads, 1) attn_table_mma_kernel(const Attn
         if (cnt <= 8) {
 #pragma unroll
           for (int q = 0; q < 8; ++q)
-            if (q < cnt) *reinterpret_cast<__half*>(arow + a_off(i, jv[q])) = __float2half_rn(ev[q] * inv);
+            if (q < cnt) *reinterpret_cast<__half*>(arow + a_off(wr, jv[q])) = __float2half_rn(ev[q] * inv);
         } else {
           for (int k = 0; k < cnt; ++k) {
             const int j = k >= self ? rbase + src[k - self] : i;
-            *reinterpret_cast<__half*>(arow + a_off(i, j)) = __float2half_rn(f_ex2(__ldg(Erow + (int)cid[j] * 4) - mx) * inv);
+            *reinterpret_cast<__half*>(arow + a_off(wr, j)) = __float2half_rn(f_ex2(__ldg(Erow + (int)cid[j] * 4) - mx) * inv);
           }
         }
-        *reinterpret_cast<uint16_t*>(arow + a_off(i, kb)) = 0x3C00;          // 1.0 (fp16): + bias (hi)
-        *reinterpret_cast<uint16_t*>(arow + a_off(i, kb + 1)) = 0x3C00;      // 1.0 (fp16): + bias (lo)
+        *reinterpret_cast<uint16_t*>(arow + a_off(wr, kb)) = 0x3C00;         // 1.0 (fp16): + bias (hi)
+        *reinterpret_cast<uint16_t*>(arow + a_off(wr, kb + 1)) = 0x3C00;     // 1.0 (fp16): + bias (lo)
       }
       cp_async_wait_all();
       fence_proxy_async();

@@ -56,41 +56,56 @@ __device__ __forceinline__ uint64_t desc_mn(uint32_t smem_addr, uint32_t lbo16, 
   return d;
 }
 
-size_t conv2_smem_bytes(int N, bool tr) {
-  const int edge_cap = (N * (kMaxNbr + 1) + 15) & ~15;
-  return 1024 + kXBytes + kWBytes + (size_t)64 * kRowPad * (tr ? 2 : 1) + 256 /*att*/ + 64 * kMaxNbr /*csr*/ + 16 /*barrier, tmem*/ +
-         512 /*as, bt*/ + (size_t)edge_cap * 4 + 68 * 4 + 72 * 2 + 128 + (size_t)edge_cap * 2;
+struct Conv2Layout {       // shared-memory offsets behind the three 1024-byte aligned MMA operands
+  int edge_cap, t_rows;
+  size_t off_T, off_K, off_att, off_as, off_bt, off_e, off_eptr, off_ent, off_bar, total;
+};
+Conv2Layout conv2_layout(int N, bool tr) {
+  Conv2Layout L;
+  L.edge_cap = (N * (kMaxNbr + 1) + 15) & ~15;
+  L.t_rows = N;
+  size_t o = kXBytes + kWBytes;
+  L.off_T = o; o += (size_t)L.t_rows * kRowPad;
+  L.off_K = o; o += tr ? (size_t)64 * kRowPad : 0;
+  L.off_att = o; o += 256;
+  L.off_as = o; o += 256;
+  L.off_bt = o; o += 256;
+  L.off_e = o; o += (size_t)L.edge_cap * 4;
+  L.off_eptr = o; o += 68 * 4;
+  L.off_ent = o; o += (size_t)L.edge_cap * 2;
+  L.off_bar = o; o += 16;
+  L.total = o + 1024;
+  return L;
 }
 
-template <bool TR>
-__global__ void __launch_bounds__(kThreads, TR ? 3 : 4) conv2_attn_kernel(const Conv2Args a, const int edge_cap) {
+// cp.async group bookkeeping of the pipeline (per item):
+//   group A: target rows, <att, x> dots of the sources   -- free to refill once the logits are done
+//   group B: source rows (MMA operand + logit operand), edge entries -- free once the MMA has completed
+template <bool TR, int LDZ>
+__global__ void __launch_bounds__(kThreads, TR ? 3 : 4) conv2_attn_kernel(const Conv2Args a, const Conv2Layout L) {
   extern __shared__ __align__(16) unsigned char sm_raw[];
   unsigned char* sm = sm_raw + ((1024u - (smem_u32(sm_raw) & 1023u)) & 1023u);
-  unsigned char* sX = sm;                                   // values [source][channel], MN-major SW128 (GATv2: also logit operand)
-  unsigned char* sW = sX + kXBytes;                         // weights [target][source], K-major SW128
-  unsigned char* sT = sW + kWBytes;                         // targets (x_r / q): [64][kRowPad]
-  unsigned char* sK = sT + 64 * kRowPad;                    // Transformer keys: [64][kRowPad] by node
-  unsigned char* p = sK + (TR ? 64 * kRowPad : 0);
-  __half* att_s = reinterpret_cast<__half*>(p); p += 256;
-  uint8_t* s_src = p; p += 64 * kMaxNbr;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(p); p += 8;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p); p += 8;
-  float* s_as = reinterpret_cast<float*>(p); p += 256;
-  float* s_bt = reinterpret_cast<float*>(p); p += 256;
-  float* s_e = reinterpret_cast<float*>(p); p += (size_t)edge_cap * 4;
-  int* s_eptr = reinterpret_cast<int*>(p); p += 68 * 4;
-  uint16_t* s_ptr = reinterpret_cast<uint16_t*>(p); p += 72 * 2;
-  uint8_t* s_tl = p; p += 64;
-  uint8_t* s_nl = p; p += 64;
-  uint8_t* s_esrc = p; p += edge_cap;
-  uint8_t* s_etgt = p;
+  unsigned char* sX = sm;                                   // values [source k][channel], MN-major SW128 (GATv2: also logit operand)
+  unsigned char* sW = sX + kXBytes;                         // weights [target][source k], K-major SW128
+  unsigned char* sT = sm + L.off_T;                         // targets (x_r / q): [cnt][kRowPad]
+  unsigned char* sK = sm + L.off_K;                         // Transformer keys: [k][kRowPad]
+  __half* att_s = reinterpret_cast<__half*>(sm + L.off_att);
+  float* s_as = reinterpret_cast<float*>(sm + L.off_as);    // [k]  <att, x_l[source k]> * 0.6 log2e
+  float* s_bt = reinterpret_cast<float*>(sm + L.off_bt);    // [tk] <att, x_r[target]>  * 0.6 log2e
+  float* s_e = reinterpret_cast<float*>(sm + L.off_e);      // [edge] logit -> 2^(e - max)
+  int* s_eptr = reinterpret_cast<int*>(sm + L.off_eptr);    // [cnt + 1] edge offsets per target
+  uint16_t* s_ent = reinterpret_cast<uint16_t*>(sm + L.off_ent);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sm + L.off_bar);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
 
-  const int N = a.N, H = a.H, HC = H * kC;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int H = a.H, HC = H * kC;
+  const int tid = threadIdx.x, warp = tid >> 5;
   const int h = blockIdx.x % H;                             // gridDim.x is a multiple of H: the head is fixed per CTA
+  const int gstep = gridDim.x / H;
   constexpr float kLog2e = 1.4426950408889634f;
   const float k06 = 0.6f * kLog2e;
   const float tr_scale = kLog2e / sqrtf((float)kC);
+  const int ldz = LDZ > 0 ? LDZ : a.ldz;
 
   // stale value rows only ever meet zero weights, so they just have to stay finite: zero once
   for (int u = tid; u < kXBytes / 16; u += kThreads) reinterpret_cast<uint4*>(sX)[u] = make_uint4(0, 0, 0, 0);
@@ -104,75 +119,67 @@ __global__ void __launch_bounds__(kThreads, TR ? 3 : 4) conv2_attn_kernel(const 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   uint32_t parity = 0;
-  const int self = TR ? 0 : 1;
 
-  for (int g = blockIdx.x / H; g < a.n_graphs; g += gridDim.x / H) {
-    const int cnt = a.gcnt[g];
-    if (cnt == 0) continue;                                  // uniform over the CTA
-    const int first = a.gfirst[g], nf = a.nfirst[g], nc = a.ncnt[g];
-    const int base = g * N;
-    const size_t cg = a.graph_id ? (size_t)a.graph_id[(size_t)g * a.gid_stride] : (size_t)g;
-    const int nmma = cnt <= 16 ? 16 : ((cnt + 15) & ~15);
-    // ---------------------------------------------------------------- stage
-    if (tid < nc) s_nl[tid] = (uint8_t)(a.nidx[nf + tid] - base);
-    if (tid < cnt) {
-      s_tl[tid] = (uint8_t)(a.idx[first + tid] - base);
-      if (!TR) s_bt[tid] = a.bt[(size_t)(first + tid) * H + h] * k06;
+  auto load_meta = [&](int g, int4& m0, int2& m1) {
+    if (g < a.n_graphs) {
+      m0 = __ldg(reinterpret_cast<const int4*>(a.gmeta) + (size_t)g * 2);
+      m1 = __ldg(reinterpret_cast<const int2*>(a.gmeta) + (size_t)g * 4 + 2);
+    } else {
+      m0 = make_int4(0, 0, 0, 0); m1 = make_int2(0, 0);
     }
-    {
-      const uint16_t* gp = a.csr_ptr + cg * (N + 1);
-      for (int t = tid; t <= N; t += kThreads) s_ptr[t] = gp[t];
-      const uint8_t* gs = a.csr_src + cg * N * kMaxNbr;
-      for (int t = tid; t < N * 2; t += kThreads) cp16(s_src + t * 16, gs + t * 16);
-    }
-    for (int u = tid; u < nmma * 8; u += kThreads) reinterpret_cast<uint4*>(sW)[u] = make_uint4(0, 0, 0, 0);
+  };
+  // group A of item (first, cnt, nf, nc): target rows + per-row logit scalars
+  auto issue_A = [&](int first, int cnt, int nf, int nc) {
     for (int t = tid; t < cnt * 16; t += kThreads) {
       const int k = t >> 4, c = t & 15;
       cp16(sT + k * kRowPad + c * 16, a.Pt + (size_t)(first + k) * a.ldt + h * kC + c * 8);
     }
-    __syncthreads();
+    if (!TR) {
+      if (tid < nc) s_as[tid] = __ldg(a.as + (size_t)(nf + tid) * H + h) * k06;
+      if (tid < cnt) s_bt[tid] = __ldg(a.bt + (size_t)(first + tid) * H + h) * k06;
+    }
+  };
+  // group B: source rows (compact index k) + the graph's edge entries and per-target offsets
+  auto issue_B = [&](int first, int cnt, int nf, int nc, int ef, int ne) {
     for (int t = tid; t < nc * 16; t += kThreads) {
-      const int k = t >> 4, c = t & 15, j = s_nl[k];
+      const int k = t >> 4, c = t & 15;
       const __half* row = a.Ps + (size_t)(nf + k) * a.lds + h * kC + c * 8;
-      unsigned char* xd = sX + (c >> 3) * kPanel + j * 128 + (((c & 7) ^ (j & 7)) << 4);
+      unsigned char* xd = sX + (c >> 3) * kPanel + k * 128 + (((c & 7) ^ (k & 7)) << 4);
       if (TR) {
-        cp16(sK + j * kRowPad + c * 16, row);
+        cp16(sK + k * kRowPad + c * 16, row);
         cp16(xd, row + HC);
       } else {
         cp16(xd, row);
       }
     }
-    if (!TR && tid < nc) s_as[s_nl[tid]] = a.as[(size_t)(nf + tid) * H + h] * k06;
-    if (warp == 0) {                                         // edge offsets: exclusive scan of (degree + self) over the targets
-      int run = 0;
-      for (int c0 = 0; c0 < cnt; c0 += 32) {
-        const int tk = c0 + lane;
-        int v = 0;
-        if (tk < cnt) { const int i = s_tl[tk]; v = (int)s_ptr[i + 1] - (int)s_ptr[i] + self; }
-        int incl = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const int t = __shfl_up_sync(0xffffffffu, incl, o);
-          if (lane >= o) incl += t;
-        }
-        if (tk < cnt) s_eptr[tk] = run + incl - v;
-        run += __shfl_sync(0xffffffffu, incl, 31);
-      }
-      if (lane == 0) s_eptr[cnt] = run;
-    }
+    for (int t = tid; t * 8 < ne; t += kThreads) cp16(reinterpret_cast<unsigned char*>(s_ent) + t * 16, a.eent + ef + t * 8);
+    if (tid < cnt) s_eptr[tid] = __ldg(a.eabs + first + tid) - ef;
+    if (tid == 0) s_eptr[cnt] = ne;
+  };
+
+  int g = blockIdx.x / H;
+  int4 m0; int2 m1;
+  load_meta(g, m0, m1);
+  // skip empty graphs
+  while (g < a.n_graphs && m0.y == 0) { g += gstep; load_meta(g, m0, m1); }
+  if (g < a.n_graphs) { issue_A(m0.x, m0.y, m0.z, m0.w); issue_B(m0.x, m0.y, m0.z, m0.w, m1.x, m1.y); }
+
+  while (g < a.n_graphs) {
+    const int first = m0.x, cnt = m0.y, nc = m0.w;
+    const int nmma = cnt <= 16 ? 16 : ((cnt + 15) & ~15);
+    // next non-empty item of this CTA (meta only: two 16-byte loads, long before they are needed)
+    int gn = g + gstep;
+    int4 n0; int2 n1;
+    load_meta(gn, n0, n1);
+    while (gn < a.n_graphs && n0.y == 0) { gn += gstep; load_meta(gn, n0, n1); }
+    for (int u = tid; u < nmma * 8; u += kThreads) reinterpret_cast<uint4*>(sW)[u] = make_uint4(0, 0, 0, 0);
     cp_wait_all();
-    __syncthreads();
-    if (tid < cnt) {                                         // edge list: (source node, target slot) per entry
-      const int i = s_tl[tid], r0 = s_ptr[i], d = (int)s_ptr[i + 1] - r0;
-      int e0 = s_eptr[tid];
-      if (!TR) { s_esrc[e0] = (uint8_t)i; s_etgt[e0] = (uint8_t)tid; ++e0; }
-      for (int k = 0; k < d; ++k) { s_esrc[e0 + k] = s_src[r0 + k]; s_etgt[e0 + k] = (uint8_t)tid; }
-    }
     __syncthreads();
     // ---------------------------------------------------------------- logits: one lane per edge
     const int E = s_eptr[cnt];
     for (int e = tid; e < E; e += kThreads) {
-      const int tk = s_etgt[e], j = s_esrc[e];
+      const uint32_t ent = s_ent[e];
+      const int j = ent & 255u, tk = ent >> 8;
       const unsigned char* tr = sT + tk * kRowPad;
       __half2 acc[4];
 #pragma unroll
@@ -209,6 +216,8 @@ __global__ void __launch_bounds__(kThreads, TR ? 3 : 4) conv2_attn_kernel(const 
       s_e[e] = TR ? s * tr_scale : s + (s_as[j] + s_bt[tk]);
     }
     __syncthreads();
+    // the target rows and logit scalars are dead: refill them with the next item's (overlaps softmax, MMA, epilogue)
+    if (gn < a.n_graphs) issue_A(n0.x, n0.y, n0.z, n0.w);
     // ---------------------------------------------------------------- softmax -> W (4 lanes per target)
     for (int it = 0; it * kThreads < cnt * 4; ++it) {
       const int u = tid + it * kThreads, tk = u >> 2, l = u & 3;
@@ -227,7 +236,7 @@ __global__ void __launch_bounds__(kThreads, TR ? 3 : 4) conv2_attn_kernel(const 
       const float inv = rcpf(sum + 1e-16f);
       unsigned char* wrow = sW + tk * 128;
       for (int x = lo + l; x < hi; x += 4) {
-        const int j = s_esrc[x];
+        const int j = s_ent[x] & 255u;
         *reinterpret_cast<__half*>(wrow + ((((j >> 3) ^ tk) & 7) << 4) + (j & 7) * 2) = __float2half_rn(s_e[x] * inv);
       }
     }
@@ -240,27 +249,31 @@ __global__ void __launch_bounds__(kThreads, TR ? 3 : 4) conv2_attn_kernel(const 
       const uint32_t idesc = (make_idesc(128, nmma) & ~((7u << 7) | (7u << 10))) | (1u << 15);
       const uint64_t dv = desc_mn(smem_u32(sX), kPanel >> 4, 1024 >> 4);
       const uint64_t dw = make_smem_desc(smem_u32(sW));
-      const int ksteps = (N + 15) >> 4;
+      const int ksteps = (nc + 15) >> 4;
       for (int k = 0; k < ksteps; ++k) umma_bf16(tmem_base, dv + (uint64_t)(k * 128), dw + (uint64_t)(k * 2), idesc, k ? 1u : 0u);
       umma_commit(smem_u32(bar));
     }
     mbar_wait(smem_u32(bar), parity);
     parity ^= 1u;
     tc_fence_after();
+    // the source rows, edge entries and offsets are dead: refill them with the next item's (overlaps the epilogue)
+    if (gn < a.n_graphs) issue_B(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y);
     // ---------------------------------------------------------------- epilogue: lane = channel, registers = targets
     {
-      uint16_t* zo = reinterpret_cast<uint16_t*>(a.z) + (size_t)first * a.ldz + a.z_col + h * kC + tid;
+      uint16_t* zo = reinterpret_cast<uint16_t*>(a.z) + (size_t)first * ldz + a.z_col + h * kC + tid;
       for (int c0 = 0; c0 < nmma; c0 += 32) {
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+        uint16_t* zc = zo + (size_t)c0 * ldz;
 #pragma unroll
         for (int t = 0; t < 32; ++t)
-          if (c0 + t < cnt) zo[(size_t)(c0 + t) * a.ldz] = relu_bf16_bits(__uint_as_float(v[t]) + bias_c);
+          if (c0 + t < cnt) zc[t * ldz] = relu_bf16_bits(__uint_as_float(v[t]) + bias_c);
       }
     }
     tc_fence_before();
-    __syncthreads();
+    g = gn; m0 = n0; m1 = n1;
   }
+  cp_wait_all();
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base, kCols);
@@ -268,13 +281,14 @@ __global__ void __launch_bounds__(kThreads, TR ? 3 : 4) conv2_attn_kernel(const 
 
 template <bool TR>
 int launch(const Conv2Args& a, int sm_count, cudaStream_t st) {
-  const size_t smem = conv2_smem_bytes(a.N, TR);
-  const int edge_cap = (a.N * (kMaxNbr + 1) + 15) & ~15;
+  const Conv2Layout L = conv2_layout(a.N, TR);
   static size_t configured = 0;
-  if (smem > configured) {
-    MLS_CUDA(cudaFuncSetAttribute(conv2_attn_kernel<TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    MLS_CUDA(cudaFuncSetAttribute(conv2_attn_kernel<TR>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    configured = smem;
+  if (L.total > configured) {
+    MLS_CUDA(cudaFuncSetAttribute(conv2_attn_kernel<TR, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+    MLS_CUDA(cudaFuncSetAttribute(conv2_attn_kernel<TR, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    MLS_CUDA(cudaFuncSetAttribute(conv2_attn_kernel<TR, 1152>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+    MLS_CUDA(cudaFuncSetAttribute(conv2_attn_kernel<TR, 1152>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    configured = L.total;
   }
   const int per_sm = TR ? 3 : 4;
   long long items = (long long)a.n_graphs * a.H;
@@ -283,7 +297,8 @@ int launch(const Conv2Args& a, int sm_count, cudaStream_t st) {
   if (grid < a.H) grid = a.H;
   if (grid > items) grid = items;                           // items is a multiple of H
   if (grid <= 0) return MLS_OK;
-  conv2_attn_kernel<TR><<<(unsigned)grid, kThreads, smem, st>>>(a, edge_cap);
+  if (a.ldz == 1152) conv2_attn_kernel<TR, 1152><<<(unsigned)grid, kThreads, L.total, st>>>(a, L);   // immediate store offsets
+  else conv2_attn_kernel<TR, 0><<<(unsigned)grid, kThreads, L.total, st>>>(a, L);
   mls_count_launch();
   MLS_LAUNCH_CHECK();
   return MLS_OK;

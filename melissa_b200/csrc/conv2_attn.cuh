@@ -25,18 +25,14 @@ struct Conv2Args {
   const float* bias;     // GATv2 conv bias [H*C]; NULL for the Transformer conv
   int transformer;
   int N, H, n_graphs;
-  // row sets (ctrl_need_list_kernel): the slots / needed rows of graph g are consecutive, in node order
-  const int* idx;        // [slots]       node row of every slot
-  const int* gfirst;     // [graphs]      first slot of the graph
-  const int* gcnt;       // [graphs]      controlling nodes of the graph
-  const int* nidx;       // [needed rows] node row of every needed row
-  const int* nfirst;     // [graphs]
-  const int* ncnt;       // [graphs]
-  // radius-graph source lists (self loops not stored); cg = graph_id ? graph_id[g * gid_stride] : g
-  const uint16_t* csr_ptr;   // [*][N+1]
-  const uint8_t* csr_src;    // [*][N*32]
-  const int* graph_id;
-  int gid_stride;
+  // row sets and edge lists (ctrl_need_list_kernel): the slots / needed rows / edge entries of graph g are consecutive
+  //   gmeta[g] = {first slot, controlling nodes, first needed row, needed rows, first edge entry, edge entries, 0, 0}
+  //   eabs[slot] = position of the slot's first edge entry (its entries run to the next slot's, the last to the block end)
+  //   eent[e]    = compact source index (rank in the graph's needed list) | target index within the graph << 8;
+  //                the GATv2 self loop is an ordinary entry; blocks start 16-byte aligned
+  const int* gmeta;
+  const int* eabs;
+  const uint16_t* eent;
   // output: relu(conv2)[slot] as bf16 at z[slot][z_col + h*C ...]
   __nv_bfloat16* z;
   int ldz, z_col;

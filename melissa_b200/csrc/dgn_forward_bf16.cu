@@ -524,7 +524,10 @@ __global__ void ctrl_need_list_kernel(const uint8_t* __restrict__ ctrl_mask, con
                                       const int* __restrict__ graph_id, int gid_stride, int* __restrict__ idx,
                                       int* __restrict__ slot, int* __restrict__ count, int* __restrict__ gfirst,
                                       int* __restrict__ gcnt, int* __restrict__ nidx, int* __restrict__ xrow,
-                                      int* __restrict__ ncount, int* __restrict__ nfirst, int* __restrict__ ncnt) {
+                                      int* __restrict__ ncount, int* __restrict__ nfirst, int* __restrict__ ncnt,
+                                      const uint16_t* __restrict__ csr_ptr, const uint8_t* __restrict__ csr_src, int self_loops,
+                                      int* __restrict__ ecount, int* __restrict__ eabs, uint16_t* __restrict__ eent,
+                                      int* __restrict__ gmeta) {
   const int lane = threadIdx.x & 31;
   const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (g >= n_graphs) return;
@@ -554,6 +557,7 @@ __global__ void ctrl_need_list_kernel(const uint8_t* __restrict__ ctrl_mask, con
     s = __shfl_sync(0xffffffffu, s, 0);
   }
   if (lane == 0) { gfirst[g] = s; gcnt[g] = total; }
+  const int slot0 = s;
 #pragma unroll
   for (int w = 0; w < W; ++w) {
     const int i = w * 32 + lane;
@@ -588,16 +592,72 @@ __global__ void ctrl_need_list_kernel(const uint8_t* __restrict__ ctrl_mask, con
   if (lane == 0 && nn) ns = atomicAdd(ncount, nn);
   ns = __shfl_sync(0xffffffffu, ns, 0);
   if (lane == 0) { nfirst[g] = ns; ncnt[g] = nn; }
+  {
+    int run = ns;
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+      const int i = w * 32 + lane;
+      if (i < N) {
+        const bool c = (nw[w] >> lane) & 1u;
+        const int r = run + __popc(nw[w] & ((1u << lane) - 1));
+        if (c) nidx[r] = g * N + i;
+        xrow[(size_t)g * N + i] = c ? r : -1;
+      }
+      run += __popc(nw[w]);
+    }
+  }
+  if (!eent) return;
+  // conv2 edge list of the graph, shared by the heads: per controlling node (slot order) one entry per incoming edge
+  // (the GATv2 self loop first), entry = compact source index (rank in the needed list) | target index << 8; the
+  // graph's block starts 16-byte aligned, eabs[slot] = absolute position of the slot's first entry
+  const size_t cg = graph_id ? (size_t)graph_id[(size_t)g * gid_stride] : (size_t)g;
+  const uint16_t* gp = csr_ptr + cg * (N + 1);
+  const uint8_t* gs = csr_src + cg * N * kMaxNbr;
+  int etot = 0;
+  int r0v[W], dv[W], offv[W];
 #pragma unroll
   for (int w = 0; w < W; ++w) {
     const int i = w * 32 + lane;
-    if (i < N) {
-      const bool c = (nw[w] >> lane) & 1u;
-      const int r = ns + __popc(nw[w] & ((1u << lane) - 1));
-      if (c) nidx[r] = g * N + i;
-      xrow[(size_t)g * N + i] = c ? r : -1;
+    const bool c = (cw[w] >> lane) & 1u;
+    r0v[w] = 0; dv[w] = 0;
+    if (c) { r0v[w] = gp[i]; dv[w] = (int)gp[i + 1] - r0v[w]; }
+    const int v = c ? dv[w] + self_loops : 0;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
     }
-    ns += __popc(nw[w]);
+    offv[w] = etot + incl - v;
+    etot += __shfl_sync(0xffffffffu, incl, 31);
+  }
+  int e0 = 0;
+  if (lane == 0 && etot) e0 = atomicAdd(ecount, (etot + 7) & ~7);          // 8 entries of 2 bytes = 16 bytes
+  e0 = __shfl_sync(0xffffffffu, e0, 0);
+  if (lane == 0) {
+    int* gm = gmeta + (size_t)g * 8;
+    gm[0] = slot0; gm[1] = total; gm[2] = ns; gm[3] = nn; gm[4] = e0; gm[5] = etot; gm[6] = 0; gm[7] = 0;
+  }
+  int tk_base = 0;
+#pragma unroll
+  for (int w = 0; w < W; ++w) {
+    const int i = w * 32 + lane;
+    if ((cw[w] >> lane) & 1u) {
+      const int tk = tk_base + __popc(cw[w] & ((1u << lane) - 1));
+      int pos = e0 + offv[w];
+      eabs[slot0 + tk] = pos;
+      auto rank_of = [&](int j) {
+        const int jw = j >> 5;
+        const uint32_t below = (1u << (j & 31)) - 1u;
+        int r = 0;
+#pragma unroll
+        for (int v = 0; v < W; ++v) r += __popc(nw[v] & (v < jw ? 0xffffffffu : (v == jw ? below : 0u)));
+        return r;
+      };
+      if (self_loops) eent[pos++] = (uint16_t)(rank_of(i) | (tk << 8));
+      for (int k = 0; k < dv[w]; ++k) eent[pos + k] = (uint16_t)(rank_of(gs[r0v[w] + k]) | (tk << 8));
+    }
+    tk_base += __popc(cw[w]);
   }
 }
 
@@ -730,6 +790,8 @@ struct WsB {
   float* qg;
   int *idx, *slot, *count, *gfirst, *gcnt;
   int *nidx, *xrow, *ncount, *nfirst, *ncnt;   // needed rows (conv2 sources)
+  int *ecount, *eabs, *gmeta;                  // conv2 edge lists (conv2_attn.cu)
+  uint16_t* eent;
   uint16_t* csr_ptr;
   uint8_t* csr_src;
   uint32_t* adjm;             // [graphs][N][W] radius-graph source masks
@@ -768,7 +830,10 @@ size_t carve_b(const MlsNetDesc* d, int Gc, unsigned char* base, WsB* ws) {
   const size_t o_h = take(R * hid * 2), o_x0 = take(R * hid * 2), o_P = take(R * nproj * HC * 2);
   const size_t o_x1 = take(hl ? 0 : R * HC * 2), o_z = take(T * latent * 2), o_h1 = take(T * hh2 * 2), o_h2 = take(T * hh2 * 2);
   const size_t o_hd = take(T * 4 * 4);
-  const size_t o_qg = take((size_t)Gc * 8), o_idx = take(R * 4), o_slot = take(R * 4), o_cnt = take(8);
+  const size_t o_qg = take((size_t)Gc * 8), o_idx = take(R * 4), o_slot = take(R * 4), o_cnt = take(16);
+  const bool c2 = !hl && conv2_attn_supported(d->n_nodes, d->heads);
+  const size_t o_eabs = take(c2 ? R * 4 : 0), o_gmeta = take(c2 ? (size_t)Gc * 32 : 0);
+  const size_t o_eent = take(c2 ? (R * (kMaxNbr + 1) + (size_t)Gc * 8 + 64) * 2 : 0);
   const size_t o_gf = take((size_t)Gc * 4), o_gc = take((size_t)Gc * 4);
   const size_t o_nidx = take(hl ? 0 : R * 4), o_xrow = take(hl ? 0 : R * 4), o_nf = take(hl ? 0 : (size_t)Gc * 4), o_nc = take(hl ? 0 : (size_t)Gc * 4);
   const size_t o_cptr = take(((size_t)Gc * (d->n_nodes + 1) + 64) * 2), o_csrc = take((size_t)Gc * d->n_nodes * kMaxNbr + 64);
@@ -787,7 +852,8 @@ size_t carve_b(const MlsNetDesc* d, int Gc, unsigned char* base, WsB* ws) {
     ws->hv1 = F(o_hv1); ws->hv2 = F(o_hv2); ws->hd = F(o_hd);
     ws->h = B(o_h); ws->x0 = B(o_x0); ws->P = B(o_P); ws->x1 = B(o_x1); ws->z = B(o_z); ws->hid1 = B(o_h1); ws->hid2 = B(o_h2);
     ws->qg = F(o_qg);
-    ws->idx = I(o_idx); ws->slot = I(o_slot); ws->count = I(o_cnt); ws->ncount = I(o_cnt) + 1;
+    ws->idx = I(o_idx); ws->slot = I(o_slot); ws->count = I(o_cnt); ws->ncount = I(o_cnt) + 1; ws->ecount = I(o_cnt) + 2;
+    ws->eabs = I(o_eabs); ws->gmeta = I(o_gmeta); ws->eent = reinterpret_cast<uint16_t*>(base + o_eent);
     ws->gfirst = I(o_gf); ws->gcnt = I(o_gc);
     ws->nidx = I(o_nidx); ws->xrow = I(o_xrow); ws->nfirst = I(o_nf); ws->ncnt = I(o_nc);
     ws->csr_ptr = reinterpret_cast<uint16_t*>(base + o_cptr); ws->csr_src = base + o_csrc;
@@ -1037,10 +1103,11 @@ int dgn_forward_bf16(const MlsNetDesc* d, const MlsNetWeights* w, const MlsForwa
     // radius graph (unless cached), then the controlling-node list and the needed rows
     if (!cached && (rc = launch_csr(st, obs, a->obs_stride, N, gc, ws.csr_ptr, ws.csr_src, hl ? nullptr : ws.adjm))) return rc;
     if (!hl) {
-      MLS_CUDA(cudaMemsetAsync(ws.count, 0, 2 * sizeof(int), st));
+      MLS_CUDA(cudaMemsetAsync(ws.count, 0, 4 * sizeof(int), st));
       const unsigned grid = (unsigned)((gc * 32 + 255) / 256);
 #define MLS_LIST(WW) ctrl_need_list_kernel<WW><<<grid, 256, 0, st>>>(cm, obs, a->obs_stride, N, gc, a->ctrl_mode, adjm, gid, gid_stride, ws.idx, \
-                                                                      ws.slot, ws.count, ws.gfirst, ws.gcnt, ws.nidx, ws.xrow, ws.ncount, ws.nfirst, ws.ncnt)
+                                                                      ws.slot, ws.count, ws.gfirst, ws.gcnt, ws.nidx, ws.xrow, ws.ncount, ws.nfirst, ws.ncnt, \
+                                                                      csr_ptr, csr_src, tr ? 0 : 1, ws.ecount, ws.eabs, use_c2 ? ws.eent : nullptr, ws.gmeta)
       switch (Wn) { case 1: MLS_LIST(1); break; case 2: MLS_LIST(2); break; case 4: MLS_LIST(4); break; default: MLS_LIST(8); break; }
 #undef MLS_LIST
       mls_count_launch();
@@ -1116,9 +1183,8 @@ int dgn_forward_bf16(const MlsNetDesc* d, const MlsNetWeights* w, const MlsForwa
         Conv2Args ca{};
         ca.Ps = reinterpret_cast<const __half*>(Psrc); ca.lds = nsrc * HC; ca.Pt = reinterpret_cast<const __half*>(Ptgt); ca.ldt = HC;
         ca.as = ws.ab; ca.bt = dots_t; ca.att = w->c2_att; ca.bias = tr ? nullptr : w->c2_bias; ca.transformer = tr ? 1 : 0;
-        ca.N = N; ca.H = H; ca.n_graphs = gc; ca.idx = ws.idx; ca.gfirst = ws.gfirst; ca.gcnt = ws.gcnt;
-        ca.nidx = ws.nidx; ca.nfirst = ws.nfirst; ca.ncnt = ws.ncnt; ca.csr_ptr = csr_ptr; ca.csr_src = csr_src;
-        ca.graph_id = gid; ca.gid_stride = gid_stride; ca.z = ws.z; ca.ldz = latent; ca.z_col = hid + HC;
+        ca.N = N; ca.H = H; ca.n_graphs = gc; ca.gmeta = ws.gmeta; ca.eabs = ws.eabs; ca.eent = ws.eent;
+        ca.z = ws.z; ca.ldz = latent; ca.z_col = hid + HC;
         if ((rc = conv2_attn_launch(ca, sms, st))) return rc;
       } else {
         EdgeArgs ea{};

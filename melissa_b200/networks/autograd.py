@@ -1,0 +1,141 @@
+"""Differentiable forward of the three Q-networks for the TRAINING step (loss + backward through torch autograd).
+
+The rollout forward is hand-written CUDA (``mls_dgn_forward``) and has no backward; a gradient step needs one.  This
+module evaluates the same math with torch ops over the module's own parameters, so ``loss.backward()`` fills their
+``.grad`` ("v1 can use autograd").  Reference math: ``networks/{l_dgn.py:92-151,
+dgn_r.py:82-129, hl_dgn.py:82-119}``, ``networks/common.py:6-64`` and the PyG / tianshou ops they call (SURVEY.md
+Appendix B).  It is a product module -- it never imports ``oracle`` -- and follows the structure of the CUDA path
+rather than PyG's: one agent observation controls ONE node, so only the rows that node reads are evaluated
+
+    conv2 at the controlling node c          <- sources  S1 = {c} + radius-neighbours(c)
+    conv1 at the nodes of S1 (x1 rows)       <- sources  S2 = S1 + their radius-neighbours
+
+as edge lists over (sample, target, source) triples with scatter softmax; the dense layers are plain ``F.linear``.
+Runs wherever the parameters live (the training loop keeps them on the GPU).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn.functional as F
+
+R2 = float(torch.tensor(0.2, dtype=torch.float64).pow(2).to(torch.float32))     # torch_cluster: r*r narrowed to fp32
+MAX_NUM_NEIGHBORS = 32
+
+
+def split_rows(obs: torch.Tensor, n_agents: int, input_dim: int = 5):
+    """networks/common.py:20-44,63: agent rows [bs, N*(F+3)+1] -> pos, feats, dm, ctrl."""
+    if obs.ndim != 2:
+        raise ValueError(f"Expected obs to be 2D, but got shape {obs.shape}")
+    bs, dim = obs.shape
+    d = input_dim + 3
+    if dim - 1 != n_agents * d:
+        raise ValueError(f"Expected {n_agents * d} feature cols for nodes, got {dim - 1}")
+    node = obs[:, : dim - 1].reshape(bs, n_agents, d).float()
+    return node[..., :2], node[..., 2:-1], node[..., -1:], obs[:, -1].clamp(0, n_agents - 1).long()
+
+
+def radius_mask(pos: torch.Tensor) -> torch.Tensor:
+    """radius_graph(pos, r=0.2, loop=False, max_num_neighbors=32) as bool [bs, target i, source j]: candidates in
+    index order, kept while fma(dy, dy, dx*dx) < r^2 in fp32, the scan stops after 33 hits (self included)."""
+    p = pos.to(torch.float32)
+    dx = p[:, None, :, 0] - p[:, :, None, 0]
+    dy = p[:, None, :, 1] - p[:, :, None, 1]
+    d2 = (dy.double() * dy.double() + (dx * dx).double()).float()
+    hit = d2 < R2
+    hit = hit & (hit.cumsum(dim=2) <= MAX_NUM_NEIGHBORS + 1)
+    n = p.shape[1]
+    return hit & ~torch.eye(n, dtype=torch.bool, device=p.device)
+
+
+def _segment_softmax(e: torch.Tensor, seg: torch.Tensor, n_seg: int) -> torch.Tensor:
+    """PyG utils.softmax: exp(e - max_seg) / (sum_seg + 1e-16); e [E, H], seg [E] segment id per edge."""
+    H = e.shape[1]
+    idx = seg[:, None].expand(-1, H)
+    mx = torch.full((n_seg, H), -torch.inf, dtype=e.dtype, device=e.device).scatter_reduce(0, idx, e.detach(), "amax", include_self=True)
+    ex = (e - mx[seg]).exp()
+    den = torch.zeros(n_seg, H, dtype=e.dtype, device=e.device).index_add_(0, seg, ex)
+    return ex / (den[seg] + 1e-16)
+
+
+def _edges(mask: torch.Tensor, targets: torch.Tensor, self_loops: bool):
+    """Edge list (sample m, target i, source j) of ``mask`` [bs, i, j] restricted to target rows where ``targets``
+    [bs, N] is set (+ a self loop per such target)."""
+    m = mask & targets[:, :, None]
+    if self_loops:
+        m = m | (torch.eye(mask.shape[1], dtype=torch.bool, device=mask.device)[None] & targets[:, :, None])
+    return torch.nonzero(m, as_tuple=True)
+
+
+def _gatv2(conv, x, edges, heads, N):
+    """PyG GATv2Conv(concat=True, negative_slope=0.2, add_self_loops=True, share_weights=False) on an edge list.
+    x [bs, N, D]; returns [bs*N, H*C] with rows of non-target nodes = bias only (never read)."""
+    sm, ti, sj = edges
+    bs = x.shape[0]
+    C = conv.att.shape[-1]
+    xl = conv.lin_l(x).view(bs * N, heads, C)
+    xr = conv.lin_r(x).view(bs * N, heads, C)
+    tgt, src = sm * N + ti, sm * N + sj
+    s = F.leaky_relu(xl[src] + xr[tgt], 0.2)
+    e = (s * conv.att.view(1, heads, C)).sum(-1)
+    a = _segment_softmax(e, tgt, bs * N)
+    out = torch.zeros(bs * N, heads, C, dtype=x.dtype, device=x.device).index_add_(0, tgt, a[:, :, None] * xl[src])
+    return out.view(bs * N, heads * C) + conv.bias
+
+
+def _transformer(conv, x, edges, heads, N):
+    """PyG TransformerConv(root_weight=False, beta=False): no self loops, no output bias, ``lin_skip`` unused."""
+    sm, ti, sj = edges
+    bs = x.shape[0]
+    HC = conv.lin_query.out_features
+    C = HC // heads
+    q = conv.lin_query(x).view(bs * N, heads, C)
+    k = conv.lin_key(x).view(bs * N, heads, C)
+    v = conv.lin_value(x).view(bs * N, heads, C)
+    tgt, src = sm * N + ti, sm * N + sj
+    e = (q[tgt] * k[src]).sum(-1) / math.sqrt(C)
+    a = _segment_softmax(e, tgt, bs * N)
+    out = torch.zeros(bs * N, heads, C, dtype=x.dtype, device=x.device).index_add_(0, tgt, a[:, :, None] * v[src])
+    return out.view(bs * N, HC)
+
+
+def _mlp(params, x):
+    return params.model(x)
+
+
+def _dueling(net, z):
+    q = _mlp(net.Q, z)
+    if not net.use_dueling:
+        return q
+    v = _mlp(net.V, z)
+    return q - q.mean(dim=1, keepdim=True) + v
+
+
+def q_values(net, obs_rows: torch.Tensor) -> torch.Tensor:
+    """Q-values [bs, 2] of agent-observation rows [bs, 8N+1] (last column = controlling index), differentiable
+    with respect to ``net``'s parameters."""
+    N, heads = net.agents_num, net.num_heads
+    pos, feats, dm, ctrl = split_rows(obs_rows, N, net.input_dim)
+    bs = obs_rows.shape[0]
+    mask = radius_mask(pos)
+    ar = torch.arange(bs, device=obs_rows.device)
+    x0 = F.relu(_mlp(net.encoder, feats))                                       # [bs, N, hid]
+    kind = net.KIND
+    if kind == "hl_dgn":
+        every = torch.ones(bs, N, dtype=torch.bool, device=obs_rows.device)
+        x1 = F.relu(_gatv2(net.conv1, x0, _edges(mask, every, True), heads, N)).view(bs, N, -1) * dm
+        agg = net.aggregator_name
+        z = x1.amax(dim=1) if agg == "max" else (x1.mean(dim=1) if agg == "mean" else x1.sum(dim=1))
+        return _dueling(net, z)
+    tr = kind == "dgn_r"
+    conv = _transformer if tr else _gatv2
+    is_ctrl = torch.zeros(bs, N, dtype=torch.bool, device=obs_rows.device)
+    is_ctrl[ar, ctrl] = True
+    s1 = is_ctrl | mask[ar, ctrl]                                               # conv2 sources = conv1 targets
+    x1 = F.relu(conv(net.conv1, x0, _edges(mask, s1, not tr), heads, N)).view(bs, N, -1)
+    snap1, snap2 = x0[ar, ctrl], x1[ar, ctrl]                                   # x1 snapshot is taken BEFORE the dm mask
+    x1 = x1 * dm
+    x2 = F.relu(conv(net.conv2, x1, _edges(mask, is_ctrl, not tr), heads, N)).view(bs, N, -1)
+    z = torch.cat([snap1, snap2, x2[ar, ctrl]], dim=1)
+    return _dueling(net, z)

@@ -182,8 +182,27 @@ class DGNBase(nn.Module):
         return bs
 
     def _param_version(self):
-        """Changes whenever a parameter tensor is written in place or replaced (optimizer step, load_state_dict)."""
-        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+        """Changes whenever a parameter tensor is written in place or replaced (optimizer step, load_state_dict), or
+        when a kernel that writes the parameters behind torch's back says so (:meth:`mark_parameters_changed`)."""
+        return (getattr(self, "_manual_version", 0),) + tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def mark_parameters_changed(self):
+        self._manual_version = getattr(self, "_manual_version", 0) + 1
+
+    def clone_for_target(self):
+        """A detached copy for the DQN target network (tianshou: ``deepcopy(model)``) with its own, still
+        unallocated, forward workspace."""
+        import copy
+        ws, prof = self._ws, getattr(self, "_prof", None)
+        self._ws, self._prof = _Workspace(), None
+        try:
+            twin = copy.deepcopy(self)
+        finally:
+            self._ws, self._prof = ws, prof
+        twin._prepared = None
+        for p in twin.parameters():
+            p.requires_grad_(False)
+        return twin
 
     def prepare(self, n_graphs: int = 1, *, discrete_features: bool = True):
         """Pack the parameters into the forward workspace once (bf16 weight matrices, stacked biases and -- with
