@@ -311,9 +311,7 @@ def run_ours(args):
         if args.e2e_sub_batches > 1 and use_graph:
             ro.capture_host(args.e2e_sub_batches)    # one CUDA graph per episode slice
         prepare(False)
-        ro._host["obs"].copy_(env.obs)
-        ro._host["active"].copy_(env.active)
-        torch.cuda.synchronize()
+        ro.sync_host()
         # rounds are issued back to back: slice i of round k+1 waits only for slice i of round k to be back on the
         # host (the dependency of a caller feeding observations back); the timed region ends when the last copy lands
         pipelined = args.e2e_sub_batches > 1

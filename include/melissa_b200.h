@@ -242,6 +242,9 @@ typedef struct MlsForwardArgs {
   int32_t graph_id_stride;   /* in int32 elements (MLS_EP_STRIDE when pointing at episode[b][MLS_EP_GRAPH]) */
   int32_t csr_cache_graphs;  /* pool size the cache was built for */
   const void* csr_cache;
+  /* added to the output-row index that keys the exploration draw (Philox counter = row): a caller that processes a
+   * batch in slices passes the slice's first row so that the draws equal those of one full-batch call */
+  uint64_t philox_row0;
 } MlsForwardArgs;
 
 /* The caller guarantees that obs columns 2..6 (degree, messages transmitted, last action, interested,

@@ -79,7 +79,8 @@ class MlsForwardArgs(C.Structure):
                 ("philox_seed", C.c_uint64), ("philox_offset", C.c_uint64), ("rand3", vp), ("workspace", vp),
                 ("workspace_bytes", C.c_size_t), ("prof_start", vp), ("prof_stop", vp), ("prof_kernel", C.c_int32),
                 ("pad2_", C.c_int32), ("philox_offset_dev", vp), ("feature_errors", vp),
-                ("graph_ids", vp), ("graph_id_stride", C.c_int32), ("csr_cache_graphs", C.c_int32), ("csr_cache", vp)]
+                ("graph_ids", vp), ("graph_id_stride", C.c_int32), ("csr_cache_graphs", C.c_int32), ("csr_cache", vp),
+                ("philox_row0", C.c_uint64)]
 
 
 FWD_DISCRETE_FEATURES = 1

@@ -246,7 +246,7 @@ constexpr int kStageB = 8 * kBPanel;           // 64 KiB
 constexpr int kStage = kStageA + kStageB;      // 96 KiB
 constexpr int kMetaSrc = 64 * kMaxNbr;         // CSR source lists of a tile
 constexpr int kMeta = kMetaSrc + 64 * 4 /*keys*/ + 64 * 2 /*ids*/ + 128 * 2 /*CSR row pointers*/ + 64 * 4 /*dm*/;
-constexpr int kTSmem = 2 * kStage + 2 * kMeta + 256 /*barriers*/ + 1024;
+constexpr int kTSmem = 2 * kStage + 2 * kMeta + 256 /*barriers*/ + 512 /*epilogue row tables*/ + 1024;
 
 __device__ __forceinline__ float f_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float f_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -286,6 +286,8 @@ __global__ void __launch_bounds__(kTThreads, 1) attn_table_mma_kernel(const Attn
   unsigned char* meta = smem + 2 * kStage;                                        // [2][kMeta]
   uint64_t* bars = reinterpret_cast<uint64_t*>(meta + 2 * kMeta);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  int* tab_x = reinterpret_cast<int*>(meta + 2 * kMeta + 256);               // [64] x_out row of TMEM column t (this tile)
+  int* tab_s = tab_x + 64;                                                     // [64] snapshot slot of TMEM column t or -1
   const uint32_t bar0 = smem_u32(bars);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (2 + s); };
@@ -350,8 +352,7 @@ __global__ void __launch_bounds__(kTThreads, 1) attn_table_mma_kernel(const Attn
           for (int k = 0; k < ksteps; ++k)
             umma_bf16(tmem_base + (uint32_t)(s * 256 + h * 64), dv + (uint64_t)(k * 128), dw + (uint64_t)(k * 2), idesc, k ? 1u : 0u);
         }
-        umma_commit(tfull_bar(s));
-        umma_commit(empty_bar(s));
+        umma_commit(tfull_bar(s));                                              // the epilogue frees the stage (empty_bar)
       }
     }
   } else if (is_epi) {
@@ -395,7 +396,7 @@ __global__ void __launch_bounds__(kTThreads, 1) attn_table_mma_kernel(const Attn
       int xfirst = 0;
       if (nm0) xfirst = __shfl_sync(0xffffffffu, xr0, __ffs(nm0) - 1);
       else if (nm1) xfirst = __shfl_sync(0xffffffffu, xr1, __ffs(nm1) - 1);
-      const uint32_t ldz_u = (uint32_t)a.ldz;
+      if (warp == 4) { tab_x[lane] = cx0; tab_x[lane + 32] = cx1; tab_s[lane] = cs0; tab_s[lane + 32] = cs1; }
       mbar_wait_backoff(tfull_bar(b), (it >> 1) & 1, 64);
       tc_fence_after();
       float pool = 0.f;                          // relu(conv) * dm >= 0: 0 is the identity of max and add here
@@ -425,37 +426,29 @@ __global__ void __launch_bounds__(kTThreads, 1) attn_table_mma_kernel(const Attn
           }
           continue;
         }
-        uint16_t* xo = reinterpret_cast<uint16_t*>(a.x_out) + col;
-        uint16_t* zo = reinterpret_cast<uint16_t*>(a.z) + a.z_col + col;
+        // stage relu(conv) as bf16 rows [column t][512 channels] in the (now free) value region of the stage
+        unsigned char* stg = smem + b * kStage + kStageA + (size_t)t0 * 1024 + col * 2;
         const int nv = nn - t0;                                                // columns of this half that hold a target
-        if (G == 1) {
-          // one graph per tile: its needed rows are consecutive (column t -> row xfirst + t: immediate offsets) and so
-          // are its slots (rank among the controlling columns)
-          const uint32_t zc = t0 ? zc1 : zc0;
-          uint16_t* xb = xo + (size_t)(xfirst + t0) * HC;
-          uint16_t* zb = zo + (uint32_t)(zfirst + (t0 ? __popc(zc0) : 0)) * ldz_u;   // < 2^31 elements (checked at launch)
 #pragma unroll
-          for (int t = 0; t < 32; ++t) {
-            if (t < nv) {                                                      // warp uniform
-              const uint16_t o = relu_bf16(__uint_as_float(v[t]));
-              xb[t * HC] = o;                                                  // 32 lanes = 64 contiguous bytes
-              if ((zc >> t) & 1u) zb[(uint32_t)__popc(zc & ((1u << t) - 1u)) * ldz_u] = o;
-            }
-          }
-        } else {
-          const int slv = t0 ? cs1 : cs0, xrv = t0 ? cx1 : cx0;                // -1 beyond the needed columns
-#pragma unroll
-          for (int t = 0; t < 32; ++t) {
-            if (t < nv) {
-              const int xr = __shfl_sync(0xffffffffu, xrv, t);
-              const int sl = __shfl_sync(0xffffffffu, slv, t);
-              const uint16_t o = relu_bf16(__uint_as_float(v[t]));
-              xo[(size_t)xr * HC] = o;
-              if (sl >= 0) zo[(uint32_t)sl * ldz_u] = o;
-            }
-          }
-        }
+        for (int t = 0; t < 32; ++t)
+          if (t < nv) *reinterpret_cast<uint16_t*>(stg + t * 1024) = relu_bf16(__uint_as_float(v[t]));   // warp uniform
       }
+      if (a.pool_mode < 0) {
+        // ... and write them out as whole 1 KiB rows, 16 bytes per lane: x1 row of every needed target, snapshot row of
+        // the controlling ones
+        asm volatile("bar.sync 3, 256;" ::: "memory");
+        const unsigned char* stg = smem + b * kStage + kStageA;
+        const int et = threadIdx.x - 128;                                      // 0..255 within the epilogue warps
+        for (int u = et; u < nn * 64; u += 256) {
+          const int t = u >> 6, c = u & 63;
+          const uint4 val = *reinterpret_cast<const uint4*>(stg + t * 1024 + c * 16);
+          *reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(a.x_out) + (size_t)tab_x[t] * (HC * 2) + c * 16) = val;
+          const int sl = tab_s[t];
+          if (sl >= 0) *reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(a.z) + ((size_t)sl * a.ldz + a.z_col) * 2 + c * 16) = val;
+        }
+        asm volatile("bar.sync 3, 256;" ::: "memory");
+      }
+      if (threadIdx.x == 128) mbar_arrive(empty_bar(b));                        // stage free for the producers
     }
   } else if (warp != 1) {
     // ===================================================================== producer teams
@@ -475,6 +468,17 @@ __global__ void __launch_bounds__(kTThreads, 1) attn_table_mma_kernel(const Attn
     // 16-byte slot (c & 7) ^ (row & 7) -- all offsets but two per-thread registers are immediates
     const int gp = pt & 3;
     const unsigned char* gsrc = reinterpret_cast<const unsigned char*>(a.Vh) + gp * 16;   // fp16 value rows of the present keys
+    // The epilogue stages its output rows in this stage's value region, clobbering the two bias rows (kb, kb + 1) and the
+    // unused rows behind them: every tile restores the former and clears the latter (they meet zero weights, but must
+    // stay finite as fp16).  This thread's channels: pt, pt + 224, pt + 448.
+    uint32_t bias_hl[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int ch = pt + r * kTeam;
+      const float bv = (a.bias && ch < 512) ? a.bias[ch] : 0.f;
+      const __half hi = __float2half_rn(bv), lo = __float2half_rn(bv - __half2float(hi));
+      bias_hl[r] = (uint32_t)__half_as_ushort(hi) | ((uint32_t)__half_as_ushort(lo) << 16);
+    }
     int use = 0;
     for (int tile = blockIdx.x + team * gridDim.x; tile < n_tiles; tile += 2 * gridDim.x, ++use) {
       const int g0 = tile * G, gt = min(G, a.n_graphs - g0), rt = gt * N;
@@ -504,6 +508,26 @@ __global__ void __launch_bounds__(kTThreads, 1) attn_table_mma_kernel(const Attn
       const uint32_t nbal = __ballot_sync(0xffffffffu, pt < rt && xrv >= 0);
       mbar_wait_backoff(empty_bar(team), (use & 1) ^ 1);                       // the MMAs that read this stage are done
       for (int u = pt; u < kStageA / 16; u += kTeam) reinterpret_cast<uint4*>(sA)[u] = make_uint4(0, 0, 0, 0);
+      if (a.pool_mode < 0) {
+        unsigned char* sBv = sA + kStageA;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          const int ch = pt + r * kTeam;
+          if (ch < 512) {
+            unsigned char* panel = sBv + (ch >> 6) * kBPanel;
+            const int e = ch & 63;
+            *reinterpret_cast<uint16_t*>(panel + kb * 128 + ((((e >> 3) ^ kb) & 7) << 4) + (e & 7) * 2) = (uint16_t)(bias_hl[r] & 0xffffu);
+            *reinterpret_cast<uint16_t*>(panel + (kb + 1) * 128 + ((((e >> 3) ^ (kb + 1)) & 7) << 4) + (e & 7) * 2) = (uint16_t)(bias_hl[r] >> 16);
+          }
+        }
+        const int tail = 62 - rt;                                              // rows rt .. 63 of the 8 panels except kb, kb + 1
+        for (int u = pt; u < tail * 64; u += kTeam) {
+          int row = rt + (u >> 6);
+          if (row >= kb) row += 2;
+          const int pc = u & 63;                                               // panel = pc >> 3, 16-byte chunk = pc & 7
+          *reinterpret_cast<uint4*>(sBv + (pc >> 3) * kBPanel + row * 128 + ((pc & 7) << 4)) = make_uint4(0, 0, 0, 0);
+        }
+      }
       if (pt < rt) { cid[pt] = cv; dm_s[pt] = dmv; }
       if (pt < gt * (N + 1)) ptr_s[pt] = (uint16_t)pv;
       if (pt < rt * 2) reinterpret_cast<uint4*>(src_s)[pt] = sv;

@@ -290,6 +290,7 @@ struct ActArgs {
   uint64_t seed, offset;
   const double* rand3;
   const unsigned long long* offset_dev;   // optional device-side addend (round counter under CUDA-graph replay)
+  uint64_t row0;                          // added to the row index that keys the Philox draw (sub-batch calls)
 };
 
 __device__ __forceinline__ int select_action(float q0, float q1, const ActArgs& a, uint64_t row) {
@@ -300,7 +301,7 @@ __device__ __forceinline__ int select_action(float q0, float q1, const ActArgs& 
     double ue, u0, u1;
     if (a.rand3) { ue = a.rand3[row * 3 + 0]; u0 = a.rand3[row * 3 + 1]; u1 = a.rand3[row * 3 + 2]; }
     else {
-      Philox4 r = philox4x32_10(a.seed, row, a.offset + (a.offset_dev ? *a.offset_dev : 0ull));
+      Philox4 r = philox4x32_10(a.seed, row + a.row0, a.offset + (a.offset_dev ? *a.offset_dev : 0ull));
       ue = u01_from_u32x2(r.v[0], r.v[1]);
       u0 = (double)r.v[2] * (1.0 / 4294967296.0);
       u1 = (double)r.v[3] * (1.0 / 4294967296.0);
@@ -503,7 +504,7 @@ extern "C" int mls_dgn_forward(const MlsNetDesc* d, const MlsNetWeights* w, cons
   const bool hl = d->kind == MLS_NET_HL_DGN, tr = d->kind == MLS_NET_DGN_R;
   const int nproj = tr ? 3 : 2;
   const int latent = hl ? HC : hid + 2 * HC;
-  ActArgs aa{a->eps, a->philox_seed, a->philox_offset, a->rand3, reinterpret_cast<const unsigned long long*>(a->philox_offset_dev)};
+  ActArgs aa{a->eps, a->philox_seed, a->philox_offset, a->rand3, reinterpret_cast<const unsigned long long*>(a->philox_offset_dev), a->philox_row0};
   if (a->ctrl_mode == 0) {
     MLS_CUDA(cudaMemsetAsync(a->q, 0, (size_t)a->n_graphs * N * 2 * sizeof(float), st));
     if (a->act) MLS_CUDA(cudaMemsetAsync(a->act, 0xFF, (size_t)a->n_graphs * N, st));

@@ -676,6 +676,7 @@ struct ActArgsB {
   uint64_t seed, offset;
   const double* rand3;
   const unsigned long long* offset_dev;   // optional device-side addend (round counter under CUDA-graph replay)
+  uint64_t row0;                          // added to the row index that keys the Philox draw (sub-batch calls)
 };
 __device__ __forceinline__ int select_action_b(float q0, float q1, const ActArgsB& a, uint64_t row) {
   int act = q1 > q0 ? 1 : 0;
@@ -683,7 +684,7 @@ __device__ __forceinline__ int select_action_b(float q0, float q1, const ActArgs
     double ue, u0, u1;
     if (a.rand3) { ue = a.rand3[row * 3 + 0]; u0 = a.rand3[row * 3 + 1]; u1 = a.rand3[row * 3 + 2]; }
     else {
-      Philox4 r = philox4x32_10(a.seed, row, a.offset + (a.offset_dev ? *a.offset_dev : 0ull));
+      Philox4 r = philox4x32_10(a.seed, row + a.row0, a.offset + (a.offset_dev ? *a.offset_dev : 0ull));
       ue = u01_from_u32x2(r.v[0], r.v[1]);
       u0 = (double)r.v[2] * (1.0 / 4294967296.0);
       u1 = (double)r.v[3] * (1.0 / 4294967296.0);
@@ -1062,7 +1063,7 @@ int dgn_forward_bf16(const MlsNetDesc* d, const MlsNetWeights* w, const MlsForwa
   const bool hl = d->kind == MLS_NET_HL_DGN, tr = d->kind == MLS_NET_DGN_R;
   const int nproj = tr ? 3 : 2;
   const int latent = hl ? HC : hid + 2 * HC;
-  ActArgsB aa{a->eps, a->philox_seed, a->philox_offset, a->rand3, reinterpret_cast<const unsigned long long*>(a->philox_offset_dev)};
+  ActArgsB aa{a->eps, a->philox_seed, a->philox_offset, a->rand3, reinterpret_cast<const unsigned long long*>(a->philox_offset_dev), a->philox_row0};
   if (a->ctrl_mode == 0) {
     MLS_CUDA(cudaMemsetAsync(a->q, 0, (size_t)a->n_graphs * N * 2 * sizeof(float), st));
     if (a->act) MLS_CUDA(cudaMemsetAsync(a->act, 0xFF, (size_t)a->n_graphs * N, st));

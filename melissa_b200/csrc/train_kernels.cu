@@ -20,7 +20,7 @@ namespace {
 // Columns 2..7 are small non-negative integers / flags: packed as one word
 //   bits 0..2 has_message | interested | action, bits 3..8 messages (< 64), bits 9..16 degree (< 256), bit 31 dm
 // (bits 0..16 are exactly the feature key of dgn_forward_bf16.cu).  12 bytes per node instead of 32.
-struct __align__(4) PackedNode { float x, y; uint32_t w; };
+struct PackedNode { uint32_t x, y, w; };     // x, y: fp32 bit patterns; accessed as three 4-byte words (12-byte stride)
 
 __global__ void obs_pack_kernel(const float* __restrict__ obs, long long rows, PackedNode* __restrict__ out, int* __restrict__ errors) {
   const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -32,9 +32,8 @@ __global__ void obs_pack_kernel(const float* __restrict__ obs, long long rows, P
   uint32_t w = 0;
   if (ok) w = ((((((uint32_t)deg << 6) | (uint32_t)msgs) << 1 | (uint32_t)act) << 1 | (uint32_t)intr) << 1 | (uint32_t)hm) | ((uint32_t)dm << 31);
   else if (errors) atomicAdd(errors, 1);
-  PackedNode p;
-  p.x = lo.x; p.y = lo.y; p.w = w;
-  out[r] = p;
+  uint32_t* o = reinterpret_cast<uint32_t*>(out) + r * 3;
+  o[0] = __float_as_uint(lo.x); o[1] = __float_as_uint(lo.y); o[2] = w;
 }
 
 // out row m = frame rows of src_row[m] (NULL: m), N nodes each, expanded to 8 floats per node; with `agent` the row is
@@ -46,10 +45,10 @@ __global__ void obs_unpack_kernel(const PackedNode* __restrict__ in, const long 
   const long long m = t / N;
   const int i = (int)(t - m * N);
   const long long f = src_frame ? src_frame[m] : m;
-  const PackedNode p = in[f * N + i];
-  const uint32_t w = p.w;
+  const uint32_t* pw = reinterpret_cast<const uint32_t*>(in) + (f * N + i) * 3;
+  const uint32_t w = pw[2];
   float* o = out + m * out_stride + (long long)i * 8;
-  o[0] = p.x; o[1] = p.y;
+  o[0] = __uint_as_float(pw[0]); o[1] = __uint_as_float(pw[1]);
   o[2] = (float)((w >> 9) & 255u); o[3] = (float)((w >> 3) & 63u); o[4] = (float)((w >> 2) & 1u);
   o[5] = (float)((w >> 1) & 1u); o[6] = (float)(w & 1u); o[7] = (float)(w >> 31);
   if (agent && i == 0) out[m * out_stride + (long long)N * 8] = (float)agent[m];

@@ -29,17 +29,22 @@ class FlatParameters:
         if any(p.device != dev or p.dtype != dt for p in params):
             raise ValueError("parameters must share one device and dtype")
         self.module, self.params = module, params
-        self.numel = sum(p.numel() for p in params)
-        self.flat = torch.empty(self.numel, dtype=dt, device=dev)
+        # every parameter starts on a 64-byte boundary (the CUDA kernels read weight rows with 16-byte loads); the
+        # padding stays zero in both buffers, so the optimiser never moves it
+        ALIGN = 16
+        self.offsets, off = [], 0
+        for p in params:
+            self.offsets.append(off)
+            off += (p.numel() + ALIGN - 1) // ALIGN * ALIGN
+        self.numel = off
+        self.flat = torch.zeros(self.numel, dtype=dt, device=dev)
         self.grad = torch.zeros(self.numel, dtype=dt, device=dev)
-        off = 0
         with torch.no_grad():
-            for p in params:
+            for p, off in zip(params, self.offsets):
                 n = p.numel()
                 self.flat[off:off + n].copy_(p.detach().reshape(-1))
                 p.data = self.flat[off:off + n].view_as(p)
                 p.grad = self.grad[off:off + n].view_as(p)
-                off += n
 
     def zero_grad(self):
         self.grad.zero_()
@@ -50,11 +55,8 @@ class FlatParameters:
                 break
 
     def _rehome(self):
-        off = 0
-        for p in self.params:
-            n = p.numel()
-            p.grad = self.grad[off:off + n].view_as(p)
-            off += n
+        for p, off in zip(self.params, self.offsets):
+            p.grad = self.grad[off:off + p.numel()].view_as(p)
 
     def bump_versions(self):
         """The fused Adam kernel writes the flat buffer behind torch's back: tell caches keyed on the parameter

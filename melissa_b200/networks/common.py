@@ -168,6 +168,8 @@ class DGNBase(nn.Module):
                     f"parameter {k} must be a float32 CUDA tensor (module on {x.device}, {x.dtype}); "
                     "there is no CPU forward -- move the module to the GPU")
             x = x.contiguous()
+            if x.data_ptr() % 16:
+                raise _lib.MelissaLibraryError(f"parameter {k} must start on a 16-byte boundary (the kernels read it with 16-byte loads)")
             keep.append(x)
             setattr(ws, k, x.data_ptr())
         return ws, keep
@@ -242,7 +244,8 @@ class DGNBase(nn.Module):
         return {"buf": buf, "graphs": G}
 
     def _call(self, obs, stride, n_graphs, ctrl_mode, ctrl_mask, q, act, eps, seed, offset, rand3, offset_dev=None,
-              flags=0, feature_errors=None, graph_ids=None, graph_id_stride=1, topology_cache=None, prepared=False):
+              flags=0, feature_errors=None, graph_ids=None, graph_id_stride=1, topology_cache=None, prepared=False,
+              philox_row0=0):
         L = _lib.lib()
         desc = self._desc()
         ws, keep = self.weights_struct()
@@ -260,6 +263,7 @@ class DGNBase(nn.Module):
         args = _lib.MlsForwardArgs(obs.data_ptr(), stride, n_graphs, ctrl_mode, _lib.ptr(ctrl_mask), q.data_ptr(),
                                    _lib.ptr(act), float(eps), int(flags), int(seed), int(offset), _lib.ptr(rand3),
                                    wsp.data_ptr(), wsp.numel(), None, None, 0, 0, _lib.ptr(offset_dev), _lib.ptr(feature_errors))
+        args.philox_row0 = int(philox_row0)
         if topology_cache is not None and graph_ids is not None and self.precision == "bf16":
             if graph_ids.dtype != torch.int32:
                 raise ValueError("graph_ids must be an int32 tensor")
@@ -313,7 +317,7 @@ class DGNBase(nn.Module):
                        q_out: Optional[torch.Tensor] = None, act_out: Optional[torch.Tensor] = None,
                        philox_offset_dev: Optional[torch.Tensor] = None, discrete_features: bool = False,
                        feature_errors: Optional[torch.Tensor] = None, graph_ids: Optional[torch.Tensor] = None,
-                       graph_id_stride: int = 1, topology_cache=None, prepared: bool = False):
+                       graph_id_stride: int = 1, topology_cache=None, prepared: bool = False, philox_row0: int = 0):
         """Rollout form: obs_matrix f32 [B, N, 8] (what ``BatchedGraphEnv`` emits), ctrl_mask
         u8 [B, N] (the active set).  One GNN pass per graph; returns (q f32 [B,N,2] -- zero
         where not controlling, act i8 [B,N] -- -1 where not controlling).
@@ -324,7 +328,9 @@ class DGNBase(nn.Module):
         ``feature_errors`` (int32[1] device tensor) receives the number of rows violating that promise.
         ``graph_ids`` (int32 device tensor, graph g's pool index at ``graph_ids.flatten()[g * graph_id_stride]``) +
         ``topology_cache`` (:meth:`build_topology_cache`): static graph pools skip the per-call radius_graph pass.
-        ``prepared=True``: weights / feature tables are packed once per parameter version (:meth:`prepare`)."""
+        ``prepared=True``: weights / feature tables are packed once per parameter version (:meth:`prepare`).
+        ``philox_row0``: first batch-wide row (episode * N) of a sub-batch call, so that the exploration draws of a
+        batch processed in slices equal those of one full-batch call."""
         B, N, F = obs_matrix.shape
         if N != self.agents_num or F != self.input_dim + 3:
             raise ValueError(f"Expected obs_matrix [B, {self.agents_num}, {self.input_dim + 3}], got {tuple(obs_matrix.shape)}")
@@ -335,5 +341,5 @@ class DGNBase(nn.Module):
             flags = _lib.FWD_DISCRETE_FEATURES if (discrete_features and self.precision == "bf16") else 0
             self._call(obs_matrix.contiguous(), N * F, B, 0, ctrl_mask.contiguous(), q, act, eps, philox_seed,
                        philox_offset, rand3, philox_offset_dev, flags, feature_errors, graph_ids, graph_id_stride,
-                       topology_cache, prepared)
+                       topology_cache, prepared, philox_row0)
         return q, act

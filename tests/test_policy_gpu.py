@@ -128,9 +128,11 @@ def test_evaluation_collect_in_testing_mode():
 @pytest.mark.parametrize("precision,dynamic", [("bf16", False), ("fp32", True)])
 def test_pipelined_host_round_equals_single_shot_round(precision, dynamic):
     """Rollout.round_host(sub_batches=4): H2D / compute / D2H of episode slices overlap on three streams.
-    Greedy policy -> deterministic: the host buffers after every round equal those of the single-shot
-    host round (the sliced environment step keys recycling and the device movement stream by the batch-wide
-    episode index, include/melissa_b200.h MlsEnvDesc.episode_offset)."""
+    The host buffers after every round equal those of the single-shot host round, WITH exploration (eps = 0.3): the
+    sliced environment step keys recycling and the device movement stream by the batch-wide episode index
+    (include/melissa_b200.h MlsEnvDesc.episode_offset) and the exploration draws are keyed by the batch-wide row
+    (MlsForwardArgs.philox_row0).  Host observations travel packed (12 bytes per node); unpacked they are bit-equal
+    to the environment's obs rows."""
     from melissa_b200.batched_env import BatchedGraphEnv, ResetTuplesDevice
     from melissa_b200.networks import LDGNNetwork
     from melissa_b200.rollout import Rollout
@@ -144,7 +146,7 @@ def test_pipelined_host_round_equals_single_shot_round(precision, dynamic):
         net.load_state_dict(sd)
         net = net.cuda().set_precision(precision)
         env = BatchedGraphEnv(B, N, pool, dynamic_graph=dynamic)
-        ro = Rollout(env, net, eps=0.0, seed=9)
+        ro = Rollout(env, net, eps=0.3, seed=9)
         nowait = sub < 0
         if sub < 0:
             sub = -sub
@@ -162,6 +164,7 @@ def test_pipelined_host_round_equals_single_shot_round(precision, dynamic):
                 ro.round_host(sub)
             torch.cuda.synchronize()
             trace.append({k: v.clone() for k, v in ro._host.items()})
+            assert np.array_equal(Rollout.unpack_obs_host(ro._host["obs"]).view(np.uint32), env.obs.cpu().numpy().view(np.uint32))
         outs.append((trace, ro.transitions()))
         assert ro.feature_violations() == 0
     (t1, n1) = outs[0]
