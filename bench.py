@@ -51,6 +51,12 @@ def parse_args():
     ap.add_argument("--cpu-episodes", type=int, default=8, help="episodes per CPU process in the CPU arm")
     ap.add_argument("--prof-kernel", default=None)
     ap.add_argument("--dynamic", action="store_true", help="dynamic_graph=True: nodes move every round (Philox stream on the device)")
+    ap.add_argument("--train", action="store_true", help="headline = the TRAINING step (rollout round + DQN update with gradient all-reduce)")
+    ap.add_argument("--no-train", action="store_true", help="skip the short training measurement appended as the 'train' key")
+    ap.add_argument("--train-batch", type=int, default=4096, help="sampled transitions per update and per GPU")
+    ap.add_argument("--train-steps", type=int, default=10)
+    ap.add_argument("--no-extra", action="store_true", help="skip the short runs of the other BASELINE configurations ('other_configs')")
+    ap.add_argument("--no-flip", action="store_true", help="skip the bf16-vs-fp32 action-flip measurement")
     return ap.parse_args()
 
 
@@ -319,6 +325,42 @@ def run_ours(args):
                                         finish=ro.host_drain if pipelined else None)
         e2e = (e_ms, e_trans, ex[0])
 
+    # row-set sizes of the forward at the benchmark state (means over the resident episodes): controlling nodes,
+    # needed rows (controlling nodes + their radius-graph sources: the only rows of conv1's output anybody reads),
+    # conv2 edge-list entries (self loops included for GATv2)
+    sets = None
+    if net is not None and two_convs:
+        act = env.active.bool()
+        adj = torch.as_tensor(pool.adj, device=dev)[env.episode[:, 3].long()]           # [B, i, j]
+        srcs = adj & act[:, :, None]                                                     # sources j of controlling targets i
+        need = act | srcs.any(1)
+        sets = {"ctrl": float(act.sum()) / B, "needed": float(need.sum()) / B,
+                "edges": float(srcs.sum()) / B + (float(act.sum()) / B if args.model == "l_dgn" else 0.0)}
+        del adj, srcs, need
+    flip = None
+    if net is not None and args.precision == "bf16" and not args.no_flip and not args.dynamic and rank == 0:
+        flip = measure_flip_rate(dev, args.model, N, env, net, ro)
+    train = None
+    if net is not None and not args.no_train and args.precision == "bf16" and not args.dynamic:
+        torch.cuda.empty_cache()
+        train = measure_training(args, dev, world, rank, args.model, N, B, pool, (gi, src, inter, scr), args.train_steps, 3,
+                                 args.train_batch)
+    others = None
+    if rank == 0 and world == 1 and not args.no_extra and args.model == "l_dgn" and N == 50 and not args.dynamic:
+        others = {}
+        for name, kw in (("config3_dgn_r_n20_b16384", dict(model="dgn_r", N=20, B=16384)),
+                         ("config5_hl_dgn_n50_b32768", dict(model="hl_dgn", N=50, B=32768)),
+                         ("dgn_r_n50_b32768", dict(model="dgn_r", N=50, B=32768)),
+                         ("l_dgn_dynamic_graph_n50_b32768", dict(model="l_dgn", N=50, B=32768, dynamic=True)),
+                         ("config5_stress_l_dgn_n200_b2048", dict(model="l_dgn", N=200, B=2048, G=64)),
+                         ("config2_env_only_mpr_n20_b4096", dict(model="none", N=20, B=4096, heuristic="mpr", is_testing=True,
+                                                                  scripted_ratio=1.0)),
+                         ("env_only_random_policy_n50_b32768", dict(model="none", N=50, B=32768))):
+            try:
+                others[name] = measure_config(dev, rank, kw.pop("model"), kw.pop("N"), kw.pop("B"), kw.pop("G", G), **kw)
+            except Exception as e:                                       # a failed side run must not void the headline line
+                others[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
+
     def reduce(v, op):
         if world == 1:
             return v
@@ -344,7 +386,7 @@ def run_ours(args):
         # (profiles/r01_traffic.json), valid for the default workload only
         traffic = {}
         try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
             if tj.get("model") == args.model and tj.get("episodes") == B and tj.get("nodes") == N and tj.get("precision") == args.precision:
                 traffic = tj.get("traffic", {})
         except (OSError, ValueError):
@@ -358,6 +400,8 @@ def run_ours(args):
         n_out = HC if args.precision == "fp32" else (nproj * HC if gemm_name == "proj1" else (nproj - 1) * HC)
         gk = HC if gemm_name == "proj2" else hid
         gemm_rows = chunk_rows
+        if gemm_name == "proj2" and sets is not None and args.precision == "bf16":
+            gemm_rows = sets["needed"] * chunk_graphs               # source-side projection runs on the needed rows only
         if gemm_name == "head0":                                    # [graphs x H*C] x [H*C x 2*128] (HL-DGN: one row per graph)
             gemm_rows, n_out, gk = chunk_graphs, 256, HC
         gemm_flops = 2.0 * gemm_rows * n_out * gk
@@ -365,15 +409,18 @@ def run_ours(args):
         roof_gemm = None
         if gemm_ms:
             ach = gemm_flops / (gemm_ms * 1e-3) / 1e12
-            roof_gemm = {"kernel": f"{args.precision} GEMM ({gemm_name}, [{gemm_rows}x{gk}]x[{gk}x{n_out}])",
-                         "bound": "tensor", "achieved": round(ach, 3), "peak": tensor_peak, "unit": "TFLOP/s",
-                         "frac": round(ach / tensor_peak, 5), "traffic": traffic.get(gemm_name),
-                         "peak_source": f"{peak_src} (sustained bf16)", "kernel_ms": round(gemm_ms, 5), "launch_flops": gemm_flops}
+            burst = float(peaks.get("bf16_tflops", tensor_peak))
+            roof_gemm = {"kernel": f"{args.precision} GEMM ({gemm_name}, [{int(gemm_rows)}x{gk}]x[{gk}x{n_out}])",
+                         "bound": "tensor", "achieved": round(ach, 3), "peak": burst, "unit": "TFLOP/s",
+                         "frac": round(ach / burst, 5), "frac_of_sustained": round(ach / tensor_peak, 5), "traffic": traffic.get(gemm_name),
+                         "peak_source": f"{peak_src} (burst bf16: the kernel is timed alone inside a step of a few ms)",
+                         "kernel_ms": round(gemm_ms, 5), "launch_flops": gemm_flops}
         roofline = roof_gemm
         kern_ms = float(np.mean(prof_ms)) if prof_ms else None
         esz = 2
         ctrl_rows = A * chunk_graphs                                # controlling nodes (= agent transitions) per launch
-        csr_bytes = chunk_graphs * (deg + 2 * (N + 1))              # neighbour lists + row pointers, once per graph
+        need_rows = (sets["needed"] if sets else N) * chunk_graphs  # rows of relu(conv1) anybody reads
+        edge_ents = (sets["edges"] if sets else 0.0) * chunk_graphs
 
         def hbm_line(kernel, ms_k, nbytes, key, note):
             ach = nbytes / (ms_k * 1e-3) / 1e9
@@ -382,26 +429,28 @@ def run_ours(args):
                     "kernel_ms": round(ms_k, 5), "launch_bytes": int(nbytes), "note": note}
 
         def conv1_bytes():
-            # discrete-feature mode: the projections come from an L2-resident table; the kernel reads the keys
-            # (4 B/node) and lists and writes relu(conv) (HC bf16 per node) + the controlling-node snapshot
-            if args.model == "hl_dgn":                              # gather kernel + pooling: reads keys, writes one row per graph
-                return chunk_rows * 4 + csr_bytes + chunk_graphs * HC * esz
-            return chunk_rows * (4 + HC * esz) + csr_bytes + ctrl_rows * HC * esz
+            # discrete-feature mode: projections / pair logits come from L2-resident tables, the radius-graph lists from
+            # the per-pool topology cache; per node the stage reads key 4 + compact id 2 (written and read) + slot 4 +
+            # xrow 4 bytes and writes relu(conv1) of the NEEDED rows (HC bf16) + the controlling-node snapshot (HC bf16)
+            if args.model == "hl_dgn":                              # pooling: reads keys, writes one row per graph
+                return chunk_rows * (4 + 2 + 2) + chunk_graphs * HC * esz
+            return chunk_rows * (4 + 2 + 2 + 4 + 4) + (need_rows + ctrl_rows) * HC * esz
 
         roof_conv1 = None
         if kern_ms and prof_name == "edge2":
-            # conv2 attention (edge_bf16_kernel, compact targets): reads the source-side projections of every node
-            # ((nproj-1)*HC bf16), the target-side projection of the controlling nodes (HC bf16), the per-node dots,
-            # slots and lists; writes the conv2 snapshot of the controlling nodes (HC bf16)
-            nb = (chunk_rows * ((nproj - 1) * HC * esz + 4 * 4 + 4) + ctrl_rows * (HC * esz + 4 * 4 + 4) + csr_bytes +
+            # conv2 attention (conv2_attn_kernel): reads the source-side projections of the needed rows ((nproj-1)*HC fp16)
+            # and their logit dots, the target-side projection of the controlling nodes (HC fp16) and their dots, the edge
+            # entries (2 B) and per-target offsets; writes the conv2 snapshot of the controlling nodes (HC bf16)
+            nb = (need_rows * ((nproj - 1) * HC * esz + 4 * 4) + ctrl_rows * (HC * esz + 4 * 4 + 4) + edge_ents * 2 + chunk_graphs * 32 +
                   ctrl_rows * HC * esz)
-            roofline = hbm_line(f"edge_bf16_kernel (conv2 attention, {chunk_graphs} graphs x 4 heads, {int(ctrl_rows)} targets)", kern_ms, nb,
-                                "edge2", "largest single-kernel share of the step; SIMT issue/latency bound (ncu: profiles/), not bandwidth bound")
+            roofline = hbm_line(f"conv2_attn_kernel (conv2 attention: half2 logits + tcgen05 aggregation, {chunk_graphs} graphs x 4 heads, "
+                                f"{int(ctrl_rows)} targets, {int(need_rows)} source rows)", kern_ms, nb,
+                                "edge2", "largest single-kernel share of the step")
             if prof_ms_conv1:
                 c1_ms = float(np.mean(prof_ms_conv1))
                 name = ("attn_table_mma_kernel + key compaction + pair-logit table (conv1 attention on tcgen05"
-                        if N <= 62 and args.model != "hl_dgn" else "edge_bf16_kernel (conv1 attention, gather from the feature table")
-                roof_conv1 = hbm_line(f"{name}, {chunk_graphs} graphs)", c1_ms, conv1_bytes(), "edge1",
+                        if N <= 62 else "edge_bf16_kernel (conv1 attention, gather from the feature table")
+                roof_conv1 = hbm_line(f"{name}, {chunk_graphs} graphs, {int(need_rows)} output rows)", c1_ms, conv1_bytes(), "edge1",
                                       "event pair spans the whole conv1 attention stage")
         elif kern_ms and prof_name == "edge1":
             roofline = hbm_line(f"conv1 attention stage ({chunk_graphs} graphs x 4 heads)", kern_ms, conv1_bytes(), "edge1",
@@ -426,6 +475,10 @@ def run_ours(args):
                 "eager_ms_per_step": (eager_ms / steps) if eager_ms else None,
                 "kernel_timing": "event pair around one launch per step in an eager pass over the same rounds",
                 "active_agents_per_graph_round": round(A, 3), "graph_rounds_per_s": world * B * steps / (ms_max / 1e3),
+                "needed_rows_per_graph_round": round(sets["needed"], 3) if sets else None,
+                "conv2_edges_per_graph_round": round(sets["edges"], 3) if sets else None,
+                "bf16_vs_fp32": flip,
+                "e2e_wire_format": "packed observations: 12 bytes per node (fp32 x, y + one word of feature bits) both ways",
                 "model_tflops_algorithmic": round(flops_round * B * steps / (ms / 1e3) / 1e12, 3),
             },
             "gpu_launches": int(launches_sum),
@@ -434,6 +487,8 @@ def run_ours(args):
             "roofline_tensor": roof_gemm,
             "roofline_conv1": roof_conv1,
             "roofline_env": env_roof,
+            "train": train,
+            "other_configs": others,
         }
         if e2e is not None:
             out["e2e"] = {"value": e_trans_sum / (e_ms_max / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(e2e[2][0]),
@@ -443,9 +498,225 @@ def run_ours(args):
                                        "(pinned host buffers; every byte of every round crosses PCIe inside the timed region, "
                                        "which ends when the last copy has landed)"
                                        if args.e2e_sub_batches > 1 else "one stream: H2D -> compute -> D2H")}
+        if args.train and train:
+            # --train: the headline is the training step (BASELINE configs 4 / 5); the rollout-only numbers stay beside it
+            out["rollout_only"] = {"value": out["value"], "ms_per_step": out["ms_per_step"]}
+            out["value"], out["ms_per_step"], out["steps"] = train["value"], train["ms_per_step"], train["steps"]
+            out["config"]["workload"] = train["workload"]
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    return out
+
+
+# ------------------------------------------------------------------------------ training step (BASELINE configs 4 / 5)
+def measure_training(args, dev, world, rank, model, N, B, pool, tuple_arrays, steps, warmup, batch):
+    """One training step = one rollout round of all B episodes (bf16 kernels, transitions stored in the device replay
+    ring) + one DQN update on ``batch`` sampled transitions per GPU (autograd forward/backward, ONE all-reduce of the flat
+    fp32 gradient over NCCL, fused Adam, bf16 re-pack).  The optimiser step of update k is deferred until round k+1 has
+    been issued, so the collective overlaps the next rollout.  Reference loop: OffpolicyTrainer + DQNPolicy.update
+    (l_dgn.py:246-261), n_step 4, gamma 0.99, target_update_freq 500, lr 1e-3 (common.py:24-31)."""
+    import torch
+    import torch.distributed as dist
+
+    from melissa_b200.batched_env import BatchedGraphEnv, ResetTuplesDevice
+    from melissa_b200.data_parallel import FlatParameters, FusedAdam, GradSync
+    from melissa_b200.networks import NETWORKS
+    from melissa_b200.policy import BatchedCollector, DQNPolicy
+    from melissa_b200.replay import DeviceReplay
+
+    torch.manual_seed(9)
+    kw = dict(aggregator="max") if model == "hl_dgn" else {}
+    net = NETWORKS[model](5, 128, 2, 4, N, dueling_param=({"hidden_sizes": [128, 128]}, {"hidden_sizes": [128, 128]}),
+                          device=str(dev), **kw).to(dev)
+    net.set_precision("bf16")
+    flat = FlatParameters(net)
+    optim = FusedAdam(flat, lr=1e-3)
+    pol = DQNPolicy(net, optim, discount_factor=0.99, estimation_step=4, target_update_freq=500, eps=0.05, seed=9 + rank)
+    sync = GradSync(flat.grad)
+    sync.broadcast_parameters(flat.flat, src=0)
+    pol.grad_sync = sync if world > 1 else None
+    env = BatchedGraphEnv(B, N, pool, device=dev, want_obs=True, want_info=True)
+    replay = DeviceReplay(B, N, ring_rounds=8, device=dev, seed=rank)
+    gi, src, inter, scr = tuple_arrays
+    col = BatchedCollector(agents_num=N, policy=pol, env=env, buffer=replay, exploration_noise=True,
+                           tuples=ResetTuplesDevice(gi, src, inter, scr, N, dev, pool_size=len(pool)))
+    for _ in range(8):                          # fill the ring (and spread the episodes over their lifetime)
+        col.iterate(0.05)
+
+    def step():
+        col.iterate(0.05)                       # round k+1 is issued while the all-reduce of update k is in flight
+        pol.finish_update()
+        return pol.update(batch, replay, defer_step=True)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(3, warmup)):
+        out = step()
+    sync_all()
+    t_before = int(env.transitions.item())
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(steps):
+        out = step()
+    pol.finish_update()
+    ev1.record()
+    sync_all()
+    ms = ev0.elapsed_time(ev1)
+    trans = int(env.transitions.item()) - t_before
+    loss = float(out["loss"])
+    # rollout round alone and update alone (same state), to attribute the step
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        col.iterate(0.05)
+    e1.record()
+    torch.cuda.synchronize()
+    round_ms = e0.elapsed_time(e1) / 5
+    e0.record()
+    for _ in range(5):
+        pol.update(batch, replay)
+    e1.record()
+    torch.cuda.synchronize()
+    update_ms = e0.elapsed_time(e1) / 5
+    # the collective alone: all-reduce of the flat gradient buffer
+    ar_us, busbw = None, None
+    if world > 1:
+        for _ in range(5):
+            dist.all_reduce(flat.grad)
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0.record()
+        for _ in range(20):
+            dist.all_reduce(flat.grad)
+        e1.record()
+        torch.cuda.synchronize()
+        ar_us = e0.elapsed_time(e1) / 20 * 1e3
+        nbytes = flat.grad.numel() * 4
+        busbw = 2.0 * (world - 1) / world * nbytes / (ar_us * 1e-6) / 1e9
+    # weights must be identical on every rank after the synchronous updates
+    chk = flat.flat.double().sum().reshape(1)
+    same = True
+    if world > 1:
+        lo, hi = chk.clone(), chk.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        same = bool((lo == hi).item())
+    t = torch.tensor([ms, float(trans)], dtype=torch.float64, device=dev)
+    if world > 1:
+        tm = t.clone()
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        ts = t.clone()
+        dist.all_reduce(ts, op=dist.ReduceOp.SUM)
+        ms_max, trans_sum = float(tm[0]), float(ts[1])
+    else:
+        ms_max, trans_sum = ms, float(trans)
+    res = {
+        "workload": f"{model} training step: rollout round of {B} episodes/GPU ({N}-node graphs, bf16 kernels) + 1 DQN update on "
+                    f"{batch} sampled transitions/GPU (n_step 4, gamma 0.99, target_update_freq 500, Adam lr 1e-3)",
+        "value": trans_sum / (ms_max / 1e3), "unit": UNIT, "ms_per_step": ms_max / steps, "steps": steps,
+        "updates_per_s": steps / (ms_max / 1e3), "sampled_transitions_per_s": world * batch * steps / (ms_max / 1e3),
+        "rollout_round_ms": round_ms, "update_ms": update_ms, "loss": loss, "parameters": int(sum(p.numel() for p in net.parameters())),
+        "grad_buffer_bytes": int(flat.grad.numel() * 4),
+        "collective": ("ncclAllReduce(sum) of the flat fp32 gradient buffer, one per update, overlapped with the next rollout round"
+                       if world > 1 else "none (1 GPU)"),
+        "allreduce_us": ar_us, "allreduce_busbw_GBs": busbw,
+        "allreduce_share_of_step": (ar_us * 1e-3 / (ms_max / steps)) if ar_us else 0.0,
+        "weights_identical_across_ranks": same,
+        "backward": "torch autograd over melissa_b200/networks/autograd.py (v1); optimiser = mls_adam_step kernel",
+    }
+    del col, replay, env, pol, optim, flat, net
+    torch.cuda.empty_cache()
+    return res
+
+
+# ------------------------------------------------------------------------------ other BASELINE configurations (short runs)
+def measure_config(dev, rank, model, N, B, G, steps=6, warmup=3, dynamic=False, heuristic=None, is_testing=False,
+                   scripted_ratio=0.0, preroll=24, eps=0.05):
+    """Short device-resident run (CUDA-graph replay) of another configuration; value in agent-transitions/s."""
+    import torch
+
+    from melissa_b200 import reset_chain
+    from melissa_b200.batched_env import BatchedGraphEnv, ResetTuplesDevice
+    from melissa_b200.networks import NETWORKS
+    from melissa_b200.rollout import Rollout
+    from melissa_b200.topology import GraphPool
+
+    path = os.path.join(CACHE_DIR, f"pool_n{N}_{G}.npz")
+    pool = GraphPool.load_npz(path) if os.path.exists(path) else GraphPool.synthetic(N, G, first_seed=0, side=None if N in (20, 50) else 1.0)
+    P = 2 * B
+    if scripted_ratio == 0.0 and os.path.exists(os.path.join(CACHE_DIR, f"tuples_n{N}_g{G}_c{P}_s9.npz")):
+        gi, src, inter, scr = load_tuples(N, G, P)
+    else:
+        gi, src, inter, scr, _ = reset_chain.episode_pool(9, P, N, len(pool), scripted_ratio)
+    env = BatchedGraphEnv(B, N, pool, device=dev, dynamic_graph=dynamic, heuristic=heuristic, is_testing=is_testing)
+    net = None
+    if model != "none":
+        torch.manual_seed(9)
+        kw = dict(aggregator="max") if model == "hl_dgn" else {}
+        net = NETWORKS[model](5, 128, 2, 4, N, dueling_param=({"hidden_sizes": [128, 128]}, {"hidden_sizes": [128, 128]}),
+                              device=str(dev), **kw).to(dev)
+        net.set_precision("bf16")
+    ro = Rollout(env, net, eps=eps, seed=9 + rank)
+    ro.start(ResetTuplesDevice(gi, src, inter, scr, N, dev, pool_size=len(pool)))
+    if net is None:
+        ro.act.copy_(torch.randint(0, 2, ro.act.shape, device=dev, dtype=torch.int8))
+    for _ in range(preroll):
+        ro.round()
+    ro.capture(warmup_rounds=2)
+    for _ in range(warmup):
+        ro.round()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+    t0 = ro.transitions()
+    evs = []
+    for _ in range(steps):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); ro.round(); b.record()
+        evs.append((a, b))
+    torch.cuda.synchronize()
+    ms = sum(a.elapsed_time(b) for a, b in evs)
+    trans = ro.transitions() - t0
+    viol = ro.feature_violations() if net is not None else 0
+    out = {"model": model, "n_nodes": N, "episodes": B, "dynamic_graph": dynamic, "heuristic": heuristic,
+           "value": trans / (ms / 1e3), "unit": UNIT, "ms_per_step": ms / steps, "steps": steps,
+           "graph_rounds_per_s": B * steps / (ms / 1e3), "active_agents_per_graph_round": trans / (steps * B),
+           "feature_violations": viol}
+    del ro, env, net, flush
+    torch.cuda.empty_cache()
+    return out
+
+
+def measure_flip_rate(dev, model, N, env, net, ro):
+    """bf16 product path vs the fp32 CUDA path (the <= 1e-5 parity anchor) on the observations the benchmark's
+    environment holds right now: max |dq|, greedy-action flip rate, largest fp32 margin among the flipped decisions."""
+    import torch
+
+    from melissa_b200.networks import NETWORKS
+    obs, active = env.obs.clone(), env.active.clone()
+    q_b, a_b = net.forward_graphs(obs, active, discrete_features=True, graph_ids=ro.graph_ids, graph_id_stride=8,
+                                  topology_cache=ro.topology_cache, prepared=True)
+    kw = dict(aggregator="max") if model == "hl_dgn" else {}
+    ref = NETWORKS[model](5, 128, 2, 4, N, dueling_param=({"hidden_sizes": [128, 128]}, {"hidden_sizes": [128, 128]}),
+                          device=str(dev), **kw).to(dev)
+    ref.load_state_dict(net.state_dict())
+    q_f, a_f = ref.forward_graphs(obs, active)
+    m = active.bool()
+    n = int(m.sum())
+    flips = (a_b != a_f) & m
+    margin = (q_f[..., 1] - q_f[..., 0]).abs()
+    out = {"decisions": n, "max_abs_dq": float((q_b - q_f).abs()[m].max()), "q_scale": float(q_f[m].abs().max()),
+           "flip_rate": float(flips.sum()) / max(1, n),
+           "largest_flipped_fp32_margin": float(margin[flips].max()) if bool(flips.any()) else 0.0,
+           "median_fp32_margin": float(margin[m].median()),
+           "note": "bf16 product path vs fp32 CUDA path on the benchmark environment's current observations (random-init weights)"}
+    del ref, q_f, a_f, q_b, a_b
+    torch.cuda.empty_cache()
     return out
 
 

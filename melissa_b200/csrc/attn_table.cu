@@ -245,8 +245,9 @@ constexpr int kStageA = 4 * kAHead;            // 32 KiB
 constexpr int kStageB = 8 * kBPanel;           // 64 KiB
 constexpr int kStage = kStageA + kStageB;      // 96 KiB
 constexpr int kMetaSrc = 64 * kMaxNbr;         // CSR source lists of a tile
-constexpr int kMeta = kMetaSrc + 64 * 4 /*keys*/ + 64 * 2 /*ids*/ + 128 * 2 /*CSR row pointers*/ + 64 * 4 /*dm*/;
-constexpr int kTSmem = 2 * kStage + 2 * kMeta + 256 /*barriers*/ + 512 /*epilogue row tables*/ + 1024;
+constexpr int kMetaTab = kMetaSrc + 64 * 4 /*need list, counts*/ + 64 * 2 /*ids*/ + 128 * 2 /*CSR row pointers*/ + 64 * 4 /*dm*/;
+constexpr int kMeta = kMetaTab + 2 * 64 * 4 /*x_out row and snapshot slot of every TMEM column*/;
+constexpr int kTSmem = 2 * kStage + 2 * kMeta + 256 /*barriers*/ + 1024;
 
 __device__ __forceinline__ float f_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float f_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -286,8 +287,6 @@ __global__ void __launch_bounds__(kTThreads, 1) attn_table_mma_kernel(const Attn
   unsigned char* meta = smem + 2 * kStage;                                        // [2][kMeta]
   uint64_t* bars = reinterpret_cast<uint64_t*>(meta + 2 * kMeta);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
-  int* tab_x = reinterpret_cast<int*>(meta + 2 * kMeta + 256);               // [64] x_out row of TMEM column t (this tile)
-  int* tab_s = tab_x + 64;                                                     // [64] snapshot slot of TMEM column t or -1
   const uint32_t bar0 = smem_u32(bars);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (2 + s); };
@@ -361,44 +360,15 @@ __global__ void __launch_bounds__(kTThreads, 1) attn_table_mma_kernel(const Attn
     int it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const int b = it & 1;
-      const int g0 = tile * G, gt = min(G, a.n_graphs - g0), rt = gt * N;
-      const size_t m0 = (size_t)g0 * N;
-      // controlling-list slots of the tile's targets: lane t holds targets t and t + 32
-      const int sl0 = (lane < rt && a.slot) ? a.slot[m0 + lane] : -1;
-      const int sl1 = (lane + 32 < rt && a.slot) ? a.slot[m0 + lane + 32] : -1;
-      // x_out rows of the tile's targets (-1: not needed / beyond the tile)
-      int xr0 = -1, xr1 = -1;
-      if (a.pool_mode < 0) {
-        if (lane < rt) xr0 = a.xrow ? a.xrow[m0 + lane] : (int)m0 + lane;
-        if (lane + 32 < rt) xr1 = a.xrow ? a.xrow[m0 + lane + 32] : (int)m0 + lane + 32;
-      }
-      const uint32_t nm0 = __ballot_sync(0xffffffffu, xr0 >= 0), nm1 = __ballot_sync(0xffffffffu, xr1 >= 0);
-      // TMEM column t = the t-th needed target of the tile (the producers compact the weight rows): lane t gets that
-      // target's x_out row and slot
-      const int n0c = __popc(nm0), nn = a.pool_mode >= 0 ? 64 : n0c + __popc(nm1);
-      int cx0, cx1, cs0, cs1;
-      {
-        auto pick = [&](int v0, int v1, int t) {
-          const bool lo = t < n0c;
-          const unsigned srcl = lo ? __fns(nm0, 0, t + 1) : __fns(nm1, 0, t - n0c + 1);
-          const int a0 = __shfl_sync(0xffffffffu, v0, srcl & 31), a1 = __shfl_sync(0xffffffffu, v1, srcl & 31);
-          return t < nn ? (lo ? a0 : a1) : -1;
-        };
-        cx0 = pick(xr0, xr1, lane); cx1 = pick(xr0, xr1, lane + 32);
-        cs0 = pick(sl0, sl1, lane); cs1 = pick(sl0, sl1, lane + 32);
-      }
-      const uint32_t zc0 = __ballot_sync(0xffffffffu, cs0 >= 0), zc1 = __ballot_sync(0xffffffffu, cs1 >= 0);
-      // a graph's slots are consecutive in node order (ctrl_need_list_kernel): first slot of the tile's first controlling node
-      const uint32_t zm0 = __ballot_sync(0xffffffffu, sl0 >= 0), zm1 = __ballot_sync(0xffffffffu, sl1 >= 0);
-      int zfirst = 0;
-      if (zm0) zfirst = __shfl_sync(0xffffffffu, sl0, __ffs(zm0) - 1);
-      else if (zm1) zfirst = __shfl_sync(0xffffffffu, sl1, __ffs(zm1) - 1);
-      int xfirst = 0;
-      if (nm0) xfirst = __shfl_sync(0xffffffffu, xr0, __ffs(nm0) - 1);
-      else if (nm1) xfirst = __shfl_sync(0xffffffffu, xr1, __ffs(nm1) - 1);
-      if (warp == 4) { tab_x[lane] = cx0; tab_x[lane + 32] = cx1; tab_s[lane] = cs0; tab_s[lane + 32] = cs1; }
+      const int g0 = tile * G;
       mbar_wait_backoff(tfull_bar(b), (it >> 1) & 1, 64);
       tc_fence_after();
+      // TMEM column t = the t-th needed target of the tile; the producers left the column count and, per column, the
+      // x_out row and the snapshot slot (-1: not a controlling node) in the stage's metadata
+      const int* cnt_b = reinterpret_cast<const int*>(meta + b * kMeta + kMetaSrc + 64);
+      const int* tab_x = reinterpret_cast<const int*>(meta + b * kMeta + kMetaTab);
+      const int* tab_s = tab_x + 64;
+      const int nn = a.pool_mode >= 0 ? 64 : cnt_b[0] + cnt_b[1];
       float pool = 0.f;                          // relu(conv) * dm >= 0: 0 is the identity of max and add here
 #pragma unroll 1
       for (int q = 0; q < 4; ++q) {
@@ -463,6 +433,8 @@ __global__ void __launch_bounds__(kTThreads, 1) attn_table_mma_kernel(const Attn
     uint16_t* cid = reinterpret_cast<uint16_t*>(need_s + 256);                  // [64]
     uint16_t* ptr_s = cid + 64;                                                 // [gt][N+1]
     float* dm_s = reinterpret_cast<float*>(ptr_s + 128);                        // [64] decision-maker flag (pooling variant)
+    int* tabx_s = reinterpret_cast<int*>(meta + team * kMeta + kMetaTab);       // [64] x_out row of TMEM column t
+    int* tabs_s = tabx_s + 64;                                                  // [64] snapshot slot of TMEM column t or -1
     // value gather: 4 lanes per node, lane part p copies the 16-byte chunks 4i + p (i = 0..15) of the node's 1 KiB
     // fp16 row: a warp instruction reads 64 contiguous bytes of each of 8 rows; chunk c lands in panel c >> 3 at
     // 16-byte slot (c & 7) ^ (row & 7) -- all offsets but two per-thread registers are immediates
@@ -488,11 +460,13 @@ __global__ void __launch_bounds__(kTThreads, 1) attn_table_mma_kernel(const Attn
       uint16_t cv = 0;
       uint4 sv = make_uint4(0, 0, 0, 0);
       float dmv = 1.f;
-      int xrv = 0;                                                             // >= 0: somebody reads this target's output
+      int xrv = 0, slv = -1;                                                   // xrv >= 0: somebody reads this target's output (its x_out row)
       if (pt < rt) {
         cv = __ldg(a.row_cid + m0 + pt);
         if (a.pool_mode >= 0) dmv = __ldg(a.obs + (long long)(g0 + pt / N) * a.obs_stride + (pt % N) * 8 + 7);
         if (a.xrow) xrv = __ldg(a.xrow + m0 + pt);
+        else if (a.pool_mode < 0) xrv = (int)m0 + pt;
+        if (a.slot) slv = __ldg(a.slot + m0 + pt);
       }
       if (pt < gt * (N + 1)) {                                                 // gt * (N + 1) <= 128
         const int gl = pt / (N + 1), il = pt - gl * (N + 1);
@@ -533,7 +507,12 @@ __global__ void __launch_bounds__(kTThreads, 1) attn_table_mma_kernel(const Attn
       if (pt < rt * 2) reinterpret_cast<uint4*>(src_s)[pt] = sv;
       if (pt < 64 && lane == 0) cnt_s[pt >> 5] = __popc(nbal);
       bar_team(team);
-      if (pt < rt && xrv >= 0) need_s[(pt >= 32 ? cnt_s[0] : 0) + __popc(nbal & ((1u << lane) - 1u))] = (uint8_t)pt;
+      if (pt < rt && xrv >= 0) {
+        const int rank = (pt >= 32 ? cnt_s[0] : 0) + __popc(nbal & ((1u << lane) - 1u));
+        need_s[rank] = (uint8_t)pt;
+        tabx_s[rank] = xrv;                                                    // for the epilogue (read after the accumulators are ready)
+        tabs_s[rank] = slv;
+      }
       // ---- phase B: value rows of the tile's nodes, asynchronously (swizzled by the node's row residue) ...
       for (int j = pt >> 2; j < rt; j += kTeam / 4) {
         const unsigned char* src = gsrc + (size_t)cid[j] * (HC * 2);

@@ -68,19 +68,34 @@ def _edges(mask: torch.Tensor, targets: torch.Tensor, self_loops: bool):
     return torch.nonzero(m, as_tuple=True)
 
 
+def _used_rows(n_rows, *index_lists):
+    """Rows that appear in an edge list, and the map row -> position among them: the dense projections are evaluated
+    on those rows only (most of a graph's nodes are neither a source nor a target of what one agent reads)."""
+    used = torch.zeros(n_rows, dtype=torch.bool, device=index_lists[0].device)
+    for ix in index_lists:
+        used[ix] = True
+    rows = torch.nonzero(used, as_tuple=True)[0]
+    remap = torch.full((n_rows,), -1, dtype=torch.long, device=rows.device)
+    remap[rows] = torch.arange(rows.numel(), device=rows.device)
+    return rows, remap
+
+
 def _gatv2(conv, x, edges, heads, N):
     """PyG GATv2Conv(concat=True, negative_slope=0.2, add_self_loops=True, share_weights=False) on an edge list.
     x [bs, N, D]; returns [bs*N, H*C] with rows of non-target nodes = bias only (never read)."""
     sm, ti, sj = edges
     bs = x.shape[0]
     C = conv.att.shape[-1]
-    xl = conv.lin_l(x).view(bs * N, heads, C)
-    xr = conv.lin_r(x).view(bs * N, heads, C)
     tgt, src = sm * N + ti, sm * N + sj
-    s = F.leaky_relu(xl[src] + xr[tgt], 0.2)
+    xf = x.reshape(bs * N, -1)
+    rows_s, map_s = _used_rows(bs * N, src)
+    rows_t, map_t = _used_rows(bs * N, tgt)
+    xl = conv.lin_l(xf[rows_s]).view(-1, heads, C)[map_s[src]]               # [E, H, C] source side
+    xr = conv.lin_r(xf[rows_t]).view(-1, heads, C)[map_t[tgt]]               # [E, H, C] target side
+    s = F.leaky_relu(xl + xr, 0.2)
     e = (s * conv.att.view(1, heads, C)).sum(-1)
     a = _segment_softmax(e, tgt, bs * N)
-    out = torch.zeros(bs * N, heads, C, dtype=x.dtype, device=x.device).index_add_(0, tgt, a[:, :, None] * xl[src])
+    out = torch.zeros(bs * N, heads, C, dtype=x.dtype, device=x.device).index_add_(0, tgt, a[:, :, None] * xl)
     return out.view(bs * N, heads * C) + conv.bias
 
 
@@ -90,13 +105,16 @@ def _transformer(conv, x, edges, heads, N):
     bs = x.shape[0]
     HC = conv.lin_query.out_features
     C = HC // heads
-    q = conv.lin_query(x).view(bs * N, heads, C)
-    k = conv.lin_key(x).view(bs * N, heads, C)
-    v = conv.lin_value(x).view(bs * N, heads, C)
     tgt, src = sm * N + ti, sm * N + sj
-    e = (q[tgt] * k[src]).sum(-1) / math.sqrt(C)
+    xf = x.reshape(bs * N, -1)
+    rows_s, map_s = _used_rows(bs * N, src)
+    rows_t, map_t = _used_rows(bs * N, tgt)
+    q = conv.lin_query(xf[rows_t]).view(-1, heads, C)[map_t[tgt]]
+    k = conv.lin_key(xf[rows_s]).view(-1, heads, C)[map_s[src]]
+    v = conv.lin_value(xf[rows_s]).view(-1, heads, C)[map_s[src]]
+    e = (q * k).sum(-1) / math.sqrt(C)
     a = _segment_softmax(e, tgt, bs * N)
-    out = torch.zeros(bs * N, heads, C, dtype=x.dtype, device=x.device).index_add_(0, tgt, a[:, :, None] * v[src])
+    out = torch.zeros(bs * N, heads, C, dtype=x.dtype, device=x.device).index_add_(0, tgt, a[:, :, None] * v)
     return out.view(bs * N, HC)
 
 

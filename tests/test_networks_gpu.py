@@ -396,3 +396,44 @@ def test_tensor_core_table_attention_falls_back_when_keys_overflow():
     q0, a0 = m.forward_graphs(*args)
     q1, a1 = m.forward_graphs(*args, discrete_features=True)
     assert torch.equal(q0, q1) and torch.equal(a0, a1)
+
+
+@pytest.mark.parametrize("kind,kw", [("l_dgn", {}), ("dgn_r", {}), ("hl_dgn", {"aggregator": "max"})])
+def test_bf16_product_path_on_environment_observations_flip_rate(kind, kw):
+    """The headline configuration's inputs, not synthetic feature columns: 4096 episodes of 50-node graphs rolled out for
+    36 rounds with the bf16 product path (discrete-feature tables, tensor-core attention, topology cache); on the
+    observations the environment then holds, the bf16 path and the fp32 CUDA path (the <= 1e-5 parity anchor) are
+    compared decision by decision: max |dq| within the stated bf16 tolerance, and every greedy-action flip sits on a
+    decision whose fp32 margin |q1 - q0| is below 2 * max|dq| (a flip needs both Q-values to move across the gap)."""
+    from melissa_b200.batched_env import BatchedGraphEnv, ResetTuplesDevice
+    from melissa_b200.rollout import Rollout
+    N, B, G = 50, 4096, 64
+    pool = GraphPool.synthetic(N, G, first_seed=0)
+    gi, src, inter, scr, _ = reset_chain.episode_pool(9, 2 * B, N, G)
+    sd = _random_sd(kind, 9)
+    net = _module(kind, N, sd, **kw).set_precision("bf16")
+    env = BatchedGraphEnv(B, N, pool)
+    ro = Rollout(env, net, eps=0.05, seed=9)
+    ro.start(ResetTuplesDevice(gi, src, inter, scr, N, "cuda", pool_size=G))
+    for _ in range(36):
+        ro.round()
+    assert ro.feature_violations() == 0
+    obs, active = env.obs.clone(), env.active.clone()
+    q_b, a_b = net.forward_graphs(obs, active, discrete_features=True, graph_ids=ro.graph_ids, graph_id_stride=8,
+                                  topology_cache=ro.topology_cache, prepared=True)
+    ref = _module(kind, N, sd, **kw)                                  # fp32 kernels
+    q_f, a_f = ref.forward_graphs(obs, active)
+    m = active.bool()
+    n_dec = int(m.sum())
+    assert n_dec > 2 * B
+    dq = float((q_b - q_f).abs()[m].max())
+    scale = max(1.0, float(q_f[m].abs().max()))
+    flips = (a_b != a_f) & m
+    rate = float(flips.sum()) / n_dec
+    margin = (q_f[..., 1] - q_f[..., 0]).abs()
+    worst = float(margin[flips].max()) if bool(flips.any()) else 0.0
+    print(f"{kind}: {n_dec} decisions, max|dq| {dq:.5f} (scale {scale:.2f}), flip rate {rate:.5f}, largest flipped margin {worst:.5f}, "
+          f"median margin {float(margin[m].median()):.4f}")
+    assert dq <= BF16_TOL * scale
+    assert worst <= 2.0 * dq + 1e-7
+    assert rate <= 0.02
