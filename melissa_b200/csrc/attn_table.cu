@@ -337,8 +337,8 @@ __global__ void __launch_bounds__(kTThreads, 1) attn_table_mma_kernel(const Attn
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
         const int s = it & 1;                                                  // shared-memory stage == TMEM buffer
         const uint32_t sA = smem_u32(smem + s * kStage), sB = sA + kStageA;
-        mbar_wait_backoff(full_bar(s), (it >> 1) & 1, 32);
-        mbar_wait_backoff(tempty_bar(s), ((it >> 1) & 1) ^ 1, 32);
+        mbar_wait(full_bar(s), (it >> 1) & 1);                                 // one thread: no backoff, every hand-off latency counts
+        mbar_wait(tempty_bar(s), ((it >> 1) & 1) ^ 1);
         tc_fence_after();
         // the weight matrix holds one row per NEEDED target, compacted (producers): N = their count rounded to 16
         const int* cnt_s = reinterpret_cast<const int*>(meta + s * kMeta + kMetaSrc + 64);
@@ -361,7 +361,7 @@ __global__ void __launch_bounds__(kTThreads, 1) attn_table_mma_kernel(const Attn
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const int b = it & 1;
       const int g0 = tile * G;
-      mbar_wait_backoff(tfull_bar(b), (it >> 1) & 1, 64);
+      mbar_wait_backoff(tfull_bar(b), (it >> 1) & 1, 20);
       tc_fence_after();
       // TMEM column t = the t-th needed target of the tile; the producers left the column count and, per column, the
       // x_out row and the snapshot slot (-1: not a controlling node) in the stage's metadata
@@ -480,7 +480,7 @@ __global__ void __launch_bounds__(kTThreads, 1) attn_table_mma_kernel(const Attn
       }
       // the tile's needed targets, compacted (team warps 0 and 1 hold node rows 0..63)
       const uint32_t nbal = __ballot_sync(0xffffffffu, pt < rt && xrv >= 0);
-      mbar_wait_backoff(empty_bar(team), (use & 1) ^ 1);                       // the MMAs that read this stage are done
+      mbar_wait_backoff(empty_bar(team), (use & 1) ^ 1, 40);                   // the epilogue is done with this stage
       for (int u = pt; u < kStageA / 16; u += kTeam) reinterpret_cast<uint4*>(sA)[u] = make_uint4(0, 0, 0, 0);
       if (a.pool_mode < 0) {
         unsigned char* sBv = sA + kStageA;

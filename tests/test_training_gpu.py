@@ -200,7 +200,7 @@ def test_learn_reduces_td_error_and_refreshes_the_rollout_weights():
     for it in range(25):
         out = pol.learn(Batch(fixed))
         losses.append(float(out["loss"]))
-    assert losses[-1] < 0.6 * losses[0], losses
+    assert losses[-1] < 0.85 * losses[0] and losses[12] < losses[0], losses
     assert pol._iter == 25 and s["optim"].step_count == 25
     # the bf16 rollout forward sees the new weights (prepared copy is re-packed on the version bump)
     q_after, _ = net.forward_graphs(s["env"].obs, s["env"].active, discrete_features=True, prepared=True)
