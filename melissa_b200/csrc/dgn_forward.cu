@@ -9,6 +9,7 @@
 // dgn_r.py:82-129, hl_dgn.py:82-119}; PyG GATv2Conv/TransformerConv/softmax/pool,
 // torch_cluster radius_graph, tianshou MLP/DQNPolicy.
 #include "dgn_kernels.cuh"
+#include "gemm_tcgen05.cuh"
 
 namespace mls {
 
@@ -89,6 +90,44 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A,
       C[(size_t)r * ldc + c] = v;
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// fp32-grade GEMM on the tensor cores.  Every fp32 operand value is split three ways into bf16,
+//     a = hi + mid + lo,  hi = bf16(a), mid = bf16(a - hi), lo = bf16(a - hi - mid)      (|a - hi - mid - lo| <= 2^-26 |a|)
+// and the six significant cross products hi.hi + hi.mid + mid.hi + hi.lo + lo.hi + mid.mid (dropped terms <= 2^-26) become
+// ONE bf16 GEMM by concatenating the pieces along K:
+//     A' = [hi | hi | mid | hi | lo | mid]   (M x 6K),   B' = [hi | mid | hi | lo | hi | mid]   (N x 6K)
+// accumulated in fp32 in TMEM by gemm_bf16_tcgen05_kernel, which then writes fp32 (GemmEpilogue::Cf).
+// which = 0: A' pattern, 1: B' pattern.  One thread per (row, 4 columns).
+__global__ void __launch_bounds__(256) split3_kernel(const float* __restrict__ X, int ld, long long rows, int K, int which,
+                                                     __nv_bfloat16* __restrict__ out) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int kq = K >> 2;
+  if (t >= rows * kq) return;
+  const long long r = t / kq;
+  const int k = (int)(t - r * kq) * 4;
+  const float4 v = *reinterpret_cast<const float4*>(X + r * ld + k);
+  const float a[4] = {v.x, v.y, v.z, v.w};
+  __nv_bfloat16 hi[4], mid[4], lo[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    hi[i] = __float2bfloat16_rn(a[i]);
+    const float r1 = a[i] - __bfloat162float(hi[i]);
+    mid[i] = __float2bfloat16_rn(r1);
+    lo[i] = __float2bfloat16_rn(r1 - __bfloat162float(mid[i]));
+  }
+  auto pack = [](const __nv_bfloat16* p) {
+    uint2 u;
+    u.x = (uint32_t)__bfloat16_as_ushort(p[0]) | ((uint32_t)__bfloat16_as_ushort(p[1]) << 16);
+    u.y = (uint32_t)__bfloat16_as_ushort(p[2]) | ((uint32_t)__bfloat16_as_ushort(p[3]) << 16);
+    return u;
+  };
+  const uint2 H = pack(hi), Mi = pack(mid), L = pack(lo);
+  __nv_bfloat16* o = out + r * (6ll * K) + k;
+  const uint2 seqA[6] = {H, H, Mi, H, L, Mi}, seqB[6] = {H, Mi, H, L, H, Mi};
+#pragma unroll
+  for (int p = 0; p < 6; ++p) *reinterpret_cast<uint2*>(o + (long long)p * K) = which ? seqB[p] : seqA[p];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -377,12 +416,17 @@ using namespace mls;
 struct Ws {      // fp32 workspace carve-up for a chunk of Gc graphs (R = Gc*N rows)
   float *h, *x0, *P, *x1, *x2, *z, *hid1, *hid2, *qg;
   int *idx, *count;
+  // tensor-core route (option fp32_tc): 3-way bf16 splits of the weights (B' operands) and of the current activation (A')
+  __nv_bfloat16 *asplit, *w_enc1, *w_c1[3], *w_c2[3], *w_q0, *w_v0, *w_q1, *w_v1;
 };
+
+bool fp32_tc_enabled() { return mls_get_option("fp32_tc") != 0; }
 
 size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
 
 int chunk_graphs(const MlsNetDesc* d, int n_graphs) {
-  int gc = 8192 / d->n_nodes;
+  // tensor-core route: 32768-row chunks (256 GEMM tiles of 128 rows); SIMT route: L2-sized chunks
+  int gc = (fp32_tc_enabled() ? 32768 : 8192) / d->n_nodes;
   if (gc < 1) gc = 1;
   return n_graphs < gc ? n_graphs : gc;
 }
@@ -400,7 +444,20 @@ size_t carve(const MlsNetDesc* d, int Gc, unsigned char* base, Ws* ws) {
   size_t o_z = take(head_rows * latent * 4), o_h1 = take(head_rows * 2 * d->head_hidden * 4);
   size_t o_h2 = take(head_rows * 2 * d->head_hidden * 4), o_qg = take((size_t)Gc * 2 * 4);
   size_t o_idx = take(R * 4), o_cnt = take(4);
+  const bool tc = fp32_tc_enabled();
+  const int hh = d->head_hidden;
+  const size_t kmax = (size_t)(latent > HC ? latent : HC);
+  size_t o_as = take(tc ? R * 6 * kmax * 2 : 0), o_we = take(tc ? (size_t)hid * 6 * hid * 2 : 0);
+  size_t o_wc1[3], o_wc2[3];
+  for (int t = 0; t < 3; ++t) o_wc1[t] = take(tc && t < nproj ? (size_t)HC * 6 * hid * 2 : 0);
+  for (int t = 0; t < 3; ++t) o_wc2[t] = take(tc && t < nproj && d->kind != MLS_NET_HL_DGN ? (size_t)HC * 6 * HC * 2 : 0);
+  size_t o_wq0 = take(tc ? (size_t)hh * 6 * latent * 2 : 0), o_wv0 = take(tc ? (size_t)hh * 6 * latent * 2 : 0);
+  size_t o_wq1 = take(tc ? (size_t)hh * 6 * hh * 2 : 0), o_wv1 = take(tc ? (size_t)hh * 6 * hh * 2 : 0);
   if (ws) {
+    auto B16 = [&](size_t o) { return reinterpret_cast<__nv_bfloat16*>(base + o); };
+    ws->asplit = B16(o_as); ws->w_enc1 = B16(o_we);
+    for (int t = 0; t < 3; ++t) { ws->w_c1[t] = B16(o_wc1[t]); ws->w_c2[t] = B16(o_wc2[t]); }
+    ws->w_q0 = B16(o_wq0); ws->w_v0 = B16(o_wv0); ws->w_q1 = B16(o_wq1); ws->w_v1 = B16(o_wv1);
     ws->h = (float*)(base + o_h); ws->x0 = (float*)(base + o_x0); ws->P = (float*)(base + o_P);
     ws->x1 = (float*)(base + o_x1); ws->x2 = (float*)(base + o_x2); ws->z = (float*)(base + o_z);
     ws->hid1 = (float*)(base + o_h1); ws->hid2 = (float*)(base + o_h2); ws->qg = (float*)(base + o_qg);
@@ -414,6 +471,23 @@ void sgemm(cudaStream_t st, const float* A, int lda, const float* obs_scale, int
   dim3 grid((Nout + GB - 1) / GB, (M + GB - 1) / GB);
   sgemm_kernel<<<grid, 256, 0, st>>>(A, lda, obs_scale, obs_stride, N, Wt, ldw, bias, C, ldc, M, m_dev, Nout, K, relu);
   mls_count_launch();
+}
+
+void split3(cudaStream_t st, const float* X, int ld, long long rows, int K, int which, __nv_bfloat16* out) {
+  const long long n = rows * (K >> 2);
+  split3_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(X, ld, rows, K, which, out);
+  mls_count_launch();
+}
+
+// Same contract as sgemm, on the tensor cores: A is split into `scratch` (M x 6K bf16), Wsplit is the pre-split weight.
+int tcgemm(cudaStream_t st, int sms, const float* A, int lda, const float* obs_scale, int64_t obs_stride, int N,
+           const __nv_bfloat16* Wsplit, const float* bias, float* C, int ldc, int M, const int* m_dev, int Nout, int K, int relu,
+           __nv_bfloat16* scratch) {
+  split3(st, A, lda, M, K, 0, scratch);
+  GemmEpilogue e{};
+  e.C = nullptr; e.ldc = 0; e.bias = bias; e.obs = obs_scale; e.obs_stride = obs_stride; e.nodes = N; e.relu = relu;
+  e.Cf = C; e.ldcf = ldc;
+  return gemm_bf16_launch(scratch, 6 * K, Wsplit, 6 * K, GemmShape{M, Nout, 6 * K, m_dev}, e, sms, st);
 }
 
 template <int W>
@@ -514,6 +588,34 @@ extern "C" int mls_dgn_forward(const MlsNetDesc* d, const MlsNetWeights* w, cons
   bool first_chunk = true;
   auto prof_begin = [&](int which) { if (first_chunk && ev0 && ev1 && a->prof_kernel == which) cudaEventRecord(ev0, st); };
   auto prof_end = [&](int which) { if (first_chunk && ev0 && ev1 && a->prof_kernel == which) cudaEventRecord(ev1, st); };
+  // dense layers: tensor cores through the 3-way bf16 split (fp32-grade), or the SIMT sgemm (option fp32_tc = 0)
+  const bool tc = fp32_tc_enabled() && hid % 64 == 0 && hh % 128 == 0;
+  int sms = 0, rc_g = MLS_OK;
+  if (tc) {
+    int dev = 0;
+    MLS_CUDA(cudaGetDevice(&dev));
+    MLS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    split3(st, w->enc_w1, hid, hid, hid, 1, ws.w_enc1);
+    const float* c1w[3] = {w->c1_wa, w->c1_wb, w->c1_wc};
+    const float* c2w[3] = {w->c2_wa, w->c2_wb, w->c2_wc};
+    for (int t = 0; t < nproj; ++t) {
+      split3(st, c1w[t], hid, HC, hid, 1, ws.w_c1[t]);
+      if (!hl) split3(st, c2w[t], HC, HC, HC, 1, ws.w_c2[t]);
+    }
+    split3(st, w->q_w0, latent, hh, latent, 1, ws.w_q0);
+    split3(st, w->v_w0, latent, hh, latent, 1, ws.w_v0);
+    split3(st, w->q_w1, hh, hh, hh, 1, ws.w_q1);
+    split3(st, w->v_w1, hh, hh, hh, 1, ws.w_v1);
+  }
+  auto gemm32 = [&](const float* A, int lda, const float* obs_scale, const float* Wt, const __nv_bfloat16* Wsplit, int ldw,
+                    const float* bias, float* C, int ldc, int M, const int* m_dev, int Nout, int K, int relu) {
+    if (tc) {
+      const int rc = tcgemm(st, sms, A, lda, obs_scale, a->obs_stride, N, Wsplit, bias, C, ldc, M, m_dev, Nout, K, relu, ws.asplit);
+      if (rc) rc_g = rc;
+    } else {
+      sgemm(st, A, lda, obs_scale, a->obs_stride, N, Wt, ldw, bias, C, ldc, M, m_dev, Nout, K, relu);
+    }
+  };
   auto edge = [&](const float* P, const float* obs, int rows, const float* att, const float* bias, float* out) {
     if (tr) {
       switch (Wn) {
@@ -533,12 +635,20 @@ extern "C" int mls_dgn_forward(const MlsNetDesc* d, const MlsNetWeights* w, cons
   };
   // projection weights are separate tensors in the state_dict: one GEMM per tensor, written side by side
   auto project = [&](const float* X, int K, const float* obs_scale, int prof_id, const float* wa, const float* ba,
-                     const float* wb, const float* bb, const float* wc, const float* bc, int rows) {
+                     const float* wb, const float* bb, const float* wc, const float* bc, int rows, __nv_bfloat16* const* wsplit) {
     const float* ws_[3] = {wa, wb, wc};
     const float* bs_[3] = {ba, bb, bc};
+    if (tc) split3(st, X, K, rows, K, 0, ws.asplit);                 // one split of the input serves all projections
     for (int t = 0; t < nproj; ++t) {
       if (t == 0) prof_begin(prof_id);
-      sgemm(st, X, K, obs_scale, a->obs_stride, N, ws_[t], K, bs_[t], ws.P + (size_t)t * HC, nproj * HC, rows, nullptr, HC, K, 0);
+      if (tc) {
+        GemmEpilogue e{};
+        e.bias = bs_[t]; e.obs = obs_scale; e.obs_stride = a->obs_stride; e.nodes = N; e.Cf = ws.P + (size_t)t * HC; e.ldcf = nproj * HC;
+        const int rc = gemm_bf16_launch(ws.asplit, 6 * K, wsplit[t], 6 * K, GemmShape{rows, HC, 6 * K, nullptr}, e, sms, st);
+        if (rc) rc_g = rc;
+      } else {
+        sgemm(st, X, K, obs_scale, a->obs_stride, N, ws_[t], K, bs_[t], ws.P + (size_t)t * HC, nproj * HC, rows, nullptr, HC, K, 0);
+      }
       if (t == 0) prof_end(prof_id);
     }
   };
@@ -553,18 +663,18 @@ extern "C" int mls_dgn_forward(const MlsNetDesc* d, const MlsNetWeights* w, cons
       dim3 blk(32, 8);
       enc0_kernel<<<(rows + 7) / 8, blk, 0, st>>>(obs, a->obs_stride, N, rows, d->input_dim, w->enc_w0, w->enc_b0, hid, ws.h);
       mls_count_launch();
-      sgemm(st, ws.h, hid, nullptr, 0, N, w->enc_w1, hid, w->enc_b1, ws.x0, hid, rows, nullptr, hid, hid, 1);
+      gemm32(ws.h, hid, nullptr, w->enc_w1, ws.w_enc1, hid, w->enc_b1, ws.x0, hid, rows, nullptr, hid, hid, 1);
     }
     // conv1 (+relu)
-    if (tr) project(ws.x0, hid, nullptr, MLS_PROF_PROJ1, w->c1_wa, w->c1_ba, w->c1_wb, w->c1_bb, w->c1_wc, w->c1_bc, rows);
-    else project(ws.x0, hid, nullptr, MLS_PROF_PROJ1, w->c1_wa, w->c1_ba, w->c1_wb, w->c1_bb, nullptr, nullptr, rows);
+    if (tr) project(ws.x0, hid, nullptr, MLS_PROF_PROJ1, w->c1_wa, w->c1_ba, w->c1_wb, w->c1_bb, w->c1_wc, w->c1_bc, rows, ws.w_c1);
+    else project(ws.x0, hid, nullptr, MLS_PROF_PROJ1, w->c1_wa, w->c1_ba, w->c1_wb, w->c1_bb, nullptr, nullptr, rows, ws.w_c1);
     prof_begin(MLS_PROF_EDGE1);
     edge(ws.P, obs, rows, w->c1_att, w->c1_bias, ws.x1);
     prof_end(MLS_PROF_EDGE1);
     if (!hl) {
       // conv2 on x1 * dm (+relu); the x1 snapshot used by the head stays unmasked
-      if (tr) project(ws.x1, HC, obs, MLS_PROF_PROJ2, w->c2_wa, w->c2_ba, w->c2_wb, w->c2_bb, w->c2_wc, w->c2_bc, rows);
-      else project(ws.x1, HC, obs, MLS_PROF_PROJ2, w->c2_wa, w->c2_ba, w->c2_wb, w->c2_bb, nullptr, nullptr, rows);
+      if (tr) project(ws.x1, HC, obs, MLS_PROF_PROJ2, w->c2_wa, w->c2_ba, w->c2_wb, w->c2_bb, w->c2_wc, w->c2_bc, rows, ws.w_c2);
+      else project(ws.x1, HC, obs, MLS_PROF_PROJ2, w->c2_wa, w->c2_ba, w->c2_wb, w->c2_bb, nullptr, nullptr, rows, ws.w_c2);
       prof_begin(MLS_PROF_EDGE2);
       edge(ws.P, obs, rows, w->c2_att, w->c2_bias, ws.x2);
       prof_end(MLS_PROF_EDGE2);
@@ -580,11 +690,12 @@ extern "C" int mls_dgn_forward(const MlsNetDesc* d, const MlsNetWeights* w, cons
     const int* m_dev = hl ? nullptr : ws.count;
     // dueling head: Q = MLP(latent->hh->hh->2), V = MLP(latent->hh->hh->1)
     prof_begin(MLS_PROF_HEAD0);
-    sgemm(st, ws.z, latent, nullptr, 0, N, w->q_w0, latent, w->q_b0, ws.hid1, 2 * hh, head_rows, m_dev, hh, latent, 1);
+    gemm32(ws.z, latent, nullptr, w->q_w0, ws.w_q0, latent, w->q_b0, ws.hid1, 2 * hh, head_rows, m_dev, hh, latent, 1);
     prof_end(MLS_PROF_HEAD0);
-    sgemm(st, ws.z, latent, nullptr, 0, N, w->v_w0, latent, w->v_b0, ws.hid1 + hh, 2 * hh, head_rows, m_dev, hh, latent, 1);
-    sgemm(st, ws.hid1, 2 * hh, nullptr, 0, N, w->q_w1, hh, w->q_b1, ws.hid2, 2 * hh, head_rows, m_dev, hh, hh, 1);
-    sgemm(st, ws.hid1 + hh, 2 * hh, nullptr, 0, N, w->v_w1, hh, w->v_b1, ws.hid2 + hh, 2 * hh, head_rows, m_dev, hh, hh, 1);
+    gemm32(ws.z, latent, nullptr, w->v_w0, ws.w_v0, latent, w->v_b0, ws.hid1 + hh, 2 * hh, head_rows, m_dev, hh, latent, 1);
+    gemm32(ws.hid1, 2 * hh, nullptr, w->q_w1, ws.w_q1, hh, w->q_b1, ws.hid2, 2 * hh, head_rows, m_dev, hh, hh, 1);
+    gemm32(ws.hid1 + hh, 2 * hh, nullptr, w->v_w1, ws.w_v1, hh, w->v_b1, ws.hid2 + hh, 2 * hh, head_rows, m_dev, hh, hh, 1);
+    if (rc_g) return rc_g;
     if (!hl) {
       head_out_kernel<<<(rows * 32 + 255) / 256, 256, 0, st>>>(ws.hid2, hh, ws.idx, ws.count, rows, w->q_w2, w->q_b2, w->v_w2,
                                                                w->v_b2, (int64_t)g0 * N, N, a->q, a->act, a->ctrl_mode, aa);

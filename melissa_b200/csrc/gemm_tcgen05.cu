@@ -168,6 +168,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             }
           }
           if (epi.relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f); }
+          if (epi.Cf && r < M)                                // lane = row: 16-byte stores, 128 contiguous bytes per lane and chunk
+            *reinterpret_cast<float4*>(epi.Cf + (size_t)r * epi.ldcf + n0 + c0 + j) = make_float4(x0, x1, x2, x3);
           if (epi.c_fp16) {
             asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(packed[j >> 1]) : "f"(x1), "f"(x0));
             asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(packed[(j >> 1) + 1]) : "f"(x3), "f"(x2));
@@ -268,7 +270,8 @@ int gemm_bf16_launch(const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, in
                      int sm_count, cudaStream_t st) {
   MLS_CHECK_ARG(shape.K % kBK == 0 && shape.K >= kBK, "GEMM K must be a multiple of %d (got %d)", kBK, shape.K);
   MLS_CHECK_ARG(shape.N % 128 == 0, "GEMM N must be a multiple of 128 (got %d)", shape.N);
-  MLS_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0 && epi.ldc % 8 == 0, "GEMM leading dimensions must be multiples of 8 elements");
+  MLS_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0 && (!epi.C || epi.ldc % 8 == 0), "GEMM leading dimensions must be multiples of 8 elements");
+  MLS_CHECK_ARG(!epi.Cf || (epi.ldcf % 4 == 0 && (reinterpret_cast<uintptr_t>(epi.Cf) & 15) == 0), "fp32 GEMM output must be 16-byte aligned");
   MLS_CHECK_ARG(!epi.dotvec || shape.N % 256 == 0, "the fused per-group dot products need N to be a multiple of 256");
   if (shape.M <= 0) return MLS_OK;
   const int BN = (shape.N % 256 == 0) ? 256 : 128;

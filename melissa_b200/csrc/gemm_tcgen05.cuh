@@ -39,6 +39,10 @@ struct GemmEpilogue {
   // C is written as IEEE fp16 (saturated to +-65504) instead of bf16: 11 significant bits for operands that feed
   // packed-half math (conv2 attention)
   int c_fp16;
+  // optional fp32 output (beside or instead of C): Cf[m][n] = the epilogue value before narrowing.  Used by the
+  // fp32-grade route, whose operands are 3-way bf16 splits concatenated along K (dgn_forward.cu).
+  float* Cf;
+  int ldcf;
 };
 
 struct GemmShape {

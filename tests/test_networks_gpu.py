@@ -437,3 +437,32 @@ def test_bf16_product_path_on_environment_observations_flip_rate(kind, kw):
     assert dq <= BF16_TOL * scale
     assert worst <= 2.0 * dq + 1e-7
     assert rate <= 0.02
+
+
+@pytest.mark.parametrize("kind,kw", [("l_dgn", {}), ("dgn_r", {}), ("hl_dgn", {"aggregator": "mean"})])
+def test_fp32_tensor_core_route_meets_the_fp32_bar(kind, kw):
+    """precision fp32 runs its dense layers on tcgen05 through 3-way bf16 operand splits concatenated along K
+    (option fp32_tc, default on): same <= 1e-5 bar against the fp32 oracle as the SIMT sgemm route, on a batch large
+    enough for several 128-row GEMM tiles and with trained-scale (x8) weights in one layer to stress the split."""
+    from melissa_b200 import _lib
+    N, B = 50, 60
+    sd = _random_sd(kind, 33)
+    sd["conv1.lin_l.weight" if kind != "dgn_r" else "conv1.lin_key.weight"] *= 8.0
+    om = _obs_matrix(N, B, 41)
+    cm = np.random.default_rng(6).random((B, N)) < 0.3
+    want = no.forward_graphs(kind, sd, torch.as_tensor(om), torch.as_tensor(cm), N, **kw).numpy()
+    m = _module(kind, N, sd, **kw)
+    args = (torch.as_tensor(om, device="cuda"), torch.as_tensor(cm, device="cuda").to(torch.uint8))
+    assert _lib.get_option("fp32_tc") == 1
+    q1, a1 = m.forward_graphs(*args)
+    _assert_q(q1.cpu().numpy(), want, f"{kind} fp32 tensor-core route")
+    _lib.set_option("fp32_tc", 0)
+    try:
+        q0, a0 = m.forward_graphs(*args)
+    finally:
+        _lib.set_option("fp32_tc", 1)
+    _assert_q(q0.cpu().numpy(), want, f"{kind} fp32 SIMT route")
+    scale = max(1.0, float(np.abs(want).max()))
+    print(f"{kind}: tensor-core route err {float(np.abs(q1.cpu().numpy() - want).max()):.2e}, SIMT route err "
+          f"{float(np.abs(q0.cpu().numpy() - want).max()):.2e} (scale {scale:.2f})")
+    assert not torch.equal(q0, q1)                          # really another code path
