@@ -371,7 +371,8 @@ class MultiAgentSharedPolicy:
 
     def __init__(self, policy: DQNPolicy, env, **kwargs):
         self.policy = policy
-        self.agents = list(getattr(env, "agents", env))
+        # tianshou's PettingZooEnv exposes ``agents = possible_agents``; a bare AEC env's ``agents`` is the live subset
+        self.agents = list(getattr(env, "possible_agents", None) or getattr(env, "agents", env))
         self.agent_idx = getattr(env, "agent_idx", {a: i for i, a in enumerate(self.agents)})
         self.action_space = getattr(env, "action_space", None)
 
