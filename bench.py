@@ -178,6 +178,8 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"          # the version banner goes to stdout, which carries the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     peaks = {}
     try:

@@ -67,19 +67,26 @@ class CudaRoundStepper:
     def _pos(self):
         return self.env.pos.cpu().numpy()[0] if self.dynamic else self._static_pos
 
-    def reset(self, adj, pos, source, interested, scripted, move_offsets=None):
+    def has_taken_action(self):
+        return self.env.flags()["has_taken_action"][0]
+
+    def reset(self, adj, pos, source, interested, scripted, move_offsets=None, gossip_bits=None, relay_bits=None):
         from .batched_env import ResetTuplesDevice
         pool = topology.GraphPool(adj[None], pos[None])
         self.env = self._mk(pool)                       # a fresh single-slot environment on the given topology
         self._static_adj, self._static_pos = adj.copy(), pos.copy()
         tup = ResetTuplesDevice(np.zeros(1, np.int32), np.array([source], np.int32), interested[None], scripted[None],
                                 self.N, self.device)
-        obs, active = self.env.reset(tup, move_offsets=None if move_offsets is None else move_offsets[None])
+        obs, active = self.env.reset(tup, move_offsets=None if move_offsets is None else move_offsets[None],
+                                     gossip_bits=None if gossip_bits is None else gossip_bits[None],
+                                     relay_bits=None if relay_bits is None else relay_bits[None])
         return dict(obs=obs.cpu().numpy()[0], active=active.cpu().numpy()[0].astype(bool), adj=self._adj(), pos=self._pos())
 
-    def step(self, actions, move_offsets=None):
+    def step(self, actions, move_offsets=None, gossip_bits=None, relay_bits=None):
         obs, rew, active, term, done = self.env.step(np.asarray(actions, dtype=np.int8)[None],
-                                                     move_offsets=None if move_offsets is None else move_offsets[None])
+                                                     move_offsets=None if move_offsets is None else move_offsets[None],
+                                                     gossip_bits=None if gossip_bits is None else gossip_bits[None],
+                                                     relay_bits=None if relay_bits is None else relay_bits[None])
         return dict(obs=obs.cpu().numpy()[0], reward=rew.cpu().numpy()[0], active=active.cpu().numpy()[0].astype(bool),
                     terminated=term.cpu().numpy()[0].astype(bool), done=bool(done.cpu().numpy()[0]), adj=self._adj(),
                     pos=self._pos())
@@ -139,11 +146,10 @@ class GraphEnv:
             raise ValueError(f"Unknown heuristic policy: {heuristic}")
         if heuristic_params is not None and not isinstance(heuristic_params, dict):
             raise ValueError("Heuristic parameters must be a dictionary.")
-        if heuristic in ("probabilistic_gossip", "probabilistic_relay"):
-            raise NotImplementedError("probabilistic heuristics draw from numpy's global RNG in the reference; "
-                                      "use BatchedGraphEnv with host-fed bits")
-        if random_graph:
-            raise NotImplementedError("random_graph=True is not part of the accelerated path")
+        self.heuristic_params = dict(heuristic_params or {})
+        if heuristic in ("probabilistic_gossip", "probabilistic_relay") and "prob" not in self.heuristic_params:
+            raise TypeError(f"{heuristic}() missing 1 required positional argument: 'prob'")     # what the reference's partial raises
+        self.random_graph = bool(random_graph)
         self.device, self.render_mode, self.local_ratio, self.radius = device, render_mode, local_ratio, radius
         self.number_of_agents = N = number_of_agents
         self.max_cycles = max_cycles
@@ -156,6 +162,8 @@ class GraphEnv:
         if self.is_graph_fixed:
             self._graph_adj, self._graph_pos = topology.graph_to_arrays(graph, N)
             self._graph_paths = []
+        elif self.random_graph and not is_testing:
+            self._graph_paths = []                      # every training episode draws a fresh graph (core.py:375-376)
         else:
             split = "testing" if is_testing else "training"
             self._graph_paths = topology.list_topology_dir(".", N, split)
@@ -179,7 +187,12 @@ class GraphEnv:
         self._skip_agent_selection = None
         # the reference constructor performs two unseeded resets (core.py:190, graph.py:117); keep the
         # RNG / test-episode cursor in the same place
-        self._draw_reset_tuple()
+        t0 = self._draw_reset_tuple()
+        if self.random_graph and not is_testing:
+            self._topology_for(t0)                      # World.__init__'s own reset draws (and discards) a graph too
+        if heuristic in ("probabilistic_gossip", "probabilistic_relay"):
+            self._scripted = t0.scripted.copy()         # ... and its forced first step draws the heuristics' bits
+            self._heuristic_bits(np.zeros(N, dtype=bool))
         self.reset()
 
     # ------------------------------------------------------------------ plumbing
@@ -201,16 +214,45 @@ class GraphEnv:
     def close(self):
         return None
 
+    def _heuristic_bits(self, has_taken_action):
+        """The probabilistic heuristics draw from numpy's GLOBAL stream, one scripted agent after the other in id order
+        (heuristics/core.py:20-42, World.step core.py:226-235): probabilistic_gossip one binomial(1, prob) per scripted
+        agent that has not taken its action yet, probabilistic_relay binomial(1, prob, size=N) per scripted agent (the
+        kernel masks it with the agent's 1-hop row).  Same draws, fed to the kernel as bits."""
+        N, prob = self.number_of_agents, self.heuristic_params.get("prob")
+        if self.heuristic == "probabilistic_gossip":
+            bits = np.zeros(N, dtype=np.uint8)
+            for i in np.flatnonzero(self._scripted):
+                if not has_taken_action[i]:
+                    bits[i] = np.random.binomial(1, prob)
+            return dict(gossip_bits=bits)
+        if self.heuristic == "probabilistic_relay":
+            m = np.zeros((N, N), dtype=bool)
+            for i in np.flatnonzero(self._scripted):
+                m[i] = np.random.binomial(1, prob, size=N).astype(bool)
+            return dict(relay_bits=m)
+        return {}
+
     def _draw_reset_tuple(self):
         N = self.number_of_agents
         if self.is_testing:
             t = self._test_stream.next(self.np_random, self.scripted_agents_ratio)
         else:
-            t = reset_chain.training_reset(self.np_random, N, n_graphs=0 if self.is_graph_fixed else len(self._graph_paths),
+            fixed = self.is_graph_fixed or self.random_graph          # neither draws np_random.choice(train_graphs)
+            t = reset_chain.training_reset(self.np_random, N, n_graphs=0 if fixed else len(self._graph_paths),
                                            scripted_agents_ratio=self.scripted_agents_ratio)
         return t
 
     def _topology_for(self, t):
+        if self.random_graph and not self.is_testing:
+            # core.py:375-376 + create_connected_graph (core.py:440-447): nx.random_geometric_graph(n, radius) -- positions
+            # from networkx's default (Python global `random`) stream, exactly as the reference draws them -- until connected
+            import networkx as nx
+            while True:
+                g = nx.random_geometric_graph(n=self.number_of_agents, radius=self.radius)
+                if nx.is_connected(g):
+                    break
+            return topology.graph_to_arrays(g, self.number_of_agents)
         if self.is_graph_fixed:
             return self._graph_adj, self._graph_pos
         return topology.graph_to_arrays(topology.load_graph(self._graph_paths[t.graph_index]), self.number_of_agents)
@@ -232,10 +274,10 @@ class GraphEnv:
         adj, pos = self._topology_for(t)
         self._movement_rng = np.random.RandomState(t.movement_seed)
         mo = reset_chain.movement_offsets(self._movement_rng, N) if self.dynamic_graph else None
-        out = self.stepper.reset(adj, pos, t.source, t.interested, t.scripted, mo)
+        self._scripted = t.scripted.copy()
+        out = self.stepper.reset(adj, pos, t.source, t.interested, t.scripted, mo, **self._heuristic_bits(np.zeros(N, dtype=bool)))
         self._after_world_step(out)
         self.origin_agent = t.source
-        self._scripted = t.scripted.copy()
         self._truncated = np.zeros(N, dtype=bool)
         self.agents = [str(i) for i in np.flatnonzero(out["active"])]                       # graph.py:242-245
         self._agent_selector.enable(self.agents, on_reset=True, source_agent=str(t.source))
@@ -310,7 +352,8 @@ class GraphEnv:
             N = self.number_of_agents
             acts = np.array([-1 if a is None else int(a) for a in self.current_actions], dtype=np.int8)
             mo = reset_chain.movement_offsets(self._movement_rng, N) if self.dynamic_graph else None
-            out = self.stepper.step(acts, mo)
+            hb = self._heuristic_bits(self.stepper.has_taken_action()) if self.heuristic in ("probabilistic_gossip", "probabilistic_relay") else {}
+            out = self.stepper.step(acts, mo, **hb)
             self._after_world_step(out)
             for a in self.agents:
                 self.rewards[a] = float(out["reward"][int(a)])

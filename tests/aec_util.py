@@ -28,16 +28,23 @@ class OracleRoundStepper:
         d.update(extra or {})
         return d
 
-    def reset(self, adj, pos, source, interested, scripted, move_offsets=None):
+    def has_taken_action(self):
+        return self.o.has_taken_action[0].copy()
+
+    def reset(self, adj, pos, source, interested, scripted, move_offsets=None, gossip_bits=None, relay_bits=None):
         from oracle.env_oracle import BatchedEnvOracle
         self.o = BatchedEnvOracle(1, self.N, dynamic=self.dynamic, is_testing=self.is_testing, heuristic=self.heuristic)
         self.o.reset([0], adj[None], pos[None], np.array([source]), interested[None], scripted[None],
-                     move_offsets=None if move_offsets is None else move_offsets[None])
+                     move_offsets=None if move_offsets is None else move_offsets[None],
+                     gossip_bits=None if gossip_bits is None else gossip_bits[None],
+                     relay_bits=None if relay_bits is None else relay_bits[None])
         return self._pack()
 
-    def step(self, actions, move_offsets=None):
+    def step(self, actions, move_offsets=None, gossip_bits=None, relay_bits=None):
         obs, rew, active, term, done = self.o.step(np.asarray(actions, dtype=np.int8)[None],
-                                                   move_offsets=None if move_offsets is None else move_offsets[None])
+                                                   move_offsets=None if move_offsets is None else move_offsets[None],
+                                                   gossip_bits=None if gossip_bits is None else gossip_bits[None],
+                                                   relay_bits=None if relay_bits is None else relay_bits[None])
         return self._pack(dict(reward=rew[0], terminated=term[0], done=bool(done[0])))
 
     def info(self):
