@@ -277,6 +277,18 @@ def run_ours(args):
     ms, trans, launches, _, _ = timed(ro.round, args.steps)
     clocks.mark_end()
     clk = clocks.stop() if rank == 0 else None
+    # row-set sizes of the forward at the benchmark state (means over the resident episodes): controlling nodes,
+    # needed rows (controlling nodes + their radius-graph sources: the only rows of conv1's output anybody reads),
+    # conv2 edge-list entries (self loops included for GATv2)
+    sets = None
+    if net is not None and two_convs and not args.dynamic:
+        act = env.active.bool()
+        adj = torch.as_tensor(pool.adj, device=dev)[env.episode[:, 3].long()]           # [B, i, j]
+        srcs = adj & act[:, :, None]                                                     # sources j of controlling targets i
+        need = act | srcs.any(1)
+        sets = {"ctrl": float(act.sum()) / B, "needed": float(need.sum()) / B,
+                "edges": float(srcs.sum()) / B + (float(act.sum()) / B if args.model == "l_dgn" else 0.0)}
+        del adj, srcs, need
     if net is not None and ro.feature_violations() != 0:
         raise RuntimeError("discrete-feature mode: the environment produced non-integer feature columns")
     launches_per_step = None
@@ -327,18 +339,6 @@ def run_ours(args):
                                         finish=ro.host_drain if pipelined else None)
         e2e = (e_ms, e_trans, ex[0])
 
-    # row-set sizes of the forward at the benchmark state (means over the resident episodes): controlling nodes,
-    # needed rows (controlling nodes + their radius-graph sources: the only rows of conv1's output anybody reads),
-    # conv2 edge-list entries (self loops included for GATv2)
-    sets = None
-    if net is not None and two_convs:
-        act = env.active.bool()
-        adj = torch.as_tensor(pool.adj, device=dev)[env.episode[:, 3].long()]           # [B, i, j]
-        srcs = adj & act[:, :, None]                                                     # sources j of controlling targets i
-        need = act | srcs.any(1)
-        sets = {"ctrl": float(act.sum()) / B, "needed": float(need.sum()) / B,
-                "edges": float(srcs.sum()) / B + (float(act.sum()) / B if args.model == "l_dgn" else 0.0)}
-        del adj, srcs, need
     flip = None
     if net is not None and args.precision == "bf16" and not args.no_flip and not args.dynamic and rank == 0:
         flip = measure_flip_rate(dev, args.model, N, env, net, ro)

@@ -30,9 +30,7 @@ namespace {
 constexpr int kThreads = 128;
 constexpr int kPanel = 64 * 128;          // one 64-channel panel of the value operand: 64 source rows x 128 B
 constexpr int kXBytes = 2 * kPanel;       // the head's 128 channels
-constexpr int kWBytes = 64 * 128;         // W[target][source]: 64 rows of 64 fp16
 constexpr int kRowPad = kC * 2 + 16;      // padded row of 128 fp16 (bank-conflict-free 16 B reads by row-owning lanes)
-constexpr int kCols = 64;                 // TMEM columns per CTA
 
 __device__ __forceinline__ void cp16(unsigned char* dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
@@ -56,45 +54,53 @@ __device__ __forceinline__ uint64_t desc_mn(uint32_t smem_addr, uint32_t lbo16, 
   return d;
 }
 
-struct Conv2Layout {       // shared-memory offsets behind the three 1024-byte aligned MMA operands
-  int edge_cap, t_rows;
-  size_t off_T, off_K, off_att, off_as, off_bt, off_e, off_eptr, off_ent, off_bar, total;
+// Targets are processed in blocks of at most kTB targets and kEdgeCap edge entries (one block for the typical graph:
+// ~17 controlling nodes, ~106 entries; the worst case -- 64 targets x 33 entries -- takes several): the per-item shared
+// memory is sized for a block, not for the worst case, so that six CTAs fit an SM.
+constexpr int kTB = 32;
+constexpr int kEdgeCap = 256;
+constexpr int kWRows = kTB;
+constexpr int kWTile = kWRows * 128;      // 4 KB
+constexpr int kTCols = 32;                // TMEM columns per CTA
+
+struct Conv2Layout {       // shared-memory offsets behind the 1024-byte aligned MMA operands
+  size_t off_W, off_T, off_K, off_att, off_as, off_bt, off_e, off_eptr, off_ent, off_bar, total;
 };
-Conv2Layout conv2_layout(int N, bool tr) {
+Conv2Layout conv2_layout(bool tr) {
   Conv2Layout L;
-  L.edge_cap = (N * (kMaxNbr + 1) + 15) & ~15;
-  L.t_rows = N;
-  size_t o = kXBytes + kWBytes;
-  L.off_T = o; o += (size_t)L.t_rows * kRowPad;
+  size_t o = kXBytes;
+  L.off_W = o; o += kWTile;
+  L.off_T = o; o += (size_t)kTB * kRowPad;
   L.off_K = o; o += tr ? (size_t)64 * kRowPad : 0;
   L.off_att = o; o += 256;
   L.off_as = o; o += 256;
   L.off_bt = o; o += 256;
-  L.off_e = o; o += (size_t)L.edge_cap * 4;
+  L.off_e = o; o += (size_t)kEdgeCap * 4;
   L.off_eptr = o; o += 68 * 4;
-  L.off_ent = o; o += (size_t)L.edge_cap * 2;
+  L.off_ent = o; o += (size_t)kEdgeCap * 2;
   L.off_bar = o; o += 16;
   L.total = o + 1024;
   return L;
 }
 
-// cp.async group bookkeeping of the pipeline (per item):
-//   group A: target rows, <att, x> dots of the sources   -- free to refill once the logits are done
-//   group B: source rows (MMA operand + logit operand), edge entries -- free once the MMA has completed
+// Prefetch groups of the pipeline (plain cp.async + a few scalar loads, all waited for at the top of the next item):
+//   group A: the first block's target rows, the per-row logit scalars -- free to refill once the item's last logits are done
+//   group B: source rows (MMA operand + logit operand), the first block's edge entries, per-target offsets -- free once
+//            the item's last MMA has completed
 template <bool TR, int LDZ>
-__global__ void __launch_bounds__(kThreads, TR ? 3 : 4) conv2_attn_kernel(const Conv2Args a, const Conv2Layout L) {
+__global__ void __launch_bounds__(kThreads, TR ? 4 : 6) conv2_attn_kernel(const Conv2Args a, const Conv2Layout L) {
   extern __shared__ __align__(16) unsigned char sm_raw[];
   unsigned char* sm = sm_raw + ((1024u - (smem_u32(sm_raw) & 1023u)) & 1023u);
   unsigned char* sX = sm;                                   // values [source k][channel], MN-major SW128 (GATv2: also logit operand)
-  unsigned char* sW = sX + kXBytes;                         // weights [target][source k], K-major SW128
-  unsigned char* sT = sm + L.off_T;                         // targets (x_r / q): [cnt][kRowPad]
+  unsigned char* sW = sm + L.off_W;                         // weights [target of the block][source k], K-major SW128
+  unsigned char* sT = sm + L.off_T;                         // targets of the block (x_r / q): [kTB][kRowPad]
   unsigned char* sK = sm + L.off_K;                         // Transformer keys: [k][kRowPad]
   __half* att_s = reinterpret_cast<__half*>(sm + L.off_att);
   float* s_as = reinterpret_cast<float*>(sm + L.off_as);    // [k]  <att, x_l[source k]> * 0.6 log2e
   float* s_bt = reinterpret_cast<float*>(sm + L.off_bt);    // [tk] <att, x_r[target]>  * 0.6 log2e
-  float* s_e = reinterpret_cast<float*>(sm + L.off_e);      // [edge] logit -> 2^(e - max)
-  int* s_eptr = reinterpret_cast<int*>(sm + L.off_eptr);    // [cnt + 1] edge offsets per target
-  uint16_t* s_ent = reinterpret_cast<uint16_t*>(sm + L.off_ent);
+  float* s_e = reinterpret_cast<float*>(sm + L.off_e);      // [entry of the block] logit -> 2^(e - max)
+  int* s_eptr = reinterpret_cast<int*>(sm + L.off_eptr);    // [cnt + 1] entry offsets per target (relative to the graph's block)
+  uint16_t* s_ent = reinterpret_cast<uint16_t*>(sm + L.off_ent);   // entries of the block
   uint64_t* bar = reinterpret_cast<uint64_t*>(sm + L.off_bar);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
 
@@ -112,7 +118,7 @@ __global__ void __launch_bounds__(kThreads, TR ? 3 : 4) conv2_attn_kernel(const 
   if (!TR) att_s[tid] = __float2half_rn(a.att[h * kC + tid] * (0.4f * kLog2e));
   const float bias_c = a.bias ? a.bias[h * kC + tid] : 0.f;  // this thread's output channel in the epilogue
   if (tid == 0) { mbar_init(smem_u32(bar), 1); fence_barrier_init(); }
-  if (warp == 0) tmem_alloc(smem_u32(tmem_slot), kCols);
+  if (warp == 0) tmem_alloc(smem_u32(tmem_slot), kTCols);
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
@@ -128,18 +134,28 @@ __global__ void __launch_bounds__(kThreads, TR ? 3 : 4) conv2_attn_kernel(const 
       m0 = make_int4(0, 0, 0, 0); m1 = make_int2(0, 0);
     }
   };
-  // group A of item (first, cnt, nf, nc): target rows + per-row logit scalars
-  auto issue_A = [&](int first, int cnt, int nf, int nc) {
-    for (int t = tid; t < cnt * 16; t += kThreads) {
+  // target rows [t0, t0 + n) of the graph whose first slot is `first` -> sT rows 0..n-1
+  auto load_targets = [&](int first, int t0, int n) {
+    for (int t = tid; t < n * 16; t += kThreads) {
       const int k = t >> 4, c = t & 15;
-      cp16(sT + k * kRowPad + c * 16, a.Pt + (size_t)(first + k) * a.ldt + h * kC + c * 8);
+      cp16(sT + k * kRowPad + c * 16, a.Pt + (size_t)(first + t0 + k) * a.ldt + h * kC + c * 8);
     }
+  };
+  // edge entries [e0, e0 + n) of the graph's block at `ef` (e0 a multiple of 8 is not required: copied 2 bytes each when unaligned)
+  auto load_entries = [&](int ef, int e0, int n) {
+    if ((e0 & 7) == 0) {
+      for (int t = tid; t * 8 < n; t += kThreads) cp16(reinterpret_cast<unsigned char*>(s_ent) + t * 16, a.eent + ef + e0 + t * 8);
+    } else {
+      for (int t = tid; t < n; t += kThreads) s_ent[t] = __ldg(a.eent + ef + e0 + t);
+    }
+  };
+  auto issue_A = [&](int first, int cnt, int nf, int nc) {
+    load_targets(first, 0, cnt < kTB ? cnt : kTB);
     if (!TR) {
       if (tid < nc) s_as[tid] = __ldg(a.as + (size_t)(nf + tid) * H + h) * k06;
       if (tid < cnt) s_bt[tid] = __ldg(a.bt + (size_t)(first + tid) * H + h) * k06;
     }
   };
-  // group B: source rows (compact index k) + the graph's edge entries and per-target offsets
   auto issue_B = [&](int first, int cnt, int nf, int nc, int ef, int ne) {
     for (int t = tid; t < nc * 16; t += kThreads) {
       const int k = t >> 4, c = t & 15;
@@ -152,7 +168,7 @@ __global__ void __launch_bounds__(kThreads, TR ? 3 : 4) conv2_attn_kernel(const 
         cp16(xd, row);
       }
     }
-    for (int t = tid; t * 8 < ne; t += kThreads) cp16(reinterpret_cast<unsigned char*>(s_ent) + t * 16, a.eent + ef + t * 8);
+    load_entries(ef, 0, ne < kEdgeCap ? ne : kEdgeCap);
     if (tid < cnt) s_eptr[tid] = __ldg(a.eabs + first + tid) - ef;
     if (tid == 0) s_eptr[cnt] = ne;
   };
@@ -160,137 +176,149 @@ __global__ void __launch_bounds__(kThreads, TR ? 3 : 4) conv2_attn_kernel(const 
   int g = blockIdx.x / H;
   int4 m0; int2 m1;
   load_meta(g, m0, m1);
-  // skip empty graphs
-  while (g < a.n_graphs && m0.y == 0) { g += gstep; load_meta(g, m0, m1); }
+  while (g < a.n_graphs && m0.y == 0) { g += gstep; load_meta(g, m0, m1); }     // skip graphs without controlling nodes
   if (g < a.n_graphs) { issue_A(m0.x, m0.y, m0.z, m0.w); issue_B(m0.x, m0.y, m0.z, m0.w, m1.x, m1.y); }
 
   while (g < a.n_graphs) {
-    const int first = m0.x, cnt = m0.y, nc = m0.w;
-    const int nmma = cnt <= 16 ? 16 : ((cnt + 15) & ~15);
+    const int first = m0.x, cnt = m0.y, nc = m0.w, ef = m1.x;
     // next non-empty item of this CTA (meta only: two 16-byte loads, long before they are needed)
     int gn = g + gstep;
     int4 n0; int2 n1;
     load_meta(gn, n0, n1);
     while (gn < a.n_graphs && n0.y == 0) { gn += gstep; load_meta(gn, n0, n1); }
-    for (int u = tid; u < nmma * 8; u += kThreads) reinterpret_cast<uint4*>(sW)[u] = make_uint4(0, 0, 0, 0);
     cp_wait_all();
     __syncthreads();
-    // ---------------------------------------------------------------- logits: one lane per edge
-    const int E = s_eptr[cnt];
-    for (int e = tid; e < E; e += kThreads) {
-      const uint32_t ent = s_ent[e];
-      const int j = ent & 255u, tk = ent >> 8;
-      const unsigned char* tr = sT + tk * kRowPad;
-      __half2 acc[4];
+    for (int t0 = 0; t0 < cnt;) {
+      // ---- block [t0, t1): at most kTB targets and kEdgeCap entries (a single target has at most 33)
+      const int eb = s_eptr[t0];
+      int t1 = t0 + 1;
+      while (t1 < cnt && t1 - t0 < kTB && s_eptr[t1 + 1] - eb <= kEdgeCap) ++t1;
+      const int nt = t1 - t0, E = s_eptr[t1] - eb;
+      const bool last = t1 == cnt;
+      const int nmma = nt <= 16 ? 16 : 32;
+      if (t0 > 0) {                                            // later blocks (rare): their rows and entries, synchronously
+        load_targets(first, t0, nt);
+        load_entries(ef, eb, E);
+        cp_wait_all();
+      }
+      for (int u = tid; u < nmma * 8; u += kThreads) reinterpret_cast<uint4*>(sW)[u] = make_uint4(0, 0, 0, 0);
+      if (t0 > 0) __syncthreads();
+      // ---------------------------------------------------------------- logits: one lane per edge entry
+      for (int e = tid; e < E; e += kThreads) {
+        const uint32_t ent = s_ent[e];
+        const int j = ent & 255u, tk = (int)(ent >> 8), tl = tk - t0;
+        const unsigned char* tr = sT + tl * kRowPad;
+        __half2 acc[4];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) acc[q] = __float2half2_rn(0.f);
-      if (!TR) {
-        const unsigned char* xr = sX + j * 128;
-        const int jx = j & 7;
+        for (int q = 0; q < 4; ++q) acc[q] = __float2half2_rn(0.f);
+        if (!TR) {
+          const unsigned char* xr = sX + j * 128;
+          const int jx = j & 7;
 #pragma unroll
-        for (int c = 0; c < 16; ++c) {
-          const uint4 xs = *reinterpret_cast<const uint4*>(xr + (c >> 3) * kPanel + (((c & 7) ^ jx) << 4));
-          const uint4 xt = *reinterpret_cast<const uint4*>(tr + c * 16);
-          const uint4 at = *reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(att_s) + c * 16);
-          const __half2* x2 = reinterpret_cast<const __half2*>(&xs);
-          const __half2* t2 = reinterpret_cast<const __half2*>(&xt);
-          const __half2* a2 = reinterpret_cast<const __half2*>(&at);
+          for (int c = 0; c < 16; ++c) {
+            const uint4 xs = *reinterpret_cast<const uint4*>(xr + (c >> 3) * kPanel + (((c & 7) ^ jx) << 4));
+            const uint4 xt = *reinterpret_cast<const uint4*>(tr + c * 16);
+            const uint4 at = *reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(att_s) + c * 16);
+            const __half2* x2 = reinterpret_cast<const __half2*>(&xs);
+            const __half2* t2 = reinterpret_cast<const __half2*>(&xt);
+            const __half2* a2 = reinterpret_cast<const __half2*>(&at);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) acc[q] = __hfma2(a2[q], __habs2(__hadd2(x2[q], t2[q])), acc[q]);
+            for (int q = 0; q < 4; ++q) acc[q] = __hfma2(a2[q], __habs2(__hadd2(x2[q], t2[q])), acc[q]);
+          }
+        } else {
+          const unsigned char* kr = sK + j * kRowPad;
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            const uint4 xs = *reinterpret_cast<const uint4*>(kr + c * 16);
+            const uint4 xt = *reinterpret_cast<const uint4*>(tr + c * 16);
+            const __half2* x2 = reinterpret_cast<const __half2*>(&xs);
+            const __half2* t2 = reinterpret_cast<const __half2*>(&xt);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[q] = __hfma2(x2[q], t2[q], acc[q]);
+          }
         }
-      } else {
-        const unsigned char* kr = sK + j * kRowPad;
+        float s = 0.f;
 #pragma unroll
-        for (int c = 0; c < 16; ++c) {
-          const uint4 xs = *reinterpret_cast<const uint4*>(kr + c * 16);
-          const uint4 xt = *reinterpret_cast<const uint4*>(tr + c * 16);
-          const __half2* x2 = reinterpret_cast<const __half2*>(&xs);
-          const __half2* t2 = reinterpret_cast<const __half2*>(&xt);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) acc[q] = __hfma2(x2[q], t2[q], acc[q]);
+        for (int q = 0; q < 4; ++q) { const float2 f = __half22float2(acc[q]); s += f.x + f.y; }
+        s_e[e] = TR ? s * tr_scale : s + (s_as[j] + s_bt[tk]);
+      }
+      __syncthreads();
+      // the target rows and logit scalars are dead after the item's last block: refill them with the next item's
+      // (overlaps softmax, MMA, epilogue)
+      if (last && gn < a.n_graphs) issue_A(n0.x, n0.y, n0.z, n0.w);
+      // ---------------------------------------------------------------- softmax -> W (4 lanes per target)
+      {
+        const int u = tid, tl = u >> 2, l = u & 3;             // kTB * 4 = kThreads: one pass
+        int lo = 0, hi = 0;
+        if (tl < nt) { lo = s_eptr[t0 + tl] - eb; hi = s_eptr[t0 + tl + 1] - eb; }
+        float mx = -INFINITY;
+        for (int x = lo + l; x < hi; x += 4) mx = fmaxf(mx, s_e[x]);
+        __syncwarp();
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+        float sum = 0.f;
+        for (int x = lo + l; x < hi; x += 4) { const float pv = ex2f(s_e[x] - mx); s_e[x] = pv; sum += pv; }
+        __syncwarp();
+        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+        const float inv = rcpf(sum + 1e-16f);
+        unsigned char* wrow = sW + tl * 128;
+        for (int x = lo + l; x < hi; x += 4) {
+          const int j = s_ent[x] & 255u;
+          *reinterpret_cast<__half*>(wrow + ((((j >> 3) ^ tl) & 7) << 4) + (j & 7) * 2) = __float2half_rn(s_e[x] * inv);
         }
       }
-      float s = 0.f;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) { const float2 f = __half22float2(acc[q]); s += f.x + f.y; }
-      s_e[e] = TR ? s * tr_scale : s + (s_as[j] + s_bt[tk]);
-    }
-    __syncthreads();
-    // the target rows and logit scalars are dead: refill them with the next item's (overlaps softmax, MMA, epilogue)
-    if (gn < a.n_graphs) issue_A(n0.x, n0.y, n0.z, n0.w);
-    // ---------------------------------------------------------------- softmax -> W (4 lanes per target)
-    for (int it = 0; it * kThreads < cnt * 4; ++it) {
-      const int u = tid + it * kThreads, tk = u >> 2, l = u & 3;
-      int lo = 0, hi = 0;
-      if (tk < cnt) { lo = s_eptr[tk]; hi = s_eptr[tk + 1]; }
-      float mx = -INFINITY;
-      for (int x = lo + l; x < hi; x += 4) mx = fmaxf(mx, s_e[x]);
-      __syncwarp();
-      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-      float sum = 0.f;
-      for (int x = lo + l; x < hi; x += 4) { const float pv = ex2f(s_e[x] - mx); s_e[x] = pv; sum += pv; }
-      __syncwarp();
-      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-      sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-      const float inv = rcpf(sum + 1e-16f);
-      unsigned char* wrow = sW + tk * 128;
-      for (int x = lo + l; x < hi; x += 4) {
-        const int j = s_ent[x] & 255u;
-        *reinterpret_cast<__half*>(wrow + ((((j >> 3) ^ tk) & 7) << 4) + (j & 7) * 2) = __float2half_rn(s_e[x] * inv);
+      fence_proxy_async();
+      __syncthreads();
+      // ---------------------------------------------------------------- aggregate on the tensor core
+      if (tid == 0) {
+        tc_fence_after();
+        // both operands fp16 (format 0), A (values) MN-major (bit 15), see attn_table.cu
+        const uint32_t idesc = (make_idesc(128, nmma) & ~((7u << 7) | (7u << 10))) | (1u << 15);
+        const uint64_t dv = desc_mn(smem_u32(sX), kPanel >> 4, 1024 >> 4);
+        const uint64_t dw = make_smem_desc(smem_u32(sW));
+        const int ksteps = (nc + 15) >> 4;
+        for (int k = 0; k < ksteps; ++k) umma_bf16(tmem_base, dv + (uint64_t)(k * 128), dw + (uint64_t)(k * 2), idesc, k ? 1u : 0u);
+        umma_commit(smem_u32(bar));
       }
-    }
-    fence_proxy_async();
-    __syncthreads();
-    // ---------------------------------------------------------------- aggregate on the tensor core
-    if (tid == 0) {
+      mbar_wait(smem_u32(bar), parity);
+      parity ^= 1u;
       tc_fence_after();
-      // both operands fp16 (format 0), A (values) MN-major (bit 15), see attn_table.cu
-      const uint32_t idesc = (make_idesc(128, nmma) & ~((7u << 7) | (7u << 10))) | (1u << 15);
-      const uint64_t dv = desc_mn(smem_u32(sX), kPanel >> 4, 1024 >> 4);
-      const uint64_t dw = make_smem_desc(smem_u32(sW));
-      const int ksteps = (nc + 15) >> 4;
-      for (int k = 0; k < ksteps; ++k) umma_bf16(tmem_base, dv + (uint64_t)(k * 128), dw + (uint64_t)(k * 2), idesc, k ? 1u : 0u);
-      umma_commit(smem_u32(bar));
-    }
-    mbar_wait(smem_u32(bar), parity);
-    parity ^= 1u;
-    tc_fence_after();
-    // the source rows, edge entries and offsets are dead: refill them with the next item's (overlaps the epilogue)
-    if (gn < a.n_graphs) issue_B(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y);
-    // ---------------------------------------------------------------- epilogue: lane = channel, registers = targets
-    {
-      uint16_t* zo = reinterpret_cast<uint16_t*>(a.z) + (size_t)first * ldz + a.z_col + h * kC + tid;
-      for (int c0 = 0; c0 < nmma; c0 += 32) {
+      // the source rows, edge entries and offsets are dead after the item's last MMA: refill them (overlaps the epilogue)
+      if (last && gn < a.n_graphs) issue_B(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y);
+      // ---------------------------------------------------------------- epilogue: lane = channel, registers = targets
+      {
+        uint16_t* zc = reinterpret_cast<uint16_t*>(a.z) + (size_t)(first + t0) * ldz + a.z_col + h * kC + tid;
         uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
-        uint16_t* zc = zo + (size_t)c0 * ldz;
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16), v);
 #pragma unroll
         for (int t = 0; t < 32; ++t)
-          if (c0 + t < cnt) zc[t * ldz] = relu_bf16_bits(__uint_as_float(v[t]) + bias_c);
+          if (t < nt) zc[t * ldz] = relu_bf16_bits(__uint_as_float(v[t]) + bias_c);
       }
+      tc_fence_before();
+      if (!last) __syncthreads();                              // the next block rewrites sT / s_ent / s_e / W
+      t0 = t1;
     }
-    tc_fence_before();
     g = gn; m0 = n0; m1 = n1;
   }
   cp_wait_all();
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, kCols);
+  if (warp == 0) tmem_dealloc(tmem_base, kTCols);
 }
 
 template <bool TR>
 int launch(const Conv2Args& a, int sm_count, cudaStream_t st) {
-  const Conv2Layout L = conv2_layout(a.N, TR);
-  static size_t configured = 0;
-  if (L.total > configured) {
+  const Conv2Layout L = conv2_layout(TR);
+  static bool configured = false;
+  if (!configured) {
     MLS_CUDA(cudaFuncSetAttribute(conv2_attn_kernel<TR, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
     MLS_CUDA(cudaFuncSetAttribute(conv2_attn_kernel<TR, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     MLS_CUDA(cudaFuncSetAttribute(conv2_attn_kernel<TR, 1152>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
     MLS_CUDA(cudaFuncSetAttribute(conv2_attn_kernel<TR, 1152>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    configured = L.total;
+    configured = true;
   }
-  const int per_sm = TR ? 3 : 4;
+  const int per_sm = TR ? 4 : 6;
   long long items = (long long)a.n_graphs * a.H;
   long long grid = (long long)sm_count * per_sm;
   grid -= grid % a.H;
