@@ -582,6 +582,318 @@ __global__ void __launch_bounds__(kTThreads, 1) attn_table_mma_kernel(const Attn
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
+// ------------------------------------------------------------------------------ head-pair stages (default)
+// Same algorithm with the work item cut in two: (tile, head pair).  A stage is 48 KiB (2 weight matrices + 4 value panels),
+// so FOUR stages fit and four producer teams of 3 warps are in flight; the per-stage chain produce -> MMA -> epilogue ->
+// produce is half as long and twice as many of them overlap (the two-stage kernel above is bound by exactly that chain:
+// ncu shows producers waiting 62 % and the epilogue 46 % of their time).
+//   warp 0  MMA issuer      warp 1  TMEM allocation      warps 2..9  epilogue (quarter = w & 3, head of the pair = (w - 2) >> 2)
+//   warps 10..21  four producer teams of 3 warps; team t builds items t, t+4, ... (item k: tile k >> 1, head pair k & 1)
+constexpr int kT4Threads = 704;
+constexpr int kTeam4 = 96;
+constexpr int kStageA2 = 2 * kAHead;           // 16 KiB
+constexpr int kStageB2 = 4 * kBPanel;          // 32 KiB
+constexpr int kStage2 = kStageA2 + kStageB2;   // 48 KiB
+constexpr int kT4Smem = 4 * kStage2 + 4 * kMeta + 256 /*barriers*/ + 1024;
+
+__device__ __forceinline__ void bar_team4(int team) { asm volatile("bar.sync %0, 96;" ::"r"(team + 1) : "memory"); }
+// bounded waits: a protocol bug traps instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait_guard(uint32_t bar, uint32_t parity, unsigned ns) {
+  for (unsigned spins = 0;; ++spins) {
+    uint32_t ok;
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (spins > (1u << 26)) __trap();
+    if (ns) __nanosleep(ns);
+  }
+}
+
+__global__ void __launch_bounds__(kT4Threads, 1) attn_table_mma4_kernel(const AttnTableArgs a, const int G) {
+  if (*a.n_used > kAttnUcap) return;            // uniform: the gather kernel handles this pass
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  unsigned char* meta = smem + 4 * kStage2;                                       // [4][kMeta]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(meta + 4 * kMeta);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  const uint32_t bar0 = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (4 + s); };
+  auto tfull_bar = [&](int b) { return bar0 + 8u * (8 + b); };
+  auto tempty_bar = [&](int b) { return bar0 + 8u * (12 + b); };
+
+  const int N = a.N, HC = 4 * kC;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tiles = (a.n_graphs + G - 1) / G;
+  const int my_tiles = blockIdx.x < n_tiles ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const int n_items = 2 * my_tiles;              // item k: tile blockIdx.x + (k >> 1) * gridDim.x, head pair k & 1
+  const int kb = G * N;                          // K index of the two bias rows (hi, lo); <= 62
+  const int ksteps = (kb + 2 + 15) >> 4;
+
+  for (int u = threadIdx.x; u < 4 * kStage2 / 16; u += kT4Threads) reinterpret_cast<uint4*>(smem)[u] = make_uint4(0, 0, 0, 0);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 4; ++s) {
+      mbar_init(full_bar(s), kTeam4); mbar_init(empty_bar(s), 1);
+      mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 8 * 32);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================================================== MMA issuer
+    if (lane == 0) {
+      for (int k = 0; k < n_items; ++k) {
+        const int s = k & 3;                                                   // shared-memory stage == TMEM buffer
+        const uint32_t sA = smem_u32(smem + s * kStage2), sB = sA + kStageA2;
+        mbar_wait_guard(full_bar(s), (k >> 2) & 1, 0);
+        mbar_wait_guard(tempty_bar(s), ((k >> 2) & 1) ^ 1, 0);
+        tc_fence_after();
+        const int* cnt_s = reinterpret_cast<const int*>(meta + s * kMeta + kMetaSrc + 64);
+        const int nn = cnt_s[0] + cnt_s[1];
+        const int nmma = a.pool_mode >= 0 ? 64 : (nn <= 16 ? 16 : ((nn + 15) & ~15));   // pooling reads all 64 columns
+        const uint32_t idesc = (make_idesc(128, nmma) & ~((7u << 7) | (7u << 10))) | (1u << 15);   // fp16 x fp16, A MN-major
+        for (int hl = 0; hl < 2; ++hl) {
+          const uint64_t dv = make_smem_desc_ex(sB + hl * 2 * kBPanel, kBPanel >> 4, 1024 >> 4);
+          const uint64_t dw = make_smem_desc(sA + hl * kAHead);
+          for (int ks = 0; ks < ksteps; ++ks)
+            umma_bf16(tmem_base + (uint32_t)(s * 128 + hl * 64), dv + (uint64_t)(ks * 128), dw + (uint64_t)(ks * 2), idesc, ks ? 1u : 0u);
+        }
+        umma_commit(tfull_bar(s));                                              // the epilogue frees the stage (empty_bar)
+      }
+    }
+  } else if (warp >= 2 && warp < 10) {
+    // ===================================================================== epilogue: lane = channel, registers = targets
+    const int quarter = warp & 3, hl = (warp - 2) >> 2;
+    const int et = threadIdx.x - 64;                                           // 0..255 within the epilogue warps
+    for (int k = 0; k < n_items; ++k) {
+      const int b = k & 3, hp = k & 1;
+      const int tile = blockIdx.x + (k >> 1) * gridDim.x;
+      const int g0 = tile * G;
+      mbar_wait_guard(tfull_bar(b), (k >> 2) & 1, 20);
+      tc_fence_after();
+      const int* cnt_b = reinterpret_cast<const int*>(meta + b * kMeta + kMetaSrc + 64);
+      const int* tab_x = reinterpret_cast<const int*>(meta + b * kMeta + kMetaTab);
+      const int* tab_s = tab_x + 64;
+      const int nn = a.pool_mode >= 0 ? 64 : cnt_b[0] + cnt_b[1];
+      const int h = hp * 2 + hl;
+      unsigned char* stg0 = smem + b * kStage2 + kStageA2;                      // staging rows [column t][256 channels of the pair]
+      float pool = 0.f;                          // relu(conv) * dm >= 0: 0 is the identity of max and add here
+#pragma unroll 1
+      for (int q = 0; q < 2; ++q) {
+        const int t0 = q * 32;
+        const bool skip = t0 >= nn;                                            // warp uniform: no needed target in this half
+        uint32_t v[32];
+        if (!skip) tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(b * 128 + hl * 64 + t0), v);
+        if (q == 1) { tc_fence_before(); mbar_arrive(tempty_bar(b)); }
+        if (skip) continue;
+        if (a.pool_mode >= 0) {
+          if (a.pool_mode == MLS_POOL_MAX) {
+#pragma unroll
+            for (int t = 0; t < 32; ++t) pool = fmaxf(pool, __uint_as_float(v[t]));
+          } else {
+#pragma unroll
+            for (int t = 0; t < 32; ++t) pool += fmaxf(__uint_as_float(v[t]), 0.f);
+          }
+          if (q == 1) {
+            if (a.pool_mode == MLS_POOL_MEAN) pool = pool / (float)N;
+            a.z[(size_t)g0 * a.ldz + a.z_col + h * kC + quarter * 32 + lane] = __float2bfloat16_rn(pool);
+          }
+          continue;
+        }
+        unsigned char* stg = stg0 + (size_t)t0 * 512 + (hl * kC + quarter * 32 + lane) * 2;
+        const int nv = nn - t0;
+#pragma unroll
+        for (int t = 0; t < 32; ++t)
+          if (t < nv) *reinterpret_cast<uint16_t*>(stg + t * 512) = relu_bf16(__uint_as_float(v[t]));   // warp uniform
+      }
+      if (a.pool_mode < 0) {
+        asm volatile("bar.sync 5, 256;" ::: "memory");
+        for (int u = et; u < nn * 32; u += 256) {                              // 512-byte half rows, 16 bytes per lane
+          const int t = u >> 5, c = u & 31;
+          const uint4 val = *reinterpret_cast<const uint4*>(stg0 + t * 512 + c * 16);
+          *reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(a.x_out) + (size_t)tab_x[t] * (HC * 2) + hp * 512 + c * 16) = val;
+          const int sl = tab_s[t];
+          if (sl >= 0)
+            *reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(a.z) + ((size_t)sl * a.ldz + a.z_col) * 2 + hp * 512 + c * 16) = val;
+        }
+        asm volatile("bar.sync 5, 256;" ::: "memory");
+      }
+      if (threadIdx.x == 64) mbar_arrive(empty_bar(b));                         // stage free for its producer team
+    }
+  } else if (warp >= 10) {
+    // ===================================================================== producer teams
+    const int team = (warp - 10) / 3, pt = ((warp - 10) % 3) * 32 + lane;      // 0..95
+    const int hp = team & 1;
+    const int self = a.transformer ? 0 : 1;
+    unsigned char* sA = smem + team * kStage2;
+    unsigned char* sBv = sA + kStageA2;
+    const uint32_t sB32 = smem_u32(sBv);
+    uint8_t* src_s = meta + team * kMeta;                                       // [gt][N*32]
+    uint8_t* need_s = src_s + kMetaSrc;                                         // [64] node rows of the tile whose output is read
+    int* cnt_s = reinterpret_cast<int*>(need_s + 64);                           // [2]
+    uint16_t* cid = reinterpret_cast<uint16_t*>(need_s + 256);                  // [64]
+    uint16_t* ptr_s = cid + 64;                                                 // [gt][N+1]
+    float* dm_s = reinterpret_cast<float*>(ptr_s + 128);                        // [64]
+    int* tabx_s = reinterpret_cast<int*>(meta + team * kMeta + kMetaTab);       // [64] x_out row of TMEM column t
+    int* tabs_s = tabx_s + 64;                                                  // [64] snapshot slot of TMEM column t or -1
+    const int gp = pt & 3;
+    const unsigned char* gsrc = reinterpret_cast<const unsigned char*>(a.Vh) + hp * 512 + gp * 16;   // this pair's half of a value row
+    uint32_t bias_hl[3];                                                        // channels pt, pt + 96, pt + 192 of the pair
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int chl = pt + r * kTeam4;
+      const float bv = (a.bias && chl < 256) ? a.bias[hp * 256 + chl] : 0.f;
+      const __half hi = __float2half_rn(bv), lo = __float2half_rn(bv - __half2float(hi));
+      bias_hl[r] = (uint32_t)__half_as_ushort(hi) | ((uint32_t)__half_as_ushort(lo) << 16);
+    }
+    int use = 0;
+    for (int k = team; k < n_items; k += 4, ++use) {
+      const int tile = blockIdx.x + (k >> 1) * gridDim.x;
+      const int g0 = tile * G, gt = min(G, a.n_graphs - g0), rt = gt * N;
+      const size_t m0 = (size_t)g0 * N;
+      // ---- phase A: tile metadata (global loads first) and the cleared weight matrices
+      uint32_t pv = 0;
+      uint16_t cv = 0;
+      uint4 sv0 = make_uint4(0, 0, 0, 0), sv1 = make_uint4(0, 0, 0, 0);
+      float dmv = 1.f;
+      int xrv = 0, slv = -1;
+      if (pt < rt) {
+        cv = __ldg(a.row_cid + m0 + pt);
+        if (a.pool_mode >= 0) dmv = __ldg(a.obs + (long long)(g0 + pt / N) * a.obs_stride + (pt % N) * 8 + 7);
+        if (a.xrow) xrv = __ldg(a.xrow + m0 + pt);
+        else if (a.pool_mode < 0) xrv = (int)m0 + pt;
+        if (a.slot) slv = __ldg(a.slot + m0 + pt);
+      }
+      if (pt < gt * (N + 1)) {                                                 // gt * (N + 1) <= 64
+        const int gl = pt / (N + 1), il = pt - gl * (N + 1);
+        const size_t cg = a.graph_id ? (size_t)__ldg(a.graph_id + (size_t)(g0 + gl) * a.gid_stride) : (size_t)(g0 + gl);
+        pv = __ldg(a.csr_ptr + cg * (N + 1) + il);
+      }
+      {                                                                        // N*32 bytes (2N chunks of 16 B) per graph: <= 124 chunks
+        const int c0 = pt, c1 = pt + kTeam4;
+        if (c0 < rt * 2) {
+          const int gl = c0 / (2 * N), cl = c0 - gl * 2 * N;
+          const size_t cg = a.graph_id ? (size_t)__ldg(a.graph_id + (size_t)(g0 + gl) * a.gid_stride) : (size_t)(g0 + gl);
+          sv0 = __ldg(reinterpret_cast<const uint4*>(a.csr_src + cg * N * kMaxNbr) + cl);
+        }
+        if (c1 < rt * 2) {
+          const int gl = c1 / (2 * N), cl = c1 - gl * 2 * N;
+          const size_t cg = a.graph_id ? (size_t)__ldg(a.graph_id + (size_t)(g0 + gl) * a.gid_stride) : (size_t)(g0 + gl);
+          sv1 = __ldg(reinterpret_cast<const uint4*>(a.csr_src + cg * N * kMaxNbr) + cl);
+        }
+      }
+      const uint32_t nbal = __ballot_sync(0xffffffffu, pt < rt && xrv >= 0);
+      mbar_wait_guard(empty_bar(team), (use & 1) ^ 1, 40);                     // the epilogue is done with this stage
+      for (int u = pt; u < kStageA2 / 16; u += kTeam4) reinterpret_cast<uint4*>(sA)[u] = make_uint4(0, 0, 0, 0);
+      if (a.pool_mode < 0 || use == 0) {
+        // bias rows (kb, kb + 1) of the pair's 4 panels; the epilogue's staging clobbers them and the rows behind them
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          const int chl = pt + r * kTeam4;
+          if (chl < 256) {
+            unsigned char* panel = sBv + (chl >> 6) * kBPanel;
+            const int e = chl & 63;
+            *reinterpret_cast<uint16_t*>(panel + kb * 128 + ((((e >> 3) ^ kb) & 7) << 4) + (e & 7) * 2) = (uint16_t)(bias_hl[r] & 0xffffu);
+            *reinterpret_cast<uint16_t*>(panel + (kb + 1) * 128 + ((((e >> 3) ^ (kb + 1)) & 7) << 4) + (e & 7) * 2) = (uint16_t)(bias_hl[r] >> 16);
+          }
+        }
+        const int tail = 62 - rt;                                              // rows rt .. 63 of the 4 panels except kb, kb + 1
+        for (int u = pt; u < tail * 32; u += kTeam4) {
+          int row = rt + (u >> 5);
+          if (row >= kb) row += 2;
+          const int pc = u & 31;                                               // panel = pc >> 3, 16-byte chunk = pc & 7
+          *reinterpret_cast<uint4*>(sBv + (pc >> 3) * kBPanel + row * 128 + ((pc & 7) << 4)) = make_uint4(0, 0, 0, 0);
+        }
+      }
+      if (pt < rt) { cid[pt] = cv; dm_s[pt] = dmv; }
+      if (pt < gt * (N + 1)) ptr_s[pt] = (uint16_t)pv;
+      if (pt < rt * 2) reinterpret_cast<uint4*>(src_s)[pt] = sv0;
+      if (pt + kTeam4 < rt * 2) reinterpret_cast<uint4*>(src_s)[pt + kTeam4] = sv1;
+      if (pt < 64 && lane == 0) cnt_s[pt >> 5] = __popc(nbal);
+      bar_team4(team);
+      if (pt < rt && xrv >= 0) {
+        const int rank = (pt >= 32 ? cnt_s[0] : 0) + __popc(nbal & ((1u << lane) - 1u));
+        need_s[rank] = (uint8_t)pt;
+        tabx_s[rank] = xrv;
+        tabs_s[rank] = slv;
+      }
+      // ---- phase B: this pair's half (512 B) of the value rows of the tile's nodes, asynchronously ...
+      for (int j = pt >> 2; j < rt; j += kTeam4 / 4) {
+        const unsigned char* src = gsrc + (size_t)cid[j] * (HC * 2);
+        const uint32_t row = sB32 + j * 128;
+        const uint32_t d0 = row + ((gp ^ (j & 7)) << 4), d1 = row + (((gp + 4) ^ (j & 7)) << 4);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) cp_async16(((i & 1) ? d1 : d0) + (i >> 1) * kBPanel, src + i * 64);
+      }
+      bar_team4(team);                                                         // need_s complete
+      // ---- ... and the normalised softmax weights of (needed target i, head hl of the pair)
+      const int n_tasks = (cnt_s[0] + cnt_s[1]) * 2;
+      for (int tt = pt; tt < n_tasks; tt += kTeam4) {
+        const int wr = tt >> 1, i = need_s[wr], hl = tt & 1, h = hp * 2 + hl;
+        if (a.pool_mode >= 0 && dm_s[i] == 0.f) continue;                       // relu(conv) * 0: the row stays all zero
+        const int gl = i / N, il = i - gl * N, rbase = gl * N;
+        const uint16_t* ptr = ptr_s + gl * (N + 1);
+        const int r0 = ptr[il], d = (int)ptr[il + 1] - r0;
+        const uint8_t* src = src_s + gl * N * kMaxNbr + r0;
+        const float* Erow = a.E + (size_t)cid[i] * kAttnUcap * 4 + h;
+        const int cnt = d + self;
+        unsigned char* arow = sA + hl * kAHead;
+        float ev[8];
+        int jv[8];
+        float mx = -INFINITY;
+        for (int k0 = 0; k0 < cnt; k0 += 8) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const int kk = k0 + q;
+            jv[q] = (kk < cnt && kk >= self) ? rbase + src[kk - self] : i;
+            ev[q] = __ldg(Erow + (int)cid[jv[q]] * 4);
+          }
+#pragma unroll
+          for (int q = 0; q < 8; ++q) if (k0 + q < cnt) mx = fmaxf(mx, ev[q]);
+        }
+        float sum = 0.f;
+        if (cnt <= 8) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) { ev[q] = q < cnt ? f_ex2(ev[q] - mx) : 0.f; sum += ev[q]; }
+        } else {
+          for (int kk = 0; kk < cnt; ++kk) {
+            const int j = kk >= self ? rbase + src[kk - self] : i;
+            sum += f_ex2(__ldg(Erow + (int)cid[j] * 4) - mx);
+          }
+        }
+        const float inv = f_rcp(sum + 1e-16f);
+        if (cnt <= 8) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            if (q < cnt) *reinterpret_cast<__half*>(arow + a_off(wr, jv[q])) = __float2half_rn(ev[q] * inv);
+        } else {
+          for (int kk = 0; kk < cnt; ++kk) {
+            const int j = kk >= self ? rbase + src[kk - self] : i;
+            *reinterpret_cast<__half*>(arow + a_off(wr, j)) = __float2half_rn(f_ex2(__ldg(Erow + (int)cid[j] * 4) - mx) * inv);
+          }
+        }
+        *reinterpret_cast<uint16_t*>(arow + a_off(wr, kb)) = 0x3C00;         // 1.0 (fp16): + bias (hi)
+        *reinterpret_cast<uint16_t*>(arow + a_off(wr, kb + 1)) = 0x3C00;     // 1.0 (fp16): + bias (lo)
+      }
+      cp_async_wait_all();
+      fence_proxy_async();
+      mbar_arrive(full_bar(team));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
 }  // namespace
 
 int attn_table_conv_launch(const AttnTableArgs& a, int sm_count, cudaStream_t st) {
@@ -596,6 +908,7 @@ int attn_table_conv_launch(const AttnTableArgs& a, int sm_count, cudaStream_t st
   static bool configured = false;
   if (!configured) {
     MLS_CUDA(cudaFuncSetAttribute(attn_table_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTSmem));
+    MLS_CUDA(cudaFuncSetAttribute(attn_table_mma4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kT4Smem));
     configured = true;
   }
   compact_keys_kernel<<<1, 1024, 0, st>>>(a.used_bits, a.n_keys, a.cid_of_key, a.key_of_cid, a.n_used);
@@ -606,7 +919,10 @@ int attn_table_conv_launch(const AttnTableArgs& a, int sm_count, cudaStream_t st
   const int G = a.pool_mode >= 0 ? 1 : kAttnMaxRows / a.N;     // pooling: one graph per tile
   const int n_tiles = (a.n_graphs + G - 1) / G;
   const int grid = n_tiles < sm_count ? n_tiles : sm_count;
-  if (grid > 0) attn_table_mma_kernel<<<grid, kTThreads, kTSmem, st>>>(a, G);
+  if (grid > 0) {
+    if (mls_get_option("attn_hp")) attn_table_mma4_kernel<<<grid, kT4Threads, kT4Smem, st>>>(a, G);    // head-pair stages (default)
+    else attn_table_mma_kernel<<<grid, kTThreads, kTSmem, st>>>(a, G);
+  }
   mls_count_launch(5);
   MLS_LAUNCH_CHECK();
   return MLS_OK;
