@@ -16,11 +16,11 @@ struct GemmSmem {
   static constexpr int kABytes = kBM * kBK * 2;      // 16 KiB
   static constexpr int kBBytes = BN * kBK * 2;       // 16 / 32 KiB
   static constexpr int kStageBytes = kABytes + kBBytes;
-  // epilogue staging: 8 warps, each 32 rows x BN/2 bf16 (+16 B pad: conflict-free 16 B stores by row-owning lanes)
-  static constexpr int kOutRowBytes = BN + 16;
+  // epilogue staging: 16 warps, each 32 rows x BN/4 bf16 (+16 B pad: conflict-free 16 B stores by row-owning lanes)
+  static constexpr int kOutRowBytes = BN / 2 + 16;
   static constexpr int kOutWarpBytes = 32 * kOutRowBytes;
   static constexpr int kOutOffset = kNumStages * kStageBytes;
-  static constexpr int kBiasOffset = kOutOffset + 8 * kOutWarpBytes;      // BN floats
+  static constexpr int kBiasOffset = kOutOffset + kGemmEpiWarps * kOutWarpBytes;      // BN floats
   static constexpr int kDotOffset = kBiasOffset + BN * 4;                 // BN floats
   static constexpr int kDot2Offset = kDotOffset + BN * 4;                 // BN floats
   static constexpr int kBarOffset = kDot2Offset + BN * 4;
@@ -59,7 +59,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 256); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), kGemmEpiWarps * 32); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(smem_u32(tmem_slot), 2 * BN);      // 2 accumulator stages of BN fp32 columns
@@ -115,15 +115,16 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   } else if (warp >= 4) {
     // ===================================================================== epilogue
     // TMEM -> registers (lane = row) -> scale/bias/ReLU -> bf16 -> per-warp smem tile -> coalesced row stores
-    // eight warps: warp % 4 selects the TMEM lane quarter (rows) a warp may read, (warp - 4) / 4 the column half
+    // sixteen warps (the epilogue, not the MMA, bounds the tile rate with fewer): warp % 4 selects the TMEM lane quarter
+    // (rows) a warp may read, (warp - 4) / 4 the column quarter
     const int ew = (warp - 4) & 3, half = (warp - 4) >> 2;
-    constexpr int HN = BN / 2;
+    constexpr int HN = BN / 4;
     const int cb = half * HN;
     unsigned char* stage_out = smem + S::kOutOffset + (warp - 4) * S::kOutWarpBytes;
     float* bias_s = reinterpret_cast<float*>(smem + S::kBiasOffset);
     float* dot_s = reinterpret_cast<float*>(smem + S::kDotOffset);
     float* dot2_s = reinterpret_cast<float*>(smem + S::kDot2Offset);
-    const int et = threadIdx.x - 128;                       // 0..255 within the epilogue warps
+    const int et = threadIdx.x - 128;                       // 0..511 within the epilogue warps
     int it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -137,13 +138,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         scale = epi.obs[(long long)g * epi.obs_stride + i * 8 + 7];
       }
       // bias slice of this tile -> smem (all four epilogue warps; named barrier 1 keeps the other warps out of it)
-      asm volatile("bar.sync 1, 256;" ::: "memory");        // previous tile's readers are done with bias_s
-      for (int c = et; c < BN; c += 256) {
+      asm volatile("bar.sync 1, 512;" ::: "memory");        // previous tile's readers are done with bias_s
+      for (int c = et; c < BN; c += kGemmEpiWarps * 32) {
         bias_s[c] = epi.bias ? __ldg(epi.bias + n0 + c) : 0.0f;
         if (epi.dotvec) dot_s[c] = __ldg(epi.dotvec + n0 + c);
         if (epi.dotvec2) dot2_s[c] = __ldg(epi.dotvec2 + n0 + c);
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, 512;" ::: "memory");
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       float dot = 0.f, dot2 = 0.f;
@@ -184,10 +185,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 #pragma unroll
           for (int q = 0; q < 4; ++q) dst[q] = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
         }
-        if (epi.dotvec && (c0 & 96) == 96) {                 // end of a 128-column group
+        if (epi.dotvec && (c0 & 32) == 32) {                 // end of this warp's half (64 columns) of a 128-column group
+          // the group's two halves come from two warps: two atomic adds onto a zeroed cell (launcher) -- with exactly two
+          // terms the sum does not depend on their order (0 + x + y == 0 + y + x), so the result is deterministic
           if (r < M) {
-            epi.dots[(size_t)r * (shape.N >> 7) + ((n0 + c0) >> 7)] = dot;
-            if (epi.dotvec2) epi.dots2[(size_t)r * (shape.N >> 7) + ((n0 + c0) >> 7)] = dot2;
+            atomicAdd(epi.dots + (size_t)r * (shape.N >> 7) + ((n0 + c0) >> 7), dot);
+            if (epi.dotvec2) atomicAdd(epi.dots2 + (size_t)r * (shape.N >> 7) + ((n0 + c0) >> 7), dot2);
           }
           dot = 0.f; dot2 = 0.f;
         }
@@ -274,6 +277,10 @@ int gemm_bf16_launch(const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, in
   MLS_CHECK_ARG(!epi.Cf || (epi.ldcf % 4 == 0 && (reinterpret_cast<uintptr_t>(epi.Cf) & 15) == 0), "fp32 GEMM output must be 16-byte aligned");
   MLS_CHECK_ARG(!epi.dotvec || shape.N % 256 == 0, "the fused per-group dot products need N to be a multiple of 256");
   if (shape.M <= 0) return MLS_OK;
+  if (epi.dotvec) {                                         // the epilogue accumulates two partial sums per cell
+    MLS_CUDA(cudaMemsetAsync(epi.dots, 0, (size_t)shape.M * (shape.N >> 7) * sizeof(float), st));
+    if (epi.dotvec2) MLS_CUDA(cudaMemsetAsync(epi.dots2, 0, (size_t)shape.M * (shape.N >> 7) * sizeof(float), st));
+  }
   const int BN = (shape.N % 256 == 0) ? 256 : 128;
   CUtensorMap ta, tb;
   int rc = make_tmap_bf16(&ta, A, shape.M, shape.K, lda, kBM);

@@ -14,7 +14,8 @@
 namespace mls {
 
 constexpr int kBM = 128, kBK = 64, kUmmaK = 16;
-constexpr int kGemmThreads = 384;      // 4 control warps (TMA, MMA, TMEM alloc, spare) + 8 epilogue warps
+constexpr int kGemmEpiWarps = 16;       // 4 per TMEM lane quarter, each drains a quarter of the tile's columns
+constexpr int kGemmThreads = 128 + kGemmEpiWarps * 32;      // 4 control warps (TMA, MMA, TMEM alloc, spare) + the epilogue warps
 
 struct GemmEpilogue {
   __nv_bfloat16* C;      // [M, ldc]
