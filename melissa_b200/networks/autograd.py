@@ -44,7 +44,7 @@ def radius_mask(pos: torch.Tensor) -> torch.Tensor:
     dy = p[:, None, :, 1] - p[:, :, None, 1]
     d2 = (dy.double() * dy.double() + (dx * dx).double()).float()
     hit = d2 < R2
-    hit = hit & (hit.cumsum(dim=2) <= MAX_NUM_NEIGHBORS + 1)
+    hit = hit & (hit.to(torch.int16).cumsum(dim=2, dtype=torch.int16) <= MAX_NUM_NEIGHBORS + 1)
     n = p.shape[1]
     return hit & ~torch.eye(n, dtype=torch.bool, device=p.device)
 
