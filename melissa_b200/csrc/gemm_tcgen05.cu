@@ -20,10 +20,13 @@ struct GemmSmem {
   static constexpr int kOutRowBytes = BN / 2 + 16;
   static constexpr int kOutWarpBytes = 32 * kOutRowBytes;
   static constexpr int kOutOffset = kNumStages * kStageBytes;
-  static constexpr int kBiasOffset = kOutOffset + kGemmEpiWarps * kOutWarpBytes;      // BN floats
-  static constexpr int kDotOffset = kBiasOffset + BN * 4;                 // BN floats
-  static constexpr int kDot2Offset = kDotOffset + BN * 4;                 // BN floats
-  static constexpr int kBarOffset = kDot2Offset + BN * 4;
+  // bias / dot vectors of a tile's column slice, double buffered: the next tile's slices arrive by cp.async while this
+  // tile's accumulator is drained (the epilogue, not the MMA, bounds the tile rate: ncu showed the MMA warp waiting for
+  // a free accumulator and the epilogue warps exposed to three dependent global-load latencies per tile)
+  static constexpr int kBiasOffset = kOutOffset + kGemmEpiWarps * kOutWarpBytes;      // 2 x BN floats
+  static constexpr int kDotOffset = kBiasOffset + 2 * BN * 4;             // 2 x BN floats
+  static constexpr int kDot2Offset = kDotOffset + 2 * BN * 4;             // 2 x BN floats
+  static constexpr int kBarOffset = kDot2Offset + 2 * BN * 4;
   static constexpr int kTotal = kBarOffset + 256 + 1024;   // barriers + alignment slack
 };
 
@@ -125,26 +128,52 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     float* dot_s = reinterpret_cast<float*>(smem + S::kDotOffset);
     float* dot2_s = reinterpret_cast<float*>(smem + S::kDot2Offset);
     const int et = threadIdx.x - 128;                       // 0..511 within the epilogue warps
+    auto cp4 = [](float* dst, const float* src) {
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+    };
+    // column slices (bias, dot vectors) of `tile` -> buffer `buf`, asynchronously
+    auto fill = [&](int buf, int tile) {
+      if (tile >= n_tiles) return;
+      const int fn0 = (tile % n_n) * BN;
+      for (int c = et; c < BN; c += kGemmEpiWarps * 32) {
+        if (epi.bias) cp4(bias_s + buf * BN + c, epi.bias + fn0 + c);
+        else bias_s[buf * BN + c] = 0.0f;
+        if (epi.dotvec) cp4(dot_s + buf * BN + c, epi.dotvec + fn0 + c);
+        if (epi.dotvec2) cp4(dot2_s + buf * BN + c, epi.dotvec2 + fn0 + c);
+      }
+    };
+    // row scale of this thread's row in `tile`: node row index (one tile ahead), then the observation's dm flag
+    auto ld_index = [&](int tile) -> int {
+      if (!epi.obs || tile >= n_tiles) return -1;
+      const int rr = (tile / n_n) * kBM + ew * 32 + lane;
+      if (rr >= M) return -1;
+      return epi.row_index ? __ldg(epi.row_index + rr) : rr;
+    };
+    auto ld_scale = [&](int nr) -> float {
+      if (nr < 0) return 1.0f;
+      const int g = nr / epi.nodes, i = nr - g * epi.nodes;
+      return __ldg(epi.obs + (long long)g * epi.obs_stride + i * 8 + 7);
+    };
+    fill(0, blockIdx.x);
+    int nr_next = ld_index(blockIdx.x);
+    float scale_cur = ld_scale(nr_next);
+    nr_next = ld_index(blockIdx.x + gridDim.x);
     int it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int m0 = (tile / n_n) * kBM, n0 = (tile % n_n) * BN;
       const int r = m0 + ew * 32 + lane;
-      float scale = 1.0f;
-      if (epi.obs && r < M) {
-        const int nr = epi.row_index ? __ldg(epi.row_index + r) : r;
-        const int g = nr / epi.nodes, i = nr - g * epi.nodes;
-        scale = epi.obs[(long long)g * epi.obs_stride + i * 8 + 7];
-      }
-      // bias slice of this tile -> smem (all four epilogue warps; named barrier 1 keeps the other warps out of it)
-      asm volatile("bar.sync 1, 512;" ::: "memory");        // previous tile's readers are done with bias_s
-      for (int c = et; c < BN; c += kGemmEpiWarps * 32) {
-        bias_s[c] = epi.bias ? __ldg(epi.bias + n0 + c) : 0.0f;
-        if (epi.dotvec) dot_s[c] = __ldg(epi.dotvec + n0 + c);
-        if (epi.dotvec2) dot2_s[c] = __ldg(epi.dotvec2 + n0 + c);
-      }
-      asm volatile("bar.sync 1, 512;" ::: "memory");
+      const float scale = scale_cur;
+      // software pipeline: the next tile's scale (its index arrived during the previous tile) and the index after that
+      const float scale_nx = ld_scale(nr_next);
+      const int nr_nx2 = ld_index(tile + 2 * gridDim.x);
+      const float* bias_b = bias_s + (it & 1) * BN;
+      const float* dot_b = dot_s + (it & 1) * BN;
+      const float* dot2_b = dot2_s + (it & 1) * BN;
+      asm volatile("cp.async.wait_all;" ::: "memory");      // this thread's part of this tile's slices has landed
+      asm volatile("bar.sync 1, 512;" ::: "memory");        // ... everybody's has, and the previous tile's readers are done
+      fill((it & 1) ^ 1, tile + gridDim.x);
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       float dot = 0.f, dot2 = 0.f;
@@ -155,16 +184,16 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         uint32_t packed[16];
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
-          const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c0 + j);
+          const float4 b4 = *reinterpret_cast<const float4*>(bias_b + c0 + j);
           float x0 = fmaf(__uint_as_float(v[j]), scale, b4.x), x1 = fmaf(__uint_as_float(v[j + 1]), scale, b4.y);
           float x2 = fmaf(__uint_as_float(v[j + 2]), scale, b4.z), x3 = fmaf(__uint_as_float(v[j + 3]), scale, b4.w);
           if (epi.dotvec) {
-            const float4 d4 = *reinterpret_cast<const float4*>(dot_s + c0 + j);
+            const float4 d4 = *reinterpret_cast<const float4*>(dot_b + c0 + j);
             const float y0 = epi.dot_relu ? fmaxf(x0, 0.f) : x0, y1 = epi.dot_relu ? fmaxf(x1, 0.f) : x1;
             const float y2 = epi.dot_relu ? fmaxf(x2, 0.f) : x2, y3 = epi.dot_relu ? fmaxf(x3, 0.f) : x3;
             dot = fmaf(y0, d4.x, dot); dot = fmaf(y1, d4.y, dot); dot = fmaf(y2, d4.z, dot); dot = fmaf(y3, d4.w, dot);
             if (epi.dotvec2) {
-              const float4 e4 = *reinterpret_cast<const float4*>(dot2_s + c0 + j);
+              const float4 e4 = *reinterpret_cast<const float4*>(dot2_b + c0 + j);
               dot2 = fmaf(y0, e4.x, dot2); dot2 = fmaf(y1, e4.y, dot2); dot2 = fmaf(y2, e4.z, dot2); dot2 = fmaf(y3, e4.w, dot2);
             }
           }
@@ -213,7 +242,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         }
       }
       __syncwarp();
+      scale_cur = scale_nx;
+      nr_next = nr_nx2;
     }
+    asm volatile("cp.async.wait_all;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
