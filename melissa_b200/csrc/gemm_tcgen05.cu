@@ -30,7 +30,11 @@ struct GemmSmem {
   static constexpr int kTotal = kBarOffset + 256 + 1024;   // barriers + alignment slack
 };
 
-template <int BN>
+// MODE fixes the epilogue options at compile time for the hot launches (0 = read them from `epi` at run time):
+//   1 = one dot vector on the raw values, C written (GATv2 projections)   2 = ReLU, C written, no dots (hidden layers)
+//   3 = ReLU + two dot vectors on the rectified values, C not written (last hidden layer with the output layer fused)
+// The epilogue bounds the tile rate, and the run-time selects were a fifth of its instructions.
+template <int BN, int MODE>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          const GemmShape shape, const GemmEpilogue epi) {
@@ -121,6 +125,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     // sixteen warps (the epilogue, not the MMA, bounds the tile rate with fewer): warp % 4 selects the TMEM lane quarter
     // (rows) a warp may read, (warp - 4) / 4 the column quarter
     const int ew = (warp - 4) & 3, half = (warp - 4) >> 2;
+    const bool has_dot = MODE == 0 ? epi.dotvec != nullptr : (MODE == 1 || MODE == 3);
+    const bool has_dot2 = MODE == 0 ? epi.dotvec2 != nullptr : MODE == 3;
+    const bool dot_relu = MODE == 0 ? epi.dot_relu != 0 : MODE == 3;
+    const bool relu = MODE == 0 ? epi.relu != 0 : (MODE == 2 || MODE == 3);
+    const bool has_cf = MODE == 0 ? epi.Cf != nullptr : false;
+    const bool has_c = MODE == 0 ? epi.C != nullptr : MODE != 3;
     constexpr int HN = BN / 4;
     const int cb = half * HN;
     unsigned char* stage_out = smem + S::kOutOffset + (warp - 4) * S::kOutWarpBytes;
@@ -138,8 +148,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       for (int c = et; c < BN; c += kGemmEpiWarps * 32) {
         if (epi.bias) cp4(bias_s + buf * BN + c, epi.bias + fn0 + c);
         else bias_s[buf * BN + c] = 0.0f;
-        if (epi.dotvec) cp4(dot_s + buf * BN + c, epi.dotvec + fn0 + c);
-        if (epi.dotvec2) cp4(dot2_s + buf * BN + c, epi.dotvec2 + fn0 + c);
+        if (has_dot) cp4(dot_s + buf * BN + c, epi.dotvec + fn0 + c);
+        if (has_dot2) cp4(dot2_s + buf * BN + c, epi.dotvec2 + fn0 + c);
       }
     };
     // row scale of this thread's row in `tile`: node row index (one tile ahead), then the observation's dm flag
@@ -187,20 +197,21 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           const float4 b4 = *reinterpret_cast<const float4*>(bias_b + c0 + j);
           float x0 = fmaf(__uint_as_float(v[j]), scale, b4.x), x1 = fmaf(__uint_as_float(v[j + 1]), scale, b4.y);
           float x2 = fmaf(__uint_as_float(v[j + 2]), scale, b4.z), x3 = fmaf(__uint_as_float(v[j + 3]), scale, b4.w);
-          if (epi.dotvec) {
+          if (has_dot) {
             const float4 d4 = *reinterpret_cast<const float4*>(dot_b + c0 + j);
-            const float y0 = epi.dot_relu ? fmaxf(x0, 0.f) : x0, y1 = epi.dot_relu ? fmaxf(x1, 0.f) : x1;
-            const float y2 = epi.dot_relu ? fmaxf(x2, 0.f) : x2, y3 = epi.dot_relu ? fmaxf(x3, 0.f) : x3;
+            const float y0 = dot_relu ? fmaxf(x0, 0.f) : x0, y1 = dot_relu ? fmaxf(x1, 0.f) : x1;
+            const float y2 = dot_relu ? fmaxf(x2, 0.f) : x2, y3 = dot_relu ? fmaxf(x3, 0.f) : x3;
             dot = fmaf(y0, d4.x, dot); dot = fmaf(y1, d4.y, dot); dot = fmaf(y2, d4.z, dot); dot = fmaf(y3, d4.w, dot);
-            if (epi.dotvec2) {
+            if (has_dot2) {
               const float4 e4 = *reinterpret_cast<const float4*>(dot2_b + c0 + j);
               dot2 = fmaf(y0, e4.x, dot2); dot2 = fmaf(y1, e4.y, dot2); dot2 = fmaf(y2, e4.z, dot2); dot2 = fmaf(y3, e4.w, dot2);
             }
           }
-          if (epi.relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f); }
-          if (epi.Cf && r < M)                                // lane = row: 16-byte stores, 128 contiguous bytes per lane and chunk
+          if (relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f); }
+          if (has_cf && r < M)                                // lane = row: 16-byte stores, 128 contiguous bytes per lane and chunk
             *reinterpret_cast<float4*>(epi.Cf + (size_t)r * epi.ldcf + n0 + c0 + j) = make_float4(x0, x1, x2, x3);
-          if (epi.c_fp16) {
+          if (!has_c) {
+          } else if (epi.c_fp16) {
             asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(packed[j >> 1]) : "f"(x1), "f"(x0));
             asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(packed[(j >> 1) + 1]) : "f"(x3), "f"(x2));
           } else {
@@ -209,17 +220,17 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             packed[(j >> 1) + 1] = *reinterpret_cast<uint32_t*>(&p1);
           }
         }
-        if (epi.C) {
+        if (has_c) {
           uint4* dst = reinterpret_cast<uint4*>(stage_out + lane * S::kOutRowBytes + (c0 - cb) * 2);
 #pragma unroll
           for (int q = 0; q < 4; ++q) dst[q] = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
         }
-        if (epi.dotvec && (c0 & 32) == 32) {                 // end of this warp's half (64 columns) of a 128-column group
+        if (has_dot && (c0 & 32) == 32) {                 // end of this warp's half (64 columns) of a 128-column group
           // the group's two halves come from two warps: two atomic adds onto a zeroed cell (launcher) -- with exactly two
           // terms the sum does not depend on their order (0 + x + y == 0 + y + x), so the result is deterministic
           if (r < M) {
             atomicAdd(epi.dots + (size_t)r * (shape.N >> 7) + ((n0 + c0) >> 7), dot);
-            if (epi.dotvec2) atomicAdd(epi.dots2 + (size_t)r * (shape.N >> 7) + ((n0 + c0) >> 7), dot2);
+            if (has_dot2) atomicAdd(epi.dots2 + (size_t)r * (shape.N >> 7) + ((n0 + c0) >> 7), dot2);
           }
           dot = 0.f; dot2 = 0.f;
         }
@@ -232,13 +243,16 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       constexpr int kLanesPerRow = HN * 2 / 16;             // 8 (BN=128) or 16 (BN=256) lanes cover one row segment
       constexpr int kRowsPerIter = 32 / kLanesPerRow;
       const int sub = lane / kLanesPerRow, cl = lane % kLanesPerRow;
-      if (epi.C) {
+      if (has_c) {
+        const int gr0 = m0 + ew * 32 + sub;
+        __nv_bfloat16* crow = epi.C + (size_t)gr0 * epi.ldc + n0 + cb + cl * 8;
+        const size_t cstep = (size_t)kRowsPerIter * epi.ldc;
+        const unsigned char* srow = stage_out + sub * S::kOutRowBytes + cl * 16;
 #pragma unroll 4
         for (int rr = 0; rr < 32; rr += kRowsPerIter) {
-          const int row = rr + sub;
-          const int gr = m0 + ew * 32 + row;
-          const uint4 val = *reinterpret_cast<const uint4*>(stage_out + row * S::kOutRowBytes + cl * 16);
-          if (gr < M) *reinterpret_cast<uint4*>(epi.C + (size_t)gr * epi.ldc + n0 + cb + cl * 8) = val;
+          const uint4 val = *reinterpret_cast<const uint4*>(srow + rr * S::kOutRowBytes);
+          if (gr0 + rr < M) *reinterpret_cast<uint4*>(crow) = val;
+          crow += cstep;
         }
       }
       __syncwarp();
@@ -285,17 +299,17 @@ int make_tmap_bf16(CUtensorMap* tm, const void* base, int rows, int cols, int ld
 
 size_t gemm_smem_bytes(int BN) { return BN == 256 ? GemmSmem<256>::kTotal : GemmSmem<128>::kTotal; }
 
-template <int BN>
+template <int BN, int MODE>
 static int launch_bn(const CUtensorMap& ta, const CUtensorMap& tb, GemmShape shape, GemmEpilogue epi, int sm_count, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    MLS_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN>::kTotal));
+    MLS_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN>::kTotal));
     configured = true;
   }
   const int n_tiles = ((shape.M + kBM - 1) / kBM) * (shape.N / BN);
   const int grid = n_tiles < sm_count ? n_tiles : sm_count;
   if (grid <= 0) return MLS_OK;
-  gemm_bf16_tcgen05_kernel<BN><<<grid, kGemmThreads, GemmSmem<BN>::kTotal, st>>>(ta, tb, shape, epi);
+  gemm_bf16_tcgen05_kernel<BN, MODE><<<grid, kGemmThreads, GemmSmem<BN>::kTotal, st>>>(ta, tb, shape, epi);
   mls_count_launch();
   MLS_LAUNCH_CHECK();
   return MLS_OK;
@@ -319,7 +333,21 @@ int gemm_bf16_launch(const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, in
   if (rc) return rc;
   rc = make_tmap_bf16(&tb, B, shape.N, shape.K, ldb, BN);
   if (rc) return rc;
-  return BN == 256 ? launch_bn<256>(ta, tb, shape, epi, sm_count, st) : launch_bn<128>(ta, tb, shape, epi, sm_count, st);
+  int mode = 0;
+  if (!epi.Cf) {
+    if (epi.C && epi.dotvec && !epi.dotvec2 && !epi.dot_relu && !epi.relu) mode = 1;
+    else if (epi.C && !epi.dotvec && epi.relu) mode = 2;
+    else if (!epi.C && epi.dotvec && epi.dotvec2 && epi.dot_relu && epi.relu) mode = 3;
+  }
+  if (BN == 256) {
+    switch (mode) {
+      case 1: return launch_bn<256, 1>(ta, tb, shape, epi, sm_count, st);
+      case 2: return launch_bn<256, 2>(ta, tb, shape, epi, sm_count, st);
+      case 3: return launch_bn<256, 3>(ta, tb, shape, epi, sm_count, st);
+      default: return launch_bn<256, 0>(ta, tb, shape, epi, sm_count, st);
+    }
+  }
+  return launch_bn<128, 0>(ta, tb, shape, epi, sm_count, st);
 }
 
 }  // namespace mls
