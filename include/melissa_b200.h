@@ -320,6 +320,35 @@ int mls_adam_step(float* param, const float* grad, float* exp_avg, float* exp_av
                   float beta1, float beta2, float eps, float weight_decay, int64_t step, float grad_scale,
                   void* stream);
 
+/* ---- training forward / backward of the GATv2 edge phase on per-sample edge lists (melissa_b200/csrc/train_gatv2.cu).
+ * Replaces, for the gradient step, the edge phase of torch_geometric.nn.GATv2Conv as called by
+ * graph_env/env/utils/networks/l_dgn.py:125,133 (gather, leaky_relu(x_l[j] + x_r[i]) . att, softmax over the
+ * incoming edges, weighted sum) and its autograd.  Dense projections stay with the caller. */
+
+/* Capacity of one edge list (self loop + 32 neighbours, rounded up). */
+int mls_train_list_capacity(void);
+/* Per sampled agent observation (rows of 8 * n_nodes + 1 floats, last column = controlling index): the nodes the
+ * controlling node reads, S1 = {c} + radius neighbours (torch_cluster.radius_graph rule, networks/common.py:48), as
+ * consecutive "slots" starting at slot_base[sample], and for every slot its source rows (self first).
+ *   mode 0: s1_cnt[sample] = |S1|            (caller: slot_base = exclusive prefix sum)
+ *   mode 1: tgt_row[slot] = sample * n_nodes + node, src_row[slot][capacity], src_cnt[slot]  (row = sample * n_nodes + node);
+ *           used[row] = 1 (optional, caller-zeroed bytes [n_samples * n_nodes]) for every node row that is a source */
+int mls_train_lists(const float* obs_rows, int64_t row_stride, int32_t n_samples, int32_t n_nodes, float r2, int32_t mode,
+                    int32_t* s1_cnt, const int64_t* slot_base, int32_t* tgt_row, int32_t* src_row, int32_t* src_cnt,
+                    uint8_t* used, void* stream);
+/* out[t][heads * 128] = sum_e alpha[t][e][h] * xl[src_row[t][e]], alpha = softmax_e(<att_h, leaky_relu(xl[src] + xr[tgt_row[t]], 0.2)>)
+ * (exp(e - max) / (sum + 1e-16)); tgt_row[t] < 0: zeros.  fp32. */
+int mls_gatv2_edge_fwd(const float* xl, int64_t ldl, const float* xr, int64_t ldr, const float* att, const int32_t* tgt_row,
+                       const int32_t* src_row, const int32_t* src_cnt, int32_t n_targets, int32_t heads, float* out,
+                       float* alpha, void* stream);
+/* Gradients of the above: d_xl [source rows][heads * 128] (accumulated atomically: zero it first), d_xr [target rows]
+ * [heads * 128] (rows of real targets are overwritten), d_att_part [mls_gatv2_edge_bwd_blocks(n_targets)][heads * 128]
+ * (per-block partial sums of d att: the caller adds them up). */
+int mls_gatv2_edge_bwd_blocks(int32_t n_targets);
+int mls_gatv2_edge_bwd(const float* xl, int64_t ldl, const float* xr, int64_t ldr, const float* att, const int32_t* tgt_row,
+                       const int32_t* src_row, const int32_t* src_cnt, int32_t n_targets, int32_t heads, const float* alpha,
+                       const float* dout, float* d_xl, float* d_xr, float* d_att_part, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -91,7 +91,8 @@ PROF_KERNELS = {None: 0, "proj1": 1, "proj2": 2, "edge1": 3, "edge2": 4, "head0"
 EXPORTS = ["mls_version", "mls_last_error", "mls_device_info", "mls_words_per_row", "mls_launch_count", "mls_set_option", "mls_get_option", "mls_env_reset", "mls_env_step",
            "mls_env_info", "mls_dgn_workspace_bytes", "mls_dgn_chunk_graphs", "mls_dgn_forward", "mls_dgn_prepare",
            "mls_dgn_csr_cache_bytes", "mls_dgn_csr_cache_build", "mls_obs_pack", "mls_obs_unpack", "mls_nstep_returns",
-           "mls_adam_step"]
+           "mls_adam_step", "mls_train_list_capacity", "mls_train_lists", "mls_gatv2_edge_fwd", "mls_gatv2_edge_bwd_blocks",
+           "mls_gatv2_edge_bwd"]
 PACKED_NODE_BYTES = 12
 
 _lib = None
@@ -138,6 +139,10 @@ def lib():
                                     vp, vp, vp, vp]
     L.mls_adam_step.argtypes = [vp, vp, vp, vp, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
                                 C.c_int64, C.c_float, vp]
+    L.mls_train_lists.argtypes = [vp, C.c_int64, C.c_int32, C.c_int32, C.c_float, C.c_int32, vp, vp, vp, vp, vp, vp, vp]
+    L.mls_gatv2_edge_fwd.argtypes = [vp, C.c_int64, vp, C.c_int64, vp, vp, vp, vp, C.c_int32, C.c_int32, vp, vp, vp]
+    L.mls_gatv2_edge_bwd_blocks.argtypes = [C.c_int32]
+    L.mls_gatv2_edge_bwd.argtypes = [vp, C.c_int64, vp, C.c_int64, vp, vp, vp, vp, C.c_int32, C.c_int32, vp, vp, vp, vp, vp, vp]
     for name in EXPORTS:
         getattr(L, name)
     _lib = L

@@ -130,9 +130,113 @@ def _dueling(net, z):
     return q - q.mean(dim=1, keepdim=True) + v
 
 
+class _GATv2Edge(torch.autograd.Function):
+    """Edge phase of GATv2Conv on fixed-capacity edge lists, forward and backward as CUDA kernels
+    (``csrc/train_gatv2.cu``): out[t] = sum_e softmax_e(<att, leaky_relu(xl[src[t, e]] + xr[tgt[t]])>) xl[src[t, e]]."""
+
+    @staticmethod
+    def forward(ctx, xl, xr, att, tgt_row, src_row, src_cnt):
+        from .. import _lib
+        L = _lib.lib()
+        xl, xr, att = xl.contiguous(), xr.contiguous(), att.contiguous()
+        T, heads = tgt_row.numel(), att.numel() // 128
+        out = torch.empty(T, heads * 128, dtype=torch.float32, device=xl.device)
+        alpha = torch.empty(T, src_row.shape[1], heads, dtype=torch.float32, device=xl.device)
+        _lib.check(L.mls_gatv2_edge_fwd(xl.data_ptr(), xl.shape[1], xr.data_ptr(), xr.shape[1], att.data_ptr(), tgt_row.data_ptr(),
+                                        src_row.data_ptr(), src_cnt.data_ptr(), T, heads, out.data_ptr(), alpha.data_ptr(),
+                                        _lib.current_stream_ptr()))
+        ctx.save_for_backward(xl, xr, att, tgt_row, src_row, src_cnt, alpha)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        from .. import _lib
+        L = _lib.lib()
+        xl, xr, att, tgt_row, src_row, src_cnt, alpha = ctx.saved_tensors
+        T, heads = tgt_row.numel(), att.numel() // 128
+        dout = dout.contiguous()
+        d_xl, d_xr = torch.zeros_like(xl), torch.zeros_like(xr)
+        part = torch.empty(L.mls_gatv2_edge_bwd_blocks(T), heads * 128, dtype=torch.float32, device=xl.device)
+        _lib.check(L.mls_gatv2_edge_bwd(xl.data_ptr(), xl.shape[1], xr.data_ptr(), xr.shape[1], att.data_ptr(), tgt_row.data_ptr(),
+                                        src_row.data_ptr(), src_cnt.data_ptr(), T, heads, alpha.data_ptr(), dout.data_ptr(),
+                                        d_xl.data_ptr(), d_xr.data_ptr(), part.data_ptr(), _lib.current_stream_ptr()))
+        return d_xl, d_xr, part.sum(dim=0).view_as(att), None, None, None
+
+
+def train_lists(obs_rows: torch.Tensor, n_agents: int):
+    """Per-sample edge lists on the device (``mls_train_lists``): slot_base [bs], s1_cnt [bs], and for the R slots (the nodes
+    the controlling nodes read, sample after sample, controlling node first) tgt_row [R], src_row [R, cap], src_cnt [R];
+    rows are sample * N + node; used [bs * N] marks the node rows that are a source of some slot.  One host
+    synchronisation (R)."""
+    from .. import _lib
+    L = _lib.lib()
+    obs_rows = obs_rows.contiguous().float()
+    bs, dev = obs_rows.shape[0], obs_rows.device
+    cap, st = L.mls_train_list_capacity(), _lib.current_stream_ptr()
+    s1_cnt = torch.empty(bs, dtype=torch.int32, device=dev)
+    _lib.check(L.mls_train_lists(obs_rows.data_ptr(), obs_rows.shape[1], bs, n_agents, R2, 0, s1_cnt.data_ptr(), None, None, None, None, None, st))
+    incl = torch.cumsum(s1_cnt, dim=0, dtype=torch.int64)
+    slot_base = (incl - s1_cnt).contiguous()
+    R = int(incl[-1].item()) if bs else 0
+    tgt_row = torch.empty(R, dtype=torch.int32, device=dev)
+    src_row = torch.zeros(R, cap, dtype=torch.int32, device=dev)
+    src_cnt = torch.empty(R, dtype=torch.int32, device=dev)
+    used = torch.zeros(bs * n_agents, dtype=torch.uint8, device=dev)
+    _lib.check(L.mls_train_lists(obs_rows.data_ptr(), obs_rows.shape[1], bs, n_agents, R2, 1, None, slot_base.data_ptr(),
+                                 tgt_row.data_ptr(), src_row.data_ptr(), src_cnt.data_ptr(), used.data_ptr(), st))
+    return slot_base, s1_cnt, tgt_row, src_row, src_cnt, used
+
+
+def q_values_l_dgn_fused(net, obs_rows: torch.Tensor) -> torch.Tensor:
+    """L-DGN Q-values with the two GATv2 edge phases (and their backward) on the CUDA kernels of ``csrc/train_gatv2.cu``;
+    same math as ``q_values`` (``l_dgn.py:92-151``), dense layers through ``F.linear``.  CUDA tensors only."""
+    N, heads = net.agents_num, net.num_heads
+    pos, feats, dm, ctrl = split_rows(obs_rows, N, net.input_dim)
+    bs, dev = obs_rows.shape[0], obs_rows.device
+    slot_base, s1_cnt, tgt_row, src_row, src_cnt, used = train_lists(obs_rows, N)
+    cap = src_row.shape[1]
+    # encoder and conv1 source projection only on the node rows somebody reads (a third of them at N = 50)
+    rows_u = torch.nonzero(used, as_tuple=True)[0]
+    remap = torch.zeros(bs * N, dtype=torch.int32, device=dev)
+    remap[rows_u] = torch.arange(rows_u.numel(), dtype=torch.int32, device=dev)
+    x0 = F.relu(_mlp(net.encoder, feats.reshape(bs * N, -1)[rows_u]))          # [used rows, hid]
+    tgt_l = tgt_row.long()
+    tgt_u = remap[tgt_l].long()                                                 # a slot's node is its own first source
+    # conv1 at the S1 slots: sources are (used) node rows, targets the slots' own nodes
+    xl1 = net.conv1.lin_l(x0)
+    xr1 = net.conv1.lin_r(x0[tgt_u])                                            # [R, HC]
+    ar_r = torch.arange(tgt_row.numel(), dtype=torch.int32, device=dev)
+    x1 = F.relu(_GATv2Edge.apply(xl1, xr1, net.conv1.att.view(-1), ar_r, remap[src_row.long()], src_cnt) + net.conv1.bias)   # [R, HC]
+    ctrl_slot = slot_base                                                       # slot 0 of a sample = its controlling node
+    snap1 = x0[tgt_u[ctrl_slot]]
+    snap2 = x1[ctrl_slot]                                                       # before the dm mask
+    x1m = x1 * dm.reshape(bs * N, 1)[tgt_l]
+    # conv2 at the controlling node: sources are the sample's slots (controlling node = self loop first)
+    xl2 = net.conv2.lin_l(x1m)
+    xr2 = net.conv2.lin_r(x1m[ctrl_slot])                                       # [bs, HC]
+    src2 = (slot_base[:, None] + torch.arange(cap, device=dev)[None, :]).to(torch.int32)
+    src2 = torch.where(torch.arange(cap, device=dev)[None, :] < s1_cnt[:, None], src2, torch.zeros_like(src2)).contiguous()
+    ar_b = torch.arange(bs, dtype=torch.int32, device=dev)
+    x2 = F.relu(_GATv2Edge.apply(xl2, xr2, net.conv2.att.view(-1), ar_b, src2, s1_cnt) + net.conv2.bias)       # [bs, HC]
+    return _dueling(net, torch.cat([snap1, snap2, x2], dim=1))
+
+
+def fused_training_available(net, obs_rows) -> bool:
+    import os
+    return (net.KIND == "l_dgn" and obs_rows.is_cuda and net.hidden_dim == 128 and net.num_heads <= 4
+            and os.environ.get("MLS_TRAIN_FUSED", "1") != "0")
+
+
 def q_values(net, obs_rows: torch.Tensor) -> torch.Tensor:
     """Q-values [bs, 2] of agent-observation rows [bs, 8N+1] (last column = controlling index), differentiable
     with respect to ``net``'s parameters."""
+    if fused_training_available(net, obs_rows):
+        return q_values_l_dgn_fused(net, obs_rows)
+    return q_values_torch(net, obs_rows)
+
+
+def q_values_torch(net, obs_rows: torch.Tensor) -> torch.Tensor:
+    """The same through plain torch ops only (any device; every network kind)."""
     N, heads = net.agents_num, net.num_heads
     pos, feats, dm, ctrl = split_rows(obs_rows, N, net.input_dim)
     bs = obs_rows.shape[0]

@@ -185,6 +185,48 @@ def test_training_forward_agrees_with_the_rollout_kernels(kind, kw):
     assert float((q_b - q_t).abs().max()) <= 1e-2 * scale
 
 
+@pytest.mark.parametrize("N", [20, 50])
+def test_fused_gatv2_training_kernels_match_the_torch_autograd_path(N):
+    """mls_train_lists + mls_gatv2_edge_fwd / _bwd (the L-DGN training forward / backward) against the plain torch-op
+    formulation of the same math (autograd.q_values_torch, itself pinned to the oracle on the CPU): Q-values to 1e-5 and
+    every parameter gradient to 1e-4 of the gradient's scale (fp32, different summation orders and atomics)."""
+    from melissa_b200.networks import autograd as ag
+    s = _setup(kind="l_dgn", N=N)
+    for _ in range(6):
+        s["col"].iterate(0.3)
+    env, net = s["env"], s["net"]
+    b_idx, a_idx = torch.nonzero(env.active, as_tuple=True)
+    rows = torch.cat([env.obs.view(env.B, -1)[b_idx], a_idx.float()[:, None]], dim=1)[:400]
+    assert rows.shape[0] >= 50 and ag.fused_training_available(net, rows)
+    target = torch.linspace(-1, 1, rows.shape[0], device=rows.device)
+    grads = []
+    for fn in (ag.q_values_torch, ag.q_values_l_dgn_fused):
+        s["optim"].zero_grad()
+        q = fn(net, rows)
+        ((q[:, 0] - target).pow(2).mean() + q[:, 1].mean()).backward()
+        grads.append((q.detach().clone(), {k: p.grad.detach().clone() for k, p in net.named_parameters()}))
+    (q_t, g_t), (q_f, g_f) = grads
+    assert float((q_t - q_f).abs().max()) <= 1e-5 * max(1.0, float(q_t.abs().max()))
+    assert set(g_t) == set(g_f)
+    for k in g_t:
+        scale = max(float(g_t[k].abs().max()), 1e-6)
+        assert float((g_t[k] - g_f[k]).abs().max()) <= 1e-4 * scale, k
+    # the edge lists themselves: slots of a sample = controlling node first, then its radius neighbours in index order
+    slot_base, s1_cnt, tgt_row, src_row, src_cnt, used = ag.train_lists(rows, N)
+    assert bool(used.bool()[tgt_row.long()].all())
+    pos, _, _, ctrl = ag.split_rows(rows, N, net.input_dim)
+    mask = ag.radius_mask(pos)
+    for b in (0, rows.shape[0] // 2, rows.shape[0] - 1):
+        c = int(ctrl[b])
+        want = [c] + torch.nonzero(mask[b, c]).flatten().tolist()
+        lo = int(slot_base[b])
+        assert (tgt_row[lo:lo + int(s1_cnt[b])] - b * N).tolist() == want
+        for k, i in enumerate(want):
+            srcs = [i] + torch.nonzero(mask[b, i]).flatten().tolist()
+            assert int(src_cnt[lo + k]) == len(srcs)
+            assert (src_row[lo + k, :len(srcs)] - b * N).tolist() == srcs
+
+
 def test_learn_reduces_td_error_and_refreshes_the_rollout_weights():
     s = _setup(N=20, B=128, ring=10, lr=5e-4)
     col, replay, pol, net = s["col"], s["replay"], s["pol"], s["net"]
