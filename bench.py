@@ -629,7 +629,8 @@ def measure_training(args, dev, world, rank, model, N, B, pool, tuple_arrays, st
         "allreduce_us": ar_us, "allreduce_busbw_GBs": busbw,
         "allreduce_share_of_step": (ar_us * 1e-3 / (ms_max / steps)) if ar_us else 0.0,
         "weights_identical_across_ranks": same,
-        "backward": "torch autograd over melissa_b200/networks/autograd.py (v1); optimiser = mls_adam_step kernel",
+        "backward": ("GATv2 edge phase forward + backward = mls_gatv2_edge_fwd / _bwd kernels on per-sample edge lists (mls_train_lists), dense layers = torch fp32 GEMMs under autograd"
+                     if model == "l_dgn" else "torch autograd over melissa_b200/networks/autograd.py") + "; optimiser = mls_adam_step kernel",
     }
     del col, replay, env, pol, optim, flat, net
     torch.cuda.empty_cache()

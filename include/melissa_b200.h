@@ -205,6 +205,9 @@ typedef struct MlsNetWeights {
   const float *c2_wa, *c2_ba, *c2_wb, *c2_bb, *c2_wc, *c2_bc, *c2_att, *c2_bias;
   const float *q_w0, *q_b0, *q_w1, *q_b1, *q_w2, *q_b2; /* Q.model.{0,2,4}                 */
   const float *v_w0, *v_b0, *v_w1, *v_b1, *v_w2, *v_b2; /* V.model.{0,2,4}                 */
+  /* network built without dueling_param (l_dgn.py:88-90,149; dgn_r.py, hl_dgn.py alike): q = out_linear(latent);
+   * out_w [2][latent], out_b [2]; the Q / V pointers are then ignored (may be NULL).  NULL: dueling heads. */
+  const float *out_w, *out_b;
 } MlsNetWeights;
 
 typedef struct MlsForwardArgs {
@@ -332,7 +335,8 @@ int mls_train_list_capacity(void);
  * consecutive "slots" starting at slot_base[sample], and for every slot its source rows (self first).
  *   mode 0: s1_cnt[sample] = |S1|            (caller: slot_base = exclusive prefix sum)
  *   mode 1: tgt_row[slot] = sample * n_nodes + node, src_row[slot][capacity], src_cnt[slot]  (row = sample * n_nodes + node);
- *           used[row] = 1 (optional, caller-zeroed bytes [n_samples * n_nodes]) for every node row that is a source */
+ *           used[row] = 1 (optional, caller-zeroed bytes [n_samples * n_nodes]) for every node row that is a source
+ *   mode 2: the lists of EVERY node (HL-DGN pools over all of them): slot = sample * n_nodes + node, slot_base unused */
 int mls_train_lists(const float* obs_rows, int64_t row_stride, int32_t n_samples, int32_t n_nodes, float r2, int32_t mode,
                     int32_t* s1_cnt, const int64_t* slot_base, int32_t* tgt_row, int32_t* src_row, int32_t* src_cnt,
                     uint8_t* used, void* stream);

@@ -66,7 +66,8 @@ class MlsNetDesc(C.Structure):
 WEIGHT_FIELDS = ["enc_w0", "enc_b0", "enc_w1", "enc_b1",
                  "c1_wa", "c1_ba", "c1_wb", "c1_bb", "c1_wc", "c1_bc", "c1_att", "c1_bias",
                  "c2_wa", "c2_ba", "c2_wb", "c2_bb", "c2_wc", "c2_bc", "c2_att", "c2_bias",
-                 "q_w0", "q_b0", "q_w1", "q_b1", "q_w2", "q_b2", "v_w0", "v_b0", "v_w1", "v_b1", "v_w2", "v_b2"]
+                 "q_w0", "q_b0", "q_w1", "q_b1", "q_w2", "q_b2", "v_w0", "v_b0", "v_w1", "v_b1", "v_w2", "v_b2",
+                 "out_w", "out_b"]
 
 
 class MlsNetWeights(C.Structure):

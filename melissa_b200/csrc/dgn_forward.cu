@@ -385,6 +385,32 @@ __global__ void head_out_kernel(const float* __restrict__ hid, int hh, const int
   }
 }
 
+// Network without dueling heads: q = out_linear(latent) (l_dgn.py:88-90,149).  One warp per row of z.
+__global__ void head_linear_kernel(const float* __restrict__ z, int latent, const int* __restrict__ idx, const int* __restrict__ count,
+                                   int max_rows, const float* __restrict__ w, const float* __restrict__ b, int64_t row0, int per_graph_N,
+                                   float* __restrict__ q_out, int8_t* __restrict__ act_out, int out_mode, ActArgs aa) {
+  const int lane = threadIdx.x & 31;
+  const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int n = count ? min(*count, max_rows) : max_rows;
+  if (t >= n) return;
+  const float* zr = z + (size_t)t * latent;
+  float s0 = 0.f, s1 = 0.f;
+  for (int c = lane; c < latent; c += 32) {
+    s0 = fmaf(zr[c], w[c], s0);
+    s1 = fmaf(zr[c], w[latent + c], s1);
+  }
+  s0 = warp_sum(s0) + b[0]; s1 = warp_sum(s1) + b[1];
+  if (lane == 0) {
+    int64_t orow;
+    if (out_mode == 0) orow = row0 + idx[t];
+    else if (out_mode == 1) orow = row0 / per_graph_N + idx[t] / per_graph_N;
+    else orow = t;
+    q_out[orow * 2 + 0] = s0;
+    q_out[orow * 2 + 1] = s1;
+    if (act_out && out_mode != 2) act_out[orow] = (int8_t)select_action(s0, s1, aa, (uint64_t)orow);
+  }
+}
+
 // HL-DGN: the Q-values of a graph are shared by all its controlling agents (hl_dgn.py:108).
 __global__ void hl_scatter_kernel(const float* __restrict__ qg, const uint8_t* __restrict__ ctrl_mask, int N, int n_graphs,
                                   int64_t graph0, int mode, float* __restrict__ q_out, int8_t* __restrict__ act_out,
@@ -602,10 +628,12 @@ extern "C" int mls_dgn_forward(const MlsNetDesc* d, const MlsNetWeights* w, cons
       split3(st, c1w[t], hid, HC, hid, 1, ws.w_c1[t]);
       if (!hl) split3(st, c2w[t], HC, HC, HC, 1, ws.w_c2[t]);
     }
-    split3(st, w->q_w0, latent, hh, latent, 1, ws.w_q0);
-    split3(st, w->v_w0, latent, hh, latent, 1, ws.w_v0);
-    split3(st, w->q_w1, hh, hh, hh, 1, ws.w_q1);
-    split3(st, w->v_w1, hh, hh, hh, 1, ws.w_v1);
+    if (!w->out_w) {
+      split3(st, w->q_w0, latent, hh, latent, 1, ws.w_q0);
+      split3(st, w->v_w0, latent, hh, latent, 1, ws.w_v0);
+      split3(st, w->q_w1, hh, hh, hh, 1, ws.w_q1);
+      split3(st, w->v_w1, hh, hh, hh, 1, ws.w_v1);
+    }
   }
   auto gemm32 = [&](const float* A, int lda, const float* obs_scale, const float* Wt, const __nv_bfloat16* Wsplit, int ldw,
                     const float* bias, float* C, int ldc, int M, const int* m_dev, int Nout, int K, int relu) {
@@ -688,6 +716,22 @@ extern "C" int mls_dgn_forward(const MlsNetDesc* d, const MlsNetWeights* w, cons
     }
     const int head_rows = hl ? gc : rows;
     const int* m_dev = hl ? nullptr : ws.count;
+    if (w->out_w) {                                           // no dueling heads: one linear layer on the latent row
+      if (!hl) {
+        head_linear_kernel<<<(rows * 32 + 255) / 256, 256, 0, st>>>(ws.z, latent, ws.idx, ws.count, rows, w->out_w, w->out_b,
+                                                                    (int64_t)g0 * N, N, a->q, a->act, a->ctrl_mode, aa);
+        mls_count_launch();
+      } else {
+        head_linear_kernel<<<(gc * 32 + 255) / 256, 256, 0, st>>>(ws.z, latent, nullptr, nullptr, gc, w->out_w, w->out_b, 0, N, ws.qg,
+                                                                  nullptr, 2, aa);
+        const long long nthr = a->ctrl_mode == 1 ? gc : (long long)gc * N;
+        hl_scatter_kernel<<<(unsigned)((nthr + 255) / 256), 256, 0, st>>>(ws.qg, cm, N, gc, g0, a->ctrl_mode, a->q, a->act, aa);
+        mls_count_launch(2);
+      }
+      MLS_LAUNCH_CHECK();
+      first_chunk = false;
+      continue;
+    }
     // dueling head: Q = MLP(latent->hh->hh->2), V = MLP(latent->hh->hh->1)
     prof_begin(MLS_PROF_HEAD0);
     gemm32(ws.z, latent, nullptr, w->q_w0, ws.w_q0, latent, w->q_b0, ws.hid1, 2 * hh, head_rows, m_dev, hh, latent, 1);

@@ -747,6 +747,35 @@ __global__ void head_final_kernel(const float* __restrict__ dots, const float* _
   if (act_out && out_mode != 2) act_out[orow] = (int8_t)select_action_b(o0, o1, aa, (uint64_t)orow);
 }
 
+// Network without dueling heads: q = out_linear(latent) (l_dgn.py:88-90,149) on the bf16 latent rows.  One warp per row.
+__global__ void head_linear_b_kernel(const bf16* __restrict__ z, int latent, const int* __restrict__ idx, const int* __restrict__ count,
+                                     int max_rows, const float* __restrict__ w, const float* __restrict__ b, int64_t row0, int per_graph_N,
+                                     float* __restrict__ q_out, int8_t* __restrict__ act_out, int out_mode, ActArgsB aa) {
+  const int lane = threadIdx.x & 31;
+  const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int n = count ? min(*count, max_rows) : max_rows;
+  if (t >= n) return;
+  const bf16* zr = z + (size_t)t * latent;
+  float s0 = 0.f, s1 = 0.f;
+  for (int c = lane; c < latent; c += 32) {
+    const float v = __bfloat162float(zr[c]);
+    s0 = fmaf(v, w[c], s0);
+    s1 = fmaf(v, w[latent + c], s1);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); }
+  s0 += b[0]; s1 += b[1];
+  if (lane == 0) {
+    int64_t orow;
+    if (out_mode == 0) orow = row0 + idx[t];
+    else if (out_mode == 1) orow = row0 / per_graph_N + idx[t] / per_graph_N;
+    else orow = t;
+    q_out[orow * 2 + 0] = s0;
+    q_out[orow * 2 + 1] = s1;
+    if (act_out && out_mode != 2) act_out[orow] = (int8_t)select_action_b(s0, s1, aa, (uint64_t)orow);
+  }
+}
+
 __global__ void hl_scatter_b_kernel(const float* __restrict__ qg, const uint8_t* __restrict__ ctrl_mask, int N, int n_graphs,
                                     int64_t graph0, int mode, float* __restrict__ q_out, int8_t* __restrict__ act_out, ActArgsB aa) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -952,24 +981,29 @@ int pack_parameters(const MlsNetDesc* d, const MlsNetWeights* w, const WsB& ws, 
     add2(w->c2_wb, ws.w_c2, HC, HC, HC, HC, 0);
     if (tr) add2(w->c2_wc, ws.w_c2, HC, HC, HC, 2 * HC, 0);
   }
+  const bool dueling = w->out_w == nullptr;
   MLS_CUDA(cudaMemsetAsync(ws.w_h1, 0, (size_t)hh2 * hh2 * 2, st));
-  add2(w->q_w0, ws.w_h0, hh, latent, latent, 0, 0);
-  add2(w->v_w0, ws.w_h0, hh, latent, latent, hh, 0);
-  add2(w->q_w1, ws.w_h1, hh, hh, hh2, 0, 0);         // block diagonal: Q and V hidden layers in one GEMM
-  add2(w->v_w1, ws.w_h1, hh, hh, hh2, hh, hh);
+  if (dueling) {
+    add2(w->q_w0, ws.w_h0, hh, latent, latent, 0, 0);
+    add2(w->v_w0, ws.w_h0, hh, latent, latent, hh, 0);
+    add2(w->q_w1, ws.w_h1, hh, hh, hh2, 0, 0);       // block diagonal: Q and V hidden layers in one GEMM
+    add2(w->v_w1, ws.w_h1, hh, hh, hh2, hh, hh);
+  }
   c2.n = n;
-  cvt_weights_kernel<<<dim3(128, n), 256, 0, st>>>(c2);
+  if (n > 0) cvt_weights_kernel<<<dim3(128, n), 256, 0, st>>>(c2);
   CatJobs bj{};
   int m = 0;
   auto addb = [&](const float* src, float* dst, int cnt) { bj.src[m] = src; bj.dst[m] = dst; bj.n[m] = cnt; ++m; };
   addb(w->c1_ba, ws.b_c1, HC); addb(w->c1_bb, ws.b_c1 + HC, HC);
   if (tr) addb(w->c1_bc, ws.b_c1 + 2 * HC, HC);
   if (!tr) { addb(w->c1_att, ws.att1, HC); addb(w->c1_att, ws.att1 + HC, HC); }
-  addb(w->q_b0, ws.b_h0, hh); addb(w->v_b0, ws.b_h0 + hh, hh);
-  addb(w->q_b1, ws.b_h1, hh); addb(w->v_b1, ws.b_h1 + hh, hh);
-  // output layer as dot vectors for the epilogue of the last hidden-layer GEMM: [wq[0] | wv], [wq[1] | 0]
   MLS_CUDA(cudaMemsetAsync(ws.hv2, 0, (size_t)hh2 * 4, st));
-  addb(w->q_w2, ws.hv1, hh); addb(w->v_w2, ws.hv1 + hh, hh); addb(w->q_w2 + hh, ws.hv2, hh);
+  if (dueling) {
+    addb(w->q_b0, ws.b_h0, hh); addb(w->v_b0, ws.b_h0 + hh, hh);
+    addb(w->q_b1, ws.b_h1, hh); addb(w->v_b1, ws.b_h1 + hh, hh);
+    // output layer as dot vectors for the epilogue of the last hidden-layer GEMM: [wq[0] | wv], [wq[1] | 0]
+    addb(w->q_w2, ws.hv1, hh); addb(w->v_w2, ws.hv1 + hh, hh); addb(w->q_w2 + hh, ws.hv2, hh);
+  }
   bj.count = m;
   cat_bias_kernel<<<dim3(2, m), 256, 0, st>>>(bj);
   if (!hl) {
@@ -1204,7 +1238,19 @@ int dgn_forward_bf16(const MlsNetDesc* d, const MlsNetWeights* w, const MlsForwa
     // dueling head on the tensor cores: [Q0;V0] stacked, then block-diagonal [Q1 0; 0 V1]
     const int head_rows = hl ? gc : rows;
     const int* m_dev = hl ? nullptr : ws.count;
-    {
+    if (w->out_w) {                                           // no dueling heads: one linear layer on the latent row
+      if (!hl) {
+        head_linear_b_kernel<<<(rows * 32 + 255) / 256, 256, 0, st>>>(ws.z, latent, ws.idx, ws.count, rows, w->out_w, w->out_b,
+                                                                      (int64_t)g0 * N, N, a->q, a->act, a->ctrl_mode, aa);
+        mls_count_launch();
+      } else {
+        head_linear_b_kernel<<<(gc * 32 + 255) / 256, 256, 0, st>>>(ws.z, latent, nullptr, nullptr, gc, w->out_w, w->out_b, 0, N, ws.qg,
+                                                                    nullptr, 2, aa);
+        const long long nthr = a->ctrl_mode == 1 ? gc : (long long)gc * N;
+        hl_scatter_b_kernel<<<(unsigned)((nthr + 255) / 256), 256, 0, st>>>(ws.qg, cm, N, gc, g0, a->ctrl_mode, a->q, a->act, aa);
+        mls_count_launch(2);
+      }
+    } else {
       GemmEpilogue e0{ws.hid1, hh2, ws.b_h0, nullptr, 0, N, 1, nullptr, nullptr};
       prof_begin(MLS_PROF_HEAD0);
       if ((rc = gemm_bf16_launch(ws.z, latent, ws.w_h0, latent, GemmShape{head_rows, hh2, latent, m_dev}, e0, sms, st))) return rc;

@@ -49,7 +49,7 @@ __device__ __forceinline__ int scan_neighbours(const float* __restrict__ row, in
   return emitted;
 }
 
-// mode 0: s1_cnt[b] = |S1|.   mode 1: fill the compact slot arrays at slot_base[b].
+// mode 0: s1_cnt[b] = |S1|.   mode 1: fill the compact slot arrays at slot_base[b].   mode 2: lists of ALL nodes, slot = node row.
 __global__ void __launch_bounds__(128) train_lists_kernel(const float* __restrict__ obs, long long stride, int bs, int N, float r2, int mode,
                                                           int* __restrict__ s1_cnt, const long long* __restrict__ slot_base,
                                                           int* __restrict__ tgt_row, int* __restrict__ src_row, int* __restrict__ src_cnt,
@@ -59,6 +59,15 @@ __global__ void __launch_bounds__(128) train_lists_kernel(const float* __restric
   const int b = blockIdx.x * 4 + warp;
   if (b >= bs) return;
   const float* row = obs + (long long)b * stride;
+  if (mode == 2) {                               // every node is a target (HL-DGN): slot = node row, no compaction
+    for (int i = 0; i < N; ++i) {
+      const long long slot = (long long)b * N + i;
+      int* dst = src_row + slot * kCap;
+      const int d = scan_neighbours(row, N, i, r2, lane, [&](int pos, int j) { dst[1 + pos] = b * N + j; });
+      if (lane == 0) { tgt_row[slot] = b * N + i; dst[0] = b * N + i; src_cnt[slot] = 1 + d; }
+    }
+    return;
+  }
   int c = (int)row[(long long)N * 8];
   c = c < 0 ? 0 : (c > N - 1 ? N - 1 : c);
   int* my = s1[warp];
@@ -195,7 +204,7 @@ extern "C" int mls_train_lists(const float* obs_rows, int64_t row_stride, int32_
                                int32_t* s1_cnt, const int64_t* slot_base, int32_t* tgt_row, int32_t* src_row, int32_t* src_cnt,
                                uint8_t* used, void* stream) {
   MLS_CHECK_ARG(obs_rows && n_nodes > 0 && row_stride >= (int64_t)n_nodes * 8 + 1, "bad observation rows");
-  MLS_CHECK_ARG(mode == 0 ? s1_cnt != nullptr : (slot_base && tgt_row && src_row && src_cnt), "NULL output");
+  MLS_CHECK_ARG(mode == 0 ? s1_cnt != nullptr : ((slot_base || mode == 2) && tgt_row && src_row && src_cnt), "NULL output");
   MLS_CHECK_ARG((int64_t)n_samples * n_nodes < (1ll << 31), "too many node rows for 32-bit row indices");
   if (n_samples <= 0) return MLS_OK;
   train_lists_kernel<<<(n_samples + 3) / 4, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(

@@ -123,9 +123,9 @@ def _mlp(params, x):
 
 
 def _dueling(net, z):
-    q = _mlp(net.Q, z)
     if not net.use_dueling:
-        return q
+        return net.out_linear(z)
+    q = _mlp(net.Q, z)
     v = _mlp(net.V, z)
     return q - q.mean(dim=1, keepdim=True) + v
 
@@ -221,9 +221,32 @@ def q_values_l_dgn_fused(net, obs_rows: torch.Tensor) -> torch.Tensor:
     return _dueling(net, torch.cat([snap1, snap2, x2], dim=1))
 
 
+def q_values_hl_dgn_fused(net, obs_rows: torch.Tensor) -> torch.Tensor:
+    """HL-DGN Q-values (``hl_dgn.py:82-119``): one GATv2 layer at every node, masked, pooled over the graph; the edge
+    phase and its backward on the CUDA kernels."""
+    from .. import _lib
+    L = _lib.lib()
+    N = net.agents_num
+    pos, feats, dm, ctrl = split_rows(obs_rows, N, net.input_dim)
+    obs_c = obs_rows.contiguous().float()
+    bs, dev = obs_rows.shape[0], obs_rows.device
+    cap = L.mls_train_list_capacity()
+    tgt_row = torch.empty(bs * N, dtype=torch.int32, device=dev)
+    src_row = torch.zeros(bs * N, cap, dtype=torch.int32, device=dev)
+    src_cnt = torch.empty(bs * N, dtype=torch.int32, device=dev)
+    _lib.check(L.mls_train_lists(obs_c.data_ptr(), obs_c.shape[1], bs, N, R2, 2, None, None, tgt_row.data_ptr(), src_row.data_ptr(),
+                                 src_cnt.data_ptr(), None, _lib.current_stream_ptr()))
+    x0 = F.relu(_mlp(net.encoder, feats.reshape(bs * N, -1)))
+    out = _GATv2Edge.apply(net.conv1.lin_l(x0), net.conv1.lin_r(x0), net.conv1.att.view(-1), tgt_row, src_row, src_cnt)
+    x1 = F.relu(out + net.conv1.bias).view(bs, N, -1) * dm
+    agg = net.aggregator_name
+    z = x1.amax(dim=1) if agg == "max" else (x1.mean(dim=1) if agg == "mean" else x1.sum(dim=1))
+    return _dueling(net, z)
+
+
 def fused_training_available(net, obs_rows) -> bool:
     import os
-    return (net.KIND == "l_dgn" and obs_rows.is_cuda and net.hidden_dim == 128 and net.num_heads <= 4
+    return (net.KIND in ("l_dgn", "hl_dgn") and obs_rows.is_cuda and net.hidden_dim == 128 and net.num_heads <= 4
             and os.environ.get("MLS_TRAIN_FUSED", "1") != "0")
 
 
@@ -231,7 +254,7 @@ def q_values(net, obs_rows: torch.Tensor) -> torch.Tensor:
     """Q-values [bs, 2] of agent-observation rows [bs, 8N+1] (last column = controlling index), differentiable
     with respect to ``net``'s parameters."""
     if fused_training_available(net, obs_rows):
-        return q_values_l_dgn_fused(net, obs_rows)
+        return q_values_l_dgn_fused(net, obs_rows) if net.KIND == "l_dgn" else q_values_hl_dgn_fused(net, obs_rows)
     return q_values_torch(net, obs_rows)
 
 

@@ -115,7 +115,13 @@ class DGNBase(nn.Module):
 
     def _build_heads(self, latent, dueling_param, output_dim):
         if dueling_param is None:
-            raise NotImplementedError("only the dueling head used by every reference script is implemented")
+            # l_dgn.py:88-90 / dgn_r.py / hl_dgn.py: a single linear layer on the latent row
+            if output_dim != 2:
+                raise NotImplementedError("the environment's action space is Discrete(2)")
+            self.head_hidden = 128                   # unused by the kernels for this head
+            self.out_linear = nn.Linear(latent, output_dim)
+            self.output_dim = output_dim
+            return
         q_kwargs, v_kwargs = dict(dueling_param[0]), dict(dueling_param[1])
         qh, vh = list(q_kwargs.get("hidden_sizes", ())), list(v_kwargs.get("hidden_sizes", ()))
         if len(qh) != 2 or qh != vh or qh[0] != qh[1]:
@@ -146,8 +152,10 @@ class DGNBase(nn.Module):
     def weights_struct(self):
         """MlsNetWeights over the live parameters (must be fp32, contiguous, on the GPU)."""
         enc = self.encoder.linears()
-        q, v = self.Q.linears(), self.V.linears()
+        q, v = (self.Q.linears(), self.V.linears()) if self.use_dueling else ([], [])
         t = {"enc_w0": enc[0].weight, "enc_b0": enc[0].bias, "enc_w1": enc[1].weight, "enc_b1": enc[1].bias}
+        if not self.use_dueling:
+            t["out_w"], t["out_b"] = self.out_linear.weight, self.out_linear.bias
         for name, conv in (("c1", self.conv1), ("c2", getattr(self, "conv2", None))):
             vals = self._conv_tensors(conv) if conv is not None else [None] * 8
             for k, val in zip(("wa", "ba", "wb", "bb", "wc", "bc", "att", "bias"), vals):

@@ -118,6 +118,8 @@ def transformer_conv(sd, prefix, x, edges, heads):
 
 
 def _dueling(sd, z):
+    if "out_linear.weight" in sd:                # network built without dueling_param (l_dgn.py:88-90,149)
+        return F.linear(z, sd["out_linear.weight"], sd["out_linear.bias"])
     q = mlp(sd, "Q", z, 3)
     v = mlp(sd, "V", z, 3)
     return q - q.mean(dim=1, keepdim=True) + v
@@ -222,7 +224,7 @@ def exploration_noise(act: np.ndarray, eps: float, u_eps: np.ndarray, u_act: np.
 
 # ------------------------------------------------------------------ random parameters
 def init_state_dict(kind: str, seed: int = 9, hidden: int = 128, heads: int = 4, input_dim: int = 5,
-                    dtype=torch.float32):
+                    dtype=torch.float32, dueling: bool = True):
     """Random weights with the reference's parameter names/shapes and
     the libraries' default initialisers (nn.Linear default for tianshou MLP and
     TransformerConv linears; glorot + zero bias for GATv2Conv)."""
@@ -254,6 +256,9 @@ def init_state_dict(kind: str, seed: int = 9, hidden: int = 128, heads: int = 4,
             linear(f"{name}.lin_l", hc, din, glorot=True)
             linear(f"{name}.lin_r", hc, din, glorot=True)
     latent = hc if kind == "hl_dgn" else hidden + 2 * hc
+    if not dueling:
+        linear("out_linear", 2, latent)
+        return {k: v.to(dtype) for k, v in sd.items()}
     for head, out in (("Q", 2), ("V", 1)):
         linear(f"{head}.model.0", 128, latent)
         linear(f"{head}.model.2", 128, 128)

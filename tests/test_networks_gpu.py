@@ -58,6 +58,36 @@ def _assert_q(got, want, what=""):
     assert err <= REL_TOL * scale, f"{what}: max abs err {err:.3e} > {REL_TOL} * {scale:.3f}"
 
 
+@pytest.mark.parametrize("kind,kw", [("l_dgn", {}), ("dgn_r", {}), ("hl_dgn", {"aggregator": "mean"})])
+@pytest.mark.parametrize("precision", ["fp32", "bf16", "bf16-tables"])
+def test_network_without_dueling_heads(kind, kw, precision):
+    """dueling_param=None: q = out_linear(latent) (l_dgn.py:88-90,149), agent rows and obs-matrix batches, every precision."""
+    from melissa_b200.networks import NETWORKS
+    N, B = 20, 48
+    sd = no.init_state_dict(kind, seed=31, dueling=False)
+    sd["out_linear.bias"] = torch.tensor([0.3, -0.2])
+    m = NETWORKS[kind](5, 128, 2, 4, N, dueling_param=None, device="cuda", **kw)
+    assert sorted(m.state_dict()) == sorted(sd) and not m.use_dueling
+    m.load_state_dict(sd)
+    m = m.cuda().set_precision("fp32" if precision == "fp32" else "bf16")
+    tol = REL_TOL if precision == "fp32" else BF16_TOL
+    om = _obs_matrix(N, B, 13)
+    cm = np.random.default_rng(3).random((B, N)) < 0.3
+    want = no.forward_graphs(kind, sd, torch.as_tensor(om), torch.as_tensor(cm), N, **kw).numpy()
+    q, act = m.forward_graphs(torch.as_tensor(om, device="cuda"), torch.as_tensor(cm, device="cuda").to(torch.uint8),
+                              discrete_features=precision == "bf16-tables")
+    q, act = q.cpu().numpy(), act.cpu().numpy()
+    scale = max(1.0, float(np.abs(want).max()))
+    assert float(np.abs(q - want).max()) <= tol * scale
+    assert np.all(q[~cm] == 0) and np.all(act[~cm] == -1)
+    np.testing.assert_array_equal(act[cm], (q[..., 1] > q[..., 0]).astype(np.int8)[cm])
+    ctrl = np.random.default_rng(1).integers(0, N, size=B).astype(np.float32)
+    rows = np.concatenate([om.reshape(B, -1), ctrl[:, None]], axis=1)
+    want_r = no.FORWARDS[kind](sd, torch.as_tensor(rows), N, **kw).numpy()
+    q_r, _ = m(rows)
+    assert float(np.abs(q_r.cpu().numpy() - want_r).max()) <= tol * max(1.0, float(np.abs(want_r).max()))
+
+
 @pytest.mark.parametrize("kind", ["l_dgn", "dgn_r", "hl_dgn"])
 @pytest.mark.parametrize("N", [20, 50])
 def test_forward_agent_rows_matches_oracle(kind, N):

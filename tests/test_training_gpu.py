@@ -185,6 +185,29 @@ def test_training_forward_agrees_with_the_rollout_kernels(kind, kw):
     assert float((q_b - q_t).abs().max()) <= 1e-2 * scale
 
 
+@pytest.mark.parametrize("agg", ["max", "mean", "add"])
+def test_fused_hl_dgn_training_forward_backward_matches_the_torch_path(agg):
+    from melissa_b200.networks import autograd as ag
+    s = _setup(kind="hl_dgn", N=20, aggregator=agg)
+    for _ in range(6):
+        s["col"].iterate(0.3)
+    env, net = s["env"], s["net"]
+    b_idx, a_idx = torch.nonzero(env.active, as_tuple=True)
+    rows = torch.cat([env.obs.view(env.B, -1)[b_idx], a_idx.float()[:, None]], dim=1)[:200]
+    assert ag.fused_training_available(net, rows)
+    target = torch.linspace(-1, 1, rows.shape[0], device=rows.device)
+    res = []
+    for fn in (ag.q_values_torch, ag.q_values_hl_dgn_fused):
+        s["optim"].zero_grad()
+        q = fn(net, rows)
+        ((q[:, 0] - target).pow(2).mean() + q[:, 1].mean()).backward()
+        res.append((q.detach().clone(), {k: p.grad.detach().clone() for k, p in net.named_parameters()}))
+    (q_t, g_t), (q_f, g_f) = res
+    assert float((q_t - q_f).abs().max()) <= 1e-5 * max(1.0, float(q_t.abs().max()))
+    for k in g_t:
+        assert float((g_t[k] - g_f[k]).abs().max()) <= 1e-4 * max(float(g_t[k].abs().max()), 1e-6), k
+
+
 @pytest.mark.parametrize("N", [20, 50])
 def test_fused_gatv2_training_kernels_match_the_torch_autograd_path(N):
     """mls_train_lists + mls_gatv2_edge_fwd / _bwd (the L-DGN training forward / backward) against the plain torch-op

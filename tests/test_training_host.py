@@ -46,6 +46,26 @@ def test_autograd_forward_equals_oracle_and_reaches_every_parameter(kind, kw, N)
             assert p.grad is not None and torch.isfinite(p.grad).all(), name
 
 
+@pytest.mark.parametrize("kind,kw", [("l_dgn", {}), ("dgn_r", {}), ("hl_dgn", {"aggregator": "add"})])
+def test_network_without_dueling_heads_on_the_host(kind, kw):
+    """dueling_param=None builds ``out_linear`` (l_dgn.py:88-90,149): checkpoint keys, the differentiable forward against
+    the oracle, gradients reaching it."""
+    from melissa_b200.networks import NETWORKS
+    from melissa_b200.networks.autograd import q_values
+    N = 12
+    sd = no.init_state_dict(kind, seed=6, dueling=False)
+    assert "out_linear.weight" in sd and not any(k.startswith(("Q.", "V.")) for k in sd)
+    m = NETWORKS[kind](5, 128, 2, 4, N, dueling_param=None, device="cpu", **kw)
+    assert sorted(m.state_dict()) == sorted(sd)
+    m.load_state_dict(sd)
+    rows = _rows(N, 10, 4)
+    want = no.FORWARDS[kind](sd, rows, N, **kw)
+    got = q_values(m, rows)
+    assert float((got - want).abs().max()) <= 1e-5 * max(1.0, float(want.abs().max()))
+    got.pow(2).sum().backward()
+    assert m.out_linear.weight.grad is not None and float(m.out_linear.weight.grad.abs().sum()) > 0
+
+
 def test_batch_container_operations():
     from melissa_b200.policy import Batch
     b = Batch(obs=Batch(obs=np.arange(12).reshape(4, 3), mask=np.ones((4, 2), bool), agent_id=np.array(["0", "1", "0", "2"])),
