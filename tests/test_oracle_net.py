@@ -5,6 +5,7 @@ import math
 import numpy as np
 import pytest
 import torch
+import torch.nn.functional as F
 
 from oracle import net_oracle as no
 
@@ -128,3 +129,62 @@ def test_dqn_act_and_exploration_noise():
     out = no.exploration_noise(act, 0.05, np.array([0.01, 0.9, 0.04]), np.array([[0.8, 0.7], [0.9, 0.1], [0.4, 0.5]]))
     assert out.tolist() == [0, 0, 1]
     assert no.exploration_noise(act, 0.0, u_eps, u_act).tolist() == act.tolist()
+
+
+def test_transformer_conv_equals_torch_scaled_dot_product_attention():
+    """An implementation maintained by somebody else for the one conv that has one in torch itself: PyG's
+    TransformerConv(root_weight=False, beta=False) is multi-head scaled dot-product attention of every target over its
+    incoming edges -- torch.nn.functional.scaled_dot_product_attention with the edge mask (targets with at least one
+    edge; PyG's softmax adds 1e-16 to the denominator, far below fp32 resolution here)."""
+    torch.manual_seed(4)
+    B, N, D, H, C = 3, 14, 32, 4, 16
+    sd = {}
+    for lin in ("lin_query", "lin_key", "lin_value"):
+        sd[f"c.{lin}.weight"] = torch.randn(H * C, D) / math.sqrt(D)
+        sd[f"c.{lin}.bias"] = torch.randn(H * C) * 0.1
+    x = torch.randn(B, N, D)
+    edges = torch.rand(B, N, N) < 0.3
+    edges &= ~torch.eye(N, dtype=torch.bool)
+    edges[:, :, 0] |= torch.arange(N)[None, :] != 0           # every target but node 0 has an edge
+    edges[:, 0, 1] = True
+    got = no.transformer_conv(sd, "c", x, edges, H).view(B, N, H, C)
+    q = F.linear(x, sd["c.lin_query.weight"], sd["c.lin_query.bias"]).view(B, N, H, C).transpose(1, 2)
+    k = F.linear(x, sd["c.lin_key.weight"], sd["c.lin_key.bias"]).view(B, N, H, C).transpose(1, 2)
+    v = F.linear(x, sd["c.lin_value.weight"], sd["c.lin_value.bias"]).view(B, N, H, C).transpose(1, 2)
+    want = F.scaled_dot_product_attention(q, k, v, attn_mask=edges[:, None, :, :]).transpose(1, 2)
+    assert float((got - want).abs().max()) < 1e-5
+
+
+def test_net_oracle_against_torch_geometric_when_installed():
+    """Auto-pinning: wherever torch_geometric (and torch_cluster for radius_graph) can be imported, the oracle's convs
+    and edge rule are compared with the real GATv2Conv / TransformerConv / radius_graph.  Not installable in the build
+    image (no index access): skipped there, and the network half of the oracle stays 'parity unpinned'."""
+    tg = pytest.importorskip("torch_geometric")
+    from torch_geometric.nn import GATv2Conv, TransformerConv
+    torch.manual_seed(7)
+    B, N, D, H, C = 2, 11, 24, 4, 16
+    x = torch.randn(B, N, D)
+    edges = torch.rand(B, N, N) < 0.35
+    edges &= ~torch.eye(N, dtype=torch.bool)
+    bi, ti, sj = torch.nonzero(edges, as_tuple=True)                          # edges[b, target i, source j]
+    edge_index = torch.stack([bi * N + sj, bi * N + ti])                      # PyG: row 0 = source, row 1 = target
+    xf = x.reshape(B * N, D)
+    gat = GATv2Conv(D, C, heads=H)
+    sd = {f"c.{k}": v.detach().clone() for k, v in gat.state_dict().items()}
+    want = gat(xf, edge_index).view(B, N, H * C)
+    assert float((no.gatv2_conv(sd, "c", x, edges, H) - want).abs().max()) < 1e-5
+    tr = TransformerConv(D, C, heads=H, root_weight=False)
+    sd = {f"c.{k}": v.detach().clone() for k, v in tr.state_dict().items()}
+    want = tr(xf, edge_index).view(B, N, H * C)
+    assert float((no.transformer_conv(sd, "c", x, edges, H) - want).abs().max()) < 1e-5
+    try:
+        from torch_geometric.nn import radius_graph
+        pos = torch.rand(B, N, 2) * 0.5
+        ei = radius_graph(pos.reshape(-1, 2), r=no.RADIUS, batch=torch.arange(B).repeat_interleave(N), loop=False, max_num_neighbors=32)
+        got = torch.zeros(B * N, B * N, dtype=torch.bool)
+        got[ei[1], ei[0]] = True
+        mask = no.radius_graph_mask(pos)
+        for b in range(B):
+            assert torch.equal(got[b * N:(b + 1) * N, b * N:(b + 1) * N], mask[b])
+    except ImportError:                                                       # torch_cluster missing: the conv checks above still count
+        pass
