@@ -353,6 +353,17 @@ int mls_gatv2_edge_bwd(const float* xl, int64_t ldl, const float* xr, int64_t ld
                        const int32_t* src_row, const int32_t* src_cnt, int32_t n_targets, int32_t heads, const float* alpha,
                        const float* dout, float* d_xl, float* d_xr, float* d_att_part, void* stream);
 
+/* The same for torch_geometric.nn.TransformerConv(root_weight=False, beta=False) (dgn_r.py:105,113): logit = <q[tgt], k[src]> /
+ * sqrt(128), out = sum_e alpha_e v[src]; no self loop (the first entry of every list -- the node itself -- is skipped).
+ * k, v share the row stride lds.  Backward: d_k, d_v accumulated atomically (zero them first), d_q rows of real targets
+ * overwritten. */
+int mls_transformer_edge_fwd(const float* k, const float* v, int64_t lds, const float* q, int64_t ldq, const int32_t* tgt_row,
+                             const int32_t* src_row, const int32_t* src_cnt, int32_t n_targets, int32_t heads, float* out,
+                             float* alpha, void* stream);
+int mls_transformer_edge_bwd(const float* k, const float* v, int64_t lds, const float* q, int64_t ldq, const int32_t* tgt_row,
+                             const int32_t* src_row, const int32_t* src_cnt, int32_t n_targets, int32_t heads,
+                             const float* alpha, const float* dout, float* d_k, float* d_v, float* d_q, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

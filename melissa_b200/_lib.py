@@ -93,7 +93,7 @@ EXPORTS = ["mls_version", "mls_last_error", "mls_device_info", "mls_words_per_ro
            "mls_env_info", "mls_dgn_workspace_bytes", "mls_dgn_chunk_graphs", "mls_dgn_forward", "mls_dgn_prepare",
            "mls_dgn_csr_cache_bytes", "mls_dgn_csr_cache_build", "mls_obs_pack", "mls_obs_unpack", "mls_nstep_returns",
            "mls_adam_step", "mls_train_list_capacity", "mls_train_lists", "mls_gatv2_edge_fwd", "mls_gatv2_edge_bwd_blocks",
-           "mls_gatv2_edge_bwd"]
+           "mls_gatv2_edge_bwd", "mls_transformer_edge_fwd", "mls_transformer_edge_bwd"]
 PACKED_NODE_BYTES = 12
 
 _lib = None
@@ -144,6 +144,8 @@ def lib():
     L.mls_gatv2_edge_fwd.argtypes = [vp, C.c_int64, vp, C.c_int64, vp, vp, vp, vp, C.c_int32, C.c_int32, vp, vp, vp]
     L.mls_gatv2_edge_bwd_blocks.argtypes = [C.c_int32]
     L.mls_gatv2_edge_bwd.argtypes = [vp, C.c_int64, vp, C.c_int64, vp, vp, vp, vp, C.c_int32, C.c_int32, vp, vp, vp, vp, vp, vp]
+    L.mls_transformer_edge_fwd.argtypes = [vp, vp, C.c_int64, vp, C.c_int64, vp, vp, vp, C.c_int32, C.c_int32, vp, vp, vp]
+    L.mls_transformer_edge_bwd.argtypes = [vp, vp, C.c_int64, vp, C.c_int64, vp, vp, vp, C.c_int32, C.c_int32, vp, vp, vp, vp, vp, vp]
     for name in EXPORTS:
         getattr(L, name)
     _lib = L

@@ -191,6 +191,90 @@ __global__ void __launch_bounds__(128) gatv2_bwd_kernel(const EdgeArgs a, const 
   *reinterpret_cast<float4*>(d_att_part + (long long)blockIdx.x * HC + col) = datt;
 }
 
+// ---- TransformerConv(root_weight=False, beta=False) edge phase (DGN-R): logit_e = <q_t, k_e> / sqrt(128), out = sum_e a_e v_e;
+// no self loop: the lists' first entry (the node itself) is skipped.
+struct TrArgs {
+  const float* k; const float* v; long long lds;   // source-side projections
+  const float* q; long long ldq;                   // target-side projection
+  const int* tgt_row; const int* src_row; const int* src_cnt;
+  int T, H;
+};
+
+__global__ void __launch_bounds__(128) transformer_fwd_kernel(const TrArgs a, float* __restrict__ out, float* __restrict__ alpha) {
+  __shared__ float lg[4][kCap];
+  const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int HC = a.H * kTC, col = h * kTC + lane * 4;
+  const float scale = rsqrtf((float)kTC);
+  float* my = lg[h];
+  for (int t = blockIdx.x; t < a.T; t += gridDim.x) {
+    const int r = a.tgt_row[t];
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r >= 0) {
+      const int cnt = a.src_cnt[t];
+      const int* src = a.src_row + (long long)t * kCap;
+      const float4 q = *reinterpret_cast<const float4*>(a.q + (long long)r * a.ldq + col);
+      float mx = -INFINITY;
+      for (int e = 1; e < cnt; ++e) {
+        const float4 ke = *reinterpret_cast<const float4*>(a.k + (long long)src[e] * a.lds + col);
+        const float p = warp_sum(fmaf(q.x, ke.x, fmaf(q.y, ke.y, fmaf(q.z, ke.z, q.w * ke.w)))) * scale;
+        if (lane == 0) my[e] = p;
+        mx = fmaxf(mx, p);
+      }
+      __syncwarp();
+      float sum = 0.f;
+      for (int e = 1; e < cnt; ++e) sum += expf(my[e] - mx);
+      const float inv = 1.f / (sum + 1e-16f);
+      for (int e = 1; e < cnt; ++e) {
+        const float w = expf(my[e] - mx) * inv;
+        const float4 ve = *reinterpret_cast<const float4*>(a.v + (long long)src[e] * a.lds + col);
+        acc.x = fmaf(w, ve.x, acc.x); acc.y = fmaf(w, ve.y, acc.y); acc.z = fmaf(w, ve.z, acc.z); acc.w = fmaf(w, ve.w, acc.w);
+        if (lane == 0) alpha[((long long)t * kCap + e) * a.H + h] = w;
+      }
+      __syncwarp();
+    }
+    *reinterpret_cast<float4*>(out + (long long)t * HC + col) = acc;
+  }
+}
+
+__global__ void __launch_bounds__(128) transformer_bwd_kernel(const TrArgs a, const float* __restrict__ alpha, const float* __restrict__ dout,
+                                                              float* __restrict__ d_k, float* __restrict__ d_v, float* __restrict__ d_q) {
+  __shared__ float ge[4][kCap];
+  const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int HC = a.H * kTC, col = h * kTC + lane * 4;
+  const float scale = rsqrtf((float)kTC);
+  float* my = ge[h];
+  for (int t = blockIdx.x; t < a.T; t += gridDim.x) {
+    const int r = a.tgt_row[t];
+    if (r < 0) continue;
+    const int cnt = a.src_cnt[t];
+    const int* src = a.src_row + (long long)t * kCap;
+    const float* al = alpha + (long long)t * kCap * a.H + h;
+    const float4 g = *reinterpret_cast<const float4*>(dout + (long long)t * HC + col);
+    const float4 q = *reinterpret_cast<const float4*>(a.q + (long long)r * a.ldq + col);
+    float dot = 0.f;
+    for (int e = 1; e < cnt; ++e) {
+      const float4 ve = *reinterpret_cast<const float4*>(a.v + (long long)src[e] * a.lds + col);
+      const float p = warp_sum(fmaf(g.x, ve.x, fmaf(g.y, ve.y, fmaf(g.z, ve.z, g.w * ve.w))));
+      if (lane == 0) my[e] = p;
+      dot = fmaf(al[e * a.H], p, dot);
+    }
+    __syncwarp();
+    float4 dq = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int e = 1; e < cnt; ++e) {
+      const float w = al[e * a.H];
+      const float dl = w * (my[e] - dot) * scale;          // d loss / d <q, k_e>
+      const float4 ke = *reinterpret_cast<const float4*>(a.k + (long long)src[e] * a.lds + col);
+      float* dv = d_v + (long long)src[e] * HC + col;
+      float* dk = d_k + (long long)src[e] * HC + col;
+      atomicAdd(dv, w * g.x); atomicAdd(dv + 1, w * g.y); atomicAdd(dv + 2, w * g.z); atomicAdd(dv + 3, w * g.w);
+      atomicAdd(dk, dl * q.x); atomicAdd(dk + 1, dl * q.y); atomicAdd(dk + 2, dl * q.z); atomicAdd(dk + 3, dl * q.w);
+      dq.x = fmaf(dl, ke.x, dq.x); dq.y = fmaf(dl, ke.y, dq.y); dq.z = fmaf(dl, ke.z, dq.z); dq.w = fmaf(dl, ke.w, dq.w);
+    }
+    __syncwarp();
+    *reinterpret_cast<float4*>(d_q + (long long)r * HC + col) = dq;
+  }
+}
+
 int edge_grid(int T) {
   int g = 148 * 8;
   return T < g ? (T > 0 ? T : 1) : g;
@@ -237,6 +321,32 @@ extern "C" int mls_gatv2_edge_bwd(const float* xl, int64_t ldl, const float* xr,
   if (n_targets <= 0) return MLS_OK;
   EdgeArgs a{xl, ldl, xr, ldr, att, tgt_row, src_row, src_cnt, n_targets, heads};
   gatv2_bwd_kernel<<<edge_grid(n_targets), 32 * heads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a, alpha, dout, d_xl, d_xr, d_att_part);
+  mls_count_launch();
+  MLS_LAUNCH_CHECK();
+  return MLS_OK;
+}
+
+extern "C" int mls_transformer_edge_fwd(const float* k, const float* v, int64_t lds, const float* q, int64_t ldq, const int32_t* tgt_row,
+                                        const int32_t* src_row, const int32_t* src_cnt, int32_t n_targets, int32_t heads, float* out,
+                                        float* alpha, void* stream) {
+  MLS_CHECK_ARG(k && v && q && tgt_row && src_row && src_cnt && out && alpha, "NULL argument");
+  MLS_CHECK_ARG(heads >= 1 && heads <= 4 && lds % 4 == 0 && ldq % 4 == 0, "heads must be 1..4 and rows 16-byte aligned");
+  if (n_targets <= 0) return MLS_OK;
+  TrArgs a{k, v, lds, q, ldq, tgt_row, src_row, src_cnt, n_targets, heads};
+  transformer_fwd_kernel<<<edge_grid(n_targets), 32 * heads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a, out, alpha);
+  mls_count_launch();
+  MLS_LAUNCH_CHECK();
+  return MLS_OK;
+}
+
+extern "C" int mls_transformer_edge_bwd(const float* k, const float* v, int64_t lds, const float* q, int64_t ldq, const int32_t* tgt_row,
+                                        const int32_t* src_row, const int32_t* src_cnt, int32_t n_targets, int32_t heads,
+                                        const float* alpha, const float* dout, float* d_k, float* d_v, float* d_q, void* stream) {
+  MLS_CHECK_ARG(k && v && q && tgt_row && src_row && src_cnt && alpha && dout && d_k && d_v && d_q, "NULL argument");
+  MLS_CHECK_ARG(heads >= 1 && heads <= 4 && lds % 4 == 0 && ldq % 4 == 0, "heads must be 1..4 and rows 16-byte aligned");
+  if (n_targets <= 0) return MLS_OK;
+  TrArgs a{k, v, lds, q, ldq, tgt_row, src_row, src_cnt, n_targets, heads};
+  transformer_bwd_kernel<<<edge_grid(n_targets), 32 * heads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a, alpha, dout, d_k, d_v, d_q);
   mls_count_launch();
   MLS_LAUNCH_CHECK();
   return MLS_OK;

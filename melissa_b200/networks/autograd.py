@@ -163,6 +163,38 @@ class _GATv2Edge(torch.autograd.Function):
         return d_xl, d_xr, part.sum(dim=0).view_as(att), None, None, None
 
 
+class _TransformerEdge(torch.autograd.Function):
+    """Edge phase of TransformerConv(root_weight=False) on the same edge lists (their first entry, the node itself, is
+    skipped: no self loops): out[t] = sum_e softmax_e(<q[tgt[t]], k[src]> / sqrt(C)) v[src]."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, tgt_row, src_row, src_cnt):
+        from .. import _lib
+        L = _lib.lib()
+        q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
+        T, heads = tgt_row.numel(), q.shape[1] // 128
+        out = torch.empty(T, heads * 128, dtype=torch.float32, device=q.device)
+        alpha = torch.empty(T, src_row.shape[1], heads, dtype=torch.float32, device=q.device)
+        _lib.check(L.mls_transformer_edge_fwd(k.data_ptr(), v.data_ptr(), k.shape[1], q.data_ptr(), q.shape[1], tgt_row.data_ptr(),
+                                              src_row.data_ptr(), src_cnt.data_ptr(), T, heads, out.data_ptr(), alpha.data_ptr(),
+                                              _lib.current_stream_ptr()))
+        ctx.save_for_backward(q, k, v, tgt_row, src_row, src_cnt, alpha)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        from .. import _lib
+        L = _lib.lib()
+        q, k, v, tgt_row, src_row, src_cnt, alpha = ctx.saved_tensors
+        T, heads = tgt_row.numel(), q.shape[1] // 128
+        dout = dout.contiguous()
+        d_q, d_k, d_v = torch.zeros_like(q), torch.zeros_like(k), torch.zeros_like(v)
+        _lib.check(L.mls_transformer_edge_bwd(k.data_ptr(), v.data_ptr(), k.shape[1], q.data_ptr(), q.shape[1], tgt_row.data_ptr(),
+                                              src_row.data_ptr(), src_cnt.data_ptr(), T, heads, alpha.data_ptr(), dout.data_ptr(),
+                                              d_k.data_ptr(), d_v.data_ptr(), d_q.data_ptr(), _lib.current_stream_ptr()))
+        return d_q, d_k, d_v, None, None, None
+
+
 def train_lists(obs_rows: torch.Tensor, n_agents: int):
     """Per-sample edge lists on the device (``mls_train_lists``): slot_base [bs], s1_cnt [bs], and for the R slots (the nodes
     the controlling nodes read, sample after sample, controlling node first) tgt_row [R], src_row [R, cap], src_cnt [R];
@@ -188,9 +220,17 @@ def train_lists(obs_rows: torch.Tensor, n_agents: int):
 
 
 def q_values_l_dgn_fused(net, obs_rows: torch.Tensor) -> torch.Tensor:
-    """L-DGN Q-values with the two GATv2 edge phases (and their backward) on the CUDA kernels of ``csrc/train_gatv2.cu``;
-    same math as ``q_values`` (``l_dgn.py:92-151``), dense layers through ``F.linear``.  CUDA tensors only."""
+    """L-DGN / DGN-R Q-values with the two attention edge phases (and their backward) on the CUDA kernels of
+    ``csrc/train_gatv2.cu``; same math as ``q_values_torch`` (``l_dgn.py:92-151``, ``dgn_r.py:82-129``), dense layers through
+    ``F.linear``.  CUDA tensors only."""
     N, heads = net.agents_num, net.num_heads
+    tr = net.KIND == "dgn_r"
+
+    def conv(c, x_src, x_tgt, tgt, src, cnt):
+        if tr:
+            return _TransformerEdge.apply(c.lin_query(x_tgt), c.lin_key(x_src), c.lin_value(x_src), tgt, src, cnt)
+        return _GATv2Edge.apply(c.lin_l(x_src), c.lin_r(x_tgt), c.att.view(-1), tgt, src, cnt) + c.bias
+
     pos, feats, dm, ctrl = split_rows(obs_rows, N, net.input_dim)
     bs, dev = obs_rows.shape[0], obs_rows.device
     slot_base, s1_cnt, tgt_row, src_row, src_cnt, used = train_lists(obs_rows, N)
@@ -203,21 +243,17 @@ def q_values_l_dgn_fused(net, obs_rows: torch.Tensor) -> torch.Tensor:
     tgt_l = tgt_row.long()
     tgt_u = remap[tgt_l].long()                                                 # a slot's node is its own first source
     # conv1 at the S1 slots: sources are (used) node rows, targets the slots' own nodes
-    xl1 = net.conv1.lin_l(x0)
-    xr1 = net.conv1.lin_r(x0[tgt_u])                                            # [R, HC]
     ar_r = torch.arange(tgt_row.numel(), dtype=torch.int32, device=dev)
-    x1 = F.relu(_GATv2Edge.apply(xl1, xr1, net.conv1.att.view(-1), ar_r, remap[src_row.long()], src_cnt) + net.conv1.bias)   # [R, HC]
+    x1 = F.relu(conv(net.conv1, x0, x0[tgt_u], ar_r, remap[src_row.long()], src_cnt))                           # [R, HC]
     ctrl_slot = slot_base                                                       # slot 0 of a sample = its controlling node
     snap1 = x0[tgt_u[ctrl_slot]]
     snap2 = x1[ctrl_slot]                                                       # before the dm mask
     x1m = x1 * dm.reshape(bs * N, 1)[tgt_l]
     # conv2 at the controlling node: sources are the sample's slots (controlling node = self loop first)
-    xl2 = net.conv2.lin_l(x1m)
-    xr2 = net.conv2.lin_r(x1m[ctrl_slot])                                       # [bs, HC]
     src2 = (slot_base[:, None] + torch.arange(cap, device=dev)[None, :]).to(torch.int32)
     src2 = torch.where(torch.arange(cap, device=dev)[None, :] < s1_cnt[:, None], src2, torch.zeros_like(src2)).contiguous()
     ar_b = torch.arange(bs, dtype=torch.int32, device=dev)
-    x2 = F.relu(_GATv2Edge.apply(xl2, xr2, net.conv2.att.view(-1), ar_b, src2, s1_cnt) + net.conv2.bias)       # [bs, HC]
+    x2 = F.relu(conv(net.conv2, x1m, x1m[ctrl_slot], ar_b, src2, s1_cnt))                                      # [bs, HC]
     return _dueling(net, torch.cat([snap1, snap2, x2], dim=1))
 
 
@@ -246,7 +282,7 @@ def q_values_hl_dgn_fused(net, obs_rows: torch.Tensor) -> torch.Tensor:
 
 def fused_training_available(net, obs_rows) -> bool:
     import os
-    return (net.KIND in ("l_dgn", "hl_dgn") and obs_rows.is_cuda and net.hidden_dim == 128 and net.num_heads <= 4
+    return (net.KIND in ("l_dgn", "hl_dgn", "dgn_r") and obs_rows.is_cuda and net.hidden_dim == 128 and net.num_heads <= 4
             and os.environ.get("MLS_TRAIN_FUSED", "1") != "0")
 
 
@@ -254,7 +290,7 @@ def q_values(net, obs_rows: torch.Tensor) -> torch.Tensor:
     """Q-values [bs, 2] of agent-observation rows [bs, 8N+1] (last column = controlling index), differentiable
     with respect to ``net``'s parameters."""
     if fused_training_available(net, obs_rows):
-        return q_values_l_dgn_fused(net, obs_rows) if net.KIND == "l_dgn" else q_values_hl_dgn_fused(net, obs_rows)
+        return q_values_hl_dgn_fused(net, obs_rows) if net.KIND == "hl_dgn" else q_values_l_dgn_fused(net, obs_rows)
     return q_values_torch(net, obs_rows)
 
 
