@@ -168,7 +168,11 @@ int mls_env_reset(const MlsEnvDesc* desc, const MlsEnvState* state, const int32_
 
 /* One round for all B episodes.  If `recycle` is non-NULL an episode that ends in this round
  * is restarted in the same launch from tuple (b + n_resets*B) % count: reward/terminated/
- * done/info describe the finished round, obs/active describe the fresh episode. */
+ * done/info describe the finished round, obs/active describe the fresh episode.
+ * Host-fed draws and recycling: the forced first step of a restarted episode reads row b of move_offsets /
+ * gossip_bits / relay_bits a second time in the same launch (the reference draws fresh values there); feed draws
+ * from the host only without `recycle` (reset with mls_env_reset and its own rows) when that matters.  The device
+ * Philox movement stream gives the forced step its own counter value. */
 int mls_env_step(const MlsEnvDesc* desc, const MlsEnvState* state, const MlsRoundInputs* in,
                  const MlsRoundOutputs* out, const MlsResetTuples* recycle, void* stream);
 

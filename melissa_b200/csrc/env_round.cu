@@ -295,8 +295,10 @@ __device__ __forceinline__ int world_step(const EnvParams& p, const Smem<W>& sm,
       } else {
         // keyed by the batch-wide episode index (sub-batch views draw what the full-batch call draws)
         const uint32_t rng_row = (uint32_t)in_row + (uint32_t)((p.mode == 0 && p.d.batch_episodes > 0) ? p.d.episode_offset : 0);
+        // the forced first step of a recycled episode runs before n_resets is bumped and with num_moves == 0, the counter of
+        // the previous episode's first round: it draws under its own counter value instead
         Philox4 r = philox4x32_10(p.in.philox_seed, ((uint64_t)rng_row << 32) | (uint32_t)i,
-                                  ((uint64_t)(uint32_t)ep.n_resets << 32) | (uint32_t)ep.num_moves);
+                                  ((uint64_t)(uint32_t)ep.n_resets << 32) | (reset_step ? 0xFFFFFFFFu : (uint32_t)ep.num_moves));
         ox = kMoveStep * (-1.0 + 2.0 * u01_from_u32x2(r.v[0], r.v[1]));
         oy = kMoveStep * (-1.0 + 2.0 * u01_from_u32x2(r.v[2], r.v[3]));
       }
