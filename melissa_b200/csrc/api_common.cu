@@ -35,7 +35,8 @@ extern "C" int mls_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc
 //   "attn_mma":  1 = in discrete-feature mode run conv1's attention through the pair-logit table and the tensor-core
 //                aggregation kernel (attn_table.cu); 0 = gather kernel only
 //   "conv2_mma": 1 = conv2 attention with half2 logits + tensor-core aggregation (conv2_attn.cu); 0 = gather kernel
-//   "attn_hp":   1 = the conv1 table kernel works on (tile, head pair) items with four 48 KiB stages; 0 = (tile) items, two stages
+//   "attn_hp":   2 = conv1 table kernel fed by per-tile records of a pre-pass, row-major output (default); 1 = (tile, head pair)
+//                items built in the kernel, channel-major output staged through shared memory; 0 = (tile) items, two stages
 //   "fp32_tc":   1 = precision fp32 runs its dense layers on the tensor cores through 3-way bf16 operand splits
 //                (fp32-grade, dgn_forward.cu); 0 = SIMT sgemm
 #include <stdlib.h>
@@ -47,7 +48,7 @@ extern "C" int mls_get_option(const char* key) {
     return g_attn_mma;
   }
   if (key && !strcmp(key, "attn_hp")) {
-    if (g_attn_hp < 0) { const char* e = getenv("MLS_ATTN_HP"); g_attn_hp = e ? atoi(e) : 1; }
+    if (g_attn_hp < 0) { const char* e = getenv("MLS_ATTN_HP"); g_attn_hp = e ? atoi(e) : 2; }
     return g_attn_hp;
   }
   if (key && !strcmp(key, "fp32_tc")) {
@@ -63,7 +64,7 @@ extern "C" int mls_get_option(const char* key) {
 extern "C" int mls_set_option(const char* key, int value) {
   if (key && !strcmp(key, "conv2_mma")) { g_conv2_mma = value ? 1 : 0; return MLS_OK; }
   if (key && !strcmp(key, "fp32_tc")) { g_fp32_tc = value ? 1 : 0; return MLS_OK; }
-  if (key && !strcmp(key, "attn_hp")) { g_attn_hp = value ? 1 : 0; return MLS_OK; }
+  if (key && !strcmp(key, "attn_hp")) { g_attn_hp = value < 0 ? 0 : (value > 2 ? 2 : value); return MLS_OK; }
   if (key && !strcmp(key, "attn_mma")) { g_attn_mma = value ? 1 : 0; return MLS_OK; }
   mls_set_error("unknown option %s", key ? key : "(null)");
   return MLS_ERR_INVALID;

@@ -23,6 +23,7 @@
 #include "attn_table.cuh"
 
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "dgn_kernels.cuh"
 #include "tcgen05_ptx.cuh"
@@ -894,9 +895,402 @@ __global__ void __launch_bounds__(kT4Threads, 1) attn_table_mma4_kernel(const At
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
+// ------------------------------------------------------------------------------ per-tile records + row-major MMA kernel (option attn_hp = 2)
+// The staged kernels above spend their time in the per-item PROGRAM of a producer team (metadata loads, ballots, need
+// list, CSR walk, pair-logit reads, softmax: chains of dependent latencies run by 2-3 warps; profiles/
+// r02_conv1_experiments.txt).  Here that program runs ONCE per tile in a full-occupancy pre-pass (one warp per tile, all
+// four heads from one float4 table read) that leaves a record per tile:
+//     hdr {nn, ne, 0, 0} | x_out row of every needed target [64] | its snapshot slot [64] | compact key id of every tile row [64]
+//     | entries: (target rank << 8 | source row) [ne] | normalised softmax weights fp16 [4 heads][ne]
+// and the MMA kernel's producers only move data: three bulk copies (cp.async.bulk -> mbarrier) bring the record's fixed
+// part and the head's entry list into the stage, the value rows are gathered with cp.async by the record's key ids, and the
+// weights are scattered into the (cleared) K-major weight tile.
+//   D[target][channel] = W[target][source] (A, K-major) x V[source][channel] (B, MN-major), M = 128, N = 128 per (tile, head)
+// item; a TMEM lane is a target: an epilogue thread adds the conv bias, converts and writes 16-byte pieces of its target's
+// x1 row (and snapshot row) through a warp-private transposition tile (whole 128-byte row segments per store).  Six 24 KiB
+// stages / producer teams of 2 warps; four independent epilogue warp pairs (pair g owns head g and TMEM buffer g); a stage
+// returns to its team on tcgen05.commit.
+constexpr int kRecFixed = 16 + 64 * 4 + 64 * 4 + 64 * 2;   // 656 bytes: header, x_out rows, snapshot slots, key ids
+constexpr int kRecChunk = 512;                             // entries per in-kernel chunk
+__host__ __device__ inline int rec_entry_cap(int rows) { return (rows * (kMaxNbr + 1) + 7) & ~7; }
+__host__ __device__ inline int rec_stride(int rows) { return kRecFixed + 10 * rec_entry_cap(rows); }
+
+// One warp per tile.  Lane l owns tile rows l and l + 32.
+__global__ void __launch_bounds__(256) attn_table_prep_kernel(const AttnTableArgs a, const int G) {
+  if (*a.n_used > kAttnUcap) return;
+  __shared__ uint16_t cid_sm[8][64];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int N = a.N;
+  const int n_tiles = (a.n_graphs + G - 1) / G;
+  const int tile = blockIdx.x * 8 + warp;
+  if (tile >= n_tiles) return;
+  const int g0 = tile * G, gt = min(G, a.n_graphs - g0), rt = gt * N;
+  const size_t m0 = (size_t)g0 * N;
+  const int self = a.transformer ? 0 : 1;
+  unsigned char* rec = a.rec + (size_t)tile * rec_stride(G * N);
+  const int cap = rec_entry_cap(G * N);
+  uint16_t* cid_s = cid_sm[warp];
+  int xr[2], sl[2], cnt[2], p0[2], gl[2];
+  uint16_t cv[2];
+  const uint8_t* srcp[2];
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const int r = lane + 32 * q;
+    xr[q] = -1; sl[q] = -1; cnt[q] = 0; cv[q] = 0; p0[q] = 0; gl[q] = 0; srcp[q] = nullptr;
+    if (r < rt) {
+      cv[q] = __ldg(a.row_cid + m0 + r);
+      xr[q] = a.xrow ? __ldg(a.xrow + m0 + r) : (int)m0 + r;
+      if (a.slot) sl[q] = __ldg(a.slot + m0 + r);
+      gl[q] = r / N;
+      const int il = r - gl[q] * N;
+      const size_t cg = a.graph_id ? (size_t)__ldg(a.graph_id + (size_t)(g0 + gl[q]) * a.gid_stride) : (size_t)(g0 + gl[q]);
+      p0[q] = __ldg(a.csr_ptr + cg * (N + 1) + il);
+      const int d = (int)__ldg(a.csr_ptr + cg * (N + 1) + il + 1) - p0[q];
+      srcp[q] = a.csr_src + cg * N * kMaxNbr + p0[q];
+      if (xr[q] >= 0) cnt[q] = d + self;
+    }
+    cid_s[r] = cv[q];
+  }
+  __syncwarp();
+  const uint32_t lt = (1u << lane) - 1u;
+  const uint32_t b0 = __ballot_sync(0xffffffffu, xr[0] >= 0), b1 = __ballot_sync(0xffffffffu, xr[1] >= 0);
+  const int n0 = __popc(b0), nn = n0 + __popc(b1);
+  const int rank[2] = {__popc(b0 & lt), n0 + __popc(b1 & lt)};
+  // entry offsets in rank order: rows 0..31 first, then 32..63 (ranks are assigned the same way)
+  int inc0 = cnt[0], inc1 = cnt[1];
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v0 = __shfl_up_sync(0xffffffffu, inc0, o), v1 = __shfl_up_sync(0xffffffffu, inc1, o);
+    if (lane >= o) { inc0 += v0; inc1 += v1; }
+  }
+  const int tot0 = __shfl_sync(0xffffffffu, inc0, 31), ne = tot0 + __shfl_sync(0xffffffffu, inc1, 31);
+  const int off[2] = {inc0 - cnt[0], tot0 + inc1 - cnt[1]};
+  const int ne_pad = (ne + 7) & ~7;
+  if (lane == 0) {
+    *reinterpret_cast<int4*>(rec) = make_int4(nn, ne, 0, 0);
+    a.tile_idx[tile] = make_int2(ne_pad, nn);
+  }
+  int* tab_x = reinterpret_cast<int*>(rec + 16);
+  int* tab_s = tab_x + 64;
+  uint16_t* cid_g = reinterpret_cast<uint16_t*>(rec + 16 + 512);
+  uint16_t* jr = reinterpret_cast<uint16_t*>(rec + kRecFixed);
+  __half* wts = reinterpret_cast<__half*>(rec + kRecFixed + 2 * cap);          // [4][cap]
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const int r = lane + 32 * q;
+    cid_g[r] = cv[q];
+    if (xr[q] >= 0) { tab_x[rank[q]] = xr[q]; tab_s[rank[q]] = sl[q]; }
+  }
+  // padding entries (read by the 16-byte granular copies, never scattered): keep them defined
+  if (lane < ne_pad - ne) {
+    jr[ne + lane] = 0;
+    for (int h = 0; h < 4; ++h) wts[(size_t)h * cap + ne + lane] = __float2half_rn(0.f);
+  }
+#pragma unroll 1
+  for (int q = 0; q < 2; ++q) {
+    const int c = cnt[q];
+    if (c == 0) continue;
+    const int r = lane + 32 * q, rbase = gl[q] * N;
+    const float4* Erow = reinterpret_cast<const float4*>(a.E) + (size_t)cv[q] * kAttnUcap;
+    const uint8_t* src = srcp[q];
+    uint16_t* jo = jr + off[q];
+    __half* wo = wts + off[q];
+    const int rk = rank[q] << 8;
+    if (c <= 8) {
+      float4 e[8];
+      int jv[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        jv[k] = (k < c && k >= self) ? rbase + src[k - self] : r;
+        e[k] = __ldg(Erow + cid_s[jv[k]]);
+      }
+      float4 mx = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (k < c) { mx.x = fmaxf(mx.x, e[k].x); mx.y = fmaxf(mx.y, e[k].y); mx.z = fmaxf(mx.z, e[k].z); mx.w = fmaxf(mx.w, e[k].w); }
+      float4 sm = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (k < c) {
+          e[k].x = f_ex2(e[k].x - mx.x); e[k].y = f_ex2(e[k].y - mx.y); e[k].z = f_ex2(e[k].z - mx.z); e[k].w = f_ex2(e[k].w - mx.w);
+          sm.x += e[k].x; sm.y += e[k].y; sm.z += e[k].z; sm.w += e[k].w;
+        }
+      const float4 inv = make_float4(f_rcp(sm.x + 1e-16f), f_rcp(sm.y + 1e-16f), f_rcp(sm.z + 1e-16f), f_rcp(sm.w + 1e-16f));
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (k < c) {
+          jo[k] = (uint16_t)(rk | jv[k]);
+          wo[k] = __float2half_rn(e[k].x * inv.x); wo[cap + k] = __float2half_rn(e[k].y * inv.y);
+          wo[2 * cap + k] = __float2half_rn(e[k].z * inv.z); wo[3 * cap + k] = __float2half_rn(e[k].w * inv.w);
+        }
+    } else {
+      float4 mx = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+      for (int k = 0; k < c; ++k) {
+        const int j = k >= self ? rbase + src[k - self] : r;
+        const float4 v = __ldg(Erow + cid_s[j]);
+        mx.x = fmaxf(mx.x, v.x); mx.y = fmaxf(mx.y, v.y); mx.z = fmaxf(mx.z, v.z); mx.w = fmaxf(mx.w, v.w);
+      }
+      float4 sm = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int k = 0; k < c; ++k) {
+        const int j = k >= self ? rbase + src[k - self] : r;
+        const float4 v = __ldg(Erow + cid_s[j]);
+        sm.x += f_ex2(v.x - mx.x); sm.y += f_ex2(v.y - mx.y); sm.z += f_ex2(v.z - mx.z); sm.w += f_ex2(v.w - mx.w);
+      }
+      const float4 inv = make_float4(f_rcp(sm.x + 1e-16f), f_rcp(sm.y + 1e-16f), f_rcp(sm.z + 1e-16f), f_rcp(sm.w + 1e-16f));
+      for (int k = 0; k < c; ++k) {
+        const int j = k >= self ? rbase + src[k - self] : r;
+        const float4 v = __ldg(Erow + cid_s[j]);
+        jo[k] = (uint16_t)(rk | j);
+        wo[k] = __float2half_rn(f_ex2(v.x - mx.x) * inv.x); wo[cap + k] = __float2half_rn(f_ex2(v.y - mx.y) * inv.y);
+        wo[2 * cap + k] = __float2half_rn(f_ex2(v.z - mx.z) * inv.z); wo[3 * cap + k] = __float2half_rn(f_ex2(v.w - mx.w) * inv.w);
+      }
+    }
+  }
+}
+
+constexpr int kT6Threads = 704;
+constexpr int kTeam6 = 64;
+constexpr int kNumSt6 = 6;
+constexpr int kStage1 = kAHead + 2 * kBPanel;  // 24 KiB
+constexpr int kMetaFix = 768;                  // record fixed part (656) rounded up
+constexpr int kMeta8 = kMetaFix + 4 * kRecChunk;   // + one chunk of entries (2 B each) and of weights (2 B each)
+constexpr int kEpiRow = 144;                   // epilogue staging row: 64 bf16 + 16 B pad (conflict-free 16-byte accesses)
+constexpr int kEpiTile = 32 * kEpiRow;         // one warp's transposition tile
+constexpr int kT6Smem = kNumSt6 * kStage1 + kNumSt6 * kMeta8 + 8 * kEpiTile + 512 * 4 /*bias*/ + 512 /*barriers*/ + 1024;
+
+__device__ __forceinline__ void bar_team6(int team) { asm volatile("bar.sync %0, 64;" ::"r"(team + 1) : "memory"); }
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+// relu(v[0..7] + bias[0..7]) as 8 bf16
+__device__ __forceinline__ uint4 bias_relu_pack8(const uint32_t* v, const float* bias) {
+  const float4 b0 = *reinterpret_cast<const float4*>(bias), b1 = *reinterpret_cast<const float4*>(bias + 4);
+  uint4 o;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(o.x) : "f"(__uint_as_float(v[1]) + b0.y), "f"(__uint_as_float(v[0]) + b0.x));
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(o.y) : "f"(__uint_as_float(v[3]) + b0.w), "f"(__uint_as_float(v[2]) + b0.z));
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(o.z) : "f"(__uint_as_float(v[5]) + b1.y), "f"(__uint_as_float(v[4]) + b1.x));
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(o.w) : "f"(__uint_as_float(v[7]) + b1.w), "f"(__uint_as_float(v[6]) + b1.z));
+  return o;
+}
+
+__global__ void __launch_bounds__(kT6Threads, 1) attn_table_rows_kernel(const AttnTableArgs a, const int G) {
+  if (*a.n_used > kAttnUcap) return;            // uniform: the gather kernel handles this pass
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  unsigned char* meta = smem + kNumSt6 * kStage1;                                 // [6][kMeta8]
+  unsigned char* epi_tiles = meta + kNumSt6 * kMeta8;                             // [8][kEpiTile]
+  float* bias_s = reinterpret_cast<float*>(epi_tiles + 8 * kEpiTile);             // [512]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + 512);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 40);
+  const uint32_t bar0 = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (8 + s); };
+  auto meta_bar = [&](int s) { return bar0 + 8u * (16 + s); };
+  auto tfull_bar = [&](int b) { return bar0 + 8u * (24 + b); };
+  auto tempty_bar = [&](int b) { return bar0 + 8u * (28 + b); };
+
+  const int N = a.N, HC = 4 * kC;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tiles = (a.n_graphs + G - 1) / G;
+  const int my_tiles = blockIdx.x < n_tiles ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const int n_items = 4 * my_tiles;              // item k: tile blockIdx.x + (k >> 2) * gridDim.x, head k & 3, stage k % 6
+  const int ksteps = (G * N + 15) >> 4;          // value rows behind the tile's nodes stay zero
+  const int stride = rec_stride(G * N), cap = rec_entry_cap(G * N);
+
+  for (int u = threadIdx.x; u < kNumSt6 * kStage1 / 16; u += kT6Threads) reinterpret_cast<uint4*>(smem)[u] = make_uint4(0, 0, 0, 0);
+  for (int u = threadIdx.x; u < 512; u += kT6Threads) bias_s[u] = a.bias ? a.bias[u] : 0.f;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kNumSt6; ++s) { mbar_init(full_bar(s), kTeam6); mbar_init(empty_bar(s), 1 + 2); mbar_init(meta_bar(s), 1); }
+    for (int b = 0; b < 4; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 2 * 32); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const bool is_epi = warp >= 4 && warp < 18 && (warp & 3) < 2;
+  const bool is_prod = warp >= 2 && !is_epi;
+  if (warp == 0) {
+    // ===================================================================== MMA issuer
+    if (lane == 0) {
+      // fp16 x fp16 (format fields cleared), B (values) MN-major (bit 16)
+      const uint32_t idesc = (make_idesc(128, 128) & ~((7u << 7) | (7u << 10))) | (1u << 16);
+      int s = 0;
+      uint32_t sph = 0;
+      for (int k = 0; k < n_items; ++k) {
+        const int b = k & 3;
+        const uint32_t sA = smem_u32(smem + s * kStage1), sB = sA + kAHead;
+        mbar_wait_guard(full_bar(s), sph, 0);
+        mbar_wait_guard(tempty_bar(b), ((k >> 2) & 1) ^ 1, 0);
+        tc_fence_after();
+        // A = weight rows [target][source]; the descriptor spans 128 rows, the tile holds 64: rows 64.. are whatever
+        // follows in the stage (finite fp16) and only reach TMEM lanes 64.. , which nobody reads
+        const uint64_t dw = make_smem_desc(sA);
+        const uint64_t dv = make_smem_desc_ex(sB, kBPanel >> 4, 1024 >> 4);
+        for (int ks = 0; ks < ksteps; ++ks)
+          umma_bf16(tmem_base + (uint32_t)(b * 128), dw + (uint64_t)(ks * 2), dv + (uint64_t)(ks * 128), idesc, ks ? 1u : 0u);
+        umma_commit(empty_bar(s));                                              // operands read: the stage goes back to its team
+        umma_commit(tfull_bar(b));
+        if (++s == kNumSt6) { s = 0; sph ^= 1u; }
+      }
+    }
+  } else if (is_epi) {
+    // ===================================================================== epilogue: lane = target, registers = channels
+    // Tiles with at most 32 needed targets (the rule at N = 50) carry every weight row twice, at rows t and t + 32: the
+    // lane quarters 0 and 1 hold the same targets and split the head's 128 channels; larger tiles: quarter = targets
+    // 32 qq .., all 128 channels.  64 channels at a time go through the warp's private transposition tile so that a store
+    // instruction writes whole 128-byte row segments (per-lane 16-byte pieces of 32 different rows are one L2 request
+    // each: 0.39 ms of this kernel).
+    const int qq = warp & 3, b = (warp >> 2) - 1;                              // b == head == accumulator buffer
+    unsigned char* tile_s = epi_tiles + (b * 2 + qq) * kEpiTile;
+    const int srow = lane >> 3, schunk = lane & 7;                             // store phase: 4 rows x 8 chunks per instruction
+    int s = b % kNumSt6;
+    for (int k = b; k < n_items; k += 4) {
+      mbar_wait_guard(tfull_bar(b), (k >> 2) & 1, 20);
+      tc_fence_after();
+      const int4 hdr = *reinterpret_cast<const int4*>(meta + s * kMeta8);      // {nn, ne, 0, 0}
+      const int* tab_x = reinterpret_cast<const int*>(meta + s * kMeta8 + 16);
+      const int* tab_s = tab_x + 64;
+      const int nn = hdr.x;
+      const bool rep = nn <= 32;
+      const int t0 = rep ? 0 : qq * 32;                                        // first target of this warp's TMEM lanes
+      const int nv = min(32, nn - t0);                                         // targets among them
+      int xr = 0, sl = -1;
+      if (lane < nv) { xr = tab_x[t0 + lane]; sl = tab_s[t0 + lane]; }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty_bar(s));                                // this warp is done with the stage's record
+      s += 4; if (s >= kNumSt6) s -= kNumSt6;
+      const int c0 = rep ? qq * 64 : 0, nhalf = rep ? 1 : 2;                   // this warp's channels of the head: [c0, c0 + 64 nhalf)
+      const uint32_t tcol = tmem_base + ((uint32_t)(qq * 32) << 16) + (uint32_t)(b * 128 + c0);
+      for (int hf = 0; hf < nhalf; ++hf) {
+        if (nv > 0) {
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t v[32];
+            tmem_ld32(tcol + (uint32_t)(hf * 64 + c * 32), v);
+            const float* bp = bias_s + b * kC + c0 + hf * 64 + c * 32;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              *reinterpret_cast<uint4*>(tile_s + lane * kEpiRow + c * 64 + q * 16) = bias_relu_pack8(v + 8 * q, bp + 8 * q);
+          }
+        }
+        if (hf == nhalf - 1) { tc_fence_before(); mbar_arrive(tempty_bar(b)); }   // accumulator drained
+        __syncwarp();
+        const int colb = (b * kC + c0 + hf * 64) * 2 + schunk * 16;            // byte offset inside an x1 row
+        for (int r0 = 0; r0 < nv; r0 += 4) {
+          const int r = r0 + srow;
+          const int xr_r = __shfl_sync(0xffffffffu, xr, r & 31), sl_r = __shfl_sync(0xffffffffu, sl, r & 31);
+          if (r < nv) {
+            const uint4 val = *reinterpret_cast<const uint4*>(tile_s + r * kEpiRow + schunk * 16);
+            *reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(a.x_out) + (size_t)xr_r * (HC * 2) + colb) = val;
+            if (sl_r >= 0)
+              *reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(a.z) + ((size_t)sl_r * a.ldz + a.z_col) * 2 + colb) = val;
+          }
+        }
+        __syncwarp();
+      }
+    }
+  } else if (is_prod) {
+    // ===================================================================== producer teams: data movement only
+    const int p = warp >= 20 ? warp - 10 : ((warp - 2) >> 2) * 2 + ((warp - 2) & 1);   // 0..11
+    const int team = p >> 1, pt = (p & 1) * 32 + lane;                         // 0..63
+    unsigned char* sA = smem + team * kStage1;
+    const uint32_t sB32 = smem_u32(sA + kAHead);
+    unsigned char* mt = meta + team * kMeta8;
+    const uint16_t* cid = reinterpret_cast<const uint16_t*>(mt + 16 + 512);     // [64] compact key id of every tile row
+    const uint16_t* jr_s = reinterpret_cast<const uint16_t*>(mt + kMetaFix);    // [kRecChunk]
+    const __half* w_s = reinterpret_cast<const __half*>(mt + kMetaFix + 2 * kRecChunk);
+    const uint32_t mt32 = smem_u32(mt), mbar = meta_bar(team);
+    const int gp = pt & 3;
+    auto load_idx = [&](int k) -> int2 {
+      if (k >= n_items) return make_int2(0, 0);
+      return __ldg(a.tile_idx + blockIdx.x + (k >> 2) * gridDim.x);
+    };
+    int2 ix = load_idx(team);
+    uint32_t mph = 0;
+    int use = 0;
+    for (int k = team; k < n_items; k += kNumSt6, ++use) {
+      const int tile = blockIdx.x + (k >> 2) * gridDim.x, h = k & 3;
+      const int g0 = tile * G, gt = min(G, a.n_graphs - g0), rt = gt * N;
+      const int ne_pad = ix.x, nn = ix.y;
+      ix = load_idx(k + kNumSt6);                                               // next item's sizes: in flight during this one
+      const bool rep = nn <= 32;
+      const unsigned char* rec = a.rec + (size_t)tile * stride;
+      const unsigned char* gsrc = reinterpret_cast<const unsigned char*>(a.Vh) + h * (kC * 2) + gp * 16;   // this head's quarter of a value row
+      mbar_wait_guard(empty_bar(team), (use & 1) ^ 1, 40);                     // MMAs and epilogue are done with this stage
+      int c0 = 0, cn = ne_pad < kRecChunk ? ne_pad : kRecChunk;                 // first chunk of entries
+      if (pt == 0) {
+        mbar_expect_tx(mbar, (uint32_t)(kRecFixed + 4 * cn));
+        bulk_g2s(mt32, rec, kRecFixed, mbar);
+        if (cn > 0) {
+          bulk_g2s(mt32 + kMetaFix, rec + kRecFixed, 2 * cn, mbar);
+          bulk_g2s(mt32 + kMetaFix + 2 * kRecChunk, rec + kRecFixed + 2 * (size_t)cap * (1 + h), 2 * cn, mbar);
+        }
+      }
+      // weight rows of the needed targets, cleared (rows behind them keep stale finite data: their TMEM lanes are not read)
+      for (int u = pt; u < nn * 8; u += kTeam6) {
+        reinterpret_cast<uint4*>(sA)[u] = make_uint4(0, 0, 0, 0);
+        if (rep) reinterpret_cast<uint4*>(sA + 32 * 128)[u] = make_uint4(0, 0, 0, 0);
+      }
+      mbar_wait_guard(mbar, mph, 20);                                           // the record is here
+      mph ^= 1u;
+      // this head's quarter (256 B) of the value rows of the tile's nodes, asynchronously
+      for (int j = pt >> 2; j < rt; j += kTeam6 / 4) {
+        const unsigned char* src = gsrc + (size_t)cid[j] * (HC * 2);
+        const uint32_t row = sB32 + j * 128;
+        const uint32_t d0 = row + ((gp ^ (j & 7)) << 4), d1 = row + (((gp + 4) ^ (j & 7)) << 4);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) cp_async16(((i & 1) ? d1 : d0) + (i >> 1) * kBPanel, src + i * 64);
+      }
+      bar_team6(team);                                                         // weight rows cleared by everybody
+      const int rep_off = rep ? 32 * 128 : 0;
+      const int ne = reinterpret_cast<const int*>(mt)[1];                       // real entries (the copies are 16-byte granular)
+      for (;;) {
+        const int ce = min(cn, ne - c0);
+        for (int e = pt; e < ce; e += kTeam6) {
+          const uint32_t ent = jr_s[e];
+          unsigned char* cell = sA + a_off((int)(ent >> 8), (int)(ent & 255u));
+          const __half w = w_s[e];
+          *reinterpret_cast<__half*>(cell) = w;
+          *reinterpret_cast<__half*>(cell + rep_off) = w;
+        }
+        c0 += cn;
+        if (c0 >= ne_pad) break;
+        bar_team6(team);                                                       // everybody has read this chunk
+        cn = ne_pad - c0 < kRecChunk ? ne_pad - c0 : kRecChunk;
+        if (pt == 0) {
+          mbar_expect_tx(mbar, (uint32_t)(4 * cn));
+          bulk_g2s(mt32 + kMetaFix, rec + kRecFixed + 2 * (size_t)c0, 2 * cn, mbar);
+          bulk_g2s(mt32 + kMetaFix + 2 * kRecChunk, rec + kRecFixed + 2 * (size_t)cap * (1 + h) + 2 * (size_t)c0, 2 * cn, mbar);
+        }
+        mbar_wait_guard(mbar, mph, 20);
+        mph ^= 1u;
+      }
+      cp_async_wait_all();
+      fence_proxy_async();
+      mbar_arrive(full_bar(team));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
 }  // namespace
 
-int attn_table_conv_launch(const AttnTableArgs& a, int sm_count, cudaStream_t st) {
+size_t attn_table_record_bytes(int N, int n_graphs) {
+  const int G = kAttnMaxRows / N;
+  const size_t n_tiles = ((size_t)n_graphs + G - 1) / G;
+  return n_tiles * (size_t)rec_stride(G * N);
+}
+
+int attn_table_conv_launch(const AttnTableArgs& a_in, int sm_count, cudaStream_t st) {
+  AttnTableArgs a = a_in;
+  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("MLS_ATTN_DBG"); dbg = e ? atoi(e) : 0; } a.dbg = dbg; }
   if (!attn_table_supported(a.N, a.H)) {
     mls_set_error("table-mode attention: unsupported shape (N=%d, H=%d)", a.N, a.H);
     return MLS_ERR_UNSUPPORTED;
@@ -909,6 +1303,7 @@ int attn_table_conv_launch(const AttnTableArgs& a, int sm_count, cudaStream_t st
   if (!configured) {
     MLS_CUDA(cudaFuncSetAttribute(attn_table_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTSmem));
     MLS_CUDA(cudaFuncSetAttribute(attn_table_mma4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kT4Smem));
+    MLS_CUDA(cudaFuncSetAttribute(attn_table_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kT6Smem));
     configured = true;
   }
   compact_keys_kernel<<<1, 1024, 0, st>>>(a.used_bits, a.n_keys, a.cid_of_key, a.key_of_cid, a.n_used);
@@ -920,8 +1315,16 @@ int attn_table_conv_launch(const AttnTableArgs& a, int sm_count, cudaStream_t st
   const int n_tiles = (a.n_graphs + G - 1) / G;
   const int grid = n_tiles < sm_count ? n_tiles : sm_count;
   if (grid > 0) {
-    if (mls_get_option("attn_hp")) attn_table_mma4_kernel<<<grid, kT4Threads, kT4Smem, st>>>(a, G);    // head-pair stages (default)
-    else attn_table_mma_kernel<<<grid, kTThreads, kTSmem, st>>>(a, G);
+    const int mode = mls_get_option("attn_hp");
+    if (mode >= 2 && a.pool_mode < 0 && a.rec && a.tile_idx) {                 // per-tile records + row-major MMA (default)
+      attn_table_prep_kernel<<<(n_tiles + 7) / 8, 256, 0, st>>>(a, G);
+      attn_table_rows_kernel<<<grid, kT6Threads, kT6Smem, st>>>(a, G);
+      mls_count_launch();
+    } else if (mode) {
+      attn_table_mma4_kernel<<<grid, kT4Threads, kT4Smem, st>>>(a, G);        // head-pair stages, channel-major (pooling)
+    } else {
+      attn_table_mma_kernel<<<grid, kTThreads, kTSmem, st>>>(a, G);
+    }
   }
   mls_count_launch(5);
   MLS_LAUNCH_CHECK();

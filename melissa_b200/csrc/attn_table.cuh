@@ -48,6 +48,11 @@ struct AttnTableArgs {
   int* n_used;               // [1] number of distinct keys; > kAttnUcap: the caller's gather kernel runs instead
   void* Vh;                  // [kAttnUcap][H*C] fp16 value rows of the present keys (by compact id)
   float* E;                  // [kAttnUcap][kAttnUcap][4] base-2 logits of (target key, source key) for the 4 heads
+  // optional (x_out / snapshot variant): per-tile records written by the pre-pass, attn_table_record_bytes() bytes, and
+  // {padded entry count, needed targets} of every tile; NULL: the staged kernel builds everything per item
+  unsigned char* rec;
+  int2* tile_idx;            // [tiles]
+  int dbg;
 };
 
 // scratch bytes behind `E`
@@ -56,6 +61,8 @@ inline size_t attn_table_value_bytes() { return (size_t)kAttnUcap * 512 * 2; }
 // true when this (N, H) can take the tensor-core path at all
 inline bool attn_table_supported(int N, int H) { return N >= 1 && N <= kAttnMaxRows && H == 4; }
 
+// bytes behind `rec` for a pass of n_graphs graphs of N nodes
+size_t attn_table_record_bytes(int N, int n_graphs);
 int attn_table_conv_launch(const AttnTableArgs& a, int sm_count, cudaStream_t st);
 
 }  // namespace mls

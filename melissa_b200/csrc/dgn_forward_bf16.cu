@@ -835,6 +835,8 @@ struct WsB {
   uint16_t* row_cid;          // [R]
   float* pairE;               // [kAttnUcap][kAttnUcap][4]
   void* Vh;                   // [kAttnUcap][512] fp16
+  unsigned char* rec;         // per-tile records of the conv1 pre-pass (attn_table_record_bytes)
+  int2* tile_idx;             // [tiles]
 };
 
 size_t carve_b(const MlsNetDesc* d, int Gc, unsigned char* base, WsB* ws) {
@@ -873,6 +875,7 @@ size_t carve_b(const MlsNetDesc* d, int Gc, unsigned char* base, WsB* ws) {
   const bool mma_ok = attn_table_supported(d->n_nodes, d->heads);
   const size_t o_used = take(KT), o_cok = take(KT * 2), o_koc = take(kAttnUcap * 4), o_nu = take(4);
   const size_t o_pe = take(mma_ok ? attn_table_pair_bytes() : 0), o_rcid = take(R * 2), o_vh = take(mma_ok ? attn_table_value_bytes() : 0);
+  const size_t o_rec = take(mma_ok && !hl ? attn_table_record_bytes(d->n_nodes, Gc) : 0), o_tix = take(mma_ok && !hl ? ((size_t)Gc + 1) * 8 : 0);
   if (ws) {
     auto B = [&](size_t o) { return reinterpret_cast<bf16*>(base + o); };
     auto F = [&](size_t o) { return reinterpret_cast<float*>(base + o); };
@@ -893,6 +896,7 @@ size_t carve_b(const MlsNetDesc* d, int Gc, unsigned char* base, WsB* ws) {
     ws->used = reinterpret_cast<uint32_t*>(base + o_used); ws->cid_of_key = reinterpret_cast<uint16_t*>(base + o_cok);
     ws->key_of_cid = reinterpret_cast<uint32_t*>(base + o_koc); ws->n_used = reinterpret_cast<int*>(base + o_nu);
     ws->pairE = F(o_pe); ws->row_cid = reinterpret_cast<uint16_t*>(base + o_rcid); ws->Vh = base + o_vh;
+    ws->rec = (mma_ok && !hl) ? base + o_rec : nullptr; ws->tile_idx = (mma_ok && !hl) ? reinterpret_cast<int2*>(base + o_tix) : nullptr;
   }
   return off;
 }
@@ -1186,6 +1190,7 @@ int dgn_forward_bf16(const MlsNetDesc* d, const MlsNetWeights* w, const MlsForwa
         if (hl) { ta.slot = nullptr; ta.xrow = nullptr; ta.x_out = nullptr; ta.z_col = 0; ta.pool_mode = d->pool; ta.obs = obs; ta.obs_stride = a->obs_stride; }
         ta.used_bits = ws.used; ta.n_keys = n_keys; ta.cid_of_key = ws.cid_of_key; ta.key_of_cid = ws.key_of_cid;
         ta.n_used = ws.n_used; ta.E = ws.pairE; ta.row_cid = ws.row_cid; ta.Vh = ws.Vh;
+        ta.rec = ws.rec; ta.tile_idx = ws.tile_idx;
         if ((rc = attn_table_conv_launch(ta, sms, st))) return rc;
         ea.run_if_gt = ws.n_used; ea.run_thresh = kAttnUcap;      // more distinct keys than the table holds: gather kernel
       }
