@@ -23,7 +23,6 @@
 #include "attn_table.cuh"
 
 #include <cuda_fp16.h>
-#include <stdlib.h>
 
 #include "dgn_kernels.cuh"
 #include "tcgen05_ptx.cuh"
@@ -916,7 +915,7 @@ __host__ __device__ inline int rec_entry_cap(int rows) { return (rows * (kMaxNbr
 __host__ __device__ inline int rec_stride(int rows) { return kRecFixed + 10 * rec_entry_cap(rows); }
 
 // One warp per tile.  Lane l owns tile rows l and l + 32.
-__global__ void __launch_bounds__(256) attn_table_prep_kernel(const AttnTableArgs a, const int G) {
+__global__ void __launch_bounds__(256, 4) attn_table_prep_kernel(const AttnTableArgs a, const int G) {
   if (*a.n_used > kAttnUcap) return;
   __shared__ uint16_t cid_sm[8][64];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1288,9 +1287,7 @@ size_t attn_table_record_bytes(int N, int n_graphs) {
   return n_tiles * (size_t)rec_stride(G * N);
 }
 
-int attn_table_conv_launch(const AttnTableArgs& a_in, int sm_count, cudaStream_t st) {
-  AttnTableArgs a = a_in;
-  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("MLS_ATTN_DBG"); dbg = e ? atoi(e) : 0; } a.dbg = dbg; }
+int attn_table_conv_launch(const AttnTableArgs& a, int sm_count, cudaStream_t st) {
   if (!attn_table_supported(a.N, a.H)) {
     mls_set_error("table-mode attention: unsupported shape (N=%d, H=%d)", a.N, a.H);
     return MLS_ERR_UNSUPPORTED;

@@ -52,7 +52,6 @@ struct AttnTableArgs {
   // {padded entry count, needed targets} of every tile; NULL: the staged kernel builds everything per item
   unsigned char* rec;
   int2* tile_idx;            // [tiles]
-  int dbg;
 };
 
 // scratch bytes behind `E`
