@@ -450,7 +450,7 @@ def run_ours(args):
                                 "edge2", "largest single-kernel share of the step")
             if prof_ms_conv1:
                 c1_ms = float(np.mean(prof_ms_conv1))
-                name = ("attn_table_mma_kernel + key compaction + pair-logit table (conv1 attention on tcgen05"
+                name = ("key compaction + pair-logit table + attn_table_prep_kernel (per-tile records) + attn_table_rows_kernel (conv1 attention on tcgen05"
                         if N <= 62 else "edge_bf16_kernel (conv1 attention, gather from the feature table")
                 roof_conv1 = hbm_line(f"{name}, {chunk_graphs} graphs, {int(need_rows)} output rows)", c1_ms, conv1_bytes(), "edge1",
                                       "event pair spans the whole conv1 attention stage")

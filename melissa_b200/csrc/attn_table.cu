@@ -1062,6 +1062,14 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+__device__ __forceinline__ uint4 relu_pack8(const uint32_t* v) {
+  uint4 o;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(o.x) : "f"(__uint_as_float(v[1])), "f"(__uint_as_float(v[0])));
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(o.y) : "f"(__uint_as_float(v[3])), "f"(__uint_as_float(v[2])));
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(o.z) : "f"(__uint_as_float(v[5])), "f"(__uint_as_float(v[4])));
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(o.w) : "f"(__uint_as_float(v[7])), "f"(__uint_as_float(v[6])));
+  return o;
+}
 // relu(v[0..7] + bias[0..7]) as 8 bf16
 __device__ __forceinline__ uint4 bias_relu_pack8(const uint32_t* v, const float* bias) {
   const float4 b0 = *reinterpret_cast<const float4*>(bias), b1 = *reinterpret_cast<const float4*>(bias + 4);
@@ -1094,11 +1102,27 @@ __global__ void __launch_bounds__(kT6Threads, 1) attn_table_rows_kernel(const At
   const int n_tiles = (a.n_graphs + G - 1) / G;
   const int my_tiles = blockIdx.x < n_tiles ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   const int n_items = 4 * my_tiles;              // item k: tile blockIdx.x + (k >> 2) * gridDim.x, head k & 3, stage k % 6
-  const int ksteps = (G * N + 15) >> 4;          // value rows behind the tile's nodes stay zero
+  const int ksteps = (G * N + 8 <= 64) ? 4 : ((G * N + 15) >> 4);   // value rows behind the tile's nodes: bias rows or zero
   const int stride = rec_stride(G * N), cap = rec_entry_cap(G * N);
 
   for (int u = threadIdx.x; u < kNumSt6 * kStage1 / 16; u += kT6Threads) reinterpret_cast<uint4*>(smem)[u] = make_uint4(0, 0, 0, 0);
-  for (int u = threadIdx.x; u < 512; u += kT6Threads) bias_s[u] = a.bias ? a.bias[u] : 0.f;
+  // conv bias: as 8 extra value rows (fp16 hi + lo for each of the 4 heads, rows kb + 2h, kb + 2h + 1 of every stage; the
+  // weight rows of head h carry ones in those two columns) when the tile leaves room for them, else added in the epilogue
+  const int kb = G * N;
+  const bool bias_mma = kb + 8 <= 64;
+  for (int u = threadIdx.x; u < 512; u += kT6Threads) bias_s[u] = (a.bias && !bias_mma) ? a.bias[u] : 0.f;
+  __syncthreads();
+  if (bias_mma) {
+    for (int u = threadIdx.x; u < kNumSt6 * 512; u += kT6Threads) {
+      const int st = u >> 9, hh = (u >> 7) & 3, ch = u & 127;                 // head hh's bias for channel ch -> rows kb + 2 hh (+1)
+      const float bv = a.bias ? a.bias[hh * kC + ch] : 0.f;
+      const __half hi = __float2half_rn(bv), lo = __float2half_rn(bv - __half2float(hi));
+      unsigned char* panel = smem + st * kStage1 + kAHead + (ch >> 6) * kBPanel;
+      const int e = ch & 63, r0 = kb + 2 * hh;
+      *reinterpret_cast<__half*>(panel + r0 * 128 + ((((e >> 3) ^ r0) & 7) << 4) + (e & 7) * 2) = hi;
+      *reinterpret_cast<__half*>(panel + (r0 + 1) * 128 + ((((e >> 3) ^ (r0 + 1)) & 7) << 4) + (e & 7) * 2) = lo;
+    }
+  }
   if (threadIdx.x == 0) {
     for (int s = 0; s < kNumSt6; ++s) { mbar_init(full_bar(s), kTeam6); mbar_init(empty_bar(s), 1 + 2); mbar_init(meta_bar(s), 1); }
     for (int b = 0; b < 4; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 2 * 32); }
@@ -1172,9 +1196,14 @@ __global__ void __launch_bounds__(kT6Threads, 1) attn_table_rows_kernel(const At
             uint32_t v[32];
             tmem_ld32(tcol + (uint32_t)(hf * 64 + c * 32), v);
             const float* bp = bias_s + b * kC + c0 + hf * 64 + c * 32;
+            if (bias_mma) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-              *reinterpret_cast<uint4*>(tile_s + lane * kEpiRow + c * 64 + q * 16) = bias_relu_pack8(v + 8 * q, bp + 8 * q);
+              for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(tile_s + lane * kEpiRow + c * 64 + q * 16) = relu_pack8(v + 8 * q);
+            } else {
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                *reinterpret_cast<uint4*>(tile_s + lane * kEpiRow + c * 64 + q * 16) = bias_relu_pack8(v + 8 * q, bp + 8 * q);
+            }
           }
         }
         if (hf == nhalf - 1) { tc_fence_before(); mbar_arrive(tempty_bar(b)); }   // accumulator drained
@@ -1268,6 +1297,14 @@ __global__ void __launch_bounds__(kT6Threads, 1) attn_table_rows_kernel(const At
         }
         mbar_wait_guard(mbar, mph, 20);
         mph ^= 1u;
+      }
+      if (bias_mma) {                                                          // + bias (hi, lo) of this head
+        for (int r = pt; r < nn; r += kTeam6) {
+          unsigned char* c0p = sA + a_off(r, kb + 2 * h);
+          unsigned char* c1p = sA + a_off(r, kb + 2 * h + 1);
+          *reinterpret_cast<uint16_t*>(c0p) = 0x3C00; *reinterpret_cast<uint16_t*>(c1p) = 0x3C00;
+          *reinterpret_cast<uint16_t*>(c0p + rep_off) = 0x3C00; *reinterpret_cast<uint16_t*>(c1p + rep_off) = 0x3C00;
+        }
       }
       cp_async_wait_all();
       fence_proxy_async();

@@ -26,6 +26,7 @@ for r in rows[2:]:
     tot = float(r[ix["dram__bytes_read.sum"]]) * mult(u[ix["dram__bytes_read.sum"]]) + float(r[ix["dram__bytes_write.sum"]]) * mult(u[ix["dram__bytes_write.sum"]])
     key = None
     if "conv2_attn" in name: key = "edge2"
+    elif "attn_table_prep" in name: key = "edge1_prep"
     elif "attn_table" in name: key = "edge1"
     elif "env_round" in name: key = "env"
     elif "ctrl_need" in name: key = "ctrl_need_list"
