@@ -906,9 +906,9 @@ __global__ void __launch_bounds__(kT4Threads, 1) attn_table_mma4_kernel(const At
 // weights are scattered into the (cleared) K-major weight tile.
 //   D[target][channel] = W[target][source] (A, K-major) x V[source][channel] (B, MN-major), M = 128, N = 128 per (tile, head)
 // item; a TMEM lane is a target: an epilogue thread adds the conv bias, converts and writes 16-byte pieces of its target's
-// x1 row (and snapshot row) through a warp-private transposition tile (whole 128-byte row segments per store).  Six 24 KiB
-// stages / producer teams of 2 warps; four independent epilogue warp pairs (pair g owns head g and TMEM buffer g); a stage
-// returns to its team on tcgen05.commit.
+// x1 row (and snapshot row) through a transposition tile (whole 128-byte row segments per store).  Six 24 KiB stages /
+// producer teams of 2 warps; four independent pairs of DRAIN warps (pair g owns head g and TMEM buffer g; TMEM -> tile) each
+// followed by its STORE warp (tile -> global); a stage returns to its team on tcgen05.commit.
 constexpr int kRecFixed = 16 + 64 * 4 + 64 * 4 + 64 * 2;   // 656 bytes: header, x_out rows, snapshot slots, key ids
 constexpr int kRecChunk = 512;                             // entries per in-kernel chunk
 __host__ __device__ inline int rec_entry_cap(int rows) { return (rows * (kMaxNbr + 1) + 7) & ~7; }
@@ -1047,7 +1047,7 @@ __global__ void __launch_bounds__(256, 4) attn_table_prep_kernel(const AttnTable
   }
 }
 
-constexpr int kT6Threads = 704;
+constexpr int kT6Threads = 960;
 constexpr int kTeam6 = 64;
 constexpr int kNumSt6 = 6;
 constexpr int kStage1 = kAHead + 2 * kBPanel;  // 24 KiB
@@ -1089,13 +1089,15 @@ __global__ void __launch_bounds__(kT6Threads, 1) attn_table_rows_kernel(const At
   unsigned char* epi_tiles = meta + kNumSt6 * kMeta8;                             // [8][kEpiTile]
   float* bias_s = reinterpret_cast<float*>(epi_tiles + 8 * kEpiTile);             // [512]
   uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + 512);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 40);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 56);
   const uint32_t bar0 = smem_u32(bars);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (8 + s); };
   auto meta_bar = [&](int s) { return bar0 + 8u * (16 + s); };
   auto tfull_bar = [&](int b) { return bar0 + 8u * (24 + b); };
   auto tempty_bar = [&](int b) { return bar0 + 8u * (28 + b); };
+  auto tile_full_bar = [&](int w) { return bar0 + 8u * (32 + w); };
+  auto tile_free_bar = [&](int w) { return bar0 + 8u * (40 + w); };
 
   const int N = a.N, HC = 4 * kC;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1126,6 +1128,7 @@ __global__ void __launch_bounds__(kT6Threads, 1) attn_table_rows_kernel(const At
   if (threadIdx.x == 0) {
     for (int s = 0; s < kNumSt6; ++s) { mbar_init(full_bar(s), kTeam6); mbar_init(empty_bar(s), 1 + 2); mbar_init(meta_bar(s), 1); }
     for (int b = 0; b < 4; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 2 * 32); }
+    for (int w = 0; w < 8; ++w) { mbar_init(tile_full_bar(w), 32); mbar_init(tile_free_bar(w), 32); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
@@ -1136,7 +1139,8 @@ __global__ void __launch_bounds__(kT6Threads, 1) attn_table_rows_kernel(const At
   const uint32_t tmem_base = *tmem_slot;
 
   const bool is_epi = warp >= 4 && warp < 18 && (warp & 3) < 2;
-  const bool is_prod = warp >= 2 && !is_epi;
+  const bool is_store = warp >= 22;
+  const bool is_prod = warp >= 2 && !is_epi && !is_store;
   if (warp == 0) {
     // ===================================================================== MMA issuer
     if (lane == 0) {
@@ -1169,8 +1173,13 @@ __global__ void __launch_bounds__(kT6Threads, 1) attn_table_rows_kernel(const At
     // instruction writes whole 128-byte row segments (per-lane 16-byte pieces of 32 different rows are one L2 request
     // each: 0.39 ms of this kernel).
     const int qq = warp & 3, b = (warp >> 2) - 1;                              // b == head == accumulator buffer
-    unsigned char* tile_s = epi_tiles + (b * 2 + qq) * kEpiTile;
-    const int srow = lane >> 3, schunk = lane & 7;                             // store phase: 4 rows x 8 chunks per instruction
+    // Drain warps (this branch) move the accumulator into the pair's transposition tile; a STORE warp per drain warp
+    // (below) writes the rows out, so that the address arithmetic / global stores of item k overlap the tcgen05.ld /
+    // conversion of item k + 4 (the epilogue was the kernel's limiter: its warps were 75 % busy).  A tile row = 128 bytes of
+    // channels + 16 bytes {x1 row, snapshot slot, rows in the tile (-1: stop), byte offset inside a row}.
+    const int dw = b * 2 + qq;
+    unsigned char* tile_s = epi_tiles + dw * kEpiTile;
+    uint32_t msg = 0;
     int s = b % kNumSt6;
     for (int k = b; k < n_items; k += 4) {
       mbar_wait_guard(tfull_bar(b), (k >> 2) & 1, 20);
@@ -1181,7 +1190,7 @@ __global__ void __launch_bounds__(kT6Threads, 1) attn_table_rows_kernel(const At
       const int nn = hdr.x;
       const bool rep = nn <= 32;
       const int t0 = rep ? 0 : qq * 32;                                        // first target of this warp's TMEM lanes
-      const int nv = min(32, nn - t0);                                         // targets among them
+      const int nv = max(0, min(32, nn - t0));                                 // targets among them
       int xr = 0, sl = -1;
       if (lane < nv) { xr = tab_x[t0 + lane]; sl = tab_s[t0 + lane]; }
       __syncwarp();
@@ -1190,6 +1199,7 @@ __global__ void __launch_bounds__(kT6Threads, 1) attn_table_rows_kernel(const At
       const int c0 = rep ? qq * 64 : 0, nhalf = rep ? 1 : 2;                   // this warp's channels of the head: [c0, c0 + 64 nhalf)
       const uint32_t tcol = tmem_base + ((uint32_t)(qq * 32) << 16) + (uint32_t)(b * 128 + c0);
       for (int hf = 0; hf < nhalf; ++hf) {
+        mbar_wait_guard(tile_free_bar(dw), (msg & 1u) ^ 1u, 20);               // the store warp has read the previous tile
         if (nv > 0) {
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
@@ -1206,21 +1216,37 @@ __global__ void __launch_bounds__(kT6Threads, 1) attn_table_rows_kernel(const At
             }
           }
         }
+        *reinterpret_cast<int4*>(tile_s + lane * kEpiRow + 128) = make_int4(xr, sl, nv, (b * kC + c0 + hf * 64) * 2);
         if (hf == nhalf - 1) { tc_fence_before(); mbar_arrive(tempty_bar(b)); }   // accumulator drained
-        __syncwarp();
-        const int colb = (b * kC + c0 + hf * 64) * 2 + schunk * 16;            // byte offset inside an x1 row
-        for (int r0 = 0; r0 < nv; r0 += 4) {
-          const int r = r0 + srow;
-          const int xr_r = __shfl_sync(0xffffffffu, xr, r & 31), sl_r = __shfl_sync(0xffffffffu, sl, r & 31);
-          if (r < nv) {
-            const uint4 val = *reinterpret_cast<const uint4*>(tile_s + r * kEpiRow + schunk * 16);
-            *reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(a.x_out) + (size_t)xr_r * (HC * 2) + colb) = val;
-            if (sl_r >= 0)
-              *reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(a.z) + ((size_t)sl_r * a.ldz + a.z_col) * 2 + colb) = val;
-          }
-        }
-        __syncwarp();
+        mbar_arrive(tile_full_bar(dw));
+        ++msg;
       }
+    }
+    mbar_wait_guard(tile_free_bar(dw), (msg & 1u) ^ 1u, 20);
+    *reinterpret_cast<int4*>(tile_s + lane * kEpiRow + 128) = make_int4(0, -1, -1, 0);   // stop
+    mbar_arrive(tile_full_bar(dw));
+  } else if (is_store) {
+    // ===================================================================== store warps: tile -> x1 rows / snapshot rows
+    const int sw = warp - 22;
+    const unsigned char* tile_s = epi_tiles + sw * kEpiTile;
+    const int srow = lane >> 3, schunk = lane & 7;                             // 4 rows x 8 chunks per instruction
+    for (uint32_t msg = 0;; ++msg) {
+      mbar_wait_guard(tile_full_bar(sw), msg & 1u, 20);
+      const int nv = reinterpret_cast<const int*>(tile_s + 128)[2];
+      if (nv < 0) break;
+      for (int r0 = 0; r0 < nv; r0 += 4) {
+        const int r = r0 + srow;
+        if (r < nv) {
+          const int4 pd = *reinterpret_cast<const int4*>(tile_s + r * kEpiRow + 128);
+          const uint4 val = *reinterpret_cast<const uint4*>(tile_s + r * kEpiRow + schunk * 16);
+          const size_t colb = (size_t)pd.w + schunk * 16;
+          *reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(a.x_out) + (size_t)pd.x * (HC * 2) + colb) = val;
+          if (pd.y >= 0)
+            *reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(a.z) + ((size_t)pd.y * a.ldz + a.z_col) * 2 + colb) = val;
+        }
+      }
+      __syncwarp();
+      mbar_arrive(tile_free_bar(sw));
     }
   } else if (is_prod) {
     // ===================================================================== producer teams: data movement only
