@@ -10,6 +10,8 @@
 //
 // Accumulation is fp32 everywhere; activations and weights are rounded to bf16
 // (tolerance stated in tests/test_networks_gpu.py).  Reference math: see dgn_forward.cu.
+#include <algorithm>
+
 #include "dgn_kernels.cuh"
 #include "gemm_tcgen05.cuh"
 #include "attn_table.cuh"
@@ -664,11 +666,14 @@ __global__ void ctrl_need_list_kernel(const uint8_t* __restrict__ ctrl_mask, con
 // z[t][0:hidden] = x0[idx[t]]  (encoder snapshot, l_dgn.py:121-122)
 __global__ void gather_x0_kernel(const int* __restrict__ idx, const int* __restrict__ count, const bf16* __restrict__ x0,
                                  const uint32_t* __restrict__ row_key, int hidden, bf16* __restrict__ z, int ldz) {
-  const int t = blockIdx.x * blockDim.y + threadIdx.y;
-  if (t >= *count) return;
-  const size_t r = row_key ? (size_t)row_key[idx[t]] : (size_t)idx[t];
-  for (int c = threadIdx.x * 8; c < hidden; c += blockDim.x * 8)
-    *reinterpret_cast<uint4*>(z + (size_t)t * ldz + c) = *reinterpret_cast<const uint4*>(x0 + (size_t)r * hidden + c);
+  // grid-stride over the compacted controlling rows (their count is only known on the device: most of a grid sized for
+  // every node row would exit at once)
+  const int n = *count;
+  for (int t = blockIdx.x * blockDim.y + threadIdx.y; t < n; t += gridDim.x * blockDim.y) {
+    const size_t r = row_key ? (size_t)__ldg(row_key + __ldg(idx + t)) : (size_t)__ldg(idx + t);
+    for (int c = threadIdx.x * 8; c < hidden; c += blockDim.x * 8)
+      *reinterpret_cast<uint4*>(z + (size_t)t * ldz + c) = __ldg(reinterpret_cast<const uint4*>(x0 + (size_t)r * hidden + c));
+  }
 }
 
 struct ActArgsB {
@@ -1237,7 +1242,7 @@ int dgn_forward_bf16(const MlsNetDesc* d, const MlsNetWeights* w, const MlsForwa
       }
       prof_end(MLS_PROF_EDGE2);
       dim3 blk(16, 16);
-      gather_x0_kernel<<<(rows + 15) / 16, blk, 0, st>>>(ws.idx, ws.count, use_table ? ws.t_x0 : ws.x0, use_table ? ws.key : nullptr, hid, ws.z, latent);
+      gather_x0_kernel<<<std::min((rows + 15) / 16, sms * 16), blk, 0, st>>>(ws.idx, ws.count, use_table ? ws.t_x0 : ws.x0, use_table ? ws.key : nullptr, hid, ws.z, latent);
       mls_count_launch();
     }
     // dueling head on the tensor cores: [Q0;V0] stacked, then block-diagonal [Q1 0; 0 V1]
