@@ -21,6 +21,6 @@ for name, body in zip(names, blocks):
         op = m.group(1)
         n += 1
         ops[op] += 1
-    short = re.sub(r"\(.*", "", name).replace("mls::", "").replace("(anonymous namespace)::", "").replace("void ", "")
+    short = re.sub(r"\(.*", "", name.replace("(anonymous namespace)::", "")).replace("mls::", "").replace("void ", "")
     d = sum(v for k, v in ops.items() if k in ("DADD", "DMUL", "DFMA", "DSETP", "MUFU") and k != "MUFU") + ops.get("DFMA", 0) * 0
     print(f"{short[:58]:58s} {n:6d} " + " ".join(f"{ops.get(c, 0):7d}" for c in COLS) + f" {d:5d}")

@@ -411,6 +411,30 @@ def test_tensor_core_table_attention_within_tolerance(kind, kw, N, B):
     assert torch.equal(q1, q2)
 
 
+@pytest.mark.parametrize("kind,N,B", [("l_dgn", 50, 600), ("dgn_r", 20, 700), ("l_dgn", 12, 333), ("l_dgn", 60, 64)])
+def test_record_based_conv1_kernel_agrees_with_the_staged_kernel(kind, N, B):
+    """Option attn_hp: 2 = per-tile records from the pre-pass + row-major tcgen05 kernel (default), 1 = the staged kernel that
+    builds every item itself.  Same math, same fp16 weights and value rows, different accumulation layouts: Q-values
+    agree to bf16 rounding of the conv1 output, on tiles of 1..5 graphs, with and without room for the bias rows
+    (N = 60), many tiles per CTA."""
+    from melissa_b200 import _lib
+    sd = _random_sd(kind, 61)
+    om = _obs_matrix(N, B, 17)
+    cm = np.random.default_rng(4).random((B, N)) < 0.35
+    m = _module(kind, N, sd).set_precision("bf16")
+    args = (torch.as_tensor(om, device="cuda"), torch.as_tensor(cm, device="cuda").to(torch.uint8))
+    outs = {}
+    try:
+        for mode in (1, 2):
+            _lib.set_option("attn_hp", mode)
+            outs[mode] = m.forward_graphs(*args, discrete_features=True)[0].clone()
+    finally:
+        _lib.set_option("attn_hp", 2)
+    scale = max(1.0, float(outs[1].abs().max()))
+    assert float((outs[1] - outs[2]).abs().max()) <= 2e-3 * scale
+    assert not torch.equal(outs[1], outs[2]) or B < 8          # really two kernels
+
+
 def test_tensor_core_table_attention_falls_back_when_keys_overflow():
     """More than 1024 distinct feature keys in one pass: the pair-logit table cannot hold them, the gather
     kernel takes the pass (decided on the device) -- bit-identical to the per-node path."""
