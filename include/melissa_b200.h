@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define MLS_VERSION 200
+#define MLS_VERSION 210
 #define MLS_MAX_NODES 256
 
 /* ---- errors ------------------------------------------------------------------------- */
