@@ -917,7 +917,9 @@ __host__ __device__ inline int rec_stride(int rows) { return kRecFixed + 10 * re
 // One warp per tile.  Lane l owns tile rows l and l + 32.
 __global__ void __launch_bounds__(256, 4) attn_table_prep_kernel(const AttnTableArgs a, const int G) {
   if (*a.n_used > kAttnUcap) return;
-  __shared__ uint16_t cid_sm[8][64];
+  __shared__ uint16_t cid_sm[8][64], p0_sm[8][64], off_sm[8][64];
+  __shared__ uint8_t need_sm[8][64], cnt_sm[8][64];
+  __shared__ int cg_sm[8][64];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int N = a.N;
   const int n_tiles = (a.n_graphs + G - 1) / G;
@@ -929,6 +931,11 @@ __global__ void __launch_bounds__(256, 4) attn_table_prep_kernel(const AttnTable
   unsigned char* rec = a.rec + (size_t)tile * rec_stride(G * N);
   const int cap = rec_entry_cap(G * N);
   uint16_t* cid_s = cid_sm[warp];
+  uint16_t* p0_s = p0_sm[warp];
+  uint16_t* off_s = off_sm[warp];
+  uint8_t* need_s = need_sm[warp];
+  uint8_t* cnt_s = cnt_sm[warp];
+  int* cg_s = cg_sm[warp];
   int xr[2], sl[2], cnt[2], p0[2], gl[2];
   uint16_t cv[2];
   const uint8_t* srcp[2];
@@ -947,8 +954,11 @@ __global__ void __launch_bounds__(256, 4) attn_table_prep_kernel(const AttnTable
       const int d = (int)__ldg(a.csr_ptr + cg * (N + 1) + il + 1) - p0[q];
       srcp[q] = a.csr_src + cg * N * kMaxNbr + p0[q];
       if (xr[q] >= 0) cnt[q] = d + self;
+      if (il == 0) cg_s[gl[q]] = (int)cg;
     }
     cid_s[r] = cv[q];
+    p0_s[r] = (uint16_t)p0[q];
+    cnt_s[r] = (uint8_t)cnt[q];
   }
   __syncwarp();
   const uint32_t lt = (1u << lane) - 1u;
@@ -978,23 +988,26 @@ __global__ void __launch_bounds__(256, 4) attn_table_prep_kernel(const AttnTable
   for (int q = 0; q < 2; ++q) {
     const int r = lane + 32 * q;
     cid_g[r] = cv[q];
-    if (xr[q] >= 0) { tab_x[rank[q]] = xr[q]; tab_s[rank[q]] = sl[q]; }
+    if (xr[q] >= 0) { tab_x[rank[q]] = xr[q]; tab_s[rank[q]] = sl[q]; need_s[rank[q]] = (uint8_t)r; off_s[rank[q]] = (uint16_t)off[q]; }
   }
+  __syncwarp();
   // padding entries (read by the 16-byte granular copies, never scattered): keep them defined
   if (lane < ne_pad - ne) {
     jr[ne + lane] = 0;
     for (int h = 0; h < 4; ++h) wts[(size_t)h * cap + ne + lane] = __float2half_rn(0.f);
   }
+  // one needed target per lane, in rank order (at most 32 of them in the typical tile: a single pass with every lane's
+  // table reads in flight together, instead of one pass per half of the tile's rows)
 #pragma unroll 1
-  for (int q = 0; q < 2; ++q) {
-    const int c = cnt[q];
+  for (int rki = lane; rki < nn; rki += 32) {
+    const int r = need_s[rki], c = cnt_s[r];
     if (c == 0) continue;
-    const int r = lane + 32 * q, rbase = gl[q] * N;
-    const float4* Erow = reinterpret_cast<const float4*>(a.E) + (size_t)cv[q] * kAttnUcap;
-    const uint8_t* src = srcp[q];
-    uint16_t* jo = jr + off[q];
-    __half* wo = wts + off[q];
-    const int rk = rank[q] << 8;
+    const int glr = r / N, rbase = glr * N;
+    const float4* Erow = reinterpret_cast<const float4*>(a.E) + (size_t)cid_s[r] * kAttnUcap;
+    const uint8_t* src = a.csr_src + (size_t)cg_s[glr] * N * kMaxNbr + p0_s[r];
+    uint16_t* jo = jr + off_s[rki];
+    __half* wo = wts + off_s[rki];
+    const int rk = rki << 8;
     if (c <= 8) {
       float4 e[8];
       int jv[8];
