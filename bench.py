@@ -438,6 +438,19 @@ def run_ours(args):
                 return chunk_rows * (4 + 2 + 2) + chunk_graphs * HC * esz
             return chunk_rows * (4 + 2 + 2 + 4 + 4) + (need_rows + ctrl_rows) * HC * esz
 
+        def write_only_peak():
+            """HBM bandwidth of a pure write stream, measured here (2 GiB memset, best of 5): on this part a write-only
+            kernel tops out far below the read + write copy figure of MEASURED_PEAKS.json (3.9 vs 6.5 TB/s), which is the
+            ceiling that matters for the conv1 stage (it reads tables from L2 and writes 1.4 GB)."""
+            buf = torch.empty(1 << 31, dtype=torch.uint8, device=dev)
+            best = 1e9
+            for _ in range(6):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); buf.zero_(); e1.record(); torch.cuda.synchronize()
+                best = min(best, e0.elapsed_time(e1))
+            del buf
+            return (1 << 31) / (best * 1e-3) / 1e9
+
         roof_conv1 = None
         if kern_ms and prof_name == "edge2":
             # conv2 attention (conv2_attn_kernel): reads the source-side projections of the needed rows ((nproj-1)*HC fp16)
@@ -454,6 +467,15 @@ def run_ours(args):
                         if N <= 62 else "edge_bf16_kernel (conv1 attention, gather from the feature table")
                 roof_conv1 = hbm_line(f"{name}, {chunk_graphs} graphs, {int(need_rows)} output rows)", c1_ms, conv1_bytes(), "edge1",
                                       "event pair spans the whole conv1 attention stage")
+                try:
+                    wp = write_only_peak()
+                    roof_conv1["write_only_peak"] = round(wp, 1)
+                    roof_conv1["frac_of_write_only_peak"] = round(roof_conv1["achieved"] / wp, 4)
+                    roof_conv1["note"] += ("; the stage is a write stream (tables come from L2): write_only_peak = 2 GiB memset measured in "
+                                           "this run, the copy figure in `peak` needs reads and writes in flight together")
+                except Exception as e:                                  # the extra line must never cost the bench its result
+                    roof_conv1["write_only_peak"] = None
+                    roof_conv1["note"] += f"; write-only peak not measured ({type(e).__name__})"
         elif kern_ms and prof_name == "edge1":
             roofline = hbm_line(f"conv1 attention stage ({chunk_graphs} graphs x 4 heads)", kern_ms, conv1_bytes(), "edge1",
                                 "largest share of the step")
