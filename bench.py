@@ -436,7 +436,9 @@ def run_ours(args):
             # xrow 4 bytes and writes relu(conv1) of the NEEDED rows (HC bf16) + the controlling-node snapshot (HC bf16)
             if args.model == "hl_dgn":                              # pooling: reads keys, writes one row per graph
                 return chunk_rows * (4 + 2 + 2) + chunk_graphs * HC * esz
-            return chunk_rows * (4 + 2 + 2 + 4 + 4) + (need_rows + ctrl_rows) * HC * esz
+            # (option ctrl_first, default: a controlling node's row is written once -- its x1 row is the snapshot row)
+            snap_rows = 0 if _lib.get_option("ctrl_first") else ctrl_rows
+            return chunk_rows * (4 + 2 + 2 + 4 + 4) + (need_rows + snap_rows) * HC * esz
 
         def write_only_peak():
             """HBM bandwidth of a pure write stream, measured here (2 GiB memset, best of 5): on this part a write-only

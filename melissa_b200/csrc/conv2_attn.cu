@@ -149,17 +149,19 @@ __global__ void __launch_bounds__(kThreads, TR ? 4 : 6) conv2_attn_kernel(const 
       for (int t = tid; t < n; t += kThreads) s_ent[t] = __ldg(a.eent + ef + e0 + t);
     }
   };
+  // row of source k (compact index) in Ps / as
+  auto src_row = [&](int first, int cnt, int nf, int k) { return a.ctrl_first ? (k < cnt ? first + k : nf + k - cnt) : nf + k; };
   auto issue_A = [&](int first, int cnt, int nf, int nc) {
     load_targets(first, 0, cnt < kTB ? cnt : kTB);
     if (!TR) {
-      if (tid < nc) s_as[tid] = __ldg(a.as + (size_t)(nf + tid) * H + h) * k06;
+      if (tid < nc) s_as[tid] = __ldg(a.as + (size_t)src_row(first, cnt, nf, tid) * H + h) * k06;
       if (tid < cnt) s_bt[tid] = __ldg(a.bt + (size_t)(first + tid) * H + h) * k06;
     }
   };
   auto issue_B = [&](int first, int cnt, int nf, int nc, int ef, int ne) {
     for (int t = tid; t < nc * 16; t += kThreads) {
       const int k = t >> 4, c = t & 15;
-      const __half* row = a.Ps + (size_t)(nf + k) * a.lds + h * kC + c * 8;
+      const __half* row = a.Ps + (size_t)src_row(first, cnt, nf, k) * a.lds + h * kC + c * 8;
       unsigned char* xd = sX + (c >> 3) * kPanel + k * 128 + (((c & 7) ^ (k & 7)) << 4);
       if (TR) {
         cp16(sK + k * kRowPad + c * 16, row);

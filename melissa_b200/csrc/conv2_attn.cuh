@@ -36,6 +36,9 @@ struct Conv2Args {
   // output: relu(conv2)[slot] as bf16 at z[slot][z_col + h*C ...]
   __nv_bfloat16* z;
   int ldz, z_col;
+  // needed rows ordered [controlling nodes by slot][the others]: source k of graph g (compact index, controlling nodes
+  // first) lives in row first_slot + k for k < controlling nodes, else gmeta[2] + k - controlling nodes
+  int ctrl_first;
 };
 
 inline bool conv2_attn_supported(int N, int H) { return N >= 1 && N <= kConv2MaxNodes && H >= 1; }

@@ -529,7 +529,7 @@ __global__ void ctrl_need_list_kernel(const uint8_t* __restrict__ ctrl_mask, con
                                       int* __restrict__ ncount, int* __restrict__ nfirst, int* __restrict__ ncnt,
                                       const uint16_t* __restrict__ csr_ptr, const uint8_t* __restrict__ csr_src, int self_loops,
                                       int* __restrict__ ecount, int* __restrict__ eabs, uint16_t* __restrict__ eent,
-                                      int* __restrict__ gmeta) {
+                                      int* __restrict__ gmeta, int ctrl_first) {
   const int lane = threadIdx.x & 31;
   const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (g >= n_graphs) return;
@@ -590,11 +590,31 @@ __global__ void ctrl_need_list_kernel(const uint8_t* __restrict__ ctrl_mask, con
     nw[w] = __reduce_or_sync(0xffffffffu, nw[w]) | cw[w];
     nn += __popc(nw[w]);
   }
+  // ctrl_first: the needed rows are ordered [all controlling nodes, in slot order][the other needed nodes]: a controlling
+  // node's compact row IS its slot, so relu(conv1) of the controlling rows is written once and x1[0 : count) doubles as the
+  // snapshot matrix.  The other needed nodes get -2 - j here (j from a counter of their own); need_rows_fixup_kernel turns
+  // that into count + j once the total number of controlling nodes is known, and builds nidx.
+  const int nalloc = ctrl_first ? nn - total : nn;
   int ns = 0;
-  if (lane == 0 && nn) ns = atomicAdd(ncount, nn);
+  if (lane == 0 && nalloc) ns = atomicAdd(ncount, nalloc);
   ns = __shfl_sync(0xffffffffu, ns, 0);
   if (lane == 0) { nfirst[g] = ns; ncnt[g] = nn; }
-  {
+  if (ctrl_first) {
+    int run_c = slot0, run_o = ns;
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+      const int i = w * 32 + lane;
+      const uint32_t ow = nw[w] & ~cw[w], below = (1u << lane) - 1;
+      if (i < N) {
+        int r = -1;
+        if ((cw[w] >> lane) & 1u) r = run_c + __popc(cw[w] & below);
+        else if ((ow >> lane) & 1u) r = -2 - (run_o + __popc(ow & below));
+        xrow[(size_t)g * N + i] = r;
+      }
+      run_c += __popc(cw[w]);
+      run_o += __popc(ow);
+    }
+  } else {
     int run = ns;
 #pragma unroll
     for (int w = 0; w < W; ++w) {
@@ -652,15 +672,41 @@ __global__ void ctrl_need_list_kernel(const uint8_t* __restrict__ ctrl_mask, con
         const int jw = j >> 5;
         const uint32_t below = (1u << (j & 31)) - 1u;
         int r = 0;
+        if (!ctrl_first) {
 #pragma unroll
-        for (int v = 0; v < W; ++v) r += __popc(nw[v] & (v < jw ? 0xffffffffu : (v == jw ? below : 0u)));
-        return r;
+          for (int v = 0; v < W; ++v) r += __popc(nw[v] & (v < jw ? 0xffffffffu : (v == jw ? below : 0u)));
+          return r;
+        }
+        // controlling nodes first (rank among them), then the other needed nodes
+        const bool jc = (cw[jw] >> (j & 31)) & 1u;
+#pragma unroll
+        for (int v = 0; v < W; ++v) {
+          const uint32_t m = v < jw ? 0xffffffffu : (v == jw ? below : 0u);
+          r += __popc((jc ? cw[v] : (nw[v] & ~cw[v])) & m);
+        }
+        return jc ? r : total + r;
       };
       if (self_loops) eent[pos++] = (uint16_t)(rank_of(i) | (tk << 8));
       for (int k = 0; k < dv[w]; ++k) eent[pos + k] = (uint16_t)(rank_of(gs[r0v[w] + k]) | (tk << 8));
     }
     tk_base += __popc(cw[w]);
   }
+}
+
+// ctrl_first: final compact rows (see ctrl_need_list_kernel).  One thread per node row: -2 - j -> count + j, nidx[row] = node
+// row; one thread per graph: first non-controlling needed row of the graph (gmeta[2]) made absolute; thread 0: ncount (the
+// other needed nodes so far) -> total number of needed rows.
+__global__ void need_rows_fixup_kernel(int* __restrict__ xrow, int* __restrict__ nidx, int* __restrict__ gmeta, const int* __restrict__ count,
+                                       const int* __restrict__ ncount, int* __restrict__ ntotal, int rows, int n_graphs) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = *count;
+  if (t < rows) {
+    int r = xrow[t];
+    if (r <= -2) { r = c + (-2 - r); xrow[t] = r; }
+    if (r >= 0) nidx[r] = t;
+  }
+  if (gmeta && t < n_graphs) gmeta[(size_t)t * 8 + 2] += c;
+  if (t == 0) *ntotal = *ncount + c;
 }
 
 // z[t][0:hidden] = x0[idx[t]]  (encoder snapshot, l_dgn.py:121-122)
@@ -825,6 +871,7 @@ struct WsB {
   float* qg;
   int *idx, *slot, *count, *gfirst, *gcnt;
   int *nidx, *xrow, *ncount, *nfirst, *ncnt;   // needed rows (conv2 sources)
+  int* ntotal;                                 // ctrl_first: controlling + other needed rows (ncount then counts the others only)
   int *ecount, *eabs, *gmeta;                  // conv2 edge lists (conv2_attn.cu)
   uint16_t* eent;
   uint16_t* csr_ptr;
@@ -890,7 +937,7 @@ size_t carve_b(const MlsNetDesc* d, int Gc, unsigned char* base, WsB* ws) {
     ws->hv1 = F(o_hv1); ws->hv2 = F(o_hv2); ws->hd = F(o_hd);
     ws->h = B(o_h); ws->x0 = B(o_x0); ws->P = B(o_P); ws->x1 = B(o_x1); ws->z = B(o_z); ws->hid1 = B(o_h1); ws->hid2 = B(o_h2);
     ws->qg = F(o_qg);
-    ws->idx = I(o_idx); ws->slot = I(o_slot); ws->count = I(o_cnt); ws->ncount = I(o_cnt) + 1; ws->ecount = I(o_cnt) + 2;
+    ws->idx = I(o_idx); ws->slot = I(o_slot); ws->count = I(o_cnt); ws->ncount = I(o_cnt) + 1; ws->ecount = I(o_cnt) + 2; ws->ntotal = I(o_cnt) + 3;
     ws->eabs = I(o_eabs); ws->gmeta = I(o_gmeta); ws->eent = reinterpret_cast<uint16_t*>(base + o_eent);
     ws->gfirst = I(o_gf); ws->gcnt = I(o_gc);
     ws->nidx = I(o_nidx); ws->xrow = I(o_xrow); ws->nfirst = I(o_nf); ws->ncnt = I(o_nc);
@@ -1146,15 +1193,23 @@ int dgn_forward_bf16(const MlsNetDesc* d, const MlsNetWeights* w, const MlsForwa
     const uint32_t* adjm = cached ? cache.adjm : ws.adjm;
     // radius graph (unless cached), then the controlling-node list and the needed rows
     if (!cached && (rc = launch_csr(st, obs, a->obs_stride, N, gc, ws.csr_ptr, ws.csr_src, hl ? nullptr : ws.adjm))) return rc;
+    // needed rows ordered with the controlling nodes first (row = slot): relu(conv1) of a controlling node is written once
+    // (not with the single-linear head, which reads whole latent rows of z)
+    const bool ctrl_first = !hl && !w->out_w && mls_get_option("ctrl_first");
     if (!hl) {
       MLS_CUDA(cudaMemsetAsync(ws.count, 0, 4 * sizeof(int), st));
       const unsigned grid = (unsigned)((gc * 32 + 255) / 256);
 #define MLS_LIST(WW) ctrl_need_list_kernel<WW><<<grid, 256, 0, st>>>(cm, obs, a->obs_stride, N, gc, a->ctrl_mode, adjm, gid, gid_stride, ws.idx, \
                                                                       ws.slot, ws.count, ws.gfirst, ws.gcnt, ws.nidx, ws.xrow, ws.ncount, ws.nfirst, ws.ncnt, \
-                                                                      csr_ptr, csr_src, tr ? 0 : 1, ws.ecount, ws.eabs, use_c2 ? ws.eent : nullptr, ws.gmeta)
+                                                                      csr_ptr, csr_src, tr ? 0 : 1, ws.ecount, ws.eabs, use_c2 ? ws.eent : nullptr, ws.gmeta, ctrl_first ? 1 : 0)
       switch (Wn) { case 1: MLS_LIST(1); break; case 2: MLS_LIST(2); break; case 4: MLS_LIST(4); break; default: MLS_LIST(8); break; }
 #undef MLS_LIST
       mls_count_launch();
+      if (ctrl_first) {
+        const int nthr = rows > gc ? rows : gc;
+        need_rows_fixup_kernel<<<(nthr + 255) / 256, 256, 0, st>>>(ws.xrow, ws.nidx, use_c2 ? ws.gmeta : nullptr, ws.count, ws.ncount, ws.ntotal, rows, gc);
+        mls_count_launch();
+      }
     }
     // encoder (or, in discrete-feature mode, just the table keys of this pass)
     if (use_table) {
@@ -1183,14 +1238,14 @@ int dgn_forward_bf16(const MlsNetDesc* d, const MlsNetWeights* w, const MlsForwa
       ea.att = w->c1_att; ea.bias = w->c1_bias; ea.csr_ptr = csr_ptr; ea.csr_src = csr_src; ea.ab = use_table ? ws.t_ab : ws.ab;
       ea.graph_id = gid; ea.gid_stride = gid_stride;
       if (hl) { ea.x_out = nullptr; ea.slot = nullptr; ea.z = ws.z; ea.ldz = latent; ea.z_col = 0; ea.ctrl_only = 0; ea.pool_mode = d->pool; }
-      else { ea.x_out = ws.x1; ea.slot = ws.slot; ea.z = ws.z; ea.ldz = latent; ea.z_col = hid; ea.ctrl_only = 0; ea.pool_mode = -1; ea.xrow_out = ws.xrow; }
+      else { ea.x_out = ws.x1; ea.slot = ctrl_first ? nullptr : ws.slot; ea.z = ws.z; ea.ldz = latent; ea.z_col = hid; ea.ctrl_only = 0; ea.pool_mode = -1; ea.xrow_out = ws.xrow; }
       prof_begin(MLS_PROF_EDGE1);
       if (use_mma) {
         AttnTableArgs ta{};
         ta.t_P = ws.t_P; ta.ldp = nproj * HC; ta.t_ab = ws.t_ab; ta.att = w->c1_att; ta.bias = tr ? nullptr : w->c1_bias;
         ta.transformer = tr ? 1 : 0; ta.key = ws.key; ta.N = N; ta.H = H; ta.n_graphs = gc; ta.csr_ptr = csr_ptr;
         ta.csr_src = csr_src; ta.graph_id = gid; ta.gid_stride = gid_stride;
-        ta.slot = ws.slot; ta.xrow = ws.xrow; ta.x_out = ws.x1; ta.z = ws.z; ta.ldz = latent; ta.z_col = hid;
+        ta.slot = ctrl_first ? nullptr : ws.slot; ta.xrow = ws.xrow; ta.x_out = ws.x1; ta.z = ws.z; ta.ldz = latent; ta.z_col = hid;
         ta.pool_mode = -1;
         if (hl) { ta.slot = nullptr; ta.xrow = nullptr; ta.x_out = nullptr; ta.z_col = 0; ta.pool_mode = d->pool; ta.obs = obs; ta.obs_stride = a->obs_stride; }
         ta.used_bits = ws.used; ta.n_keys = n_keys; ta.cid_of_key = ws.cid_of_key; ta.key_of_cid = ws.key_of_cid;
@@ -1217,11 +1272,12 @@ int dgn_forward_bf16(const MlsNetDesc* d, const MlsNetWeights* w, const MlsForwa
       GemmEpilogue e{Psrc, nsrc * HC, b_src, obs, a->obs_stride, N, 0, tr ? nullptr : ws.att2, tr ? nullptr : ws.ab, ws.nidx};
       e.c_fp16 = use_c2 ? 1 : 0;
       prof_begin(MLS_PROF_PROJ2);
-      if ((rc = gemm_bf16_launch(ws.x1, HC, w_src, HC, GemmShape{rows, nsrc * HC, HC, ws.ncount}, e, sms, st))) return rc;
+      if ((rc = gemm_bf16_launch(ws.x1, HC, w_src, HC, GemmShape{rows, nsrc * HC, HC, ctrl_first ? ws.ntotal : ws.ncount}, e, sms, st))) return rc;
       prof_end(MLS_PROF_PROJ2);
       GemmEpilogue et{Ptgt, HC, b_tgt, obs, a->obs_stride, N, 0, tr ? nullptr : ws.att2, tr ? nullptr : dots_t, ws.idx};
       et.c_fp16 = use_c2 ? 1 : 0;
-      if ((rc = gemm_bf16_launch(ws.z + hid, latent, w_tgt, HC, GemmShape{rows, HC, HC, ws.count}, et, sms, st))) return rc;
+      // target side: the controlling nodes' relu(conv1) rows -- the snapshot columns of z, or x1[0 : count) itself (ctrl_first)
+      if ((rc = gemm_bf16_launch(ctrl_first ? ws.x1 : ws.z + hid, ctrl_first ? HC : latent, w_tgt, HC, GemmShape{rows, HC, HC, ws.count}, et, sms, st))) return rc;
       // conv2 attention only where a controlling agent reads it; the result goes straight into z
       prof_begin(MLS_PROF_EDGE2);
       if (use_c2) {
@@ -1229,7 +1285,7 @@ int dgn_forward_bf16(const MlsNetDesc* d, const MlsNetWeights* w, const MlsForwa
         ca.Ps = reinterpret_cast<const __half*>(Psrc); ca.lds = nsrc * HC; ca.Pt = reinterpret_cast<const __half*>(Ptgt); ca.ldt = HC;
         ca.as = ws.ab; ca.bt = dots_t; ca.att = w->c2_att; ca.bias = tr ? nullptr : w->c2_bias; ca.transformer = tr ? 1 : 0;
         ca.N = N; ca.H = H; ca.n_graphs = gc; ca.gmeta = ws.gmeta; ca.eabs = ws.eabs; ca.eent = ws.eent;
-        ca.z = ws.z; ca.ldz = latent; ca.z_col = hid + HC;
+        ca.z = ws.z; ca.ldz = latent; ca.z_col = hid + HC; ca.ctrl_first = ctrl_first ? 1 : 0;
         if ((rc = conv2_attn_launch(ca, sms, st))) return rc;
       } else {
         EdgeArgs ea{};
@@ -1263,7 +1319,9 @@ int dgn_forward_bf16(const MlsNetDesc* d, const MlsNetWeights* w, const MlsForwa
     } else {
       GemmEpilogue e0{ws.hid1, hh2, ws.b_h0, nullptr, 0, N, 1, nullptr, nullptr};
       prof_begin(MLS_PROF_HEAD0);
-      if ((rc = gemm_bf16_launch(ws.z, latent, ws.w_h0, latent, GemmShape{head_rows, hh2, latent, m_dev}, e0, sms, st))) return rc;
+      GemmShape sh0{head_rows, hh2, latent, m_dev};
+      if (ctrl_first) { sh0.A2 = ws.x1; sh0.lda2 = HC; sh0.k2_lo = hid; sh0.k2_hi = hid + HC; }   // snapshot columns come from x1
+      if ((rc = gemm_bf16_launch(ws.z, latent, ws.w_h0, latent, sh0, e0, sms, st))) return rc;
       prof_end(MLS_PROF_HEAD0);
       // last hidden layer: with 128-wide heads the output layer rides in the epilogue as three dot products per
       // row and the hidden activations are never written

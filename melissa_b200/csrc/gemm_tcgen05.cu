@@ -37,7 +37,7 @@ struct GemmSmem {
 template <int BN, int MODE>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                         const GemmShape shape, const GemmEpilogue epi) {
+                         const __grid_constant__ CUtensorMap tmA2, const GemmShape shape, const GemmEpilogue epi) {
   using S = GemmSmem<BN>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment
@@ -86,7 +86,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t sa = smem_u32(smem + stage * S::kStageBytes);
           mbar_expect_tx(full_bar(stage), S::kStageBytes);
-          tma_load_2d(sa, &tmA, full_bar(stage), kb * kBK, m0);
+          if (kb * kBK >= shape.k2_lo && kb * kBK < shape.k2_hi) tma_load_2d(sa, &tmA2, full_bar(stage), kb * kBK - shape.k2_lo, m0);
+          else tma_load_2d(sa, &tmA, full_bar(stage), kb * kBK, m0);
           tma_load_2d(sa + S::kABytes, &tmB, full_bar(stage), kb * kBK, n0);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
@@ -300,7 +301,7 @@ int make_tmap_bf16(CUtensorMap* tm, const void* base, int rows, int cols, int ld
 size_t gemm_smem_bytes(int BN) { return BN == 256 ? GemmSmem<256>::kTotal : GemmSmem<128>::kTotal; }
 
 template <int BN, int MODE>
-static int launch_bn(const CUtensorMap& ta, const CUtensorMap& tb, GemmShape shape, GemmEpilogue epi, int sm_count, cudaStream_t st) {
+static int launch_bn(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ta2, GemmShape shape, GemmEpilogue epi, int sm_count, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
     MLS_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN>::kTotal));
@@ -309,7 +310,7 @@ static int launch_bn(const CUtensorMap& ta, const CUtensorMap& tb, GemmShape sha
   const int n_tiles = ((shape.M + kBM - 1) / kBM) * (shape.N / BN);
   const int grid = n_tiles < sm_count ? n_tiles : sm_count;
   if (grid <= 0) return MLS_OK;
-  gemm_bf16_tcgen05_kernel<BN, MODE><<<grid, kGemmThreads, GemmSmem<BN>::kTotal, st>>>(ta, tb, shape, epi);
+  gemm_bf16_tcgen05_kernel<BN, MODE><<<grid, kGemmThreads, GemmSmem<BN>::kTotal, st>>>(ta, tb, ta2, shape, epi);
   mls_count_launch();
   MLS_LAUNCH_CHECK();
   return MLS_OK;
@@ -333,6 +334,15 @@ int gemm_bf16_launch(const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, in
   if (rc) return rc;
   rc = make_tmap_bf16(&tb, B, shape.N, shape.K, ldb, BN);
   if (rc) return rc;
+  CUtensorMap ta2 = ta;
+  if (shape.A2) {
+    MLS_CHECK_ARG(shape.k2_lo % kBK == 0 && shape.k2_hi % kBK == 0 && shape.k2_lo >= 0 && shape.k2_lo < shape.k2_hi && shape.k2_hi <= shape.K && shape.lda2 % 8 == 0,
+                  "GEMM second A matrix: K range must be multiples of %d inside [0, K)", kBK);
+    rc = make_tmap_bf16(&ta2, shape.A2, shape.M, shape.k2_hi - shape.k2_lo, shape.lda2, kBM);
+    if (rc) return rc;
+  } else {
+    shape.k2_lo = shape.k2_hi = 0;
+  }
   int mode = 0;
   if (!epi.Cf) {
     if (epi.C && epi.dotvec && !epi.dotvec2 && !epi.dot_relu && !epi.relu) mode = 1;
@@ -341,13 +351,13 @@ int gemm_bf16_launch(const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, in
   }
   if (BN == 256) {
     switch (mode) {
-      case 1: return launch_bn<256, 1>(ta, tb, shape, epi, sm_count, st);
-      case 2: return launch_bn<256, 2>(ta, tb, shape, epi, sm_count, st);
-      case 3: return launch_bn<256, 3>(ta, tb, shape, epi, sm_count, st);
-      default: return launch_bn<256, 0>(ta, tb, shape, epi, sm_count, st);
+      case 1: return launch_bn<256, 1>(ta, tb, ta2, shape, epi, sm_count, st);
+      case 2: return launch_bn<256, 2>(ta, tb, ta2, shape, epi, sm_count, st);
+      case 3: return launch_bn<256, 3>(ta, tb, ta2, shape, epi, sm_count, st);
+      default: return launch_bn<256, 0>(ta, tb, ta2, shape, epi, sm_count, st);
     }
   }
-  return launch_bn<128, 0>(ta, tb, shape, epi, sm_count, st);
+  return launch_bn<128, 0>(ta, tb, ta2, shape, epi, sm_count, st);
 }
 
 }  // namespace mls

@@ -49,6 +49,11 @@ struct GemmEpilogue {
 struct GemmShape {
   int M, N, K;
   const int* m_dev;      // optional device-side row count (clamped to M)
+  // optional second A matrix for the K range [k2_lo, k2_hi) (multiples of 64): those columns of the logical A come from
+  // A2[m][k - k2_lo] (row stride lda2) instead of A[m][k] -- the dueling heads read their latent row from two matrices
+  // (snapshot columns of relu(conv1) live in x1, the rest in z)
+  const __nv_bfloat16* A2;
+  int lda2, k2_lo, k2_hi;
 };
 
 size_t gemm_smem_bytes(int BN);

@@ -437,6 +437,34 @@ def test_record_based_conv1_kernel_agrees_with_the_staged_kernel(kind, N, B):
     assert launches[2] > launches[1]                            # really two code paths: the pre-pass is one more launch per chunk
 
 
+@pytest.mark.parametrize("kind,N,B,tables", [("l_dgn", 50, 500, True), ("dgn_r", 20, 600, True), ("l_dgn", 20, 300, False), ("l_dgn", 100, 40, True)])
+def test_controlling_rows_first_layout_agrees_with_the_snapshot_copy(kind, N, B, tables):
+    """Option ctrl_first (default): needed rows ordered [controlling nodes by slot][others], relu(conv1) of a controlling node
+    written once, the heads' GEMM reading its snapshot columns from x1 through a second A descriptor; 0: per-graph node
+    order + a separate snapshot copy in z.  Same Q-values up to the summation order of conv2's sources; tensor-core and
+    gather attention paths (N = 100), table and GEMM projections."""
+    from melissa_b200 import _lib
+    sd = _random_sd(kind, 71)
+    om = _obs_matrix(N, B, 19)
+    cm = np.random.default_rng(6).random((B, N)) < 0.35
+    m = _module(kind, N, sd).set_precision("bf16")
+    args = (torch.as_tensor(om, device="cuda"), torch.as_tensor(cm, device="cuda").to(torch.uint8))
+    outs, launches = {}, {}
+    try:
+        for mode in (0, 1):
+            _lib.set_option("ctrl_first", mode)
+            before = _lib.lib().mls_launch_count()
+            q, act = m.forward_graphs(*args, discrete_features=tables)
+            outs[mode] = (q.clone(), act.clone())
+            launches[mode] = _lib.lib().mls_launch_count() - before
+    finally:
+        _lib.set_option("ctrl_first", 1)
+    scale = max(1.0, float(outs[0][0].abs().max()))
+    assert float((outs[0][0] - outs[1][0]).abs().max()) <= 2e-3 * scale
+    assert torch.equal(outs[0][1] >= 0, outs[1][1] >= 0)
+    assert launches[1] > launches[0]                            # the row fix-up kernel only runs in the new layout
+
+
 def test_tensor_core_table_attention_falls_back_when_keys_overflow():
     """More than 1024 distinct feature keys in one pass: the pair-logit table cannot hold them, the gather
     kernel takes the pass (decided on the device) -- bit-identical to the per-node path."""
