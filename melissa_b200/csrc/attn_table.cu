@@ -199,11 +199,13 @@ __global__ void __launch_bounds__(256) pair_logit_kernel(const AttnTableArgs a) 
     }
     const float b_i = a.transformer ? 0.f : a.t_ab[(size_t)ki * (2 * H) + H + h] * (0.6f * kLog2e);
     const int cj1 = min(U, cj0 + 32);
+    // four source keys in flight (read-only loads: free to move above the previous iterations' table stores)
+#pragma unroll 4
     for (int cj = cj0; cj < cj1; ++cj) {
-      const uint32_t kj = a.key_of_cid[cj];
+      const uint32_t kj = __ldg(a.key_of_cid + cj);
       float x[16];
       const uint4* p = reinterpret_cast<const uint4*>(a.t_P + (size_t)kj * a.ldp + src_col);
-      unpack8(p[0], x); unpack8(p[1], x + 8);
+      unpack8(__ldg(p), x); unpack8(__ldg(p + 1), x + 8);
       float pa = 0.f, pb = 0.f;
       if (a.transformer) {
 #pragma unroll
@@ -217,7 +219,7 @@ __global__ void __launch_bounds__(256) pair_logit_kernel(const AttnTableArgs a) 
       e += __shfl_xor_sync(0xffffffffu, e, 2);
       e += __shfl_xor_sync(0xffffffffu, e, 4);
       if (a.transformer) e *= tr_scale;
-      else e += a.t_ab[(size_t)kj * (2 * H) + h] * (0.6f * kLog2e) + b_i;
+      else e += __ldg(a.t_ab + (size_t)kj * (2 * H) + h) * (0.6f * kLog2e) + b_i;
       float4 o;
       o.x = __shfl_sync(0xffffffffu, e, 0); o.y = __shfl_sync(0xffffffffu, e, 8);
       o.z = __shfl_sync(0xffffffffu, e, 16); o.w = __shfl_sync(0xffffffffu, e, 24);
