@@ -556,6 +556,8 @@ def measure_training(args, dev, world, rank, model, N, B, pool, tuple_arrays, st
     net = NETWORKS[model](5, 128, 2, 4, N, dueling_param=({"hidden_sizes": [128, 128]}, {"hidden_sizes": [128, 128]}),
                           device=str(dev), **kw).to(dev)
     net.set_precision("bf16")
+    from melissa_b200.networks.autograd import fused_training_available
+    fused = bool(fused_training_available(net, torch.empty(1, device=dev)))
     flat = FlatParameters(net)
     optim = FusedAdam(flat, lr=1e-3)
     pol = DQNPolicy(net, optim, discount_factor=0.99, estimation_step=4, target_update_freq=500, eps=0.05, seed=9 + rank)
@@ -603,12 +605,14 @@ def measure_training(args, dev, world, rank, model, N, B, pool, tuple_arrays, st
     e1.record()
     torch.cuda.synchronize()
     round_ms = e0.elapsed_time(e1) / 5
-    e0.record()
-    for _ in range(5):
+    pol.update(batch, replay)                   # untimed: the non-deferred call order may grow the caching allocator
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(10)]
+    for i in range(9):
+        evs[i].record()
         pol.update(batch, replay)
-    e1.record()
+    evs[9].record()
     torch.cuda.synchronize()
-    update_ms = e0.elapsed_time(e1) / 5
+    update_ms = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(9))[4]   # median of 9 updates
     # the collective alone: all-reduce of the flat gradient buffer
     ar_us, busbw = None, None
     if world > 1:
@@ -653,8 +657,11 @@ def measure_training(args, dev, world, rank, model, N, B, pool, tuple_arrays, st
         "allreduce_us": ar_us, "allreduce_busbw_GBs": busbw,
         "allreduce_share_of_step": (ar_us * 1e-3 / (ms_max / steps)) if ar_us else 0.0,
         "weights_identical_across_ranks": same,
-        "backward": ("GATv2 edge phase forward + backward = mls_gatv2_edge_fwd / _bwd kernels on per-sample edge lists (mls_train_lists), dense layers = torch fp32 GEMMs under autograd"
-                     if model == "l_dgn" else "torch autograd over melissa_b200/networks/autograd.py") + "; optimiser = mls_adam_step kernel",
+        "backward": ({"l_dgn": "GATv2 edge phase forward + backward = mls_gatv2_edge_fwd / _bwd kernels",
+                      "hl_dgn": "GATv2 edge phase of both hops forward + backward = mls_gatv2_edge_fwd / _bwd kernels",
+                      "dgn_r": "TransformerConv edge phase forward + backward = mls_transformer_edge_fwd / _bwd kernels"}[model]
+                     + " on per-sample edge lists (mls_train_lists), dense layers = torch fp32 GEMMs under autograd"
+                     if fused else "torch autograd over melissa_b200/networks/autograd.py") + "; optimiser = mls_adam_step kernel",
     }
     del col, replay, env, pol, optim, flat, net
     torch.cuda.empty_cache()
