@@ -35,6 +35,9 @@ constexpr int kRowPad = kC * 2 + 16;      // padded row of 128 fp16 (bank-confli
 __device__ __forceinline__ void cp16(unsigned char* dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
+__device__ __forceinline__ void cp4(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
 __device__ __forceinline__ void cp_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ float ex2f(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rcpf(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -62,6 +65,7 @@ constexpr int kEdgeCap = 256;
 constexpr int kWRows = kTB;
 constexpr int kWTile = kWRows * 128;      // 4 KB
 constexpr int kTCols = 32;                // TMEM columns per CTA
+constexpr int kCtasPerSm = 7;             // GATv2 form: 31.8 KB + 1 KB reserved per CTA, <= 72 registers (Transformer form: 4)
 
 struct Conv2Layout {       // shared-memory offsets behind the 1024-byte aligned MMA operands
   size_t off_W, off_T, off_K, off_att, off_as, off_bt, off_e, off_eptr, off_ent, off_bar, total;
@@ -79,7 +83,7 @@ Conv2Layout conv2_layout(bool tr) {
   L.off_eptr = o; o += 68 * 4;
   L.off_ent = o; o += (size_t)kEdgeCap * 2;
   L.off_bar = o; o += 16;
-  L.total = o + 1024;
+  L.total = o;                 // the dynamic window is declared 1024-byte aligned: no slack (7 GATv2 CTAs per SM need <= 32.1 KB each)
   return L;
 }
 
@@ -88,9 +92,10 @@ Conv2Layout conv2_layout(bool tr) {
 //   group B: source rows (MMA operand + logit operand), the first block's edge entries, per-target offsets -- free once
 //            the item's last MMA has completed
 template <bool TR, int LDZ>
-__global__ void __launch_bounds__(kThreads, TR ? 4 : 6) conv2_attn_kernel(const Conv2Args a, const Conv2Layout L) {
-  extern __shared__ __align__(16) unsigned char sm_raw[];
-  unsigned char* sm = sm_raw + ((1024u - (smem_u32(sm_raw) & 1023u)) & 1023u);
+__global__ void __launch_bounds__(kThreads, TR ? 4 : kCtasPerSm) conv2_attn_kernel(const Conv2Args a, const Conv2Layout L) {
+  extern __shared__ __align__(1024) unsigned char sm_raw[];
+  if (smem_u32(sm_raw) & 1023u) __trap();                   // SWIZZLE_128B operands need the 1024-byte alignment declared above
+  unsigned char* sm = sm_raw;
   unsigned char* sX = sm;                                   // values [source k][channel], MN-major SW128 (GATv2: also logit operand)
   unsigned char* sW = sm + L.off_W;                         // weights [target of the block][source k], K-major SW128
   unsigned char* sT = sm + L.off_T;                         // targets of the block (x_r / q): [kTB][kRowPad]
@@ -154,8 +159,8 @@ __global__ void __launch_bounds__(kThreads, TR ? 4 : 6) conv2_attn_kernel(const 
   auto issue_A = [&](int first, int cnt, int nf, int nc) {
     load_targets(first, 0, cnt < kTB ? cnt : kTB);
     if (!TR) {
-      if (tid < nc) s_as[tid] = __ldg(a.as + (size_t)src_row(first, cnt, nf, tid) * H + h) * k06;
-      if (tid < cnt) s_bt[tid] = __ldg(a.bt + (size_t)(first + tid) * H + h) * k06;
+      if (tid < nc) cp4(s_as + tid, a.as + (size_t)src_row(first, cnt, nf, tid) * H + h);   // scaled by k06 where they are used
+      if (tid < cnt) cp4(s_bt + tid, a.bt + (size_t)(first + tid) * H + h);
     }
   };
   auto issue_B = [&](int first, int cnt, int nf, int nc, int ef, int ne) {
@@ -171,25 +176,27 @@ __global__ void __launch_bounds__(kThreads, TR ? 4 : 6) conv2_attn_kernel(const 
       }
     }
     load_entries(ef, 0, ne < kEdgeCap ? ne : kEdgeCap);
-    if (tid < cnt) s_eptr[tid] = __ldg(a.eabs + first + tid) - ef;
-    if (tid == 0) s_eptr[cnt] = ne;
+    if (tid < cnt) cp4(s_eptr + tid, a.eabs + first + tid);      // absolute offsets: only differences are used below
+    if (tid == 0) s_eptr[cnt] = ef + ne;
   };
 
   int g = blockIdx.x / H;
   int4 m0; int2 m1;
   load_meta(g, m0, m1);
-  while (g < a.n_graphs && m0.y == 0) { g += gstep; load_meta(g, m0, m1); }     // skip graphs without controlling nodes
+  int4 n0; int2 n1;                                         // the item after: its meta is fetched a whole item before it is read
+  load_meta(g + gstep, n0, n1);
   if (g < a.n_graphs) { issue_A(m0.x, m0.y, m0.z, m0.w); issue_B(m0.x, m0.y, m0.z, m0.w, m1.x, m1.y); }
 
   while (g < a.n_graphs) {
     const int first = m0.x, cnt = m0.y, nc = m0.w, ef = m1.x;
-    // next non-empty item of this CTA (meta only: two 16-byte loads, long before they are needed)
-    int gn = g + gstep;
-    int4 n0; int2 n1;
-    load_meta(gn, n0, n1);
-    while (gn < a.n_graphs && n0.y == 0) { gn += gstep; load_meta(gn, n0, n1); }
+    // meta of the item after the next (two 16-byte loads, not read before the end of this item: no thread waits for them).
+    // A graph without controlling nodes is an item with no blocks.
+    const int gn = g + gstep;
+    int4 p0; int2 p1;
+    load_meta(gn + gstep, p0, p1);
     cp_wait_all();
     __syncthreads();
+    if (cnt == 0 && gn < a.n_graphs) { issue_A(n0.x, n0.y, n0.z, n0.w); issue_B(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y); }
     for (int t0 = 0; t0 < cnt;) {
       // ---- block [t0, t1): at most kTB targets and kEdgeCap entries (a single target has at most 33)
       const int eb = s_eptr[t0];
@@ -205,7 +212,7 @@ __global__ void __launch_bounds__(kThreads, TR ? 4 : 6) conv2_attn_kernel(const 
       const int nmma = nt <= 16 ? 16 : 32;
       if (t0 > 0) {                                            // later blocks (rare): their rows and entries, synchronously
         load_targets(first, t0, nt);
-        load_entries(ef, eb, E);
+        load_entries(ef, eb - ef, E);
         cp_wait_all();
       }
       for (int u = tid; u < nmma * 8; u += kThreads) reinterpret_cast<uint4*>(sW)[u] = make_uint4(0, 0, 0, 0);
@@ -247,7 +254,7 @@ __global__ void __launch_bounds__(kThreads, TR ? 4 : 6) conv2_attn_kernel(const 
         float s = 0.f;
 #pragma unroll
         for (int q = 0; q < 4; ++q) { const float2 f = __half22float2(acc[q]); s += f.x + f.y; }
-        s_e[e] = TR ? s * tr_scale : s + (s_as[j] + s_bt[tk]);
+        s_e[e] = TR ? s * tr_scale : fmaf(s_as[j] + s_bt[tk], k06, s);
       }
       __syncthreads();
       // the target rows and logit scalars are dead after the item's last block: refill them with the next item's
@@ -311,7 +318,7 @@ __global__ void __launch_bounds__(kThreads, TR ? 4 : 6) conv2_attn_kernel(const 
       if (!last) __syncthreads();                              // the next block rewrites sT / s_ent / s_e / W
       t0 = t1;
     }
-    g = gn; m0 = n0; m1 = n1;
+    g = gn; m0 = n0; m1 = n1; n0 = p0; n1 = p1;
   }
   cp_wait_all();
   tc_fence_before();
@@ -330,7 +337,7 @@ int launch(const Conv2Args& a, int sm_count, cudaStream_t st) {
     MLS_CUDA(cudaFuncSetAttribute(conv2_attn_kernel<TR, 1152>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     configured = true;
   }
-  const int per_sm = TR ? 4 : 6;
+  const int per_sm = TR ? 4 : kCtasPerSm;
   long long items = (long long)a.n_graphs * a.H;
   long long grid = (long long)sm_count * per_sm;
   grid -= grid % a.H;
