@@ -583,17 +583,33 @@ def measure_training(args, dev, world, rank, model, N, B, pool, tuple_arrays, st
             dist.barrier()
             torch.cuda.synchronize()
 
-    for _ in range(max(3, warmup)):
+    for _ in range(max(10, warmup)):            # the sampled row counts differ per update: cuBLAS picks (and lazily loads) a few kernel variants
         out = step()
     sync_all()
+    # host-side stalls inside the timed region (the update is ~250 small launches per step: a Python GC pass or a
+    # slow step shows up one-to-one in the device-timed figure) -- reported, not hidden
+    import gc
+    import time
+    gc_log, gc_t0 = [], [0.0]
+
+    def gc_cb(phase, info):
+        if phase == "start":
+            gc_t0[0] = time.perf_counter()
+        else:
+            gc_log.append((info.get("generation"), (time.perf_counter() - gc_t0[0]) * 1e3))
+    gc.callbacks.append(gc_cb)
+    host_ms = []
     t_before = int(env.transitions.item())
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(steps):
+        h0 = time.perf_counter()
         out = step()
+        host_ms.append((time.perf_counter() - h0) * 1e3)
     pol.finish_update()
     ev1.record()
     sync_all()
+    gc.callbacks.remove(gc_cb)
     ms = ev0.elapsed_time(ev1)
     trans = int(env.transitions.item()) - t_before
     loss = float(out["loss"])
@@ -657,6 +673,9 @@ def measure_training(args, dev, world, rank, model, N, B, pool, tuple_arrays, st
         "allreduce_us": ar_us, "allreduce_busbw_GBs": busbw,
         "allreduce_share_of_step": (ar_us * 1e-3 / (ms_max / steps)) if ar_us else 0.0,
         "weights_identical_across_ranks": same,
+        "host_issue_ms_per_step": {"median": sorted(host_ms)[len(host_ms) // 2], "max": max(host_ms)},
+        "python_gc_in_timed_region": {"passes": len(gc_log), "ms": sum(t for _, t in gc_log), "max_ms": max([t for _, t in gc_log] or [0.0]),
+                                      "generations": sorted({g for g, _ in gc_log})},
         "backward": ({"l_dgn": "GATv2 edge phase forward + backward = mls_gatv2_edge_fwd / _bwd kernels",
                       "hl_dgn": "GATv2 edge phase of both hops forward + backward = mls_gatv2_edge_fwd / _bwd kernels",
                       "dgn_r": "TransformerConv edge phase forward + backward = mls_transformer_edge_fwd / _bwd kernels"}[model]
