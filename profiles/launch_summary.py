@@ -10,8 +10,10 @@ H = rows[hdr]
 ki, vi = H.index("Kernel Name"), H.index("Metric Value")
 L = [(r[ki], float(r[vi].replace(",", ""))) for r in rows[hdr + 1:] if len(r) > vi]
 idx = [i for i, (k, _) in enumerate(L) if "env_round" in k]
-a, b = idx[-2], idx[-1]
-step = L[a + 1:b + 1]
+# the last window between two env_round launches that holds a whole round (bench.py ends with env-only and fill launches)
+pairs = [(idx[i], idx[i + 1]) for i in range(len(idx) - 1) if any("conv2_attn" in k or "edge_bf16" in k for k, _ in L[idx[i] + 1:idx[i + 1]])]
+a, b = pairs[-1] if pairs else (idx[-2], idx[-1])
+step = [(k, v) for k, v in L[a + 1:b + 1] if "FillFunctor" not in k]     # bench.py's L2 flush (256 MiB fill) sits outside its timed events
 if "--list" in sys.argv:
     for k, v in step:
         print(f"{v / 1e3:9.1f} us  {k[:90]}")
