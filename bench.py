@@ -47,6 +47,7 @@ def parse_args():
     ap.add_argument("--preroll", type=int, default=32, help="untimed rounds so episodes are spread over their lifetime")
     ap.add_argument("--e2e-sub-batches", type=int, default=2, help="episode slices per host round (Rollout.round_host)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-trace", action="store_true", help="after the e2e timing: print the phase timeline of 4 pipelined host rounds to stderr")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-episodes", type=int, default=8, help="episodes per CPU process in the CPU arm")
     ap.add_argument("--prof-kernel", default=None)
@@ -338,6 +339,24 @@ def run_ours(args):
         e_ms, e_trans, _, _, ex = timed(lambda: ro.round_host(args.e2e_sub_batches, wait=not pipelined), args.steps,
                                         finish=ro.host_drain if pipelined else None)
         e2e = (e_ms, e_trans, ex[0])
+        if args.e2e_trace and pipelined and rank == 0:
+            import time
+            tr, host = [], []
+            base = torch.cuda.Event(enable_timing=True)
+            sync_all()
+            base.record()
+            for k in range(4):
+                flush.zero_()
+                h0 = time.perf_counter()
+                n0 = len(tr)
+                ro.round_host(args.e2e_sub_batches, wait=False, trace=tr)
+                host.append((time.perf_counter() - h0) * 1e3)
+                tr[n0:] = [(f"r{k} {t}", i, e) for t, i, e in tr[n0:]]
+            ro.host_drain()
+            sync_all()
+            for t, i, e in sorted(tr, key=lambda x: base.elapsed_time(x[2])):
+                print(f"e2e-trace {base.elapsed_time(e):8.3f} ms  {t} slice {i}", file=sys.stderr)
+            print("e2e-trace host issue ms per round:", [round(x, 3) for x in host], file=sys.stderr)
 
     flip = None
     if net is not None and args.precision == "bf16" and not args.no_flip and not args.dynamic and rank == 0:

@@ -223,7 +223,7 @@ class Rollout:
         (always 0 for observations produced by the environment kernel; see MLS_FWD_DISCRETE_FEATURES)."""
         return int(self.feature_errors.item())
 
-    def round_host(self, sub_batches: int = 1, wait: bool = True):
+    def round_host(self, sub_batches: int = 1, wait: bool = True, trace: list | None = None):
         """The same round through host buffers, as a caller holding numpy observations would
         drive it: obs/active H2D -> forward + act -> env round -> obs/reward/active/done/act D2H.
         With ``sub_batches`` > 1 the batch is processed in that many slices of episodes: the H2D copy of
@@ -232,7 +232,8 @@ class Rollout:
         ``wait=False`` does not make the calling stream wait for the round's last D2H copy: the slices of
         consecutive rounds then overlap too (slice i of round k+1 only waits for slice i of round k to be back
         on the host, exactly the dependency a caller feeding observations back has); call :meth:`host_drain`
-        before reading the host buffers.  Returns (h2d_bytes, d2h_bytes)."""
+        before reading the host buffers.  ``trace`` (a list) collects (tag, slice, timing event) marks of the pipeline's
+        phases on their streams (diagnostics: bench.py --e2e-trace).  Returns (h2d_bytes, d2h_bytes)."""
         h = self._host_buffers()
         env = self.env
         nb = lambda t: t.numel() * t.element_size()
@@ -258,6 +259,12 @@ class Rollout:
                               ev_start=torch.cuda.Event(), ev_end=torch.cuda.Event())
         P = self._pipe
         cur = torch.cuda.current_stream()
+
+        def mark(stream, tag, i):
+            if trace is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record(stream)
+                trace.append((tag, i, e))
         bounds = [(env.B * i // S, env.B * (i + 1) // S) for i in range(S)]
         if P["rounds"] == 0 or wait:
             P["ev_start"].record(cur)               # the copies of this round start after everything queued before it
@@ -267,25 +274,31 @@ class Rollout:
             for i, (b0, b1) in enumerate(bounds):
                 if P["rounds"] > 0:
                     P["h2d"].wait_event(P["ev_d"][i])   # slice i of the previous round is back on the host (and off _dev_in)
+                mark(P["h2d"], "h2d_begin", i)
                 self._dev_in["pobs"][b0:b1].copy_(h["obs"][b0:b1], non_blocking=True)
                 self._dev_in["active"][b0:b1].copy_(h["active"][b0:b1], non_blocking=True)
                 P["ev_h"][i].record(P["h2d"])
+                mark(P["h2d"], "h2d_end", i)
         graphs = self._host_graphs[1] if getattr(self, "_host_graphs", None) and self._host_graphs[0] == S else None
         for i, (b0, b1) in enumerate(bounds):
             cur.wait_event(P["ev_h"][i])
+            mark(cur, "compute_begin", i)
             if graphs is not None:
                 graphs[i].replay()
             else:
                 self._compute_slice(i, b0, b1)
             P["ev_c"][i].record(cur)
+            mark(cur, "compute_end", i)
             with torch.cuda.stream(P["d2h"]):
                 P["d2h"].wait_event(P["ev_c"][i])
+                mark(P["d2h"], "d2h_begin", i)
                 h["act"][b0:b1].copy_(self.act[b0:b1], non_blocking=True)
                 h["obs"][b0:b1].copy_(self._dev_out["pobs"][b0:b1], non_blocking=True)
                 h["reward"][b0:b1].copy_(env.reward[b0:b1], non_blocking=True)
                 h["active"][b0:b1].copy_(env.active[b0:b1], non_blocking=True)
                 h["done"][b0:b1].copy_(env.done[b0:b1], non_blocking=True)
                 P["ev_d"][i].record(P["d2h"])
+                mark(P["d2h"], "d2h_end", i)
         P["rounds"] += 1
         if wait:
             P["ev_end"].record(P["d2h"])
