@@ -59,7 +59,7 @@ __device__ __forceinline__ uint64_t desc_mn(uint32_t smem_addr, uint32_t lbo16, 
 
 // Targets are processed in blocks of at most kTB targets and kEdgeCap edge entries (one block for the typical graph:
 // ~17 controlling nodes, ~106 entries; the worst case -- 64 targets x 33 entries -- takes several): the per-item shared
-// memory is sized for a block, not for the worst case, so that six CTAs fit an SM.
+// memory is sized for a block, not for the worst case, so that seven CTAs fit an SM.
 constexpr int kTB = 32;
 constexpr int kEdgeCap = 256;
 constexpr int kWRows = kTB;
