@@ -617,20 +617,34 @@ def measure_training(args, dev, world, rank, model, N, B, pool, tuple_arrays, st
         else:
             gc_log.append((info.get("generation"), (time.perf_counter() - gc_t0[0]) * 1e3))
     gc.callbacks.append(gc_cb)
-    host_ms = []
-    t_before = int(env.transitions.item())
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for _ in range(steps):
-        h0 = time.perf_counter()
-        out = step()
-        host_ms.append((time.perf_counter() - h0) * 1e3)
-    pol.finish_update()
-    ev1.record()
-    sync_all()
+
+    def timed_steps():
+        host = []
+        t_before = int(env.transitions.item())
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(steps):
+            h0 = time.perf_counter()
+            o = step()
+            host.append((time.perf_counter() - h0) * 1e3)
+        pol.finish_update()
+        ev1.record()
+        sync_all()
+        return ev0.elapsed_time(ev1), int(env.transitions.item()) - t_before, host, o
+
+    ms, trans, host_ms, out = timed_steps()
+    # a one-off host stall (cuBLAS kernel variants loaded lazily for a row count not met before) is
+    # re-measured once, like a throttled run; the first attempt stays in the line.  All ranks take the same decision.
+    first_attempt = None
+    stalled = max(host_ms) > 2.5 * sorted(host_ms)[len(host_ms) // 2] or os.environ.get("MLS_BENCH_FORCE_REMEASURE") == "1"
+    stall = torch.tensor([1.0 if stalled else 0.0], device=dev)
+    if world > 1:
+        dist.all_reduce(stall, op=dist.ReduceOp.MAX)
+    if stall.item() > 0:
+        first_attempt = {"ms_per_step": ms / steps, "host_issue_ms_max": max(host_ms)}
+        gc_log.clear()
+        ms, trans, host_ms, out = timed_steps()
     gc.callbacks.remove(gc_cb)
-    ms = ev0.elapsed_time(ev1)
-    trans = int(env.transitions.item()) - t_before
     loss = float(out["loss"])
     # rollout round alone and update alone (same state), to attribute the step
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -693,6 +707,7 @@ def measure_training(args, dev, world, rank, model, N, B, pool, tuple_arrays, st
         "allreduce_share_of_step": (ar_us * 1e-3 / (ms_max / steps)) if ar_us else 0.0,
         "weights_identical_across_ranks": same,
         "host_issue_ms_per_step": {"median": sorted(host_ms)[len(host_ms) // 2], "max": max(host_ms)},
+        "remeasured_after_host_stall": first_attempt,
         "python_gc_in_timed_region": {"passes": len(gc_log), "ms": sum(t for _, t in gc_log), "max_ms": max([t for _, t in gc_log] or [0.0]),
                                       "generations": sorted({g for g, _ in gc_log})},
         "backward": ({"l_dgn": "GATv2 edge phase forward + backward = mls_gatv2_edge_fwd / _bwd kernels",
