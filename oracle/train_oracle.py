@@ -9,7 +9,8 @@ reference has no test or golden vector for its training step, so these functions
       terminal = indices[-1]; target_q = target_q_fn(terminal) * ~terminated[terminal];
       backward recursion  returns = rew[now] + gamma * returns, reset to 0 / gammas = n+1 where end_flag[now];
       result = target_q * gamma ** gammas + returns
-* ``torch.optim.Adam`` (single tensor, amsgrad = False), reference l_dgn.py:66
+* ``torch.optim.Adam`` (single tensor, amsgrad = False), reference l_dgn.py:66 -- this part IS pinned: torch is installed,
+  tests/test_training_host.py::test_adam_restatement_is_pinned_on_torch_optim_adam runs the real optimiser beside it
 * ``tianshou DQNPolicy.learn`` loss  mean((returns - Q(obs)[act])^2)  and ``DGNPolicy.learn`` (policies/dgn.py:22-71).
 
 Not product code: melissa_b200 never imports this module.

@@ -80,6 +80,22 @@ def test_batch_container_operations():
     assert Batch().is_empty() and not b.is_empty()
 
 
+def test_adam_restatement_is_pinned_on_torch_optim_adam():
+    """The reference optimises with torch.optim.Adam (l_dgn.py:66) and torch IS installed here, so this part of
+    oracle/train_oracle.py is pinned on the real thing: 25 steps in float64 with and without weight decay."""
+    rng = np.random.default_rng(3)
+    for wd in (0.0, 0.01):
+        p0 = rng.standard_normal(257)
+        grads = [rng.standard_normal(257) * (10.0 ** rng.integers(-3, 2)) for _ in range(25)]
+        want_p = torch.tensor(p0, dtype=torch.float64, requires_grad=True)
+        opt = torch.optim.Adam([want_p], lr=1e-3, weight_decay=wd)
+        for g in grads:
+            want_p.grad = torch.tensor(g, dtype=torch.float64)
+            opt.step()
+        got = train_oracle.adam_reference(p0, grads, lr=1e-3, weight_decay=wd)
+        np.testing.assert_allclose(got, want_p.detach().numpy(), rtol=1e-12, atol=1e-14)
+
+
 def test_nstep_restatement_on_hand_cases():
     rew = np.array([1.0, 2.0, 3.0, 4.0])
     term = np.array([False, False, False, True])
